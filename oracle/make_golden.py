@@ -1,0 +1,432 @@
+"""Generate the golden fixtures under ``tests/golden/`` from the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the only place where
+``/root/reference`` exists):
+
+    PYTHONPATH=oracle/refshim:/root/reference python oracle/make_golden.py
+
+It (1) converts the reference's own golden pickles for the hot path
+(``tests/resources/consistency_expected_outgoing/*.pkl``, pinned by the reference's
+``tests/test_elements.py:356-431``) into ``tests/golden/consistency.npz`` +
+``consistency.json`` and (2) runs the reference itself on ARES, aperture, cloud-in-cell
+and space-charge cases, storing inputs and outputs.  Nothing at test / bench time reads
+``/root/reference``; only the committed fixtures are used.
+"""
+
+from __future__ import annotations
+
+import json
+import pickle
+import sys
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+sys.path.insert(0, str(REPO / "oracle" / "refshim"))
+sys.path.insert(0, str(REF))
+sys.path.insert(0, str(REPO))
+
+import cheetah  # noqa: E402  (the reference)
+
+from oracle import lattice_io  # noqa: E402
+
+OUT = REPO / "tests" / "golden"
+OUT.mkdir(parents=True, exist_ok=True)
+warnings.simplefilter("ignore")
+
+ROW_STRIDE = 4  # expected outputs are stored for every 4th particle to keep fixtures small
+
+
+def np64(t: torch.Tensor) -> np.ndarray:
+    return t.detach().to(torch.float64).cpu().numpy()
+
+
+def beam_arrays(prefix: str, beam, rows=slice(None)) -> dict:
+    return {
+        f"{prefix}.particles": np64(beam.particles[..., rows, :]),
+        f"{prefix}.energy": np64(beam.energy),
+        f"{prefix}.particle_charges": np64(beam.particle_charges[..., rows]),
+        f"{prefix}.survival_probabilities": np64(beam.survival_probabilities[..., rows]),
+        f"{prefix}.s": np64(beam.s),
+        f"{prefix}.mass_eV": np64(beam.species.mass_eV),
+        f"{prefix}.num_elementary_charges": np64(beam.species.num_elementary_charges),
+    }
+
+
+# --------------------------------------------------------------------------------------
+# 1. the reference's own golden pickles (tests/test_elements.py:356-431)
+# --------------------------------------------------------------------------------------
+CONSISTENCY_CASES = {
+    # (class name, label): constructor kwargs -- tests/conftest.py:12-152, hot-path rows only
+    ("Aperture", "inactive"): {"is_active": False},
+    ("Aperture", "active"): {"is_active": True},
+    ("BPM", "inactive"): {"is_active": False},
+    ("Cavity", "default"): {"length": torch.tensor(1.0)},
+    ("CombinedCorrector", "default"): {
+        "length": torch.tensor(1.0),
+        "horizontal_angle": torch.tensor([1.0, -2.0]),
+        "vertical_angle": torch.tensor([1.0, -2.0]),
+    },
+    ("CustomTransferMap", "identity"): {"predefined_transfer_map": torch.eye(7)},
+    ("Dipole", "linear"): {
+        "length": torch.tensor(1.0),
+        "angle": torch.tensor([1.0, -2.0]),
+        "tilt": torch.tensor(0.42),
+        "tracking_method": "linear",
+    },
+    ("Drift", "linear"): {"length": torch.tensor([1.0, -1.0]), "tracking_method": "linear"},
+    ("HorizontalCorrector", "default"): {
+        "length": torch.tensor(1.0),
+        "angle": torch.tensor([1.0, -2.0]),
+    },
+    ("Marker", "default"): {},
+    ("Quadrupole", "linear"): {
+        "length": torch.tensor(1.0),
+        "k1": torch.tensor([1.0, -2.0]),
+        "tilt": torch.tensor(0.42),
+        "misalignment": torch.tensor([0.01, -0.02]),
+        "tracking_method": "linear",
+    },
+    ("RBend", "linear"): {
+        "length": torch.tensor(1.0),
+        "angle": torch.tensor([1.0, -2.0]),
+        "tilt": torch.tensor(0.42),
+        "tracking_method": "linear",
+    },
+    ("Screen", "default"): {},
+    ("Sextupole", "linear"): {
+        "length": torch.tensor(1.0),
+        "k2": torch.tensor([1.0, -2.0]),
+        "tilt": torch.tensor(0.42),
+        "misalignment": torch.tensor([0.01, -0.02]),
+        "tracking_method": "linear",
+    },
+    ("Solenoid", "default"): {
+        "length": torch.tensor(1.0),
+        "k": torch.tensor([1.0, -2.0]),
+        "misalignment": torch.tensor([0.01, -0.02]),
+    },
+    ("SpaceChargeKick", "default"): {"effect_length": torch.tensor(1.0)},
+    ("Undulator", "default"): {
+        "length": torch.tensor(1.0),
+        "period": torch.tensor(0.1),
+        "kx": torch.tensor(1.3),
+    },
+    ("VerticalCorrector", "default"): {
+        "length": torch.tensor(1.0),
+        "angle": torch.tensor([1.0, -2.0]),
+    },
+}
+
+
+def make_consistency() -> None:
+    resources = REF / "tests" / "resources"
+    with (resources / "ACHIP_EA1_2021.1351.001_subsampled_3000.pkl").open("rb") as f:
+        incoming = pickle.load(f).to(torch.float64)
+    arrays = beam_arrays("incoming", incoming)
+    parameter_incoming = incoming.as_parameter_beam()
+    arrays["incoming.mu"] = np64(parameter_incoming.mu)
+    arrays["incoming.cov"] = np64(parameter_incoming.cov)
+    arrays["incoming.total_charge"] = np64(parameter_incoming.total_charge)
+
+    lattices = {}
+    rows = slice(None, None, ROW_STRIDE)
+    for (cls_name, label), kwargs in CONSISTENCY_CASES.items():
+        key = f"{cls_name}_{label}"
+        element = getattr(cheetah, cls_name)(name=label, **kwargs).to(torch.float64)
+        lattices[key] = lattice_io._to_json([lattice_io.describe(element)])
+        folder = resources / "consistency_expected_outgoing"
+        with (folder / f"{cls_name}_ParticleBeam_{label}.pkl").open("rb") as f:
+            expected = pickle.load(f)
+        arrays.update(beam_arrays(f"{key}.expected", expected, rows))
+        parameter_pickle = folder / f"{cls_name}_ParameterBeam_{label}.pkl"
+        if parameter_pickle.exists():
+            with parameter_pickle.open("rb") as f:
+                expected_parameter = pickle.load(f)
+            arrays[f"{key}.expected.mu"] = np64(expected_parameter.mu)
+            arrays[f"{key}.expected.cov"] = np64(expected_parameter.cov)
+        # Sanity: the reference in this container still reproduces its own pickle
+        actual = element.track(incoming)
+        assert torch.allclose(actual.particles, expected.particles), key
+        assert torch.allclose(
+            actual.survival_probabilities, expected.survival_probabilities
+        ), key
+
+    np.savez_compressed(OUT / "consistency.npz", **arrays)
+    with (OUT / "consistency.json").open("w") as f:
+        json.dump({"row_stride": ROW_STRIDE, "lattices": lattices}, f, separators=(",", ":"))
+    print("consistency:", len(CONSISTENCY_CASES), "cases")
+
+
+# --------------------------------------------------------------------------------------
+# 2. ARES through the reference itself
+# --------------------------------------------------------------------------------------
+ARES_JSON = REF / "docs" / "examples" / "ARESlatticeStage3v1_9.json"
+CONFIG2_SETTINGS = {  # README.md:73-77
+    "AREAMQZM1": ("k1", 8.2),
+    "AREAMQZM2": ("k1", -14.3),
+    "AREAMCVM1": ("angle", 9e-5),
+    "AREAMQZM3": ("k1", 3.142),
+    "AREAMCHM1": ("angle", -1e-4),
+}
+
+
+def ares_beam(num_particles: int, dtype) -> "cheetah.ParticleBeam":
+    torch.manual_seed(0)
+    beam = cheetah.ParticleBeam.from_twiss(
+        num_particles=num_particles,
+        beta_x=torch.tensor(3.14),
+        beta_y=torch.tensor(42.0),
+        dtype=torch.float64,
+    )
+    return beam.to(dtype)
+
+
+def vectorised_settings(segment, batch: int, seed: int = 1) -> dict:
+    """Config-3 recipe (DESIGN.md "Workloads"): quads U(-5,5) 1/m^2, correctors
+    U(-2e-5,2e-5) rad, drawn element by element from one seeded generator."""
+    g = torch.Generator().manual_seed(seed)
+    settings = {}
+    for element in segment.elements:
+        if isinstance(element, cheetah.Quadrupole):
+            settings[element.name] = ("k1", (torch.rand(batch, generator=g) * 2 - 1) * 5.0)
+        elif isinstance(element, (cheetah.HorizontalCorrector, cheetah.VerticalCorrector)):
+            settings[element.name] = (
+                "angle",
+                (torch.rand(batch, generator=g) * 2 - 1) * 2e-5,
+            )
+    return settings
+
+
+def make_ares() -> None:
+    num_particles = 2048
+    rows = slice(None, None, ROW_STRIDE)
+    arrays = {}
+    description = None
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        beam = ares_beam(num_particles, dtype)
+        if tag == "f64":
+            arrays.update(beam_arrays("incoming", beam))
+
+        # case A: lattice file values (all magnets off) -- BASELINE config 1 shape
+        segment = cheetah.Segment.from_lattice_json(str(ARES_JSON), dtype=dtype)
+        if description is None:
+            description = lattice_io.describe(segment)["elements"]
+        out = segment.track(beam)
+        arrays.update(beam_arrays(f"default.{tag}", out, rows))
+
+        # case B: the five EA magnets of config 2
+        for name, (attr, value) in CONFIG2_SETTINGS.items():
+            setattr(getattr(segment, name), attr, torch.tensor(value, dtype=dtype))
+        out = segment.track(beam)
+        arrays.update(beam_arrays(f"config2.{tag}", out, rows))
+
+        # case C: vectorised settings + finite apertures (config 3 recipe, small batch)
+        segment = cheetah.Segment.from_lattice_json(str(ARES_JSON), dtype=dtype)
+        batch = 6
+        for name, (attr, value) in vectorised_settings(segment, batch).items():
+            setattr(getattr(segment, name), attr, value.to(dtype))
+        segment.ARLISLHG1.x_max = torch.tensor(2e-3, dtype=dtype)
+        segment.ARLISLHG1.y_max = torch.tensor(2e-3, dtype=dtype)
+        segment.ARBCSLHB1.x_max = torch.tensor(2e-3, dtype=dtype)
+        segment.ARBCSLHB1.y_max = torch.tensor(2e-3, dtype=dtype)
+        segment.ARBCSLHS1.shape = "elliptical"
+        segment.ARBCSLHS1.x_max = torch.tensor(4e-3, dtype=dtype)
+        segment.ARBCSLHS1.y_max = torch.tensor(3e-3, dtype=dtype)
+        # fat beam (transverse x50) so that the apertures cut through the core
+        fat = beam.clone()
+        fat.particles[..., :4] *= 50.0
+        out = segment.track(fat)
+        arrays.update(beam_arrays(f"vectorised.{tag}", out, rows))
+        print(
+            "ares vectorised survival fractions",
+            tag,
+            out.survival_probabilities.mean(dim=-1),
+        )
+
+    lattice_io.dump(description, OUT / "ares_lattice.json")
+    settings = vectorised_settings(
+        cheetah.Segment.from_lattice_json(str(ARES_JSON), dtype=torch.float64), 6
+    )
+    for name, (attr, value) in settings.items():
+        arrays[f"vectorised.settings.{name}.{attr}"] = np64(value)
+    arrays["vectorised.transverse_scale"] = np.array(50.0)
+    np.savez_compressed(OUT / "ares.npz", **arrays)
+    print("ares: done,", len(description), "elements")
+
+
+# --------------------------------------------------------------------------------------
+# 3. apertures, cloud-in-cell and space charge through the reference itself
+# --------------------------------------------------------------------------------------
+def make_aperture() -> None:
+    torch.manual_seed(3)
+    particles = torch.randn(3, 1000, 7, dtype=torch.float64) * 1e-3
+    particles[..., 6] = 1.0
+    arrays = {"particles": np64(particles)}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        beam = cheetah.ParticleBeam(
+            particles.to(dtype), energy=torch.tensor(1e8, dtype=dtype), dtype=dtype
+        )
+        for shape in ("rectangular", "elliptical"):
+            aperture = cheetah.Aperture(
+                x_max=torch.tensor([[1e-3], [5e-4]], dtype=dtype),
+                y_max=torch.tensor(8e-4, dtype=dtype),
+                shape=shape,
+                dtype=dtype,
+            )
+            out = aperture.track(beam)
+            arrays[f"{shape}.{tag}.survival"] = np64(out.survival_probabilities)
+    np.savez_compressed(OUT / "aperture.npz", **arrays)
+    print("aperture: done")
+
+
+def make_cloud_in_cell() -> None:
+    from cheetah.utils.cloud_in_cell import cloud_in_cell_charge_deposition
+
+    torch.manual_seed(4)
+    positions = torch.randn(2, 2000, 3, dtype=torch.float64)
+    charges = torch.rand(2, 2000, dtype=torch.float64)
+    extent = torch.tensor(
+        [[[-2.0, 2.0], [-1.5, 2.5], [-3.0, 3.0]], [[-1.0, 1.0], [-2.0, 2.0], [-0.5, 0.5]]],
+        dtype=torch.float64,
+    )
+    bins = (8, 6, 5)
+    arrays = {
+        "positions": np64(positions),
+        "charges": np64(charges),
+        "extent": np64(extent),
+        "bins": np.array(bins),
+    }
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        grid = cloud_in_cell_charge_deposition(
+            positions.to(dtype), bins, extent.to(dtype), charges.to(dtype)
+        )
+        arrays[f"grid.{tag}"] = np64(grid)
+    np.savez_compressed(OUT / "cloud_in_cell.npz", **arrays)
+    print("cloud_in_cell: done")
+
+
+def make_space_charge() -> None:
+    arrays = {}
+    rows = slice(None, None, ROW_STRIDE)
+    num_particles = 6000
+    torch.manual_seed(5)
+    base = cheetah.ParticleBeam.from_parameters(
+        num_particles=num_particles,
+        total_charge=torch.tensor(1e-9),
+        energy=torch.tensor(1e8),
+        dtype=torch.float64,
+    )
+    arrays.update(beam_arrays("incoming", base))
+
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        # single kick, 16^3 grid (exposes every stage of the solver at small size)
+        beam = base.to(dtype)
+        kick = cheetah.SpaceChargeKick(
+            effect_length=torch.tensor(0.7, dtype=dtype), grid_shape=(16, 16, 16), dtype=dtype
+        )
+        # intermediate stages, for unit-level parity of each kernel
+        vector = cheetah.ParticleBeam(
+            particles=beam.particles.unsqueeze(0),
+            energy=beam.energy.unsqueeze(0),
+            particle_charges=beam.particle_charges.unsqueeze(0),
+            survival_probabilities=beam.survival_probabilities.unsqueeze(0),
+            species=beam.species,
+            dtype=dtype,
+        )
+        grid_dimensions = torch.stack(
+            [3.0 * vector.sigma_x, 3.0 * vector.sigma_y, 3.0 * vector.sigma_tau], dim=-1
+        )
+        cell_size = 2 * grid_dimensions / torch.tensor(kick.grid_shape, dtype=dtype)
+        xp = vector.to_xyz_pxpypz()
+        arrays[f"kick16.{tag}.grid_dimensions"] = np64(grid_dimensions)
+        arrays[f"kick16.{tag}.rho_padded"] = np64(
+            kick._array_rho(vector, xp, cell_size, grid_dimensions)
+        )
+        arrays[f"kick16.{tag}.green"] = np64(kick._integrated_green_function(vector, cell_size))
+        arrays[f"kick16.{tag}.potential"] = np64(
+            kick._solve_poisson_equation(vector, xp, cell_size, grid_dimensions)
+        )
+        arrays[f"kick16.{tag}.forces"] = np64(
+            kick._compute_forces(vector, xp, cell_size, grid_dimensions)[..., rows, :]
+        )
+        out = kick.track(beam)
+        arrays.update(beam_arrays(f"kick16.{tag}", out, rows))
+
+        # vectorised charges (2 beams), default 32^3 grid, low energy (strong kick)
+        beam2 = cheetah.ParticleBeam(
+            particles=base.particles.to(dtype),
+            energy=torch.tensor(5e6, dtype=dtype),
+            particle_charges=(
+                base.particle_charges.to(dtype) * torch.tensor([[1.0], [3.0]], dtype=dtype)
+            ),
+            dtype=dtype,
+        )
+        kick32 = cheetah.SpaceChargeKick(effect_length=torch.tensor(0.2, dtype=dtype), dtype=dtype)
+        out = kick32.track(beam2)
+        arrays.update(beam_arrays(f"kick32vec.{tag}", out, rows))
+
+        # FODO cell with the split-drift pattern (tests/test_space_charge_kick.py:56-66)
+        # + an aperture so that survival weighting matters
+        def drift_with_kick(length):
+            return [
+                cheetah.Drift(length=torch.tensor(length / 2, dtype=dtype), dtype=dtype),
+                cheetah.SpaceChargeKick(
+                    effect_length=torch.tensor(length, dtype=dtype),
+                    grid_shape=(16, 16, 16),
+                    dtype=dtype,
+                ),
+                cheetah.Drift(length=torch.tensor(length / 2, dtype=dtype), dtype=dtype),
+            ]
+
+        segment = cheetah.Segment(
+            elements=[
+                cheetah.Quadrupole(
+                    length=torch.tensor(0.2, dtype=dtype),
+                    k1=torch.tensor(4.2, dtype=dtype),
+                    dtype=dtype,
+                ),
+                *drift_with_kick(1.0),
+                cheetah.Aperture(
+                    x_max=torch.tensor(1.5e-4, dtype=dtype),
+                    y_max=torch.tensor(5e-4, dtype=dtype),
+                    dtype=dtype,
+                ),
+                cheetah.Quadrupole(
+                    length=torch.tensor(0.2, dtype=dtype),
+                    k1=torch.tensor(-4.2, dtype=dtype),
+                    dtype=dtype,
+                ),
+                *drift_with_kick(1.0),
+            ]
+        )
+        if tag == "f64":
+            lattice_io.dump(
+                lattice_io.describe(segment)["elements"], OUT / "fodo_space_charge_lattice.json"
+            )
+        low_energy = cheetah.ParticleBeam(
+            particles=base.particles.to(dtype),
+            energy=torch.tensor(5e7, dtype=dtype),
+            particle_charges=base.particle_charges.to(dtype) * 0.1,
+            dtype=dtype,
+        )
+        out = segment.track(low_energy)
+        arrays.update(beam_arrays(f"fodo.{tag}", out, rows))
+        print("fodo survival", tag, out.survival_probabilities.mean().item())
+
+    np.savez_compressed(OUT / "space_charge.npz", **arrays)
+    print("space_charge: done")
+
+
+if __name__ == "__main__":
+    make_consistency()
+    make_ares()
+    make_aperture()
+    make_cloud_in_cell()
+    make_space_charge()
+    for path in sorted(OUT.iterdir()):
+        print(f"{path.name:40s} {path.stat().st_size / 1024:8.1f} KiB")
