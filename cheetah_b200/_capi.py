@@ -1,0 +1,126 @@
+"""ctypes binding of ``include/cheetah_b200.h``.
+
+The CUDA library is the product: there is no Python or CPU fallback.  ``lib()`` raises if
+``libcheetah_b200.so`` has not been built (``python -c "import __graft_entry__ as g;
+g.build()"`` or ``python -m cheetah_b200.build``).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_int32, c_int64, c_uint32, c_void_p
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcheetah_b200.so"
+
+CH_F32, CH_F64 = 0, 1
+
+OP_IDENTITY = 0
+OP_DRIFT = 1
+OP_CORRECTOR = 2
+OP_QUADRUPOLE = 3
+OP_DIPOLE = 4
+OP_SOLENOID = 5
+OP_UNDULATOR = 6
+OP_CAVITY_OFF = 7
+OP_CUSTOM_MAP = 8
+OP_APERTURE = 9
+
+RECORD_HEADER = 2
+RECORD_MAP = 42
+RECORD_APERTURE = 16
+MAX_APERTURES = 32
+
+
+def record_len(n_apertures: int) -> int:
+    return RECORD_HEADER + RECORD_MAP + RECORD_APERTURE * n_apertures
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/cheetah_b200.h
+SIGNATURES = {
+    "ch_abi_version": (c_int32, []),
+    "ch_last_error": (c_char_p, []),
+    "ch_kernel_launch_count": (c_int64, []),
+    "ch_program_create": (
+        c_int32,
+        [
+            POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_int32,
+            POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32), c_int32,
+            c_void_p, POINTER(c_void_p),
+        ],
+    ),
+    "ch_program_destroy": (c_int32, [c_void_p]),
+    "ch_compose_maps": (
+        c_int32,
+        [
+            c_void_p, c_int32, c_int32, c_int64,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int32,
+            c_void_p, c_int64, c_int32,
+            c_void_p,
+        ],
+    ),
+    "ch_apply_maps": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_int64, c_int32, c_uint32,
+            c_int64, c_int64,
+            c_void_p, c_void_p,
+            c_int32, c_int32, c_void_p,
+        ],
+    ),
+}
+
+_lib = None
+
+
+class BackendError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"cheetah_b200: CUDA library {LIB_PATH} is missing. Build it with "
+                "`python -m cheetah_b200.build`; there is no CPU fallback."
+            )
+        handle = ctypes.CDLL(str(LIB_PATH))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        message = lib().ch_last_error().decode(errors="replace")
+        raise BackendError(f"cheetah_b200 C-ABI error {status}: {message}")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return CH_F32
+    if dtype == torch.float64:
+        return CH_F64
+    raise TypeError(f"cheetah_b200 supports float32 and float64 tensors, got {dtype}")
+
+
+def current_stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().ch_kernel_launch_count())
+
+
+def ptr(tensor: torch.Tensor | None) -> int | None:
+    return None if tensor is None else tensor.data_ptr()

@@ -1,0 +1,366 @@
+// Map application: the one streaming pass over the particles of a linear lattice section.
+//
+// Replaces every `particles @ tm.mT` (cheetah/accelerator/element.py:181-191) and every
+// aperture mask update (cheetah/accelerator/aperture.py:108-132) between two non-linear
+// elements with a single read of the incoming particles and a single write of the
+// outgoing particles and survival probabilities.
+//
+// Work decomposition (B200): a CTA owns a tile of TP = THREADS*P particles and keeps their
+// six phase-space coordinates in registers ("tile-stationary"); it then loops over a chunk
+// of lattice settings.  For each setting the per-setting record (cumulative maps from
+// ch_compose_maps) is read from a double-buffered shared-memory copy as broadcast
+// 128-bit loads, every thread evaluates the aperture rows and the final 6x7 map for its P
+// particles, writes the 7-wide rows into a shared staging tile (stride-7 stores are
+// bank-conflict free) and one elected thread hands the contiguous tile to the TMA engine
+// (cp.async.bulk shared->global, SASS UBLKCP) so the LSU never sees the 28-byte-strided
+// row layout.  Two staging tiles overlap the bulk store of setting b with the math of b+1.
+// HBM traffic per (particle, setting): 28 B + 4 B written, the shared beam is read once per
+// CTA.  No tensor cores: K = 7 is far below any MMA tile.
+#include "ch_common.cuh"
+
+namespace ch {
+namespace {
+
+template <typename T>
+struct ApplyArgs {
+  const T* particles_in;
+  const T* survival_in;  // may be null -> ones
+  const T* records;
+  T* particles_out;
+  T* survival_out;  // may be null iff n_apertures == 0
+  const int32_t* particle_index;
+  const int32_t* survival_index;
+  const int32_t* record_index;
+  int64_t particle_stride;  // elements per batch entry of particles_in (0 = shared)
+  int64_t survival_stride;
+  int64_t record_stride;
+  int64_t n_particles;
+  int64_t n_settings;
+  int32_t record_len;
+  int32_t n_apertures;
+  uint32_t elliptical_mask;
+  int32_t settings_per_cta;
+  int32_t bulk_in;   // particles_in tiles satisfy the 16-byte rules of cp.async.bulk
+  int32_t bulk_out;  // particles_out tiles do
+};
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  using type = float4;
+  static constexpr int lanes = 4;
+};
+template <>
+struct Vec4<double> {
+  using type = double2;
+  static constexpr int lanes = 2;
+};
+
+// exact IEEE helpers so that masks follow the reference's unfused elementwise ops
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+
+// load `n` scalars (n % lanes == 0, 16-byte aligned) from shared memory as 128-bit words
+template <typename T, int N>
+__device__ __forceinline__ void load_coefficients(T (&dst)[N], const T* src) {
+  using V = typename Vec4<T>::type;
+  constexpr int L = Vec4<T>::lanes;
+  static_assert(N % L == 0, "coefficient block must be a whole number of 128-bit words");
+#pragma unroll
+  for (int i = 0; i < N / L; ++i) {
+    const V v = reinterpret_cast<const V*>(src)[i];
+    if constexpr (L == 4) {
+      dst[4 * i + 0] = v.x;
+      dst[4 * i + 1] = v.y;
+      dst[4 * i + 2] = v.z;
+      dst[4 * i + 3] = v.w;
+    } else {
+      dst[2 * i + 0] = v.x;
+      dst[2 * i + 1] = v.y;
+    }
+  }
+}
+
+template <typename T, bool UNIT7>
+__device__ __forceinline__ T affine_row(const T* c, const T (&p)[7]) {
+  // c[0..6] . (p0..p5, p6) ; with UNIT7 the seventh coordinate is known to be 1
+  T acc = UNIT7 ? c[6] : c[6] * p[6];
+#pragma unroll
+  for (int j = 5; j >= 0; --j) acc = fma_t(c[j], p[j], acc);
+  return acc;
+}
+
+template <typename T, int P, int THREADS, bool UNIT7>
+__global__ void __launch_bounds__(THREADS)
+apply_maps_kernel(const ApplyArgs<T> a) {
+  constexpr int TP = P * THREADS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* stage0 = reinterpret_cast<T*>(smem_raw);
+  T* stage1 = stage0 + TP * 7;
+  T* rec0 = stage1 + TP * 7;
+  T* rec1 = rec0 + a.record_len;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(rec1 + a.record_len);
+
+  const int tid = threadIdx.x;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
+  const int count = static_cast<int>(min(static_cast<int64_t>(TP), a.n_particles - n0));
+  const int64_t b_begin = static_cast<int64_t>(blockIdx.y) * a.settings_per_cta;
+  const int64_t b_end = min(a.n_settings, b_begin + a.settings_per_cta);
+
+  if (a.bulk_in && tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+
+  auto record_offset = [&](int64_t b) {
+    return (a.record_index ? a.record_index[b] : b) * a.record_stride;
+  };
+  auto copy_record = [&](T* dst, int64_t b) {
+    const T* src = a.records + record_offset(b);
+    for (int i = tid; i < a.record_len; i += THREADS) dst[i] = src[i];
+  };
+
+  copy_record(rec0, b_begin);
+  __syncthreads();  // record 0 + mbarrier init visible
+
+  T p[P][7];
+  T sv_in[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) sv_in[k] = T(1);
+  int64_t loaded_particles = -1, loaded_survival = -1;
+  uint32_t phase = 0;
+
+  for (int64_t b = b_begin; b < b_end; ++b) {
+    const int it = static_cast<int>(b - b_begin);
+    T* stage = (it & 1) ? stage1 : stage0;
+    const T* rec = (it & 1) ? rec1 : rec0;
+    T* rec_next = (it & 1) ? rec0 : rec1;
+
+    // the staging tile we are about to reuse was handed to the TMA engine two iterations
+    // ago: wait until the engine has finished READING it (at most 1 newer group in flight)
+    if (a.bulk_out && tid == 0) bulk_wait_read<1>();
+    __syncthreads();
+
+    // ---- incoming particle tile -> registers (once per CTA when the beam is shared) ----
+    const int64_t p_off =
+        (a.particle_index ? a.particle_index[b] : b) * a.particle_stride + n0 * 7;
+    if (p_off != loaded_particles) {
+      const T* src = a.particles_in + p_off;
+      if (a.bulk_in) {
+        if (tid == 0) {
+          const uint32_t bytes = static_cast<uint32_t>(count) * 7u * sizeof(T);
+          mbar_expect_tx(bar, bytes);
+          bulk_load(stage, src, bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+      } else {
+        for (int i = tid; i < count * 7; i += THREADS) stage[i] = src[i];
+        __syncthreads();
+      }
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const int local = tid + k * THREADS;
+        if (local < count) {
+#pragma unroll
+          for (int j = 0; j < 7; ++j) p[k][j] = stage[local * 7 + j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 7; ++j) p[k][j] = T(0);
+        }
+      }
+      loaded_particles = p_off;
+      __syncthreads();  // everyone has its registers before the tile is overwritten
+    }
+    if (a.survival_out != nullptr) {
+      const int64_t s_off =
+          (a.survival_index ? a.survival_index[b] : b) * a.survival_stride + n0;
+      if (s_off != loaded_survival) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const int local = tid + k * THREADS;
+          sv_in[k] = (a.survival_in != nullptr && local < count) ? a.survival_in[s_off + local]
+                                                                 : T(1);
+        }
+        loaded_survival = s_off;
+      }
+    }
+
+    // ---- prefetch the next setting's record (visible after the next barrier) ----------
+    if (b + 1 < b_end) copy_record(rec_next, b + 1);
+
+    // ---- apertures: x, y at each cut point from the cumulative rows ---------------------
+    T sv[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) sv[k] = sv_in[k];
+    for (int ap = 0; ap < a.n_apertures; ++ap) {
+      T q[16];
+      load_coefficients(q, rec + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
+      const T x_max = q[14], y_max = q[15];
+      const bool elliptical = (a.elliptical_mask >> ap) & 1u;
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const T x = affine_row<T, UNIT7>(q, p[k]);
+        const T y = affine_row<T, UNIT7>(q + 7, p[k]);
+        bool keep;
+        if (elliptical) {
+          const T ex = div_rn(mul_rn(x, x), mul_rn(x_max, x_max));
+          const T ey = div_rn(mul_rn(y, y), mul_rn(y_max, y_max));
+          keep = add_rn(ex, ey) <= T(1);
+        } else {
+          keep = (x > -x_max) && (x < x_max) && (y > -y_max) && (y < y_max);
+        }
+        sv[k] = mul_rn(sv[k], keep ? T(1) : T(0));
+      }
+    }
+
+    // ---- final map -> staging tile ----------------------------------------------------
+    {
+      T c[44];
+      load_coefficients(c, rec);
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const int local = tid + k * THREADS;
+        T* row = stage + local * 7;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          row[i] = affine_row<T, UNIT7>(c + CH_RECORD_HEADER + i * 7, p[k]);
+        row[6] = UNIT7 ? T(1) : p[k][6];
+      }
+    }
+    if (a.survival_out != nullptr) {
+      T* dst = a.survival_out + b * a.n_particles + n0;
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const int local = tid + k * THREADS;
+        if (local < count) dst[local] = sv[k];
+      }
+    }
+
+    // ---- hand the finished tile to the TMA engine (or copy it out cooperatively) -------
+    T* out = a.particles_out + (b * a.n_particles + n0) * 7;
+    if (a.bulk_out) {
+      fence_async_shared();
+      __syncthreads();
+      if (tid == 0) {
+        bulk_store(out, stage, static_cast<uint32_t>(count) * 7u * sizeof(T));
+        bulk_commit();
+      }
+    } else {
+      __syncthreads();
+      for (int i = tid; i < count * 7; i += THREADS) out[i] = stage[i];
+    }
+  }
+  if (a.bulk_out && tid == 0) bulk_wait<0>();
+}
+
+template <typename T, int P, int THREADS>
+int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t stream) {
+  constexpr int TP = P * THREADS;
+  const size_t smem =
+      sizeof(T) * (2 * TP * 7 + 2 * static_cast<size_t>(args.record_len)) + sizeof(uint64_t);
+  const int64_t tiles = (args.n_particles + TP - 1) / TP;
+  const int64_t chunks = (args.n_settings + args.settings_per_cta - 1) / args.settings_per_cta;
+  CH_REQUIRE(tiles <= 2147483647LL && chunks <= 65535, "ch_apply_maps: grid too large");
+  dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(chunks));
+  if (unit_seventh) {
+    auto kernel = apply_maps_kernel<T, P, THREADS, true>;
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    kernel<<<grid, THREADS, smem, stream>>>(args);
+  } else {
+    auto kernel = apply_maps_kernel<T, P, THREADS, false>;
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    kernel<<<grid, THREADS, smem, stream>>>(args);
+  }
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+template <typename T>
+int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t* particle_index,
+                const void* survival_in, int64_t survival_stride, const int32_t* survival_index,
+                const void* records, int64_t record_stride, const int32_t* record_index,
+                int64_t record_len, int32_t n_apertures, uint32_t elliptical_mask,
+                int64_t n_particles, int64_t n_settings, void* particles_out, void* survival_out,
+                int32_t unit_seventh, cudaStream_t stream) {
+  ApplyArgs<T> a;
+  a.particles_in = static_cast<const T*>(particles_in);
+  a.survival_in = static_cast<const T*>(survival_in);
+  a.records = static_cast<const T*>(records);
+  a.particles_out = static_cast<T*>(particles_out);
+  a.survival_out = static_cast<T*>(survival_out);
+  a.particle_index = particle_index;
+  a.survival_index = survival_index;
+  a.record_index = record_index;
+  a.particle_stride = particle_stride;
+  a.survival_stride = survival_stride;
+  a.record_stride = record_stride;
+  a.n_particles = n_particles;
+  a.n_settings = n_settings;
+  a.record_len = static_cast<int32_t>(record_len);
+  a.n_apertures = n_apertures;
+  a.elliptical_mask = elliptical_mask;
+
+  // cp.async.bulk needs 16-byte aligned addresses and sizes for every tile
+  const size_t row_bytes = 7 * sizeof(T);
+  auto tiles_aligned = [&](const void* base, int64_t batch_stride_elems) {
+    return reinterpret_cast<uintptr_t>(base) % 16 == 0 &&
+           (static_cast<size_t>(n_particles) * row_bytes) % 16 == 0 &&
+           (static_cast<size_t>(batch_stride_elems) * sizeof(T)) % 16 == 0;
+  };
+  a.bulk_in = tiles_aligned(particles_in, particle_stride) ? 1 : 0;
+  a.bulk_out = tiles_aligned(particles_out, n_particles * 7) ? 1 : 0;
+
+  // settings per CTA: amortise the tile load over many settings but keep >= ~8 waves of CTAs
+  constexpr int P = sizeof(T) == 4 ? 4 : 2;
+  constexpr int THREADS = 256;
+  const int64_t tiles = (n_particles + P * THREADS - 1) / (P * THREADS);
+  int64_t per_cta = 64;
+  while (per_cta > 1 && tiles * ((n_settings + per_cta - 1) / per_cta) < 148 * 16) per_cta /= 2;
+  a.settings_per_cta = static_cast<int32_t>(per_cta);
+  return launch_apply<T, P, THREADS>(a, unit_seventh != 0, stream);
+}
+
+}  // namespace
+}  // namespace ch
+
+extern "C" int ch_apply_maps(const void* particles_in, int64_t particle_stride,
+                             const int32_t* particle_index, const void* survival_in,
+                             int64_t survival_stride, const int32_t* survival_index,
+                             const void* records, int64_t record_stride,
+                             const int32_t* record_index, int64_t record_len,
+                             int32_t n_apertures, uint32_t elliptical_mask, int64_t n_particles,
+                             int64_t n_settings, void* particles_out, void* survival_out,
+                             int32_t dtype, int32_t unit_seventh, void* stream) {
+  CH_REQUIRE(particles_in && records && particles_out, "ch_apply_maps: NULL pointer argument");
+  CH_REQUIRE(n_particles > 0 && n_settings > 0, "ch_apply_maps: empty beam or batch");
+  CH_REQUIRE(n_apertures >= 0 && n_apertures <= CH_MAX_APERTURES,
+             "ch_apply_maps: n_apertures %d outside [0, %d]", n_apertures, CH_MAX_APERTURES);
+  CH_REQUIRE(record_len == CH_RECORD_LEN(n_apertures),
+             "ch_apply_maps: record_len %lld does not match %d apertures",
+             static_cast<long long>(record_len), n_apertures);
+  CH_REQUIRE(n_apertures == 0 || survival_out != nullptr,
+             "ch_apply_maps: survival_out is required when apertures are present");
+  CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, "ch_apply_maps: bad dtype %d", dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CH_F32)
+    return ch::apply_typed<float>(particles_in, particle_stride, particle_index, survival_in,
+                                  survival_stride, survival_index, records, record_stride,
+                                  record_index, record_len, n_apertures, elliptical_mask,
+                                  n_particles, n_settings, particles_out, survival_out,
+                                  unit_seventh, s);
+  return ch::apply_typed<double>(particles_in, particle_stride, particle_index, survival_in,
+                                 survival_stride, survival_index, records, record_stride,
+                                 record_index, record_len, n_apertures, elliptical_mask,
+                                 n_particles, n_settings, particles_out, survival_out,
+                                 unit_seventh, s);
+}

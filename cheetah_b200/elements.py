@@ -1,0 +1,463 @@
+"""Lattice elements: the host-side mirror of ``cheetah/accelerator/*.py`` for the hot path.
+
+The classes keep the reference's names, constructor arguments, parameter attribute names
+(tensors registered as ``nn.Module`` buffers / parameters), ``is_skippable`` /
+``is_active`` rules, ``tracking_method`` hook and error behaviour, so user code and tests
+written against ``cheetah`` read the same.  They hold no physics: ``track`` and
+``first_order_transfer_map`` lower the element(s) to a lattice program and run the CUDA
+kernels (``cheetah_b200/tracking.py``).  There is no CPU path.
+
+Reference for the shared behaviour: cheetah/accelerator/element.py:17-312 (base class,
+tracking-method setter with ``PhysicsWarning`` at :239-259), segment.py:27-170 and
+:525-574 (container, flattening, skippable-run grouping).
+"""
+
+from __future__ import annotations
+
+import itertools
+import warnings
+from typing import Any, Iterable
+
+import torch
+from torch import nn
+
+from .beam import Beam
+from .species import Species
+
+
+class PhysicsWarning(UserWarning):
+    """Soft failure of a physics feature (mirror of cheetah/utils/warnings.py)."""
+
+
+_name_counter = itertools.count()
+
+# Bumped whenever any element attribute is (re)assigned or moved between devices; cached
+# lattice lowerings compare against it (the role of cheetah/utils/cache.py:29-40).
+_lattice_epoch = 0
+
+
+def lattice_epoch() -> int:
+    return _lattice_epoch
+
+
+def _bump_epoch() -> None:
+    global _lattice_epoch
+    _lattice_epoch += 1
+
+
+class Element(nn.Module):
+    """Base class of all lattice elements."""
+
+    # name -> default value of the tensor parameters a subclass registers
+    tensor_fields: dict[str, Any] = {}
+    supported_tracking_methods: list[str] = []
+
+    def __init__(
+        self,
+        name: str | None = None,
+        sanitize_name: bool | None = None,
+        metadata: dict | None = None,
+        device: torch.device | None = None,
+        dtype: torch.dtype | None = None,
+    ) -> None:
+        super().__init__()
+        self.name = name if name is not None else f"unnamed_element_{next(_name_counter)}"
+        self.metadata = metadata if metadata is not None else {}
+        if not isinstance(getattr(type(self), "length", None), property):
+            self.register_buffer("length", torch.tensor(0.0, device=device, dtype=dtype))
+        if not self.supported_tracking_methods:
+            self.supported_tracking_methods = [self.__class__.__name__.lower()]
+        self._tracking_method = self.supported_tracking_methods[0]
+
+    # ---- parameter registration ---------------------------------------------------------
+    def register_buffer_or_parameter(self, name: str, value: torch.Tensor) -> None:
+        if isinstance(value, nn.Parameter):
+            self.register_parameter(name, value)
+        else:
+            self.register_buffer(name, value)
+
+    def _register_fields(self, given: dict, factory_kwargs: dict) -> None:
+        for field, default in self.tensor_fields.items():
+            value = given.get(field)
+            if value is None:
+                value = torch.tensor(default, **factory_kwargs)
+            if field == "length":
+                self.length = value
+            else:
+                self.register_buffer_or_parameter(field, value)
+
+    def __setattr__(self, name: str, value: Any) -> None:
+        _bump_epoch()
+        super().__setattr__(name, value)
+
+    def _apply(self, fn, *args, **kwargs):
+        _bump_epoch()
+        return super()._apply(fn, *args, **kwargs)
+
+    # ---- tracking-method hook (element.py:231-259) ---------------------------------------
+    @property
+    def tracking_method(self) -> str:
+        return self._tracking_method
+
+    @tracking_method.setter
+    def tracking_method(self, tracking_method: str) -> None:
+        if tracking_method in self.supported_tracking_methods:
+            self._tracking_method = tracking_method
+        else:
+            warnings.warn(
+                f"Invalid tracking method '{tracking_method}' for element {self.name} of type "
+                f"{self.__class__.__name__}, supported methods are "
+                f"{self.supported_tracking_methods}. Keeping the previous tracking method "
+                f"{self._tracking_method}.",
+                PhysicsWarning,
+                stacklevel=2,
+            )
+
+    @property
+    def is_skippable(self) -> bool:
+        return True
+
+    # ---- the accelerated path -------------------------------------------------------------
+    def first_order_transfer_map(self, energy: torch.Tensor, species: Species) -> torch.Tensor:
+        from . import tracking
+
+        return tracking.first_order_transfer_map([self], energy, species)
+
+    def track(self, incoming: Beam) -> Beam:
+        from . import tracking
+
+        return tracking.track([self], incoming)
+
+    def forward(self, incoming: Beam) -> Beam:
+        return self.track(incoming)
+
+    def __repr__(self) -> str:
+        fields = ", ".join(f"{k}={getattr(self, k)!r}" for k in self.tensor_fields)
+        return f"{self.__class__.__name__}({fields}, name={self.name!r})"
+
+
+def _element_init(cls_fields: Iterable[str]):
+    """Build the keyword constructor shared by the simple magnet classes."""
+
+    def __init__(self, *args, name=None, sanitize_name=None, metadata=None, device=None,
+                 dtype=None, **kwargs):
+        fields = list(cls_fields)
+        if len(args) > len(fields):
+            raise TypeError(f"{type(self).__name__} takes at most {len(fields)} positional arguments")
+        given = dict(zip(fields, args))
+        tracking_method = kwargs.pop("tracking_method", None)
+        extras = {k: kwargs.pop(k) for k in list(kwargs) if k in self.plain_fields}
+        for key, value in kwargs.items():
+            if key not in fields:
+                raise TypeError(f"{type(self).__name__} got an unexpected keyword argument {key!r}")
+            given[key] = value
+        Element.__init__(self, name=name, sanitize_name=sanitize_name, metadata=metadata,
+                         device=device, dtype=dtype)
+        self._register_fields(given, {"device": device, "dtype": dtype})
+        for key, default in self.plain_fields.items():
+            setattr(self, key, extras.get(key, default))
+        if tracking_method is not None:
+            self.tracking_method = tracking_method
+
+    return __init__
+
+
+class _SimpleElement(Element):
+    plain_fields: dict[str, Any] = {}
+
+    def __init_subclass__(cls, **kwargs):
+        super().__init_subclass__(**kwargs)
+        if "__init__" not in cls.__dict__:
+            cls.__init__ = _element_init(cls.tensor_fields)
+
+
+class Drift(_SimpleElement):
+    """Drift section (cheetah/accelerator/drift.py)."""
+
+    tensor_fields = {"length": 0.0}
+    supported_tracking_methods = ["linear", "second_order", "drift_kick_drift"]
+
+    @property
+    def is_skippable(self) -> bool:
+        return self.tracking_method == "linear"
+
+
+class Quadrupole(_SimpleElement):
+    """Quadrupole magnet (cheetah/accelerator/quadrupole.py)."""
+
+    tensor_fields = {"length": 0.0, "k1": 0.0, "misalignment": (0.0, 0.0), "tilt": 0.0}
+    plain_fields = {"num_steps": 1}
+    supported_tracking_methods = ["linear", "second_order", "drift_kick_drift"]
+
+    @property
+    def is_skippable(self) -> bool:
+        return self.tracking_method == "linear"
+
+    @property
+    def is_active(self) -> bool:
+        return bool((self.k1 != 0).any())
+
+
+class Sextupole(_SimpleElement):
+    """Sextupole magnet; linear tracking is a drift (cheetah/accelerator/sextupole.py:84-88)."""
+
+    tensor_fields = {"length": 0.0, "k2": 0.0, "misalignment": (0.0, 0.0), "tilt": 0.0}
+    supported_tracking_methods = ["second_order", "linear"]
+
+    @property
+    def is_skippable(self) -> bool:
+        return self.tracking_method == "linear"
+
+
+class Dipole(_SimpleElement):
+    """Sector bend with pole-face edges (cheetah/accelerator/dipole.py)."""
+
+    tensor_fields = {
+        "length": 0.0, "angle": 0.0, "k1": 0.0, "dipole_e1": 0.0, "dipole_e2": 0.0,
+        "tilt": 0.0, "gap": 0.0, "gap_exit": None, "fringe_integral": 0.0,
+        "fringe_integral_exit": None,
+    }
+    plain_fields = {"fringe_at": "both", "fringe_type": "linear_edge"}
+    supported_tracking_methods = ["linear", "second_order", "drift_kick_drift"]
+
+    def _register_fields(self, given: dict, factory_kwargs: dict) -> None:
+        # exit values default to the entrance ones (dipole.py:111-124)
+        given = dict(given)
+        for field, default in self.tensor_fields.items():
+            if given.get(field) is None and default is not None:
+                given[field] = torch.tensor(default, **factory_kwargs)
+        if given.get("gap_exit") is None:
+            given["gap_exit"] = given["gap"]
+        if given.get("fringe_integral_exit") is None:
+            given["fringe_integral_exit"] = given["fringe_integral"]
+        for field in self.tensor_fields:
+            if field == "length":
+                self.length = given[field]
+            else:
+                self.register_buffer_or_parameter(field, given[field])
+
+    @property
+    def hx(self) -> torch.Tensor:
+        return self.angle / self.length
+
+    @property
+    def is_skippable(self) -> bool:
+        return self.tracking_method == "linear"
+
+    @property
+    def is_active(self) -> bool:
+        return bool((self.angle != 0).any())
+
+
+class RBend(Dipole):
+    """Rectangular bend: a Dipole whose edge angles are offset by angle/2 (rbend.py:83-101)."""
+
+    def __init__(self, length, angle=None, k1=None, rbend_e1=None, rbend_e2=None, tilt=None,
+                 gap=None, gap_exit=None, fringe_integral=None, fringe_integral_exit=None,
+                 fringe_at="both", fringe_type="linear_edge", tracking_method="linear",
+                 name=None, sanitize_name=None, metadata=None, device=None, dtype=None):
+        factory_kwargs = {"device": device, "dtype": dtype}
+        angle = angle if angle is not None else torch.tensor(0.0, **factory_kwargs)
+        rbend_e1 = rbend_e1 if rbend_e1 is not None else torch.tensor(0.0, **factory_kwargs)
+        rbend_e2 = rbend_e2 if rbend_e2 is not None else torch.tensor(0.0, **factory_kwargs)
+        Dipole.__init__(
+            self, length=length, angle=angle, k1=k1, dipole_e1=rbend_e1 + angle / 2,
+            dipole_e2=rbend_e2 + angle / 2, tilt=tilt, gap=gap, gap_exit=gap_exit,
+            fringe_integral=fringe_integral, fringe_integral_exit=fringe_integral_exit,
+            fringe_at=fringe_at, fringe_type=fringe_type, tracking_method=tracking_method,
+            name=name, sanitize_name=sanitize_name, metadata=metadata, **factory_kwargs,
+        )
+
+    @property
+    def rbend_e1(self) -> torch.Tensor:
+        return self.dipole_e1 - self.angle / 2
+
+    @rbend_e1.setter
+    def rbend_e1(self, value: torch.Tensor) -> None:
+        self.dipole_e1 = value + self.angle / 2
+
+    @property
+    def rbend_e2(self) -> torch.Tensor:
+        return self.dipole_e2 - self.angle / 2
+
+    @rbend_e2.setter
+    def rbend_e2(self, value: torch.Tensor) -> None:
+        self.dipole_e2 = value + self.angle / 2
+
+
+class HorizontalCorrector(_SimpleElement):
+    tensor_fields = {"length": 0.0, "angle": 0.0}
+    supported_tracking_methods = ["linear"]
+
+    @property
+    def is_active(self) -> bool:
+        return bool((self.angle != 0).any())
+
+
+class VerticalCorrector(_SimpleElement):
+    tensor_fields = {"length": 0.0, "angle": 0.0}
+    supported_tracking_methods = ["linear"]
+
+    @property
+    def is_active(self) -> bool:
+        return bool((self.angle != 0).any())
+
+
+class CombinedCorrector(_SimpleElement):
+    tensor_fields = {"length": 0.0, "horizontal_angle": 0.0, "vertical_angle": 0.0}
+    supported_tracking_methods = ["linear"]
+
+
+class Solenoid(_SimpleElement):
+    tensor_fields = {"length": 0.0, "k": 0.0, "misalignment": (0.0, 0.0)}
+    supported_tracking_methods = ["linear"]
+
+    @property
+    def is_active(self) -> bool:
+        return bool((self.k != 0).any())
+
+
+class Undulator(_SimpleElement):
+    tensor_fields = {"length": 0.0, "period": 0.0, "kx": 0.0, "ky": 0.0}
+    supported_tracking_methods = ["linear"]
+
+
+class Cavity(_SimpleElement):
+    """RF cavity; with voltage == 0 it is a skippable linear map (cavity.py:86-92)."""
+
+    tensor_fields = {"length": 0.0, "voltage": 0.0, "phase": 0.0, "frequency": 0.0}
+    plain_fields = {"cavity_type": "standing_wave"}
+
+    @property
+    def is_active(self) -> bool:
+        return bool((self.voltage != 0).any())
+
+    @property
+    def is_skippable(self) -> bool:
+        return not self.is_active
+
+
+class Marker(_SimpleElement):
+    tensor_fields = {}
+
+
+class BPM(_SimpleElement):
+    tensor_fields = {"misalignment": (0.0, 0.0)}
+    plain_fields = {"is_active": False}
+
+    @property
+    def is_skippable(self) -> bool:
+        return not self.is_active
+
+
+class Screen(_SimpleElement):
+    tensor_fields = {"pixel_size": (1e-3, 1e-3), "misalignment": (0.0, 0.0)}
+    plain_fields = {
+        "resolution": (1024, 1024), "binning": 1, "method": "cloud-in-cell",
+        "kde_bandwidth": None, "is_blocking": False, "is_active": False,
+    }
+
+    @property
+    def is_skippable(self) -> bool:
+        return not self.is_active
+
+
+class Aperture(_SimpleElement):
+    """Physical aperture (cheetah/accelerator/aperture.py)."""
+
+    tensor_fields = {"x_max": float("inf"), "y_max": float("inf")}
+    plain_fields = {"shape": "rectangular", "is_active": True}
+
+    @property
+    def is_skippable(self) -> bool:
+        return not self.is_active
+
+
+class CustomTransferMap(Element):
+    """Element defined by a user-supplied 7x7 map (custom_transfer_map.py:32-58)."""
+
+    supported_tracking_methods = ["linear"]
+    tensor_fields = {"predefined_transfer_map": None}
+
+    def __init__(self, predefined_transfer_map: torch.Tensor, length: torch.Tensor | None = None,
+                 name=None, sanitize_name=None, metadata=None, device=None, dtype=None) -> None:
+        super().__init__(name=name, sanitize_name=sanitize_name, metadata=metadata,
+                         device=device, dtype=dtype)
+        if length is not None:
+            self.length = length
+        assert predefined_transfer_map.shape[-2:] == (7, 7)
+        assert (predefined_transfer_map[..., -1, :-1] == 0.0).all() and (
+            predefined_transfer_map[..., -1, -1] == 1.0
+        ).all(), "The seventh row of the transfer map must be [0, 0, 0, 0, 0, 0, 1]."
+        self.register_buffer_or_parameter("predefined_transfer_map", predefined_transfer_map)
+
+
+class SpaceChargeKick(_SimpleElement):
+    """IGF space-charge kick (cheetah/accelerator/space_charge_kick.py)."""
+
+    tensor_fields = {
+        "effect_length": 0.0, "grid_extent_x": 3.0, "grid_extent_y": 3.0, "grid_extent_tau": 3.0,
+    }
+    plain_fields = {"grid_shape": (32, 32, 32)}
+
+    @property
+    def is_skippable(self) -> bool:
+        return False
+
+
+class Segment(Element):
+    """Ordered list of elements (cheetah/accelerator/segment.py)."""
+
+    def __init__(self, elements: list[Element], name: str | None = None,
+                 sanitize_name: bool | None = None, metadata: dict | None = None) -> None:
+        super().__init__(name=name, sanitize_name=sanitize_name, metadata=metadata)
+        self.elements = nn.ModuleList(elements)
+        for element in elements:  # `segment.<element name>` access (segment.py:60-70)
+            if element.name.isidentifier() and not hasattr(self, element.name):
+                object.__setattr__(self, "_alias_" + element.name, element)
+        self._plan_cache = None
+
+    def __getattr__(self, name: str):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            alias = self.__dict__.get("_alias_" + name)
+            if alias is not None:
+                return alias
+            raise
+
+    @property
+    def length(self) -> torch.Tensor:
+        total = None
+        for element in self.elements:
+            total = element.length if total is None else total + element.length
+        return total
+
+    @property
+    def is_skippable(self) -> bool:
+        return all(element.is_skippable for element in self.elements)
+
+    def flattened(self) -> "Segment":
+        """Flat copy of the element list (nested segments expanded; segment.py:143-157)."""
+        flat = []
+        for element in self.elements:
+            if isinstance(element, Segment):
+                flat.extend(element.flattened().elements)
+            else:
+                flat.append(element)
+        return Segment(elements=flat, name=self.name, sanitize_name=False)
+
+    def first_order_transfer_map(self, energy: torch.Tensor, species: Species) -> torch.Tensor:
+        if not self.is_skippable:
+            return None  # segment.py:542-543
+        from . import tracking
+
+        return tracking.first_order_transfer_map(list(self.elements), energy, species)
+
+    def track(self, incoming: Beam) -> Beam:
+        from . import tracking
+
+        return tracking.track(list(self.elements), incoming, cache_owner=self)
+
+    def __repr__(self) -> str:
+        return f"Segment(elements={list(self.elements)!r}, name={self.name!r})"

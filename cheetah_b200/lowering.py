@@ -1,0 +1,314 @@
+"""Lower a list of element objects to the lattice program consumed by the CUDA library.
+
+This replaces the per-call Python walk of ``Segment.track``
+(cheetah/accelerator/segment.py:545-574): consecutive skippable elements and active
+apertures form *linear sections* (one ``ch_compose_maps`` + one ``ch_apply_maps`` launch
+each); non-linear elements (``SpaceChargeKick``) are *barriers* between sections.
+
+Elements are duck-typed on their class name and the reference's attribute names, so the
+same code lowers ``cheetah_b200`` elements and the reference's own ``cheetah`` elements
+(INTEGRATION.md).  Parameter tensors are NOT copied: the program stores their device
+pointers, so in-place updates of magnet settings are picked up without re-lowering.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _capi
+
+
+@dataclass
+class SlotSpec:
+    tensor: torch.Tensor
+    inner_size: int = 1  # trailing (non-vector) elements per setting
+    inner_offset: int = 0
+    is_length: bool = False
+
+    @property
+    def vector_shape(self) -> tuple:
+        inner_dims = 0 if self.inner_size == 1 else (2 if self.inner_size == 49 else 1)
+        return tuple(self.tensor.shape[: self.tensor.dim() - inner_dims])
+
+
+@dataclass
+class Op:
+    opcode: int
+    flags: int
+    slots: list
+    element: object
+
+
+@dataclass
+class LinearSection:
+    op_begin: int
+    op_end: int
+    n_apertures: int = 0
+    elliptical_mask: int = 0
+    lattice_shape: tuple = ()          # broadcast vector shape of all parameters
+    length_shape: tuple = ()           # ... of the length parameters only
+    survival_shape: tuple = ()         # ... of everything up to and including the last aperture
+    has_maps: bool = False             # any non-identity op
+    apertures: list = field(default_factory=list)
+
+
+@dataclass
+class Barrier:
+    element: object
+    kind: str  # "space_charge" or "unsupported"
+
+
+class LatticeProgram:
+    """Owns the device-side program (``ch_program``) and keeps its tensors alive."""
+
+    def __init__(self, ops: list, stages: list, device: torch.device, watched: list) -> None:
+        self.ops = ops
+        self.stages = stages
+        self.device = device
+        self.watched = watched  # [(tensor, version)] whose VALUES shaped the lowering
+        self.handle = None  # created on first use, so lowering itself needs no GPU
+        self._keepalive = []
+
+    @property
+    def native(self):
+        """The ``ch_program*`` handle (uploads the tables on first access)."""
+        if self.handle is None:
+            self._upload()
+        return self.handle
+
+    def _upload(self) -> None:
+        lib = _capi.lib()
+        n_ops = len(self.ops)
+        opcodes = (ctypes.c_int32 * max(n_ops, 1))()
+        flags = (ctypes.c_int32 * max(n_ops, 1))()
+        slot_begin = (ctypes.c_int32 * (n_ops + 1))()
+        ptrs, strides, dtypes = [], [], []
+        for i, op in enumerate(self.ops):
+            opcodes[i] = op.opcode
+            flags[i] = op.flags
+            slot_begin[i] = len(ptrs)
+            for tensor, stride, offset in op.resolved:
+                self._keepalive.append(tensor)
+                ptrs.append(tensor.data_ptr() + offset * tensor.element_size())
+                strides.append(stride)
+                dtypes.append(_capi.dtype_code(tensor.dtype))
+        slot_begin[n_ops] = len(ptrs)
+        n_slots = len(ptrs)
+        c_ptrs = (ctypes.c_void_p * max(n_slots, 1))(*ptrs)
+        c_strides = (ctypes.c_int64 * max(n_slots, 1))(*strides)
+        c_dtypes = (ctypes.c_int32 * max(n_slots, 1))(*dtypes)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _capi.check(
+                lib.ch_program_create(
+                    opcodes, flags, slot_begin, n_ops, c_ptrs, c_strides, c_dtypes, n_slots,
+                    _capi.current_stream(self.device), ctypes.byref(handle),
+                )
+            )
+        self.handle = handle
+
+    def is_stale(self) -> bool:
+        return any(t._version != v for t, v in self.watched)
+
+    def __del__(self) -> None:
+        handle, self.handle = self.handle, None
+        if handle is not None and _capi._lib is not None:
+            try:
+                _capi._lib.ch_program_destroy(handle)
+            except Exception:  # interpreter shutdown
+                pass
+
+
+def _type_name(element) -> str:
+    return type(element).__name__
+
+
+def flatten(elements) -> list:
+    """Expand nested ``Segment`` / ``Superimposed`` (segment.py:143-157, superimposed.py:72-73)."""
+    flat = []
+    for element in elements:
+        kind = _type_name(element)
+        if kind == "Segment":
+            flat.extend(flatten(list(element.elements)))
+        elif kind == "Superimposed":
+            flat.extend(flatten(list(element._segment.elements)))
+        else:
+            flat.append(element)
+    return flat
+
+
+def _length(element) -> SlotSpec:
+    return SlotSpec(element.length, is_length=True)
+
+
+def _lower_linear(element) -> tuple[int, int, list]:
+    """(opcode, flags, slots) of one skippable element -- SURVEY appendix A."""
+    kind = _type_name(element)
+    if kind in ("Marker", "BPM", "Screen", "Aperture"):
+        return _capi.OP_IDENTITY, 0, []
+    if kind in ("Drift", "Sextupole"):
+        return _capi.OP_DRIFT, 0, [_length(element)]
+    if kind == "HorizontalCorrector":
+        return _capi.OP_CORRECTOR, 1, [_length(element), SlotSpec(element.angle)]
+    if kind == "VerticalCorrector":
+        return _capi.OP_CORRECTOR, 2, [_length(element), SlotSpec(element.angle)]
+    if kind == "CombinedCorrector":
+        return _capi.OP_CORRECTOR, 3, [
+            _length(element), SlotSpec(element.horizontal_angle), SlotSpec(element.vertical_angle),
+        ]
+    if kind == "Quadrupole":
+        return _capi.OP_QUADRUPOLE, 0, [
+            _length(element), SlotSpec(element.k1), SlotSpec(element.tilt),
+            SlotSpec(element.misalignment, 2, 0), SlotSpec(element.misalignment, 2, 1),
+        ]
+    if kind in ("Dipole", "RBend"):
+        return _capi.OP_DIPOLE, 0, [
+            _length(element), SlotSpec(element.angle), SlotSpec(element.k1),
+            SlotSpec(element.dipole_e1), SlotSpec(element.dipole_e2),
+            SlotSpec(element.fringe_integral), SlotSpec(element.fringe_integral_exit),
+            SlotSpec(element.gap), SlotSpec(element.tilt),
+        ]
+    if kind == "Solenoid":
+        return _capi.OP_SOLENOID, 0, [
+            _length(element), SlotSpec(element.k),
+            SlotSpec(element.misalignment, 2, 0), SlotSpec(element.misalignment, 2, 1),
+        ]
+    if kind == "Undulator":
+        return _capi.OP_UNDULATOR, 0, [
+            _length(element), SlotSpec(element.period), SlotSpec(element.kx),
+            SlotSpec(element.ky),
+        ]
+    if kind == "Cavity":
+        traveling = getattr(element, "cavity_type", "standing_wave") == "traveling_wave"
+        return _capi.OP_CAVITY_OFF, int(traveling), [_length(element)]
+    if kind == "CustomTransferMap":
+        return _capi.OP_CUSTOM_MAP, 0, [
+            SlotSpec(element.predefined_transfer_map, 49, 0), _length(element),
+        ]
+    raise NotImplementedError(
+        f"cheetah_b200: element type {kind} has no linear lowering (outside the hot path)"
+    )
+
+
+def _check_tensor(tensor: torch.Tensor, device: torch.device, what: str) -> None:
+    if not isinstance(tensor, torch.Tensor):
+        raise TypeError(f"{what} must be a tensor, got {type(tensor)}")
+    if tensor.device != device:
+        raise ValueError(
+            f"{what} lives on {tensor.device} but the beam is on {device}; move the lattice with "
+            "`segment.to(device)` first"
+        )
+    if tensor.requires_grad:
+        raise NotImplementedError(
+            f"{what} requires grad: the CUDA path is forward-only; differentiable tracking is the "
+            "reference implementation's job (SURVEY.md 2, row 12)"
+        )
+
+
+def lower(elements, device: torch.device, target_shape: tuple = ()) -> LatticeProgram:
+    """Lower ``elements`` for tensors on ``device``.
+
+    ``target_shape`` is the vector shape contributed from outside the lattice (the beam's
+    energy); parameters whose vector shape is neither ``()`` nor the section's full
+    broadcast shape are materialised (expanded copies) and watched for staleness.
+    """
+    ops: list[Op] = []
+    stages: list = []
+    watched: list = []
+    section: LinearSection | None = None
+
+    def open_section() -> LinearSection:
+        nonlocal section
+        if section is None:
+            section = LinearSection(op_begin=len(ops), op_end=len(ops))
+        return section
+
+    def close_section() -> None:
+        nonlocal section
+        if section is None:
+            return
+        section.op_end = len(ops)
+        _finish_section(section, ops, device, target_shape, watched)
+        stages.append(section)
+        section = None
+
+    for element in flatten(elements):
+        kind = _type_name(element)
+        if kind == "Cavity":
+            watched.append((element.voltage, element.voltage._version))
+        if element.is_skippable:
+            opcode, flags, slots = _lower_linear(element)
+            sec = open_section()
+            if opcode != _capi.OP_IDENTITY:
+                sec.has_maps = True
+            ops.append(Op(opcode, flags, slots, element))
+        elif kind == "Aperture":
+            shape = element.shape
+            assert shape in ("rectangular", "elliptical"), f"Unknown aperture shape {shape}"
+            sec = open_section()
+            if sec.n_apertures == _capi.MAX_APERTURES:
+                close_section()
+                sec = open_section()
+            if shape == "elliptical":
+                sec.elliptical_mask |= 1 << sec.n_apertures
+            sec.n_apertures += 1
+            sec.apertures.append(element)
+            ops.append(
+                Op(_capi.OP_APERTURE, int(shape == "elliptical"),
+                   [SlotSpec(element.x_max), SlotSpec(element.y_max)], element)
+            )
+        elif kind == "SpaceChargeKick":
+            close_section()
+            stages.append(Barrier(element, "space_charge"))
+        else:
+            close_section()
+            stages.append(Barrier(element, "unsupported"))
+    close_section()
+    return LatticeProgram(ops, stages, device, watched)
+
+
+def _finish_section(section: LinearSection, ops: list, device, target_shape, watched) -> None:
+    """Resolve vector shapes and per-slot strides of one linear section."""
+    shapes, length_shapes = [tuple(target_shape)], []
+    survival_shape: tuple = ()
+    running: tuple = ()
+    for op in ops[section.op_begin : section.op_end]:
+        for slot in op.slots:
+            _check_tensor(slot.tensor, device, f"parameter of element {op.element.name!r}")
+            shapes.append(slot.vector_shape)
+            running = torch.broadcast_shapes(running, slot.vector_shape)
+            if slot.is_length:
+                length_shapes.append(slot.vector_shape)
+        if op.opcode == _capi.OP_APERTURE:
+            survival_shape = running
+    full = tuple(torch.broadcast_shapes(*shapes))
+    section.lattice_shape = full
+    section.length_shape = tuple(torch.broadcast_shapes(*length_shapes)) if length_shapes else ()
+    section.survival_shape = tuple(survival_shape)
+
+    for op in ops[section.op_begin : section.op_end]:
+        resolved = []
+        for slot in op.slots:
+            tensor = slot.tensor
+            if tensor.dtype not in (torch.float32, torch.float64):
+                watched.append((tensor, tensor._version))
+                tensor = tensor.to(torch.float64)
+            vshape = slot.vector_shape
+            if math.prod(vshape) == 1:
+                stride = 0
+                if not tensor.is_contiguous():
+                    watched.append((slot.tensor, slot.tensor._version))
+                    tensor = tensor.contiguous()
+            elif vshape == full and tensor.is_contiguous():
+                stride = slot.inner_size
+            else:  # partial broadcast or strided view: expanded copy, watched for staleness
+                watched.append((slot.tensor, slot.tensor._version))
+                inner = tuple(tensor.shape[len(vshape):])
+                tensor = tensor.expand(*full, *inner).contiguous()
+                stride = slot.inner_size
+            resolved.append((tensor, stride, slot.inner_offset))
+        op.resolved = resolved

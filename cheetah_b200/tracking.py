@@ -1,0 +1,283 @@
+"""``Segment.track`` / ``Element.track`` / ``first_order_transfer_map`` on the CUDA library.
+
+Host-side mirror of cheetah/accelerator/segment.py:534-574 and element.py:159-193: beam
+bookkeeping (``s``, ``energy``, ``species.clone()``, pass-through of untouched tensors,
+NumPy-style broadcasting of vector dimensions) stays in Python; every floating-point
+operation on maps and particles happens in ``libcheetah_b200.so``.  No CPU fallback: a beam
+that is not on a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+
+from . import _capi, lowering
+from .beam import ParameterBeam, ParticleBeam
+
+
+def _is_particle_beam(beam) -> bool:
+    return type(beam).__name__ == "ParticleBeam"
+
+
+def _is_parameter_beam(beam) -> bool:
+    return type(beam).__name__ == "ParameterBeam"
+
+
+def _require_cuda(tensor: torch.Tensor, what: str) -> None:
+    if not tensor.is_cuda:
+        raise RuntimeError(
+            f"cheetah_b200: {what} is on {tensor.device}. This backend only runs on CUDA devices "
+            "(B200, sm_100a) and has no CPU fallback; move the beam and lattice to 'cuda'."
+        )
+
+
+def _plan(elements, device: torch.device, target_shape: tuple, cache_owner=None):
+    """Lowered program for ``elements``, cached on ``cache_owner`` (a Segment) while no element
+    attribute changes (the epoch) and no value-dependent decision goes stale."""
+    from .elements import lattice_epoch
+
+    key = (lattice_epoch(), device, tuple(target_shape))
+    cache = getattr(cache_owner, "_plan_cache", None) if cache_owner is not None else None
+    if cache is not None and cache[0] == key and not cache[1].is_stale():
+        return cache[1]
+    program = lowering.lower(elements, device, target_shape)
+    if cache_owner is not None and hasattr(cache_owner, "_plan_cache"):
+        object.__setattr__(cache_owner, "_plan_cache", (key, program))
+    return program
+
+
+def _index_table(source_shape: tuple, out_shape: tuple, device) -> torch.Tensor | None:
+    """int32 table mapping a flat index over ``out_shape`` to one over ``source_shape``
+    (None when the mapping is the identity or a constant)."""
+    if math.prod(source_shape) == 1 or tuple(source_shape) == tuple(out_shape):
+        return None
+    index = torch.arange(math.prod(source_shape), dtype=torch.int32, device=device)
+    return index.reshape(source_shape).expand(out_shape).reshape(-1).contiguous()
+
+
+def _compose(program, section, energy: torch.Tensor, mass_eV: torch.Tensor, dtype):
+    """Run ``ch_compose_maps`` for one section -> records ``(*map_shape, record_len)``."""
+    device = energy.device
+    map_shape = tuple(torch.broadcast_shapes(section.lattice_shape, energy.shape))
+    n_settings = math.prod(map_shape)
+    if energy.dtype not in (torch.float32, torch.float64):
+        energy = energy.to(dtype)
+    if energy.numel() == 1:
+        energy_stride = 0
+    else:
+        energy = energy.expand(map_shape).contiguous()
+        energy_stride = 1
+    rec_len = _capi.record_len(section.n_apertures)
+    records = torch.empty((n_settings, rec_len), dtype=dtype, device=device)
+    with torch.cuda.device(device):
+        _capi.check(
+            _capi.lib().ch_compose_maps(
+                program.native, section.op_begin, section.op_end, n_settings,
+                energy.data_ptr(), energy_stride, _capi.dtype_code(energy.dtype),
+                mass_eV.data_ptr(), _capi.dtype_code(mass_eV.dtype),
+                records.data_ptr(), rec_len, _capi.dtype_code(dtype),
+                _capi.current_stream(device),
+            )
+        )
+    return records, map_shape
+
+
+def _section_length(records: torch.Tensor, map_shape: tuple, length_shape: tuple) -> torch.Tensor:
+    """Sum of element lengths with the reference's (un-expanded) vector shape."""
+    total = records[:, 1].reshape(map_shape)
+    # drop the vector dims the lengths do not carry
+    lead = len(map_shape) - len(length_shape)
+    index = [0] * lead + [slice(None) if n > 1 else 0 for n in length_shape]
+    total = total[tuple(index)] if index else total
+    return total.reshape(length_shape)
+
+
+def _maps_from_records(records: torch.Tensor, map_shape: tuple) -> torch.Tensor:
+    """(..., 7, 7) maps from compose records."""
+    n = records.shape[0]
+    tm = torch.zeros((n, 7, 7), dtype=records.dtype, device=records.device)
+    tm[:, :6, :] = records[:, _capi.RECORD_HEADER : _capi.RECORD_HEADER + 42].reshape(n, 6, 7)
+    tm[:, 6, 6] = 1.0
+    return tm.reshape(*map_shape, 7, 7)
+
+
+def first_order_transfer_map(elements, energy: torch.Tensor, species) -> torch.Tensor:
+    """Merged first-order map of skippable ``elements`` (segment.py:534-541)."""
+    _require_cuda(energy, "energy")
+    program = _plan(elements, energy.device, tuple(energy.shape))
+    sections = [s for s in program.stages if isinstance(s, lowering.LinearSection)]
+    if len(program.stages) == 0:
+        return torch.eye(7, dtype=energy.dtype, device=energy.device).repeat(*energy.shape, 1, 1)
+    if len(sections) != 1 or len(program.stages) != 1 or sections[0].n_apertures:
+        raise ValueError("first_order_transfer_map needs a run of skippable elements")
+    dtype = energy.dtype if energy.dtype in (torch.float32, torch.float64) else torch.float32
+    records, map_shape = _compose(program, sections[0], energy, species.mass_eV, dtype)
+    return _maps_from_records(records, map_shape)
+
+
+def _unit_seventh(beam) -> bool:
+    flag = getattr(beam, "_unit_seventh", None)
+    if flag is None:
+        flag = bool((beam.particles[..., 6] == 1).all())
+        try:
+            beam._unit_seventh = flag
+        except Exception:
+            pass
+    return flag
+
+
+def _track_linear_section(program, section, beam):
+    """One ``ch_compose_maps`` + one ``ch_apply_maps`` for a ParticleBeam."""
+    particles = beam.particles
+    device, dtype = particles.device, particles.dtype
+    if dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"cheetah_b200 tracks float32/float64 beams, got {dtype}")
+    n = particles.shape[-2]
+    vp = tuple(particles.shape[:-2])
+
+    records, vm = _compose(program, section, beam.energy, beam.species.mass_eV, dtype)
+    new_s = beam.s + _section_length(records, vm, section.length_shape)
+
+    if not section.has_maps and section.n_apertures == 0:
+        return beam.__class__(
+            particles, beam.energy, particle_charges=beam.particle_charges,
+            survival_probabilities=beam.survival_probabilities, s=new_s,
+            species=beam.species.clone(),
+        )
+
+    vo = tuple(torch.broadcast_shapes(vm, vp))
+    n_out = math.prod(vo)
+    if not particles.is_contiguous():
+        particles = particles.contiguous()
+    particle_index = _index_table(vp, vo, device)
+    record_index = _index_table(vm, vo, device)
+    out = torch.empty((*vo, n, 7), dtype=dtype, device=device)
+
+    survival_in = beam.survival_probabilities
+    survival_out = None
+    survival_index = None
+    vs = tuple(survival_in.shape[:-1])
+    if section.n_apertures:
+        if survival_in.dtype != dtype or not survival_in.is_contiguous():
+            survival_in = survival_in.to(dtype).contiguous()
+        # the kernel works on the full output batch; the reference's survival tensor only
+        # carries the vector dims that reached the last aperture
+        vfull = tuple(torch.broadcast_shapes(vo, vs))
+        if vfull != vo:
+            raise NotImplementedError(
+                "survival_probabilities with vector dimensions beyond those of particles and "
+                "lattice are not supported"
+            )
+        survival_index = _index_table(vs, vo, device)
+        survival_out = torch.empty((*vo, n), dtype=dtype, device=device)
+
+    with torch.cuda.device(device):
+        _capi.check(
+            _capi.lib().ch_apply_maps(
+                particles.data_ptr(), 0 if math.prod(vp) == 1 else n * 7,
+                _capi.ptr(particle_index),
+                survival_in.data_ptr() if section.n_apertures else None,
+                0 if math.prod(vs) == 1 else n, _capi.ptr(survival_index),
+                records.data_ptr(), 0 if math.prod(vm) == 1 else records.shape[1],
+                _capi.ptr(record_index),
+                records.shape[1], section.n_apertures, section.elliptical_mask,
+                n, n_out, out.data_ptr(), _capi.ptr(survival_out),
+                _capi.dtype_code(dtype), int(_unit_seventh(beam)),
+                _capi.current_stream(device),
+            )
+        )
+
+    if survival_out is not None:
+        # reference shape: broadcast(survival_in, particles vector dims, everything up to and
+        # including the last aperture); later (post-aperture) vectorised elements do not widen it
+        keep = tuple(torch.broadcast_shapes(vs, vp, section.survival_shape, beam.energy.shape))
+        if keep != vo:
+            lead = len(vo) - len(keep)
+            index = [0] * lead + [slice(None) if k > 1 else 0 for k in keep]
+            survival_out = survival_out[tuple(index)].reshape(*keep, n)
+        new_survival = survival_out
+    else:
+        new_survival = beam.survival_probabilities
+
+    outgoing = beam.__class__(
+        out, beam.energy, particle_charges=beam.particle_charges,
+        survival_probabilities=new_survival, s=new_s, species=beam.species.clone(),
+    )
+    try:
+        outgoing._unit_seventh = _unit_seventh(beam)
+    except Exception:
+        pass
+    return outgoing
+
+
+def _track_parameter_beam(program, beam):
+    """tm @ mu, tm @ cov @ tm^T with the composed maps (element.py:166-179)."""
+    mu, cov, s = beam.mu, beam.cov, beam.s
+    for stage in program.stages:
+        if isinstance(stage, lowering.Barrier):
+            if stage.kind == "space_charge":
+                raise AssertionError(
+                    "SpaceChargeKick tracking is currently only supported for `ParticleBeam`."
+                )
+            raise NotImplementedError(
+                f"cheetah_b200: element {stage.element.name!r} of type "
+                f"{type(stage.element).__name__} is outside the accelerated hot path"
+            )
+        if stage.n_apertures:
+            warnings.warn(
+                "Aperture tracking is currently only supported for `ParticleBeam`.",
+                _physics_warning(), stacklevel=3,
+            )
+        dtype = mu.dtype
+        records, vm = _compose(program, stage, beam.energy, beam.species.mass_eV, dtype)
+        tm = _maps_from_records(records, vm)
+        mu = (tm @ mu.unsqueeze(-1)).squeeze(-1)
+        cov = tm @ cov @ tm.mT
+        s = s + _section_length(records, vm, stage.length_shape)
+    return beam.__class__(
+        mu, cov, beam.energy, total_charge=beam.total_charge, s=s, species=beam.species.clone()
+    )
+
+
+def _physics_warning():
+    from .elements import PhysicsWarning
+
+    return PhysicsWarning
+
+
+def track(elements, incoming, cache_owner=None):
+    """Track ``incoming`` through ``elements`` (segment.py:545-574)."""
+    if _is_parameter_beam(incoming):
+        _require_cuda(incoming.mu, "ParameterBeam")
+        program = _plan(elements, incoming.mu.device, tuple(incoming.energy.shape), cache_owner)
+        return _track_parameter_beam(program, incoming)
+    if not _is_particle_beam(incoming):
+        raise TypeError(f"Parameter incoming is of invalid type {type(incoming)}")
+    _require_cuda(incoming.particles, "ParticleBeam")
+
+    program = _plan(elements, incoming.particles.device, tuple(incoming.energy.shape), cache_owner)
+    beam = incoming
+    for stage in program.stages:
+        if isinstance(stage, lowering.LinearSection):
+            beam = _track_linear_section(program, stage, beam)
+        elif stage.kind == "space_charge":
+            from . import space_charge
+
+            beam = space_charge.track(stage.element, beam)
+        else:
+            raise NotImplementedError(
+                f"cheetah_b200: element {stage.element.name!r} of type "
+                f"{type(stage.element).__name__} (tracking_method="
+                f"{getattr(stage.element, 'tracking_method', None)!r}) is outside the accelerated "
+                "hot path of this build (SURVEY.md 8f)"
+            )
+    if beam is incoming:  # empty lattice: still hand back a new beam object
+        beam = incoming.__class__(
+            incoming.particles, incoming.energy, particle_charges=incoming.particle_charges,
+            survival_probabilities=incoming.survival_probabilities, s=incoming.s,
+            species=incoming.species.clone(),
+        )
+    return beam

@@ -1,0 +1,158 @@
+/*
+ * cheetah_b200 -- C ABI of the B200-native backend for Cheetah's
+ * Segment.track(ParticleBeam) hot path.
+ *
+ * The reference (desy-ml/cheetah @ 60d1053) is pure Python/PyTorch and has no FFI; the
+ * drop-in boundary is its public Python API.  Each entry point below
+ * replaces the body of one group of reference functions (cited as file:line relative to
+ * the reference root) and is what a ctypes binding inside those functions would call
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative CH_E* code on failure; the
+ *    message for the calling thread is available from ch_last_error().  Nothing throws
+ *    across the ABI.
+ *  - all data pointers are DEVICE pointers unless the name ends in _host; the caller
+ *    owns every buffer it passes in, including outputs.  The library only owns
+ *    ch_program objects and the ch_workspace scratch it is asked to create.
+ *  - `stream` is a cudaStream_t passed as void* (PyTorch:
+ *    torch.cuda.current_stream().cuda_stream); all work is enqueued on it, no call
+ *    synchronises the device.
+ *  - dtype arguments are CH_F32 or CH_F64.
+ *  - "settings" (B) is the flattened vectorised batch of lattice settings and/or beams.
+ */
+#ifndef CHEETAH_B200_H
+#define CHEETAH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CH_ABI_VERSION 1
+
+enum { CH_F32 = 0, CH_F64 = 1 };
+
+enum {
+  CH_OK = 0,
+  CH_EINVAL = -1,   /* bad argument */
+  CH_ECUDA = -2,    /* CUDA runtime error (message carries cudaGetErrorString) */
+  CH_ENOMEM = -3,
+  CH_EUNSUPPORTED = -4
+};
+
+/* Element opcodes of a lowered lattice program (one op per flattened element).        */
+enum {
+  CH_OP_IDENTITY = 0,     /* Marker, inactive BPM/Screen/Aperture: marker.py:44-50,      */
+                          /*   bpm.py:69-75, screen.py:176-185, aperture.py:82-88        */
+  CH_OP_DRIFT = 1,        /* slots: length            track_methods.py:284-299           */
+                          /*   (also Sextupole with tracking_method="linear",            */
+                          /*   sextupole.py:84-88)                                       */
+  CH_OP_CORRECTOR = 2,    /* slots: length, angle_h, angle_v (either may be -1)          */
+                          /*   horizontal_corrector.py:60-78, vertical_corrector.py:60-78*/
+                          /*   combined_corrector.py:76-98                               */
+  CH_OP_QUADRUPOLE = 3,   /* slots: length, k1, tilt, mis_x, mis_y  quadrupole.py:93-110 */
+  CH_OP_DIPOLE = 4,       /* slots: length, angle, k1, e1, e2, fint, fint_exit, gap,     */
+                          /*   tilt   dipole.py:372-394, :430-466 (RBend: rbend.py:83-101*/
+                          /*   lowers to the same op with e1/e2 already offset)          */
+  CH_OP_SOLENOID = 5,     /* slots: length, k, mis_x, mis_y        solenoid.py:74-116    */
+  CH_OP_UNDULATOR = 6,    /* slots: length, period, kx, ky         undulator.py:78-125   */
+  CH_OP_CAVITY_OFF = 7,   /* slots: length; op_flags bit0 = traveling wave               */
+                          /*   cavity.py:253-358 evaluated at voltage == 0               */
+  CH_OP_CUSTOM_MAP = 8,   /* slots: map (7x7 row-major, slot stride = 49 per setting),   */
+                          /*   optional length                                           */
+                          /*   custom_transfer_map.py:111-114                            */
+  CH_OP_APERTURE = 9      /* slots: x_max, y_max; op_flags bit0 = elliptical             */
+                          /*   aperture.py:90-132 (cut point, not a map)                 */
+};
+
+/* Per-setting record written by ch_compose_maps, `record_len` scalars of the beam dtype:
+ *   [0]            sparsity flags (integer stored in the scalar's bit pattern, see
+ *                  CH_FLAG_*), [1] sum of the element lengths of the section
+ *   [2 .. 43]      rows 0-5 of the cumulative 7x7 map from the start of the section to
+ *                  its end, row-major 6x7 (row 6 is always 0 0 0 0 0 0 1)
+ *   then for each aperture a (in lattice order), 16 scalars:
+ *     [0..6] row 0 (x) and [7..13] row 2 (y) of the cumulative map from the start of the
+ *     section to the aperture, [14] x_max, [15] y_max
+ */
+#define CH_RECORD_HEADER 2
+#define CH_RECORD_MAP 42
+#define CH_RECORD_APERTURE 16
+#define CH_RECORD_LEN(n_apertures) (CH_RECORD_HEADER + CH_RECORD_MAP + CH_RECORD_APERTURE * (n_apertures))
+#define CH_MAX_APERTURES 32
+
+/* sparsity flags: a set bit means the named group of map entries is exactly zero in
+ * every map of the record, so ch_apply_maps may skip its multiplies                     */
+#define CH_FLAG_XY_UNCOUPLED 1u    /* (0..1 x 2..3) and (2..3 x 0..1) blocks             */
+#define CH_FLAG_NO_TAU_COLUMN 2u   /* column 4 of rows 0-3 and row 5                     */
+#define CH_FLAG_DELTA_IDENTITY 4u  /* row 5 is 0 0 0 0 0 1 0                             */
+#define CH_FLAG_NO_Y_DISPERSION 8u /* (2..3, 5) and (4, 2..3)                            */
+
+typedef struct ch_program ch_program;
+
+/* library ------------------------------------------------------------------------- */
+int ch_abi_version(void);
+const char* ch_last_error(void);
+/* number of kernels this library has launched since load (monotonic) */
+int64_t ch_kernel_launch_count(void);
+
+/* lattice program ----------------------------------------------------------------- */
+/* Replaces the per-call walk over element objects in Segment.track
+ * (cheetah/accelerator/segment.py:545-574).  Host arrays describe the flattened lattice:
+ * op i uses slots [slot_begin[i], slot_begin[i+1]) (slot_begin has n_ops+1 entries).
+ * Slot s reads setting b at  ((T*)slot_ptrs[s])[b * slot_strides[s]]  with T given by
+ * slot_dtypes[s]; stride 0 broadcasts one value to all settings.  The slot pointers are
+ * borrowed: they must stay valid while the program is used (they are the live parameter
+ * tensors of the element objects, so in-place updates are seen without re-lowering).  */
+int ch_program_create(const int32_t* opcodes_host, const int32_t* op_flags_host,
+                      const int32_t* slot_begin_host, int32_t n_ops,
+                      const void* const* slot_ptrs_host, const int64_t* slot_strides_host,
+                      const int32_t* slot_dtypes_host, int32_t n_slots,
+                      void* stream, ch_program** program_out);
+int ch_program_destroy(ch_program* program);
+
+/* map composition ----------------------------------------------------------------- */
+/* Replaces Element.first_order_transfer_map for every element type
+ * (cheetah/track_methods.py:17-77, :284-382 and the wrappers listed at the opcodes) and
+ * the merged-map product of Segment.first_order_transfer_map
+ * (cheetah/accelerator/segment.py:534-541), for ops [op_begin, op_end) of `program`,
+ * for n_settings settings.  One thread per setting walks the ops, keeps the cumulative
+ * 6x7 map in fp64 registers, and writes one record (layout above) per setting, rounded
+ * once to `record_dtype`.  energy / mass_eV are read like slots
+ * (energy[b * energy_stride]).  gamma, beta follow cheetah/utils/physics.py:4-19.      */
+int ch_compose_maps(const ch_program* program, int32_t op_begin, int32_t op_end,
+                    int64_t n_settings,
+                    const void* energy, int64_t energy_stride, int32_t energy_dtype,
+                    const void* mass_eV, int32_t mass_dtype,
+                    void* records, int64_t record_len, int32_t record_dtype,
+                    void* stream);
+
+/* map application ----------------------------------------------------------------- */
+/* Replaces, in ONE pass over the particles, every `particles @ tm.mT` of
+ * Element._track_first_order (cheetah/accelerator/element.py:181-191) and every
+ * Aperture.track mask update (cheetah/accelerator/aperture.py:108-132) of one linear
+ * section of the lattice.
+ *
+ *   particles_out[b, n, :] = M_b . particles_in[pidx(b), n, :]
+ *   survival_out[b, n]     = survival_in[sidx(b), n] * prod_a mask_a(x_a, y_a)
+ *
+ * where M_b and the aperture rows come from records[ridx(b)], and for X in {p, r, s}
+ * Xidx(b) = (X_index ? X_index[b] : b) * X_stride (stride 0 shares one entry among all
+ * settings; strides are in units of one batch entry).  Rectangular masks use strict
+ * comparisons, elliptical ones x^2/x_max^2 + y^2/y_max^2 <= 1, evaluated with IEEE
+ * round-to-nearest operations in the beam dtype exactly as the reference does.
+ * survival_out may be NULL iff n_apertures == 0.  unit_seventh != 0 asserts that
+ * particles_in[..., 6] == 1 (then the kernel adds column 6 instead of multiplying).   */
+int ch_apply_maps(const void* particles_in, int64_t particle_stride, const int32_t* particle_index,
+                  const void* survival_in, int64_t survival_stride, const int32_t* survival_index,
+                  const void* records, int64_t record_stride, const int32_t* record_index,
+                  int64_t record_len, int32_t n_apertures, uint32_t elliptical_mask,
+                  int64_t n_particles, int64_t n_settings,
+                  void* particles_out, void* survival_out,
+                  int32_t dtype, int32_t unit_seventh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHEETAH_B200_H */

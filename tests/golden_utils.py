@@ -57,3 +57,47 @@ def set_attr(description: list, name: str, attr: str, value) -> None:
             element[attr] = value
             return
     raise KeyError(name)
+
+
+# ---- product-side helpers (need the CUDA library + a GPU) ---------------------------------
+def product_segment(description: list, device, dtype):
+    import cheetah_b200
+
+    return cheetah_b200.Segment(
+        elements=lattice_io.build(description, cheetah_b200, device=device, dtype=dtype)
+    )
+
+
+def product_beam(beam: dict, device, dtype):
+    """cheetah_b200.ParticleBeam from an oracle-style beam dict."""
+    import cheetah_b200
+
+    charges = float(beam["num_elementary_charges"])
+    mass = float(beam["mass_eV"])
+    known = {(-1.0, 510998.95069): "electron", (1.0, 938272089.4300001): "proton"}
+    name = known.get((charges, mass))
+    if name is not None:
+        species = cheetah_b200.Species(name, device=device, dtype=dtype)
+    else:
+        species = cheetah_b200.Species(
+            "custom",
+            num_elementary_charges=torch.tensor(charges, device=device, dtype=dtype),
+            mass_eV=torch.tensor(mass, device=device, dtype=torch.float64).to(dtype),
+        )
+    to = lambda t: t.to(device=device, dtype=dtype)  # noqa: E731
+    return cheetah_b200.ParticleBeam(
+        particles=to(beam["particles"]),
+        energy=to(beam["energy"]),
+        particle_charges=to(beam["particle_charges"]),
+        survival_probabilities=to(beam["survival_probabilities"]),
+        s=to(beam["s"]),
+        species=species,
+    )
+
+
+def column_scaled_error(actual: torch.Tensor, expected: torch.Tensor) -> float:
+    """max |actual - expected| / max|expected| per phase-space column (the SURVEY 7.2 metric)."""
+    actual = actual.detach().cpu().to(torch.float64)
+    expected = expected.detach().cpu().to(torch.float64)
+    scale = expected.abs().amax(dim=-2, keepdim=True).clamp_min(1e-300)
+    return float(((actual - expected).abs() / scale)[..., :6].max())

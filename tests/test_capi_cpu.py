@@ -1,0 +1,136 @@
+"""CPU-side checks of the boundary: the library loads and exports every declared symbol, and
+the host logic (lowering, shapes, errors) behaves without a GPU."""
+
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+import cheetah_b200 as cb
+from cheetah_b200 import _capi, lowering
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols() -> set:
+    header = (REPO / "include" / "cheetah_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    return set(re.findall(r"\b(ch_[a-z0-9_]+)\s*\(", header))
+
+
+def test_library_exports_every_declared_symbol():
+    from cheetah_b200 import build
+
+    build.build()
+    lib = _capi.lib()
+    symbols = declared_symbols()
+    assert symbols, "no symbols parsed from the header"
+    assert symbols == set(_capi.SIGNATURES), symbols ^ set(_capi.SIGNATURES)
+    for name in symbols:
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert lib.ch_abi_version() == 1
+    assert lib.ch_kernel_launch_count() == 0  # nothing computes on a CPU-only box
+
+
+def test_program_create_validates_arguments_without_a_gpu():
+    import ctypes
+
+    lib = _capi.lib()
+    handle = ctypes.c_void_p()
+    opcodes = (ctypes.c_int32 * 1)(99)
+    flags = (ctypes.c_int32 * 1)(0)
+    begin = (ctypes.c_int32 * 2)(0, 0)
+    status = lib.ch_program_create(opcodes, flags, begin, 1, None, None, None, 0, None,
+                                   ctypes.byref(handle))
+    assert status == -1
+    assert b"unknown opcode" in lib.ch_last_error()
+    with pytest.raises(_capi.BackendError, match="unknown opcode"):
+        _capi.check(status)
+
+
+def test_lowering_groups_runs_apertures_and_barriers():
+    t = torch.tensor
+    elements = [
+        cb.Drift(length=t(0.5)),
+        cb.Quadrupole(length=t(0.2), k1=t([1.0, 2.0, 3.0])),
+        cb.Marker(),
+        cb.Aperture(x_max=t(1e-3), y_max=t(2e-3), shape="elliptical"),
+        cb.Segment([cb.Drift(length=t(0.1)), cb.BPM()]),
+        cb.SpaceChargeKick(effect_length=t(1.0)),
+        cb.Aperture(is_active=False),
+        cb.Drift(length=t(0.5), tracking_method="drift_kick_drift"),
+        cb.HorizontalCorrector(length=t(0.1), angle=t(1e-4)),
+    ]
+    program = lowering.lower(elements, torch.device("cpu"))
+    kinds = [type(s).__name__ for s in program.stages]
+    assert kinds == ["LinearSection", "Barrier", "LinearSection", "Barrier", "LinearSection"]
+    first = program.stages[0]
+    assert (first.op_begin, first.op_end) == (0, 6)
+    assert first.n_apertures == 1 and first.elliptical_mask == 1
+    assert first.lattice_shape == (3,) and first.length_shape == () and first.survival_shape == (3,)
+    assert program.stages[1].kind == "space_charge"
+    assert program.stages[3].kind == "unsupported"
+    assert [op.opcode for op in program.ops[:6]] == [
+        _capi.OP_DRIFT, _capi.OP_QUADRUPOLE, _capi.OP_IDENTITY, _capi.OP_APERTURE,
+        _capi.OP_DRIFT, _capi.OP_IDENTITY,
+    ]
+    # vectorised k1 is referenced in place (stride 1), scalars broadcast (stride 0)
+    quad = program.ops[1]
+    assert [stride for _, stride, _ in quad.resolved] == [0, 1, 0, 0, 0]
+    assert quad.resolved[1][0].data_ptr() == elements[1].k1.data_ptr()
+    assert [offset for _, _, offset in quad.resolved] == [0, 0, 0, 0, 1]
+
+
+def test_lowering_rejects_grad_and_wrong_device():
+    k1 = torch.tensor(1.0, requires_grad=True)
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        lowering.lower([cb.Quadrupole(length=torch.tensor(1.0), k1=k1)], torch.device("cpu"))
+    with pytest.raises(ValueError, match="move the lattice"):
+        lowering.lower([cb.Drift(length=torch.tensor(1.0))], torch.device("cuda:0"))
+
+
+def test_cavity_skippability_is_watched():
+    cavity = cb.Cavity(length=torch.tensor(1.0))
+    program = lowering.lower([cavity], torch.device("cpu"))
+    assert isinstance(program.stages[0], lowering.LinearSection) and not program.is_stale()
+    cavity.voltage.fill_(1e6)
+    assert program.is_stale()
+    assert lowering.lower([cavity], torch.device("cpu")).stages[0].kind == "unsupported"
+
+
+def test_element_api_mirrors_the_reference():
+    quad = cb.Quadrupole(length=torch.tensor(1.0), k1=torch.tensor(2.0), name="Q1")
+    assert quad.tracking_method == "linear" and quad.is_skippable
+    with pytest.warns(cb.PhysicsWarning):
+        quad.tracking_method = "nonsense"
+    assert quad.tracking_method == "linear"
+    quad.tracking_method = "drift_kick_drift"
+    assert not quad.is_skippable
+    segment = cb.Segment([quad, cb.Drift(length=torch.tensor(0.5), name="D1")], name="cell")
+    assert segment.Q1 is quad
+    assert torch.equal(segment.length, torch.tensor(1.5))
+    rbend = cb.RBend(length=torch.tensor(1.0), angle=torch.tensor(0.2), rbend_e1=torch.tensor(0.05))
+    assert torch.allclose(rbend.dipole_e1, torch.tensor(0.15))
+    assert torch.allclose(rbend.rbend_e1, torch.tensor(0.05))
+    dipole = cb.Dipole(length=torch.tensor(1.0), fringe_integral=torch.tensor(0.5))
+    assert torch.equal(dipole.fringe_integral_exit, torch.tensor(0.5))
+    with pytest.raises(AssertionError):
+        cb.CustomTransferMap(torch.ones(7, 7))
+    assert cb.Sextupole(length=torch.tensor(1.0)).tracking_method == "second_order"
+    beam = cb.ParticleBeam.from_twiss(num_particles=100, beta_x=3.14, beta_y=42.0)
+    assert beam.particles.shape == (100, 7) and bool((beam.particles[:, 6] == 1).all())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        segment.track(beam)
+
+
+def test_epoch_invalidation_on_attribute_assignment():
+    from cheetah_b200.elements import lattice_epoch
+
+    quad = cb.Quadrupole(length=torch.tensor(1.0))
+    before = lattice_epoch()
+    quad.k1 = torch.tensor(3.0)
+    assert lattice_epoch() > before
+    before = lattice_epoch()
+    quad.to(torch.float64)
+    assert lattice_epoch() > before and quad.k1.dtype == torch.float64

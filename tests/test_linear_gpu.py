@@ -1,0 +1,314 @@
+"""GPU parity of the linear path (ch_compose_maps + ch_apply_maps) through the public API.
+
+Tolerances (north_star: "within a stated fp32 tolerance, bit-exact for aperture masks"):
+  * float64 beams: the reference's own golden tolerance, torch.allclose rtol 1e-5 / atol 1e-8,
+    and 1e-12 relative to the column maximum against the float64 oracle;
+  * float32 beams: 2e-6 x column maximum against the float64 oracle (the reference's own
+    fp32-vs-fp64 distance on ARES is 5e-7);
+  * survival masks: exactly equal to the oracle's on identical inputs.
+"""
+
+import pytest
+import torch
+
+from oracle import track_oracle as oracle
+
+from . import golden_utils as gu
+from .test_oracle_golden import ARES, CONSISTENCY, LATTICES, ROW_STRIDE, ares_case
+
+pytestmark = pytest.mark.gpu
+DEVICE = "cuda"
+F32_TOL = 2e-6
+F64_TOL = 1e-12
+
+LINEAR_CASES = sorted(k for k in LATTICES if not k.startswith("SpaceChargeKick"))
+
+
+@pytest.mark.parametrize("case", LINEAR_CASES)
+def test_reference_consistency_pickles_f64(case):
+    """The reference's own golden pickles at the reference's own tolerance (float64)."""
+    incoming = gu.beam_dict(CONSISTENCY, "incoming")
+    segment = gu.product_segment(LATTICES[case], DEVICE, torch.float64)
+    out = segment.track(gu.product_beam(incoming, DEVICE, torch.float64))
+    rows = slice(None, None, ROW_STRIDE)
+    expected = gu.beam_dict(CONSISTENCY, f"{case}.expected")
+    assert torch.allclose(out.particles.cpu()[..., rows, :], expected["particles"])
+    assert torch.allclose(
+        out.survival_probabilities.cpu()[..., rows], expected["survival_probabilities"]
+    )
+    assert torch.allclose(out.s.cpu(), expected["s"])
+    assert torch.allclose(out.energy.cpu(), expected["energy"])
+    assert out.particles.shape[:-2] == expected["particles"].shape[:-2]
+
+
+@pytest.mark.parametrize("case", LINEAR_CASES)
+def test_reference_consistency_pickles_f32(case):
+    incoming = gu.beam_dict(CONSISTENCY, "incoming")
+    lattice = [dict(d) for d in LATTICES[case]]
+    segment = gu.product_segment(lattice, DEVICE, torch.float32)
+    out = segment.track(gu.product_beam(incoming, DEVICE, torch.float32))
+    # oracle in float64 on the SAME float32-rounded inputs
+    from oracle import lattice_io
+
+    lattice32 = lattice_io.cast(lattice_io.cast(LATTICES[case], torch.float32), torch.float64)
+    beam32 = {
+        k: v.to(torch.float32).to(torch.float64) for k, v in incoming.items()
+    }
+    expected = oracle.track(lattice32, beam32)
+    assert gu.column_scaled_error(out.particles, expected["particles"]) < F32_TOL
+    assert torch.equal(
+        out.survival_probabilities.cpu().double(), expected["survival_probabilities"]
+    )
+
+
+@pytest.mark.parametrize("case", LINEAR_CASES)
+def test_parameter_beam_goldens_f64(case):
+    import cheetah_b200 as cb
+
+    if f"{case}.expected.mu" not in CONSISTENCY:
+        pytest.skip("no ParameterBeam pickle")
+    incoming = gu.beam_dict(CONSISTENCY, "incoming")
+    segment = gu.product_segment(LATTICES[case], DEVICE, torch.float64)
+    beam = cb.ParameterBeam(
+        mu=gu.tensor(CONSISTENCY["incoming.mu"]).to(DEVICE),
+        cov=gu.tensor(CONSISTENCY["incoming.cov"]).to(DEVICE),
+        energy=incoming["energy"].to(DEVICE),
+        total_charge=gu.tensor(CONSISTENCY["incoming.total_charge"]).to(DEVICE),
+        species=cb.Species(
+            "custom",
+            num_elementary_charges=incoming["num_elementary_charges"].to(DEVICE),
+            mass_eV=incoming["mass_eV"].to(DEVICE),
+        ),
+    )
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = segment.track(beam)
+    assert torch.allclose(out.mu.cpu(), gu.tensor(CONSISTENCY[f"{case}.expected.mu"]))
+    assert torch.allclose(out.cov.cpu(), gu.tensor(CONSISTENCY[f"{case}.expected.cov"]))
+
+
+@pytest.mark.parametrize("case", ["default", "config2", "vectorised"])
+@pytest.mark.parametrize("tag,dtype", [("f64", torch.float64), ("f32", torch.float32)])
+def test_ares_against_reference_outputs(case, tag, dtype):
+    """ARES (195 elements) against outputs of the unmodified reference (tests/golden/ares.npz)."""
+    lattice, beam = ares_case(case, dtype)
+    segment = gu.product_segment(lattice, DEVICE, dtype)
+    out = segment.track(gu.product_beam(beam, DEVICE, dtype))
+    rows = slice(None, None, 4)
+    expected = gu.beam_dict(ARES, f"{case}.{tag}", dtype)
+    # against the reference run in the same dtype: both carry their own rounding
+    tol = 1e-11 if dtype == torch.float64 else 4e-6
+    assert gu.column_scaled_error(out.particles[..., rows, :], expected["particles"]) < tol
+    # against the float64 reference: our float32 path must be at the reference's own noise floor
+    truth = gu.beam_dict(ARES, f"{case}.f64", torch.float64)
+    assert gu.column_scaled_error(out.particles[..., rows, :], truth["particles"]) < (
+        F64_TOL * 10 if dtype == torch.float64 else F32_TOL
+    )
+    flips = (
+        out.survival_probabilities.cpu().double()[..., rows] != truth["survival_probabilities"]
+    ).sum()
+    assert flips == 0, f"{int(flips)} survival mask mismatches against the float64 reference"
+    assert torch.allclose(out.s.cpu().double(), truth["s"], rtol=1e-6)
+    assert out.particles.shape[:-2] == expected["particles"].shape[:-2]
+    assert out.survival_probabilities.shape == (
+        *expected["survival_probabilities"].shape[:-1],
+        beam["particles"].shape[-2],
+    )
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", ["rectangular", "elliptical"])
+@pytest.mark.parametrize("n", [1000, 1001, 4099])
+def test_aperture_masks_bit_exact(dtype, shape, n):
+    """Aperture in isolation on identical inputs: masks equal the oracle's exactly, including
+    particles placed on and one ulp around the edge."""
+    import cheetah_b200 as cb
+
+    g = torch.Generator().manual_seed(n)
+    particles = torch.randn(3, n, 7, generator=g, dtype=torch.float64) * 1e-3
+    particles[..., 6] = 1.0
+    x_max = torch.tensor([[1e-3], [5e-4]], dtype=dtype)
+    y_max = torch.tensor(8e-4, dtype=dtype)
+    particles = particles.to(dtype)
+    # edge cases: exactly on the edge and the neighbouring representable values
+    edge = x_max[1, 0]
+    particles[0, 0, 0] = edge
+    particles[0, 1, 0] = torch.nextafter(edge, torch.tensor(0.0, dtype=dtype))
+    particles[0, 2, 0] = torch.nextafter(edge, torch.tensor(1.0, dtype=dtype))
+    particles[0, 3, 0] = -edge
+    particles[0, :4, 2] = 0.0
+    particles[1, 0, 2] = y_max
+    particles[1, 0, 0] = 0.0
+    survival = torch.rand(n, generator=g, dtype=torch.float64).to(dtype)
+
+    beam = oracle.make_beam(particles, torch.tensor(1e8, dtype=dtype), survival_probabilities=survival)
+    expected = oracle.track_aperture(
+        {"type": "Aperture", "x_max": x_max, "y_max": y_max, "shape": shape}, beam
+    )
+    aperture = cb.Aperture(x_max=x_max.to(DEVICE), y_max=y_max.to(DEVICE), shape=shape)
+    out = aperture.track(gu.product_beam(beam, DEVICE, dtype))
+    assert out.survival_probabilities.shape == expected["survival_probabilities"].shape
+    assert torch.equal(out.survival_probabilities.cpu(), expected["survival_probabilities"])
+    # particles pass through an aperture unchanged, bit for bit
+    assert torch.equal(out.particles.cpu(), particles.expand(2, 3, n, 7))
+
+
+ELEMENT_CASES = {
+    "Drift": {"length": [1.0, -1.0]},
+    "Quadrupole": {"length": 0.7, "k1": [1.0, -2.0, 0.0], "tilt": 0.42, "misalignment": (0.01, -0.02)},
+    "Dipole": {
+        "length": 1.0, "angle": [1.0, -2.0], "k1": 0.3, "dipole_e1": 0.1, "dipole_e2": -0.2,
+        "tilt": 0.42, "gap": 0.03, "fringe_integral": 0.5, "fringe_integral_exit": 0.4,
+    },
+    "RBend": {"length": 1.0, "angle": [1.0, -2.0, 0.0], "rbend_e1": 0.05, "tilt": 0.1},
+    "HorizontalCorrector": {"length": 0.2, "angle": [1e-3, -2e-3]},
+    "VerticalCorrector": {"length": 0.2, "angle": [1e-3, -2e-3]},
+    "CombinedCorrector": {"length": 0.2, "horizontal_angle": [1e-3, -2e-3], "vertical_angle": 5e-4},
+    "Solenoid": {"length": 0.5, "k": [1.0, -2.0, 0.0], "misalignment": (0.01, -0.02)},
+    "Undulator": {"length": 1.0, "period": 0.1, "kx": 1.3, "ky": 0.4},
+    "Cavity": {"length": 1.3},
+    "Sextupole": {"length": 0.3, "k2": 2.0, "tracking_method": "linear"},
+    "Marker": {},
+}
+
+
+@pytest.mark.parametrize("kind", sorted(ELEMENT_CASES))
+@pytest.mark.parametrize("energy", [1e8, [6e6, 2.5e8]])
+def test_first_order_transfer_map_matches_oracle(kind, energy):
+    import cheetah_b200 as cb
+
+    dtype = torch.float64
+    kwargs = {
+        k: (v if isinstance(v, str) else torch.tensor(v, dtype=dtype)) for k, v in ELEMENT_CASES[kind].items()
+    }
+    energy_t = torch.tensor(energy, dtype=dtype)
+    if energy_t.dim() == 1:  # make the energy dimension broadcast against the parameter dimension
+        energy_t = energy_t.unsqueeze(-1)
+    description = {"type": kind, **kwargs}
+    expected = oracle.first_order_map(
+        description, energy_t, torch.tensor(oracle.ELECTRON_MASS_EV, dtype=dtype), torch.tensor(-1.0, dtype=dtype)
+    )
+    element = getattr(cb, kind)(
+        **{k: (v.to(DEVICE) if isinstance(v, torch.Tensor) else v) for k, v in kwargs.items()}
+    )
+    species = cb.Species("electron", device=DEVICE, dtype=dtype)
+    tm = element.first_order_transfer_map(energy_t.to(DEVICE), species)
+    expected = expected.expand(tm.shape)
+    assert tm.shape[-2:] == (7, 7)
+    assert torch.allclose(tm.cpu(), expected, rtol=1e-11, atol=1e-13), (tm.cpu() - expected).abs().max()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_segment_of_every_linear_element_and_odd_sizes(dtype):
+    """A lattice with every linear element type, tilted/misaligned magnets, two apertures, a
+    particle count that is not a multiple of 4 (non-TMA path) and a non-unit 7th column."""
+    import cheetah_b200 as cb
+
+    g = torch.Generator().manual_seed(7)
+    lattice = []
+    for kind, params in ELEMENT_CASES.items():
+        entry = {"type": kind, "name": kind}
+        for k, v in params.items():
+            if isinstance(v, str):
+                entry[k] = v
+            else:
+                t = torch.tensor(v, dtype=torch.float64)
+                entry[k] = t if t.dim() == 0 or k == "misalignment" else t[0]
+        lattice.append(entry)
+    lattice.insert(4, {"type": "Aperture", "name": "a1", "x_max": torch.tensor(2e-3), "y_max": torch.tensor(3e-3), "shape": "rectangular", "is_active": True})
+    lattice.append({"type": "Aperture", "name": "a2", "x_max": torch.tensor(0.9), "y_max": torch.tensor(0.8), "shape": "elliptical", "is_active": True})
+    lattice.append({"type": "Drift", "name": "tail", "length": torch.tensor(0.25)})
+    from oracle import lattice_io
+
+    lattice = lattice_io.cast(lattice, dtype)
+    for n, unit in ((1003, True), (2048, False), (5, True)):
+        particles = torch.randn(n, 7, generator=g, dtype=torch.float64) * 1e-3
+        particles[:, 6] = 1.0 if unit else 0.5
+        beam = oracle.make_beam(particles.to(dtype), torch.tensor(8e7, dtype=dtype))
+        truth_lattice = lattice_io.cast(lattice, torch.float64)
+        truth_beam = {k: v.to(torch.float64) for k, v in beam.items()}
+        expected = oracle.track(truth_lattice, truth_beam)
+        out = gu.product_segment(lattice, DEVICE, dtype).track(gu.product_beam(beam, DEVICE, dtype))
+        tol = F32_TOL if dtype == torch.float32 else F64_TOL
+        assert gu.column_scaled_error(out.particles, expected["particles"]) < tol
+        assert torch.equal(out.particles[..., 6].cpu().double(), expected["particles"][..., 6])
+        mismatches = (out.survival_probabilities.cpu().double() != expected["survival_probabilities"]).sum()
+        assert mismatches == 0
+        assert torch.allclose(out.s.cpu().double(), expected["s"], rtol=1e-6)
+
+
+def test_broadcast_shapes_follow_the_reference():
+    """Vector dims: particles (2,1,N,7) x quad k1 (3,) -> (2,3,N,7); survival only widens up to
+    the last aperture; `s` only carries the length dims (tests/test_vectorized.py:339-371)."""
+    import cheetah_b200 as cb
+
+    dtype = torch.float32
+    n = 512
+    g = torch.Generator().manual_seed(11)
+    particles = torch.randn(2, 1, n, 7, generator=g, dtype=torch.float64) * 1e-3
+    particles[..., 6] = 1.0
+    lattice = [
+        {"type": "Drift", "name": "d0", "length": torch.tensor(0.5)},
+        {"type": "Aperture", "name": "ap", "x_max": torch.tensor(1e-3), "y_max": torch.tensor(1e-3), "shape": "rectangular", "is_active": True},
+        {"type": "Quadrupole", "name": "q", "length": torch.tensor(0.2), "k1": torch.tensor([4.0, -3.0, 0.5]), "misalignment": torch.zeros(2), "tilt": torch.tensor(0.0)},
+        {"type": "Drift", "name": "d1", "length": torch.tensor([1.0, 2.0, 3.0])},
+    ]
+    beam = oracle.make_beam(particles.to(dtype), torch.tensor(1e8, dtype=dtype))
+    from oracle import lattice_io
+
+    expected = oracle.track(lattice_io.cast(lattice, torch.float64), {k: v.double() for k, v in beam.items()})
+    out = gu.product_segment(lattice_io.cast(lattice, dtype), DEVICE, dtype).track(gu.product_beam(beam, DEVICE, dtype))
+    assert out.particles.shape == expected["particles"].shape == (2, 3, n, 7)
+    assert out.survival_probabilities.shape == expected["survival_probabilities"].shape == (2, 1, n)
+    assert out.s.shape == expected["s"].shape == (3,)
+    assert gu.column_scaled_error(out.particles, expected["particles"]) < F32_TOL
+    assert torch.equal(out.survival_probabilities.cpu().double(), expected["survival_probabilities"])
+
+
+def test_input_beam_is_not_mutated_and_outputs_are_new():
+    import cheetah_b200 as cb
+
+    beam = cb.ParticleBeam.from_parameters(num_particles=4096, device=DEVICE, dtype=torch.float32)
+    before = beam.particles.clone()
+    segment = cb.Segment([cb.Drift(length=torch.tensor(1.0, device=DEVICE))])
+    out = segment.track(beam)
+    assert torch.equal(beam.particles, before)
+    assert out.particles.data_ptr() != beam.particles.data_ptr()
+    assert out.survival_probabilities is beam.survival_probabilities  # passed through (element.py:186-188)
+    assert out.particle_charges is beam.particle_charges
+    assert out.species is not beam.species and out.species.name == beam.species.name
+
+
+def test_in_place_setting_updates_are_seen_without_relowering():
+    import cheetah_b200 as cb
+
+    quad = cb.Quadrupole(length=torch.tensor(0.2, device=DEVICE), k1=torch.tensor(1.0, device=DEVICE))
+    segment = cb.Segment([quad, cb.Drift(length=torch.tensor(1.0, device=DEVICE))])
+    beam = cb.ParticleBeam.from_parameters(num_particles=1024, device=DEVICE, dtype=torch.float32)
+    a = segment.track(beam).particles.clone()
+    quad.k1.fill_(-3.0)  # in place: same storage, program keeps pointing at it
+    b = segment.track(beam).particles.clone()
+    quad.k1 = torch.tensor(-3.0, device=DEVICE)  # re-assignment: new tensor -> re-lowered
+    c = segment.track(beam).particles
+    assert not torch.equal(a, b)
+    assert torch.equal(b, c)
+
+
+def test_errors_are_loud():
+    import cheetah_b200 as cb
+
+    beam = cb.ParticleBeam.from_parameters(num_particles=16, dtype=torch.float32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cb.Drift(length=torch.tensor(1.0)).track(beam)
+    with pytest.raises(NotImplementedError, match="outside the accelerated hot path"):
+        cb.Drift(length=torch.tensor(1.0, device=DEVICE), tracking_method="drift_kick_drift").track(
+            cb.ParticleBeam.from_parameters(num_particles=16, device=DEVICE, dtype=torch.float32)
+        )
+    with pytest.raises(ValueError, match="move the lattice"):
+        cb.Drift(length=torch.tensor(1.0)).track(
+            cb.ParticleBeam.from_parameters(num_particles=16, device=DEVICE, dtype=torch.float32)
+        )
+    with pytest.raises(TypeError):
+        cb.Drift(length=torch.tensor(1.0, device=DEVICE)).track("not a beam")
