@@ -18,6 +18,11 @@ from . import _capi, lowering
 from .beam import ParameterBeam, ParticleBeam
 
 
+# When set to a list, every ch_apply_maps launch appends a (start, stop) CUDA-event pair
+# recorded on the launching stream (bench.py uses it for the roofline line).
+apply_events: list | None = None
+
+
 def _is_particle_beam(beam) -> bool:
     return type(beam).__name__ == "ParticleBeam"
 
@@ -174,6 +179,10 @@ def _track_linear_section(program, section, beam):
         survival_index = _index_table(vs, vo, device)
         survival_out = torch.empty((*vo, n), dtype=dtype, device=device)
 
+    events = None
+    if apply_events is not None:
+        events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        events[0].record(torch.cuda.current_stream(device))
     with torch.cuda.device(device):
         _capi.check(
             _capi.lib().ch_apply_maps(
@@ -189,6 +198,9 @@ def _track_linear_section(program, section, beam):
                 _capi.current_stream(device),
             )
         )
+    if events is not None:
+        events[1].record(torch.cuda.current_stream(device))
+        apply_events.append(events)
 
     if survival_out is not None:
         # reference shape: broadcast(survival_in, particles vector dims, everything up to and

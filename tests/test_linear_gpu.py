@@ -98,8 +98,10 @@ def test_ares_against_reference_outputs(case, tag, dtype):
     out = segment.track(gu.product_beam(beam, DEVICE, dtype))
     rows = slice(None, None, 4)
     expected = gu.beam_dict(ARES, f"{case}.{tag}", dtype)
-    # against the reference run in the same dtype: both carry their own rounding
-    tol = 1e-11 if dtype == torch.float64 else 4e-6
+    # against the reference run in the same dtype: both carry their own rounding (the
+    # reference's fp32 chain of 7x7 products is the noisier side: our fp32 result is ~1e-7
+    # from the fp64 truth, the reference's fp32 up to ~7e-6 on the vectorised case)
+    tol = 1e-11 if dtype == torch.float64 else 2e-5
     assert gu.column_scaled_error(out.particles[..., rows, :], expected["particles"]) < tol
     # against the float64 reference: our float32 path must be at the reference's own noise floor
     truth = gu.beam_dict(ARES, f"{case}.f64", torch.float64)

@@ -1,0 +1,110 @@
+"""Synthetic workloads of BASELINE.json / SURVEY.md 8(d), shared by bench.py, tools/ and tests.
+
+The ARES lattice comes from ``tests/golden/ares_lattice.json`` (the reference's
+``docs/examples/ARESlatticeStage3v1_9.json`` converted by ``oracle/make_golden.py``: 195
+elements).  A workload is returned as a plain-dict lattice description (``oracle/lattice_io``
+format) plus beam parameters, and can be instantiated either as ``cheetah_b200`` objects on a
+CUDA device (the product) or kept as dicts for the CPU oracle (the baseline).
+
+Config 3 recipe (frozen; SURVEY.md 8d asks to tune the ranges once so that the mean survival
+over the settings is 30-70 %): generator seed 1; the 13 quadrupoles' k1 ~ U(-5, 5) 1/m^2 and
+the 30 correctors' angle ~ U(-2e-5, 2e-5) rad, drawn element by element in lattice order;
+apertures ARLISLHG1 and ARBCSLHB1 rectangular with x_max = y_max = 2 mm.  With the
+``from_twiss`` beam (beta_x 3.14 m, beta_y 42 m, 1e8 eV) the mean survival is 42 %.  (The
+U(-30, 30) / U(-1e-3, 1e-3) ranges first suggested by the survey lose every particle.)
+"""
+
+from __future__ import annotations
+
+from pathlib import Path
+
+import torch
+
+from oracle import lattice_io
+
+GOLDEN = Path(__file__).resolve().parent / "tests" / "golden"
+N_ELEMENTS_ARES = 195
+
+CONFIG2_SETTINGS = {  # reference README.md:73-77
+    "AREAMQZM1": ("k1", 8.2),
+    "AREAMQZM2": ("k1", -14.3),
+    "AREAMCVM1": ("angle", 9e-5),
+    "AREAMQZM3": ("k1", 3.142),
+    "AREAMCHM1": ("angle", -1e-4),
+}
+
+
+def _set(description: list, name: str, attr: str, value) -> None:
+    for element in description:
+        if element["name"] == name:
+            element[attr] = value
+            return
+    raise KeyError(name)
+
+
+def ares_config2(dtype=torch.float32) -> list:
+    """ARES, single setting, five EA magnets powered (BASELINE configs[1])."""
+    lattice = lattice_io.load(GOLDEN / "ares_lattice.json", dtype)
+    for name, (attr, value) in CONFIG2_SETTINGS.items():
+        _set(lattice, name, attr, torch.tensor(value, dtype=dtype))
+    return lattice
+
+
+def ares_config3(n_settings: int, dtype=torch.float32, begin: int = 0, end: int | None = None) -> list:
+    """ARES with ``n_settings`` vectorised magnet settings (BASELINE configs[2]).
+
+    ``[begin, end)`` selects a contiguous shard of the settings (multi-GPU / CPU samples): the
+    random draw is always made for the full batch so that shards of different world sizes see
+    the same settings.
+    """
+    end = n_settings if end is None else end
+    lattice = lattice_io.load(GOLDEN / "ares_lattice.json", dtype)
+    g = torch.Generator().manual_seed(1)
+    for element in lattice:
+        if element["type"] == "Quadrupole":
+            full = (torch.rand(n_settings, generator=g) * 2 - 1) * 5.0
+            element["k1"] = full[begin:end].to(dtype).contiguous()
+        elif element["type"] in ("HorizontalCorrector", "VerticalCorrector"):
+            full = (torch.rand(n_settings, generator=g) * 2 - 1) * 2e-5
+            element["angle"] = full[begin:end].to(dtype).contiguous()
+    for name in ("ARLISLHG1", "ARBCSLHB1"):
+        _set(lattice, name, "x_max", torch.tensor(2e-3, dtype=dtype))
+        _set(lattice, name, "y_max", torch.tensor(2e-3, dtype=dtype))
+    return lattice
+
+
+def twiss_beam_particles(num_particles: int, seed: int = 0) -> torch.Tensor:
+    """(N, 7) float64 particles of the README beam (beta_x 3.14, beta_y 42, defaults of
+    particle_beam.py:464-504), generated on the CPU so that every rank and the CPU baseline
+    see identical inputs."""
+    import cheetah_b200 as cb
+
+    beam = cb.ParticleBeam.from_twiss(
+        num_particles=num_particles, beta_x=3.14, beta_y=42.0, dtype=torch.float64,
+        generator=torch.Generator().manual_seed(seed),
+    )
+    return beam.particles
+
+
+def product_segment(description: list, device, dtype):
+    import cheetah_b200 as cb
+
+    return cb.Segment(elements=lattice_io.build(description, cb, device=device, dtype=dtype))
+
+
+def product_beam(particles: torch.Tensor, device, dtype, energy: float = 1e8):
+    import cheetah_b200 as cb
+
+    beam = cb.ParticleBeam(
+        particles=particles.to(device=device, dtype=dtype),
+        energy=torch.tensor(energy, device=device, dtype=dtype),
+        species=cb.Species("electron", device=device, dtype=dtype),
+    )
+    beam._unit_seventh = True
+    return beam
+
+
+def oracle_beam(particles: torch.Tensor, dtype, energy: float = 1e8) -> dict:
+    from oracle import track_oracle as oracle
+
+    return oracle.make_beam(particles.to(dtype), torch.tensor(energy, dtype=dtype))
