@@ -97,6 +97,75 @@ __device__ __forceinline__ T affine_row(const T* c, const T (&p)[7]) {
   return acc;
 }
 
+
+__device__ __forceinline__ uint32_t record_flags(float header) { return __float_as_uint(header); }
+__device__ __forceinline__ uint32_t record_flags(double header) {
+  return static_cast<uint32_t>(__double_as_longlong(header));
+}
+
+// |v| < bound  <=>  -bound < v < bound for bound >= 0 (NaNs compare false either way)
+__device__ __forceinline__ bool inside(float v, float bound) { return fabsf(v) < bound; }
+__device__ __forceinline__ bool inside(double v, double bound) { return fabs(v) < bound; }
+
+// One lattice setting for this thread's P particles: survival masks at every aperture, then
+// the final map into the staging tile.  SPARSE drops the structurally-zero terms (flags).
+template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE>
+__device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
+                                                uint32_t elliptical_mask, const T (&p)[P][7],
+                                                T (&sv)[P], T* stage, int tid) {
+  for (int ap = 0; ap < n_apertures; ++ap) {
+    T q[16];
+    load_coefficients(q, rec + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
+    const T x_max = q[14], y_max = q[15];
+    const bool elliptical = (elliptical_mask >> ap) & 1u;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      T x, y;
+      if constexpr (SPARSE) {
+        const T w = UNIT7 ? T(1) : p[k][6];
+        x = fma_t(q[0], p[k][0], fma_t(q[1], p[k][1], fma_t(q[5], p[k][5], UNIT7 ? q[6] : q[6] * w)));
+        y = fma_t(q[9], p[k][2], fma_t(q[10], p[k][3], UNIT7 ? q[13] : q[13] * w));
+      } else {
+        x = affine_row<T, UNIT7>(q, p[k]);
+        y = affine_row<T, UNIT7>(q + 7, p[k]);
+      }
+      bool keep;
+      if (elliptical) {
+        const T ex = div_rn(mul_rn(x, x), mul_rn(x_max, x_max));
+        const T ey = div_rn(mul_rn(y, y), mul_rn(y_max, y_max));
+        keep = add_rn(ex, ey) <= T(1);
+      } else {
+        keep = inside(x, x_max) && inside(y, y_max);
+      }
+      // survival * mask with mask in {0, 1}: exact for every finite survival probability
+      sv[k] = keep ? sv[k] : T(0);
+    }
+  }
+
+  T c[44];
+  load_coefficients(c, rec);
+  const T* m = c + CH_RECORD_HEADER;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    T* row = stage + (tid + k * THREADS) * 7;
+    if constexpr (SPARSE) {
+      const T w = UNIT7 ? T(1) : p[k][6];
+      auto constant = [&](int i) { return UNIT7 ? m[i * 7 + 6] : m[i * 7 + 6] * w; };
+      row[0] = fma_t(m[0], p[k][0], fma_t(m[1], p[k][1], fma_t(m[5], p[k][5], constant(0))));
+      row[1] = fma_t(m[7], p[k][0], fma_t(m[8], p[k][1], fma_t(m[12], p[k][5], constant(1))));
+      row[2] = fma_t(m[16], p[k][2], fma_t(m[17], p[k][3], constant(2)));
+      row[3] = fma_t(m[23], p[k][2], fma_t(m[24], p[k][3], constant(3)));
+      row[4] = fma_t(m[28], p[k][0],
+                     fma_t(m[29], p[k][1], fma_t(m[32], p[k][4], fma_t(m[33], p[k][5], constant(4)))));
+      row[5] = p[k][5];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) row[i] = affine_row<T, UNIT7>(m + i * 7, p[k]);
+    }
+    row[6] = UNIT7 ? T(1) : p[k][6];
+  }
+}
+
 template <typename T, int P, int THREADS, bool UNIT7>
 __global__ void __launch_bounds__(THREADS)
 apply_maps_kernel(const ApplyArgs<T> a) {
@@ -196,45 +265,22 @@ apply_maps_kernel(const ApplyArgs<T> a) {
     // ---- prefetch the next setting's record (visible after the next barrier) ----------
     if (b + 1 < b_end) copy_record(rec_next, b + 1);
 
-    // ---- apertures: x, y at each cut point from the cumulative rows ---------------------
+    // ---- apertures + final map -> staging tile -------------------------------------------
+    // The record's sparsity flags are uniform over the CTA: when the lattice has no x-y
+    // coupling, no tau dependence, no vertical dispersion and leaves delta untouched (every
+    // uncoupled, cavity-off lattice such as ARES) 29 of the 72 multiply-adds remain.
     T sv[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) sv[k] = sv_in[k];
-    for (int ap = 0; ap < a.n_apertures; ++ap) {
-      T q[16];
-      load_coefficients(q, rec + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
-      const T x_max = q[14], y_max = q[15];
-      const bool elliptical = (a.elliptical_mask >> ap) & 1u;
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const T x = affine_row<T, UNIT7>(q, p[k]);
-        const T y = affine_row<T, UNIT7>(q + 7, p[k]);
-        bool keep;
-        if (elliptical) {
-          const T ex = div_rn(mul_rn(x, x), mul_rn(x_max, x_max));
-          const T ey = div_rn(mul_rn(y, y), mul_rn(y_max, y_max));
-          keep = add_rn(ex, ey) <= T(1);
-        } else {
-          keep = (x > -x_max) && (x < x_max) && (y > -y_max) && (y < y_max);
-        }
-        sv[k] = mul_rn(sv[k], keep ? T(1) : T(0));
-      }
-    }
-
-    // ---- final map -> staging tile ----------------------------------------------------
-    {
-      T c[44];
-      load_coefficients(c, rec);
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const int local = tid + k * THREADS;
-        T* row = stage + local * 7;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-          row[i] = affine_row<T, UNIT7>(c + CH_RECORD_HEADER + i * 7, p[k]);
-        row[6] = UNIT7 ? T(1) : p[k][6];
-      }
-    }
+    const uint32_t flags = record_flags(rec[0]);
+    constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
+                                 CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
+    if ((flags & kSparse) == kSparse)
+      process_setting<T, P, THREADS, UNIT7, true>(rec, a.n_apertures, a.elliptical_mask, p, sv,
+                                                  stage, tid);
+    else
+      process_setting<T, P, THREADS, UNIT7, false>(rec, a.n_apertures, a.elliptical_mask, p, sv,
+                                                   stage, tid);
     if (a.survival_out != nullptr) {
       T* dst = a.survival_out + b * a.n_particles + n0;
 #pragma unroll

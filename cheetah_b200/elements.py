@@ -151,6 +151,10 @@ def _element_init(cls_fields: Iterable[str]):
             if key not in fields:
                 raise TypeError(f"{type(self).__name__} got an unexpected keyword argument {key!r}")
             given[key] = value
+        if device is None:  # defaults follow the tensors that were given
+            device = next(
+                (v.device for v in given.values() if isinstance(v, torch.Tensor)), None
+            )
         Element.__init__(self, name=name, sanitize_name=sanitize_name, metadata=metadata,
                          device=device, dtype=dtype)
         self._register_fields(given, {"device": device, "dtype": dtype})
@@ -256,6 +260,8 @@ class RBend(Dipole):
                  gap=None, gap_exit=None, fringe_integral=None, fringe_integral_exit=None,
                  fringe_at="both", fringe_type="linear_edge", tracking_method="linear",
                  name=None, sanitize_name=None, metadata=None, device=None, dtype=None):
+        if device is None:
+            device = length.device
         factory_kwargs = {"device": device, "dtype": dtype}
         angle = angle if angle is not None else torch.tensor(0.0, **factory_kwargs)
         rbend_e1 = rbend_e1 if rbend_e1 is not None else torch.tensor(0.0, **factory_kwargs)

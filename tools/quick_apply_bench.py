@@ -33,7 +33,8 @@ def build(batch, n, dtype=torch.float32, device="cuda"):
 
 def main():
     n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
-    for batch in [1, 16, 256] + ([int(sys.argv[2])] if len(sys.argv) > 2 else []):
+    batches = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 16, 256]
+    for batch in batches:
         segment, beam = build(batch, n)
         for _ in range(3):
             out = segment.track(beam)
