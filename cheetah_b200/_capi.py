@@ -74,7 +74,67 @@ SIGNATURES = {
             c_int32, c_int32, c_void_p,
         ],
     ),
+    "ch_sc_beam_moments": (
+        c_int32,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p],
+    ),
+    "ch_sc_grid_params": (
+        c_int32,
+        [
+            c_void_p, c_int64,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int32,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p,
+        ],
+    ),
+    "ch_sc_deposit": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+            c_void_p, c_int64, c_int64,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p,
+        ],
+    ),
+    "ch_cic_deposit3d": (
+        c_int32,
+        [
+            c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p,
+        ],
+    ),
+    "ch_sc_green_function": (
+        c_int32,
+        [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
+    ),
+    "ch_sc_poisson_solve": (
+        c_int32,
+        [
+            c_void_p, c_void_p, c_void_p, c_int64,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p, c_void_p, c_void_p,
+        ],
+    ),
+    "ch_sc_field": (
+        c_int32,
+        [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p],
+    ),
+    "ch_sc_gather_kick": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p, c_void_p,
+        ],
+    ),
 }
+
+SC_STATS = 12
+SC_PARAMS = 16
 
 _lib = None
 

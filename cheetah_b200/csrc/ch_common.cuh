@@ -126,6 +126,42 @@ __device__ __forceinline__ void fence_async_shared() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- cooperative tile movers used by the particle-streaming kernels --------------------
+// Load `n_elems` contiguous elements into shared memory with the whole CTA.  With
+// `bulk` (16-byte aligned source and size) one elected thread issues a TMA bulk copy and
+// everybody waits on the mbarrier; otherwise plain coalesced loads.  On return every
+// thread may read the tile.  `bar` must have been initialised with count 1.
+template <typename T>
+__device__ __forceinline__ void cta_load_tile(T* smem_dst, const T* gmem_src, int n_elems,
+                                              bool bulk, uint64_t* bar, uint32_t& phase) {
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(n_elems) * sizeof(T);
+      mbar_expect_tx(bar, bytes);
+      bulk_load(smem_dst, gmem_src, bytes, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  } else {
+    for (int i = threadIdx.x; i < n_elems; i += blockDim.x) smem_dst[i] = gmem_src[i];
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__host__ __device__ inline bool bulk_compatible(const void* base, int64_t n_particles,
+                                                int64_t batch_stride_elems) {
+  return reinterpret_cast<uintptr_t>(base) % 16 == 0 &&
+         (static_cast<size_t>(n_particles) * 7 * sizeof(T)) % 16 == 0 &&
+         (static_cast<size_t>(batch_stride_elems) * sizeof(T)) % 16 == 0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 }  // namespace ch
 
 // opaque program object (device-resident copy of the lowered lattice)

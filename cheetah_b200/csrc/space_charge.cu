@@ -1,0 +1,922 @@
+// SpaceChargeKick kernel family: moments -> grid parameters -> cloud-in-cell deposit ->
+// integrated Green function -> FFT Poisson solve -> field -> gather + kick.
+//
+// Reference (desy-ml/cheetah @ 60d1053): cheetah/accelerator/space_charge_kick.py:103-586,
+// cheetah/utils/cloud_in_cell.py:244-384, cheetah/particles/particle_beam.py:1262-1346,
+// :1709-1805, cheetah/utils/statistics.py:30-62, cheetah/particles/beam.py:323-336.
+//
+// Everything is batched over B independent beams; per-beam scalars travel between the
+// kernels in small fp64 device tables (include/cheetah_b200.h) so nothing synchronises with
+// the host.  Particle passes read the 28-byte AoS rows through TMA-staged shared-memory
+// tiles; the charge histogram lives in L2 (a 64^3 fp32 grid is 1 MB) and is built with
+// fire-and-forget RED atomics (N/cells is ~4: privatising tiles would cost more than the
+// atomics they save); the 3-D convolution is three shared-memory FFT passes.
+#include "ch_common.cuh"
+#include "fft.cuh"
+
+namespace ch {
+namespace {
+
+constexpr double kSpeedOfLight = 299792458.0;
+constexpr double kElementaryCharge = 1.602176634e-19;
+constexpr double kEpsilon0 = 8.8541878188e-12;
+constexpr double kEvToKg = 1.7826619216278975e-36;
+constexpr double kPi = 3.14159265358979323846;
+
+// ---------------------------------------------------------------------------------------
+// 1. survival-weighted moments
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+sc_moments_kernel(const T* __restrict__ particles, int64_t particle_stride,
+                  const T* __restrict__ survival, int64_t survival_stride, int64_t n_particles,
+                  int per_cta, double* __restrict__ stats) {
+  const int64_t b = blockIdx.y;
+  const T* p = particles + b * particle_stride;
+  const T* w = survival ? survival + b * survival_stride : nullptr;
+  const double x0 = static_cast<double>(p[0]);
+  const double y0 = static_cast<double>(p[2]);
+  const double t0 = static_cast<double>(p[4]);
+  const int64_t begin = static_cast<int64_t>(blockIdx.x) * per_cta;
+  const int64_t end = min(n_particles, begin + per_cta);
+
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const double wi = w ? static_cast<double>(w[i]) : 1.0;
+    const double dx = static_cast<double>(p[i * 7 + 0]) - x0;
+    const double dy = static_cast<double>(p[i * 7 + 2]) - y0;
+    const double dt = static_cast<double>(p[i * 7 + 4]) - t0;
+    acc[0] += wi;
+    acc[1] = fma(wi, wi, acc[1]);
+    acc[2] = fma(wi, dx, acc[2]);
+    acc[3] = fma(wi, dy, acc[3]);
+    acc[4] = fma(wi, dt, acc[4]);
+    acc[5] = fma(wi * dx, dx, acc[5]);
+    acc[6] = fma(wi * dy, dy, acc[6]);
+    acc[7] = fma(wi * dt, dt, acc[7]);
+  }
+  __shared__ double partial[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (lane == 0) partial[warp][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (int wi = 0; wi < 8; ++wi) s += partial[wi][threadIdx.x];
+    atomicAdd(&stats[b * CH_SC_STATS + threadIdx.x], s);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    stats[b * CH_SC_STATS + 8] = x0;
+    stats[b * CH_SC_STATS + 9] = y0;
+    stats[b * CH_SC_STATS + 10] = t0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 2. per-beam grid parameters
+// ---------------------------------------------------------------------------------------
+struct GridInputs {
+  ScalarRef energy, mass, length, extent_x, extent_y, extent_tau;
+};
+
+template <typename T>
+__global__ void sc_grid_params_kernel(const double* __restrict__ stats, int64_t n_beams,
+                                      GridInputs in, int nx, int ny, int nz,
+                                      double* __restrict__ params) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= n_beams) return;
+  const double* s = stats + b * CH_SC_STATS;
+  double* out = params + b * CH_SC_PARAMS;
+  const double sum_w = s[0];
+  const double correction = sum_w - s[1] / sum_w;  // statistics.py:44
+  const double extent[3] = {load_scalar(in.extent_x.ptr, b * in.extent_x.stride, in.extent_x.dtype),
+                            load_scalar(in.extent_y.ptr, b * in.extent_y.stride, in.extent_y.dtype),
+                            load_scalar(in.extent_tau.ptr, b * in.extent_tau.stride,
+                                        in.extent_tau.dtype)};
+  const int n[3] = {nx, ny, nz};
+  double volume = 1.0;
+  for (int d = 0; d < 3; ++d) {
+    // sum w (u - mean)^2 = S2 - S1^2 / S0 about the pilot
+    const double centred = s[5 + d] - s[2 + d] * s[2 + d] / sum_w;
+    // the reference carries sigma, grid_dimensions and cell_size in the beam dtype
+    const T sigma = static_cast<T>(sqrt(fmax(centred, 0.0) / correction));
+    const T half_extent = static_cast<T>(extent[d]) * sigma;
+    const T cell = T(2) * half_extent / static_cast<T>(n[d]);
+    out[d] = static_cast<double>(half_extent);
+    out[3 + d] = static_cast<double>(cell);
+    out[11 + d] = static_cast<double>(sigma);
+    volume *= static_cast<double>(cell);
+  }
+  const double mass = load_scalar(in.mass.ptr, 0, in.mass.dtype);
+  const double gamma = load_scalar(in.energy.ptr, b * in.energy.stride, in.energy.dtype) / mass;
+  const double beta = (fabs(gamma) > 0.0 && gamma > 0.0) ? sqrt(1.0 - 1.0 / (gamma * gamma)) : 1.0;
+  const double length = load_scalar(in.length.ptr, b * in.length.stride, in.length.dtype);
+  out[6] = gamma;
+  out[7] = beta;
+  out[8] = length / (kSpeedOfLight * beta);
+  out[9] = 1.0 / volume;
+  out[10] = gamma != 0.0 ? 1.0 / (gamma * gamma) : 0.0;
+  out[14] = sum_w;
+  out[15] = mass;
+}
+
+// ---------------------------------------------------------------------------------------
+// 3. cloud-in-cell deposit
+// ---------------------------------------------------------------------------------------
+// One axis of cloud_in_cell.py:275-362, in the beam dtype like the reference.
+template <typename T>
+struct AxisDeposit {
+  int lo, hi;      // clamped corner indices
+  T w_lo, w_hi;    // corner weights (0 when the corner is off-grid)
+  bool inside;     // inclusive extent test
+};
+
+template <typename T>
+__device__ __forceinline__ AxisDeposit<T> deposit_axis(T pos, T left, T right, int bins) {
+  AxisDeposit<T> a;
+  a.inside = (pos >= left) && (pos <= right);
+  const T width = (right - left) / static_cast<T>(bins);
+  const T q = (pos - left) / width - T(0.5);
+  const T fl = floor(q);
+  const T frac = q - fl;
+  // clamp before the int conversion so that far-away particles cannot overflow
+  const T lim = static_cast<T>(bins + 1);
+  const int qi = static_cast<int>(fmin(fmax(fl, -lim), lim));
+  a.lo = min(max(qi, 0), bins - 1);
+  a.hi = min(max(qi + 1, 0), bins - 1);
+  a.w_lo = (qi >= 0 && qi < bins) ? T(1) - frac : T(0);
+  a.w_hi = (qi + 1 >= 0 && qi + 1 < bins) ? frac : T(0);
+  return a;
+}
+
+template <typename T>
+__device__ __forceinline__ void deposit_particle(T* __restrict__ grid, T x, T y, T z, T charge,
+                                                 const T* lo, const T* hi, int nx, int ny, int nz) {
+  const AxisDeposit<T> ax = deposit_axis(x, lo[0], hi[0], nx);
+  const AxisDeposit<T> ay = deposit_axis(y, lo[1], hi[1], ny);
+  const AxisDeposit<T> az = deposit_axis(z, lo[2], hi[2], nz);
+  if (!(ax.inside && ay.inside && az.inside)) return;  // masked_charges = charges * in_extent
+  const int ix[2] = {ax.lo, ax.hi}, iy[2] = {ay.lo, ay.hi}, iz[2] = {az.lo, az.hi};
+  const T wx[2] = {ax.w_lo, ax.w_hi}, wy[2] = {ay.w_lo, ay.w_hi}, wz[2] = {az.w_lo, az.w_hi};
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const T w = wx[a] * wy[b] * wz[c];
+        if (w != T(0)) atomicAdd(&grid[(ix[a] * ny + iy[b]) * nz + iz[c]], charge * w);
+      }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sc_deposit_kernel(const T* __restrict__ particles, int64_t particle_stride,
+                  const T* __restrict__ charges, int64_t charge_stride,
+                  const T* __restrict__ survival, int64_t survival_stride,
+                  const double* __restrict__ params, int64_t n_particles, int nx, int ny, int nz,
+                  T* __restrict__ rho) {
+  const int64_t b = blockIdx.y;
+  const double* prm = params + b * CH_SC_PARAMS;
+  const T lo[3] = {-static_cast<T>(prm[0]), -static_cast<T>(prm[1]), -static_cast<T>(prm[2])};
+  const T hi[3] = {static_cast<T>(prm[0]), static_cast<T>(prm[1]), static_cast<T>(prm[2])};
+  const T minus_beta = -static_cast<T>(prm[7]);
+  const T* p = particles + b * particle_stride;
+  const T* q = charges + b * charge_stride;
+  const T* w = survival ? survival + b * survival_stride : nullptr;
+  T* grid = rho + b * static_cast<int64_t>(nx) * ny * nz;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_particles;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const T charge = w ? q[i] * w[i] : q[i];
+    // positions are (x, y, z = -beta tau): particle_beam.py:1335
+    deposit_particle(grid, p[i * 7 + 0], p[i * 7 + 2], p[i * 7 + 4] * minus_beta, charge, lo, hi,
+                     nx, ny, nz);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cic_deposit3d_kernel(const T* __restrict__ positions, const T* __restrict__ extent,
+                     const T* __restrict__ charges, int64_t n_particles, int nx, int ny, int nz,
+                     T* __restrict__ out) {
+  const int64_t b = blockIdx.y;
+  const T* e = extent + b * 6;
+  const T lo[3] = {e[0], e[2], e[4]};
+  const T hi[3] = {e[1], e[3], e[5]};
+  const T* p = positions + b * n_particles * 3;
+  const T* q = charges ? charges + b * n_particles : nullptr;
+  T* grid = out + b * static_cast<int64_t>(nx) * ny * nz;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_particles;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    deposit_particle(grid, p[i * 3 + 0], p[i * 3 + 1], p[i * 3 + 2], q ? q[i] : T(1), lo, hi, nx,
+                     ny, nz);
+}
+
+// ---------------------------------------------------------------------------------------
+// 4. integrated Green function
+// ---------------------------------------------------------------------------------------
+// Antiderivative of 1/r (space_charge_kick.py:103-123), fp64.
+__device__ __forceinline__ double igf_antiderivative(double x, double y, double t) {
+  const double r = sqrt(x * x + y * y + t * t);
+  return -0.5 * t * t * atan(x * y / (t * r)) - 0.5 * y * y * atan(x * t / (y * r)) -
+         0.5 * x * x * atan(y * t / (x * r)) + y * t * asinh(x / sqrt(y * y + t * t)) +
+         x * t * asinh(y / sqrt(x * x + t * t)) + x * y * asinh(t / sqrt(x * x + y * y));
+}
+
+// lattice[i][j][k] = F((i - 1/2) dx, (j - 1/2) dy, (k - 1/2) dt), 0 <= i <= nx, ...
+__global__ void __launch_bounds__(256)
+sc_green_lattice_kernel(const double* __restrict__ params, int nx, int ny, int nz,
+                        double* __restrict__ lattice) {
+  const int64_t b = blockIdx.y;
+  const double* prm = params + b * CH_SC_PARAMS;
+  const double dx = prm[3], dy = prm[4], dt = prm[5] * prm[6];  // only d_tau is scaled by gamma
+  const int64_t total = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
+  double* out = lattice + b * total;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx % (nz + 1));
+    const int j = static_cast<int>((idx / (nz + 1)) % (ny + 1));
+    const int i = static_cast<int>(idx / (static_cast<int64_t>(nz + 1) * (ny + 1)));
+    out[idx] = igf_antiderivative((i - 0.5) * dx, (j - 0.5) * dy, (k - 0.5) * dt);
+  }
+}
+
+// green[2nx][2ny][2nz]: 8-corner signed difference of the lattice (:195-236), mirrored
+// (:247-289); the planes with index n stay zero.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sc_green_mirror_kernel(const double* __restrict__ lattice, int nx, int ny, int nz,
+                       T* __restrict__ green) {
+  const int64_t b = blockIdx.y;
+  const int64_t total = static_cast<int64_t>(8) * nx * ny * nz;
+  const double* f = lattice + b * static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
+  T* out = green + b * total;
+  const int sy = nz + 1, sx = (ny + 1) * (nz + 1);
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k2 = static_cast<int>(idx % (2 * nz));
+    const int j2 = static_cast<int>((idx / (2 * nz)) % (2 * ny));
+    const int i2 = static_cast<int>(idx / (static_cast<int64_t>(4) * ny * nz));
+    if (i2 == nx || j2 == ny || k2 == nz) {
+      out[idx] = T(0);
+      continue;
+    }
+    const int i = i2 < nx ? i2 : 2 * nx - i2;
+    const int j = j2 < ny ? j2 : 2 * ny - j2;
+    const int k = k2 < nz ? k2 : 2 * nz - k2;
+    const double* c = f + i * sx + j * sy + k;
+    const double g = c[sx + sy + 1] - c[sy + 1] - c[sx + 1] - c[sx + sy] + c[sx] + c[sy] + c[1] -
+                     c[0];
+    out[idx] = static_cast<T>(g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 5. FFT passes of the Poisson solve
+// ---------------------------------------------------------------------------------------
+constexpr int kFftThreads = 256;
+constexpr int kRowPairs = 8;   // z pass: 8 pairs of real rows per CTA
+constexpr int kColumns = 16;   // strided passes: 16 adjacent columns per CTA
+
+// z pass, real -> complex.  Two real rows are packed as (a + i b), transformed once and
+// separated with the Hermitian symmetry.  in: [B][in_x][in_y][in_z] real (in_z <= len valid
+// entries, the rest of the length-`len` transform is zero padding);
+// out: [B][2nx][2ny][len/2 + 1] complex, rows (x < in_x, y < in_y).
+template <typename T>
+__global__ void __launch_bounds__(kFftThreads)
+fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int len, int log2_len,
+                 int out_nx, int out_ny, typename fft::Complex<T>::type* __restrict__ out) {
+  using C = typename fft::Complex<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* v = reinterpret_cast<C*>(smem_raw);
+  C* tw = v + kRowPairs * len;
+  const int64_t b = blockIdx.y;
+  const int rows = in_x * in_y;
+  const int kz = len / 2 + 1;
+  const int first_row = blockIdx.x * 2 * kRowPairs;
+  const T* src = in + b * static_cast<int64_t>(rows) * in_z;
+  C* dst = out + b * static_cast<int64_t>(out_nx) * out_ny * kz;
+
+  fft::fill_twiddles(tw, len);
+  for (int t = threadIdx.x; t < kRowPairs * len; t += kFftThreads) {
+    const int pair = t / len, i = t - pair * len;
+    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
+    C value{T(0), T(0)};
+    if (i < in_z) {
+      if (r0 < rows) value.x = src[static_cast<int64_t>(r0) * in_z + i];
+      if (r1 < rows) value.y = src[static_cast<int64_t>(r1) * in_z + i];
+    }
+    v[t] = value;
+  }
+  __syncthreads();
+  fft::forward_dif(v, tw, len, log2_len, kRowPairs, len);
+
+  for (int t = threadIdx.x; t < kRowPairs * kz; t += kFftThreads) {
+    const int pair = t / kz, k = t - pair * kz;
+    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
+    if (r0 >= rows) continue;
+    const C zk = v[pair * len + fft::bit_reverse(k, log2_len)];
+    const C zm = v[pair * len + fft::bit_reverse((len - k) & (len - 1), log2_len)];
+    // A = (Z[k] + conj Z[-k]) / 2, B = (Z[k] - conj Z[-k]) / (2i)
+    const C a{T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y - zm.y)};
+    const C bb{T(0.5) * (zk.y + zm.y), T(-0.5) * (zk.x - zm.x)};
+    const int x0 = r0 / in_y, y0 = r0 - x0 * in_y;
+    dst[(static_cast<int64_t>(x0) * out_ny + y0) * kz + k] = a;
+    if (r1 < rows) {
+      const int x1 = r1 / in_y, y1 = r1 - x1 * in_y;
+      dst[(static_cast<int64_t>(x1) * out_ny + y1) * kz + k] = bb;
+    }
+  }
+}
+
+// z pass, complex -> real, for rows (x < out_x, y < out_y); stores the first out_z samples of
+// each length-`len` inverse transform times scale(b) = params[9] / (4 pi eps0 * 8 nx ny nz).
+template <typename T>
+__global__ void __launch_bounds__(kFftThreads)
+fft_c2r_z_kernel(const typename fft::Complex<T>::type* __restrict__ in, int in_nx, int in_ny,
+                 int len, int log2_len, int out_x, int out_y, int out_z,
+                 const double* __restrict__ params, double norm, T* __restrict__ out) {
+  using C = typename fft::Complex<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* v = reinterpret_cast<C*>(smem_raw);
+  C* tw = v + kRowPairs * len;
+  const int64_t b = blockIdx.y;
+  const int rows = out_x * out_y;
+  const int kz = len / 2 + 1;
+  const int first_row = blockIdx.x * 2 * kRowPairs;
+  const C* src = in + b * static_cast<int64_t>(in_nx) * in_ny * kz;
+  T* dst = out + b * static_cast<int64_t>(rows) * out_z;
+  const T scale = static_cast<T>(params[b * CH_SC_PARAMS + 9] * norm);
+
+  fft::fill_twiddles(tw, len);
+  for (int t = threadIdx.x; t < kRowPairs * len; t += kFftThreads) {
+    const int pair = t / len, k = t - pair * len;
+    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
+    const int kk = k < kz ? k : len - k;  // Hermitian partner for the upper half
+    C a{T(0), T(0)}, bb{T(0), T(0)};
+    if (r0 < rows) {
+      const int x0 = r0 / out_y, y0 = r0 - x0 * out_y;
+      a = src[(static_cast<int64_t>(x0) * in_ny + y0) * kz + kk];
+    }
+    if (r1 < rows) {
+      const int x1 = r1 / out_y, y1 = r1 - x1 * out_y;
+      bb = src[(static_cast<int64_t>(x1) * in_ny + y1) * kz + kk];
+    }
+    if (k >= kz) {  // conj for the mirrored half
+      a.y = -a.y;
+      bb.y = -bb.y;
+    }
+    if (k == 0 || k == len / 2) a.y = bb.y = T(0);  // c2r ignores Im of DC / Nyquist
+    // Z = A + i B
+    v[pair * len + fft::bit_reverse(k, log2_len)] = C{a.x - bb.y, a.y + bb.x};
+  }
+  __syncthreads();
+  fft::inverse_dit(v, tw, len, log2_len, kRowPairs, len);
+
+  for (int t = threadIdx.x; t < kRowPairs * out_z; t += kFftThreads) {
+    const int pair = t / out_z, i = t - pair * out_z;
+    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
+    const C z = v[pair * len + i];
+    if (r0 < rows) dst[static_cast<int64_t>(r0) * out_z + i] = z.x * scale;
+    if (r1 < rows) dst[static_cast<int64_t>(r1) * out_z + i] = z.y * scale;
+  }
+}
+
+// Strided complex pass over columns of `data`.  Column (outer, inner) starts at
+// outer * outer_stride + inner and steps by axis_stride; a CTA owns kColumns adjacent `inner`
+// values so that every global access is a contiguous run.
+//   MODE 0: forward, in place: in_len valid inputs (rest zero), `len` outputs
+//   MODE 1: inverse, in place: `len` inputs, out_len outputs
+//   MODE 2: forward, multiply by `green` (same layout), inverse: in_len in, out_len out
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kFftThreads)
+fft_strided_kernel(typename fft::Complex<T>::type* __restrict__ data,
+                   const typename fft::Complex<T>::type* __restrict__ green, int len, int log2_len,
+                   int in_len, int out_len, int64_t axis_stride, int inner_count,
+                   int64_t outer_stride, int64_t batch_stride) {
+  using C = typename fft::Complex<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* v = reinterpret_cast<C*>(smem_raw);
+  const int pitch = len + 1;  // odd pitch: the 16 columns of a row fall into distinct banks
+  C* tw = v + kColumns * pitch;
+  const int64_t base = blockIdx.z * batch_stride + blockIdx.y * outer_stride;
+  const int inner0 = blockIdx.x * kColumns;
+  const int columns = min(kColumns, inner_count - inner0);
+  C* col0 = data + base + inner0;
+
+  fft::fill_twiddles(tw, len);
+  for (int t = threadIdx.x; t < kColumns * len; t += kFftThreads) {
+    const int i = t / kColumns, c = t - i * kColumns;
+    C value{T(0), T(0)};
+    if (c < columns && i < in_len) value = col0[i * axis_stride + c];
+    const int slot = (MODE == 1) ? fft::bit_reverse(i, log2_len) : i;
+    v[c * pitch + slot] = value;
+  }
+  __syncthreads();
+
+  if (MODE == 0 || MODE == 2) fft::forward_dif(v, tw, len, log2_len, kColumns, pitch);
+  if (MODE == 2) {
+    const C* g0 = green + base + inner0;
+    for (int t = threadIdx.x; t < kColumns * len; t += kFftThreads) {
+      const int k = t / kColumns, c = t - k * kColumns;
+      if (c < columns) {
+        C* slot = &v[c * pitch + fft::bit_reverse(k, log2_len)];
+        *slot = fft::cmul(*slot, g0[k * axis_stride + c]);
+      }
+    }
+    __syncthreads();
+  }
+  if (MODE == 1 || MODE == 2) fft::inverse_dit(v, tw, len, log2_len, kColumns, pitch);
+
+  const int n_store = (MODE == 0) ? len : out_len;
+  for (int t = threadIdx.x; t < kColumns * n_store; t += kFftThreads) {
+    const int i = t / kColumns, c = t - i * kColumns;
+    if (c >= columns) continue;
+    const int slot = (MODE == 0) ? fft::bit_reverse(i, log2_len) : i;
+    col0[i * axis_stride + c] = v[c * pitch + slot];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 6. field
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct Field4;
+template <>
+struct Field4<float> {
+  using type = float4;
+};
+template <>
+struct Field4<double> {
+  using type = double4;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sc_field_kernel(const T* __restrict__ phi, const double* __restrict__ params, int nx, int ny,
+                int nz, typename Field4<T>::type* __restrict__ field) {
+  const int64_t b = blockIdx.y;
+  const double* prm = params + b * CH_SC_PARAMS;
+  const int64_t total = static_cast<int64_t>(nx) * ny * nz;
+  const T* f = phi + b * total;
+  // reference: (phi[i+1] - phi[i-1]) * (0.5 * inv_cell), then * (-igamma2), in the beam dtype
+  const T hx = T(0.5) * (T(1) / static_cast<T>(prm[3]));
+  const T hy = T(0.5) * (T(1) / static_cast<T>(prm[4]));
+  const T hz = T(0.5) * (T(1) / static_cast<T>(prm[5]));
+  const T scale = -static_cast<T>(prm[10]);
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx % nz);
+    const int j = static_cast<int>((idx / nz) % ny);
+    const int i = static_cast<int>(idx / (static_cast<int64_t>(nz) * ny));
+    typename Field4<T>::type e;
+    e.x = (i > 0 && i < nx - 1) ? scale * ((f[idx + ny * nz] - f[idx - ny * nz]) * hx) : T(0);
+    e.y = (j > 0 && j < ny - 1) ? scale * ((f[idx + nz] - f[idx - nz]) * hy) : T(0);
+    e.z = (k > 0 && k < nz - 1) ? scale * ((f[idx + 1] - f[idx - 1]) * hz) : T(0);
+    e.w = T(0);
+    field[b * total + idx] = e;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 7. gather + kick
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_stride,
+                      const typename Field4<T>::type* __restrict__ field,
+                      const double* __restrict__ params, int64_t n_particles, int nx, int ny,
+                      int nz, int bulk_in, int bulk_out, T* __restrict__ particles_out,
+                      T* __restrict__ forces_out) {
+  constexpr int P = 4, THREADS = 256, TP = P * THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  __shared__ uint64_t bar;
+  const int64_t b = blockIdx.y;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
+  const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
+  const double* prm = params + b * CH_SC_PARAMS;
+  const typename Field4<T>::type* grid = field + b * static_cast<int64_t>(nx) * ny * nz;
+
+  if (bulk_in && threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  cta_load_tile(tile, particles_in + b * particle_stride + n0 * 7, count * 7, bulk_in != 0, &bar,
+                phase);
+
+  // per-beam constants; grid geometry in the beam dtype (as the reference computes it)
+  const T gd[3] = {static_cast<T>(prm[0]), static_cast<T>(prm[1]), static_cast<T>(prm[2])};
+  const T cell[3] = {static_cast<T>(prm[3]), static_cast<T>(prm[4]), static_cast<T>(prm[5])};
+  const int n[3] = {nx, ny, nz};
+  const double gamma0 = prm[6], beta0 = prm[7], dt = prm[8];
+  const double mc = prm[15] * kEvToKg * kSpeedOfLight;  // mass * c in kg m / s
+  const double p0 = gamma0 * beta0 * mc;
+
+  T out[P][7];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int local = threadIdx.x + k * THREADS;
+    T p[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) p[j] = (local < count) ? tile[local * 7 + j] : T(0);
+
+    // ---- trilinear gather on the node-centred grid (space_charge_kick.py:388-475) ----
+    const T pos[3] = {p[0], p[2], p[4] * -static_cast<T>(beta0)};
+    int base[3];
+    T w_lo[3], w_hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const T norm = (pos[d] + gd[d]) / cell[d];
+      const T fl = floor(norm);
+      const T lim = static_cast<T>(n[d] + 1);
+      base[d] = static_cast<int>(fmin(fmax(fl, -lim), lim));
+      w_lo[d] = T(1) - fabs(norm - fl);           // 1 - |normalised - corner|  (:411-413)
+      w_hi[d] = T(1) - fabs(norm - (fl + T(1)));
+    }
+    T fx = T(0), fy = T(0), fz = T(0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ox = c >> 2, oy = (c >> 1) & 1, oz = c & 1;
+      const int ix = base[0] + ox, iy = base[1] + oy, iz = base[2] + oz;
+      const bool valid = ix >= 0 && ix < nx && iy >= 0 && iy < ny && iz >= 0 && iz < nz;
+      if (valid) {
+        const T w = (ox ? w_hi[0] : w_lo[0]) * (oy ? w_hi[1] : w_lo[1]) * (oz ? w_hi[2] : w_lo[2]);
+        const typename Field4<T>::type e = grid[(static_cast<int64_t>(ix) * ny + iy) * nz + iz];
+        const T we = w * static_cast<T>(kElementaryCharge);
+        fx += we * e.x;
+        fy += we * e.y;
+        fz += we * e.z;
+      }
+    }
+    if (forces_out != nullptr && local < count) {
+      T* f = forces_out + (b * n_particles + n0 + local) * 3;
+      f[0] = fx;
+      f[1] = fy;
+      f[2] = fz;
+    }
+
+    // ---- Cheetah -> SI, kick, SI -> Cheetah in fp64 (particle_beam.py:1262-1346) -------
+    const double gamma = gamma0 * (1.0 + static_cast<double>(p[5]) * beta0);
+    const double momentum = mc * sqrt(gamma * gamma - 1.0);  // gamma m c beta
+    double px = static_cast<double>(p[1]) * p0;
+    double py = static_cast<double>(p[3]) * p0;
+    double pz = sqrt(momentum * momentum - px * px - py * py);
+    px = fma(static_cast<double>(fx), dt, px);
+    py = fma(static_cast<double>(fy), dt, py);
+    pz = fma(static_cast<double>(fz), dt, pz);
+    const double u2 = (px * px + py * py + pz * pz) / (mc * mc);
+    const double gamma_new = sqrt(1.0 + u2);
+    out[k][0] = p[0];
+    out[k][1] = static_cast<T>(px / p0);
+    out[k][2] = p[2];
+    out[k][3] = static_cast<T>(py / p0);
+    out[k][4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
+    out[k][5] = static_cast<T>((gamma_new - gamma0) / (beta0 * gamma0));
+    out[k][6] = p[6];
+  }
+  __syncthreads();  // everybody is done reading the input tile
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int local = threadIdx.x + k * THREADS;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) tile[local * 7 + j] = out[k][j];
+  }
+  T* dst = particles_out + (b * n_particles + n0) * 7;
+  if (bulk_out) {
+    fence_async_shared();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_store(dst, tile, static_cast<uint32_t>(count) * 7u * sizeof(T));
+      bulk_commit();
+      bulk_wait<0>();
+    }
+  } else {
+    __syncthreads();
+    for (int i = threadIdx.x; i < count * 7; i += THREADS) dst[i] = tile[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------
+int log2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return ((1 << l) == v) ? l : -1;
+}
+
+bool grid_ok(int nx, int ny, int nz) {
+  for (int v : {nx, ny, nz})
+    if (v < 4 || v > 256 || log2_exact(v) < 0) return false;
+  return true;
+}
+
+template <typename K>
+int allow_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(bytes)));
+  return CH_OK;
+}
+
+unsigned blocks_for(int64_t work, int threads, int64_t cap = 148 * 16) {
+  const int64_t blocks = (work + threads - 1) / threads;
+  return static_cast<unsigned>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+template <typename T>
+int poisson_solve(const T* rho, const T* green, const double* params, int64_t B, int nx, int ny,
+                  int nz, typename fft::Complex<T>::type* rs, typename fft::Complex<T>::type* gs,
+                  T* phi, cudaStream_t stream) {
+  using C = typename fft::Complex<T>::type;
+  const int Nx = 2 * nx, Ny = 2 * ny, Nz = 2 * nz, Kz = Nz / 2 + 1;
+  const int lx = log2_exact(Nx), ly = log2_exact(Ny), lz = log2_exact(Nz);
+  const int64_t spectrum = static_cast<int64_t>(Nx) * Ny * Kz;
+  auto z_smem = [&](int len) { return sizeof(C) * (kRowPairs * len + len / 2); };
+  auto s_smem = [&](int len) { return sizeof(C) * (kColumns * (len + 1) + len / 2); };
+  const unsigned nb = static_cast<unsigned>(B);
+
+  // ---- rho: z (zero-padded rows of the physical octant), then y ------------------------
+  {
+    auto k = fft_r2c_z_kernel<T>;
+    if (allow_smem(k, z_smem(Nz)) != CH_OK) return CH_ECUDA;
+    dim3 grid((nx * ny + 2 * kRowPairs - 1) / (2 * kRowPairs), nb);
+    k<<<grid, kFftThreads, z_smem(Nz), stream>>>(rho, nx, ny, nz, Nz, lz, Nx, Ny, rs);
+    CH_LAUNCH_CHECK();
+  }
+  {
+    auto k = fft_strided_kernel<T, 0>;
+    if (allow_smem(k, s_smem(Ny)) != CH_OK) return CH_ECUDA;
+    dim3 grid((Kz + kColumns - 1) / kColumns, nx, nb);
+    k<<<grid, kFftThreads, s_smem(Ny), stream>>>(rs, nullptr, Ny, ly, ny, Ny, Kz, Kz,
+                                                  static_cast<int64_t>(Ny) * Kz, spectrum);
+    CH_LAUNCH_CHECK();
+  }
+  // ---- Green function: full z, y, x passes --------------------------------------------
+  {
+    auto k = fft_r2c_z_kernel<T>;
+    dim3 grid((Nx * Ny + 2 * kRowPairs - 1) / (2 * kRowPairs), nb);
+    k<<<grid, kFftThreads, z_smem(Nz), stream>>>(green, Nx, Ny, Nz, Nz, lz, Nx, Ny, gs);
+    CH_LAUNCH_CHECK();
+  }
+  {
+    auto k = fft_strided_kernel<T, 0>;
+    dim3 grid((Kz + kColumns - 1) / kColumns, Nx, nb);
+    k<<<grid, kFftThreads, s_smem(Ny), stream>>>(gs, nullptr, Ny, ly, Ny, Ny, Kz, Kz,
+                                                  static_cast<int64_t>(Ny) * Kz, spectrum);
+    CH_LAUNCH_CHECK();
+  }
+  {
+    auto k = fft_strided_kernel<T, 0>;
+    if (allow_smem(k, s_smem(Nx)) != CH_OK) return CH_ECUDA;
+    const int inner = Ny * Kz;
+    dim3 grid((inner + kColumns - 1) / kColumns, 1, nb);
+    k<<<grid, kFftThreads, s_smem(Nx), stream>>>(gs, nullptr, Nx, lx, Nx, Nx, inner, inner, 0,
+                                                  spectrum);
+    CH_LAUNCH_CHECK();
+  }
+  // ---- x: forward . multiply . inverse, fused; only x < nx is stored --------------------
+  {
+    auto k = fft_strided_kernel<T, 2>;
+    if (allow_smem(k, s_smem(Nx)) != CH_OK) return CH_ECUDA;
+    const int inner = Ny * Kz;
+    dim3 grid((inner + kColumns - 1) / kColumns, 1, nb);
+    k<<<grid, kFftThreads, s_smem(Nx), stream>>>(rs, gs, Nx, lx, nx, nx, inner, inner, 0, spectrum);
+    CH_LAUNCH_CHECK();
+  }
+  // ---- inverse y (keep y < ny) and inverse z (keep z < nz) -------------------------------
+  {
+    auto k = fft_strided_kernel<T, 1>;
+    if (allow_smem(k, s_smem(Ny)) != CH_OK) return CH_ECUDA;
+    dim3 grid((Kz + kColumns - 1) / kColumns, nx, nb);
+    k<<<grid, kFftThreads, s_smem(Ny), stream>>>(rs, nullptr, Ny, ly, Ny, ny, Kz, Kz,
+                                                  static_cast<int64_t>(Ny) * Kz, spectrum);
+    CH_LAUNCH_CHECK();
+  }
+  {
+    auto k = fft_c2r_z_kernel<T>;
+    if (allow_smem(k, z_smem(Nz)) != CH_OK) return CH_ECUDA;
+    dim3 grid((nx * ny + 2 * kRowPairs - 1) / (2 * kRowPairs), nb);
+    const double norm = 1.0 / (4.0 * kPi * kEpsilon0) / (static_cast<double>(Nx) * Ny * Nz);
+    k<<<grid, kFftThreads, z_smem(Nz), stream>>>(rs, Nx, Ny, Nz, lz, nx, ny, nz, params, norm, phi);
+    CH_LAUNCH_CHECK();
+  }
+  return CH_OK;
+}
+
+}  // namespace
+}  // namespace ch
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+#define CH_SC_COMMON_CHECKS(fn)                                                          \
+  CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, fn ": bad dtype %d", dtype);            \
+  CH_REQUIRE(n_beams > 0 && n_beams <= 65535, fn ": n_beams must be in [1, 65535]")
+
+extern "C" int ch_sc_beam_moments(const void* particles, int64_t particle_stride,
+                                  const void* survival, int64_t survival_stride,
+                                  int64_t n_particles, int64_t n_beams, int32_t dtype,
+                                  double* stats, void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_beam_moments");
+  CH_REQUIRE(particles && stats && n_particles > 0, "ch_sc_beam_moments: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CH_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * CH_SC_STATS * n_beams, s));
+  const int per_cta = 8192;
+  dim3 grid(static_cast<unsigned>((n_particles + per_cta - 1) / per_cta),
+            static_cast<unsigned>(n_beams));
+  if (dtype == CH_F32)
+    ch::sc_moments_kernel<float><<<grid, 256, 0, s>>>(
+        static_cast<const float*>(particles), particle_stride, static_cast<const float*>(survival),
+        survival_stride, n_particles, per_cta, stats);
+  else
+    ch::sc_moments_kernel<double><<<grid, 256, 0, s>>>(
+        static_cast<const double*>(particles), particle_stride,
+        static_cast<const double*>(survival), survival_stride, n_particles, per_cta, stats);
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_sc_grid_params(const double* stats, int64_t n_beams, const void* energy,
+                                 int64_t energy_stride, int32_t energy_dtype, const void* mass_eV,
+                                 int32_t mass_dtype, const void* effect_length,
+                                 int64_t length_stride, int32_t length_dtype, const void* extent_x,
+                                 int64_t extent_x_stride, const void* extent_y,
+                                 int64_t extent_y_stride, const void* extent_tau,
+                                 int64_t extent_tau_stride, int32_t extent_dtype, int32_t nx,
+                                 int32_t ny, int32_t nz, int32_t dtype, double* params,
+                                 void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_grid_params");
+  CH_REQUIRE(stats && energy && mass_eV && effect_length && extent_x && extent_y && extent_tau &&
+                 params,
+             "ch_sc_grid_params: NULL pointer argument");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz),
+             "ch_sc_grid_params: grid (%d, %d, %d) must be powers of two in [4, 256]", nx, ny, nz);
+  ch::GridInputs in{{energy, energy_stride, energy_dtype},
+                    {mass_eV, 0, mass_dtype},
+                    {effect_length, length_stride, length_dtype},
+                    {extent_x, extent_x_stride, extent_dtype},
+                    {extent_y, extent_y_stride, extent_dtype},
+                    {extent_tau, extent_tau_stride, extent_dtype}};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((n_beams + 127) / 128);
+  if (dtype == CH_F32)
+    ch::sc_grid_params_kernel<float><<<blocks, 128, 0, s>>>(stats, n_beams, in, nx, ny, nz, params);
+  else
+    ch::sc_grid_params_kernel<double><<<blocks, 128, 0, s>>>(stats, n_beams, in, nx, ny, nz, params);
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_sc_deposit(const void* particles, int64_t particle_stride, const void* charges,
+                             int64_t charge_stride, const void* survival, int64_t survival_stride,
+                             const double* params, int64_t n_particles, int64_t n_beams,
+                             int32_t nx, int32_t ny, int32_t nz, int32_t dtype, void* rho,
+                             void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_deposit");
+  CH_REQUIRE(particles && charges && params && rho && n_particles > 0,
+             "ch_sc_deposit: bad arguments");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_deposit: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t elem = dtype == CH_F32 ? 4 : 8;
+  CH_CUDA(cudaMemsetAsync(rho, 0, elem * nx * ny * nz * n_beams, s));
+  dim3 grid(ch::blocks_for(n_particles, 256), static_cast<unsigned>(n_beams));
+  if (dtype == CH_F32)
+    ch::sc_deposit_kernel<float><<<grid, 256, 0, s>>>(
+        static_cast<const float*>(particles), particle_stride, static_cast<const float*>(charges),
+        charge_stride, static_cast<const float*>(survival), survival_stride, params, n_particles,
+        nx, ny, nz, static_cast<float*>(rho));
+  else
+    ch::sc_deposit_kernel<double><<<grid, 256, 0, s>>>(
+        static_cast<const double*>(particles), particle_stride,
+        static_cast<const double*>(charges), charge_stride, static_cast<const double*>(survival),
+        survival_stride, params, n_particles, nx, ny, nz, static_cast<double*>(rho));
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_cic_deposit3d(const void* positions, const void* extent, const void* charges,
+                                int64_t n_particles, int64_t n_beams, int32_t nx, int32_t ny,
+                                int32_t nz, int32_t dtype, void* grid_out, void* stream) {
+  CH_SC_COMMON_CHECKS("ch_cic_deposit3d");
+  CH_REQUIRE(positions && extent && grid_out && n_particles > 0, "ch_cic_deposit3d: bad arguments");
+  CH_REQUIRE(nx > 0 && ny > 0 && nz > 0, "ch_cic_deposit3d: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t elem = dtype == CH_F32 ? 4 : 8;
+  CH_CUDA(cudaMemsetAsync(grid_out, 0, elem * nx * ny * nz * n_beams, s));
+  dim3 grid(ch::blocks_for(n_particles, 256), static_cast<unsigned>(n_beams));
+  if (dtype == CH_F32)
+    ch::cic_deposit3d_kernel<float><<<grid, 256, 0, s>>>(
+        static_cast<const float*>(positions), static_cast<const float*>(extent),
+        static_cast<const float*>(charges), n_particles, nx, ny, nz, static_cast<float*>(grid_out));
+  else
+    ch::cic_deposit3d_kernel<double><<<grid, 256, 0, s>>>(
+        static_cast<const double*>(positions), static_cast<const double*>(extent),
+        static_cast<const double*>(charges), n_particles, nx, ny, nz,
+        static_cast<double*>(grid_out));
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_sc_green_function(const double* params, int64_t n_beams, int32_t nx, int32_t ny,
+                                    int32_t nz, int32_t dtype, double* lattice, void* green,
+                                    void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_green_function");
+  CH_REQUIRE(params && lattice && green, "ch_sc_green_function: NULL pointer argument");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_green_function: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
+  dim3 grid_a(ch::blocks_for(points, 256), static_cast<unsigned>(n_beams));
+  ch::sc_green_lattice_kernel<<<grid_a, 256, 0, s>>>(params, nx, ny, nz, lattice);
+  CH_LAUNCH_CHECK();
+  dim3 grid_b(ch::blocks_for(static_cast<int64_t>(8) * nx * ny * nz, 256, 148 * 32),
+              static_cast<unsigned>(n_beams));
+  if (dtype == CH_F32)
+    ch::sc_green_mirror_kernel<float><<<grid_b, 256, 0, s>>>(lattice, nx, ny, nz,
+                                                             static_cast<float*>(green));
+  else
+    ch::sc_green_mirror_kernel<double><<<grid_b, 256, 0, s>>>(lattice, nx, ny, nz,
+                                                              static_cast<double*>(green));
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_sc_poisson_solve(const void* rho, const void* green, const double* params,
+                                   int64_t n_beams, int32_t nx, int32_t ny, int32_t nz,
+                                   int32_t dtype, void* rho_spectrum, void* green_spectrum,
+                                   void* phi, void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_poisson_solve");
+  CH_REQUIRE(rho && green && params && rho_spectrum && green_spectrum && phi,
+             "ch_sc_poisson_solve: NULL pointer argument");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_poisson_solve: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CH_F32)
+    return ch::poisson_solve<float>(static_cast<const float*>(rho),
+                                    static_cast<const float*>(green), params, n_beams, nx, ny, nz,
+                                    static_cast<float2*>(rho_spectrum),
+                                    static_cast<float2*>(green_spectrum), static_cast<float*>(phi),
+                                    s);
+  return ch::poisson_solve<double>(static_cast<const double*>(rho),
+                                   static_cast<const double*>(green), params, n_beams, nx, ny, nz,
+                                   static_cast<double2*>(rho_spectrum),
+                                   static_cast<double2*>(green_spectrum),
+                                   static_cast<double*>(phi), s);
+}
+
+extern "C" int ch_sc_field(const void* phi, const double* params, int64_t n_beams, int32_t nx,
+                           int32_t ny, int32_t nz, int32_t dtype, void* field, void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_field");
+  CH_REQUIRE(phi && params && field, "ch_sc_field: NULL pointer argument");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_field: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(ch::blocks_for(static_cast<int64_t>(nx) * ny * nz, 256),
+            static_cast<unsigned>(n_beams));
+  if (dtype == CH_F32)
+    ch::sc_field_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(phi), params, nx, ny,
+                                                    nz, static_cast<float4*>(field));
+  else
+    ch::sc_field_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(phi), params, nx,
+                                                     ny, nz, static_cast<double4*>(field));
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_sc_gather_kick(const void* particles_in, int64_t particle_stride,
+                                 const void* field, const double* params, int64_t n_particles,
+                                 int64_t n_beams, int32_t nx, int32_t ny, int32_t nz,
+                                 int32_t dtype, void* particles_out, void* forces_out,
+                                 void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_gather_kick");
+  CH_REQUIRE(particles_in && field && params && particles_out && n_particles > 0,
+             "ch_sc_gather_kick: bad arguments");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_gather_kick: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(n_beams));
+  if (dtype == CH_F32) {
+    const int bulk_in = ch::bulk_compatible<float>(particles_in, n_particles, particle_stride);
+    const int bulk_out = ch::bulk_compatible<float>(particles_out, n_particles, n_particles * 7);
+    ch::sc_gather_kick_kernel<float><<<grid, 256, 1024 * 7 * sizeof(float), s>>>(
+        static_cast<const float*>(particles_in), particle_stride,
+        static_cast<const float4*>(field), params, n_particles, nx, ny, nz, bulk_in, bulk_out,
+        static_cast<float*>(particles_out), static_cast<float*>(forces_out));
+  } else {
+    const int bulk_in = ch::bulk_compatible<double>(particles_in, n_particles, particle_stride);
+    const int bulk_out = ch::bulk_compatible<double>(particles_out, n_particles, n_particles * 7);
+    auto kernel = ch::sc_gather_kick_kernel<double>;
+    const size_t smem = 1024 * 7 * sizeof(double);
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    kernel<<<grid, 256, smem, s>>>(static_cast<const double*>(particles_in), particle_stride,
+                                static_cast<const double4*>(field), params, n_particles, nx, ny,
+                                nz, bulk_in, bulk_out, static_cast<double*>(particles_out),
+                                static_cast<double*>(forces_out));
+  }
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}

@@ -1,0 +1,183 @@
+"""``SpaceChargeKick.track`` and ``cloud_in_cell_charge_deposition`` on the CUDA library.
+
+Host-side mirror of cheetah/accelerator/space_charge_kick.py:477-586: broadcast the beam's
+vector dimensions, flatten them to one batch of B beams, run the seven-kernel chain (moments,
+grid parameters, deposit, Green function, FFT Poisson solve, field, gather+kick) and restore
+the vector shape.  All per-beam scalars stay on the device between kernels.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _capi
+
+
+def _flat(tensor: torch.Tensor, vector_shape: tuple, inner: tuple, dtype) -> tuple:
+    """(contiguous tensor, batch stride in elements) of ``tensor`` viewed as [B, *inner]."""
+    vshape = tuple(tensor.shape[: tensor.dim() - len(inner)])
+    if tensor.dtype != dtype:
+        tensor = tensor.to(dtype)
+    if math.prod(vshape) == 1:
+        return tensor.contiguous(), 0
+    if vshape != tuple(vector_shape):
+        tensor = tensor.expand(*vector_shape, *inner)
+    return tensor.contiguous(), math.prod(inner)
+
+
+def _scalar_ref(tensor: torch.Tensor, vector_shape: tuple, dtype) -> tuple:
+    tensor, stride = _flat(tensor, vector_shape, (), dtype)
+    return tensor, min(stride, 1)
+
+
+class Workspace:
+    """Scratch buffers of one kick (torch's caching allocator makes re-allocation cheap)."""
+
+    def __init__(self, n_beams: int, grid_shape: tuple, dtype, device) -> None:
+        nx, ny, nz = grid_shape
+        cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
+        spectrum = (n_beams, 2 * nx, 2 * ny, nz + 1)
+        self.stats = torch.empty((n_beams, _capi.SC_STATS), dtype=torch.float64, device=device)
+        self.params = torch.empty((n_beams, _capi.SC_PARAMS), dtype=torch.float64, device=device)
+        self.rho = torch.empty((n_beams, nx, ny, nz), dtype=dtype, device=device)
+        self.lattice = torch.empty(
+            (n_beams, nx + 1, ny + 1, nz + 1), dtype=torch.float64, device=device
+        )
+        self.green = torch.empty((n_beams, 2 * nx, 2 * ny, 2 * nz), dtype=dtype, device=device)
+        self.rho_spectrum = torch.empty(spectrum, dtype=cdtype, device=device)
+        self.green_spectrum = torch.empty(spectrum, dtype=cdtype, device=device)
+        self.phi = torch.empty((n_beams, nx, ny, nz), dtype=dtype, device=device)
+        self.field = torch.empty((n_beams, nx, ny, nz, 4), dtype=dtype, device=device)
+
+
+def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, grid_shape,
+         want_intermediates: bool = False):
+    """Run one kick on already-broadcast inputs; returns (particles_out [B,N,7], workspace)."""
+    device, dtype = particles.device, particles.dtype
+    lib = _capi.lib()
+    code = _capi.dtype_code(dtype)
+    nx, ny, nz = (int(v) for v in grid_shape)
+    for v in (nx, ny, nz):
+        if v < 4 or v > 256 or v & (v - 1):
+            raise NotImplementedError(
+                f"cheetah_b200 SpaceChargeKick needs power-of-two grid sizes in [4, 256], got "
+                f"{tuple(grid_shape)}"
+            )
+
+    vector_shape = torch.broadcast_shapes(
+        particles.shape[:-2], energy.shape, charges.shape[:-1], survival.shape[:-1],
+        effect_length.shape, *(e.shape for e in extents), (1,),
+    )
+    n_beams = math.prod(vector_shape)
+    n = particles.shape[-2]
+    p, p_stride = _flat(particles, vector_shape, (n, 7), dtype)
+    q, q_stride = _flat(charges, vector_shape, (n,), dtype)
+    w, w_stride = _flat(survival, vector_shape, (n,), dtype)
+    e, e_stride = _scalar_ref(energy, vector_shape, dtype)
+    length, l_stride = _scalar_ref(effect_length, vector_shape, dtype)
+    ext = [_scalar_ref(x, vector_shape, dtype) for x in extents]
+    mass = mass_eV if mass_eV.dtype in (torch.float32, torch.float64) else mass_eV.to(dtype)
+
+    ws = Workspace(n_beams, (nx, ny, nz), dtype, device)
+    out = torch.empty((n_beams, n, 7), dtype=dtype, device=device)
+    forces = torch.empty((n_beams, n, 3), dtype=dtype, device=device) if want_intermediates else None
+    stream = _capi.current_stream(device)
+    with torch.cuda.device(device):
+        _capi.check(lib.ch_sc_beam_moments(
+            p.data_ptr(), p_stride, w.data_ptr(), w_stride, n, n_beams, code,
+            ws.stats.data_ptr(), stream))
+        _capi.check(lib.ch_sc_grid_params(
+            ws.stats.data_ptr(), n_beams,
+            e.data_ptr(), e_stride, _capi.dtype_code(e.dtype),
+            mass.data_ptr(), _capi.dtype_code(mass.dtype),
+            length.data_ptr(), l_stride, _capi.dtype_code(length.dtype),
+            ext[0][0].data_ptr(), ext[0][1], ext[1][0].data_ptr(), ext[1][1],
+            ext[2][0].data_ptr(), ext[2][1], code,
+            nx, ny, nz, code, ws.params.data_ptr(), stream))
+        _capi.check(lib.ch_sc_deposit(
+            p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
+            ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho.data_ptr(), stream))
+        _capi.check(lib.ch_sc_green_function(
+            ws.params.data_ptr(), n_beams, nx, ny, nz, code, ws.lattice.data_ptr(),
+            ws.green.data_ptr(), stream))
+        _capi.check(lib.ch_sc_poisson_solve(
+            ws.rho.data_ptr(), ws.green.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz,
+            code, ws.rho_spectrum.data_ptr(), ws.green_spectrum.data_ptr(), ws.phi.data_ptr(),
+            stream))
+        _capi.check(lib.ch_sc_field(
+            ws.phi.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
+            ws.field.data_ptr(), stream))
+        _capi.check(lib.ch_sc_gather_kick(
+            p.data_ptr(), p_stride, ws.field.data_ptr(), ws.params.data_ptr(), n, n_beams,
+            nx, ny, nz, code, out.data_ptr(), _capi.ptr(forces), stream))
+    ws.forces = forces
+    return out.reshape(*vector_shape, n, 7), ws
+
+
+def track(element, incoming):
+    """``SpaceChargeKick.track`` (space_charge_kick.py:477-586)."""
+    assert type(incoming).__name__ == "ParticleBeam", (
+        "SpaceChargeKick tracking is currently only supported for `ParticleBeam`."
+    )
+    particles = incoming.particles
+    if particles.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"cheetah_b200 tracks float32/float64 beams, got {particles.dtype}")
+    for name in ("effect_length", "grid_extent_x", "grid_extent_y", "grid_extent_tau"):
+        tensor = getattr(element, name)
+        if tensor.device != particles.device:
+            raise ValueError(
+                f"{name} of element {element.name!r} lives on {tensor.device} but the beam is on "
+                f"{particles.device}; move the lattice with `segment.to(device)` first"
+            )
+    out, _ = kick(
+        particles, incoming.energy, incoming.particle_charges, incoming.survival_probabilities,
+        incoming.species.mass_eV, element.effect_length,
+        (element.grid_extent_x, element.grid_extent_y, element.grid_extent_tau),
+        element.grid_shape,
+    )
+    # the reference drops the (1,) helper dimension again when nothing is vectorised
+    out_shape = torch.broadcast_shapes(
+        particles.shape[:-2], incoming.energy.shape, incoming.particle_charges.shape[:-1],
+        incoming.survival_probabilities.shape[:-1], element.effect_length.shape,
+        element.grid_extent_x.shape, element.grid_extent_y.shape, element.grid_extent_tau.shape,
+    )
+    out = out.reshape(*out_shape, particles.shape[-2], 7)
+    outgoing = incoming.__class__(
+        out, incoming.energy, particle_charges=incoming.particle_charges,
+        survival_probabilities=incoming.survival_probabilities, s=incoming.s,
+        species=incoming.species,
+    )
+    try:
+        outgoing._unit_seventh = getattr(incoming, "_unit_seventh", None)
+    except Exception:
+        pass
+    return outgoing
+
+
+def cloud_in_cell_charge_deposition(positions, bins, extent=None, charges=None):
+    """3-D cloud-in-cell deposit with the signature of cheetah/utils/cloud_in_cell.py:8-13."""
+    if positions.shape[-1] != 3:
+        raise NotImplementedError("cheetah_b200 accelerates the 3-D deposit only (SURVEY.md 8f)")
+    if not positions.is_cuda:
+        raise RuntimeError("cheetah_b200: positions must be on a CUDA device (no CPU fallback)")
+    dtype, device = positions.dtype, positions.device
+    shape = [bins] * 3 if isinstance(bins, int) else list(bins)
+    assert len(shape) == 3, "Number of bin values must match number of position dimensions."
+    if extent is None:
+        extent = torch.stack([positions.amin(dim=-2), positions.amax(dim=-2)], dim=-1)
+    vector_shape = tuple(positions.shape[:-2])
+    n = positions.shape[-2]
+    n_beams = max(1, math.prod(vector_shape))
+    pos = positions.reshape(n_beams, n, 3).contiguous()
+    ext = extent.to(dtype).expand(*vector_shape, 3, 2).reshape(n_beams, 3, 2).contiguous()
+    q = None
+    if charges is not None:
+        q = charges.to(dtype).expand(*vector_shape, n).reshape(n_beams, n).contiguous()
+    grid = torch.empty((n_beams, *shape), dtype=dtype, device=device)
+    with torch.cuda.device(device):
+        _capi.check(_capi.lib().ch_cic_deposit3d(
+            pos.data_ptr(), ext.data_ptr(), _capi.ptr(q), n, n_beams, *shape,
+            _capi.dtype_code(dtype), grid.data_ptr(), _capi.current_stream(device)))
+    return grid.reshape(*vector_shape, *shape)

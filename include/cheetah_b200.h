@@ -14,7 +14,7 @@
  *    across the ABI.
  *  - all data pointers are DEVICE pointers unless the name ends in _host; the caller
  *    owns every buffer it passes in, including outputs.  The library only owns
- *    ch_program objects and the ch_workspace scratch it is asked to create.
+ *    ch_program objects; scratch buffers are passed in by the caller.
  *  - `stream` is a cudaStream_t passed as void* (PyTorch:
  *    torch.cuda.current_stream().cuda_stream); all work is enqueued on it, no call
  *    synchronises the device.
@@ -151,6 +151,102 @@ int ch_apply_maps(const void* particles_in, int64_t particle_stride, const int32
                   int64_t n_particles, int64_t n_settings,
                   void* particles_out, void* survival_out,
                   int32_t dtype, int32_t unit_seventh, void* stream);
+
+/* space charge ----------------------------------------------------------------------- */
+/* One SpaceChargeKick (cheetah/accelerator/space_charge_kick.py:477-586) is the sequence
+ *   ch_sc_beam_moments -> ch_sc_grid_params -> ch_sc_deposit -> ch_sc_green_function ->
+ *   ch_sc_poisson_solve -> ch_sc_field -> ch_sc_gather_kick
+ * over B independent beams (the flattened vector dims, space_charge_kick.py:493-528).
+ * All per-beam scalars live on the device in fp64 tables so that no step synchronises
+ * with the host:
+ *   stats  [B][CH_SC_STATS]   0 sum w, 1 sum w^2, 2-4 sum w (u - u0), 5-7 sum w (u - u0)^2
+ *                             for u = x, y, tau; 8-10 the pilot u0 (particle 0), 11 unused
+ *   params [B][CH_SC_PARAMS]  0-2 grid half-extent (extent * sigma), 3-5 cell size,
+ *                             6 gamma, 7 beta, 8 dt = L / (c beta), 9 1 / cell volume,
+ *                             10 1 / gamma^2 (0 if gamma == 0), 11-13 sigma x, y, tau,
+ *                             14 sum w, 15 mass in eV
+ * Grid sizes nx, ny, nz must be powers of two in [4, 256] (the doubled FFT length <= 512).
+ * Batch strides are in elements per beam; 0 shares one array among all beams.           */
+#define CH_SC_STATS 12
+#define CH_SC_PARAMS 16
+
+/* Survival-weighted sums for the unbiased weighted standard deviations of x, y, tau:
+ * ParticleBeam.sigma_{x,y,tau} (cheetah/particles/particle_beam.py:1709-1717, :1761-1765,
+ * :1801-1805) -> unbiased_weighted_variance (cheetah/utils/statistics.py:30-48).  One pass,
+ * fp64 accumulation about a pilot particle.  survival may be NULL (all ones).           */
+int ch_sc_beam_moments(const void* particles, int64_t particle_stride,
+                       const void* survival, int64_t survival_stride,
+                       int64_t n_particles, int64_t n_beams, int32_t dtype,
+                       double* stats, void* stream);
+
+/* sigma -> grid_dimensions, cell_size, dt, gamma, beta: space_charge_kick.py:531-550,
+ * cheetah/particles/beam.py:323-336.  energy / effect_length / extents are read like
+ * slots: value(b) = ptr[b * stride] with the given dtype.                               */
+int ch_sc_grid_params(const double* stats, int64_t n_beams,
+                      const void* energy, int64_t energy_stride, int32_t energy_dtype,
+                      const void* mass_eV, int32_t mass_dtype,
+                      const void* effect_length, int64_t length_stride, int32_t length_dtype,
+                      const void* extent_x, int64_t extent_x_stride,
+                      const void* extent_y, int64_t extent_y_stride,
+                      const void* extent_tau, int64_t extent_tau_stride, int32_t extent_dtype,
+                      int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                      double* params, void* stream);
+
+/* Cloud-in-cell deposit of charge * survival at (x, y, -beta tau) on the (nx, ny, nz) grid
+ * spanning +-grid half-extent: _array_rho (space_charge_kick.py:125-146) ->
+ * _cloud_in_cell_3d (cheetah/utils/cloud_in_cell.py:244-384; cell-centred, inclusive
+ * extent test, clamped corners with zeroed weights).  rho [B][nx*ny*nz] is zeroed here;
+ * it holds CHARGE per cell (the 1/cell-volume factor is applied in ch_sc_poisson_solve). */
+int ch_sc_deposit(const void* particles, int64_t particle_stride,
+                  const void* charges, int64_t charge_stride,
+                  const void* survival, int64_t survival_stride,
+                  const double* params, int64_t n_particles, int64_t n_beams,
+                  int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                  void* rho, void* stream);
+
+/* General 3-D cloud-in-cell deposit: cloud_in_cell_charge_deposition
+ * (cheetah/utils/cloud_in_cell.py:8-64) for positions [B][N][3], extent [B][3][2]
+ * (left, right per axis), charges [B][N] (NULL = ones); grid [B][nx*ny*nz] is zeroed here. */
+int ch_cic_deposit3d(const void* positions, const void* extent, const void* charges,
+                     int64_t n_particles, int64_t n_beams,
+                     int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                     void* grid, void* stream);
+
+/* Integrated Green function on the doubled grid: _integrated_potential +
+ * _integrated_green_function (space_charge_kick.py:103-123, :163-291).  The antiderivative
+ * is evaluated ONCE per half-shifted lattice point in fp64 (lattice [B][(nx+1)(ny+1)(nz+1)]
+ * doubles of scratch) and differenced, then mirrored into green [B][2nx][2ny][2nz] with
+ * plane index n of every axis left zero, as the reference does.  d_tau is scaled by gamma. */
+int ch_sc_green_function(const double* params, int64_t n_beams,
+                         int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                         double* lattice, void* green, void* stream);
+
+/* phi = irfftn(rfftn(rho_padded) * rfftn(green)) / (4 pi eps0 * cell volume), cropped to
+ * the physical octant: _solve_poisson_equation (space_charge_kick.py:293-322).  Hand-written
+ * shared-memory FFT passes (no cuFFT): z real<->complex with two rows packed per transform,
+ * y and x strided passes; the x pass fuses forward FFT, the multiply by the Green spectrum
+ * and the inverse FFT.  rho_spectrum / green_spectrum: [B][2nx][2ny][nz+1] complex scratch. */
+int ch_sc_poisson_solve(const void* rho, const void* green, const double* params,
+                        int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                        void* rho_spectrum, void* green_spectrum, void* phi, void* stream);
+
+/* -(1/gamma^2) grad(phi) by central differences, zero on the boundary cells:
+ * _E_plus_vB_field (space_charge_kick.py:324-365).  field [B][nx*ny*nz][4] = (gx, gy, gz, 0). */
+int ch_sc_field(const void* phi, const double* params, int64_t n_beams,
+                int32_t nx, int32_t ny, int32_t nz, int32_t dtype, void* field, void* stream);
+
+/* Node-centred trilinear gather of the field at the 8 surrounding grid points x elementary
+ * charge (_compute_forces, space_charge_kick.py:367-475), momentum kick P += F dt
+ * (:557-565) and both coordinate conversions ParticleBeam.to_xyz_pxpypz /
+ * from_xyz_pxpypz (cheetah/particles/particle_beam.py:1262-1346), fused: one read and one
+ * write of the particles.  The SI round trip is evaluated in fp64 (the reference's fp32
+ * version squares momenta of 1e-20 kg m/s into the subnormal range).
+ * forces_out (optional, [B][N][3]) receives the interpolated forces for tests.          */
+int ch_sc_gather_kick(const void* particles_in, int64_t particle_stride,
+                      const void* field, const double* params,
+                      int64_t n_particles, int64_t n_beams,
+                      int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                      void* particles_out, void* forces_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,190 @@
+"""GPU parity of the SpaceChargeKick kernel family against the reference's own outputs
+(tests/golden/space_charge.npz, cloud_in_cell.npz, consistency.npz) and the float64 oracle.
+
+Tolerances.  The reference's own float32 result differs from its float64 result by ~1e-3 of
+the kick (its IGF loses digits to cancellation in float32), so
+  * float64 beams: every stage and the final kick within 1e-9 of the reference (relative to
+    the stage's maximum);
+  * float32 beams: kicks within 2e-3 x the largest kick of the float64 oracle evaluated on the
+    same float32-rounded inputs (our Green function and SI conversions run in float64, so this
+    path is CLOSER to the float64 truth than the reference's float32 path);
+  * cloud-in-cell with particles at bin centres: exactly torch.histogramdd.
+"""
+
+import pytest
+import torch
+
+from oracle import lattice_io
+from oracle import track_oracle as oracle
+
+from . import golden_utils as gu
+from .test_oracle_golden import CONSISTENCY, LATTICES, ROW_STRIDE, SPACE_CHARGE
+
+pytestmark = pytest.mark.gpu
+DEVICE = "cuda"
+
+
+def rel_err(actual, expected) -> float:
+    actual = actual.detach().cpu().double()
+    expected = expected.detach().cpu().double()
+    return float((actual - expected).abs().max() / expected.abs().max())
+
+
+def incoming(dtype):
+    return gu.beam_dict(SPACE_CHARGE, "incoming", dtype)
+
+
+@pytest.mark.parametrize("tag,dtype", [("f64", torch.float64), ("f32", torch.float32)])
+def test_every_stage_matches_the_reference(tag, dtype):
+    from cheetah_b200 import space_charge
+
+    beam = incoming(dtype)
+    to = lambda t: t.to(DEVICE)  # noqa: E731
+    out, ws = space_charge.kick(
+        to(beam["particles"]), to(beam["energy"]), to(beam["particle_charges"]),
+        to(beam["survival_probabilities"]), to(beam["mass_eV"]),
+        torch.tensor(0.7, dtype=dtype, device=DEVICE),
+        tuple(torch.tensor(3.0, dtype=dtype, device=DEVICE) for _ in range(3)),
+        (16, 16, 16), want_intermediates=True,
+    )
+    torch.cuda.synchronize()
+    f64 = dtype == torch.float64
+    golden = lambda name: gu.tensor(SPACE_CHARGE[f"kick16.{tag}.{name}"])  # noqa: E731
+    truth = lambda name: gu.tensor(SPACE_CHARGE[f"kick16.f64.{name}"])  # noqa: E731
+
+    assert rel_err(ws.params[:, 0:3], golden("grid_dimensions")) < (1e-12 if f64 else 1e-6)
+    density = ws.rho.double() * ws.params[:, 9, None, None, None]
+    assert rel_err(density, golden("rho_padded")[:, :16, :16, :16]) < (1e-12 if f64 else 1e-5)
+    # Green function: ours is evaluated in float64, so compare with the float64 reference
+    assert rel_err(ws.green, truth("green")) < (1e-10 if f64 else 1e-6)
+    assert rel_err(ws.phi, truth("potential")) < (1e-10 if f64 else 2e-5)
+    rows = slice(None, None, 4)
+    assert rel_err(ws.forces[:, rows], truth("forces")) < (1e-9 if f64 else 2e-4)
+    expected = gu.beam_dict(SPACE_CHARGE, "kick16.f64")
+    kick_ours = out.cpu().double()[0, rows] - beam["particles"].double()[rows]
+    kick_ref = expected["particles"] - gu.beam_dict(SPACE_CHARGE, "incoming")["particles"][rows]
+    for col in (1, 3, 5):
+        err = (kick_ours[:, col] - kick_ref[:, col]).abs().max() / kick_ref[:, col].abs().max()
+        assert err < (1e-9 if f64 else 2e-3), (col, float(err))
+    for col in (0, 2, 4, 6):  # positions untouched
+        assert torch.equal(out.cpu()[0, :, col], beam["particles"][:, col])
+
+
+def _track_case(case, dtype):
+    import cheetah_b200 as cb
+
+    beam = incoming(dtype)
+    if case == "kick16":
+        lattice = [{"type": "SpaceChargeKick", "name": "sc", "effect_length": torch.tensor(0.7),
+                    "grid_shape": (16, 16, 16)}]
+    elif case == "kick32vec":
+        lattice = [{"type": "SpaceChargeKick", "name": "sc", "effect_length": torch.tensor(0.2)}]
+        beam["energy"] = torch.tensor(5e6, dtype=dtype)
+        beam["particle_charges"] = beam["particle_charges"] * torch.tensor([[1.0], [3.0]], dtype=dtype)
+    else:
+        lattice = lattice_io.load(gu.GOLDEN / "fodo_space_charge_lattice.json", dtype)
+        beam["energy"] = torch.tensor(5e7, dtype=dtype)
+        beam["particle_charges"] = beam["particle_charges"] * 0.1
+    lattice = lattice_io.cast(lattice, dtype)
+    out = gu.product_segment(lattice, DEVICE, dtype).track(gu.product_beam(beam, DEVICE, dtype))
+    return lattice, beam, out
+
+
+@pytest.mark.parametrize("tag,dtype", [("f64", torch.float64), ("f32", torch.float32)])
+@pytest.mark.parametrize("case", ["kick16", "kick32vec", "fodo"])
+def test_track_matches_reference_outputs(case, tag, dtype):
+    lattice, beam, out = _track_case(case, dtype)
+    rows = slice(None, None, 4)
+    f64 = dtype == torch.float64
+    truth = gu.beam_dict(SPACE_CHARGE, f"{case}.f64")
+    assert out.particles.shape[:-2] == truth["particles"].shape[:-2]
+    ours = out.particles.cpu().double()[..., rows, :]
+    start = beam["particles"].double()[rows]
+    moved = (truth["particles"] - start).abs().amax(dim=-2, keepdim=True)
+    # coordinates a kick leaves alone only "move" by the reference's rounding (tau -> -z/beta)
+    floor = 1e-12 * truth["particles"].abs().amax(dim=-2, keepdim=True)
+    err = ((ours - truth["particles"]).abs() / torch.maximum(moved, floor).clamp_min(1e-300))
+    err = err[..., :6].max()
+    # errors are relative to how far each coordinate moved through the whole lattice
+    assert err < (1e-8 if f64 else 3e-3), float(err)
+    assert torch.equal(
+        out.survival_probabilities.cpu().double()[..., rows], truth["survival_probabilities"]
+    )
+    assert torch.allclose(out.s.cpu().double(), truth["s"], rtol=1e-6)
+
+
+def test_reference_consistency_pickle_space_charge_kick():
+    """The reference's own golden pickle for SpaceChargeKick (32^3 default grid), float64,
+    at the reference's own tolerance (tests/test_elements.py:356-431)."""
+    beam = gu.beam_dict(CONSISTENCY, "incoming")
+    case = "SpaceChargeKick_default"
+    out = gu.product_segment(LATTICES[case], DEVICE, torch.float64).track(
+        gu.product_beam(beam, DEVICE, torch.float64)
+    )
+    expected = gu.beam_dict(CONSISTENCY, f"{case}.expected")
+    rows = slice(None, None, ROW_STRIDE)
+    assert torch.allclose(out.particles.cpu()[rows], expected["particles"])
+    assert out.survival_probabilities is not None and out.particles.shape == (3000, 7)
+
+
+def test_float32_track_is_at_least_as_close_to_float64_truth_as_the_reference():
+    """Our float32 kick vs the reference's float32 kick, both measured against float64."""
+    _, beam, out = _track_case("kick16", torch.float32)
+    rows = slice(None, None, 4)
+    truth = gu.beam_dict(SPACE_CHARGE, "kick16.f64")["particles"]
+    ref32 = gu.beam_dict(SPACE_CHARGE, "kick16.f32")["particles"]
+    ours = out.particles.cpu().double()[rows]
+    for col in (1, 3, 5):
+        ours_err = (ours[:, col] - truth[:, col]).abs().max()
+        ref_err = (ref32[:, col] - truth[:, col]).abs().max()
+        assert ours_err <= 1.5 * ref_err + 1e-12, (col, float(ours_err), float(ref_err))
+
+
+def test_input_not_mutated_and_passthrough():
+    import cheetah_b200 as cb
+
+    beam = cb.ParticleBeam.from_parameters(
+        num_particles=20_000, total_charge=torch.tensor(1e-9), device=DEVICE, dtype=torch.float32
+    )
+    before = beam.particles.clone()
+    kick = cb.SpaceChargeKick(effect_length=torch.tensor(1.0, device=DEVICE))
+    out = kick.track(beam)
+    assert torch.equal(beam.particles, before)  # tests/test_space_charge_kick.py:171-199
+    assert out.particle_charges is beam.particle_charges
+    assert out.energy is beam.energy and out.s is beam.s
+    assert not torch.equal(out.particles[:, 1], beam.particles[:, 1])
+    with pytest.raises(AssertionError, match="only supported for `ParticleBeam`"):
+        kick.track(cb.ParameterBeam(mu=torch.zeros(7, device=DEVICE), cov=torch.zeros(7, 7, device=DEVICE),
+                                    energy=torch.tensor(1e8, device=DEVICE)))
+    with pytest.raises(NotImplementedError, match="power-of-two"):
+        cb.SpaceChargeKick(effect_length=torch.tensor(1.0, device=DEVICE), grid_shape=(30, 32, 32)).track(beam)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_cloud_in_cell_matches_reference_and_histogram(dtype):
+    from cheetah_b200.space_charge import cloud_in_cell_charge_deposition
+
+    data = gu.load_npz("cloud_in_cell.npz")
+    tag = "f64" if dtype == torch.float64 else "f32"
+    grid = cloud_in_cell_charge_deposition(
+        gu.tensor(data["positions"], dtype).to(DEVICE), tuple(int(b) for b in data["bins"]),
+        gu.tensor(data["extent"], dtype).to(DEVICE), gu.tensor(data["charges"], dtype).to(DEVICE),
+    )
+    expected = gu.tensor(data[f"grid.{tag}"], dtype)
+    assert grid.shape == expected.shape
+    assert rel_err(grid, expected) < (1e-13 if dtype == torch.float64 else 2e-6)
+
+    # particles on bin centres: exactly the histogram (tests/test_cloud_in_cell.py:98-150)
+    g = torch.Generator().manual_seed(0)
+    bins = (8, 4, 16)
+    idx = torch.stack([torch.randint(0, b, (5000,), generator=g) for b in bins], dim=-1)
+    extent = torch.tensor([[-1.0, 1.0], [0.0, 2.0], [-4.0, 4.0]], dtype=dtype)
+    width = (extent[:, 1] - extent[:, 0]) / torch.tensor(bins, dtype=dtype)
+    positions = extent[:, 0] + (idx.to(dtype) + 0.5) * width
+    hist = torch.histogramdd(positions.double(), bins=list(bins), range=extent.double().flatten().tolist()).hist
+    grid = cloud_in_cell_charge_deposition(positions.to(DEVICE), bins, extent.to(DEVICE))
+    assert torch.equal(grid.cpu().double(), hist)
+    # particles outside the extent contribute nothing (tests/test_cloud_in_cell.py:244-259)
+    outside = torch.tensor([[0.0, 1.0, 0.0], [5.0, 1.0, 0.0], [0.0, -1.0, 0.0], [0.5, 0.5, 1.0]], dtype=dtype)
+    grid = cloud_in_cell_charge_deposition(outside.to(DEVICE), bins, extent.to(DEVICE))
+    assert float(grid.sum()) == 2.0
