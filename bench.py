@@ -282,6 +282,15 @@ def main() -> None:
     algorithmic_bytes = per_rank * args.particles * 32 + args.particles * 32
     mean_apply_ms = sum(apply_ms) / len(apply_ms)
     achieved = algorithmic_bytes / (mean_apply_ms * 1e-3) / 1e9
+    traffic, traffic_note = None, None
+    traffic_path = REPO / "profiles" / "apply_maps_traffic.json"
+    if traffic_path.exists():
+        # dram__bytes_read + dram__bytes_write of one `ncu --set full` capture of the same kernel
+        # at 256 settings (a 4096-setting launch writes 131 GB, too much for ncu's replay
+        # save/restore), scaled per (particle, setting) to this launch
+        per_unit = json.loads(traffic_path.read_text())["dram_bytes_per_particle_setting"]
+        traffic = per_unit * per_rank * args.particles
+        traffic_note = "ncu dram bytes at 256 settings, scaled per (particle, setting)"
     roofline = {
         "kernel": "apply_maps_kernel<float,4,256,true> (ch_apply_maps)",
         "bound": "hbm",
@@ -290,7 +299,8 @@ def main() -> None:
         "peak_kind": peak_kind,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_note": traffic_note,
         "algorithmic_bytes_per_launch": algorithmic_bytes,
         "mean_launch_ms": mean_apply_ms,
         "launches_timed": len(apply_ms),

@@ -1,0 +1,75 @@
+"""The lowering is duck-typed: it must accept the REFERENCE's own element objects
+(INTEGRATION.md section 2).  Runs only where /root/reference exists (the build container)."""
+
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+REF = Path("/root/reference")
+REPO = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.skipif(not REF.exists(), reason="reference checkout not available")
+
+
+@pytest.fixture(scope="module")
+def cheetah():
+    sys.path.insert(0, str(REPO / "oracle" / "refshim"))
+    sys.path.insert(0, str(REF))
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import cheetah as reference
+    yield reference
+    sys.path.remove(str(REF))
+    sys.path.remove(str(REPO / "oracle" / "refshim"))
+
+
+def test_reference_ares_lowers_to_the_same_program(cheetah):
+    from cheetah_b200 import lowering
+
+    from . import golden_utils as gu
+
+    reference_segment = cheetah.Segment.from_lattice_json(
+        str(REF / "docs" / "examples" / "ARESlatticeStage3v1_9.json")
+    )
+    reference_segment.AREAMQZM1.k1 = torch.tensor([8.2, 1.0])
+    mirror_description = gu.ares_lattice(torch.float32)
+    gu.set_attr(mirror_description, "AREAMQZM1", "k1", torch.tensor([8.2, 1.0]))
+    mirror_segment = gu.product_segment(mirror_description, "cpu", torch.float32)
+
+    a = lowering.lower([reference_segment], torch.device("cpu"))
+    b = lowering.lower([mirror_segment], torch.device("cpu"))
+    assert [op.opcode for op in a.ops] == [op.opcode for op in b.ops]
+    assert [op.flags for op in a.ops] == [op.flags for op in b.ops]
+    assert len(a.ops) == 195
+    assert [type(s).__name__ for s in a.stages] == [type(s).__name__ for s in b.stages]
+    sa, sb = a.stages[0], b.stages[0]
+    assert (sa.n_apertures, sa.lattice_shape, sa.length_shape) == (3, (2,), ())
+    assert (sb.n_apertures, sb.lattice_shape, sb.length_shape) == (3, (2,), ())
+    for op_a, op_b in zip(a.ops, b.ops):
+        for (ta, stride_a, off_a), (tb, stride_b, off_b) in zip(op_a.resolved, op_b.resolved):
+            assert stride_a == stride_b and off_a == off_b
+            assert torch.equal(ta.double(), tb.double())
+
+
+def test_reference_space_charge_and_superimposed_lower(cheetah):
+    from cheetah_b200 import lowering
+
+    t = torch.tensor
+    elements = [
+        cheetah.Superimposed(
+            base_element=cheetah.Quadrupole(length=t(1.0), k1=t(0.5)),
+            superimposed_element=cheetah.BPM(),
+        ),
+        cheetah.SpaceChargeKick(effect_length=t(1.0)),
+        cheetah.RBend(length=t(1.0), angle=t(0.2), rbend_e1=t(0.05)),
+        cheetah.Cavity(length=t(1.0), voltage=t(1e6)),
+    ]
+    program = lowering.lower(elements, torch.device("cpu"))
+    kinds = [getattr(s, "kind", "linear") for s in program.stages]
+    assert kinds == ["linear", "space_charge", "linear", "unsupported"]
+    assert len(program.ops) == 4  # two half quadrupoles + BPM, then the bend
+    dipole = program.ops[3]
+    assert torch.allclose(dipole.resolved[3][0], t(0.15))  # e1 = rbend_e1 + angle / 2

@@ -1,0 +1,83 @@
+"""World-size-2 gloo tests of the multi-GPU plumbing (host logic only, no compute)."""
+
+import os
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def test_shard_bounds_cover_the_batch_exactly():
+    from cheetah_b200.sharding import shard_bounds
+
+    for n in (1, 7, 4096, 4097):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank: int, world: int, port: int, results) -> None:
+    sys.path.insert(0, str(REPO))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cheetah_b200 as cb
+    import workloads
+    from cheetah_b200 import lowering, sharding
+
+    n_settings = 10
+    # every rank draws the FULL batch from the same seed and keeps its own contiguous slice
+    begin, end = sharding.shard_bounds(n_settings, rank, world)
+    description = workloads.ares_config3(n_settings, torch.float32, begin, end)
+    segment = workloads.product_segment(description, "cpu", torch.float32)
+
+    # rank 0's beam is broadcast once at set-up: afterwards all ranks hold identical particles
+    torch.manual_seed(100 + rank)
+    beam = cb.ParticleBeam.from_parameters(num_particles=256, dtype=torch.float32)
+    nbytes = sharding.broadcast_module(beam)
+    gathered = [torch.zeros_like(beam.particles) for _ in range(world)]
+    dist.all_gather(gathered, beam.particles)
+
+    program = lowering.lower(list(segment.elements), torch.device("cpu"))
+    section = program.stages[0]
+    k1 = segment.AREAMQZM1.k1.clone()
+    all_k1 = [torch.zeros(end - begin) for _ in range(world)] if (n_settings % world == 0) else None
+    if all_k1 is not None:
+        dist.all_gather(all_k1, k1)
+    results[rank] = {
+        "bounds": (begin, end),
+        "lattice_shape": section.lattice_shape,
+        "n_stages": len(program.stages),
+        "beam_equal": all(torch.equal(g, gathered[0]) for g in gathered),
+        "broadcast_bytes": nbytes,
+        "k1": torch.cat(all_k1) if all_k1 is not None else k1,
+    }
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_settings_and_share_the_beam():
+    import workloads
+
+    world = 2
+    manager = mp.Manager()
+    results = manager.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+    assert results[0]["bounds"] == (0, 5) and results[1]["bounds"] == (5, 10)
+    for rank in range(world):
+        assert results[rank]["lattice_shape"] == (5,)
+        assert results[rank]["n_stages"] == 1
+        assert results[rank]["beam_equal"]
+        assert results[rank]["broadcast_bytes"] > 256 * 7 * 4
+    # the shards concatenate to the single-process batch: no setting lost or duplicated
+    full = workloads.ares_config3(10, torch.float32)
+    k1_full = next(e for e in full if e["name"] == "AREAMQZM1")["k1"]
+    assert torch.equal(results[0]["k1"], k1_full)

@@ -1,0 +1,47 @@
+"""Summarise an .ncu-rep (read with `ncu -i`, no GPU needed) into a small CSV-like text."""
+import csv
+import io
+import subprocess
+import sys
+
+METRICS = [
+    "gpu__time_duration.sum",
+    "dram__bytes_read.sum",
+    "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.sum",
+    "smsp__inst_executed.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread",
+    "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem",
+    "launch__waves_per_multiprocessor",
+    "launch__grid_size",
+    "launch__block_size",
+    "sm__cycles_elapsed.avg.per_second",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "lts__t_sectors_op_red.sum",
+    "lts__t_sectors_op_atom.sum",
+]
+
+
+def main(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    header, units = rows[0], rows[1]
+    for row in rows[2:]:
+        print("kernel:", row[header.index("Kernel Name")])
+        for metric in METRICS:
+            if metric in header:
+                i = header.index(metric)
+                print(f"  {metric:70s} {row[i]:>20s} {units[i]}")
+        print()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
