@@ -155,6 +155,8 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
+    torch.set_num_threads(os.cpu_count() or 1)
     steps = max(1, min(args.steps, 5))
     warmup = max(1, min(args.warmup, 2))
     base = time_cpu_oracle(args.settings, args.cpu_sample_settings, args.particles, steps, warmup)
@@ -178,7 +180,7 @@ def run_reference_arm(args) -> None:
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, per_rank: int) -> dict:
@@ -198,6 +200,18 @@ def workload_config(args, per_rank: int) -> dict:
 
 
 # ----------------------------------------------------------------------------------------
+def emit(line: dict) -> None:
+    """Write the one JSON line to the REAL stdout (fd saved before libraries could print)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Libraries (NCCL prints its version banner) write to fd 1; keep stdout clean for the JSON line
+# by pointing fd 1 at stderr for the rest of the process.
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main() -> None:
     args = parse_args()
     if args.impl == "reference":
@@ -377,8 +391,9 @@ def main() -> None:
             "mean_survival": survival_mean,
             "setup_broadcast_bytes": setup_bytes,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
