@@ -111,12 +111,16 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
     ),
+    "ch_sc_green_spectrum": (
+        c_int32,
+        [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
+    ),
     "ch_sc_poisson_solve": (
         c_int32,
         [
             c_void_p, c_void_p, c_void_p, c_int64,
             c_int32, c_int32, c_int32, c_int32,
-            c_void_p, c_void_p, c_void_p, c_void_p,
+            c_void_p, c_void_p, c_void_p,
         ],
     ),
     "ch_sc_field": (

@@ -390,11 +390,14 @@ fft_c2r_z_kernel(const typename fft::Complex<T>::type* __restrict__ in, int in_n
 // values so that every global access is a contiguous run.
 //   MODE 0: forward, in place: in_len valid inputs (rest zero), `len` outputs
 //   MODE 1: inverse, in place: `len` inputs, out_len outputs
-//   MODE 2: forward, multiply by `green` (same layout), inverse: in_len in, out_len out
+//   MODE 2: forward, multiply by the Green spectrum, inverse: in_len in, out_len out.  The
+//           spectrum of the mirrored (even) Green array is real and even in every index, so it
+//           is stored compactly as green[B][len/2 + 1][green_ny][green_kz] (x pass only:
+//           inner = ky * green_kz + kz, ky in [0, 2 (green_ny - 1)))
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kFftThreads)
 fft_strided_kernel(typename fft::Complex<T>::type* __restrict__ data,
-                   const typename fft::Complex<T>::type* __restrict__ green, int len, int log2_len,
+                   const T* __restrict__ green, int green_ny, int green_kz, int len, int log2_len,
                    int in_len, int out_len, int64_t axis_stride, int inner_count,
                    int64_t outer_stride, int64_t batch_stride) {
   using C = typename fft::Complex<T>::type;
@@ -419,12 +422,20 @@ fft_strided_kernel(typename fft::Complex<T>::type* __restrict__ data,
 
   if (MODE == 0 || MODE == 2) fft::forward_dif(v, tw, len, log2_len, kColumns, pitch);
   if (MODE == 2) {
-    const C* g0 = green + base + inner0;
+    const int64_t plane = static_cast<int64_t>(green_ny) * green_kz;
+    const T* g0 = green + blockIdx.z * (len / 2 + 1) * plane;
+    const int full_ny = 2 * (green_ny - 1);
     for (int t = threadIdx.x; t < kColumns * len; t += kFftThreads) {
       const int k = t / kColumns, c = t - k * kColumns;
       if (c < columns) {
+        const int inner = inner0 + c;
+        const int ky = inner / green_kz, kz = inner - ky * green_kz;
+        const int kx_even = k <= len / 2 ? k : len - k;
+        const int ky_even = ky <= full_ny / 2 ? ky : full_ny - ky;
+        const T g = g0[kx_even * plane + ky_even * green_kz + kz];
         C* slot = &v[c * pitch + fft::bit_reverse(k, log2_len)];
-        *slot = fft::cmul(*slot, g0[k * axis_stride + c]);
+        slot->x *= g;
+        slot->y *= g;
       }
     }
     __syncthreads();
@@ -437,6 +448,79 @@ fft_strided_kernel(typename fft::Complex<T>::type* __restrict__ data,
     if (c >= columns) continue;
     const int slot = (MODE == 0) ? fft::bit_reverse(i, log2_len) : i;
     col0[i * axis_stride + c] = v[c * pitch + slot];
+  }
+}
+
+
+// Transform of real EVEN sequences (the mirrored Green function, space_charge_kick.py:247-289):
+// the column g[0..n) stands for the length-2n sequence g[0..n), 0, g[n-1..1]; its DFT is real
+// and even, so only outputs k = 0..n are stored.  Two columns are packed as real and imaginary
+// part of one complex transform (both spectra are real, so they separate for free).
+// Column c -> (outer, inner) = divmod(c, inner_count); element i of the column lives at
+//   outer * outer_stride + inner + i * axis_stride      (input and output each have their own)
+// With FROM_LATTICE the input is the 8-corner difference of the antiderivative lattice
+// (:195-236) evaluated on the fly (z pass: outer = x * ny + y, axis = z).
+template <typename T, bool FROM_LATTICE>
+__global__ void __launch_bounds__(kFftThreads)
+fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, int len,
+                     int log2_len, int total_columns, int inner_count, int64_t in_outer_stride,
+                     int64_t in_axis_stride, int64_t in_batch_stride, int64_t out_outer_stride,
+                     int64_t out_axis_stride, int64_t out_batch_stride, int lattice_ny,
+                     int lattice_nz) {
+  using C = typename fft::Complex<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* v = reinterpret_cast<C*>(smem_raw);
+  const int pitch = len + 1;
+  constexpr int kPairs = kColumns / 2;
+  C* tw = v + kPairs * pitch;
+  const int c0 = blockIdx.x * kColumns;
+  const int columns = min(kColumns, total_columns - c0);
+  const bool axis_contiguous = in_axis_stride == 1;
+
+  fft::fill_twiddles(tw, len);
+  for (int t = threadIdx.x; t < kColumns * n; t += kFftThreads) {
+    // fastest index follows the contiguous direction of the input
+    const int c = axis_contiguous ? t / n : t % kColumns;
+    const int i = axis_contiguous ? t - c * n : t / kColumns;
+    T value = T(0);
+    if (c < columns) {
+      const int col = c0 + c;
+      const int outer = col / inner_count, inner = col - outer * inner_count;
+      if (FROM_LATTICE) {
+        const double* f = static_cast<const double*>(in) + blockIdx.y * in_batch_stride;
+        const int x = outer / lattice_ny, y = outer - x * lattice_ny;
+        const int sy = lattice_nz + 1, sx = (lattice_ny + 1) * (lattice_nz + 1);
+        const double* q = f + static_cast<int64_t>(x) * sx + y * sy + i;
+        value = static_cast<T>(q[sx + sy + 1] - q[sy + 1] - q[sx + 1] - q[sx + sy] + q[sx] +
+                               q[sy] + q[1] - q[0]);
+      } else {
+        const T* src = static_cast<const T*>(in) + blockIdx.y * in_batch_stride;
+        value = src[outer * in_outer_stride + inner + i * in_axis_stride];
+      }
+    }
+    // even extension: position i and its mirror len - i (position n stays zero)
+    C* column = v + (c >> 1) * pitch;
+    if (c & 1) {
+      column[i].y = value;
+      if (i > 0) column[len - i].y = value;
+    } else {
+      column[i].x = value;
+      if (i > 0) column[len - i].x = value;
+    }
+  }
+  if (threadIdx.x < kPairs) v[threadIdx.x * pitch + n] = C{T(0), T(0)};
+  __syncthreads();
+  fft::forward_dif(v, tw, len, log2_len, kPairs, pitch);
+
+  T* dst = out + blockIdx.y * out_batch_stride;
+  for (int t = threadIdx.x; t < kColumns * (n + 1); t += kFftThreads) {
+    const int c = axis_contiguous ? t / (n + 1) : t % kColumns;
+    const int k = axis_contiguous ? t - c * (n + 1) : t / kColumns;
+    if (c >= columns) continue;
+    const int col = c0 + c;
+    const int outer = col / inner_count, inner = col - outer * inner_count;
+    const C z = v[(c >> 1) * pitch + fft::bit_reverse(k, log2_len)];
+    dst[outer * out_outer_stride + inner + k * out_axis_stride] = (c & 1) ? z.y : z.x;
   }
 }
 
@@ -630,10 +714,55 @@ unsigned blocks_for(int64_t work, int threads, int64_t cap = 148 * 16) {
   return static_cast<unsigned>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
+// Compact Green spectrum [B][nx+1][ny+1][nz+1] from the antiderivative lattice: three even
+// passes through two scratch arrays s1 [B][nx][ny][nz+1], s2 [B][nx][ny+1][nz+1].
 template <typename T>
-int poisson_solve(const T* rho, const T* green, const double* params, int64_t B, int nx, int ny,
-                  int nz, typename fft::Complex<T>::type* rs, typename fft::Complex<T>::type* gs,
-                  T* phi, cudaStream_t stream) {
+int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* s1, T* s2,
+                   T* spectrum, cudaStream_t stream) {
+  using C = typename fft::Complex<T>::type;
+  const int Kz = nz + 1;
+  const unsigned nb = static_cast<unsigned>(B);
+  auto smem = [&](int len) { return sizeof(C) * ((kColumns / 2) * (len + 1) + len / 2); };
+  const int64_t lattice_points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
+  {  // z: rows (x, y) of the lattice difference -> s1[x][y][kz]
+    auto k = fft_even_pass_kernel<T, true>;
+    if (allow_smem(k, smem(2 * nz)) != CH_OK) return CH_ECUDA;
+    const int columns = nx * ny;
+    dim3 grid((columns + kColumns - 1) / kColumns, nb);
+    k<<<grid, kFftThreads, smem(2 * nz), stream>>>(
+        lattice, s1, nz, 2 * nz, log2_exact(2 * nz), columns, 1, 0, 1, lattice_points, Kz, 1,
+        static_cast<int64_t>(nx) * ny * Kz, ny, nz);
+    CH_LAUNCH_CHECK();
+  }
+  {  // y: columns (x, kz) -> s2[x][ky][kz]
+    auto k = fft_even_pass_kernel<T, false>;
+    if (allow_smem(k, smem(2 * ny)) != CH_OK) return CH_ECUDA;
+    const int columns = nx * Kz;
+    dim3 grid((columns + kColumns - 1) / kColumns, nb);
+    k<<<grid, kFftThreads, smem(2 * ny), stream>>>(
+        s1, s2, ny, 2 * ny, log2_exact(2 * ny), columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
+        static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
+        static_cast<int64_t>(nx) * (ny + 1) * Kz, 0, 0);
+    CH_LAUNCH_CHECK();
+  }
+  {  // x: columns (ky, kz) -> spectrum[kx][ky][kz]
+    auto k = fft_even_pass_kernel<T, false>;
+    if (allow_smem(k, smem(2 * nx)) != CH_OK) return CH_ECUDA;
+    const int columns = (ny + 1) * Kz;
+    dim3 grid((columns + kColumns - 1) / kColumns, nb);
+    k<<<grid, kFftThreads, smem(2 * nx), stream>>>(
+        s2, spectrum, nx, 2 * nx, log2_exact(2 * nx), columns, columns, 0, columns,
+        static_cast<int64_t>(nx) * columns, 0, columns, static_cast<int64_t>(nx + 1) * columns, 0,
+        0);
+    CH_LAUNCH_CHECK();
+  }
+  return CH_OK;
+}
+
+template <typename T>
+int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* params, int64_t B,
+                  int nx, int ny, int nz, typename fft::Complex<T>::type* rs, T* phi,
+                  cudaStream_t stream) {
   using C = typename fft::Complex<T>::type;
   const int Nx = 2 * nx, Ny = 2 * ny, Nz = 2 * nz, Kz = Nz / 2 + 1;
   const int lx = log2_exact(Nx), ly = log2_exact(Ny), lz = log2_exact(Nz);
@@ -654,40 +783,18 @@ int poisson_solve(const T* rho, const T* green, const double* params, int64_t B,
     auto k = fft_strided_kernel<T, 0>;
     if (allow_smem(k, s_smem(Ny)) != CH_OK) return CH_ECUDA;
     dim3 grid((Kz + kColumns - 1) / kColumns, nx, nb);
-    k<<<grid, kFftThreads, s_smem(Ny), stream>>>(rs, nullptr, Ny, ly, ny, Ny, Kz, Kz,
+    k<<<grid, kFftThreads, s_smem(Ny), stream>>>(rs, nullptr, 0, 0, Ny, ly, ny, Ny, Kz, Kz,
                                                   static_cast<int64_t>(Ny) * Kz, spectrum);
     CH_LAUNCH_CHECK();
   }
-  // ---- Green function: full z, y, x passes --------------------------------------------
-  {
-    auto k = fft_r2c_z_kernel<T>;
-    dim3 grid((Nx * Ny + 2 * kRowPairs - 1) / (2 * kRowPairs), nb);
-    k<<<grid, kFftThreads, z_smem(Nz), stream>>>(green, Nx, Ny, Nz, Nz, lz, Nx, Ny, gs);
-    CH_LAUNCH_CHECK();
-  }
-  {
-    auto k = fft_strided_kernel<T, 0>;
-    dim3 grid((Kz + kColumns - 1) / kColumns, Nx, nb);
-    k<<<grid, kFftThreads, s_smem(Ny), stream>>>(gs, nullptr, Ny, ly, Ny, Ny, Kz, Kz,
-                                                  static_cast<int64_t>(Ny) * Kz, spectrum);
-    CH_LAUNCH_CHECK();
-  }
-  {
-    auto k = fft_strided_kernel<T, 0>;
-    if (allow_smem(k, s_smem(Nx)) != CH_OK) return CH_ECUDA;
-    const int inner = Ny * Kz;
-    dim3 grid((inner + kColumns - 1) / kColumns, 1, nb);
-    k<<<grid, kFftThreads, s_smem(Nx), stream>>>(gs, nullptr, Nx, lx, Nx, Nx, inner, inner, 0,
-                                                  spectrum);
-    CH_LAUNCH_CHECK();
-  }
-  // ---- x: forward . multiply . inverse, fused; only x < nx is stored --------------------
+  // ---- x: forward . multiply by the Green spectrum . inverse, fused; only x < nx stored ----
   {
     auto k = fft_strided_kernel<T, 2>;
     if (allow_smem(k, s_smem(Nx)) != CH_OK) return CH_ECUDA;
     const int inner = Ny * Kz;
     dim3 grid((inner + kColumns - 1) / kColumns, 1, nb);
-    k<<<grid, kFftThreads, s_smem(Nx), stream>>>(rs, gs, Nx, lx, nx, nx, inner, inner, 0, spectrum);
+    k<<<grid, kFftThreads, s_smem(Nx), stream>>>(rs, green_spectrum_compact, ny + 1, Kz, Nx, lx,
+                                                  nx, nx, inner, inner, 0, spectrum);
     CH_LAUNCH_CHECK();
   }
   // ---- inverse y (keep y < ny) and inverse z (keep z < nz) -------------------------------
@@ -695,7 +802,7 @@ int poisson_solve(const T* rho, const T* green, const double* params, int64_t B,
     auto k = fft_strided_kernel<T, 1>;
     if (allow_smem(k, s_smem(Ny)) != CH_OK) return CH_ECUDA;
     dim3 grid((Kz + kColumns - 1) / kColumns, nx, nb);
-    k<<<grid, kFftThreads, s_smem(Ny), stream>>>(rs, nullptr, Ny, ly, Ny, ny, Kz, Kz,
+    k<<<grid, kFftThreads, s_smem(Ny), stream>>>(rs, nullptr, 0, 0, Ny, ly, Ny, ny, Kz, Kz,
                                                   static_cast<int64_t>(Ny) * Kz, spectrum);
     CH_LAUNCH_CHECK();
   }
@@ -828,13 +935,14 @@ extern "C" int ch_sc_green_function(const double* params, int64_t n_beams, int32
                                     int32_t nz, int32_t dtype, double* lattice, void* green,
                                     void* stream) {
   CH_SC_COMMON_CHECKS("ch_sc_green_function");
-  CH_REQUIRE(params && lattice && green, "ch_sc_green_function: NULL pointer argument");
+  CH_REQUIRE(params && lattice, "ch_sc_green_function: NULL pointer argument");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_green_function: bad grid (%d, %d, %d)", nx, ny, nz);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
   dim3 grid_a(ch::blocks_for(points, 256), static_cast<unsigned>(n_beams));
   ch::sc_green_lattice_kernel<<<grid_a, 256, 0, s>>>(params, nx, ny, nz, lattice);
   CH_LAUNCH_CHECK();
+  if (green == nullptr) return CH_OK;  // the solver only needs the lattice
   dim3 grid_b(ch::blocks_for(static_cast<int64_t>(8) * nx * ny * nz, 256, 148 * 32),
               static_cast<unsigned>(n_beams));
   if (dtype == CH_F32)
@@ -847,25 +955,41 @@ extern "C" int ch_sc_green_function(const double* params, int64_t n_beams, int32
   return CH_OK;
 }
 
-extern "C" int ch_sc_poisson_solve(const void* rho, const void* green, const double* params,
-                                   int64_t n_beams, int32_t nx, int32_t ny, int32_t nz,
-                                   int32_t dtype, void* rho_spectrum, void* green_spectrum,
-                                   void* phi, void* stream) {
+extern "C" int ch_sc_green_spectrum(const double* lattice, int64_t n_beams, int32_t nx, int32_t ny,
+                                    int32_t nz, int32_t dtype, void* scratch, void* spectrum,
+                                    void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_green_spectrum");
+  CH_REQUIRE(lattice && scratch && spectrum, "ch_sc_green_spectrum: NULL pointer argument");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_green_spectrum: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t s1 = n_beams * static_cast<int64_t>(nx) * ny * (nz + 1);
+  if (dtype == CH_F32) {
+    float* base = static_cast<float*>(scratch);
+    return ch::green_spectrum<float>(lattice, n_beams, nx, ny, nz, base, base + s1,
+                                     static_cast<float*>(spectrum), s);
+  }
+  double* base = static_cast<double*>(scratch);
+  return ch::green_spectrum<double>(lattice, n_beams, nx, ny, nz, base, base + s1,
+                                    static_cast<double*>(spectrum), s);
+}
+
+extern "C" int ch_sc_poisson_solve(const void* rho, const void* green_spectrum,
+                                   const double* params, int64_t n_beams, int32_t nx, int32_t ny,
+                                   int32_t nz, int32_t dtype, void* rho_spectrum, void* phi,
+                                   void* stream) {
   CH_SC_COMMON_CHECKS("ch_sc_poisson_solve");
-  CH_REQUIRE(rho && green && params && rho_spectrum && green_spectrum && phi,
+  CH_REQUIRE(rho && green_spectrum && params && rho_spectrum && phi,
              "ch_sc_poisson_solve: NULL pointer argument");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_poisson_solve: bad grid (%d, %d, %d)", nx, ny, nz);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == CH_F32)
     return ch::poisson_solve<float>(static_cast<const float*>(rho),
-                                    static_cast<const float*>(green), params, n_beams, nx, ny, nz,
-                                    static_cast<float2*>(rho_spectrum),
-                                    static_cast<float2*>(green_spectrum), static_cast<float*>(phi),
-                                    s);
+                                    static_cast<const float*>(green_spectrum), params, n_beams,
+                                    nx, ny, nz, static_cast<float2*>(rho_spectrum),
+                                    static_cast<float*>(phi), s);
   return ch::poisson_solve<double>(static_cast<const double*>(rho),
-                                   static_cast<const double*>(green), params, n_beams, nx, ny, nz,
-                                   static_cast<double2*>(rho_spectrum),
-                                   static_cast<double2*>(green_spectrum),
+                                   static_cast<const double*>(green_spectrum), params, n_beams, nx,
+                                   ny, nz, static_cast<double2*>(rho_spectrum),
                                    static_cast<double*>(phi), s);
 }
 

@@ -45,9 +45,14 @@ class Workspace:
         self.lattice = torch.empty(
             (n_beams, nx + 1, ny + 1, nz + 1), dtype=torch.float64, device=device
         )
-        self.green = torch.empty((n_beams, 2 * nx, 2 * ny, 2 * nz), dtype=dtype, device=device)
+        self.green = None  # the mirrored (2n)^3 array is only built for the parity tests
+        self.green_scratch = torch.empty(
+            (n_beams * (nx * ny * (nz + 1) + nx * (ny + 1) * (nz + 1)),), dtype=dtype, device=device
+        )
+        self.green_spectrum = torch.empty(
+            (n_beams, nx + 1, ny + 1, nz + 1), dtype=dtype, device=device
+        )
         self.rho_spectrum = torch.empty(spectrum, dtype=cdtype, device=device)
-        self.green_spectrum = torch.empty(spectrum, dtype=cdtype, device=device)
         self.phi = torch.empty((n_beams, nx, ny, nz), dtype=dtype, device=device)
         self.field = torch.empty((n_beams, nx, ny, nz, 4), dtype=dtype, device=device)
 
@@ -99,13 +104,17 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
         _capi.check(lib.ch_sc_deposit(
             p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
             ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho.data_ptr(), stream))
+        if want_intermediates:
+            ws.green = torch.empty((n_beams, 2 * nx, 2 * ny, 2 * nz), dtype=dtype, device=device)
         _capi.check(lib.ch_sc_green_function(
             ws.params.data_ptr(), n_beams, nx, ny, nz, code, ws.lattice.data_ptr(),
-            ws.green.data_ptr(), stream))
+            _capi.ptr(ws.green), stream))
+        _capi.check(lib.ch_sc_green_spectrum(
+            ws.lattice.data_ptr(), n_beams, nx, ny, nz, code, ws.green_scratch.data_ptr(),
+            ws.green_spectrum.data_ptr(), stream))
         _capi.check(lib.ch_sc_poisson_solve(
-            ws.rho.data_ptr(), ws.green.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz,
-            code, ws.rho_spectrum.data_ptr(), ws.green_spectrum.data_ptr(), ws.phi.data_ptr(),
-            stream))
+            ws.rho.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
+            nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))
         _capi.check(lib.ch_sc_field(
             ws.phi.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
             ws.field.data_ptr(), stream))

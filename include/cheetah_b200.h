@@ -155,7 +155,7 @@ int ch_apply_maps(const void* particles_in, int64_t particle_stride, const int32
 /* space charge ----------------------------------------------------------------------- */
 /* One SpaceChargeKick (cheetah/accelerator/space_charge_kick.py:477-586) is the sequence
  *   ch_sc_beam_moments -> ch_sc_grid_params -> ch_sc_deposit -> ch_sc_green_function ->
- *   ch_sc_poisson_solve -> ch_sc_field -> ch_sc_gather_kick
+ *   ch_sc_green_spectrum -> ch_sc_poisson_solve -> ch_sc_field -> ch_sc_gather_kick
  * over B independent beams (the flattened vector dims, space_charge_kick.py:493-528).
  * All per-beam scalars live on the device in fp64 tables so that no step synchronises
  * with the host:
@@ -212,23 +212,33 @@ int ch_cic_deposit3d(const void* positions, const void* extent, const void* char
                      int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                      void* grid, void* stream);
 
-/* Integrated Green function on the doubled grid: _integrated_potential +
- * _integrated_green_function (space_charge_kick.py:103-123, :163-291).  The antiderivative
- * is evaluated ONCE per half-shifted lattice point in fp64 (lattice [B][(nx+1)(ny+1)(nz+1)]
- * doubles of scratch) and differenced, then mirrored into green [B][2nx][2ny][2nz] with
- * plane index n of every axis left zero, as the reference does.  d_tau is scaled by gamma. */
+/* Integrated Green function: _integrated_potential + _integrated_green_function
+ * (space_charge_kick.py:103-123, :163-291).  The antiderivative is evaluated ONCE per
+ * half-shifted lattice point in fp64 (lattice [B][(nx+1)(ny+1)(nz+1)] doubles; the reference
+ * evaluates it 8 n^3 times).  If `green` is not NULL the differenced, mirrored array
+ * [B][2nx][2ny][2nz] of the reference is also written (plane n of every axis zero) -- used by
+ * the parity tests; the solver itself only needs the lattice.  d_tau is scaled by gamma.   */
 int ch_sc_green_function(const double* params, int64_t n_beams,
                          int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                          double* lattice, void* green, void* stream);
 
+/* rfftn of the mirrored Green array without ever building it: the array is even in every axis,
+ * so its spectrum is real and even and is stored compactly as spectrum [B][nx+1][ny+1][nz+1]
+ * (3 passes of packed real-even FFTs, ~4x less work than a general rfftn).
+ * scratch: B * (nx*ny*(nz+1) + nx*(ny+1)*(nz+1)) scalars of the beam dtype.                 */
+int ch_sc_green_spectrum(const double* lattice, int64_t n_beams,
+                         int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                         void* scratch, void* spectrum, void* stream);
+
 /* phi = irfftn(rfftn(rho_padded) * rfftn(green)) / (4 pi eps0 * cell volume), cropped to
  * the physical octant: _solve_poisson_equation (space_charge_kick.py:293-322).  Hand-written
  * shared-memory FFT passes (no cuFFT): z real<->complex with two rows packed per transform,
- * y and x strided passes; the x pass fuses forward FFT, the multiply by the Green spectrum
- * and the inverse FFT.  rho_spectrum / green_spectrum: [B][2nx][2ny][nz+1] complex scratch. */
-int ch_sc_poisson_solve(const void* rho, const void* green, const double* params,
+ * y and x strided passes; zero padding is never materialised; the x pass fuses forward FFT,
+ * the multiply by the compact Green spectrum and the inverse FFT.
+ * rho_spectrum: [B][2nx][2ny][nz+1] complex scratch.                                        */
+int ch_sc_poisson_solve(const void* rho, const void* green_spectrum, const double* params,
                         int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
-                        void* rho_spectrum, void* green_spectrum, void* phi, void* stream);
+                        void* rho_spectrum, void* phi, void* stream);
 
 /* -(1/gamma^2) grad(phi) by central differences, zero on the boundary cells:
  * _E_plus_vB_field (space_charge_kick.py:324-365).  field [B][nx*ny*nz][4] = (gx, gy, gz, 0). */
