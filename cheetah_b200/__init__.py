@@ -28,6 +28,8 @@ from .elements import (  # noqa: F401
     Undulator,
     VerticalCorrector,
 )
+from .graphs import GraphedTrack  # noqa: F401
+from .space_charge import cloud_in_cell_charge_deposition  # noqa: F401
 from .species import Species  # noqa: F401
 from .tracking import first_order_transfer_map, track  # noqa: F401
 

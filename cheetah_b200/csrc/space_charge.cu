@@ -30,32 +30,48 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 sc_moments_kernel(const T* __restrict__ particles, int64_t particle_stride,
                   const T* __restrict__ survival, int64_t survival_stride, int64_t n_particles,
-                  int per_cta, double* __restrict__ stats) {
+                  int bulk_in, double* __restrict__ stats) {
+  constexpr int P = 4, THREADS = 256, TP = P * THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  __shared__ uint64_t bar;
+  __shared__ double partial[8][8];
   const int64_t b = blockIdx.y;
   const T* p = particles + b * particle_stride;
   const T* w = survival ? survival + b * survival_stride : nullptr;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
+  const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
+  if (bulk_in && threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  cta_load_tile(tile, p + n0 * 7, count * 7, bulk_in != 0, &bar, phase);
+  // pilot = particle 0 of the beam: the sums are taken about it to avoid cancellation
   const double x0 = static_cast<double>(p[0]);
   const double y0 = static_cast<double>(p[2]);
   const double t0 = static_cast<double>(p[4]);
-  const int64_t begin = static_cast<int64_t>(blockIdx.x) * per_cta;
-  const int64_t end = min(n_particles, begin + per_cta);
 
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    const double wi = w ? static_cast<double>(w[i]) : 1.0;
-    const double dx = static_cast<double>(p[i * 7 + 0]) - x0;
-    const double dy = static_cast<double>(p[i * 7 + 2]) - y0;
-    const double dt = static_cast<double>(p[i * 7 + 4]) - t0;
-    acc[0] += wi;
-    acc[1] = fma(wi, wi, acc[1]);
-    acc[2] = fma(wi, dx, acc[2]);
-    acc[3] = fma(wi, dy, acc[3]);
-    acc[4] = fma(wi, dt, acc[4]);
-    acc[5] = fma(wi * dx, dx, acc[5]);
-    acc[6] = fma(wi * dy, dy, acc[6]);
-    acc[7] = fma(wi * dt, dt, acc[7]);
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int local = threadIdx.x + k * THREADS;
+    if (local < count) {
+      const double wi = w ? static_cast<double>(w[n0 + local]) : 1.0;
+      const double dx = static_cast<double>(tile[local * 7 + 0]) - x0;
+      const double dy = static_cast<double>(tile[local * 7 + 2]) - y0;
+      const double dt = static_cast<double>(tile[local * 7 + 4]) - t0;
+      acc[0] += wi;
+      acc[1] = fma(wi, wi, acc[1]);
+      acc[2] = fma(wi, dx, acc[2]);
+      acc[3] = fma(wi, dy, acc[3]);
+      acc[4] = fma(wi, dt, acc[4]);
+      acc[5] = fma(wi * dx, dx, acc[5]);
+      acc[6] = fma(wi * dy, dy, acc[6]);
+      acc[7] = fma(wi * dt, dt, acc[7]);
+    }
   }
-  __shared__ double partial[8][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -129,6 +145,7 @@ __global__ void sc_grid_params_kernel(const double* __restrict__ stats, int64_t 
 // One axis of cloud_in_cell.py:275-362, in the beam dtype like the reference.
 template <typename T>
 struct AxisDeposit {
+  int base;        // unclamped lower corner index (floor of the bin-space position)
   int lo, hi;      // clamped corner indices
   T w_lo, w_hi;    // corner weights (0 when the corner is off-grid)
   bool inside;     // inclusive extent test
@@ -145,6 +162,7 @@ __device__ __forceinline__ AxisDeposit<T> deposit_axis(T pos, T left, T right, i
   // clamp before the int conversion so that far-away particles cannot overflow
   const T lim = static_cast<T>(bins + 1);
   const int qi = static_cast<int>(fmin(fmax(fl, -lim), lim));
+  a.base = qi;
   a.lo = min(max(qi, 0), bins - 1);
   a.hi = min(max(qi + 1, 0), bins - 1);
   a.w_lo = (qi >= 0 && qi < bins) ? T(1) - frac : T(0);
@@ -172,28 +190,80 @@ __device__ __forceinline__ void deposit_particle(T* __restrict__ grid, T x, T y,
       }
 }
 
+// Two adjacent cells along z in ONE L2 transaction (SASS REDG.E.ADD.F32x2): needs an 8-byte
+// aligned address, i.e. an even first index -- see the split-row layout below.
+__device__ __forceinline__ void add_pair(float* address, float a, float b) {
+  atomicAdd(reinterpret_cast<float2*>(address), make_float2(a, b));
+}
+__device__ __forceinline__ void add_pair(double* address, double a, double b) {
+  atomicAdd(address, a);
+  atomicAdd(address + 1, b);
+}
+
+// Space-charge deposit.  Each particle touches 4 (x, y) rows x 2 adjacent z cells.  The grid
+// is kept as SPLIT ROWS  rho[B][nx * ny][2][nz + 2]:  part 0 (A) receives the z pairs that
+// start at an even cell, part 1 (B) -- indexed by z + 1 -- those that start at an odd cell
+// (including -1), so every pair is 8-byte aligned and one vector RED serves two cells: 4 L2
+// atomics per particle instead of 8.  The logical grid is A[z] + B[z + 1]; the z pass of the
+// FFT sums the two parts while loading (ch_sc_poisson_solve).
 template <typename T>
 __global__ void __launch_bounds__(256)
 sc_deposit_kernel(const T* __restrict__ particles, int64_t particle_stride,
                   const T* __restrict__ charges, int64_t charge_stride,
                   const T* __restrict__ survival, int64_t survival_stride,
                   const double* __restrict__ params, int64_t n_particles, int nx, int ny, int nz,
-                  T* __restrict__ rho) {
+                  int bulk_in, T* __restrict__ rho) {
+  constexpr int P = 4, THREADS = 256, TP = P * THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  __shared__ uint64_t bar;
   const int64_t b = blockIdx.y;
   const double* prm = params + b * CH_SC_PARAMS;
   const T lo[3] = {-static_cast<T>(prm[0]), -static_cast<T>(prm[1]), -static_cast<T>(prm[2])};
   const T hi[3] = {static_cast<T>(prm[0]), static_cast<T>(prm[1]), static_cast<T>(prm[2])};
   const T minus_beta = -static_cast<T>(prm[7]);
-  const T* p = particles + b * particle_stride;
   const T* q = charges + b * charge_stride;
   const T* w = survival ? survival + b * survival_stride : nullptr;
-  T* grid = rho + b * static_cast<int64_t>(nx) * ny * nz;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_particles;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const T charge = w ? q[i] * w[i] : q[i];
+  const int part = nz + 2, pitch = 2 * part;
+  T* grid = rho + b * static_cast<int64_t>(nx) * ny * pitch;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
+  const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
+
+  if (bulk_in && threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  cta_load_tile(tile, particles + b * particle_stride + n0 * 7, count * 7, bulk_in != 0, &bar,
+                phase);
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int local = threadIdx.x + k * THREADS;
+    if (local >= count) continue;
+    const T charge = w ? q[n0 + local] * w[n0 + local] : q[n0 + local];
     // positions are (x, y, z = -beta tau): particle_beam.py:1335
-    deposit_particle(grid, p[i * 7 + 0], p[i * 7 + 2], p[i * 7 + 4] * minus_beta, charge, lo, hi,
-                     nx, ny, nz);
+    const AxisDeposit<T> ax = deposit_axis(tile[local * 7 + 0], lo[0], hi[0], nx);
+    const AxisDeposit<T> ay = deposit_axis(tile[local * 7 + 2], lo[1], hi[1], ny);
+    const T z = tile[local * 7 + 4] * minus_beta;
+    const AxisDeposit<T> az = deposit_axis(z, lo[2], hi[2], nz);
+    if (!(ax.inside && ay.inside && az.inside)) continue;  // charges * in_extent
+    // lower z index: in [-1, nz - 1] for a particle inside the extent (off-grid corners carry
+    // zero weight, so the clamp only guards against rounding at the very edge)
+    const int iz = min(max(az.base, -1), nz - 1);
+    const int ix[2] = {ax.lo, ax.hi}, iy[2] = {ay.lo, ay.hi};
+    const T wx[2] = {ax.w_lo, ax.w_hi}, wy[2] = {ay.w_lo, ay.w_hi};
+    // pair start: even -> part A at z, odd (or -1) -> part B at z + 1
+    const int slot = (iz & 1) ? part + iz + 1 : iz;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const T wxy = wx[a] * wy[c] * charge;
+        if (wxy != T(0))
+          add_pair(grid + static_cast<int64_t>(ix[a] * ny + iy[c]) * pitch + slot, wxy * az.w_lo,
+                   wxy * az.w_hi);
+      }
   }
 }
 
@@ -287,8 +357,9 @@ constexpr int kColumns = 16;   // strided passes: 16 adjacent columns per CTA
 // out: [B][2nx][2ny][len/2 + 1] complex, rows (x < in_x, y < in_y).
 template <typename T>
 __global__ void __launch_bounds__(kFftThreads)
-fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int len, int log2_len,
-                 int out_nx, int out_ny, typename fft::Complex<T>::type* __restrict__ out) {
+fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int in_pitch,
+                 int split_offset, int len, int log2_len, int out_nx, int out_ny,
+                 typename fft::Complex<T>::type* __restrict__ out) {
   using C = typename fft::Complex<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* v = reinterpret_cast<C*>(smem_raw);
@@ -297,7 +368,9 @@ fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int len
   const int rows = in_x * in_y;
   const int kz = len / 2 + 1;
   const int first_row = blockIdx.x * 2 * kRowPairs;
-  const T* src = in + b * static_cast<int64_t>(rows) * in_z;
+  // rows are `in_pitch` apart; with split_offset != 0 a row is stored as two parts (see
+  // sc_deposit_kernel) and the logical value is part A[i] + part B[i + 1]
+  const T* src = in + b * static_cast<int64_t>(rows) * in_pitch;
   C* dst = out + b * static_cast<int64_t>(out_nx) * out_ny * kz;
 
   fft::fill_twiddles(tw, len);
@@ -306,8 +379,14 @@ fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int len
     const int r0 = first_row + 2 * pair, r1 = r0 + 1;
     C value{T(0), T(0)};
     if (i < in_z) {
-      if (r0 < rows) value.x = src[static_cast<int64_t>(r0) * in_z + i];
-      if (r1 < rows) value.y = src[static_cast<int64_t>(r1) * in_z + i];
+      if (r0 < rows) {
+        const T* row = src + static_cast<int64_t>(r0) * in_pitch;
+        value.x = split_offset ? row[i] + row[split_offset + i + 1] : row[i];
+      }
+      if (r1 < rows) {
+        const T* row = src + static_cast<int64_t>(r1) * in_pitch;
+        value.y = split_offset ? row[i] + row[split_offset + i + 1] : row[i];
+      }
     }
     v[t] = value;
   }
@@ -776,7 +855,8 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
     auto k = fft_r2c_z_kernel<T>;
     if (allow_smem(k, z_smem(Nz)) != CH_OK) return CH_ECUDA;
     dim3 grid((nx * ny + 2 * kRowPairs - 1) / (2 * kRowPairs), nb);
-    k<<<grid, kFftThreads, z_smem(Nz), stream>>>(rho, nx, ny, nz, Nz, lz, Nx, Ny, rs);
+    k<<<grid, kFftThreads, z_smem(Nz), stream>>>(rho, nx, ny, nz, 2 * (nz + 2), nz + 2, Nz, lz, Nx,
+                                                  Ny, rs);
     CH_LAUNCH_CHECK();
   }
   {
@@ -835,17 +915,22 @@ extern "C" int ch_sc_beam_moments(const void* particles, int64_t particle_stride
   CH_REQUIRE(particles && stats && n_particles > 0, "ch_sc_beam_moments: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CH_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * CH_SC_STATS * n_beams, s));
-  const int per_cta = 8192;
-  dim3 grid(static_cast<unsigned>((n_particles + per_cta - 1) / per_cta),
-            static_cast<unsigned>(n_beams));
-  if (dtype == CH_F32)
-    ch::sc_moments_kernel<float><<<grid, 256, 0, s>>>(
+  dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(n_beams));
+  if (dtype == CH_F32) {
+    const int bulk = ch::bulk_compatible<float>(particles, n_particles, particle_stride);
+    ch::sc_moments_kernel<float><<<grid, 256, 1024 * 7 * sizeof(float), s>>>(
         static_cast<const float*>(particles), particle_stride, static_cast<const float*>(survival),
-        survival_stride, n_particles, per_cta, stats);
-  else
-    ch::sc_moments_kernel<double><<<grid, 256, 0, s>>>(
-        static_cast<const double*>(particles), particle_stride,
-        static_cast<const double*>(survival), survival_stride, n_particles, per_cta, stats);
+        survival_stride, n_particles, bulk, stats);
+  } else {
+    const int bulk = ch::bulk_compatible<double>(particles, n_particles, particle_stride);
+    auto kernel = ch::sc_moments_kernel<double>;
+    const size_t smem = 1024 * 7 * sizeof(double);
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    kernel<<<grid, 256, smem, s>>>(static_cast<const double*>(particles), particle_stride,
+                                   static_cast<const double*>(survival), survival_stride,
+                                   n_particles, bulk, stats);
+  }
   CH_LAUNCH_CHECK();
   return CH_OK;
 }
@@ -892,18 +977,25 @@ extern "C" int ch_sc_deposit(const void* particles, int64_t particle_stride, con
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_deposit: bad grid (%d, %d, %d)", nx, ny, nz);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t elem = dtype == CH_F32 ? 4 : 8;
-  CH_CUDA(cudaMemsetAsync(rho, 0, elem * nx * ny * nz * n_beams, s));
-  dim3 grid(ch::blocks_for(n_particles, 256), static_cast<unsigned>(n_beams));
-  if (dtype == CH_F32)
-    ch::sc_deposit_kernel<float><<<grid, 256, 0, s>>>(
+  CH_CUDA(cudaMemsetAsync(rho, 0, elem * nx * ny * 2 * (nz + 2) * n_beams, s));
+  dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(n_beams));
+  if (dtype == CH_F32) {
+    const int bulk = ch::bulk_compatible<float>(particles, n_particles, particle_stride);
+    ch::sc_deposit_kernel<float><<<grid, 256, 1024 * 7 * sizeof(float), s>>>(
         static_cast<const float*>(particles), particle_stride, static_cast<const float*>(charges),
         charge_stride, static_cast<const float*>(survival), survival_stride, params, n_particles,
-        nx, ny, nz, static_cast<float*>(rho));
-  else
-    ch::sc_deposit_kernel<double><<<grid, 256, 0, s>>>(
+        nx, ny, nz, bulk, static_cast<float*>(rho));
+  } else {
+    const int bulk = ch::bulk_compatible<double>(particles, n_particles, particle_stride);
+    auto kernel = ch::sc_deposit_kernel<double>;
+    const size_t smem = 1024 * 7 * sizeof(double);
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    kernel<<<grid, 256, smem, s>>>(
         static_cast<const double*>(particles), particle_stride,
         static_cast<const double*>(charges), charge_stride, static_cast<const double*>(survival),
-        survival_stride, params, n_particles, nx, ny, nz, static_cast<double*>(rho));
+        survival_stride, params, n_particles, nx, ny, nz, bulk, static_cast<double*>(rho));
+  }
   CH_LAUNCH_CHECK();
   return CH_OK;
 }

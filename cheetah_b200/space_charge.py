@@ -35,13 +35,19 @@ def _scalar_ref(tensor: torch.Tensor, vector_shape: tuple, dtype) -> tuple:
 class Workspace:
     """Scratch buffers of one kick (torch's caching allocator makes re-allocation cheap)."""
 
+    def charge_grid(self) -> torch.Tensor:
+        """Deposited charge per cell [B, nx, ny, nz] (merges the split rows)."""
+        nz = self.rho_split.shape[-1] - 2
+        return self.rho_split[..., 0, :nz] + self.rho_split[..., 1, 1 : nz + 1]
+
     def __init__(self, n_beams: int, grid_shape: tuple, dtype, device) -> None:
         nx, ny, nz = grid_shape
         cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
         spectrum = (n_beams, 2 * nx, 2 * ny, nz + 1)
         self.stats = torch.empty((n_beams, _capi.SC_STATS), dtype=torch.float64, device=device)
         self.params = torch.empty((n_beams, _capi.SC_PARAMS), dtype=torch.float64, device=device)
-        self.rho = torch.empty((n_beams, nx, ny, nz), dtype=dtype, device=device)
+        # split rows [.., 2, nz + 2] (see ch_sc_deposit); `charge_grid()` merges them
+        self.rho_split = torch.empty((n_beams, nx, ny, 2, nz + 2), dtype=dtype, device=device)
         self.lattice = torch.empty(
             (n_beams, nx + 1, ny + 1, nz + 1), dtype=torch.float64, device=device
         )
@@ -55,6 +61,21 @@ class Workspace:
         self.rho_spectrum = torch.empty(spectrum, dtype=cdtype, device=device)
         self.phi = torch.empty((n_beams, nx, ny, nz), dtype=dtype, device=device)
         self.field = torch.empty((n_beams, nx, ny, nz, 4), dtype=dtype, device=device)
+
+
+_workspace_cache: dict = {}
+
+
+def _workspace(n_beams: int, grid_shape: tuple, dtype, device) -> Workspace:
+    """One cached workspace per (batch, grid, dtype, device, stream): kicks on a stream are
+    ordered, so the scratch of the previous kick is free when the next one starts."""
+    key = (n_beams, tuple(grid_shape), dtype, device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspace_cache.get(key)
+    if ws is None:
+        if len(_workspace_cache) >= 4:
+            _workspace_cache.clear()
+        ws = _workspace_cache[key] = Workspace(n_beams, grid_shape, dtype, device)
+    return ws
 
 
 def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, grid_shape,
@@ -85,7 +106,7 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
     ext = [_scalar_ref(x, vector_shape, dtype) for x in extents]
     mass = mass_eV if mass_eV.dtype in (torch.float32, torch.float64) else mass_eV.to(dtype)
 
-    ws = Workspace(n_beams, (nx, ny, nz), dtype, device)
+    ws = _workspace(n_beams, (nx, ny, nz), dtype, device)
     out = torch.empty((n_beams, n, 7), dtype=dtype, device=device)
     forces = torch.empty((n_beams, n, 3), dtype=dtype, device=device) if want_intermediates else None
     stream = _capi.current_stream(device)
@@ -103,9 +124,11 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
             nx, ny, nz, code, ws.params.data_ptr(), stream))
         _capi.check(lib.ch_sc_deposit(
             p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
-            ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho.data_ptr(), stream))
-        if want_intermediates:
-            ws.green = torch.empty((n_beams, 2 * nx, 2 * ny, 2 * nz), dtype=dtype, device=device)
+            ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_split.data_ptr(), stream))
+        ws.green = (
+            torch.empty((n_beams, 2 * nx, 2 * ny, 2 * nz), dtype=dtype, device=device)
+            if want_intermediates else None
+        )
         _capi.check(lib.ch_sc_green_function(
             ws.params.data_ptr(), n_beams, nx, ny, nz, code, ws.lattice.data_ptr(),
             _capi.ptr(ws.green), stream))
@@ -113,7 +136,7 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
             ws.lattice.data_ptr(), n_beams, nx, ny, nz, code, ws.green_scratch.data_ptr(),
             ws.green_spectrum.data_ptr(), stream))
         _capi.check(lib.ch_sc_poisson_solve(
-            ws.rho.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
+            ws.rho_split.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
             nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))
         _capi.check(lib.ch_sc_field(
             ws.phi.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,

@@ -70,15 +70,13 @@ class Species(nn.Module):
         return self.num_elementary_charges * ELEMENTARY_CHARGE
 
     def clone(self) -> "Species":
-        if self.name in self.known:
-            return self.__class__(
-                name=self.name, device=self.mass_eV.device, dtype=self.mass_eV.dtype
-            )
-        return self.__class__(
-            name=self.name,
-            num_elementary_charges=self.num_elementary_charges.clone(),
-            mass_eV=self.mass_eV.clone(),
-        )
+        """Copy of the species (device-side tensor clones only: CUDA-graph capturable)."""
+        copy = self.__class__.__new__(self.__class__)
+        nn.Module.__init__(copy)
+        copy.name = self.name
+        copy.register_buffer("num_elementary_charges", self.num_elementary_charges.clone())
+        copy.register_buffer("mass_eV", self.mass_eV.clone())
+        return copy
 
     def __repr__(self) -> str:
         return (

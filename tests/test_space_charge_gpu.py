@@ -53,7 +53,7 @@ def test_every_stage_matches_the_reference(tag, dtype):
     truth = lambda name: gu.tensor(SPACE_CHARGE[f"kick16.f64.{name}"])  # noqa: E731
 
     assert rel_err(ws.params[:, 0:3], golden("grid_dimensions")) < (1e-12 if f64 else 1e-6)
-    density = ws.rho.double() * ws.params[:, 9, None, None, None]
+    density = ws.charge_grid().double() * ws.params[:, 9, None, None, None]
     assert rel_err(density, golden("rho_padded")[:, :16, :16, :16]) < (1e-12 if f64 else 1e-5)
     # Green function: ours is evaluated in float64, so compare with the float64 reference
     assert rel_err(ws.green, truth("green")) < (1e-10 if f64 else 1e-6)

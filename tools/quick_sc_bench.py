@@ -54,6 +54,20 @@ def main():
     print(f"FODO x{cells} ({len(elements)} elements, {kicks} kicks): {ms:.2f} ms device, {wall:.2f} ms wall, "
           f"{n * len(elements) / ms / 1e3:.1f} M particle-steps/s, {n * kicks / ms / 1e3:.1f} M particle-kicks/s, "
           f"{ms / kicks * 1e3:.1f} us per kick+run")
+    graphed = cb.GraphedTrack(segment, beam)
+    ms, wall = timed(lambda: graphed.replay(), reps=3, warm=1)
+    print(f"FODO x{cells} CUDA graph replay: {ms:.2f} ms device, {wall:.2f} ms wall, "
+          f"{n * len(elements) / ms / 1e3:.1f} M particle-steps/s, {ms / kicks * 1e3:.1f} us per kick+run")
+    eager = segment.track(beam)
+    replayed = graphed.replay()
+    eager2 = segment.track(beam)
+    scale = eager.particles.std(dim=0)
+    print("eager vs eager (atomics order), max |diff| / column std:",
+          ((eager.particles - eager2.particles).abs().amax(dim=0) / scale.clamp_min(1e-30)).tolist())
+    print("graph vs eager, max |diff| / column std:",
+          ((eager.particles - replayed.particles).abs().amax(dim=0) / scale.clamp_min(1e-30)).tolist())
+    print("graph == eager:", torch.equal(eager.particles, replayed.particles) or
+          float((eager.particles - replayed.particles).abs().max()))
     print("launches", _capi.launch_count())
 
 
