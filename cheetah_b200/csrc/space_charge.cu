@@ -640,7 +640,12 @@ sc_field_kernel(const T* __restrict__ phi, const double* __restrict__ params, in
     e.y = (j > 0 && j < ny - 1) ? scale * ((f[idx + nz] - f[idx - nz]) * hy) : T(0);
     e.z = (k > 0 && k < nz - 1) ? scale * ((f[idx + 1] - f[idx - 1]) * hz) : T(0);
     e.w = T(0);
-    field[b * total + idx] = e;
+    // paired layout field[cell][2] = {E(i, j, k), E(i, j, k + 1)}: the gather reads both z
+    // neighbours of a corner pair with one 32-byte sector
+    typename Field4<T>::type* cell = field + (b * total + idx) * 2;
+    cell[0] = e;
+    if (k > 0) cell[-1] = e;
+    if (k == nz - 1) cell[1] = typename Field4<T>::type{T(0), T(0), T(0), T(0)};
   }
 }
 
@@ -648,7 +653,7 @@ sc_field_kernel(const T* __restrict__ phi, const double* __restrict__ params, in
 // 7. gather + kick
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
 sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_stride,
                       const typename Field4<T>::type* __restrict__ field,
                       const double* __restrict__ params, int64_t n_particles, int nx, int ny,
@@ -662,7 +667,7 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
   const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
   const double* prm = params + b * CH_SC_PARAMS;
-  const typename Field4<T>::type* grid = field + b * static_cast<int64_t>(nx) * ny * nz;
+  const typename Field4<T>::type* grid = field + b * static_cast<int64_t>(nx) * ny * nz * 2;
 
   if (bulk_in && threadIdx.x == 0) {
     mbar_init(&bar, 1);
@@ -682,41 +687,72 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
   const double p0 = gamma0 * beta0 * mc;
 
   T out[P][7];
+  T force[P][3];
+  // ---- trilinear gather on the node-centred grid (space_charge_kick.py:388-475), two
+  // particles at a time so that their 16 sector loads are in flight together ------------
+#pragma unroll
+  for (int half = 0; half < P; half += 2) {
+    using F4 = typename Field4<T>::type;
+    F4 lower[2][4], upper[2][4];
+    T w_row[2][4], wz_lo[2], wz_hi[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int local = threadIdx.x + (half + u) * THREADS;
+      const bool live = local < count;
+      const T pos[3] = {live ? tile[local * 7 + 0] : T(0), live ? tile[local * 7 + 2] : T(0),
+                        (live ? tile[local * 7 + 4] : T(0)) * -static_cast<T>(beta0)};
+      int base[3];
+      T w_lo[3], w_hi[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const T norm = (pos[d] + gd[d]) / cell[d];
+        const T fl = floor(norm);
+        const T lim = static_cast<T>(n[d] + 1);
+        base[d] = static_cast<int>(fmin(fmax(fl, -lim), lim));
+        w_lo[d] = T(1) - fabs(norm - fl);  // 1 - |normalised - corner|  (:411-413)
+        w_hi[d] = T(1) - fabs(norm - (fl + T(1)));
+        // corners outside the grid contribute nothing (valid_mask, :425-433)
+        if (base[d] < 0 || base[d] >= n[d]) w_lo[d] = T(0);
+        if (base[d] + 1 < 0 || base[d] + 1 >= n[d]) w_hi[d] = T(0);
+      }
+      wz_lo[u] = w_lo[2];
+      wz_hi[u] = w_hi[2];
+      const bool from_first = base[2] < 0;  // base_z == -1: the upper corner is cell 0 itself
+      const int cz = min(max(base[2], 0), nz - 1);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int ox = r >> 1, oy = r & 1;
+        const T w = (ox ? w_hi[0] : w_lo[0]) * (oy ? w_hi[1] : w_lo[1]);
+        w_row[u][r] = w * static_cast<T>(kElementaryCharge);
+        const int ix = min(max(base[0] + ox, 0), nx - 1);
+        const int iy = min(max(base[1] + oy, 0), ny - 1);
+        const F4* pair = grid + ((static_cast<int64_t>(ix) * ny + iy) * nz + cz) * 2;
+        lower[u][r] = pair[0];
+        upper[u][r] = from_first ? pair[0] : pair[1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      T fx = T(0), fy = T(0), fz = T(0);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        fx += w_row[u][r] * (wz_lo[u] * lower[u][r].x + wz_hi[u] * upper[u][r].x);
+        fy += w_row[u][r] * (wz_lo[u] * lower[u][r].y + wz_hi[u] * upper[u][r].y);
+        fz += w_row[u][r] * (wz_lo[u] * lower[u][r].z + wz_hi[u] * upper[u][r].z);
+      }
+      force[half + u][0] = fx;
+      force[half + u][1] = fy;
+      force[half + u][2] = fz;
+    }
+  }
+
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     const int local = threadIdx.x + k * THREADS;
     T p[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) p[j] = (local < count) ? tile[local * 7 + j] : T(0);
-
-    // ---- trilinear gather on the node-centred grid (space_charge_kick.py:388-475) ----
-    const T pos[3] = {p[0], p[2], p[4] * -static_cast<T>(beta0)};
-    int base[3];
-    T w_lo[3], w_hi[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const T norm = (pos[d] + gd[d]) / cell[d];
-      const T fl = floor(norm);
-      const T lim = static_cast<T>(n[d] + 1);
-      base[d] = static_cast<int>(fmin(fmax(fl, -lim), lim));
-      w_lo[d] = T(1) - fabs(norm - fl);           // 1 - |normalised - corner|  (:411-413)
-      w_hi[d] = T(1) - fabs(norm - (fl + T(1)));
-    }
-    T fx = T(0), fy = T(0), fz = T(0);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int ox = c >> 2, oy = (c >> 1) & 1, oz = c & 1;
-      const int ix = base[0] + ox, iy = base[1] + oy, iz = base[2] + oz;
-      const bool valid = ix >= 0 && ix < nx && iy >= 0 && iy < ny && iz >= 0 && iz < nz;
-      if (valid) {
-        const T w = (ox ? w_hi[0] : w_lo[0]) * (oy ? w_hi[1] : w_lo[1]) * (oz ? w_hi[2] : w_lo[2]);
-        const typename Field4<T>::type e = grid[(static_cast<int64_t>(ix) * ny + iy) * nz + iz];
-        const T we = w * static_cast<T>(kElementaryCharge);
-        fx += we * e.x;
-        fy += we * e.y;
-        fz += we * e.z;
-      }
-    }
+    const T fx = force[k][0], fy = force[k][1], fz = force[k][2];
     if (forces_out != nullptr && local < count) {
       T* f = forces_out + (b * n_particles + n0 + local) * 3;
       f[0] = fx;

@@ -116,11 +116,11 @@ class LatticeProgram:
 
     def __del__(self) -> None:
         handle, self.handle = self.handle, None
-        if handle is not None and _capi._lib is not None:
-            try:
+        try:
+            if handle is not None and _capi is not None and _capi._lib is not None:
                 _capi._lib.ch_program_destroy(handle)
-            except Exception:  # interpreter shutdown
-                pass
+        except Exception:  # interpreter shutdown
+            pass
 
 
 def _type_name(element) -> str:

@@ -60,7 +60,7 @@ class Workspace:
         )
         self.rho_spectrum = torch.empty(spectrum, dtype=cdtype, device=device)
         self.phi = torch.empty((n_beams, nx, ny, nz), dtype=dtype, device=device)
-        self.field = torch.empty((n_beams, nx, ny, nz, 4), dtype=dtype, device=device)
+        self.field = torch.empty((n_beams, nx, ny, nz, 2, 4), dtype=dtype, device=device)
 
 
 _workspace_cache: dict = {}

@@ -245,7 +245,9 @@ int ch_sc_poisson_solve(const void* rho, const void* green_spectrum, const doubl
                         void* rho_spectrum, void* phi, void* stream);
 
 /* -(1/gamma^2) grad(phi) by central differences, zero on the boundary cells:
- * _E_plus_vB_field (space_charge_kick.py:324-365).  field [B][nx*ny*nz][4] = (gx, gy, gz, 0). */
+ * _E_plus_vB_field (space_charge_kick.py:324-365).  field [B][nx*ny*nz][2][4]: per cell
+ * (gx, gy, gz, 0) of the cell itself and of its +z neighbour (zero beyond the grid), so that
+ * the gather reads a z corner pair as one 32-byte sector.                                   */
 int ch_sc_field(const void* phi, const double* params, int64_t n_beams,
                 int32_t nx, int32_t ny, int32_t nz, int32_t dtype, void* field, void* stream);
 
