@@ -78,6 +78,18 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p],
     ),
+    "ch_sc_moments_and_params": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int32,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p, c_void_p,
+        ],
+    ),
     "ch_sc_grid_params": (
         c_int32,
         [

@@ -62,48 +62,115 @@ __device__ __forceinline__ void fill_twiddles(double2* tw, int len) {
   }
 }
 
+// One radix-2 DIF stage of span 2^span_log on all columns (no barrier).
+template <typename C>
+__device__ __forceinline__ void dif_stage(C* v, const C* tw, int len, int span_log, int columns,
+                                          int pitch) {
+  const int half_total = len >> 1;
+  const int half = 1 << (span_log - 1);
+  const int tw_step = len >> span_log;
+  for (int t = threadIdx.x; t < columns * half_total; t += blockDim.x) {
+    const int col = t / half_total;
+    const int j = t - col * half_total;
+    const int pos = j & (half - 1);
+    const int i0 = ((j >> (span_log - 1)) << span_log) + pos;
+    C* base = v + col * pitch;
+    const C a = base[i0];
+    const C b = base[i0 + half];
+    base[i0] = cadd(a, b);
+    base[i0 + half] = cmul(csub(a, b), tw[pos * tw_step]);
+  }
+}
+
+template <typename C>
+__device__ __forceinline__ void dit_stage(C* v, const C* tw, int len, int span_log, int columns,
+                                          int pitch) {
+  const int half_total = len >> 1;
+  const int half = 1 << (span_log - 1);
+  const int tw_step = len >> span_log;
+  for (int t = threadIdx.x; t < columns * half_total; t += blockDim.x) {
+    const int col = t / half_total;
+    const int j = t - col * half_total;
+    const int pos = j & (half - 1);
+    const int i0 = ((j >> (span_log - 1)) << span_log) + pos;
+    C* base = v + col * pitch;
+    const C a = base[i0];
+    const C b = cmul_conj(base[i0 + half], tw[pos * tw_step]);
+    base[i0] = cadd(a, b);
+    base[i0 + half] = csub(a, b);
+  }
+}
+
 // Forward DIF over `columns` columns of length `len` stored as v[col * pitch + i].
-// Natural-order input, bit-reversed output.  Ends with a __syncthreads().
+// Natural-order input, bit-reversed output.  Two consecutive radix-2 stages (spans 2^s and
+// 2^(s-1)) act on closed groups {i, i+q, i+2q, i+3q}, so each thread carries four points
+// through both stages in registers: half the shared-memory round trips and barriers of a
+// plain radix-2 loop with the identical data flow (the output order stays bit-reversed).
+// Ends with a __syncthreads().
 template <typename C>
 __device__ __forceinline__ void forward_dif(C* v, const C* tw, int len, int log2_len, int columns,
                                             int pitch) {
-  const int half_total = len >> 1;
-  for (int span_log = log2_len; span_log >= 1; --span_log) {
-    const int half = 1 << (span_log - 1);
-    const int tw_step = len >> span_log;
-    for (int t = threadIdx.x; t < columns * half_total; t += blockDim.x) {
-      const int col = t / half_total;
-      const int j = t - col * half_total;
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> (span_log - 1)) << span_log) + pos;
+  const int quarter_total = len >> 2;
+  int s = log2_len;
+  for (; s >= 2; s -= 2) {
+    const int quarter = 1 << (s - 2);
+    const int step_a = len >> s;
+    for (int t = threadIdx.x; t < columns * quarter_total; t += blockDim.x) {
+      const int col = t / quarter_total;
+      const int j = t - col * quarter_total;
+      const int pos = j & (quarter - 1);
+      const int i0 = ((j >> (s - 2)) << s) + pos;
       C* base = v + col * pitch;
-      const C a = base[i0];
-      const C b = base[i0 + half];
-      base[i0] = cadd(a, b);
-      base[i0 + half] = cmul(csub(a, b), tw[pos * tw_step]);
+      const C x0 = base[i0], x1 = base[i0 + quarter], x2 = base[i0 + 2 * quarter],
+              x3 = base[i0 + 3 * quarter];
+      const C a0 = cadd(x0, x2), a2 = cmul(csub(x0, x2), tw[pos * step_a]);
+      const C a1 = cadd(x1, x3), a3 = cmul(csub(x1, x3), tw[(pos + quarter) * step_a]);
+      const C wb = tw[pos * 2 * step_a];
+      base[i0] = cadd(a0, a1);
+      base[i0 + quarter] = cmul(csub(a0, a1), wb);
+      base[i0 + 2 * quarter] = cadd(a2, a3);
+      base[i0 + 3 * quarter] = cmul(csub(a2, a3), wb);
     }
+    __syncthreads();
+  }
+  if (s == 1) {
+    dif_stage(v, tw, len, 1, columns, pitch);
     __syncthreads();
   }
 }
 
-// Inverse DIT (unnormalised): bit-reversed input, natural-order output.
+// Inverse DIT (unnormalised): bit-reversed input, natural-order output; mirror image of
+// forward_dif (stage pairs fused in registers).
 template <typename C>
 __device__ __forceinline__ void inverse_dit(C* v, const C* tw, int len, int log2_len, int columns,
                                             int pitch) {
-  const int half_total = len >> 1;
-  for (int span_log = 1; span_log <= log2_len; ++span_log) {
-    const int half = 1 << (span_log - 1);
-    const int tw_step = len >> span_log;
-    for (int t = threadIdx.x; t < columns * half_total; t += blockDim.x) {
-      const int col = t / half_total;
-      const int j = t - col * half_total;
-      const int pos = j & (half - 1);
-      const int i0 = ((j >> (span_log - 1)) << span_log) + pos;
+  const int quarter_total = len >> 2;
+  int s = 2;
+  if (log2_len & 1) {
+    dit_stage(v, tw, len, 1, columns, pitch);
+    __syncthreads();
+    s = 3;
+  }
+  for (; s <= log2_len; s += 2) {
+    const int quarter = 1 << (s - 2);
+    const int step_a = len >> s;
+    for (int t = threadIdx.x; t < columns * quarter_total; t += blockDim.x) {
+      const int col = t / quarter_total;
+      const int j = t - col * quarter_total;
+      const int pos = j & (quarter - 1);
+      const int i0 = ((j >> (s - 2)) << s) + pos;
       C* base = v + col * pitch;
-      const C a = base[i0];
-      const C b = cmul_conj(base[i0 + half], tw[pos * tw_step]);
-      base[i0] = cadd(a, b);
-      base[i0 + half] = csub(a, b);
+      const C x0 = base[i0], x2 = base[i0 + 2 * quarter];
+      const C wb = tw[pos * 2 * step_a];
+      const C b1 = cmul_conj(base[i0 + quarter], wb);
+      const C b3 = cmul_conj(base[i0 + 3 * quarter], wb);
+      const C y0 = cadd(x0, b1), y1 = csub(x0, b1), y2 = cadd(x2, b3), y3 = csub(x2, b3);
+      const C c2 = cmul_conj(y2, tw[pos * step_a]);
+      const C c3 = cmul_conj(y3, tw[(pos + quarter) * step_a]);
+      base[i0] = cadd(y0, c2);
+      base[i0 + 2 * quarter] = csub(y0, c2);
+      base[i0 + quarter] = cadd(y1, c3);
+      base[i0 + 3 * quarter] = csub(y1, c3);
     }
     __syncthreads();
   }

@@ -26,11 +26,65 @@ constexpr double kPi = 3.14159265358979323846;
 // ---------------------------------------------------------------------------------------
 // 1. survival-weighted moments
 // ---------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------
+// 2. per-beam grid parameters
+// ---------------------------------------------------------------------------------------
+struct GridInputs {
+  ScalarRef energy, mass, length, extent_x, extent_y, extent_tau;
+};
+
+template <typename T>
+__device__ void grid_params_for_beam(const double* s, int64_t b, const GridInputs& in, int nx,
+                                     int ny, int nz, double* out) {
+  const double sum_w = s[0];
+  const double correction = sum_w - s[1] / sum_w;  // statistics.py:44
+  const double extent[3] = {load_scalar(in.extent_x.ptr, b * in.extent_x.stride, in.extent_x.dtype),
+                            load_scalar(in.extent_y.ptr, b * in.extent_y.stride, in.extent_y.dtype),
+                            load_scalar(in.extent_tau.ptr, b * in.extent_tau.stride,
+                                        in.extent_tau.dtype)};
+  const int n[3] = {nx, ny, nz};
+  double volume = 1.0;
+  for (int d = 0; d < 3; ++d) {
+    // sum w (u - mean)^2 = S2 - S1^2 / S0 about the pilot
+    const double centred = s[5 + d] - s[2 + d] * s[2 + d] / sum_w;
+    // the reference carries sigma, grid_dimensions and cell_size in the beam dtype
+    const T sigma = static_cast<T>(sqrt(fmax(centred, 0.0) / correction));
+    const T half_extent = static_cast<T>(extent[d]) * sigma;
+    const T cell = T(2) * half_extent / static_cast<T>(n[d]);
+    out[d] = static_cast<double>(half_extent);
+    out[3 + d] = static_cast<double>(cell);
+    out[11 + d] = static_cast<double>(sigma);
+    volume *= static_cast<double>(cell);
+  }
+  const double mass = load_scalar(in.mass.ptr, 0, in.mass.dtype);
+  const double gamma = load_scalar(in.energy.ptr, b * in.energy.stride, in.energy.dtype) / mass;
+  const double beta = (fabs(gamma) > 0.0 && gamma > 0.0) ? sqrt(1.0 - 1.0 / (gamma * gamma)) : 1.0;
+  const double length = load_scalar(in.length.ptr, b * in.length.stride, in.length.dtype);
+  out[6] = gamma;
+  out[7] = beta;
+  out[8] = length / (kSpeedOfLight * beta);
+  out[9] = 1.0 / volume;
+  out[10] = gamma != 0.0 ? 1.0 / (gamma * gamma) : 0.0;
+  out[14] = sum_w;
+  out[15] = mass;
+}
+
+template <typename T>
+__global__ void sc_grid_params_kernel(const double* __restrict__ stats, int64_t n_beams,
+                                      GridInputs in, int nx, int ny, int nz,
+                                      double* __restrict__ params) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= n_beams) return;
+  grid_params_for_beam<T>(stats + b * CH_SC_STATS, b, in, nx, ny, nz, params + b * CH_SC_PARAMS);
+}
+
+// ---- 1 (continued). moments kernel (after the parameter helpers it may call) -----------
 template <typename T>
 __global__ void __launch_bounds__(256)
 sc_moments_kernel(const T* __restrict__ particles, int64_t particle_stride,
                   const T* __restrict__ survival, int64_t survival_stride, int64_t n_particles,
-                  int bulk_in, double* __restrict__ stats) {
+                  int bulk_in, double* __restrict__ stats, GridInputs in, int nx, int ny, int nz,
+                  double* __restrict__ params) {
   constexpr int P = 4, THREADS = 256, TP = P * THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);
@@ -89,55 +143,22 @@ sc_moments_kernel(const T* __restrict__ particles, int64_t particle_stride,
     stats[b * CH_SC_STATS + 9] = y0;
     stats[b * CH_SC_STATS + 10] = t0;
   }
-}
-
-// ---------------------------------------------------------------------------------------
-// 2. per-beam grid parameters
-// ---------------------------------------------------------------------------------------
-struct GridInputs {
-  ScalarRef energy, mass, length, extent_x, extent_y, extent_tau;
-};
-
-template <typename T>
-__global__ void sc_grid_params_kernel(const double* __restrict__ stats, int64_t n_beams,
-                                      GridInputs in, int nx, int ny, int nz,
-                                      double* __restrict__ params) {
-  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (b >= n_beams) return;
-  const double* s = stats + b * CH_SC_STATS;
-  double* out = params + b * CH_SC_PARAMS;
-  const double sum_w = s[0];
-  const double correction = sum_w - s[1] / sum_w;  // statistics.py:44
-  const double extent[3] = {load_scalar(in.extent_x.ptr, b * in.extent_x.stride, in.extent_x.dtype),
-                            load_scalar(in.extent_y.ptr, b * in.extent_y.stride, in.extent_y.dtype),
-                            load_scalar(in.extent_tau.ptr, b * in.extent_tau.stride,
-                                        in.extent_tau.dtype)};
-  const int n[3] = {nx, ny, nz};
-  double volume = 1.0;
-  for (int d = 0; d < 3; ++d) {
-    // sum w (u - mean)^2 = S2 - S1^2 / S0 about the pilot
-    const double centred = s[5 + d] - s[2 + d] * s[2 + d] / sum_w;
-    // the reference carries sigma, grid_dimensions and cell_size in the beam dtype
-    const T sigma = static_cast<T>(sqrt(fmax(centred, 0.0) / correction));
-    const T half_extent = static_cast<T>(extent[d]) * sigma;
-    const T cell = T(2) * half_extent / static_cast<T>(n[d]);
-    out[d] = static_cast<double>(half_extent);
-    out[3 + d] = static_cast<double>(cell);
-    out[11 + d] = static_cast<double>(sigma);
-    volume *= static_cast<double>(cell);
+  if (params == nullptr) return;
+  // the last CTA of this beam to finish turns the sums into the grid parameters, so the
+  // chain needs no separate launch (threadfence-reduction pattern; stats[11] is the ticket)
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    last = atomicAdd(&stats[b * CH_SC_STATS + 11], 1.0) == static_cast<double>(gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    double sums[CH_SC_STATS];
+    for (int i = 0; i < CH_SC_STATS; ++i) sums[i] = __ldcg(&stats[b * CH_SC_STATS + i]);
+    grid_params_for_beam<T>(sums, b, in, nx, ny, nz, params + b * CH_SC_PARAMS);
   }
-  const double mass = load_scalar(in.mass.ptr, 0, in.mass.dtype);
-  const double gamma = load_scalar(in.energy.ptr, b * in.energy.stride, in.energy.dtype) / mass;
-  const double beta = (fabs(gamma) > 0.0 && gamma > 0.0) ? sqrt(1.0 - 1.0 / (gamma * gamma)) : 1.0;
-  const double length = load_scalar(in.length.ptr, b * in.length.stride, in.length.dtype);
-  out[6] = gamma;
-  out[7] = beta;
-  out[8] = length / (kSpeedOfLight * beta);
-  out[9] = 1.0 / volume;
-  out[10] = gamma != 0.0 ? 1.0 / (gamma * gamma) : 0.0;
-  out[14] = sum_w;
-  out[15] = mass;
 }
+
 
 // ---------------------------------------------------------------------------------------
 // 3. cloud-in-cell deposit
@@ -684,7 +705,7 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
   const int n[3] = {nx, ny, nz};
   const double gamma0 = prm[6], beta0 = prm[7], dt = prm[8];
   const double mc = prm[15] * kEvToKg * kSpeedOfLight;  // mass * c in kg m / s
-  const double p0 = gamma0 * beta0 * mc;
+  const double bg0 = gamma0 * beta0, inv_bg0 = 1.0 / bg0, dt_over_mc = dt / mc;
 
   T out[P][7];
   T force[P][3];
@@ -761,22 +782,22 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
     }
 
     // ---- Cheetah -> SI, kick, SI -> Cheetah in fp64 (particle_beam.py:1262-1346) -------
+    // momenta in units of m c (u = P / (m c)): P_x = px p0, p0 / (m c) = gamma0 beta0;
+    // |u|^2 = gamma^2 - 1.  Two square roots and no division per particle.
     const double gamma = gamma0 * (1.0 + static_cast<double>(p[5]) * beta0);
-    const double momentum = mc * sqrt(gamma * gamma - 1.0);  // gamma m c beta
-    double px = static_cast<double>(p[1]) * p0;
-    double py = static_cast<double>(p[3]) * p0;
-    double pz = sqrt(momentum * momentum - px * px - py * py);
-    px = fma(static_cast<double>(fx), dt, px);
-    py = fma(static_cast<double>(fy), dt, py);
-    pz = fma(static_cast<double>(fz), dt, pz);
-    const double u2 = (px * px + py * py + pz * pz) / (mc * mc);
-    const double gamma_new = sqrt(1.0 + u2);
+    double ux = static_cast<double>(p[1]) * bg0;
+    double uy = static_cast<double>(p[3]) * bg0;
+    double uz = sqrt(gamma * gamma - 1.0 - ux * ux - uy * uy);
+    ux = fma(static_cast<double>(fx), dt_over_mc, ux);
+    uy = fma(static_cast<double>(fy), dt_over_mc, uy);
+    uz = fma(static_cast<double>(fz), dt_over_mc, uz);
+    const double gamma_new = sqrt(1.0 + ux * ux + uy * uy + uz * uz);
     out[k][0] = p[0];
-    out[k][1] = static_cast<T>(px / p0);
+    out[k][1] = static_cast<T>(ux * inv_bg0);
     out[k][2] = p[2];
-    out[k][3] = static_cast<T>(py / p0);
+    out[k][3] = static_cast<T>(uy * inv_bg0);
     out[k][4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
-    out[k][5] = static_cast<T>((gamma_new - gamma0) / (beta0 * gamma0));
+    out[k][5] = static_cast<T>((gamma_new - gamma0) * inv_bg0);
     out[k][6] = p[6];
   }
   __syncthreads();  // everybody is done reading the input tile
@@ -943,10 +964,49 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
   CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, fn ": bad dtype %d", dtype);            \
   CH_REQUIRE(n_beams > 0 && n_beams <= 65535, fn ": n_beams must be in [1, 65535]")
 
+namespace {
+int launch_moments(const void* particles, int64_t particle_stride, const void* survival,
+                   int64_t survival_stride, int64_t n_particles, int64_t n_beams, int32_t dtype,
+                   double* stats, const ch::GridInputs& inputs, int nx, int ny, int nz,
+                   double* params, void* stream);
+}
+
 extern "C" int ch_sc_beam_moments(const void* particles, int64_t particle_stride,
                                   const void* survival, int64_t survival_stride,
                                   int64_t n_particles, int64_t n_beams, int32_t dtype,
                                   double* stats, void* stream) {
+  return launch_moments(particles, particle_stride, survival, survival_stride, n_particles, n_beams,
+                        dtype, stats, ch::GridInputs{}, 0, 0, 0, nullptr, stream);
+}
+
+extern "C" int ch_sc_moments_and_params(
+    const void* particles, int64_t particle_stride, const void* survival, int64_t survival_stride,
+    int64_t n_particles, int64_t n_beams, const void* energy, int64_t energy_stride,
+    int32_t energy_dtype, const void* mass_eV, int32_t mass_dtype, const void* effect_length,
+    int64_t length_stride, int32_t length_dtype, const void* extent_x, int64_t extent_x_stride,
+    const void* extent_y, int64_t extent_y_stride, const void* extent_tau,
+    int64_t extent_tau_stride, int32_t extent_dtype, int32_t nx, int32_t ny, int32_t nz,
+    int32_t dtype, double* stats, double* params, void* stream) {
+  CH_REQUIRE(energy && mass_eV && effect_length && extent_x && extent_y && extent_tau && params,
+             "ch_sc_moments_and_params: NULL pointer argument");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz),
+             "ch_sc_moments_and_params: grid (%d, %d, %d) must be powers of two in [4, 256]", nx,
+             ny, nz);
+  ch::GridInputs in{{energy, energy_stride, energy_dtype},
+                    {mass_eV, 0, mass_dtype},
+                    {effect_length, length_stride, length_dtype},
+                    {extent_x, extent_x_stride, extent_dtype},
+                    {extent_y, extent_y_stride, extent_dtype},
+                    {extent_tau, extent_tau_stride, extent_dtype}};
+  return launch_moments(particles, particle_stride, survival, survival_stride, n_particles, n_beams,
+                        dtype, stats, in, nx, ny, nz, params, stream);
+}
+
+namespace {
+int launch_moments(const void* particles, int64_t particle_stride, const void* survival,
+                   int64_t survival_stride, int64_t n_particles, int64_t n_beams, int32_t dtype,
+                   double* stats, const ch::GridInputs& inputs, int nx, int ny, int nz,
+                   double* params, void* stream) {
   CH_SC_COMMON_CHECKS("ch_sc_beam_moments");
   CH_REQUIRE(particles && stats && n_particles > 0, "ch_sc_beam_moments: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -956,7 +1016,7 @@ extern "C" int ch_sc_beam_moments(const void* particles, int64_t particle_stride
     const int bulk = ch::bulk_compatible<float>(particles, n_particles, particle_stride);
     ch::sc_moments_kernel<float><<<grid, 256, 1024 * 7 * sizeof(float), s>>>(
         static_cast<const float*>(particles), particle_stride, static_cast<const float*>(survival),
-        survival_stride, n_particles, bulk, stats);
+        survival_stride, n_particles, bulk, stats, inputs, nx, ny, nz, params);
   } else {
     const int bulk = ch::bulk_compatible<double>(particles, n_particles, particle_stride);
     auto kernel = ch::sc_moments_kernel<double>;
@@ -965,11 +1025,12 @@ extern "C" int ch_sc_beam_moments(const void* particles, int64_t particle_stride
                                  static_cast<int>(smem)));
     kernel<<<grid, 256, smem, s>>>(static_cast<const double*>(particles), particle_stride,
                                    static_cast<const double*>(survival), survival_stride,
-                                   n_particles, bulk, stats);
+                                   n_particles, bulk, stats, inputs, nx, ny, nz, params);
   }
   CH_LAUNCH_CHECK();
   return CH_OK;
 }
+}  // namespace
 
 extern "C" int ch_sc_grid_params(const double* stats, int64_t n_beams, const void* energy,
                                  int64_t energy_stride, int32_t energy_dtype, const void* mass_eV,

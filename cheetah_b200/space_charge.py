@@ -64,6 +64,14 @@ class Workspace:
 
 
 _workspace_cache: dict = {}
+_side_streams: dict = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    stream = _side_streams.get(device)
+    if stream is None:
+        stream = _side_streams[device] = torch.cuda.Stream(device)
+    return stream
 
 
 def _workspace(n_beams: int, grid_shape: tuple, dtype, device) -> Workspace:
@@ -111,30 +119,37 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
     forces = torch.empty((n_beams, n, 3), dtype=dtype, device=device) if want_intermediates else None
     stream = _capi.current_stream(device)
     with torch.cuda.device(device):
-        _capi.check(lib.ch_sc_beam_moments(
-            p.data_ptr(), p_stride, w.data_ptr(), w_stride, n, n_beams, code,
-            ws.stats.data_ptr(), stream))
-        _capi.check(lib.ch_sc_grid_params(
-            ws.stats.data_ptr(), n_beams,
+        _capi.check(lib.ch_sc_moments_and_params(
+            p.data_ptr(), p_stride, w.data_ptr(), w_stride, n, n_beams,
             e.data_ptr(), e_stride, _capi.dtype_code(e.dtype),
             mass.data_ptr(), _capi.dtype_code(mass.dtype),
             length.data_ptr(), l_stride, _capi.dtype_code(length.dtype),
             ext[0][0].data_ptr(), ext[0][1], ext[1][0].data_ptr(), ext[1][1],
             ext[2][0].data_ptr(), ext[2][1], code,
-            nx, ny, nz, code, ws.params.data_ptr(), stream))
-        _capi.check(lib.ch_sc_deposit(
-            p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
-            ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_split.data_ptr(), stream))
+            nx, ny, nz, code, ws.stats.data_ptr(), ws.params.data_ptr(), stream))
+        # the Green-function chain only needs the grid parameters: it runs on a side stream
+        # concurrently with the deposit and the first two FFT passes of the charge
+        main = torch.cuda.current_stream(device)
+        side = _side_stream(device)
+        forked = torch.cuda.Event()
+        forked.record(main)
+        side.wait_event(forked)
         ws.green = (
             torch.empty((n_beams, 2 * nx, 2 * ny, 2 * nz), dtype=dtype, device=device)
             if want_intermediates else None
         )
         _capi.check(lib.ch_sc_green_function(
             ws.params.data_ptr(), n_beams, nx, ny, nz, code, ws.lattice.data_ptr(),
-            _capi.ptr(ws.green), stream))
+            _capi.ptr(ws.green), side.cuda_stream))
         _capi.check(lib.ch_sc_green_spectrum(
             ws.lattice.data_ptr(), n_beams, nx, ny, nz, code, ws.green_scratch.data_ptr(),
-            ws.green_spectrum.data_ptr(), stream))
+            ws.green_spectrum.data_ptr(), side.cuda_stream))
+        joined = torch.cuda.Event()
+        joined.record(side)
+        _capi.check(lib.ch_sc_deposit(
+            p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
+            ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_split.data_ptr(), stream))
+        main.wait_event(joined)
         _capi.check(lib.ch_sc_poisson_solve(
             ws.rho_split.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
             nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))

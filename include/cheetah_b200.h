@@ -160,7 +160,8 @@ int ch_apply_maps(const void* particles_in, int64_t particle_stride, const int32
  * All per-beam scalars live on the device in fp64 tables so that no step synchronises
  * with the host:
  *   stats  [B][CH_SC_STATS]   0 sum w, 1 sum w^2, 2-4 sum w (u - u0), 5-7 sum w (u - u0)^2
- *                             for u = x, y, tau; 8-10 the pilot u0 (particle 0), 11 unused
+ *                             for u = x, y, tau; 8-10 the pilot u0 (particle 0), 11 ticket
+ *                             counter of ch_sc_moments_and_params
  *   params [B][CH_SC_PARAMS]  0-2 grid half-extent (extent * sigma), 3-5 cell size,
  *                             6 gamma, 7 beta, 8 dt = L / (c beta), 9 1 / cell volume,
  *                             10 1 / gamma^2 (0 if gamma == 0), 11-13 sigma x, y, tau,
@@ -178,6 +179,21 @@ int ch_sc_beam_moments(const void* particles, int64_t particle_stride,
                        const void* survival, int64_t survival_stride,
                        int64_t n_particles, int64_t n_beams, int32_t dtype,
                        double* stats, void* stream);
+
+/* ch_sc_beam_moments + ch_sc_grid_params in ONE launch: the last CTA to finish a beam's sums
+ * computes its parameters (saves a dependent launch per kick).  Arguments as in the two
+ * functions below / above.                                                                */
+int ch_sc_moments_and_params(const void* particles, int64_t particle_stride,
+                             const void* survival, int64_t survival_stride,
+                             int64_t n_particles, int64_t n_beams,
+                             const void* energy, int64_t energy_stride, int32_t energy_dtype,
+                             const void* mass_eV, int32_t mass_dtype,
+                             const void* effect_length, int64_t length_stride, int32_t length_dtype,
+                             const void* extent_x, int64_t extent_x_stride,
+                             const void* extent_y, int64_t extent_y_stride,
+                             const void* extent_tau, int64_t extent_tau_stride, int32_t extent_dtype,
+                             int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                             double* stats, double* params, void* stream);
 
 /* sigma -> grid_dimensions, cell_size, dt, gamma, beta: space_charge_kick.py:531-550,
  * cheetah/particles/beam.py:323-336.  energy / effect_length / extents are read like

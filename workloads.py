@@ -108,3 +108,37 @@ def oracle_beam(particles: torch.Tensor, dtype, energy: float = 1e8) -> dict:
     from oracle import track_oracle as oracle
 
     return oracle.make_beam(particles.to(dtype), torch.tensor(energy, dtype=dtype))
+
+
+def fodo_space_charge(cells: int = 50, grid: int = 64, dtype=torch.float32) -> list:
+    """BASELINE configs[3]: `cells` FODO cells [QF, D, QD, D]; every 1 m drift D is realised as
+    Drift(0.5) . SpaceChargeKick(effect_length=1, grid^3) . Drift(0.5) (the split-kick pattern of
+    the reference's tests/test_space_charge_kick.py:56-66) -> 8 elements and 2 kicks per cell."""
+    t = lambda v: torch.tensor(v, dtype=dtype)  # noqa: E731
+    lattice = []
+    for cell in range(cells):
+        for sign, tag in ((1.0, "f"), (-1.0, "d")):
+            lattice.append({"type": "Quadrupole", "name": f"q{tag}{cell}", "length": t(0.2),
+                            "k1": t(4.2 * sign), "misalignment": torch.zeros(2, dtype=dtype),
+                            "tilt": t(0.0), "tracking_method": "linear"})
+            lattice.append({"type": "Drift", "name": f"d{tag}{cell}a", "length": t(0.5),
+                            "tracking_method": "linear"})
+            lattice.append({"type": "SpaceChargeKick", "name": f"sc{tag}{cell}",
+                            "effect_length": t(1.0), "grid_extent_x": t(3.0),
+                            "grid_extent_y": t(3.0), "grid_extent_tau": t(3.0),
+                            "grid_shape": [grid, grid, grid]})
+            lattice.append({"type": "Drift", "name": f"d{tag}{cell}b", "length": t(0.5),
+                            "tracking_method": "linear"})
+    return lattice
+
+
+def parameters_beam_particles(num_particles: int, seed: int = 0) -> torch.Tensor:
+    """(N, 7) float64 particles of ParticleBeam.from_parameters defaults (sigma_x = sigma_y =
+    175 um, sigma_px = sigma_py = 4e-6, sigma_tau = 8 um, sigma_p = 2e-3; particle_beam.py:199-216)."""
+    import cheetah_b200 as cb
+
+    beam = cb.ParticleBeam.from_parameters(
+        num_particles=num_particles, dtype=torch.float64,
+        generator=torch.Generator().manual_seed(seed),
+    )
+    return beam.particles
