@@ -55,6 +55,7 @@ def parse_args():
     p.add_argument("--cpu-sample-settings", type=int, default=8)
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-observables", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
@@ -321,6 +322,31 @@ def main() -> None:
         "share_of_step": mean_apply_ms / (start.elapsed_time(stop) / args.steps),
     }
 
+    # ---- fused observables: moments of the outgoing beam, no (B, N, 7) array in HBM ----------
+    observables = None
+    if not args.no_observables:
+        for _ in range(2):
+            segment.track_moments(beam)
+        barrier()
+        o_start, o_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o_start.record()
+        for _ in range(args.steps):
+            observed = segment.track_moments(beam)
+        o_stop.record()
+        barrier()
+        t = torch.tensor([o_start.elapsed_time(o_stop)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        o_ms = float(t[0]) / args.steps
+        observables = {
+            "what": "Segment.track_moments: mu, sigma (6 each) and surviving-particle count per "
+                    "setting from the apply kernel's epilogue; outgoing particles never written",
+            "value": args.settings * args.particles * N_ELEMENTS / (o_ms * 1e-3),
+            "unit": UNIT,
+            "ms_per_step": o_ms,
+            "mean_sigma_x": float(observed.sigma[..., 0].mean()),
+        }
+
     # ---- end to end through the host-buffer API -------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -347,6 +373,30 @@ def main() -> None:
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
+        e2e_observables = None
+        if not args.no_observables:
+            tracker.track_moments(host_beam)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(max(args.e2e_steps, 3)):
+                moments_host = tracker.track_moments(host_beam)
+            barrier()
+            eo_s = (time.perf_counter() - t0) / max(args.e2e_steps, 3)
+            t = torch.tensor([eo_s], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            eo_s = float(t[0])
+            e2e_observables = {
+                "value": args.settings * args.particles * N_ELEMENTS / eo_s,
+                "unit": UNIT,
+                "ms_per_step": eo_s * 1e3,
+                "h2d_bytes_per_step": tracker.h2d_bytes,
+                "d2h_bytes_per_step": tracker.d2h_bytes,
+                "api": "cheetah_b200.host.HostTracker.track_moments (CPU tensors in, moments on "
+                       "the host out)",
+                "host_mu_shape": list(moments_host.mu.shape),
+            }
+            observables["e2e"] = e2e_observables
         e2e = {
             "value": args.settings * args.particles * N_ELEMENTS / e2e_s,
             "unit": UNIT,
@@ -385,6 +435,7 @@ def main() -> None:
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
+            "observables": observables,
             "gpu_launches": launches,
             "clocks": clocks,
             "particle_tracks_per_s": args.settings * args.particles / (ms_per_step * 1e-3),

@@ -31,6 +31,6 @@ from .elements import (  # noqa: F401
 from .graphs import GraphedTrack  # noqa: F401
 from .space_charge import cloud_in_cell_charge_deposition  # noqa: F401
 from .species import Species  # noqa: F401
-from .tracking import first_order_transfer_map, track  # noqa: F401
+from .tracking import BeamMoments, first_order_transfer_map, track, track_moments  # noqa: F401
 
 __version__ = "0.1.0"

@@ -74,6 +74,18 @@ SIGNATURES = {
             c_int32, c_int32, c_void_p,
         ],
     ),
+    "ch_apply_maps_moments": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_int64, c_int32, c_uint32,
+            c_int64, c_int64,
+            c_void_p, c_void_p, c_void_p,
+            c_int32, c_int32, c_void_p,
+        ],
+    ),
     "ch_sc_beam_moments": (
         c_int32,
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p],
@@ -149,6 +161,7 @@ SIGNATURES = {
     ),
 }
 
+MOMENTS = 20
 SC_STATS = 12
 SC_PARAMS = 16
 

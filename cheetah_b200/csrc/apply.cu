@@ -42,6 +42,7 @@ struct ApplyArgs {
   int32_t settings_per_cta;
   int32_t bulk_in;   // particles_in tiles satisfy the 16-byte rules of cp.async.bulk
   int32_t bulk_out;  // particles_out tiles do
+  double* moments_out;  // [n_settings][CH_MOMENTS] survival-weighted sums (MOMENTS kernels)
 };
 
 template <typename T>
@@ -109,10 +110,14 @@ __device__ __forceinline__ bool inside(double v, double bound) { return fabs(v) 
 
 // One lattice setting for this thread's P particles: survival masks at every aperture, then
 // the final map into the staging tile.  SPARSE drops the structurally-zero terms (flags).
-template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE>
+// With MOMENTS the outgoing coordinates are also accumulated into `acc` (see the kernel) about
+// `pilot`, the image of the beam's first particle under the same map.
+template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE, bool MOMENTS, bool WRITE>
 __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
                                                 uint32_t elliptical_mask, const T (&p)[P][7],
-                                                T (&sv)[P], T* stage, int tid) {
+                                                T (&sv)[P], T* stage, int tid,
+                                                const T (&first_particle)[7], T (&pilot)[6],
+                                                float (&acc)[16]) {
   for (int ap = 0; ap < n_apertures; ++ap) {
     T q[16];
     load_coefficients(q, rec + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
@@ -145,29 +150,95 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
   T c[44];
   load_coefficients(c, rec);
   const T* m = c + CH_RECORD_HEADER;
-#pragma unroll
-  for (int k = 0; k < P; ++k) {
-    T* row = stage + (tid + k * THREADS) * 7;
+  // the six outgoing coordinates of one particle
+  auto map_rows = [&](const T (&in)[7], T (&out)[6]) {
     if constexpr (SPARSE) {
-      const T w = UNIT7 ? T(1) : p[k][6];
+      const T w = UNIT7 ? T(1) : in[6];
       auto constant = [&](int i) { return UNIT7 ? m[i * 7 + 6] : m[i * 7 + 6] * w; };
-      row[0] = fma_t(m[0], p[k][0], fma_t(m[1], p[k][1], fma_t(m[5], p[k][5], constant(0))));
-      row[1] = fma_t(m[7], p[k][0], fma_t(m[8], p[k][1], fma_t(m[12], p[k][5], constant(1))));
-      row[2] = fma_t(m[16], p[k][2], fma_t(m[17], p[k][3], constant(2)));
-      row[3] = fma_t(m[23], p[k][2], fma_t(m[24], p[k][3], constant(3)));
-      row[4] = fma_t(m[28], p[k][0],
-                     fma_t(m[29], p[k][1], fma_t(m[32], p[k][4], fma_t(m[33], p[k][5], constant(4)))));
-      row[5] = p[k][5];
+      out[0] = fma_t(m[0], in[0], fma_t(m[1], in[1], fma_t(m[5], in[5], constant(0))));
+      out[1] = fma_t(m[7], in[0], fma_t(m[8], in[1], fma_t(m[12], in[5], constant(1))));
+      out[2] = fma_t(m[16], in[2], fma_t(m[17], in[3], constant(2)));
+      out[3] = fma_t(m[23], in[2], fma_t(m[24], in[3], constant(3)));
+      out[4] = fma_t(m[28], in[0],
+                     fma_t(m[29], in[1], fma_t(m[32], in[4], fma_t(m[33], in[5], constant(4)))));
+      out[5] = in[5];
     } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) row[i] = affine_row<T, UNIT7>(m + i * 7, p[k]);
+      for (int i = 0; i < 6; ++i) out[i] = affine_row<T, UNIT7>(m + i * 7, in);
     }
-    row[6] = UNIT7 ? T(1) : p[k][6];
+  };
+  if constexpr (!MOMENTS) {
+    // plain path (the headline kernel): rows go straight to the staging tile
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      T* row = stage + (tid + k * THREADS) * 7;
+      if constexpr (SPARSE) {
+        const T w = UNIT7 ? T(1) : p[k][6];
+        auto constant = [&](int i) { return UNIT7 ? m[i * 7 + 6] : m[i * 7 + 6] * w; };
+        row[0] = fma_t(m[0], p[k][0], fma_t(m[1], p[k][1], fma_t(m[5], p[k][5], constant(0))));
+        row[1] = fma_t(m[7], p[k][0], fma_t(m[8], p[k][1], fma_t(m[12], p[k][5], constant(1))));
+        row[2] = fma_t(m[16], p[k][2], fma_t(m[17], p[k][3], constant(2)));
+        row[3] = fma_t(m[23], p[k][2], fma_t(m[24], p[k][3], constant(3)));
+        row[4] = fma_t(m[28], p[k][0],
+                       fma_t(m[29], p[k][1],
+                             fma_t(m[32], p[k][4], fma_t(m[33], p[k][5], constant(4)))));
+        row[5] = p[k][5];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) row[i] = affine_row<T, UNIT7>(m + i * 7, p[k]);
+      }
+      row[6] = UNIT7 ? T(1) : p[k][6];
+    }
+    return;
+  }
+  if constexpr (MOMENTS) map_rows(first_particle, pilot);
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    T out[6];
+    map_rows(p[k], out);
+    if constexpr (WRITE) {
+      T* row = stage + (tid + k * THREADS) * 7;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) row[i] = out[i];
+      row[6] = UNIT7 ? T(1) : p[k][6];
+    }
+    if constexpr (MOMENTS) {
+      // survival-weighted fp32 sums about the pilot (no cancellation); tail lanes carry w = 0
+      const float w = static_cast<float>(sv[k]);
+      acc[0] += w;
+      acc[1] = fmaf(w, w, acc[1]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float d = static_cast<float>(out[i] - pilot[i]);
+        acc[2 + i] = fmaf(w, d, acc[2 + i]);
+        acc[8 + i] = fmaf(w * d, d, acc[8 + i]);
+      }
+    }
   }
 }
 
-template <typename T, int P, int THREADS, bool UNIT7>
-__global__ void __launch_bounds__(THREADS)
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles instead of 80: every
+// round halves the number of values a lane is responsible for.  Afterwards lane L (L even)
+// holds the warp total of value index ((L >> 4) & 1) * 8 + ((L >> 3) & 1) * 4 +
+// ((L >> 2) & 1) * 2 + ((L >> 1) & 1).
+__device__ __forceinline__ float packed_warp_sum(float (&v)[16], int lane) {
+#pragma unroll
+  for (int round = 0; round < 4; ++round) {
+    const int offset = 16 >> round;      // 16, 8, 4, 2
+    const int keep = 8 >> round;         // 8, 4, 2, 1 values kept
+    const bool upper = (lane & offset) != 0;
+#pragma unroll
+    for (int i = 0; i < keep; ++i) {
+      const float send = upper ? v[i] : v[i + keep];
+      const float mine = upper ? v[i + keep] : v[i];
+      v[i] = mine + __shfl_xor_sync(0xffffffffu, send, offset);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <typename T, int P, int THREADS, bool UNIT7, bool MOMENTS, bool WRITE>
+__global__ void __launch_bounds__(THREADS, sizeof(T) == 4 ? 3 : 1)
 apply_maps_kernel(const ApplyArgs<T> a) {
   constexpr int TP = P * THREADS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -196,10 +267,30 @@ apply_maps_kernel(const ApplyArgs<T> a) {
     for (int i = tid; i < a.record_len; i += THREADS) dst[i] = src[i];
   };
 
+  // ---- fused observables (MOMENTS): survival-weighted sums of the OUTGOING coordinates
+  // about a per-setting pilot (the image of particle 0), so that mu / sigma never need the
+  // (B, N, 7) array in HBM (ParticleBeam.mu_* / sigma_*,
+  // cheetah/particles/particle_beam.py:1699-1805, cheetah/utils/statistics.py:30-62)
+  __shared__ float partial[2][THREADS / 32][16];
+  __shared__ T pilot_shared[2][8];
+  auto flush_moments = [&](int buf, int64_t b) {  // threads 0..19 after a barrier
+    if (tid < 14) {
+      double total = 0.0;
+#pragma unroll
+      for (int wi = 0; wi < THREADS / 32; ++wi) total += static_cast<double>(partial[buf][wi][tid]);
+      atomicAdd(&a.moments_out[b * CH_MOMENTS + tid], total);
+    } else if (tid < 20 && blockIdx.x == 0) {
+      a.moments_out[b * CH_MOMENTS + tid] = static_cast<double>(pilot_shared[buf][tid - 14]);
+    }
+  };
+
   copy_record(rec0, b_begin);
   __syncthreads();  // record 0 + mbarrier init visible
 
   T p[P][7];
+  T first[7];  // the beam's particle 0 (pilot of the fused moments)
+#pragma unroll
+  for (int j = 0; j < 7; ++j) first[j] = T(0);
   T sv_in[P];
 #pragma unroll
   for (int k = 0; k < P; ++k) sv_in[k] = T(1);
@@ -216,6 +307,7 @@ apply_maps_kernel(const ApplyArgs<T> a) {
     // ago: wait until the engine has finished READING it (at most 1 newer group in flight)
     if (a.bulk_out && tid == 0) bulk_wait_read<1>();
     __syncthreads();
+    if (MOMENTS && it > 0) flush_moments((it - 1) & 1, b - 1);
 
     // ---- incoming particle tile -> registers (once per CTA when the beam is shared) ----
     const int64_t p_off =
@@ -245,10 +337,15 @@ apply_maps_kernel(const ApplyArgs<T> a) {
           for (int j = 0; j < 7; ++j) p[k][j] = T(0);
         }
       }
+      if (MOMENTS) {
+        const T* head = a.particles_in + (p_off - n0 * 7);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) first[j] = head[j];
+      }
       loaded_particles = p_off;
       __syncthreads();  // everyone has its registers before the tile is overwritten
     }
-    if (a.survival_out != nullptr) {
+    if (a.survival_out != nullptr || MOMENTS) {
       const int64_t s_off =
           (a.survival_index ? a.survival_index[b] : b) * a.survival_stride + n0;
       if (s_off != loaded_survival) {
@@ -275,12 +372,21 @@ apply_maps_kernel(const ApplyArgs<T> a) {
     const uint32_t flags = record_flags(rec[0]);
     constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
                                  CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
+    T pilot[6];
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+    if (MOMENTS) {  // lanes past the end of the beam must not count
+#pragma unroll
+      for (int k = 0; k < P; ++k)
+        if (tid + k * THREADS >= count) sv[k] = T(0);
+    }
     if ((flags & kSparse) == kSparse)
-      process_setting<T, P, THREADS, UNIT7, true>(rec, a.n_apertures, a.elliptical_mask, p, sv,
-                                                  stage, tid);
+      process_setting<T, P, THREADS, UNIT7, true, MOMENTS, WRITE>(
+          rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc);
     else
-      process_setting<T, P, THREADS, UNIT7, false>(rec, a.n_apertures, a.elliptical_mask, p, sv,
-                                                   stage, tid);
+      process_setting<T, P, THREADS, UNIT7, false, MOMENTS, WRITE>(
+          rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc);
     if (a.survival_out != nullptr) {
       T* dst = a.survival_out + b * a.n_particles + n0;
 #pragma unroll
@@ -289,8 +395,21 @@ apply_maps_kernel(const ApplyArgs<T> a) {
         if (local < count) dst[local] = sv[k];
       }
     }
+    if (MOMENTS) {
+      // packed warp reduction, then one fp64 atomic per (tile, setting, statistic) issued at
+      // the top of the next iteration
+      const int lane = tid & 31;
+      const float total = packed_warp_sum(acc, lane);
+      if ((lane & 1) == 0) {
+        const int index = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                          ((lane >> 1) & 1);
+        partial[it & 1][tid >> 5][index] = total;
+      }
+      if (tid < 6) pilot_shared[it & 1][tid] = pilot[tid];
+    }
 
     // ---- hand the finished tile to the TMA engine (or copy it out cooperatively) -------
+    if (!WRITE) continue;  // observables only: nothing leaves the SM
     T* out = a.particles_out + (b * a.n_particles + n0) * 7;
     if (a.bulk_out) {
       fence_async_shared();
@@ -304,6 +423,10 @@ apply_maps_kernel(const ApplyArgs<T> a) {
       for (int i = tid; i < count * 7; i += THREADS) out[i] = stage[i];
     }
   }
+  if (MOMENTS && b_end > b_begin) {
+    __syncthreads();
+    flush_moments(static_cast<int>((b_end - b_begin - 1) & 1), b_end - 1);
+  }
   if (a.bulk_out && tid == 0) bulk_wait<0>();
 }
 
@@ -316,17 +439,23 @@ int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t strea
   const int64_t chunks = (args.n_settings + args.settings_per_cta - 1) / args.settings_per_cta;
   CH_REQUIRE(tiles <= 2147483647LL && chunks <= 65535, "ch_apply_maps: grid too large");
   dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(chunks));
-  if (unit_seventh) {
-    auto kernel = apply_maps_kernel<T, P, THREADS, true>;
+  auto launch = [&](auto kernel) -> int {
     CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
     kernel<<<grid, THREADS, smem, stream>>>(args);
-  } else {
-    auto kernel = apply_maps_kernel<T, P, THREADS, false>;
-    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
-    kernel<<<grid, THREADS, smem, stream>>>(args);
-  }
+    return CH_OK;
+  };
+  int status;
+  if (args.moments_out != nullptr && args.particles_out == nullptr)
+    status = unit_seventh ? launch(apply_maps_kernel<T, P, THREADS, true, true, false>)
+                          : launch(apply_maps_kernel<T, P, THREADS, false, true, false>);
+  else if (args.moments_out != nullptr)
+    status = unit_seventh ? launch(apply_maps_kernel<T, P, THREADS, true, true, true>)
+                          : launch(apply_maps_kernel<T, P, THREADS, false, true, true>);
+  else
+    status = unit_seventh ? launch(apply_maps_kernel<T, P, THREADS, true, false, true>)
+                          : launch(apply_maps_kernel<T, P, THREADS, false, false, true>);
+  if (status != CH_OK) return status;
   CH_LAUNCH_CHECK();
   return CH_OK;
 }
@@ -337,8 +466,9 @@ int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t
                 const void* records, int64_t record_stride, const int32_t* record_index,
                 int64_t record_len, int32_t n_apertures, uint32_t elliptical_mask,
                 int64_t n_particles, int64_t n_settings, void* particles_out, void* survival_out,
-                int32_t unit_seventh, cudaStream_t stream) {
+                int32_t unit_seventh, double* moments_out, cudaStream_t stream) {
   ApplyArgs<T> a;
+  a.moments_out = moments_out;
   a.particles_in = static_cast<const T*>(particles_in);
   a.survival_in = static_cast<const T*>(survival_in);
   a.records = static_cast<const T*>(records);
@@ -364,7 +494,7 @@ int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t
            (static_cast<size_t>(batch_stride_elems) * sizeof(T)) % 16 == 0;
   };
   a.bulk_in = tiles_aligned(particles_in, particle_stride) ? 1 : 0;
-  a.bulk_out = tiles_aligned(particles_out, n_particles * 7) ? 1 : 0;
+  a.bulk_out = (particles_out != nullptr && tiles_aligned(particles_out, n_particles * 7)) ? 1 : 0;
 
   // settings per CTA: amortise the tile load over many settings but keep >= ~8 waves of CTAs
   constexpr int P = sizeof(T) == 4 ? 4 : 2;
@@ -379,6 +509,42 @@ int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t
 }  // namespace
 }  // namespace ch
 
+namespace {
+int apply_dispatch(const void* particles_in, int64_t particle_stride,
+                   const int32_t* particle_index, const void* survival_in,
+                   int64_t survival_stride, const int32_t* survival_index, const void* records,
+                   int64_t record_stride, const int32_t* record_index, int64_t record_len,
+                   int32_t n_apertures, uint32_t elliptical_mask, int64_t n_particles,
+                   int64_t n_settings, void* particles_out, void* survival_out, int32_t dtype,
+                   int32_t unit_seventh, double* moments_out, void* stream) {
+  CH_REQUIRE(particles_in && records, "ch_apply_maps: NULL pointer argument");
+  CH_REQUIRE(particles_out || moments_out, "ch_apply_maps: no output requested");
+  CH_REQUIRE(n_particles > 0 && n_settings > 0, "ch_apply_maps: empty beam or batch");
+  CH_REQUIRE(n_apertures >= 0 && n_apertures <= CH_MAX_APERTURES,
+             "ch_apply_maps: n_apertures %d outside [0, %d]", n_apertures, CH_MAX_APERTURES);
+  CH_REQUIRE(record_len == CH_RECORD_LEN(n_apertures),
+             "ch_apply_maps: record_len %lld does not match %d apertures",
+             static_cast<long long>(record_len), n_apertures);
+  CH_REQUIRE(n_apertures == 0 || survival_out != nullptr || particles_out == nullptr,
+             "ch_apply_maps: survival_out is required when apertures are present");
+  CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, "ch_apply_maps: bad dtype %d", dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (moments_out != nullptr)
+    CH_CUDA(cudaMemsetAsync(moments_out, 0, sizeof(double) * CH_MOMENTS * n_settings, s));
+  if (dtype == CH_F32)
+    return ch::apply_typed<float>(particles_in, particle_stride, particle_index, survival_in,
+                                  survival_stride, survival_index, records, record_stride,
+                                  record_index, record_len, n_apertures, elliptical_mask,
+                                  n_particles, n_settings, particles_out, survival_out,
+                                  unit_seventh, moments_out, s);
+  return ch::apply_typed<double>(particles_in, particle_stride, particle_index, survival_in,
+                                 survival_stride, survival_index, records, record_stride,
+                                 record_index, record_len, n_apertures, elliptical_mask,
+                                 n_particles, n_settings, particles_out, survival_out,
+                                 unit_seventh, moments_out, s);
+}
+}  // namespace
+
 extern "C" int ch_apply_maps(const void* particles_in, int64_t particle_stride,
                              const int32_t* particle_index, const void* survival_in,
                              int64_t survival_stride, const int32_t* survival_index,
@@ -387,26 +553,25 @@ extern "C" int ch_apply_maps(const void* particles_in, int64_t particle_stride,
                              int32_t n_apertures, uint32_t elliptical_mask, int64_t n_particles,
                              int64_t n_settings, void* particles_out, void* survival_out,
                              int32_t dtype, int32_t unit_seventh, void* stream) {
-  CH_REQUIRE(particles_in && records && particles_out, "ch_apply_maps: NULL pointer argument");
-  CH_REQUIRE(n_particles > 0 && n_settings > 0, "ch_apply_maps: empty beam or batch");
-  CH_REQUIRE(n_apertures >= 0 && n_apertures <= CH_MAX_APERTURES,
-             "ch_apply_maps: n_apertures %d outside [0, %d]", n_apertures, CH_MAX_APERTURES);
-  CH_REQUIRE(record_len == CH_RECORD_LEN(n_apertures),
-             "ch_apply_maps: record_len %lld does not match %d apertures",
-             static_cast<long long>(record_len), n_apertures);
-  CH_REQUIRE(n_apertures == 0 || survival_out != nullptr,
-             "ch_apply_maps: survival_out is required when apertures are present");
-  CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, "ch_apply_maps: bad dtype %d", dtype);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == CH_F32)
-    return ch::apply_typed<float>(particles_in, particle_stride, particle_index, survival_in,
-                                  survival_stride, survival_index, records, record_stride,
-                                  record_index, record_len, n_apertures, elliptical_mask,
-                                  n_particles, n_settings, particles_out, survival_out,
-                                  unit_seventh, s);
-  return ch::apply_typed<double>(particles_in, particle_stride, particle_index, survival_in,
-                                 survival_stride, survival_index, records, record_stride,
-                                 record_index, record_len, n_apertures, elliptical_mask,
-                                 n_particles, n_settings, particles_out, survival_out,
-                                 unit_seventh, s);
+  CH_REQUIRE(particles_out != nullptr, "ch_apply_maps: particles_out is NULL");
+  return apply_dispatch(particles_in, particle_stride, particle_index, survival_in,
+                        survival_stride, survival_index, records, record_stride, record_index,
+                        record_len, n_apertures, elliptical_mask, n_particles, n_settings,
+                        particles_out, survival_out, dtype, unit_seventh, nullptr, stream);
+}
+
+extern "C" int ch_apply_maps_moments(const void* particles_in, int64_t particle_stride,
+                                     const int32_t* particle_index, const void* survival_in,
+                                     int64_t survival_stride, const int32_t* survival_index,
+                                     const void* records, int64_t record_stride,
+                                     const int32_t* record_index, int64_t record_len,
+                                     int32_t n_apertures, uint32_t elliptical_mask,
+                                     int64_t n_particles, int64_t n_settings, void* particles_out,
+                                     void* survival_out, double* moments_out, int32_t dtype,
+                                     int32_t unit_seventh, void* stream) {
+  CH_REQUIRE(moments_out != nullptr, "ch_apply_maps_moments: moments_out is NULL");
+  return apply_dispatch(particles_in, particle_stride, particle_index, survival_in,
+                        survival_stride, survival_index, records, record_stride, record_index,
+                        record_len, n_apertures, elliptical_mask, n_particles, n_settings,
+                        particles_out, survival_out, dtype, unit_seventh, moments_out, stream);
 }

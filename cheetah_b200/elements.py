@@ -465,5 +465,11 @@ class Segment(Element):
 
         return tracking.track(list(self.elements), incoming, cache_owner=self)
 
+    def track_moments(self, incoming: Beam, keep_particles: bool = False):
+        """Outgoing-beam moments from the fused kernel epilogue (tracking.track_moments)."""
+        from . import tracking
+
+        return tracking.track_moments(list(self.elements), incoming, self, keep_particles)
+
     def __repr__(self) -> str:
         return f"Segment(elements={list(self.elements)!r}, name={self.name!r})"

@@ -53,6 +53,54 @@ class HostTracker:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def track_moments(self, beam_cpu):
+        """Host in, host out, but only the outgoing-beam moments come back: uploads beam and
+        settings, runs the fused-epilogue kernel over all settings and downloads
+        ``n_settings x 20`` doubles (``tracking.BeamMoments`` on the CPU)."""
+        device, dtype = self.device, self.dtype
+        self.h2d_bytes = self.d2h_bytes = 0
+        self._upload(beam_cpu)
+        beam = self._device_beam(beam_cpu)
+        observed = self.device_segment.track_moments(beam)
+        if not hasattr(self, "moments_pinned"):
+            self.moments_pinned = [
+                torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                for t in (observed.mu, observed.sigma, observed.num_particles_survived)
+            ]
+        for dst, src in zip(
+            self.moments_pinned, (observed.mu, observed.sigma, observed.num_particles_survived)
+        ):
+            dst.copy_(src, non_blocking=True)
+            self.d2h_bytes += src.numel() * src.element_size()
+        torch.cuda.current_stream(device).synchronize()
+        return tracking.BeamMoments(*self.moments_pinned, beam_cpu.energy, observed.s.cpu())
+
+    def _device_beam(self, beam_cpu):
+        from .beam import ParticleBeam
+
+        beam = ParticleBeam(
+            self.beam_dev, self.energy_dev, particle_charges=None,
+            survival_probabilities=self.survival_dev,
+            species=beam_cpu.species.__class__(beam_cpu.species.name, device=self.device,
+                                               dtype=self.dtype)
+            if beam_cpu.species.name in beam_cpu.species.known else None,
+        )
+        beam._unit_seventh = True
+        return beam
+
+    def _upload(self, beam_cpu) -> None:
+        n, dtype = self.n_particles, self.dtype
+        self.beam_pinned.copy_(beam_cpu.particles)
+        self.survival_pinned.copy_(beam_cpu.survival_probabilities.expand(n))
+        self.beam_dev.copy_(self.beam_pinned, non_blocking=True)
+        self.survival_dev.copy_(self.survival_pinned, non_blocking=True)
+        self.energy_dev.copy_(beam_cpu.energy.to(dtype), non_blocking=True)
+        self.h2d_bytes += self.beam_dev.numel() * 4 + self.survival_dev.numel() * 4 + 4
+        for (dst, src), pinned in zip(self.pairs, self.host_settings):
+            pinned.copy_(src)
+            dst.copy_(pinned, non_blocking=True)  # in place: the lowered program stays valid
+            self.h2d_bytes += dst.numel() * dst.element_size()
+
     def track(self, beam_cpu, consumer=None) -> None:
         device, dtype, n = self.device, self.dtype, self.n_particles
         compute = torch.cuda.current_stream(device)

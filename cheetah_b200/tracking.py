@@ -134,8 +134,11 @@ def _unit_seventh(beam) -> bool:
     return flag
 
 
-def _track_linear_section(program, section, beam):
-    """One ``ch_compose_maps`` + one ``ch_apply_maps`` for a ParticleBeam."""
+def _track_linear_section(program, section, beam, moments: str | None = None):
+    """One ``ch_compose_maps`` + one ``ch_apply_maps`` for a ParticleBeam.
+
+    ``moments``: None (particles only), "with" (particles + fused moments) or "only" (the
+    outgoing particles are never written to HBM; returns ``(None, BeamMoments)``)."""
     particles = beam.particles
     device, dtype = particles.device, particles.dtype
     if dtype not in (torch.float32, torch.float64):
@@ -146,7 +149,7 @@ def _track_linear_section(program, section, beam):
     records, vm = _compose(program, section, beam.energy, beam.species.mass_eV, dtype)
     new_s = beam.s + _section_length(records, vm, section.length_shape)
 
-    if not section.has_maps and section.n_apertures == 0:
+    if not section.has_maps and section.n_apertures == 0 and moments is None:
         return beam.__class__(
             particles, beam.energy, particle_charges=beam.particle_charges,
             survival_probabilities=beam.survival_probabilities, s=new_s,
@@ -159,7 +162,10 @@ def _track_linear_section(program, section, beam):
         particles = particles.contiguous()
     particle_index = _index_table(vp, vo, device)
     record_index = _index_table(vm, vo, device)
-    out = torch.empty((*vo, n, 7), dtype=dtype, device=device)
+    out = None if moments == "only" else torch.empty((*vo, n, 7), dtype=dtype, device=device)
+    sums = None
+    if moments is not None:
+        sums = torch.empty((n_out, _capi.MOMENTS), dtype=torch.float64, device=device)
 
     survival_in = beam.survival_probabilities
     survival_out = None
@@ -177,30 +183,44 @@ def _track_linear_section(program, section, beam):
                 "lattice are not supported"
             )
         survival_index = _index_table(vs, vo, device)
-        survival_out = torch.empty((*vo, n), dtype=dtype, device=device)
+        if moments != "only":
+            survival_out = torch.empty((*vo, n), dtype=dtype, device=device)
 
     events = None
     if apply_events is not None:
         events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         events[0].record(torch.cuda.current_stream(device))
+    if moments is not None and not section.n_apertures:
+        # the sums are weighted with the survival probabilities even without apertures
+        if survival_in.dtype != dtype or not survival_in.is_contiguous():
+            survival_in = survival_in.to(dtype).contiguous()
+        if tuple(torch.broadcast_shapes(vo, vs)) != vo:
+            raise NotImplementedError("survival_probabilities wider than particles and lattice")
+        survival_index = _index_table(vs, vo, device)
+    common = (
+        particles.data_ptr(), 0 if math.prod(vp) == 1 else n * 7, _capi.ptr(particle_index),
+        survival_in.data_ptr() if (section.n_apertures or moments is not None) else None,
+        0 if math.prod(vs) == 1 else n, _capi.ptr(survival_index),
+        records.data_ptr(), 0 if math.prod(vm) == 1 else records.shape[1],
+        _capi.ptr(record_index),
+        records.shape[1], section.n_apertures, section.elliptical_mask,
+        n, n_out, _capi.ptr(out), _capi.ptr(survival_out),
+    )
+    tail = (_capi.dtype_code(dtype), int(_unit_seventh(beam)), _capi.current_stream(device))
     with torch.cuda.device(device):
-        _capi.check(
-            _capi.lib().ch_apply_maps(
-                particles.data_ptr(), 0 if math.prod(vp) == 1 else n * 7,
-                _capi.ptr(particle_index),
-                survival_in.data_ptr() if section.n_apertures else None,
-                0 if math.prod(vs) == 1 else n, _capi.ptr(survival_index),
-                records.data_ptr(), 0 if math.prod(vm) == 1 else records.shape[1],
-                _capi.ptr(record_index),
-                records.shape[1], section.n_apertures, section.elliptical_mask,
-                n, n_out, out.data_ptr(), _capi.ptr(survival_out),
-                _capi.dtype_code(dtype), int(_unit_seventh(beam)),
-                _capi.current_stream(device),
-            )
-        )
+        if moments is None:
+            _capi.check(_capi.lib().ch_apply_maps(*common, *tail))
+        else:
+            _capi.check(_capi.lib().ch_apply_maps_moments(*common, sums.data_ptr(), *tail))
     if events is not None:
         events[1].record(torch.cuda.current_stream(device))
         apply_events.append(events)
+
+    observed = None
+    if sums is not None:
+        observed = BeamMoments.from_sums(sums.reshape(*vo, _capi.MOMENTS), beam.energy, new_s, dtype)
+    if moments == "only":
+        return None, observed
 
     if survival_out is not None:
         # reference shape: broadcast(survival_in, particles vector dims, everything up to and
@@ -222,7 +242,74 @@ def _track_linear_section(program, section, beam):
         outgoing._unit_seventh = _unit_seventh(beam)
     except Exception:
         pass
-    return outgoing
+    return outgoing if moments is None else (outgoing, observed)
+
+
+class BeamMoments:
+    """What ``ParticleBeam.mu_*`` / ``sigma_*`` / ``num_particles_survived`` return on the
+    outgoing beam, computed in the epilogue of the apply kernel (no (B, N, 7) array needed).
+
+    ``mu``, ``sigma``: ``(..., 6)`` for (x, px, y, py, tau, p); survival-weighted mean and
+    unbiased weighted standard deviation (cheetah/utils/statistics.py:30-62)."""
+
+    names = ("x", "px", "y", "py", "tau", "p")
+
+    def __init__(self, mu, sigma, num_particles_survived, energy, s) -> None:
+        self.mu, self.sigma = mu, sigma
+        self.num_particles_survived = num_particles_survived
+        self.energy, self.s = energy, s
+
+    @classmethod
+    def from_sums(cls, sums: torch.Tensor, energy, s, dtype) -> "BeamMoments":
+        s0, sww = sums[..., 0], sums[..., 1]
+        s1, s2, pilot = sums[..., 2:8], sums[..., 8:14], sums[..., 14:20]
+        mu = pilot + s1 / s0.unsqueeze(-1)
+        centred = s2 - s1.square() / s0.unsqueeze(-1)
+        correction = (s0 - sww / s0).unsqueeze(-1)
+        sigma = (centred.clamp_min(0.0) / correction).sqrt()
+        return cls(mu.to(dtype), sigma.to(dtype), s0.to(dtype), energy, s)
+
+    def __getattr__(self, name: str):
+        for prefix, source in (("mu_", "mu"), ("sigma_", "sigma")):
+            if name.startswith(prefix) and name[len(prefix):] in self.names:
+                return getattr(self, source)[..., self.names.index(name[len(prefix):])]
+        raise AttributeError(name)
+
+    def __repr__(self) -> str:
+        return f"BeamMoments(mu={self.mu!r}, sigma={self.sigma!r})"
+
+
+def track_moments(elements, incoming, cache_owner=None, keep_particles: bool = False):
+    """Track ``incoming`` and return the first/second moments of the outgoing beam.
+
+    The last linear section of the lattice computes them in the kernel epilogue; with
+    ``keep_particles=False`` (default) its outgoing particles are never written to HBM, which
+    removes the 32 B per (particle, setting) write and the 131 GB capacity wall of large
+    vectorised scans.  Returns ``BeamMoments`` (or ``(beam, BeamMoments)``).
+    """
+    if not _is_particle_beam(incoming):
+        raise TypeError(f"Parameter incoming is of invalid type {type(incoming)}")
+    _require_cuda(incoming.particles, "ParticleBeam")
+    program = _plan(elements, incoming.particles.device, tuple(incoming.energy.shape), cache_owner)
+    stages = program.stages
+    if not stages or not isinstance(stages[-1], lowering.LinearSection):
+        raise NotImplementedError("track_moments needs a lattice that ends with a linear section")
+    beam = incoming
+    for stage in stages[:-1]:
+        if isinstance(stage, lowering.LinearSection):
+            beam = _track_linear_section(program, stage, beam)
+        elif stage.kind == "space_charge":
+            from . import space_charge
+
+            beam = space_charge.track(stage.element, beam)
+        else:
+            raise NotImplementedError(
+                f"cheetah_b200: element {stage.element.name!r} is outside the accelerated hot path"
+            )
+    outgoing, observed = _track_linear_section(
+        program, stages[-1], beam, moments="with" if keep_particles else "only"
+    )
+    return (outgoing, observed) if keep_particles else observed
 
 
 def _track_parameter_beam(program, beam):

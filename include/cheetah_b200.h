@@ -152,6 +152,24 @@ int ch_apply_maps(const void* particles_in, int64_t particle_stride, const int32
                   void* particles_out, void* survival_out,
                   int32_t dtype, int32_t unit_seventh, void* stream);
 
+/* ch_apply_maps with a fused observables epilogue: additionally
+ * accumulates, per setting, the survival-weighted sums that ParticleBeam.mu_* / sigma_*
+ * (cheetah/particles/particle_beam.py:1699-1805 -> cheetah/utils/statistics.py:30-62) are made
+ * of, for the OUTGOING coordinates u_i (i = 0..5), about a pilot c_i (the image of particle 0):
+ *   moments_out[b][0] = sum w, [1] = sum w^2, [2+i] = sum w (u_i - c_i),
+ *   [8+i] = sum w (u_i - c_i)^2, [14+i] = c_i               (w = outgoing survival)
+ * so mu_i = c_i + S1_i / S0 and var_i = (S2_i - S1_i^2 / S0) / (S0 - sum w^2 / S0).
+ * particles_out and survival_out may be NULL: then nothing but the 20 doubles per setting
+ * leaves the SM (no (B, N, 7) array in HBM).  moments_out is zeroed here.                  */
+#define CH_MOMENTS 20
+int ch_apply_maps_moments(const void* particles_in, int64_t particle_stride, const int32_t* particle_index,
+                          const void* survival_in, int64_t survival_stride, const int32_t* survival_index,
+                          const void* records, int64_t record_stride, const int32_t* record_index,
+                          int64_t record_len, int32_t n_apertures, uint32_t elliptical_mask,
+                          int64_t n_particles, int64_t n_settings,
+                          void* particles_out, void* survival_out, double* moments_out,
+                          int32_t dtype, int32_t unit_seventh, void* stream);
+
 /* space charge ----------------------------------------------------------------------- */
 /* One SpaceChargeKick (cheetah/accelerator/space_charge_kick.py:477-586) is the sequence
  *   ch_sc_beam_moments -> ch_sc_grid_params -> ch_sc_deposit -> ch_sc_green_function ->

@@ -1,0 +1,65 @@
+"""Fused observables epilogue: moments from the apply kernel must equal the
+moments of the fully materialised outgoing beam."""
+
+import pytest
+import torch
+
+import workloads
+
+pytestmark = pytest.mark.gpu
+DEVICE = "cuda"
+
+
+def reference_moments(out):
+    """mu / sigma exactly as ParticleBeam.mu_* / sigma_* define them, in float64."""
+    w = out.survival_probabilities.double()
+    if w.dim() < out.particles.dim() - 1:
+        w = w.expand(out.particles.shape[:-1])
+    u = out.particles.double()[..., :6]
+    s0 = w.sum(dim=-1)
+    mu = (u * w.unsqueeze(-1)).sum(dim=-2) / s0.unsqueeze(-1)
+    correction = s0 - w.square().sum(dim=-1) / s0
+    var = (w.unsqueeze(-1) * (u - mu.unsqueeze(-2)).square()).sum(dim=-2) / correction.unsqueeze(-1)
+    return mu, var.sqrt(), s0
+
+
+@pytest.mark.parametrize("n,settings", [(100_000, 6), (4099, 3), (1_000_000, 4)])
+def test_track_moments_matches_moments_of_tracked_beam(n, settings):
+    description = workloads.ares_config3(settings, torch.float32)
+    segment = workloads.product_segment(description, DEVICE, torch.float32)
+    particles = workloads.twiss_beam_particles(n)
+    particles[:, :4] *= 40.0  # fat beam: the apertures cut through the core
+    beam = workloads.product_beam(particles, DEVICE, torch.float32)
+    beam.survival_probabilities = (torch.rand(n, device=DEVICE) > 0.2).float()
+
+    out = segment.track(beam)
+    mu, sigma, s0 = reference_moments(out)
+    observed = segment.track_moments(beam)
+    assert observed.mu.shape == (settings, 6) and observed.sigma.shape == (settings, 6)
+    assert torch.equal(observed.num_particles_survived.double(), s0)
+    scale = sigma.abs().clamp_min(1e-30)
+    assert ((observed.mu.double() - mu).abs() / scale).max() < 2e-5
+    assert ((observed.sigma.double() - sigma).abs() / scale).max() < 2e-5
+    assert torch.allclose(observed.sigma_x.double(), sigma[..., 0], rtol=2e-5)
+    assert torch.allclose(observed.s, out.s)
+
+    kept, observed2 = segment.track_moments(beam, keep_particles=True)
+    assert torch.equal(kept.particles, out.particles)
+    assert torch.equal(kept.survival_probabilities, out.survival_probabilities)
+    assert torch.equal(observed2.mu, observed.mu)
+
+
+def test_track_moments_without_apertures_and_single_setting():
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE)  # noqa: E731
+    segment = cb.Segment([cb.Quadrupole(length=t(0.2), k1=t(3.0), tilt=t(0.3)),
+                          cb.Drift(length=t(1.0)), cb.HorizontalCorrector(length=t(0.1), angle=t(1e-3))])
+    beam = cb.ParticleBeam.from_parameters(num_particles=50_001, device=DEVICE, dtype=torch.float32)
+    out = segment.track(beam)
+    mu, sigma, s0 = reference_moments(out)
+    observed = segment.track_moments(beam)
+    assert observed.mu.shape == (6,)
+    assert float(observed.num_particles_survived) == 50_001
+    assert ((observed.mu.double() - mu).abs() / sigma).max() < 2e-5
+    assert ((observed.sigma.double() - sigma).abs() / sigma).max() < 2e-5
