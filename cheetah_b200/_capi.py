@@ -27,15 +27,17 @@ OP_UNDULATOR = 6
 OP_CAVITY_OFF = 7
 OP_CUSTOM_MAP = 8
 OP_APERTURE = 9
+OP_CAVITY = 10
 
 RECORD_HEADER = 2
 RECORD_MAP = 42
 RECORD_APERTURE = 16
+RECORD_CAVITY = 24
 MAX_APERTURES = 32
 
 
-def record_len(n_apertures: int) -> int:
-    return RECORD_HEADER + RECORD_MAP + RECORD_APERTURE * n_apertures
+def record_len(n_apertures: int, cavity: bool = False) -> int:
+    return RECORD_HEADER + RECORD_MAP + RECORD_APERTURE * n_apertures + (RECORD_CAVITY if cavity else 0)
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/cheetah_b200.h
@@ -57,6 +59,7 @@ SIGNATURES = {
         [
             c_void_p, c_int32, c_int32, c_int64,
             c_void_p, c_int64, c_int32,
+            c_void_p, c_int32,
             c_void_p, c_int32,
             c_void_p, c_int64, c_int32,
             c_void_p,

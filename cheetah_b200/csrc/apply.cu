@@ -16,6 +16,8 @@
 // row layout.  Two staging tiles overlap the bulk store of setting b with the math of b+1.
 // HBM traffic per (particle, setting): 28 B + 4 B written, the shared beam is read once per
 // CTA.  No tensor cores: K = 7 is far below any MMA tile.
+#include <type_traits>
+
 #include "ch_common.cuh"
 
 namespace ch {
@@ -43,6 +45,7 @@ struct ApplyArgs {
   int32_t bulk_in;   // particles_in tiles satisfy the 16-byte rules of cp.async.bulk
   int32_t bulk_out;  // particles_out tiles do
   double* moments_out;  // [n_settings][CH_MOMENTS] survival-weighted sums (MOMENTS kernels)
+  int32_t has_cavity;   // the record ends with a CH_RECORD_CAVITY block
 };
 
 template <typename T>
@@ -65,6 +68,8 @@ __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, 
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ void sincos_t(float x, float& s, float& c) { sincosf(x, &s, &c); }
+__device__ __forceinline__ void sincos_t(double x, double& s, double& c) { sincos(x, &s, &c); }
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
@@ -112,12 +117,13 @@ __device__ __forceinline__ bool inside(double v, double bound) { return fabs(v) 
 // the final map into the staging tile.  SPARSE drops the structurally-zero terms (flags).
 // With MOMENTS the outgoing coordinates are also accumulated into `acc` (see the kernel) about
 // `pilot`, the image of the beam's first particle under the same map.
-template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE, bool MOMENTS, bool WRITE>
+template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE, bool MOMENTS, bool WRITE,
+          bool CAVITY>
 __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
                                                 uint32_t elliptical_mask, const T (&p)[P][7],
                                                 T (&sv)[P], T* stage, int tid,
                                                 const T (&first_particle)[7], T (&pilot)[6],
-                                                float (&acc)[16]) {
+                                                float (&acc)[16], const T* cavity) {
   for (int ap = 0; ap < n_apertures; ++ap) {
     T q[16];
     load_coefficients(q, rec + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
@@ -150,6 +156,22 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
   T c[44];
   load_coefficients(c, rec);
   const T* m = c + CH_RECORD_HEADER;
+  // Active cavity at the end of the section (cavity.py:113-220): delta is replaced by the exact
+  // update a delta_in + bV (cos(phi - tau_in b0 k) - cos phi) and tau gets the second-order
+  // terms, both from the coordinates at the cavity ENTRANCE (rows 4, 5 of the block).  The
+  // cosine difference is evaluated as -2 sin(phi + e/2) sin(e/2), which does not cancel.
+  T cav[CAVITY ? CH_RECORD_CAVITY : 2];
+  if constexpr (CAVITY) load_coefficients(cav, cavity);
+  auto cavity_tail = [&](const T (&in)[7], T& r4, T& r5) {
+    const T tau_in = affine_row<T, UNIT7>(cav, in);
+    const T delta_in = affine_row<T, UNIT7>(cav + 7, in);
+    const T half = T(-0.5) * tau_in * cav[16];
+    T sh, ch;
+    sincos_t(half, sh, ch);
+    const T dcos = T(-2) * (cav[17] * ch + cav[18] * sh) * sh;
+    r5 = fma_t(cav[14], delta_in, cav[15] * dcos);
+    r4 += cav[19] * delta_in * delta_in + cav[20] * tau_in * delta_in + cav[21] * tau_in * tau_in;
+  };
   // the six outgoing coordinates of one particle
   auto map_rows = [&](const T (&in)[7], T (&out)[6]) {
     if constexpr (SPARSE) {
@@ -188,14 +210,24 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
         for (int i = 0; i < 6; ++i) row[i] = affine_row<T, UNIT7>(m + i * 7, p[k]);
       }
       row[6] = UNIT7 ? T(1) : p[k][6];
+      if constexpr (CAVITY) {
+        T r4 = row[4], r5;
+        cavity_tail(p[k], r4, r5);
+        row[4] = r4;
+        row[5] = r5;
+      }
     }
     return;
   }
-  if constexpr (MOMENTS) map_rows(first_particle, pilot);
+  if constexpr (MOMENTS) {
+    map_rows(first_particle, pilot);
+    if constexpr (CAVITY) cavity_tail(first_particle, pilot[4], pilot[5]);
+  }
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     T out[6];
     map_rows(p[k], out);
+    if constexpr (CAVITY) cavity_tail(p[k], out[4], out[5]);
     if constexpr (WRITE) {
       T* row = stage + (tid + k * THREADS) * 7;
 #pragma unroll
@@ -237,7 +269,7 @@ __device__ __forceinline__ float packed_warp_sum(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <typename T, int P, int THREADS, bool UNIT7, bool MOMENTS, bool WRITE>
+template <typename T, int P, int THREADS, bool UNIT7, bool MOMENTS, bool WRITE, bool CAVITY>
 __global__ void __launch_bounds__(THREADS, sizeof(T) == 4 ? 3 : 1)
 apply_maps_kernel(const ApplyArgs<T> a) {
   constexpr int TP = P * THREADS;
@@ -381,12 +413,14 @@ apply_maps_kernel(const ApplyArgs<T> a) {
       for (int k = 0; k < P; ++k)
         if (tid + k * THREADS >= count) sv[k] = T(0);
     }
+    const T* cavity =
+        rec + CH_RECORD_HEADER + CH_RECORD_MAP + a.n_apertures * CH_RECORD_APERTURE;
     if ((flags & kSparse) == kSparse)
-      process_setting<T, P, THREADS, UNIT7, true, MOMENTS, WRITE>(
-          rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc);
+      process_setting<T, P, THREADS, UNIT7, true, MOMENTS, WRITE, CAVITY>(
+          rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc, cavity);
     else
-      process_setting<T, P, THREADS, UNIT7, false, MOMENTS, WRITE>(
-          rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc);
+      process_setting<T, P, THREADS, UNIT7, false, MOMENTS, WRITE, CAVITY>(
+          rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc, cavity);
     if (a.survival_out != nullptr) {
       T* dst = a.survival_out + b * a.n_particles + n0;
 #pragma unroll
@@ -445,16 +479,23 @@ int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t strea
     kernel<<<grid, THREADS, smem, stream>>>(args);
     return CH_OK;
   };
-  int status;
-  if (args.moments_out != nullptr && args.particles_out == nullptr)
-    status = unit_seventh ? launch(apply_maps_kernel<T, P, THREADS, true, true, false>)
-                          : launch(apply_maps_kernel<T, P, THREADS, false, true, false>);
-  else if (args.moments_out != nullptr)
-    status = unit_seventh ? launch(apply_maps_kernel<T, P, THREADS, true, true, true>)
-                          : launch(apply_maps_kernel<T, P, THREADS, false, true, true>);
-  else
-    status = unit_seventh ? launch(apply_maps_kernel<T, P, THREADS, true, false, true>)
-                          : launch(apply_maps_kernel<T, P, THREADS, false, false, true>);
+  // compile-time variants: (unit 7th column) x (moments epilogue) x (write particles) x (cavity)
+  auto pick = [&](auto unit, auto moments, auto write, auto cavity) -> int {
+    return launch(apply_maps_kernel<T, P, THREADS, decltype(unit)::value, decltype(moments)::value,
+                                    decltype(write)::value, decltype(cavity)::value>);
+  };
+  auto with_cavity = [&](auto unit, auto moments, auto write) -> int {
+    return args.has_cavity ? pick(unit, moments, write, std::true_type{})
+                           : pick(unit, moments, write, std::false_type{});
+  };
+  auto with_outputs = [&](auto unit) -> int {
+    if (args.moments_out != nullptr && args.particles_out == nullptr)
+      return with_cavity(unit, std::true_type{}, std::false_type{});
+    if (args.moments_out != nullptr) return with_cavity(unit, std::true_type{}, std::true_type{});
+    return with_cavity(unit, std::false_type{}, std::true_type{});
+  };
+  const int status =
+      unit_seventh ? with_outputs(std::true_type{}) : with_outputs(std::false_type{});
   if (status != CH_OK) return status;
   CH_LAUNCH_CHECK();
   return CH_OK;
@@ -483,6 +524,7 @@ int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t
   a.n_particles = n_particles;
   a.n_settings = n_settings;
   a.record_len = static_cast<int32_t>(record_len);
+  a.has_cavity = record_len == CH_RECORD_LEN(n_apertures) + CH_RECORD_CAVITY ? 1 : 0;
   a.n_apertures = n_apertures;
   a.elliptical_mask = elliptical_mask;
 
@@ -522,7 +564,8 @@ int apply_dispatch(const void* particles_in, int64_t particle_stride,
   CH_REQUIRE(n_particles > 0 && n_settings > 0, "ch_apply_maps: empty beam or batch");
   CH_REQUIRE(n_apertures >= 0 && n_apertures <= CH_MAX_APERTURES,
              "ch_apply_maps: n_apertures %d outside [0, %d]", n_apertures, CH_MAX_APERTURES);
-  CH_REQUIRE(record_len == CH_RECORD_LEN(n_apertures),
+  CH_REQUIRE(record_len == CH_RECORD_LEN(n_apertures) ||
+                 record_len == CH_RECORD_LEN(n_apertures) + CH_RECORD_CAVITY,
              "ch_apply_maps: record_len %lld does not match %d apertures",
              static_cast<long long>(record_len), n_apertures);
   CH_REQUIRE(n_apertures == 0 || survival_out != nullptr || particles_out == nullptr,

@@ -125,7 +125,8 @@ __device__ __forceinline__ void body_coefficients(double* c, double L, double k1
 
 // ---- phase A: element parameters -> coefficients -------------------------------------
 __device__ void element_coefficients(const Program& prog, int32_t op, int64_t b,
-                                     const Relativistic& rel, double* c) {
+                                     const Relativistic& rel, double mass, double charge,
+                                     double* c) {
   const int32_t code = prog.opcodes[op];
   const int32_t s0 = prog.slot_begin[op];
 #pragma unroll
@@ -266,6 +267,73 @@ __device__ void element_coefficients(const Program& prog, int32_t op, int64_t b,
       c[1] = slot_value(prog, s0 + 1, b);
       break;
     }
+    case CH_OP_CAVITY: {
+      // cavity.py:253-358 (R matrix) and :113-220 (exact delta update, T566/T556/T555)
+      const double L = slot_value(prog, s0, b);
+      const double V = slot_value(prog, s0 + 1, b);
+      const double phi = slot_value(prog, s0 + 2, b) * (3.141592653589793 / 180.0);
+      const double k = 2.0 * 3.141592653589793 * slot_value(prog, s0 + 3, b) / 299792458.0;
+      const int32_t flags = prog.op_flags[op];
+      // slot 4: device flag = the reference's batch-wide `(delta_energy > 0).any()`
+      const bool energy_gain_terms = slot_value(prog, s0 + 4, b) != 0.0;
+      const double E = rel.gamma * mass, m = mass;
+      const double v_eff = -V * charge;
+      double sphi, cphi;
+      sincos(phi, &sphi, &cphi);
+      const double delta_energy = v_eff * cphi;
+      const double Ei = E / m, dE = delta_energy / m, Ef = Ei + dE, Ep = dE / L;
+      const double E1 = E + delta_energy;
+      const double beta0 = sqrt(1.0 - 1.0 / (Ei * Ei)), beta1 = sqrt(1.0 - 1.0 / (Ef * Ef));
+      auto log1pdiv = [](double x) { return x != 0.0 ? log1p(x) / x : 1.0; };
+      if (!(flags & 1)) {  // standing wave
+        const double lg = log1pdiv(delta_energy / E);
+        const double alpha = 0.3535533905932738 * v_eff / E * lg;  // sqrt(1/8)
+        double sa, ca;
+        sincos(alpha, &sa, &ca);
+        const double rt2 = 1.4142135623730951;
+        c[0] = ca - rt2 * cphi * sa;
+        c[1] = (alpha != 0.0 ? sa / alpha : 1.0) * lg * L;
+        c[2] = -(v_eff / (E1 * rt2 * L) * (0.5 + cphi * cphi) * sa);
+        c[3] = Ei / Ef * (ca + rt2 * cphi * sa);
+        c[4] = 1.0 + (dE != 0.0 ? k * L * beta0 * tan(phi) * (Ei * Ef * (beta0 * beta1 - 1.0) + 1.0) /
+                                      (beta1 * Ef * dE)
+                                : 0.0);
+        c[5] = -L / (Ef * Ef * Ei * beta1) * (Ef + Ei) / (beta1 + beta0);
+        c[6] = k * sphi * v_eff / (beta1 * E1);
+        c[7] = Ei / Ef * beta0 / beta1;
+      } else {  // traveling wave (Rosenzweig & Serafini)
+        const double f = L * log1pdiv(dE / Ei);
+        const double fi = -Ep / (2.0 * Ei), fo = Ep / (2.0 * Ef), body22 = Ei / Ef;
+        c[0] = 1.0 + f * fi;
+        c[1] = f;
+        c[2] = fo * c[0] + body22 * fi;
+        c[3] = fo * f + body22;
+        c[4] = 1.0;
+        c[5] = 0.0;
+        c[6] = k * sphi * v_eff / E1;
+        c[7] = c[3];
+      }
+      c[8] = E * rel.beta / (E1 * beta1);
+      c[9] = V * rel.beta / (E1 * beta1);
+      c[10] = rel.beta * k;
+      c[11] = phi;
+      const double g0 = rel.gamma, g1 = E1 / m, b0 = rel.beta, b1 = beta1;
+      if (energy_gain_terms) {
+        const double dgamma = V / m;
+        const double b13 = b1 * b1 * b1, g13 = g1 * g1 * g1, b03 = b0 * b0 * b0, g03 = g0 * g0 * g0;
+        c[12] = L * (b03 * g03 - b13 * g13) / (2.0 * b0 * b13 * g0 * (g0 - g1) * g13);
+        c[13] = b0 * k * L * dgamma * g0 * (b13 * g13 + b0 * (g0 - g13)) * sphi /
+                (b13 * g13 * (g0 - g1) * (g0 - g1));
+        c[14] = b0 * b0 * k * k * L * dgamma / 2.0 *
+                (dgamma * (2.0 * g0 * g13 * (b0 * b13 - 1.0) + g0 * g0 + 3.0 * g1 * g1 - 2.0) /
+                     (b13 * g13 * (g0 - g1) * (g0 - g1) * (g0 - g1)) * sphi * sphi -
+                 (g1 * g0 * (b1 * b0 - 1.0) + 1.0) / (b1 * g1 * (g0 - g1) * (g0 - g1)) * cphi);
+      } else {
+        c[12] = 1.5 * L * rel.igamma2 / (b0 * b0 * b0);
+      }
+      c[kLengthSlot] = L;
+      break;
+    }
     default:
       break;
   }
@@ -321,7 +389,8 @@ __device__ __forceinline__ uint32_t and_over_group(uint32_t f) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 compose_maps_kernel(Program prog, int32_t op_begin, int32_t op_end, ScalarRef energy,
-                    ScalarRef mass, T* __restrict__ records, int64_t record_len) {
+                    ScalarRef mass, ScalarRef charge, int32_t n_apertures, T* __restrict__ records,
+                    int64_t record_len) {
   __shared__ double coef[kChunk][kCoef];
   __shared__ int32_t codes[kChunk];
 
@@ -330,9 +399,11 @@ compose_maps_kernel(Program prog, int32_t op_begin, int32_t op_end, ScalarRef en
   const int lane = tid;  // only meaningful for tid < 8
 
   Relativistic rel;
+  const double mass_value = load_scalar(mass.ptr, 0, mass.dtype);
+  const double charge_value = charge.ptr ? load_scalar(charge.ptr, 0, charge.dtype) : -1.0;
   {
     const double e = load_scalar(energy.ptr, b * energy.stride, energy.dtype);
-    const double m = load_scalar(mass.ptr, 0, mass.dtype);
+    const double m = mass_value;
     rel.gamma = e / m;
     rel.igamma2 = 1.0 / (rel.gamma * rel.gamma);
     rel.beta = sqrt(1.0 - rel.igamma2);
@@ -352,7 +423,7 @@ compose_maps_kernel(Program prog, int32_t op_begin, int32_t op_end, ScalarRef en
     const int32_t n = min(kChunk, op_end - chunk);
     for (int32_t i = tid; i < n; i += kThreads) {
       codes[i] = prog.opcodes[chunk + i];
-      element_coefficients(prog, chunk + i, b, rel, coef[i]);
+      element_coefficients(prog, chunk + i, b, rel, mass_value, charge_value, coef[i]);
     }
     __syncthreads();
 
@@ -427,6 +498,30 @@ compose_maps_kernel(Program prog, int32_t op_begin, int32_t op_end, ScalarRef en
             for (int r = 0; r < 6; ++r) v[r] = w[r];
             break;
           }
+          case CH_OP_CAVITY: {
+            // snapshot the rows (tau, delta) at the cavity entrance + the non-linear tail
+            T* block = rec + CH_RECORD_HEADER + CH_RECORD_MAP + n_apertures * CH_RECORD_APERTURE;
+            if (lane < 7) {
+              block[lane] = static_cast<T>(v[4]);
+              block[7 + lane] = static_cast<T>(v[5]);
+            } else {
+              double sphi, cphi;
+              sincos(c[11], &sphi, &cphi);
+              block[14] = static_cast<T>(c[8]);
+              block[15] = static_cast<T>(c[9]);
+              block[16] = static_cast<T>(c[10]);
+              block[17] = static_cast<T>(sphi);
+              block[18] = static_cast<T>(cphi);
+              block[19] = static_cast<T>(c[12]);
+              block[20] = static_cast<T>(c[13]);
+              block[21] = static_cast<T>(c[14]);
+              block[22] = block[23] = T(0);
+            }
+            mix(v[0], v[1], c[0], c[1], c[2], c[3]);
+            mix(v[2], v[3], c[0], c[1], c[2], c[3]);
+            mix(v[4], v[5], c[4], c[5], c[6], c[7]);
+            break;
+          }
           case CH_OP_APERTURE: {
             uint32_t f = kAllFlags;
             if (lane < 7) {
@@ -486,6 +581,7 @@ compose_maps_kernel(Program prog, int32_t op_begin, int32_t op_end, ScalarRef en
 extern "C" int ch_compose_maps(const ch_program* program, int32_t op_begin, int32_t op_end,
                                int64_t n_settings, const void* energy, int64_t energy_stride,
                                int32_t energy_dtype, const void* mass_eV, int32_t mass_dtype,
+                               const void* num_elementary_charges, int32_t charge_dtype,
                                void* records, int64_t record_len, int32_t record_dtype,
                                void* stream) {
   CH_REQUIRE(program != nullptr, "ch_compose_maps: program is NULL");
@@ -502,14 +598,19 @@ extern "C" int ch_compose_maps(const ch_program* program, int32_t op_begin, int3
   ch::Program prog{program->opcodes, program->op_flags, program->slot_begin, program->slots};
   ch::ScalarRef e{energy, energy_stride, energy_dtype};
   ch::ScalarRef m{mass_eV, 0, mass_dtype};
+  ch::ScalarRef q{num_elementary_charges, 0, charge_dtype};
+  // apertures in the record: everything beyond header + map, minus an optional cavity block
+  const int64_t extra = record_len - CH_RECORD_LEN(0);
+  const int32_t n_apertures = static_cast<int32_t>(
+      (extra % CH_RECORD_APERTURE == 0 ? extra : extra - CH_RECORD_CAVITY) / CH_RECORD_APERTURE);
   const unsigned blocks = static_cast<unsigned>(n_settings);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (record_dtype == CH_F32) {
     ch::compose_maps_kernel<float><<<blocks, ch::kThreads, 0, s>>>(
-        prog, op_begin, op_end, e, m, static_cast<float*>(records), record_len);
+        prog, op_begin, op_end, e, m, q, n_apertures, static_cast<float*>(records), record_len);
   } else {
     ch::compose_maps_kernel<double><<<blocks, ch::kThreads, 0, s>>>(
-        prog, op_begin, op_end, e, m, static_cast<double*>(records), record_len);
+        prog, op_begin, op_end, e, m, q, n_apertures, static_cast<double*>(records), record_len);
   }
   CH_LAUNCH_CHECK();
   return CH_OK;

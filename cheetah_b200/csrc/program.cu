@@ -44,9 +44,9 @@ extern "C" int ch_program_create(const int32_t* opcodes_host, const int32_t* op_
   for (int32_t i = 0; i < n_ops; ++i) {
     CH_REQUIRE(slot_begin_host[i] <= slot_begin_host[i + 1],
                "ch_program_create: slot_begin not monotonic at op %d", i);
-    CH_REQUIRE(opcodes_host[i] >= CH_OP_IDENTITY && opcodes_host[i] <= CH_OP_APERTURE,
+    CH_REQUIRE(opcodes_host[i] >= CH_OP_IDENTITY && opcodes_host[i] <= CH_OP_CAVITY,
                "ch_program_create: unknown opcode %d at op %d", opcodes_host[i], i);
-    static const int kMinSlots[] = {0, 1, 1, 5, 9, 4, 4, 1, 1, 2};
+    static const int kMinSlots[] = {0, 1, 1, 5, 9, 4, 4, 1, 1, 2, 5};
     CH_REQUIRE(slot_begin_host[i + 1] - slot_begin_host[i] >= kMinSlots[opcodes_host[i]],
                "ch_program_create: op %d (opcode %d) has too few slots", i, opcodes_host[i]);
   }

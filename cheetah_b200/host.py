@@ -123,8 +123,8 @@ class HostTracker:
         if len(sections) != 1 or not isinstance(sections[0], lowering.LinearSection):
             raise NotImplementedError("HostTracker handles lattices with one linear section")
         section = sections[0]
-        mass = beam_cpu.species.mass_eV.to(device=device, dtype=torch.float64)
-        records, vm = tracking._compose(program, section, self.energy_dev, mass, dtype)
+        species = beam_cpu.species.__class__(beam_cpu.species.name, device=device, dtype=dtype)
+        records, vm = tracking._compose(program, section, self.energy_dev, species, dtype)
         n_settings = math.prod(vm)
         assert n_settings == self.n_settings, (n_settings, self.n_settings)
         rec_len = records.shape[1]

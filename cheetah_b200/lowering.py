@@ -54,6 +54,7 @@ class LinearSection:
     survival_shape: tuple = ()         # ... of everything up to and including the last aperture
     has_maps: bool = False             # any non-identity op
     apertures: list = field(default_factory=list)
+    cavity: object = None              # active Cavity closing the section (element, gain flag)
 
 
 @dataclass
@@ -261,6 +262,21 @@ def lower(elements, device: torch.device, target_shape: tuple = ()) -> LatticePr
                 Op(_capi.OP_APERTURE, int(shape == "elliptical"),
                    [SlotSpec(element.x_max), SlotSpec(element.y_max)], element)
             )
+        elif kind == "Cavity":
+            # active cavity: its R matrix joins the section's cumulative map, its non-linear
+            # longitudinal tail is applied by the apply kernel; the beam energy changes, so
+            # the section ends here (cavity.py:100-251)
+            sec = open_section()
+            sec.has_maps = True
+            gain_flag = torch.zeros((), dtype=torch.float32, device=device)
+            traveling = getattr(element, "cavity_type", "standing_wave") == "traveling_wave"
+            ops.append(
+                Op(_capi.OP_CAVITY, int(traveling),
+                   [_length(element), SlotSpec(element.voltage), SlotSpec(element.phase),
+                    SlotSpec(element.frequency), SlotSpec(gain_flag)], element)
+            )
+            sec.cavity = (element, gain_flag)
+            close_section()
         elif kind == "SpaceChargeKick":
             close_section()
             stages.append(Barrier(element, "space_charge"))

@@ -63,9 +63,16 @@ def _index_table(source_shape: tuple, out_shape: tuple, device) -> torch.Tensor 
     return index.reshape(source_shape).expand(out_shape).reshape(-1).contiguous()
 
 
-def _compose(program, section, energy: torch.Tensor, mass_eV: torch.Tensor, dtype):
+def _compose(program, section, energy: torch.Tensor, species, dtype):
     """Run ``ch_compose_maps`` for one section -> records ``(*map_shape, record_len)``."""
     device = energy.device
+    mass_eV, charge = species.mass_eV, species.num_elementary_charges
+    if section.cavity is not None:
+        # the reference switches to the energy-gain second-order terms when ANY setting of the
+        # batch gains energy (cavity.py:155); evaluated on the device, no host sync
+        element, gain_flag = section.cavity
+        delta_energy = element.voltage * element.phase.deg2rad().cos() * charge * -1
+        gain_flag.copy_((delta_energy > 0).any())
     map_shape = tuple(torch.broadcast_shapes(section.lattice_shape, energy.shape))
     n_settings = math.prod(map_shape)
     if energy.dtype not in (torch.float32, torch.float64):
@@ -75,7 +82,7 @@ def _compose(program, section, energy: torch.Tensor, mass_eV: torch.Tensor, dtyp
     else:
         energy = energy.expand(map_shape).contiguous()
         energy_stride = 1
-    rec_len = _capi.record_len(section.n_apertures)
+    rec_len = _capi.record_len(section.n_apertures, section.cavity is not None)
     records = torch.empty((n_settings, rec_len), dtype=dtype, device=device)
     with torch.cuda.device(device):
         _capi.check(
@@ -83,6 +90,7 @@ def _compose(program, section, energy: torch.Tensor, mass_eV: torch.Tensor, dtyp
                 program.native, section.op_begin, section.op_end, n_settings,
                 energy.data_ptr(), energy_stride, _capi.dtype_code(energy.dtype),
                 mass_eV.data_ptr(), _capi.dtype_code(mass_eV.dtype),
+                charge.data_ptr(), _capi.dtype_code(charge.dtype),
                 records.data_ptr(), rec_len, _capi.dtype_code(dtype),
                 _capi.current_stream(device),
             )
@@ -119,7 +127,7 @@ def first_order_transfer_map(elements, energy: torch.Tensor, species) -> torch.T
     if len(sections) != 1 or len(program.stages) != 1 or sections[0].n_apertures:
         raise ValueError("first_order_transfer_map needs a run of skippable elements")
     dtype = energy.dtype if energy.dtype in (torch.float32, torch.float64) else torch.float32
-    records, map_shape = _compose(program, sections[0], energy, species.mass_eV, dtype)
+    records, map_shape = _compose(program, sections[0], energy, species, dtype)
     return _maps_from_records(records, map_shape)
 
 
@@ -146,8 +154,15 @@ def _track_linear_section(program, section, beam, moments: str | None = None):
     n = particles.shape[-2]
     vp = tuple(particles.shape[:-2])
 
-    records, vm = _compose(program, section, beam.energy, beam.species.mass_eV, dtype)
+    records, vm = _compose(program, section, beam.energy, beam.species, dtype)
     new_s = beam.s + _section_length(records, vm, section.length_shape)
+    new_energy = beam.energy
+    if section.cavity is not None:
+        cavity = section.cavity[0]
+        new_energy = beam.energy + (
+            cavity.voltage * cavity.phase.deg2rad().cos()
+            * beam.species.num_elementary_charges * -1
+        ).to(beam.energy.dtype)
 
     if not section.has_maps and section.n_apertures == 0 and moments is None:
         return beam.__class__(
@@ -218,7 +233,7 @@ def _track_linear_section(program, section, beam, moments: str | None = None):
 
     observed = None
     if sums is not None:
-        observed = BeamMoments.from_sums(sums.reshape(*vo, _capi.MOMENTS), beam.energy, new_s, dtype)
+        observed = BeamMoments.from_sums(sums.reshape(*vo, _capi.MOMENTS), new_energy, new_s, dtype)
     if moments == "only":
         return None, observed
 
@@ -235,7 +250,7 @@ def _track_linear_section(program, section, beam, moments: str | None = None):
         new_survival = beam.survival_probabilities
 
     outgoing = beam.__class__(
-        out, beam.energy, particle_charges=beam.particle_charges,
+        out, new_energy, particle_charges=beam.particle_charges,
         survival_probabilities=new_survival, s=new_s, species=beam.species.clone(),
     )
     try:
@@ -331,7 +346,11 @@ def _track_parameter_beam(program, beam):
                 _physics_warning(), stacklevel=3,
             )
         dtype = mu.dtype
-        records, vm = _compose(program, stage, beam.energy, beam.species.mass_eV, dtype)
+        if stage.cavity is not None:
+            raise NotImplementedError(
+                "cheetah_b200: an active Cavity is only accelerated for `ParticleBeam`"
+            )
+        records, vm = _compose(program, stage, beam.energy, beam.species, dtype)
         tm = _maps_from_records(records, vm)
         mu = (tm @ mu.unsqueeze(-1)).squeeze(-1)
         cov = tm @ cov @ tm.mT

@@ -63,8 +63,15 @@ enum {
   CH_OP_CUSTOM_MAP = 8,   /* slots: map (7x7 row-major, slot stride = 49 per setting),   */
                           /*   optional length                                           */
                           /*   custom_transfer_map.py:111-114                            */
-  CH_OP_APERTURE = 9      /* slots: x_max, y_max; op_flags bit0 = elliptical             */
+  CH_OP_APERTURE = 9,     /* slots: x_max, y_max; op_flags bit0 = elliptical             */
                           /*   aperture.py:90-132 (cut point, not a map)                 */
+  CH_OP_CAVITY = 10       /* ACTIVE cavity (voltage != 0), must be the LAST op of its     */
+                          /*   section.  slots: length, voltage, phase [deg], frequency,  */
+                          /*   gain flag (device scalar, non-zero = use the energy-gain   */
+                          /*   second-order terms: the reference's batch-wide             */
+                          /*   `(delta_energy > 0).any()`, cavity.py:155);                */
+                          /*   op_flags bit0 = traveling wave                             */
+                          /*   cavity.py:100-251 (track), :253-358 (R matrix)             */
 };
 
 /* Per-setting record written by ch_compose_maps, `record_len` scalars of the beam dtype:
@@ -75,11 +82,18 @@ enum {
  *   then for each aperture a (in lattice order), 16 scalars:
  *     [0..6] row 0 (x) and [7..13] row 2 (y) of the cumulative map from the start of the
  *     section to the aperture, [14] x_max, [15] y_max
+ *   and, if the section ends with an active cavity, CH_RECORD_CAVITY more scalars:
+ *     [0..6] row 4 (tau) and [7..13] row 5 (delta) of the cumulative map up to the cavity
+ *     ENTRANCE, [14] E0 b0 / (E1 b1), [15] V b0 / (E1 b1), [16] b0 k, [17] sin(phi),
+ *     [18] cos(phi), [19] T566, [20] T556, [21] T555 (cavity.py:113-220); the 6x7 map of the
+ *     record then includes the cavity's R matrix and ch_apply_maps replaces delta by the exact
+ *     update and adds the second-order terms to tau.
  */
 #define CH_RECORD_HEADER 2
 #define CH_RECORD_MAP 42
 #define CH_RECORD_APERTURE 16
 #define CH_RECORD_LEN(n_apertures) (CH_RECORD_HEADER + CH_RECORD_MAP + CH_RECORD_APERTURE * (n_apertures))
+#define CH_RECORD_CAVITY 24
 #define CH_MAX_APERTURES 32
 
 /* sparsity flags: a set bit means the named group of map entries is exactly zero in
@@ -120,11 +134,14 @@ int ch_program_destroy(ch_program* program);
  * for n_settings settings.  One thread per setting walks the ops, keeps the cumulative
  * 6x7 map in fp64 registers, and writes one record (layout above) per setting, rounded
  * once to `record_dtype`.  energy / mass_eV are read like slots
- * (energy[b * energy_stride]).  gamma, beta follow cheetah/utils/physics.py:4-19.      */
+ * (energy[b * energy_stride]); num_elementary_charges (a device scalar, may be NULL when
+ * the program has no active cavity) is the species' charge in e.  gamma, beta follow
+ * cheetah/utils/physics.py:4-19.                                                       */
 int ch_compose_maps(const ch_program* program, int32_t op_begin, int32_t op_end,
                     int64_t n_settings,
                     const void* energy, int64_t energy_stride, int32_t energy_dtype,
                     const void* mass_eV, int32_t mass_dtype,
+                    const void* num_elementary_charges, int32_t charge_dtype,
                     void* records, int64_t record_len, int32_t record_dtype,
                     void* stream);
 
@@ -142,7 +159,8 @@ int ch_compose_maps(const ch_program* program, int32_t op_begin, int32_t op_end,
  * settings; strides are in units of one batch entry).  Rectangular masks use strict
  * comparisons, elliptical ones x^2/x_max^2 + y^2/y_max^2 <= 1, evaluated with IEEE
  * round-to-nearest operations in the beam dtype exactly as the reference does.
- * survival_out may be NULL iff n_apertures == 0.  unit_seventh != 0 asserts that
+ * record_len is CH_RECORD_LEN(n_apertures), plus CH_RECORD_CAVITY when the section ends with
+ * an active cavity.  survival_out may be NULL iff n_apertures == 0.  unit_seventh != 0 asserts that
  * particles_in[..., 6] == 1 (then the kernel adds column 6 instead of multiplying).   */
 int ch_apply_maps(const void* particles_in, int64_t particle_stride, const int32_t* particle_index,
                   const void* survival_in, int64_t survival_stride, const int32_t* survival_index,

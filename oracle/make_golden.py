@@ -422,11 +422,71 @@ def make_space_charge() -> None:
     print("space_charge: done")
 
 
+def make_cavity() -> None:
+    """Active cavities: standing / traveling wave, accelerating and
+    decelerating, vectorised voltage, and inside a small segment (energy changes mid-lattice)."""
+    arrays = {}
+    rows = slice(None, None, ROW_STRIDE)
+    torch.manual_seed(6)
+    base = cheetah.ParticleBeam.from_parameters(
+        num_particles=4000, energy=torch.tensor(6e6), sigma_tau=torch.tensor(3e-4),
+        dtype=torch.float64,
+    )
+    arrays.update(beam_arrays("incoming", base))
+    cases = {
+        "standing": dict(length=1.0377, voltage=2.0e7, phase=-20.0, frequency=1.3e9,
+                         cavity_type="standing_wave"),
+        "traveling": dict(length=4.139, voltage=3.0e7, phase=15.0, frequency=2.998e9,
+                          cavity_type="traveling_wave"),
+        "decelerating": dict(length=1.0, voltage=-2.0e6, phase=0.0, frequency=1.3e9,
+                             cavity_type="standing_wave"),
+        "vectorised": dict(length=1.0377, voltage=[1.0e7, 2.0e7, 3.0e7], phase=[-10.0, 0.0, 30.0],
+                           frequency=1.3e9, cavity_type="standing_wave"),
+    }
+    descriptions = {}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        beam = base.to(dtype)
+        for name, kw in cases.items():
+            kwargs = {k: (v if isinstance(v, str) else torch.tensor(v, dtype=dtype))
+                      for k, v in kw.items()}
+            cavity = cheetah.Cavity(name=name, dtype=dtype, **kwargs)
+            out = cavity.track(beam)
+            arrays.update(beam_arrays(f"{name}.{tag}", out, rows))
+            if tag == "f64":
+                descriptions[name] = lattice_io._to_json([lattice_io.describe(cavity)])
+        t = lambda v: torch.tensor(v, dtype=dtype)  # noqa: E731
+        segment = cheetah.Segment([
+            cheetah.Drift(length=t(0.3), dtype=dtype),
+            cheetah.Cavity(length=t(1.0377), voltage=t(1.5e7), phase=t(-5.0), frequency=t(1.3e9),
+                           name="c1", dtype=dtype),
+            cheetah.Quadrupole(length=t(0.2), k1=t(3.0), dtype=dtype),
+            cheetah.Aperture(x_max=t(1.5e-4), y_max=t(2e-4), dtype=dtype),
+            cheetah.Drift(length=t(0.5), dtype=dtype),
+            cheetah.Cavity(length=t(1.0377), voltage=t(2.5e7), phase=t(10.0), frequency=t(1.3e9),
+                           name="c2", dtype=dtype),
+            cheetah.Drift(length=t(0.4), dtype=dtype),
+        ])
+        out = segment.track(beam)
+        arrays.update(beam_arrays(f"segment.{tag}", out, rows))
+        if tag == "f64":
+            descriptions["segment"] = lattice_io._to_json(lattice_io.describe(segment)["elements"])
+            print("cavity segment: energy", out.energy.item(), "survival",
+                  out.survival_probabilities.mean().item())
+    np.savez_compressed(OUT / "cavity.npz", **arrays)
+    with (OUT / "cavity.json").open("w") as f:
+        json.dump(descriptions, f, separators=(",", ":"))
+    print("cavity: done")
+
+
 if __name__ == "__main__":
+    if "--only-cavity" in sys.argv:
+        make_cavity()
+        sys.exit(0)
     make_consistency()
     make_ares()
     make_aperture()
     make_cloud_in_cell()
     make_space_charge()
+    make_cavity()
     for path in sorted(OUT.iterdir()):
         print(f"{path.name:40s} {path.stat().st_size / 1024:8.1f} KiB")

@@ -479,6 +479,73 @@ def track_aperture(el: dict, beam: dict) -> dict:
     return _with(beam, survival_probabilities=beam["survival_probabilities"] * mask)
 
 
+def track_cavity(el: dict, beam: dict) -> dict:
+    """Active cavity, ParticleBeam branch (cheetah/accelerator/cavity.py:100-251): linear R,
+    then the exact energy-deviation update and second-order longitudinal terms."""
+    particles = beam["particles"]
+    energy, mass_eV = beam["energy"], beam["mass_eV"]
+    charges = beam["num_elementary_charges"]
+    length = _get(el, "length", particles)
+    voltage = _get(el, "voltage", particles)
+    phase = _get(el, "phase", particles)
+    frequency = _get(el, "frequency", particles)
+
+    gamma0, igamma2, beta0 = relativistic_factors(energy, mass_eV)
+    phi = phase.deg2rad()
+    tm = _cavity_map(el, energy, mass_eV, charges)
+    out = particles @ tm.mT
+    delta_energy = voltage * phi.cos() * charges * -1
+    T566 = 1.5 * length * igamma2 / beta0.pow(3)
+    T556 = length.new_zeros(())
+    T555 = length.new_zeros(())
+    k = 2.0 * torch.pi * frequency / SPEED_OF_LIGHT
+    outgoing_energy = energy + delta_energy
+    gamma1, _, beta1 = relativistic_factors(outgoing_energy, mass_eV)
+
+    out[..., 5] = particles[..., 5] * energy.unsqueeze(-1) * beta0.unsqueeze(-1) / (
+        outgoing_energy.unsqueeze(-1) * beta1.unsqueeze(-1)
+    ) + voltage.unsqueeze(-1) * beta0.unsqueeze(-1) / (
+        outgoing_energy.unsqueeze(-1) * beta1.unsqueeze(-1)
+    ) * (
+        (-particles[..., 4] * beta0.unsqueeze(-1) * k.unsqueeze(-1) + phi.unsqueeze(-1)).cos()
+        - phi.cos().unsqueeze(-1)
+    )
+    dgamma = voltage / mass_eV
+    if (delta_energy > 0).any():
+        T566 = (
+            length
+            * (beta0.pow(3) * gamma0.pow(3) - beta1.pow(3) * gamma1.pow(3))
+            / (2.0 * beta0 * beta1.pow(3) * gamma0 * (gamma0 - gamma1) * gamma1.pow(3))
+        )
+        T556 = (
+            beta0 * k * length * dgamma * gamma0
+            * (beta1.pow(3) * gamma1.pow(3) + beta0 * (gamma0 - gamma1.pow(3)))
+            * phi.sin()
+            / (beta1.pow(3) * gamma1.pow(3) * (gamma0 - gamma1).square())
+        )
+        T555 = (
+            beta0.square() * k.square() * length * dgamma / 2.0
+            * (
+                dgamma
+                * (
+                    2.0 * gamma0 * gamma1.pow(3) * (beta0 * beta1.pow(3) - 1.0)
+                    + gamma0.square() + 3.0 * gamma1.square() - 2.0
+                )
+                / (beta1.pow(3) * gamma1.pow(3) * (gamma0 - gamma1).pow(3))
+                * phi.sin().square()
+                - (gamma1 * gamma0 * (beta1 * beta0 - 1.0) + 1.0)
+                / (beta1 * gamma1 * (gamma0 - gamma1).square())
+                * phi.cos()
+            )
+        )
+    out[..., 4] = out[..., 4] + (
+        T566.unsqueeze(-1) * particles[..., 5].square()
+        + T556.unsqueeze(-1) * particles[..., 4] * particles[..., 5]
+        + T555.unsqueeze(-1) * particles[..., 4].square()
+    )
+    return _with(beam, particles=out, energy=outgoing_energy, s=beam["s"] + length)
+
+
 # --------------------------------------------------------------------------------------
 # Space charge
 # --------------------------------------------------------------------------------------
@@ -785,6 +852,8 @@ def track(elements: list, beam: dict) -> dict:
             beam = track_aperture(el, beam)
         elif el["type"] == "SpaceChargeKick":
             beam = track_space_charge(el, beam)
+        elif el["type"] == "Cavity":
+            beam = track_cavity(el, beam)
         else:
             raise NotImplementedError(
                 f"oracle: non-skippable element type {el['type']} is outside the hot path"

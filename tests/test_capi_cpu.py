@@ -96,7 +96,12 @@ def test_cavity_skippability_is_watched():
     assert isinstance(program.stages[0], lowering.LinearSection) and not program.is_stale()
     cavity.voltage.fill_(1e6)
     assert program.is_stale()
-    assert lowering.lower([cavity], torch.device("cpu")).stages[0].kind == "unsupported"
+    # an active cavity closes its linear section and contributes the non-linear tail
+    active = lowering.lower([cb.Drift(length=torch.tensor(1.0)), cavity, cb.Marker()],
+                            torch.device("cpu"))
+    assert [type(s).__name__ for s in active.stages] == ["LinearSection", "LinearSection"]
+    assert active.stages[0].cavity[0] is cavity and active.stages[1].cavity is None
+    assert [op.opcode for op in active.ops] == [_capi.OP_DRIFT, _capi.OP_CAVITY, _capi.OP_IDENTITY]
 
 
 def test_element_api_mirrors_the_reference():

@@ -314,3 +314,28 @@ def test_errors_are_loud():
         )
     with pytest.raises(TypeError):
         cb.Drift(length=torch.tensor(1.0, device=DEVICE)).track("not a beam")
+
+
+# ---- active cavities -------------------------------------------------------
+@pytest.mark.parametrize("tag,dtype", [("f64", torch.float64), ("f32", torch.float32)])
+@pytest.mark.parametrize("case", ["standing", "traveling", "decelerating", "vectorised", "segment"])
+def test_active_cavity_against_reference_outputs(case, tag, dtype):
+    """Active Cavity.track (cheetah/accelerator/cavity.py:100-251): linear R + exact delta update
+    + second-order tau terms, and the energy change seen by the elements downstream."""
+    from .test_oracle_golden import CAVITY, cavity_lattices
+
+    lattice = cavity_lattices(dtype)[case]
+    beam = gu.beam_dict(CAVITY, "incoming", dtype)
+    out = gu.product_segment(lattice, DEVICE, dtype).track(gu.product_beam(beam, DEVICE, dtype))
+    truth = gu.beam_dict(CAVITY, f"{case}.f64", torch.float64)
+    rows = slice(None, None, 4)
+    assert out.particles.shape[:-2] == truth["particles"].shape[:-2]
+    # float32: compared with the float64 reference; delta carries the cos(phi + e) - cos(phi)
+    # cancellation in the reference's own float32 path, ours is evaluated without it
+    tol = 1e-10 if dtype == torch.float64 else 5e-6
+    assert gu.column_scaled_error(out.particles[..., rows, :], truth["particles"]) < tol
+    assert torch.allclose(out.energy.cpu().double(), truth["energy"], rtol=1e-12 if dtype == torch.float64 else 1e-6)
+    assert torch.allclose(out.s.cpu().double(), truth["s"], rtol=1e-6)
+    assert torch.equal(
+        out.survival_probabilities.cpu().double()[..., rows], truth["survival_probabilities"]
+    )

@@ -69,7 +69,9 @@ def test_reference_space_charge_and_superimposed_lower(cheetah):
     ]
     program = lowering.lower(elements, torch.device("cpu"))
     kinds = [getattr(s, "kind", "linear") for s in program.stages]
-    assert kinds == ["linear", "space_charge", "linear", "unsupported"]
-    assert len(program.ops) == 4  # two half quadrupoles + BPM, then the bend
+    # the active cavity joins (and closes) the bend's linear section
+    assert kinds == ["linear", "space_charge", "linear"]
+    assert program.stages[2].cavity[0] is elements[3]
+    assert len(program.ops) == 5  # two half quadrupoles + BPM, the bend, the cavity
     dipole = program.ops[3]
     assert torch.allclose(dipole.resolved[3][0], t(0.15))  # e1 = rbend_e1 + angle / 2
