@@ -344,7 +344,8 @@ def main() -> None:
             "value": args.settings * args.particles * N_ELEMENTS / (o_ms * 1e-3),
             "unit": UNIT,
             "ms_per_step": o_ms,
-            "mean_sigma_x": float(observed.sigma[..., 0].mean()),
+            # settings that lose every particle have no sigma (NaN, as in the reference)
+            "mean_sigma_x": float(observed.sigma[..., 0].nanmean()),
         }
 
     # ---- end to end through the host-buffer API -------------------------------------------------
@@ -373,6 +374,7 @@ def main() -> None:
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
+        e2e_h2d, e2e_d2h = tracker.h2d_bytes, tracker.d2h_bytes  # of HostTracker.track
         e2e_observables = None
         if not args.no_observables:
             tracker.track_moments(host_beam)
@@ -400,13 +402,13 @@ def main() -> None:
         e2e = {
             "value": args.settings * args.particles * N_ELEMENTS / e2e_s,
             "unit": UNIT,
-            "h2d_bytes_per_step": tracker.h2d_bytes,
-            "d2h_bytes_per_step": tracker.d2h_bytes,
+            "h2d_bytes_per_step": e2e_h2d,
+            "d2h_bytes_per_step": e2e_d2h,
             "ms_per_step": e2e_s * 1e3,
             "steps": args.e2e_steps,
             "api": "cheetah_b200.host.HostTracker.track (CPU tensors in, pinned host ring out; "
                    "bytes are per rank)",
-            "d2h_gbs_per_rank": tracker.d2h_bytes / e2e_s / 1e9,
+            "d2h_gbs_per_rank": e2e_d2h / e2e_s / 1e9,
         }
         del tracker
         torch.cuda.empty_cache()

@@ -39,12 +39,16 @@ _TENSOR_FIELDS = {
         "effect_length", "grid_extent_x", "grid_extent_y", "grid_extent_tau",
     ],
     "CustomTransferMap": ["length", "predefined_transfer_map"],
+    "TransverseDeflectingCavity": [
+        "length", "voltage", "phase", "frequency", "misalignment", "tilt",
+    ],
 }
 _PLAIN_FIELDS = {
     "Drift": ["tracking_method"],
-    "Quadrupole": ["tracking_method"],
-    "Dipole": ["tracking_method"],
-    "RBend": ["tracking_method"],
+    "Quadrupole": ["tracking_method", "num_steps"],
+    "Dipole": ["tracking_method", "fringe_at"],
+    "RBend": ["tracking_method", "fringe_at"],
+    "TransverseDeflectingCavity": ["num_steps"],
     "Sextupole": ["tracking_method"],
     "Cavity": ["cavity_type"],
     "BPM": ["is_active"],

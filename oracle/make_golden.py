@@ -478,9 +478,203 @@ def make_cavity() -> None:
     print("cavity: done")
 
 
+# --------------------------------------------------------------------------------------
+# 7. non-linear tracking methods: drift_kick_drift (Bmad-X) and second_order
+# --------------------------------------------------------------------------------------
+NONLINEAR_CONSISTENCY = {
+    # the reference's own golden pickles, tests/conftest.py:26-131
+    ("Dipole", "second_order"): {"length": 1.0, "angle": [1.0, -2.0], "tilt": 0.42},
+    ("Dipole", "drift_kick_drift"): {"length": 1.0, "angle": [1.0, -2.0], "tilt": 0.42},
+    ("Drift", "second_order"): {"length": [1.0, -1.0]},
+    ("Drift", "drift_kick_drift"): {"length": [1.0, -1.0]},
+    ("Quadrupole", "second_order"): {
+        "length": 1.0, "k1": [1.0, -2.0], "tilt": 0.42, "misalignment": [0.01, -0.02]},
+    ("Quadrupole", "drift_kick_drift"): {
+        "length": 1.0, "k1": [1.0, -2.0], "tilt": 0.42, "misalignment": [0.01, -0.02]},
+    ("RBend", "second_order"): {"length": 1.0, "angle": [1.0, -2.0], "tilt": 0.42},
+    ("RBend", "drift_kick_drift"): {"length": 1.0, "angle": [1.0, -2.0], "tilt": 0.42},
+    ("Sextupole", "second_order"): {
+        "length": 1.0, "k2": [1.0, -2.0], "tilt": 0.42, "misalignment": [0.01, -0.02]},
+    ("TransverseDeflectingCavity", "inactive"): {"length": 1.0, "voltage": 0.0},
+    ("TransverseDeflectingCavity", "active"): {"length": 1.0, "voltage": 1e6},
+}
+
+
+def _tensor_kwargs(kw: dict, dtype) -> dict:
+    return {
+        k: (torch.tensor(v, dtype=dtype) if isinstance(v, (float, int, list)) and k != "num_steps"
+            else v)
+        for k, v in kw.items()
+    }
+
+
+def make_nonlinear() -> None:
+    resources = REF / "tests" / "resources"
+    rows = slice(None, None, ROW_STRIDE)
+    arrays, lattices = {}, {}
+
+    # (a) the reference's consistency pickles (incoming beam = consistency.npz "incoming")
+    with (resources / "ACHIP_EA1_2021.1351.001_subsampled_3000.pkl").open("rb") as f:
+        incoming = pickle.load(f).to(torch.float64)
+    for (cls_name, label), kw in NONLINEAR_CONSISTENCY.items():
+        key = f"consistency.{cls_name}_{label}"
+        kwargs = _tensor_kwargs(kw, torch.float32)
+        if cls_name != "TransverseDeflectingCavity":
+            kwargs["tracking_method"] = label
+        element = getattr(cheetah, cls_name)(name=label, **kwargs).to(torch.float64)
+        lattices[key] = lattice_io._to_json([lattice_io.describe(element)])
+        with (resources / "consistency_expected_outgoing" /
+              f"{cls_name}_ParticleBeam_{label}.pkl").open("rb") as f:
+            expected = pickle.load(f)
+        arrays.update(beam_arrays(f"{key}.expected", expected, rows))
+        actual = element.track(incoming)
+        assert torch.allclose(actual.particles, expected.particles), key
+
+    # (b) the Bmad-X fixtures (tests/test_drift.py:43-69, test_quadrupole.py:173-208,
+    #     test_dipole.py:108-150, test_transverse_deflecting_cavity.py:10-43)
+    bmadx_incoming = torch.load(resources / "bmadx" / "incoming.pt", weights_only=False)
+    # particles are independent in these elements: every 4th one is stored, in and out
+    arrays.update(beam_arrays("bmadx.incoming", bmadx_incoming, rows))
+    angle = 20 * torch.pi / 180
+    bmadx_cases = {
+        "drift": ("Drift", {"length": 1.0, "tracking_method": "drift_kick_drift"}),
+        "quadrupole": ("Quadrupole", {
+            "length": 1.0, "k1": 10.0, "misalignment": [0.01, -0.02], "tilt": 0.5,
+            "num_steps": 10, "tracking_method": "drift_kick_drift"}),
+        "dipole": ("Dipole", {
+            "length": 0.5, "angle": angle, "dipole_e1": angle / 2, "dipole_e2": angle - angle / 2,
+            "tilt": 0.1, "fringe_integral": 0.5, "fringe_integral_exit": 0.5, "gap": 0.05,
+            "gap_exit": 0.05, "fringe_at": "both", "fringe_type": "linear_edge",
+            "tracking_method": "drift_kick_drift"}),
+        "transverse_deflecting_cavity": ("TransverseDeflectingCavity", {
+            "length": 1.0, "voltage": 1e7, "phase": 0.2, "frequency": 1e9}),
+    }
+    for name, (cls_name, kw) in bmadx_cases.items():
+        element = getattr(cheetah, cls_name)(
+            name=name, dtype=torch.float64, **_tensor_kwargs(kw, torch.float64))
+        lattices[f"bmadx.{name}"] = lattice_io._to_json([lattice_io.describe(element)])
+        outgoing = torch.load(resources / "bmadx" / f"outgoing_{name}.pt", weights_only=False)
+        arrays[f"bmadx.{name}.expected.particles"] = np64(outgoing[0, rows])
+        actual = element.track(bmadx_incoming)
+        assert torch.allclose(actual.particles, outgoing, atol=1e-14, rtol=1e-14), name
+
+    # (c) fresh reference outputs: vectorised settings, edge cases, other species, a mixed lattice
+    torch.manual_seed(11)
+    base = cheetah.ParticleBeam.from_parameters(
+        num_particles=2000, energy=torch.tensor(5e7), sigma_x=torch.tensor(4e-4),
+        sigma_y=torch.tensor(3e-4), sigma_px=torch.tensor(2e-4), sigma_py=torch.tensor(1e-4),
+        sigma_tau=torch.tensor(5e-4), sigma_p=torch.tensor(2e-3),
+        mu_x=torch.tensor(1e-4), mu_py=torch.tensor(-5e-5), dtype=torch.float64,
+    )
+    proton = cheetah.ParticleBeam.from_parameters(
+        num_particles=2000, energy=torch.tensor(1.2e9), sigma_tau=torch.tensor(1e-3),
+        sigma_p=torch.tensor(3e-3), species=cheetah.Species("proton"), dtype=torch.float64,
+    )
+    arrays.update(beam_arrays("fresh.incoming", base))
+    arrays.update(beam_arrays("fresh.proton", proton))
+    fresh = {
+        "drift_dkd_vector": ("Drift", {"length": [0.3, 1.7, -0.4],
+                                       "tracking_method": "drift_kick_drift"}, "incoming"),
+        "drift_dkd_proton": ("Drift", {"length": 2.5, "tracking_method": "drift_kick_drift"},
+                             "proton"),
+        "quadrupole_dkd_steps": ("Quadrupole", {
+            "length": 0.4, "k1": [4.2, -7.1, 0.0], "tilt": [0.0, 0.3, -0.2],
+            "misalignment": [[0.0, 0.0], [1e-4, -2e-4], [3e-4, 0.0]], "num_steps": 5,
+            "tracking_method": "drift_kick_drift"}, "incoming"),
+        "quadrupole_dkd_proton": ("Quadrupole", {
+            "length": 0.6, "k1": 2.0, "num_steps": 3, "tracking_method": "drift_kick_drift"},
+            "proton"),
+        "dipole_dkd_zero_angle": ("Dipole", {
+            "length": 0.7, "angle": 0.0, "tracking_method": "drift_kick_drift"}, "incoming"),
+        "dipole_dkd_entrance": ("Dipole", {
+            "length": 0.8, "angle": [0.2, -0.35], "dipole_e1": 0.05, "dipole_e2": -0.03,
+            "fringe_integral": 0.4, "gap": 0.03, "gap_exit": 0.05, "fringe_integral_exit": 0.3,
+            "fringe_at": "entrance", "tracking_method": "drift_kick_drift"}, "incoming"),
+        "dipole_dkd_neither": ("Dipole", {
+            "length": 0.8, "angle": 0.25, "dipole_e1": 0.05, "tilt": 0.3,
+            "fringe_at": "neither", "tracking_method": "drift_kick_drift"}, "incoming"),
+        "rbend_dkd_exit": ("RBend", {
+            "length": 0.5, "angle": 0.3, "rbend_e1": 0.02, "rbend_e2": -0.01,
+            "fringe_integral": 0.5, "gap": 0.02, "fringe_at": "exit",
+            "tracking_method": "drift_kick_drift"}, "incoming"),
+        "tdc_vector": ("TransverseDeflectingCavity", {
+            "length": 0.6, "voltage": [2e6, -5e6], "phase": [0.1, 0.35], "frequency": 2.856e9,
+            "tilt": 0.2, "misalignment": [1e-4, -1e-4]}, "incoming"),
+        "tdc_proton": ("TransverseDeflectingCavity", {
+            "length": 0.6, "voltage": 3e7, "phase": 0.05, "frequency": 4e8}, "proton"),
+        "drift_second_order_proton": ("Drift", {"length": 1.3, "tracking_method": "second_order"},
+                                      "proton"),
+        "quadrupole_second_order": ("Quadrupole", {
+            "length": 0.3, "k1": [5.0, -12.0, 0.0], "tilt": [0.0, 0.785, 0.1],
+            "tracking_method": "second_order"}, "incoming"),
+        "sextupole_second_order": ("Sextupole", {
+            "length": 0.25, "k2": [30.0, -80.0], "misalignment": [2e-4, 1e-4],
+            "tracking_method": "second_order"}, "incoming"),
+        "dipole_second_order_k1": ("Dipole", {
+            "length": 0.9, "angle": [0.3, -0.1], "k1": [1.5, -0.8], "dipole_e1": 0.1,
+            "dipole_e2": 0.05, "fringe_integral": 0.5, "gap": 0.03, "tilt": 0.15,
+            "tracking_method": "second_order"}, "incoming"),
+        "dipole_second_order_kx2_zero": ("Dipole", {
+            "length": 0.5, "angle": 0.0, "k1": 0.0, "tracking_method": "second_order"},
+            "incoming"),
+    }
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        beams = {"incoming": base.to(dtype), "proton": proton.to(dtype)}
+        for name, (cls_name, kw, which) in fresh.items():
+            element = getattr(cheetah, cls_name)(
+                name=name, dtype=dtype, **_tensor_kwargs(kw, dtype))
+            out = element.track(beams[which])
+            arrays.update(beam_arrays(f"fresh.{name}.{tag}", out, rows))
+            if tag == "f64":
+                lattices[f"fresh.{name}"] = {
+                    "beam": which,
+                    "lattice": lattice_io._to_json([lattice_io.describe(element)]),
+                }
+        # a mixed lattice: linear runs, markers, dkd and second-order elements, an aperture
+        t = lambda v: torch.tensor(v, dtype=dtype)  # noqa: E731
+        segment = cheetah.Segment([
+            cheetah.Drift(length=t(0.4), tracking_method="drift_kick_drift", dtype=dtype),
+            cheetah.Marker(name="m1"),
+            cheetah.Quadrupole(length=t(0.2), k1=t([3.0, -3.0]), num_steps=4,
+                               tracking_method="drift_kick_drift", dtype=dtype),
+            cheetah.Drift(length=t(0.3), dtype=dtype),
+            cheetah.HorizontalCorrector(length=t(0.1), angle=t(1e-4), dtype=dtype),
+            cheetah.Dipole(length=t(0.5), angle=t(0.15), dipole_e1=t(0.07), dipole_e2=t(0.08),
+                           fringe_integral=t(0.5), gap=t(0.02),
+                           tracking_method="drift_kick_drift", dtype=dtype),
+            cheetah.BPM(name="b1"),
+            cheetah.Sextupole(length=t(0.15), k2=t(40.0), tracking_method="second_order",
+                              dtype=dtype),
+            cheetah.Aperture(x_max=t(8e-4), y_max=t(6e-4), dtype=dtype),
+            cheetah.Quadrupole(length=t(0.2), k1=t(-2.5), tracking_method="second_order",
+                               dtype=dtype),
+            cheetah.Drift(length=t(0.6), tracking_method="second_order", dtype=dtype),
+            cheetah.TransverseDeflectingCavity(length=t(0.3), voltage=t(1e6), phase=t(0.1),
+                                               frequency=t(1.3e9), dtype=dtype),
+            cheetah.Drift(length=t(0.25), dtype=dtype),
+        ])
+        out = segment.track(beams["incoming"])
+        arrays.update(beam_arrays(f"fresh.segment.{tag}", out, rows))
+        if tag == "f64":
+            lattices["fresh.segment"] = {
+                "beam": "incoming",
+                "lattice": lattice_io._to_json(lattice_io.describe(segment)["elements"]),
+            }
+            print("nonlinear segment: survival", out.survival_probabilities.mean().item(),
+                  "shape", tuple(out.particles.shape))
+    np.savez_compressed(OUT / "nonlinear.npz", **arrays)
+    with (OUT / "nonlinear.json").open("w") as f:
+        json.dump({"row_stride": ROW_STRIDE, "lattices": lattices}, f, separators=(",", ":"))
+    print("nonlinear:", len(NONLINEAR_CONSISTENCY), "+", len(bmadx_cases), "+", len(fresh) + 1,
+          "cases")
+
+
 if __name__ == "__main__":
     if "--only-cavity" in sys.argv:
         make_cavity()
+        sys.exit(0)
+    if "--only-nonlinear" in sys.argv:
+        make_nonlinear()
         sys.exit(0)
     make_consistency()
     make_ares()
@@ -488,5 +682,6 @@ if __name__ == "__main__":
     make_cloud_in_cell()
     make_space_charge()
     make_cavity()
+    make_nonlinear()
     for path in sorted(OUT.iterdir()):
         print(f"{path.name:40s} {path.stat().st_size / 1024:8.1f} KiB")

@@ -854,6 +854,12 @@ def track(elements: list, beam: dict) -> dict:
             beam = track_space_charge(el, beam)
         elif el["type"] == "Cavity":
             beam = track_cavity(el, beam)
+        elif el["type"] in (
+            "Drift", "Quadrupole", "Dipole", "RBend", "Sextupole", "TransverseDeflectingCavity"
+        ):
+            from . import nonlinear_oracle  # drift_kick_drift / second_order
+
+            beam = nonlinear_oracle.track_nonlinear(el, beam)
         else:
             raise NotImplementedError(
                 f"oracle: non-skippable element type {el['type']} is outside the hot path"

@@ -101,3 +101,22 @@ def column_scaled_error(actual: torch.Tensor, expected: torch.Tensor) -> float:
     expected = expected.detach().cpu().to(torch.float64)
     scale = expected.abs().amax(dim=-2, keepdim=True).clamp_min(1e-300)
     return float(((actual - expected).abs() / scale)[..., :6].max())
+
+
+def nonlinear_cases(dtype=torch.float64) -> tuple[dict, dict, int]:
+    """(arrays, {case: {"lattice", "beam prefix"}}, row stride) of tests/golden/nonlinear.*"""
+    arrays = load_npz("nonlinear.npz")
+    with (GOLDEN / "nonlinear.json").open() as f:
+        raw = json.load(f)
+    cases = {}
+    for key, value in raw["lattices"].items():
+        if key.startswith("fresh."):
+            cases[key] = {
+                "lattice": lattice_io._from_json(value["lattice"], dtype),
+                "beam": "fresh." + value["beam"],
+            }
+        elif key.startswith("bmadx."):
+            cases[key] = {"lattice": lattice_io._from_json(value, dtype), "beam": "bmadx.incoming"}
+        else:
+            cases[key] = {"lattice": lattice_io._from_json(value, dtype), "beam": "incoming"}
+    return arrays, cases, raw["row_stride"]
