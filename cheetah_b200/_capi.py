@@ -28,6 +28,14 @@ OP_CAVITY_OFF = 7
 OP_CUSTOM_MAP = 8
 OP_APERTURE = 9
 OP_CAVITY = 10
+OP_DKD_DRIFT = 11
+OP_DKD_QUADRUPOLE = 12
+OP_DKD_DIPOLE = 13
+OP_DKD_TDC = 14
+OP_SECOND_ORDER = 15
+NONLINEAR_OPS = (OP_DKD_DRIFT, OP_DKD_QUADRUPOLE, OP_DKD_DIPOLE, OP_DKD_TDC, OP_SECOND_ORDER)
+NL_HEADER = 8
+NL_MAX_OPS = 64
 
 RECORD_HEADER = 2
 RECORD_MAP = 42
@@ -87,6 +95,27 @@ SIGNATURES = {
             c_int64, c_int64,
             c_void_p, c_void_p, c_void_p,
             c_int32, c_int32, c_void_p,
+        ],
+    ),
+    "ch_nonlinear_constants_len": (c_int64, [c_void_p, c_int32, c_int32]),
+    "ch_nonlinear_constants": (
+        c_int32,
+        [
+            c_void_p, c_int32, c_int32, c_int64,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int32,
+            c_void_p, c_int32,
+            c_void_p, c_void_p,
+        ],
+    ),
+    "ch_track_nonlinear": (
+        c_int32,
+        [
+            c_void_p, c_int32, c_int32,
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_int64, c_int64, c_void_p,
+            c_int32, c_void_p,
         ],
     ),
     "ch_sc_beam_moments": (

@@ -172,4 +172,5 @@ struct ch_program {
   int32_t* op_flags;     // device [n_ops]
   int32_t* slot_begin;   // device [n_ops + 1]
   ch::ScalarRef* slots;  // device [n_slots]
+  int32_t* opcodes_host; // host copy of opcodes (argument checks, constant-block sizes)
 };

@@ -1,0 +1,940 @@
+// Per-particle NON-LINEAR tracking: the "drift_kick_drift" (Bmad-X) maps of Drift, Quadrupole,
+// Dipole / RBend and TransverseDeflectingCavity and the "second_order" maps (T_ijk p_j p_k) of
+// Drift, Quadrupole, Sextupole, Dipole / RBend.
+//
+// The reference tracks each such element with 50-150 elementwise PyTorch kernels over the whole
+// beam.  Here a RUN of consecutive non-linear elements (markers and inactive monitors in between
+// are no-ops) is one streaming pass: a CTA stages a tile of particles with a TMA bulk copy, every
+// thread keeps its particles' six coordinates in registers, walks the ops of the run with the
+// per-(setting, op) constants broadcast from shared memory, and the tile leaves through a bulk
+// store -- 28 B read + 28 B written per (particle, setting) for the whole run.
+//
+//   ch_nonlinear_constants: one CTA per setting, one thread per op: element parameters (slot
+//     table) -> constants in fp64 (sin/cos of tilts and bend angles, fringe kicks, the 39
+//     second-order coefficients with the reference's singularity-free compound functions),
+//     rounded once to the beam dtype.
+//   ch_track_nonlinear: the particle pass.
+//
+// Numerics.  Bmad-X coordinates (z, pz) are obtained from (tau, delta) with cancellation-free
+// forms of the reference's expressions (p^2 - p0c^2 = delta p0c (2 E0 + delta p0c), etc.), so
+// the float32 path keeps ~1e-7 relative accuracy where the reference's float32 path cancels to
+// ~1e-4; consecutive drift_kick_drift ops stay in Bmad-X coordinates (the reference converts
+// back and forth between every element; same result up to rounding).  The bend body and the TDC
+// kick, whose formulas subtract path lengths of order L, are always evaluated in fp64.
+//
+// Reference behaviour restated here (desy-ml/cheetah @ 60d1053):
+//   cheetah/utils/bmadx.py:7-318, cheetah/accelerator/drift.py:106-154,
+//   quadrupole.py:168-251, dipole.py:183-370, transverse_deflecting_cavity.py:122-209,
+//   cheetah/track_methods.py:80-281 (base_ttensor), cheetah/utils/autograd.py:108-670,
+//   cheetah/accelerator/element.py:195-225, drift.py:67-83, quadrupole.py:112-143,
+//   sextupole.py:90-116, dipole.py:396-466
+#include <type_traits>
+
+#include "ch_common.cuh"
+
+namespace ch {
+namespace {
+
+constexpr double kPi = 3.141592653589793;
+constexpr double kC = 299792458.0;
+
+struct Program {
+  const int32_t* opcodes;
+  const int32_t* op_flags;
+  const int32_t* slot_begin;
+  const ScalarRef* slots;
+};
+
+__device__ __forceinline__ double slot_value(const Program& prog, int32_t slot, int64_t b) {
+  const ScalarRef ref = prog.slots[slot];
+  return load_scalar(ref.ptr, b * ref.stride, ref.dtype);
+}
+
+// cos(sqrt x) and si(sqrt x) = sin(sqrt x) / sqrt x continued to x < 0: the real closed form of
+// the reference's complex sqrt / cos / sinc
+__device__ __forceinline__ void cos_si(double x, double& c, double& s) {
+  if (x > 0.0) {
+    const double r = sqrt(x);
+    double sn;
+    sincos(r, &sn, &c);
+    s = sn / r;
+  } else if (x < 0.0) {
+    const double r = sqrt(-x);
+    c = cosh(r);
+    s = sinh(r) / r;
+  } else {
+    c = 1.0;
+    s = 1.0;
+  }
+}
+
+// the compound functions of cheetah/utils/autograd.py with their coded limits
+__device__ __forceinline__ double si1mdiv(double x) {  // :108-128
+  if (x == 0.0) return 1.0 / 6.0;
+  if (fabs(x) < 1e-3)
+    return 1.0 / 6.0 + x * (-1.0 / 120.0 + x * (1.0 / 5040.0 + x * (-1.0 / 362880.0)));
+  double c, s;
+  cos_si(x, c, s);
+  return (1.0 - s) / x;
+}
+__device__ __forceinline__ double sicos1mdiv(double x) {  // :149-174 (limit 1/6 as coded)
+  if (x == 0.0) return 1.0 / 6.0;
+  double c, s;
+  cos_si(x, c, s);
+  return (1.0 - s * c) / x;
+}
+__device__ __forceinline__ double sipsicos3mdiv(double x) {  // :209-235
+  if (x == 0.0) return 0.0;
+  double c, s;
+  cos_si(x, c, s);
+  return (3.0 - 4.0 * s + s * c) / (2.0 * x);
+}
+__device__ __forceinline__ double cossqrtmcosdivdiff(double a, double b) {  // :361-388
+  double ca, sa, cb, sb;
+  cos_si(a, ca, sa);
+  cos_si(b, cb, sb);
+  return a != b ? (cb - ca) / (a - b) : 0.5 * sa;
+}
+__device__ __forceinline__ double simsidivdiff(double a, double b) {  // :433-461
+  double ca, sa, cb, sb;
+  cos_si(a, ca, sa);
+  cos_si(b, cb, sb);
+  if (a != b) return (sa - sb) / (b - a);
+  return b != 0.0 ? 0.5 * (sb - cb) / b : 1.0 / 6.0;
+}
+__device__ __forceinline__ double si2msi2divdiff(double a, double b) {  // :546-579
+  double ca, sa, cb, sb;
+  cos_si(a, ca, sa);
+  cos_si(b, cb, sb);
+  if (a != b) return (sb * sb - sa * sa) / (a - b);
+  return b != 0.0 ? (1.0 - cb * cb - b * sb * cb) / (b * b) : 1.0 / 3.0;
+}
+
+// ---- constant-block layouts ------------------------------------------------------------------
+// header (CH_NL_HEADER scalars per setting)
+enum { H_P0C = 0, H_MC2 = 1, H_E0 = 2, H_BETA0 = 3, H_MC2_E0_SQ = 4, H_LENGTH = 5, H_CHARGE = 6 };
+// drift_kick_drift ops
+enum { D_L = 0 };
+enum { Q_L = 0, Q_K1 = 1, Q_COS = 2, Q_SIN = 3, Q_XOFF = 4, Q_YOFF = 5, Q_STEP = 6 };
+enum {
+  B_L = 0, B_ANGLE = 1, B_COS = 2, B_SIN = 3, B_G = 4, B_HX1 = 5, B_HY1 = 6, B_HX2 = 7, B_HY2 = 8,
+  B_COSA = 9, B_SINA = 10, B_LSINC = 11, B_L2GCOSC = 12
+};
+enum { T_HALF = 0, T_COS = 1, T_SIN = 2, T_XOFF = 3, T_YOFF = 4, T_V = 5, T_KRF = 6, T_PHASE = 7 };
+// second-order ops: frame change (10), body R (9), T (39)
+enum {
+  S_COS = 0, S_SIN = 1, S_OX = 2, S_OY = 3, S_KX1 = 4, S_KY1 = 5, S_KX2 = 6, S_KY2 = 7, S_MX = 8,
+  S_MY = 9, S_R = 10, S_T = 19
+};
+enum {  // body R entries (track_methods.py:62-75)
+  R_CX = 0, R_SX = 1, R_10 = 2, R_CY = 3, R_SY = 4, R_32 = 5, R_05 = 6, R_15 = 7, R_56 = 8
+};
+
+// order of the T entries in the block (i, j, k as in track_methods.py:147-279)
+enum {
+  T000, T001, T011, T005, T015, T055, T022, T023, T033,
+  T100, T101, T111, T105, T115, T155, T122, T123, T133,
+  T202, T203, T212, T213, T225, T235,
+  T302, T303, T312, T313, T325, T335,
+  T400, T401, T411, T405, T415, T455, T422, T423, T433,
+  T_COUNT
+};
+static_assert(S_T + T_COUNT <= CH_NL_BLOCK_SECOND_ORDER, "second-order block too small");
+
+// base_ttensor (track_methods.py:80-281) in fp64; out[T_COUNT]
+__device__ void second_order_coefficients(double L, double k1, double k2, double hx, double beta,
+                                          double igamma2, double* t) {
+  const double kx2 = k1 + hx * hx, ky2 = -k1;
+  double cx, six, cy, siy;
+  cos_si(kx2 * L * L, cx, six);
+  cos_si(ky2 * L * L, cy, siy);
+  const double sx = six * L, sy = siy * L;
+  double ch, sih;
+  cos_si(0.25 * kx2 * L * L, ch, sih);
+  const double dx = 0.5 * L * L * sih * sih;
+  const double L3 = L * L * L;
+  const double a = kx2 * L * L, b = ky2 * L * L;
+  const double fx = L3 * si1mdiv(a);
+  const double f2y = L3 * sicos1mdiv(b);
+  const double j1 = fx;
+  const double j2 = L3 * sipsicos3mdiv(a);
+  const double j3 = kx2 != 0.0 ? (15.0 * L - 22.5 * sx + 9.0 * sx * cx - 1.5 * sx * cx * cx +
+                                  kx2 * sx * sx * sx) / (6.0 * kx2 * kx2 * kx2)
+                               : L3 * L3 * L / 56.0;
+  const double jden = kx2 - 4.0 * ky2;
+  const double jc = L * L * cossqrtmcosdivdiff(a, b);
+  const double js = L3 * simsidivdiff(a, b);
+  const double jd = L3 * L * si2msi2divdiff(a, b);
+  const double jf = jden != 0.0 ? (f2y - fx) / jden : L3 * L * L / 120.0;
+  const double khk = k2 + 2.0 * hx * k1;
+  const double ib = 1.0 / beta, ib2 = ib * ib, ib3 = ib2 * ib;
+  const double hx2 = hx * hx, dx2 = dx * dx;
+
+  t[T000] = -khk * (sx * sx + dx) / 6.0 - 0.5 * hx * kx2 * sx * sx;
+  t[T001] = 2.0 * (-khk * sx * dx / 6.0 + 0.5 * hx * sx * cx);
+  t[T011] = -khk * dx2 / 6.0 + 0.5 * hx * dx * cx;
+  t[T005] = 2.0 * (-hx / 12.0 * ib * khk * (3.0 * sx * j1 - dx2) + 0.5 * hx2 * ib * sx * sx +
+                   0.25 * ib * k1 * L * sx);
+  t[T015] = 2.0 * (-hx / 12.0 * ib * khk * (sx * dx2 - 2.0 * cx * j2) +
+                   0.25 * hx2 * ib * (sx * dx + cx * j1) - 0.25 * ib * (sx + L * cx));
+  t[T055] = -hx2 / 6.0 * ib2 * khk * (dx2 * dx - 2.0 * sx * j2) + 0.5 * hx2 * hx * ib2 * sx * j1 -
+            0.5 * hx * ib2 * L * sx - 0.5 * hx * ib2 * igamma2 * dx;
+  t[T022] = k1 * k2 * jd + 0.5 * (k2 + hx * k1) * dx;
+  t[T023] = 2.0 * (0.5 * k2 * js);
+  t[T033] = k2 * jd - 0.5 * hx * dx;
+  t[T100] = -khk * sx * (1.0 + 2.0 * cx) / 6.0;
+  t[T101] = -2.0 * khk * dx * (1.0 + 2.0 * cx) / 6.0;
+  t[T111] = -khk * sx * dx / 3.0 - 0.5 * hx * sx;
+  t[T105] = 2.0 * (-hx / 12.0 * ib * khk * (3.0 * cx * j1 + sx * dx) -
+                   0.25 * ib * k1 * (sx - L * cx));
+  t[T115] = 2.0 * (-hx / 12.0 * ib * khk * (3.0 * sx * j1 + dx2) + 0.25 * ib * k1 * L * sx);
+  t[T155] = -hx2 / 6.0 * ib2 * khk * (sx * dx2 - 2.0 * cx * j2) -
+            0.5 * hx * ib2 * k1 * (cx * j1 - sx * dx) - 0.5 * hx * ib2 * igamma2 * sx;
+  t[T122] = k1 * k2 * js + 0.5 * (k2 + hx * k1) * sx;
+  t[T123] = 2.0 * (0.5 * k2 * jc);
+  t[T133] = k2 * js - 0.5 * hx * sx;
+  t[T202] = 2.0 * (0.5 * k2 * (cy * jc - 2.0 * k1 * sy * js) + 0.5 * hx * k1 * sx * sy);
+  t[T203] = 2.0 * (0.5 * k2 * (sy * jc - 2.0 * cy * js) + 0.5 * hx * sx * cy);
+  t[T212] = 2.0 * (0.5 * k2 * (cy * js - 2.0 * k1 * sy * jd) + 0.5 * hx * k1 * dx * sy);
+  t[T213] = 2.0 * (0.5 * k2 * (sy * js - 2.0 * cy * jd) + 0.5 * hx * dx * cy);
+  t[T225] = 2.0 * (0.5 * hx * ib * k2 * (cy * jd - 2.0 * k1 * sy * jf) +
+                   0.5 * hx2 * ib * k1 * j1 * sy - 0.25 * ib * k1 * L * sy);
+  t[T235] = 2.0 * (0.5 * hx * ib * k2 * (sy * jd - 2.0 * cy * jf) + 0.5 * hx2 * ib * j1 * cy -
+                   0.25 * ib * (sy + L * cy));
+  t[T302] = 2.0 * (0.5 * k1 * k2 * (2.0 * cy * js - sy * jc) + 0.5 * (k2 + hx * k1) * sx * cy);
+  t[T303] = 2.0 * (0.5 * k2 * (2.0 * k1 * sy * js - cy * jc) + 0.5 * (k2 + hx * k1) * sx * sy);
+  t[T312] = 2.0 * (0.5 * k1 * k2 * (2.0 * cy * jd - sy * js) + 0.5 * (k2 + hx * k1) * dx * cy);
+  t[T313] = 2.0 * (0.5 * k2 * (2.0 * k1 * sy * jd - cy * js) + 0.5 * (k2 + hx * k1) * dx * sy);
+  t[T325] = 2.0 * (0.5 * hx * ib * k1 * k2 * (2.0 * cy * jf - sy * jd) +
+                   0.5 * hx * ib * (k2 + hx * k1) * j1 * cy + 0.25 * ib * k1 * (sy - L * cy));
+  t[T335] = 2.0 * (0.5 * hx * ib * k2 * (2.0 * k1 * sy * jf - cy * jd) +
+                   0.5 * hx * ib * (k2 + hx * k1) * j1 * sy - 0.25 * ib * k1 * L * sy);
+  t[T400] = -(hx / 12.0 * ib * khk * (sx * dx + 3.0 * j1) - 0.25 * ib * k1 * (L - sx * cx));
+  t[T401] = -2.0 * (hx / 12.0 * ib * khk * dx2 + 0.25 * ib * k1 * sx * sx);
+  t[T411] = -(hx / 6.0 * ib * khk * j2 - 0.5 * ib * sx - 0.25 * ib * k1 * (j1 - sx * dx));
+  t[T405] = -2.0 * (hx2 / 12.0 * ib2 * khk * (3.0 * dx * j1 - 4.0 * j2) +
+                    0.25 * hx * ib2 * k1 * j1 * (1.0 + cx) + 0.5 * hx * ib2 * igamma2 * sx);
+  t[T415] = -2.0 * (hx2 / 12.0 * ib2 * khk * (dx * dx2 - 2.0 * sx * j2) +
+                    0.25 * hx * ib2 * k1 * sx * j1 + 0.5 * hx * ib2 * igamma2 * dx);
+  t[T455] = -(hx2 * hx / 6.0 * ib3 * khk * (3.0 * j3 - 2.0 * dx * j2) +
+              hx2 / 6.0 * ib3 * k1 * (sx * dx2 - j2 * (1.0 + 2.0 * cx)) +
+              1.5 * ib3 * igamma2 * (hx2 * j1 - L));
+  t[T422] = -(-hx * ib * k1 * k2 * jf - 0.5 * hx * ib * (k2 + hx * k1) * j1 +
+              0.25 * ib * k1 * (L - cy * sy));
+  t[T423] = -2.0 * (-0.5 * hx * ib * k2 * jd - 0.25 * ib * k1 * sy * sy);
+  t[T433] = -(-hx * ib * k2 * jf + 0.5 * hx2 * ib * j1 - 0.25 * ib * (L + cy * sy));
+}
+
+// body R of base_rmatrix (track_methods.py:17-77) in fp64; r[9]
+__device__ void body_rmatrix(double L, double k1, double hx, double beta, double igamma2,
+                             double* r) {
+  const double kx2 = k1 + hx * hx, ky2 = -k1;
+  double cx, six, cy, siy;
+  cos_si(kx2 * L * L, cx, six);
+  cos_si(ky2 * L * L, cy, siy);
+  const double sx = six * L, sy = siy * L;
+  double ch, sih;
+  cos_si(0.25 * kx2 * L * L, ch, sih);
+  const double dx = hx * 0.5 * L * L * sih * sih;
+  r[R_CX] = cx;
+  r[R_SX] = sx;
+  r[R_10] = -kx2 * sx;
+  r[R_CY] = cy;
+  r[R_SY] = sy;
+  r[R_32] = -ky2 * sy;
+  r[R_05] = dx / beta;
+  r[R_15] = sx * hx / beta;
+  r[R_56] = hx * hx * L * L * L * si1mdiv(kx2 * L * L) / (beta * beta) - L / (beta * beta) * igamma2;
+}
+
+// pole-face kicks of the linear / second-order dipole (dipole.py:430-466)
+__device__ __forceinline__ void edge_kicks(double hx, double e, double fint, double gap, double& kx,
+                                           double& ky) {
+  const double se = sin(e);
+  const double phi = fint * hx * gap / cos(e) * (1.0 + se * se);
+  kx = hx * tan(e);
+  ky = -hx * tan(e - phi);
+}
+
+// The constants table is always fp64: the bend body and the TDC kick are evaluated in fp64 from
+// unrounded constants, everything else is rounded to the beam dtype while being staged.
+__global__ void __launch_bounds__(64)
+nonlinear_constants_kernel(Program prog, int32_t op_begin, int32_t n_ops, ScalarRef energy,
+                           ScalarRef mass, ScalarRef charge, int32_t block, double* __restrict__ out) {
+  __shared__ double lengths[64];
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  double* base = out + b * (CH_NL_HEADER + static_cast<int64_t>(n_ops) * block);
+
+  const double E0 = load_scalar(energy.ptr, b * energy.stride, energy.dtype);
+  const double mc2 = load_scalar(mass.ptr, 0, mass.dtype);
+  const double q = charge.ptr ? load_scalar(charge.ptr, 0, charge.dtype) : -1.0;
+  const double p0c = sqrt(E0 * E0 - mc2 * mc2);
+  const double gamma = E0 / mc2, igamma2 = 1.0 / (gamma * gamma), beta = sqrt(1.0 - igamma2);
+
+  double length = 0.0;
+  if (tid < n_ops) {
+    const int32_t op = op_begin + tid;
+    const int32_t code = prog.opcodes[op];
+    const int32_t flags = prog.op_flags[op];
+    const int32_t s0 = prog.slot_begin[op];
+    double c[CH_NL_BLOCK_SECOND_ORDER];
+    for (int i = 0; i < block; ++i) c[i] = 0.0;
+    switch (code) {
+      case CH_OP_DKD_DRIFT:
+        length = slot_value(prog, s0, b);
+        c[D_L] = length;
+        break;
+      case CH_OP_DKD_QUADRUPOLE: {
+        length = slot_value(prog, s0, b);
+        const double tilt = slot_value(prog, s0 + 2, b);
+        double sn, cs;
+        sincos(tilt, &sn, &cs);
+        c[Q_L] = length;
+        c[Q_K1] = slot_value(prog, s0 + 1, b);
+        c[Q_COS] = cs;
+        c[Q_SIN] = sn;
+        c[Q_XOFF] = slot_value(prog, s0 + 3, b);
+        c[Q_YOFF] = slot_value(prog, s0 + 4, b);
+        c[Q_STEP] = length / static_cast<double>(flags > 0 ? flags : 1);
+        break;
+      }
+      case CH_OP_DKD_DIPOLE: {
+        // slots: length, angle, e1, e2, fint, fint_exit, gap, gap_exit, tilt
+        length = slot_value(prog, s0, b);
+        const double angle = slot_value(prog, s0 + 1, b);
+        const double tilt = slot_value(prog, s0 + 8, b);
+        const double g = angle / length;
+        double sn, cs, sa, ca;
+        sincos(tilt, &sn, &cs);
+        sincos(angle, &sa, &ca);
+        c[B_L] = length;
+        c[B_ANGLE] = angle;
+        c[B_COS] = cs;
+        c[B_SIN] = sn;
+        c[B_G] = g;
+        for (int side = 0; side < 2; ++side) {  // dipole.py:338-370
+          const double e = slot_value(prog, s0 + 2 + side, b);
+          const double fint = slot_value(prog, s0 + 4 + side, b);
+          const double h_gap = 0.5 * slot_value(prog, s0 + 6 + side, b);
+          const double se = sin(e);
+          c[side ? B_HX2 : B_HX1] = g * tan(e);
+          c[side ? B_HY2 : B_HY1] =
+              -g * tan(e - 2.0 * fint * h_gap * g * (1.0 + se * se) / cos(e));
+        }
+        c[B_COSA] = ca;
+        c[B_SINA] = sa;
+        const double sinc_a = angle != 0.0 ? sa / angle : 1.0;
+        double sh, chh;
+        sincos(0.5 * angle, &sh, &chh);
+        const double sinc_h = angle != 0.0 ? sh / (0.5 * angle) : 1.0;
+        c[B_LSINC] = length * sinc_a;
+        c[B_L2GCOSC] = length * length * g * (-0.5 * sinc_h * sinc_h);
+        break;
+      }
+      case CH_OP_DKD_TDC: {
+        // slots: length, voltage, phase, frequency, tilt, mis_x, mis_y
+        length = slot_value(prog, s0, b);
+        const double tilt = slot_value(prog, s0 + 4, b);
+        const double frequency = slot_value(prog, s0 + 3, b);
+        double sn, cs;
+        sincos(tilt, &sn, &cs);
+        c[T_HALF] = 0.5 * length;
+        c[T_COS] = cs;
+        c[T_SIN] = sn;
+        c[T_XOFF] = slot_value(prog, s0 + 5, b);
+        c[T_YOFF] = slot_value(prog, s0 + 6, b);
+        c[T_V] = slot_value(prog, s0 + 1, b) * -1.0 * q / p0c;
+        c[T_KRF] = 2.0 * kPi * frequency / kC;
+        c[T_PHASE] = 2.0 * kPi * slot_value(prog, s0 + 2, b);
+        break;
+      }
+      case CH_OP_SECOND_ORDER: {
+        // slots: length, k1, k2, angle, e1, e2, fint, fint_exit, gap, tilt, mis_x, mis_y;
+        // op_flags bit0: bend (pole faces + rotation, no offsets)
+        length = slot_value(prog, s0, b);
+        const double k1 = slot_value(prog, s0 + 1, b);
+        const double k2 = slot_value(prog, s0 + 2, b);
+        const double tilt = slot_value(prog, s0 + 9, b);
+        double sn = 0.0, cs = 1.0;
+        if (tilt != 0.0) sincos(tilt, &sn, &cs);
+        c[S_COS] = cs;
+        c[S_SIN] = sn;
+        double hx = 0.0;
+        if (flags & 1) {
+          hx = slot_value(prog, s0 + 3, b) / length;
+          const double gap = slot_value(prog, s0 + 8, b);
+          edge_kicks(hx, slot_value(prog, s0 + 4, b), slot_value(prog, s0 + 6, b), gap, c[S_KX1],
+                     c[S_KY1]);
+          edge_kicks(hx, slot_value(prog, s0 + 5, b), slot_value(prog, s0 + 7, b), gap, c[S_KX2],
+                     c[S_KY2]);
+        } else {
+          const double mx = slot_value(prog, s0 + 10, b), my = slot_value(prog, s0 + 11, b);
+          c[S_OX] = -mx * cs - my * sn;  // track_methods.py:374-376
+          c[S_OY] = mx * sn - my * cs;
+          c[S_MX] = mx;
+          c[S_MY] = my;
+        }
+        body_rmatrix(length, k1, hx, beta, igamma2, c + S_R);
+        second_order_coefficients(length, k1, k2, hx, beta, igamma2, c + S_T);
+        break;
+      }
+      default:
+        break;
+    }
+    double* dst = base + CH_NL_HEADER + static_cast<int64_t>(tid) * block;
+    for (int i = 0; i < block; ++i) dst[i] = static_cast<double>(c[i]);
+  }
+  lengths[tid] = length;
+  __syncthreads();
+  if (tid == 0) {
+    double total = 0.0;
+    for (int i = 0; i < n_ops; ++i) total += lengths[i];
+    base[H_P0C] = static_cast<double>(p0c);
+    base[H_MC2] = static_cast<double>(mc2);
+    base[H_E0] = static_cast<double>(E0);
+    base[H_BETA0] = static_cast<double>(p0c / E0);
+    base[H_MC2_E0_SQ] = static_cast<double>((mc2 / E0) * (mc2 / E0));
+    base[H_LENGTH] = static_cast<double>(total);
+    base[H_CHARGE] = static_cast<double>(q);
+    base[7] = 0.0;
+  }
+}
+
+// ---- per-particle maps ------------------------------------------------------------------------
+__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
+__device__ __forceinline__ void sincos_t(float x, float& s, float& c) { sincosf(x, &s, &c); }
+__device__ __forceinline__ void sincos_t(double x, double& s, double& c) { sincos(x, &s, &c); }
+__device__ __forceinline__ float cosh_t(float x) { return coshf(x); }
+__device__ __forceinline__ double cosh_t(double x) { return cosh(x); }
+__device__ __forceinline__ float sinh_t(float x) { return sinhf(x); }
+__device__ __forceinline__ double sinh_t(double x) { return sinh(x); }
+
+// sqrt(1 + x) - 1 without cancellation (bmadx.py:263-268)
+template <typename C>
+__device__ __forceinline__ C sqrt_one(C x) {
+  return x / (sqrt_t(C(1) + x) + C(1));
+}
+
+template <typename C>
+struct Beam0 {  // reference-particle constants of one setting
+  C p0c, mc2, E0, beta0, mc2_e0_sq;
+};
+
+// particle state: transverse coordinates + either (tau, delta) or Bmad-X (z, pz)
+template <typename C>
+struct State {
+  C x, px, y, py, l, d;
+};
+
+// (tau, delta) -> (z, pz): bmadx.py:7-30 with p^2 - p0c^2 = delta p0c (2 E0 + delta p0c)
+template <typename C>
+__device__ __forceinline__ void to_bmad(State<C>& s, const Beam0<C>& r) {
+  const C energy = r.E0 + s.d * r.p0c;
+  const C pz = sqrt_one(s.d * (C(2) * r.E0 + s.d * r.p0c) / r.p0c);
+  const C beta = (C(1) + pz) * r.p0c / energy;
+  s.l = -beta * s.l;
+  s.d = pz;
+}
+
+// (z, pz) -> (tau, delta): bmadx.py:33-55 with E^2 - E0^2 = p0c^2 pz (2 + pz)
+template <typename C>
+__device__ __forceinline__ void from_bmad(State<C>& s, const Beam0<C>& r) {
+  const C p = (C(1) + s.d) * r.p0c;
+  const C energy = sqrt_t(p * p + r.mc2 * r.mc2);
+  s.l = -s.l * energy / p;
+  s.d = r.p0c * s.d * (C(2) + s.d) / (energy + r.E0);
+}
+
+template <typename C>
+__device__ __forceinline__ void offset_set(State<C>& s, C cs, C sn, C x_off, C y_off) {
+  const C xi = s.x - x_off, yi = s.y - y_off;  // bmadx.py:115-146
+  const C px = s.px, py = s.py;
+  s.x = xi * cs + yi * sn;
+  s.y = -xi * sn + yi * cs;
+  s.px = px * cs + py * sn;
+  s.py = -px * sn + py * cs;
+}
+
+template <typename C>
+__device__ __forceinline__ void offset_unset(State<C>& s, C cs, C sn, C x_off, C y_off) {
+  const C x = s.x, y = s.y, px = s.px, py = s.py;  // bmadx.py:149-180
+  s.x = x * cs - y * sn + x_off;
+  s.y = x * sn + y * cs + y_off;
+  s.px = px * cs - py * sn;
+  s.py = px * sn + py * cs;
+}
+
+// m^2 pz (2 + pz) / ((p0c P)^2 + m^2) = (beta / beta0)^2 - 1
+template <typename C>
+__device__ __forceinline__ C beta_ratio_sq_minus_one(C pz, const Beam0<C>& r) {
+  const C pc = r.p0c * (C(1) + pz);
+  return r.mc2 * r.mc2 * (C(2) * pz + pz * pz) / (pc * pc + r.mc2 * r.mc2);
+}
+
+// exact drift (bmadx.py:271-302)
+template <typename C>
+__device__ __forceinline__ void track_a_drift(State<C>& s, C L, const Beam0<C>& r) {
+  const C iP = C(1) / (C(1) + s.d);
+  const C Px = s.px * iP, Py = s.py * iP;
+  const C Pxy2 = Px * Px + Py * Py;
+  const C iPl = C(1) / sqrt_t(C(1) - Pxy2);
+  const C dz = L * (sqrt_one(beta_ratio_sq_minus_one(s.d, r)) + sqrt_one(-Pxy2) * iPl);
+  s.x += L * Px * iPl;
+  s.y += L * Py * iPl;
+  s.l += dz;
+}
+
+// bmadx.py:183-220; the high-|pz| branch ds (beta - beta0) / beta0 is evaluated as
+// ds (sqrt(1 + ((beta/beta0)^2 - 1)) - 1), which does not cancel
+template <typename C>
+__device__ __forceinline__ C low_energy_z_correction(C pz, C ds, const Beam0<C>& r) {
+  const C evaluation = r.mc2 * (r.beta0 * pz) * (r.beta0 * pz);
+  const C b2 = r.beta0 * r.beta0;
+  if (evaluation < C(3e-7) * r.E0)
+    return ds * pz * (C(1) - C(3) * (pz * b2) / C(2) +
+                      pz * pz * b2 * (C(2) * b2 - r.mc2_e0_sq / C(2))) * r.mc2_e0_sq;
+  return ds * sqrt_one(beta_ratio_sq_minus_one(pz, r));
+}
+
+// one plane of bmadx.py:223-260 for the argument `k1` (kx^2 = -k1), step length l
+template <typename C>
+struct QuadPlane {
+  C a11, a12, a21, c1, c2, c3;
+};
+template <typename C>
+__device__ __forceinline__ QuadPlane<C> quadrupole_plane(C k1, C l, C rel_p) {
+  C cx, sx;
+  if (k1 < C(0)) {  // kx real: focusing
+    const C k = sqrt_t(-k1);
+    C sn;
+    sincos_t(k * l, sn, cx);
+    sx = sn / k;
+  } else if (k1 > C(0)) {
+    const C k = sqrt_t(k1);
+    cx = cosh_t(k * l);
+    sx = sinh_t(k * l) / k;
+  } else {
+    cx = C(1);
+    sx = l;
+  }
+  QuadPlane<C> q;
+  q.a11 = cx;
+  q.a12 = sx / rel_p;
+  q.a21 = k1 * sx * rel_p;
+  q.c1 = k1 * (-cx * sx + l) / C(4);
+  q.c2 = -k1 * sx * sx / (C(2) * rel_p);
+  q.c3 = -(cx * sx + l) / (C(4) * rel_p * rel_p);
+  return q;
+}
+
+// quadrupole.py:168-251; the per-step coefficients only depend on pz, which is constant
+template <typename C>
+__device__ __forceinline__ void track_quadrupole(State<C>& s, const C* c, int num_steps,
+                                                 const Beam0<C>& r) {
+  offset_set(s, c[Q_COS], c[Q_SIN], c[Q_XOFF], c[Q_YOFF]);
+  const C rel_p = C(1) + s.d;
+  const C k1 = c[Q_K1] / rel_p;  // b1 / (L rel_p)
+  const QuadPlane<C> tx = quadrupole_plane(-k1, c[Q_STEP], rel_p);
+  const QuadPlane<C> ty = quadrupole_plane(k1, c[Q_STEP], rel_p);
+  const C dz_low = low_energy_z_correction(s.d, c[Q_STEP], r);
+  for (int step = 0; step < num_steps; ++step) {
+    s.l += tx.c1 * s.x * s.x + tx.c2 * s.x * s.px + tx.c3 * s.px * s.px +
+           ty.c1 * s.y * s.y + ty.c2 * s.y * s.py + ty.c3 * s.py * s.py;
+    const C x = s.x, y = s.y;
+    s.x = tx.a11 * x + tx.a12 * s.px;
+    s.px = tx.a21 * x + tx.a11 * s.px;
+    s.y = ty.a11 * y + ty.a12 * s.py;
+    s.py = ty.a21 * y + ty.a11 * s.py;
+    s.l += dz_low;
+  }
+  offset_unset(s, c[Q_COS], c[Q_SIN], c[Q_XOFF], c[Q_YOFF]);
+}
+
+__device__ __forceinline__ double sinc_d(double x) { return x != 0.0 ? sin(x) / x : 1.0; }
+
+// dipole.py:183-370 in fp64 (entrance fringe, sector body, exit fringe in the tilted frame)
+template <typename C>
+__device__ __forceinline__ void track_dipole(State<C>& st, const double* cc, int flags,
+                                             const Beam0<double>& rr) {
+  const double cs = cc[B_COS], sn = cc[B_SIN];
+  State<double> s{st.x, st.px, st.y, st.py, st.l, st.d};
+  offset_set(s, cs, sn, 0.0, 0.0);
+  if (flags & 1) {
+    s.px += s.x * cc[B_HX1];
+    s.py += s.y * cc[B_HY1];
+  }
+  {  // _bmadx_body, dipole.py:244-336
+    const double L = cc[B_L], angle = cc[B_ANGLE], g = cc[B_G];
+    const double cos_a = cc[B_COSA], sin_a = cc[B_SINA], l_sinc = cc[B_LSINC];
+    const double l2gcosc = cc[B_L2GCOSC];
+    const double x = s.x, pz = s.d;
+    const double px_norm = sqrt((1.0 + pz) * (1.0 + pz) - s.py * s.py);
+    const double phi1 = asin(s.px / px_norm);
+    const double gp = g / px_norm;
+    double sin_ap, cos_ap;
+    sincos(angle + phi1, &sin_ap, &cos_ap);
+    const double gx1 = 1.0 + g * x;
+    const double alpha = 2.0 * gx1 * sin_ap * l_sinc - gp * (gx1 * l_sinc) * (gx1 * l_sinc);
+    const double x2_t1 = x * cos_a + l2gcosc;
+    const double x2_t2 = sqrt(cos_ap * cos_ap + gp * alpha);
+    const double ga = gp * alpha;
+    // Lcu = x2 - x2_t1 is the correction term itself (no subtraction of nearly equal numbers)
+    double Lcu;
+    if (fabs(angle + phi1) < 0.5 * kPi) {
+      Lcu = alpha / (x2_t2 + cos_ap);
+    } else {
+      Lcu = alpha * (ga != 0.0 ? (sqrt(cos_ap * cos_ap + ga) - cos_ap) / ga : 1.0 / (2.0 * cos_ap));
+    }
+    const double x2 = x2_t1 + Lcu;
+    const double Lcv = -l_sinc - x * sin_a;
+    const double theta_p = 2.0 * (angle + phi1 - 0.5 * kPi - atan2(Lcv, Lcu));
+    const double Lc = sqrt(Lcu * Lcu + Lcv * Lcv);
+    const double Lp = Lc / sinc_d(0.5 * theta_p);
+    const double mc2 = rr.mc2, p0c = rr.p0c;
+    const double P = p0c * (1.0 + pz);
+    const double E = sqrt(P * P + mc2 * mc2);
+    const double E0 = sqrt(p0c * p0c + mc2 * mc2);
+    const double beta = P / E, beta0 = p0c / E0;
+    s.x = x2;
+    s.px = px_norm * sin(angle + phi1 - theta_p);
+    s.y = s.y + s.py * Lp / px_norm;
+    s.l = s.l + (beta * L / beta0) - ((1.0 + pz) * Lp / px_norm);
+  }
+  if (flags & 2) {
+    s.px += s.x * cc[B_HX2];
+    s.py += s.y * cc[B_HY2];
+  }
+  offset_unset(s, cs, sn, 0.0, 0.0);
+  st.x = static_cast<C>(s.x);
+  st.px = static_cast<C>(s.px);
+  st.y = static_cast<C>(s.y);
+  st.py = static_cast<C>(s.py);
+  st.l = static_cast<C>(s.l);
+}
+
+// transverse_deflecting_cavity.py:122-209 in fp64
+template <typename C>
+__device__ __forceinline__ void track_tdc(State<C>& st, const double* cc, const Beam0<double>& r) {
+  State<double> s{st.x, st.px, st.y, st.py, st.l, st.d};
+  const double cs = cc[T_COS], sn = cc[T_SIN], xo = cc[T_XOFF], yo = cc[T_YOFF];
+  offset_set(s, cs, sn, xo, yo);
+  track_a_drift(s, cc[T_HALF], r);
+  const double voltage = cc[T_V], k_rf = cc[T_KRF];
+  const double pc_old = (1.0 + s.d) * r.p0c;
+  const double E_old = sqrt(pc_old * pc_old + r.mc2 * r.mc2);
+  const double beta_old = pc_old / E_old;
+  // phase = 2 pi (phase0 - t f) with t = -z / (beta c)
+  const double phase = cc[T_PHASE] + k_rf * s.l / beta_old;
+  double sp, cp;
+  sincos(phase, &sp, &cp);
+  s.px += voltage * sp;
+  const double E_new = E_old + voltage * cp * k_rf * s.x * r.p0c;
+  const double pc = sqrt(E_new * E_new - r.mc2 * r.mc2);
+  const double beta = pc / E_new;
+  // pz = (pc - p0c) / p0c with pc^2 - p0c^2 = (E_new - E0)(E_new + E0)
+  const double E0 = sqrt(r.p0c * r.p0c + r.mc2 * r.mc2);
+  s.d = (E_new - E0) * (E_new + E0) / (r.p0c * (pc + r.p0c));
+  s.l = s.l * beta / beta_old;
+  track_a_drift(s, cc[T_HALF], r);
+  offset_unset(s, cs, sn, xo, yo);
+  st.x = static_cast<C>(s.x);
+  st.px = static_cast<C>(s.px);
+  st.y = static_cast<C>(s.y);
+  st.py = static_cast<C>(s.py);
+  st.l = static_cast<C>(s.l);
+  st.d = static_cast<C>(s.d);
+}
+
+// element.py:195-225 with the frame changes of quadrupole.py:136-143 / dipole.py:417-426 applied
+// to the particle instead of being folded into T: q = entry(p), t = R q + T q q, out = exit(t)
+template <typename C>
+__device__ __forceinline__ void track_second_order(State<C>& s, const C* c) {
+  const C cs = c[S_COS], sn = c[S_SIN];
+  C x = s.x * cs + s.y * sn + c[S_OX];
+  C y = -s.x * sn + s.y * cs + c[S_OY];
+  C px = s.px * cs + s.py * sn;
+  C py = -s.px * sn + s.py * cs;
+  px += c[S_KX1] * x;
+  py += c[S_KY1] * y;
+  const C tau = s.l, dl = s.d;
+  const C* r = c + S_R;
+  const C* t = c + S_T;
+  const C xx = x * x, xp = x * px, pp = px * px, xd = x * dl, pd = px * dl, dd = dl * dl;
+  const C yy = y * y, yq = y * py, qq = py * py;
+  const C xy = x * y, xq = x * py, py_ = px * y, pq = px * py, yd = y * dl, qd = py * dl;
+  C ox = r[R_CX] * x + r[R_SX] * px + r[R_05] * dl + t[T000] * xx + t[T001] * xp + t[T011] * pp +
+         t[T005] * xd + t[T015] * pd + t[T055] * dd + t[T022] * yy + t[T023] * yq + t[T033] * qq;
+  C opx = r[R_10] * x + r[R_CX] * px + r[R_15] * dl + t[T100] * xx + t[T101] * xp + t[T111] * pp +
+          t[T105] * xd + t[T115] * pd + t[T155] * dd + t[T122] * yy + t[T123] * yq + t[T133] * qq;
+  C oy = r[R_CY] * y + r[R_SY] * py + t[T202] * xy + t[T203] * xq + t[T212] * py_ + t[T213] * pq +
+         t[T225] * yd + t[T235] * qd;
+  C opy = r[R_32] * y + r[R_CY] * py + t[T302] * xy + t[T303] * xq + t[T312] * py_ +
+          t[T313] * pq + t[T325] * yd + t[T335] * qd;
+  const C otau = tau + r[R_15] * x + r[R_05] * px + r[R_56] * dl + t[T400] * xx + t[T401] * xp +
+                 t[T411] * pp + t[T405] * xd + t[T415] * pd + t[T455] * dd + t[T422] * yy +
+                 t[T423] * yq + t[T433] * qq;
+  opx += c[S_KX2] * ox;
+  opy += c[S_KY2] * oy;
+  s.x = ox * cs - oy * sn + c[S_MX];
+  s.y = ox * sn + oy * cs + c[S_MY];
+  s.px = opx * cs - opy * sn;
+  s.py = opx * sn + opy * cs;
+  s.l = otau;
+}
+
+template <typename T>
+struct TrackArgs {
+  const T* particles_in;
+  const double* constants;
+  T* particles_out;
+  const int32_t* particle_index;
+  const int32_t* constants_index;
+  const int32_t* opcodes;   // device, already offset to the first op of the run
+  const int32_t* op_flags;
+  int64_t particle_stride;
+  int64_t constants_stride;
+  int64_t n_particles;
+  int64_t n_settings;
+  int32_t n_ops;
+  int32_t block;
+  int32_t bulk_in;
+  int32_t bulk_out;
+};
+
+template <typename T, int P, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+nonlinear_track_kernel(const TrackArgs<T> a) {
+  constexpr int TP = P * THREADS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* stage = reinterpret_cast<T*>(smem_raw);
+  double* consts64 = reinterpret_cast<double*>(stage + TP * 7);
+  const int n_consts = CH_NL_HEADER + a.n_ops * a.block;
+  T* consts = reinterpret_cast<T*>(consts64 + n_consts);  // the same, rounded to the beam dtype
+  uint64_t* bar = reinterpret_cast<uint64_t*>(consts + (n_consts + 3) / 4 * 4);
+  int32_t* codes = reinterpret_cast<int32_t*>(bar + 1);
+  int32_t* flags = codes + a.n_ops;
+
+  const int tid = threadIdx.x;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
+  const int count = static_cast<int>(min(static_cast<int64_t>(TP), a.n_particles - n0));
+
+  if (a.bulk_in && tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < a.n_ops; i += THREADS) {
+    codes[i] = a.opcodes[i];
+    flags[i] = a.op_flags[i];
+  }
+  __syncthreads();
+
+  T p[P][7];
+  int64_t loaded = -1;
+  uint32_t phase = 0;
+  for (int64_t b = blockIdx.y; b < a.n_settings; b += gridDim.y) {
+    // the staging tile may still be read by the bulk store of the previous setting
+    if (a.bulk_out && tid == 0) bulk_wait_read<0>();
+    __syncthreads();
+    const double* src_c =
+        a.constants + (a.constants_index ? a.constants_index[b] : b) * a.constants_stride;
+    for (int i = tid; i < n_consts; i += THREADS) {
+      const double v = src_c[i];
+      consts64[i] = v;
+      consts[i] = static_cast<T>(v);
+    }
+    const int64_t p_off =
+        (a.particle_index ? a.particle_index[b] : b) * a.particle_stride + n0 * 7;
+    if (p_off != loaded) {
+      cta_load_tile(stage, a.particles_in + p_off, count * 7, a.bulk_in != 0, bar, phase);
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const int local = tid + k * THREADS;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) p[k][j] = local < count ? stage[local * 7 + j] : T(0);
+      }
+      loaded = p_off;
+    }
+    __syncthreads();  // constants visible, tile consumed
+
+    const Beam0<T> ref{consts[H_P0C], consts[H_MC2], consts[H_E0], consts[H_BETA0],
+                       consts[H_MC2_E0_SQ]};
+    const Beam0<double> ref64{consts64[H_P0C], consts64[H_MC2], consts64[H_E0],
+                              consts64[H_BETA0], consts64[H_MC2_E0_SQ]};
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      State<T> s{p[k][0], p[k][1], p[k][2], p[k][3], p[k][4], p[k][5]};
+      bool bmad = false;  // representation of (s.l, s.d): uniform over the CTA
+      for (int op = 0; op < a.n_ops; ++op) {
+        const int code = codes[op];
+        const T* c = consts + CH_NL_HEADER + op * a.block;
+        const double* c64 = consts64 + CH_NL_HEADER + op * a.block;
+        if (code == CH_OP_IDENTITY) continue;
+        const bool wants_bmad = code != CH_OP_SECOND_ORDER;
+        if (wants_bmad && !bmad) to_bmad(s, ref);
+        if (!wants_bmad && bmad) from_bmad(s, ref);
+        bmad = wants_bmad;
+        switch (code) {
+          case CH_OP_DKD_DRIFT:
+            track_a_drift(s, c[D_L], ref);
+            break;
+          case CH_OP_DKD_QUADRUPOLE:
+            track_quadrupole(s, c, flags[op] > 0 ? flags[op] : 1, ref);
+            break;
+          case CH_OP_DKD_DIPOLE:
+            track_dipole(s, c64, flags[op], ref64);
+            break;
+          case CH_OP_DKD_TDC:
+            track_tdc(s, c64, ref64);
+            break;
+          case CH_OP_SECOND_ORDER:
+            track_second_order(s, c);
+            break;
+          default:
+            break;
+        }
+      }
+      if (bmad) from_bmad(s, ref);
+      T* row = stage + (tid + k * THREADS) * 7;
+      row[0] = s.x;
+      row[1] = s.px;
+      row[2] = s.y;
+      row[3] = s.py;
+      row[4] = s.l;
+      row[5] = s.d;
+      row[6] = p[k][6];
+    }
+
+    T* out = a.particles_out + (b * a.n_particles + n0) * 7;
+    if (a.bulk_out) {
+      fence_async_shared();
+      __syncthreads();
+      if (tid == 0) {
+        bulk_store(out, stage, static_cast<uint32_t>(count) * 7u * sizeof(T));
+        bulk_commit();
+      }
+    } else {
+      __syncthreads();
+      for (int i = tid; i < count * 7; i += THREADS) out[i] = stage[i];
+    }
+  }
+  if (a.bulk_out && tid == 0) bulk_wait<0>();
+}
+
+int block_size(const ch_program* program, int32_t op_begin, int32_t op_end) {
+  for (int32_t i = op_begin; i < op_end; ++i)
+    if (program->opcodes_host[i] == CH_OP_SECOND_ORDER) return CH_NL_BLOCK_SECOND_ORDER;
+  return CH_NL_BLOCK_DKD;
+}
+
+int check_run(const ch_program* program, int32_t op_begin, int32_t op_end, const char* who) {
+  CH_REQUIRE(program != nullptr, "%s: program is NULL", who);
+  CH_REQUIRE(op_begin >= 0 && op_begin < op_end && op_end <= program->n_ops,
+             "%s: op range [%d, %d) outside program of %d ops", who, op_begin, op_end,
+             program->n_ops);
+  CH_REQUIRE(op_end - op_begin <= CH_NL_MAX_OPS, "%s: a run holds at most %d ops, got %d", who,
+             CH_NL_MAX_OPS, op_end - op_begin);
+  for (int32_t i = op_begin; i < op_end; ++i) {
+    const int32_t code = program->opcodes_host[i];
+    CH_REQUIRE(code == CH_OP_IDENTITY || (code >= CH_OP_DKD_DRIFT && code <= CH_OP_SECOND_ORDER),
+               "%s: op %d (opcode %d) is not a non-linear tracking op", who, i, code);
+  }
+  return CH_OK;
+}
+
+template <typename T>
+int launch_track(const ch_program* program, int32_t op_begin, int32_t op_end, const double* constants,
+                 int64_t constants_stride, const int32_t* constants_index,
+                 const void* particles_in, int64_t particle_stride, const int32_t* particle_index,
+                 int64_t n_particles, int64_t n_settings, void* particles_out,
+                 cudaStream_t stream) {
+  constexpr int P = sizeof(T) == 4 ? 2 : 1;
+  constexpr int THREADS = 128;
+  constexpr int TP = P * THREADS;
+  TrackArgs<T> a;
+  a.particles_in = static_cast<const T*>(particles_in);
+  a.constants = static_cast<const double*>(constants);
+  a.particles_out = static_cast<T*>(particles_out);
+  a.particle_index = particle_index;
+  a.constants_index = constants_index;
+  a.opcodes = program->opcodes + op_begin;
+  a.op_flags = program->op_flags + op_begin;
+  a.particle_stride = particle_stride;
+  a.constants_stride = constants_stride;
+  a.n_particles = n_particles;
+  a.n_settings = n_settings;
+  a.n_ops = op_end - op_begin;
+  a.block = block_size(program, op_begin, op_end);
+  a.bulk_in = bulk_compatible<T>(particles_in, n_particles, particle_stride) ? 1 : 0;
+  a.bulk_out = bulk_compatible<T>(particles_out, n_particles, n_particles * 7) ? 1 : 0;
+  const int n_consts = CH_NL_HEADER + a.n_ops * a.block;
+  const size_t smem = sizeof(T) * (TP * 7 + (n_consts + 3) / 4 * 4) + sizeof(double) * n_consts +
+                      sizeof(uint64_t) + 2 * sizeof(int32_t) * a.n_ops;
+  const int64_t tiles = (n_particles + TP - 1) / TP;
+  CH_REQUIRE(tiles <= 2147483647LL, "ch_track_nonlinear: too many particles");
+  dim3 grid(static_cast<unsigned>(tiles),
+            static_cast<unsigned>(n_settings < 65535 ? n_settings : 65535));
+  auto kernel = nonlinear_track_kernel<T, P, THREADS>;
+  CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)));
+  kernel<<<grid, THREADS, smem, stream>>>(a);
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+}  // namespace
+}  // namespace ch
+
+extern "C" int64_t ch_nonlinear_constants_len(const ch_program* program, int32_t op_begin,
+                                              int32_t op_end) {
+  if (ch::check_run(program, op_begin, op_end, "ch_nonlinear_constants_len") != CH_OK) return -1;
+  return CH_NL_HEADER +
+         static_cast<int64_t>(op_end - op_begin) * ch::block_size(program, op_begin, op_end);
+}
+
+extern "C" int ch_nonlinear_constants(const ch_program* program, int32_t op_begin, int32_t op_end,
+                                      int64_t n_settings, const void* energy,
+                                      int64_t energy_stride, int32_t energy_dtype,
+                                      const void* mass_eV, int32_t mass_dtype,
+                                      const void* num_elementary_charges, int32_t charge_dtype,
+                                      double* constants, void* stream) {
+  const int status = ch::check_run(program, op_begin, op_end, "ch_nonlinear_constants");
+  if (status != CH_OK) return status;
+  CH_REQUIRE(n_settings > 0 && n_settings <= 2147483647LL,
+             "ch_nonlinear_constants: n_settings must be in [1, 2^31)");
+  CH_REQUIRE(energy && mass_eV && constants, "ch_nonlinear_constants: NULL pointer argument");
+  ch::Program prog{program->opcodes, program->op_flags, program->slot_begin, program->slots};
+  ch::ScalarRef e{energy, energy_stride, energy_dtype};
+  ch::ScalarRef m{mass_eV, 0, mass_dtype};
+  ch::ScalarRef q{num_elementary_charges, 0, charge_dtype};
+  const int32_t block = ch::block_size(program, op_begin, op_end);
+  const unsigned blocks = static_cast<unsigned>(n_settings);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ch::nonlinear_constants_kernel<<<blocks, 64, 0, s>>>(prog, op_begin, op_end - op_begin, e, m, q,
+                                                       block, constants);
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_track_nonlinear(const ch_program* program, int32_t op_begin, int32_t op_end,
+                                  const double* constants, int64_t constants_stride,
+                                  const int32_t* constants_index, const void* particles_in,
+                                  int64_t particle_stride, const int32_t* particle_index,
+                                  int64_t n_particles, int64_t n_settings, void* particles_out,
+                                  int32_t dtype, void* stream) {
+  const int status = ch::check_run(program, op_begin, op_end, "ch_track_nonlinear");
+  if (status != CH_OK) return status;
+  CH_REQUIRE(constants && particles_in && particles_out,
+             "ch_track_nonlinear: NULL pointer argument");
+  CH_REQUIRE(n_particles > 0 && n_settings > 0, "ch_track_nonlinear: empty beam or batch");
+  CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, "ch_track_nonlinear: bad dtype %d", dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CH_F32)
+    return ch::launch_track<float>(program, op_begin, op_end, constants, constants_stride,
+                                   constants_index, particles_in, particle_stride, particle_index,
+                                   n_particles, n_settings, particles_out, s);
+  return ch::launch_track<double>(program, op_begin, op_end, constants, constants_stride,
+                                  constants_index, particles_in, particle_stride, particle_index,
+                                  n_particles, n_settings, particles_out, s);
+}

@@ -44,9 +44,9 @@ extern "C" int ch_program_create(const int32_t* opcodes_host, const int32_t* op_
   for (int32_t i = 0; i < n_ops; ++i) {
     CH_REQUIRE(slot_begin_host[i] <= slot_begin_host[i + 1],
                "ch_program_create: slot_begin not monotonic at op %d", i);
-    CH_REQUIRE(opcodes_host[i] >= CH_OP_IDENTITY && opcodes_host[i] <= CH_OP_CAVITY,
+    CH_REQUIRE(opcodes_host[i] >= CH_OP_IDENTITY && opcodes_host[i] <= CH_OP_SECOND_ORDER,
                "ch_program_create: unknown opcode %d at op %d", opcodes_host[i], i);
-    static const int kMinSlots[] = {0, 1, 1, 5, 9, 4, 4, 1, 1, 2, 5};
+    static const int kMinSlots[] = {0, 1, 1, 5, 9, 4, 4, 1, 1, 2, 5, 1, 5, 9, 7, 12};
     CH_REQUIRE(slot_begin_host[i + 1] - slot_begin_host[i] >= kMinSlots[opcodes_host[i]],
                "ch_program_create: op %d (opcode %d) has too few slots", i, opcodes_host[i]);
   }
@@ -67,6 +67,13 @@ extern "C" int ch_program_create(const int32_t* opcodes_host, const int32_t* op_
   prog->n_slots = n_slots;
   prog->opcodes = prog->op_flags = prog->slot_begin = nullptr;
   prog->slots = nullptr;
+  prog->opcodes_host = new (std::nothrow) int32_t[n_ops > 0 ? n_ops : 1];
+  if (!prog->opcodes_host) {
+    delete prog;
+    ch::set_error("ch_program_create: out of host memory");
+    return CH_ENOMEM;
+  }
+  for (int32_t i = 0; i < n_ops; ++i) prog->opcodes_host[i] = opcodes_host[i];
 
   // one device allocation for the four tables
   const size_t ints = static_cast<size_t>(n_ops) * 2 + static_cast<size_t>(n_ops) + 1;
@@ -85,6 +92,7 @@ extern "C" int ch_program_create(const int32_t* opcodes_host, const int32_t* op_
   unsigned char* device = nullptr;
   cudaError_t err = cudaMalloc(&device, bytes);
   if (err != cudaSuccess) {
+    delete[] prog->opcodes_host;
     delete prog;
     ch::set_error("ch_program_create: cudaMalloc(%zu) failed: %s", bytes,
                   cudaGetErrorString(err));
@@ -96,6 +104,7 @@ extern "C" int ch_program_create(const int32_t* opcodes_host, const int32_t* op_
   // when cudaMemcpyAsync returns, so it may be freed at scope exit
   if (err != cudaSuccess) {
     cudaFree(device);
+    delete[] prog->opcodes_host;
     delete prog;
     ch::set_error("ch_program_create: upload failed: %s", cudaGetErrorString(err));
     return CH_ECUDA;
@@ -112,6 +121,7 @@ extern "C" int ch_program_destroy(ch_program* program) {
   if (!program) return CH_OK;
   // freed with cudaFree: implicitly waits for kernels still using the tables
   cudaError_t err = cudaFree(program->opcodes);
+  delete[] program->opcodes_host;
   delete program;
   if (err != cudaSuccess) {
     ch::set_error("ch_program_destroy: cudaFree failed: %s", cudaGetErrorString(err));

@@ -343,6 +343,26 @@ class Cavity(_SimpleElement):
         return not self.is_active
 
 
+class TransverseDeflectingCavity(_SimpleElement):
+    """Transverse deflecting RF cavity, tracked per particle with the Bmad-X drift-kick-drift
+    map (cheetah/accelerator/transverse_deflecting_cavity.py)."""
+
+    tensor_fields = {
+        "length": 0.0, "voltage": 0.0, "phase": 0.0, "frequency": 0.0,
+        "misalignment": (0.0, 0.0), "tilt": 0.0,
+    }
+    plain_fields = {"num_steps": 1}
+    supported_tracking_methods = ["drift_kick_drift"]
+
+    @property
+    def is_active(self) -> bool:
+        return bool((self.voltage != 0).any())
+
+    @property
+    def is_skippable(self) -> bool:
+        return False
+
+
 class Marker(_SimpleElement):
     tensor_fields = {}
 

@@ -58,6 +58,19 @@ class LinearSection:
 
 
 @dataclass
+class NonlinearRun:
+    """Consecutive drift_kick_drift / second_order elements (identity ops in between are
+    no-ops): one ``ch_nonlinear_constants`` + one ``ch_track_nonlinear`` launch."""
+
+    op_begin: int
+    op_end: int
+    lattice_shape: tuple = ()
+    length_shape: tuple = ()
+    survival_shape: tuple = ()
+    methods: tuple = ()                # tracking methods present (for error messages)
+
+
+@dataclass
 class Barrier:
     element: object
     kind: str  # "space_charge" or "unsupported"
@@ -195,6 +208,87 @@ def _lower_linear(element) -> tuple[int, int, list]:
     )
 
 
+_zeros: dict = {}
+
+
+def _zero(device: torch.device) -> torch.Tensor:
+    """A device scalar 0 for the unused slots of a fixed slot layout."""
+    key = str(device)
+    if key not in _zeros:
+        _zeros[key] = torch.zeros((), dtype=torch.float32, device=device)
+    return _zeros[key]
+
+
+def nonlinear_method(element) -> str | None:
+    """"drift_kick_drift" / "second_order" if ``element`` is tracked per particle by
+    ``ch_track_nonlinear``, else None."""
+    kind = _type_name(element)
+    if kind == "TransverseDeflectingCavity":
+        return "drift_kick_drift"
+    if kind in ("Drift", "Quadrupole", "Dipole", "RBend", "Sextupole"):
+        method = getattr(element, "tracking_method", "linear")
+        if method in ("drift_kick_drift", "second_order") and not (
+            kind == "Sextupole" and method == "drift_kick_drift"
+        ):
+            return method
+    return None
+
+
+def _lower_nonlinear(element, device: torch.device) -> tuple[int, int, list]:
+    """(opcode, flags, slots) of one drift_kick_drift / second_order element."""
+    kind = _type_name(element)
+    method = nonlinear_method(element)
+    zero = SlotSpec(_zero(device))
+    misalignment = lambda: [  # noqa: E731
+        SlotSpec(element.misalignment, 2, 0), SlotSpec(element.misalignment, 2, 1)
+    ]
+    if kind == "TransverseDeflectingCavity":
+        # transverse_deflecting_cavity.py:122-209
+        return _capi.OP_DKD_TDC, 0, [
+            _length(element), SlotSpec(element.voltage), SlotSpec(element.phase),
+            SlotSpec(element.frequency), SlotSpec(element.tilt), *misalignment(),
+        ]
+    if method == "drift_kick_drift":
+        if kind == "Drift":  # drift.py:106-154
+            return _capi.OP_DKD_DRIFT, 0, [_length(element)]
+        if kind == "Quadrupole":  # quadrupole.py:168-251
+            num_steps = int(element.num_steps)
+            if num_steps < 1:
+                raise ValueError(f"Quadrupole {element.name!r}: num_steps must be >= 1")
+            return _capi.OP_DKD_QUADRUPOLE, num_steps, [
+                _length(element), SlotSpec(element.k1), SlotSpec(element.tilt), *misalignment(),
+            ]
+        # Dipole / RBend, dipole.py:183-370
+        fringe_at = getattr(element, "fringe_at", "both")
+        flags = int(fringe_at in ("entrance", "both")) | (int(fringe_at in ("exit", "both")) << 1)
+        return _capi.OP_DKD_DIPOLE, flags, [
+            _length(element), SlotSpec(element.angle),
+            SlotSpec(element.dipole_e1), SlotSpec(element.dipole_e2),
+            SlotSpec(element.fringe_integral), SlotSpec(element.fringe_integral_exit),
+            SlotSpec(element.gap), SlotSpec(element.gap_exit), SlotSpec(element.tilt),
+        ]
+    # second order: slots length, k1, k2, angle, e1, e2, fint, fint_exit, gap, tilt, mis_x, mis_y
+    if kind == "Drift":  # drift.py:67-83
+        return _capi.OP_SECOND_ORDER, 0, [_length(element)] + [zero] * 11
+    if kind == "Quadrupole":  # quadrupole.py:112-143
+        return _capi.OP_SECOND_ORDER, 0, [
+            _length(element), SlotSpec(element.k1), *([zero] * 7), SlotSpec(element.tilt),
+            *misalignment(),
+        ]
+    if kind == "Sextupole":  # sextupole.py:90-116
+        return _capi.OP_SECOND_ORDER, 0, [
+            _length(element), zero, SlotSpec(element.k2), *([zero] * 6), SlotSpec(element.tilt),
+            *misalignment(),
+        ]
+    # Dipole / RBend, dipole.py:396-466
+    return _capi.OP_SECOND_ORDER, 1, [
+        _length(element), SlotSpec(element.k1), zero, SlotSpec(element.angle),
+        SlotSpec(element.dipole_e1), SlotSpec(element.dipole_e2),
+        SlotSpec(element.fringe_integral), SlotSpec(element.fringe_integral_exit),
+        SlotSpec(element.gap), SlotSpec(element.tilt), zero, zero,
+    ]
+
+
 def _check_tensor(tensor: torch.Tensor, device: torch.device, what: str) -> None:
     if not isinstance(tensor, torch.Tensor):
         raise TypeError(f"{what} must be a tensor, got {type(tensor)}")
@@ -230,6 +324,7 @@ def lower(elements, device: torch.device, target_shape: tuple = ()) -> LatticePr
 
     def close_section() -> None:
         nonlocal section
+        close_run()
         if section is None:
             return
         section.op_end = len(ops)
@@ -237,10 +332,50 @@ def lower(elements, device: torch.device, target_shape: tuple = ()) -> LatticePr
         stages.append(section)
         section = None
 
+    # a non-linear run [run_begin, run_end); identity ops appended after run_end are "pending":
+    # they join the run if another non-linear element follows, else they open a linear section
+    run_begin = run_end = -1
+    run_methods: list = []
+
+    def close_run() -> None:
+        nonlocal run_begin, run_end, section, run_methods
+        if run_begin < 0:
+            return
+        run = NonlinearRun(op_begin=run_begin, op_end=run_end, methods=tuple(run_methods))
+        _finish_section(run, ops, device, target_shape, watched)
+        stages.append(run)
+        if run_end < len(ops):  # pending identity ops start the next linear section
+            section = LinearSection(op_begin=run_end, op_end=len(ops))
+        run_begin = run_end = -1
+        run_methods = []
+
+    def is_identity(element) -> bool:
+        return element.is_skippable and _type_name(element) in ("Marker", "BPM", "Screen", "Aperture")
+
     for element in flatten(elements):
         kind = _type_name(element)
         if kind == "Cavity":
             watched.append((element.voltage, element.voltage._version))
+        method = nonlinear_method(element)
+        if method is not None:
+            if run_begin < 0:
+                close_section()
+                run_begin = len(ops)
+            elif len(ops) + 1 - run_begin > _capi.NL_MAX_OPS:
+                close_run()
+                if section is not None:  # pending identities became a linear section
+                    close_section()
+                run_begin = len(ops)
+            opcode, flags, slots = _lower_nonlinear(element, device)
+            ops.append(Op(opcode, flags, slots, element))
+            run_end = len(ops)
+            run_methods.append(method)
+            continue
+        if run_begin >= 0:
+            if is_identity(element):
+                ops.append(Op(_capi.OP_IDENTITY, 0, [], element))
+                continue
+            close_run()
         if element.is_skippable:
             opcode, flags, slots = _lower_linear(element)
             sec = open_section()

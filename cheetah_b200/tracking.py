@@ -98,9 +98,10 @@ def _compose(program, section, energy: torch.Tensor, species, dtype):
     return records, map_shape
 
 
-def _section_length(records: torch.Tensor, map_shape: tuple, length_shape: tuple) -> torch.Tensor:
+def _section_length(records: torch.Tensor, map_shape: tuple, length_shape: tuple,
+                    column: int = 1) -> torch.Tensor:
     """Sum of element lengths with the reference's (un-expanded) vector shape."""
-    total = records[:, 1].reshape(map_shape)
+    total = records[:, column].reshape(map_shape)
     # drop the vector dims the lengths do not carry
     lead = len(map_shape) - len(length_shape)
     index = [0] * lead + [slice(None) if n > 1 else 0 for n in length_shape]
@@ -260,6 +261,74 @@ def _track_linear_section(program, section, beam, moments: str | None = None):
     return outgoing if moments is None else (outgoing, observed)
 
 
+def _track_nonlinear_run(program, run, beam):
+    """One ``ch_nonlinear_constants`` + one ``ch_track_nonlinear`` for a run of
+    drift_kick_drift / second_order elements (drift.py:106-154, quadrupole.py:168-251,
+    dipole.py:183-370, transverse_deflecting_cavity.py:122-209, element.py:195-225)."""
+    particles = beam.particles
+    device, dtype = particles.device, particles.dtype
+    if dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"cheetah_b200 tracks float32/float64 beams, got {dtype}")
+    n = particles.shape[-2]
+    vp = tuple(particles.shape[:-2])
+    lib = _capi.lib()
+    species = beam.species
+    energy = beam.energy
+    vm = tuple(torch.broadcast_shapes(run.lattice_shape, energy.shape))
+    n_settings = math.prod(vm)
+    if energy.dtype not in (torch.float32, torch.float64):
+        energy = energy.to(dtype)
+    if energy.numel() == 1:
+        energy_stride = 0
+    else:
+        energy = energy.expand(vm).contiguous()
+        energy_stride = 1
+    with torch.cuda.device(device):
+        n_consts = int(lib.ch_nonlinear_constants_len(program.native, run.op_begin, run.op_end))
+        if n_consts < 0:
+            _capi.check(-1)
+        constants = torch.empty((n_settings, n_consts), dtype=torch.float64, device=device)
+        mass_eV, charge = species.mass_eV, species.num_elementary_charges
+        _capi.check(
+            lib.ch_nonlinear_constants(
+                program.native, run.op_begin, run.op_end, n_settings,
+                energy.data_ptr(), energy_stride, _capi.dtype_code(energy.dtype),
+                mass_eV.data_ptr(), _capi.dtype_code(mass_eV.dtype),
+                charge.data_ptr(), _capi.dtype_code(charge.dtype),
+                constants.data_ptr(), _capi.current_stream(device),
+            )
+        )
+        new_s = beam.s + _section_length(constants, vm, run.length_shape, column=5).to(beam.s.dtype)
+        vo = tuple(torch.broadcast_shapes(vm, vp))
+        if not particles.is_contiguous():
+            particles = particles.contiguous()
+        particle_index = _index_table(vp, vo, device)
+        constants_index = _index_table(vm, vo, device)
+        out = torch.empty((*vo, n, 7), dtype=dtype, device=device)
+        _capi.check(
+            lib.ch_track_nonlinear(
+                program.native, run.op_begin, run.op_end,
+                constants.data_ptr(), 0 if n_settings == 1 else n_consts,
+                _capi.ptr(constants_index),
+                particles.data_ptr(), 0 if math.prod(vp) == 1 else n * 7,
+                _capi.ptr(particle_index),
+                n, math.prod(vo), out.data_ptr(), _capi.dtype_code(dtype),
+                _capi.current_stream(device),
+            )
+        )
+    # the reference hands back ref_energy = sqrt(p0c^2 + m^2) == energy up to rounding, the same
+    # species object and the untouched charges / survival probabilities
+    outgoing = beam.__class__(
+        out, beam.energy, particle_charges=beam.particle_charges,
+        survival_probabilities=beam.survival_probabilities, s=new_s, species=species,
+    )
+    try:
+        outgoing._unit_seventh = _unit_seventh(beam)
+    except Exception:
+        pass
+    return outgoing
+
+
 class BeamMoments:
     """What ``ParticleBeam.mu_*`` / ``sigma_*`` / ``num_particles_survived`` return on the
     outgoing beam, computed in the epilogue of the apply kernel (no (B, N, 7) array needed).
@@ -313,6 +382,8 @@ def track_moments(elements, incoming, cache_owner=None, keep_particles: bool = F
     for stage in stages[:-1]:
         if isinstance(stage, lowering.LinearSection):
             beam = _track_linear_section(program, stage, beam)
+        elif isinstance(stage, lowering.NonlinearRun):
+            beam = _track_nonlinear_run(program, stage, beam)
         elif stage.kind == "space_charge":
             from . import space_charge
 
@@ -331,6 +402,14 @@ def _track_parameter_beam(program, beam):
     """tm @ mu, tm @ cov @ tm^T with the composed maps (element.py:166-179)."""
     mu, cov, s = beam.mu, beam.cov, beam.s
     for stage in program.stages:
+        if isinstance(stage, lowering.NonlinearRun):
+            if "drift_kick_drift" in stage.methods:
+                raise AssertionError(
+                    "Drift-kick-drift tracking is currently only supported for `ParticleBeam`."
+                )
+            raise AssertionError(
+                "Second-order tracking is currently only supported for `ParticleBeam`."
+            )
         if isinstance(stage, lowering.Barrier):
             if stage.kind == "space_charge":
                 raise AssertionError(
@@ -381,6 +460,8 @@ def track(elements, incoming, cache_owner=None):
     for stage in program.stages:
         if isinstance(stage, lowering.LinearSection):
             beam = _track_linear_section(program, stage, beam)
+        elif isinstance(stage, lowering.NonlinearRun):
+            beam = _track_nonlinear_run(program, stage, beam)
         elif stage.kind == "space_charge":
             from . import space_charge
 

@@ -65,13 +65,31 @@ enum {
                           /*   custom_transfer_map.py:111-114                            */
   CH_OP_APERTURE = 9,     /* slots: x_max, y_max; op_flags bit0 = elliptical             */
                           /*   aperture.py:90-132 (cut point, not a map)                 */
-  CH_OP_CAVITY = 10       /* ACTIVE cavity (voltage != 0), must be the LAST op of its     */
+  CH_OP_CAVITY = 10,      /* ACTIVE cavity (voltage != 0), must be the LAST op of its     */
                           /*   section.  slots: length, voltage, phase [deg], frequency,  */
                           /*   gain flag (device scalar, non-zero = use the energy-gain   */
                           /*   second-order terms: the reference's batch-wide             */
                           /*   `(delta_energy > 0).any()`, cavity.py:155);                */
                           /*   op_flags bit0 = traveling wave                             */
                           /*   cavity.py:100-251 (track), :253-358 (R matrix)             */
+  /* per-particle NON-LINEAR ops (ch_track_nonlinear; never part of a linear section)      */
+  CH_OP_DKD_DRIFT = 11,   /* Drift, tracking_method="drift_kick_drift"; slots: length      */
+                          /*   drift.py:106-154, bmadx.py:271-302                          */
+  CH_OP_DKD_QUADRUPOLE = 12, /* slots: length, k1, tilt, mis_x, mis_y; op_flags = num_steps */
+                          /*   quadrupole.py:168-251, bmadx.py:115-260                     */
+  CH_OP_DKD_DIPOLE = 13,  /* slots: length, angle, e1, e2, fint, fint_exit, gap, gap_exit, */
+                          /*   tilt; op_flags bit0 = fringe at entrance, bit1 = at exit    */
+                          /*   dipole.py:183-370                                           */
+  CH_OP_DKD_TDC = 14,     /* TransverseDeflectingCavity; slots: length, voltage, phase     */
+                          /*   [rad / 2 pi], frequency, tilt, mis_x, mis_y                 */
+                          /*   transverse_deflecting_cavity.py:122-209                     */
+  CH_OP_SECOND_ORDER = 15 /* tracking_method="second_order" of Drift / Quadrupole /        */
+                          /*   Sextupole / Dipole / RBend; slots: length, k1, k2, angle,   */
+                          /*   e1, e2, fint, fint_exit, gap, tilt, mis_x, mis_y (unused    */
+                          /*   ones point at a zero); op_flags bit0 = bend (pole faces +   */
+                          /*   rotation; otherwise rotation + misalignment)                */
+                          /*   track_methods.py:80-281, element.py:195-225, drift.py:67-83,*/
+                          /*   quadrupole.py:112-143, sextupole.py:90-116, dipole.py:396-466*/
 };
 
 /* Per-setting record written by ch_compose_maps, `record_len` scalars of the beam dtype:
@@ -187,6 +205,47 @@ int ch_apply_maps_moments(const void* particles_in, int64_t particle_stride, con
                           int64_t n_particles, int64_t n_settings,
                           void* particles_out, void* survival_out, double* moments_out,
                           int32_t dtype, int32_t unit_seventh, void* stream);
+
+/* non-linear tracking ------------------------------------------------------------------- */
+/* A RUN of consecutive CH_OP_DKD_* / CH_OP_SECOND_ORDER ops (CH_OP_IDENTITY ops in between are
+ * skipped) is tracked in ONE pass over the particles: 28 B read + 28 B written per (particle,
+ * setting) for the whole run.  Replaces Drift/Quadrupole/Dipole._track_drift_kick_drift,
+ * TransverseDeflectingCavity._track_drift_kick_drift and Element._track_second_order (files
+ * cited at the opcodes).  Per setting the constants are
+ *   [CH_NL_HEADER]  p0c, mc^2, E0, beta0, (mc^2 / E0)^2, sum of the element lengths, charge, 0
+ *   then one block per op: CH_NL_BLOCK_SECOND_ORDER scalars if the run holds a second-order op,
+ *   else CH_NL_BLOCK_DKD (ch_nonlinear_constants_len gives the total).                      */
+#define CH_NL_HEADER 8
+#define CH_NL_BLOCK_DKD 16
+#define CH_NL_BLOCK_SECOND_ORDER 64
+#define CH_NL_MAX_OPS 64
+
+/* scalars per setting that ch_nonlinear_constants writes for ops [op_begin, op_end); -1 on error */
+int64_t ch_nonlinear_constants_len(const ch_program* program, int32_t op_begin, int32_t op_end);
+
+/* Element parameters -> per-(setting, op) constants in fp64 (sin / cos of tilts and bend angles,
+ * fringe kicks, body R and the 39 second-order coefficients of base_ttensor with the compound
+ * functions of cheetah/utils/autograd.py).  The particle pass rounds them to the beam dtype,
+ * except for the bend body and the TDC kick, which it evaluates in fp64.  energy / mass / charge
+ * are read as in ch_compose_maps.                                                           */
+int ch_nonlinear_constants(const ch_program* program, int32_t op_begin, int32_t op_end,
+                           int64_t n_settings,
+                           const void* energy, int64_t energy_stride, int32_t energy_dtype,
+                           const void* mass_eV, int32_t mass_dtype,
+                           const void* num_elementary_charges, int32_t charge_dtype,
+                           double* constants, void* stream);
+
+/* particles_out[b, n, :] = (op_{end-1} o ... o op_begin)(particles_in[pidx(b), n, :]) with the
+ * constants of setting cidx(b); index / stride conventions as in ch_apply_maps
+ * (constants_stride = ch_nonlinear_constants_len, or 0 for one shared setting).  The beam
+ * energy is unchanged (the reference recomputes sqrt(p0c^2 + m^2), equal up to rounding).   */
+int ch_track_nonlinear(const ch_program* program, int32_t op_begin, int32_t op_end,
+                       const double* constants, int64_t constants_stride,
+                       const int32_t* constants_index,
+                       const void* particles_in, int64_t particle_stride,
+                       const int32_t* particle_index,
+                       int64_t n_particles, int64_t n_settings, void* particles_out,
+                       int32_t dtype, void* stream);
 
 /* space charge ----------------------------------------------------------------------- */
 /* One SpaceChargeKick (cheetah/accelerator/space_charge_kick.py:477-586) is the sequence

@@ -64,13 +64,14 @@ def test_lowering_groups_runs_apertures_and_barriers():
     ]
     program = lowering.lower(elements, torch.device("cpu"))
     kinds = [type(s).__name__ for s in program.stages]
-    assert kinds == ["LinearSection", "Barrier", "LinearSection", "Barrier", "LinearSection"]
+    assert kinds == ["LinearSection", "Barrier", "LinearSection", "NonlinearRun", "LinearSection"]
     first = program.stages[0]
     assert (first.op_begin, first.op_end) == (0, 6)
     assert first.n_apertures == 1 and first.elliptical_mask == 1
     assert first.lattice_shape == (3,) and first.length_shape == () and first.survival_shape == (3,)
     assert program.stages[1].kind == "space_charge"
-    assert program.stages[3].kind == "unsupported"
+    assert (program.stages[3].op_begin, program.stages[3].op_end) == (7, 8)
+    assert program.ops[7].opcode == _capi.OP_DKD_DRIFT
     assert [op.opcode for op in program.ops[:6]] == [
         _capi.OP_DRIFT, _capi.OP_QUADRUPOLE, _capi.OP_IDENTITY, _capi.OP_APERTURE,
         _capi.OP_DRIFT, _capi.OP_IDENTITY,
@@ -80,6 +81,44 @@ def test_lowering_groups_runs_apertures_and_barriers():
     assert [stride for _, stride, _ in quad.resolved] == [0, 1, 0, 0, 0]
     assert quad.resolved[1][0].data_ptr() == elements[1].k1.data_ptr()
     assert [offset for _, _, offset in quad.resolved] == [0, 0, 0, 0, 1]
+
+
+def test_lowering_groups_nonlinear_runs():
+    """drift_kick_drift / second_order elements form runs; identity elements in between join the
+    run, trailing ones open the next linear section."""
+    t = torch.tensor
+    elements = [
+        cb.Drift(length=t(0.5), tracking_method="drift_kick_drift"),
+        cb.Marker(),
+        cb.Quadrupole(length=t(0.2), k1=t([1.0, 2.0]), num_steps=4,
+                      tracking_method="drift_kick_drift"),
+        cb.Sextupole(length=t(0.1), k2=t(3.0)),
+        cb.BPM(),
+        cb.Marker(),
+        cb.Drift(length=t(0.3)),
+        cb.Dipole(length=t(0.4), angle=t(0.1), fringe_at="exit",
+                  tracking_method="drift_kick_drift"),
+        cb.TransverseDeflectingCavity(length=t(0.2), voltage=t(1e6)),
+        cb.Dipole(length=t(0.4), angle=t(0.1), tracking_method="second_order"),
+    ]
+    program = lowering.lower(elements, torch.device("cpu"))
+    assert [type(s).__name__ for s in program.stages] == [
+        "NonlinearRun", "LinearSection", "NonlinearRun"]
+    first, middle, last = program.stages
+    assert (first.op_begin, first.op_end) == (0, 4)
+    assert (middle.op_begin, middle.op_end) == (4, 7) and middle.has_maps
+    assert (last.op_begin, last.op_end) == (7, 10)
+    assert first.lattice_shape == (2,) and first.length_shape == ()
+    assert first.methods == ("drift_kick_drift", "drift_kick_drift", "second_order")
+    assert [op.opcode for op in program.ops] == [
+        _capi.OP_DKD_DRIFT, _capi.OP_IDENTITY, _capi.OP_DKD_QUADRUPOLE, _capi.OP_SECOND_ORDER,
+        _capi.OP_IDENTITY, _capi.OP_IDENTITY, _capi.OP_DRIFT,
+        _capi.OP_DKD_DIPOLE, _capi.OP_DKD_TDC, _capi.OP_SECOND_ORDER,
+    ]
+    assert program.ops[2].flags == 4                     # num_steps
+    assert program.ops[7].flags == 2                     # fringe at the exit only
+    assert program.ops[9].flags == 1                     # bend
+    assert len(program.ops[3].resolved) == 12 and len(program.ops[8].resolved) == 7
 
 
 def test_lowering_rejects_grad_and_wrong_device():
