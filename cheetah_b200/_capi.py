@@ -118,6 +118,14 @@ SIGNATURES = {
             c_int32, c_void_p,
         ],
     ),
+    "ch_screen_image": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+            c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+            c_int64, c_int64, c_int32, c_void_p, c_void_p,
+        ],
+    ),
     "ch_sc_beam_moments": (
         c_int32,
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p, c_void_p],

@@ -703,8 +703,10 @@ struct TrackArgs {
   int32_t bulk_out;
 };
 
-template <typename T, int P, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// FP64_OPS: the run holds a bend body or a TDC kick (evaluated in fp64); runs without them use a
+// leaner instantiation with more resident CTAs per SM (more tiles in flight).
+template <typename T, int P, int THREADS, bool FP64_OPS>
+__global__ void __launch_bounds__(THREADS, (FP64_OPS || sizeof(T) == 8) ? 1 : 6)
 nonlinear_track_kernel(const TrackArgs<T> a) {
   constexpr int TP = P * THREADS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -783,10 +785,10 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
             track_quadrupole(s, c, flags[op] > 0 ? flags[op] : 1, ref);
             break;
           case CH_OP_DKD_DIPOLE:
-            track_dipole(s, c64, flags[op], ref64);
+            if constexpr (FP64_OPS) track_dipole(s, c64, flags[op], ref64);
             break;
           case CH_OP_DKD_TDC:
-            track_tdc(s, c64, ref64);
+            if constexpr (FP64_OPS) track_tdc(s, c64, ref64);
             break;
           case CH_OP_SECOND_ORDER:
             track_second_order(s, c);
@@ -875,10 +877,19 @@ int launch_track(const ch_program* program, int32_t op_begin, int32_t op_end, co
   CH_REQUIRE(tiles <= 2147483647LL, "ch_track_nonlinear: too many particles");
   dim3 grid(static_cast<unsigned>(tiles),
             static_cast<unsigned>(n_settings < 65535 ? n_settings : 65535));
-  auto kernel = nonlinear_track_kernel<T, P, THREADS>;
-  CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem)));
-  kernel<<<grid, THREADS, smem, stream>>>(a);
+  bool fp64_ops = false;
+  for (int32_t i = op_begin; i < op_end; ++i)
+    fp64_ops |= program->opcodes_host[i] == CH_OP_DKD_DIPOLE ||
+                program->opcodes_host[i] == CH_OP_DKD_TDC;
+  auto launch = [&](auto kernel) -> int {
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    kernel<<<grid, THREADS, smem, stream>>>(a);
+    return CH_OK;
+  };
+  const int status = fp64_ops ? launch(nonlinear_track_kernel<T, P, THREADS, true>)
+                              : launch(nonlinear_track_kernel<T, P, THREADS, false>);
+  if (status != CH_OK) return status;
   CH_LAUNCH_CHECK();
   return CH_OK;
 }

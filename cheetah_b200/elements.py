@@ -368,6 +368,9 @@ class Marker(_SimpleElement):
 
 
 class BPM(_SimpleElement):
+    """Beam position monitor (cheetah/accelerator/bpm.py): when active it records
+    ``reading = (mu_x, mu_y) - misalignment`` of the passing beam."""
+
     tensor_fields = {"misalignment": (0.0, 0.0)}
     plain_fields = {"is_active": False}
 
@@ -375,17 +378,111 @@ class BPM(_SimpleElement):
     def is_skippable(self) -> bool:
         return not self.is_active
 
+    @property
+    def reading(self) -> torch.Tensor:
+        reading = self.__dict__.get("_reading")
+        if reading is None:  # bpm.py:58-63
+            reading = torch.full_like(self.misalignment, float("nan"))
+        return reading
+
+    @reading.setter
+    def reading(self, value: torch.Tensor) -> None:
+        object.__setattr__(self, "_reading", value)
+
+    def track(self, incoming: Beam) -> Beam:
+        from . import diagnostics
+
+        return diagnostics.track_bpm(self, incoming)
+
 
 class Screen(_SimpleElement):
+    """Diagnostic screen (cheetah/accelerator/screen.py): when active it remembers the passing
+    beam and renders ``reading`` (height, width) lazily with ``ch_screen_image``."""
+
     tensor_fields = {"pixel_size": (1e-3, 1e-3), "misalignment": (0.0, 0.0)}
     plain_fields = {
         "resolution": (1024, 1024), "binning": 1, "method": "cloud-in-cell",
         "kde_bandwidth": None, "is_blocking": False, "is_active": False,
     }
 
+    def __setattr__(self, name: str, value: Any) -> None:
+        if name == "resolution":
+            assert isinstance(value, (tuple, list)) and len(value) == 2, (
+                "Invalid resolution. Must be a tuple of 2 integers."
+            )
+        if name == "method":
+            assert value in ["histogram", "kde", "cloud-in-cell"], (
+                f"Invalid method {value}. Must be 'histogram', 'kde', or 'cloud-in-cell'."
+            )
+        if name in ("resolution", "binning", "method", "pixel_size", "misalignment"):
+            object.__setattr__(self, "_cached_reading", None)
+        super().__setattr__(name, value)
+
     @property
     def is_skippable(self) -> bool:
         return not self.is_active
+
+    @property
+    def effective_resolution(self) -> tuple[int, int]:
+        return (self.resolution[0] // self.binning, self.resolution[1] // self.binning)
+
+    @property
+    def effective_pixel_size(self) -> torch.Tensor:
+        return self.pixel_size * self.binning
+
+    @property
+    def extent(self) -> torch.Tensor:
+        return torch.stack([
+            -self.resolution[0] * self.pixel_size[0] / 2, self.resolution[0] * self.pixel_size[0] / 2,
+            -self.resolution[1] * self.pixel_size[1] / 2, self.resolution[1] * self.pixel_size[1] / 2,
+        ])
+
+    @property
+    def pixel_bin_edges(self) -> tuple[torch.Tensor, torch.Tensor]:
+        return tuple(
+            torch.linspace(
+                -self.resolution[i] * self.pixel_size[i] / 2,
+                self.resolution[i] * self.pixel_size[i] / 2,
+                int(self.effective_resolution[i]) + 1,
+                device=self.pixel_size.device, dtype=self.pixel_size.dtype,
+            )
+            for i in range(2)
+        )
+
+    @property
+    def pixel_bin_centers(self) -> tuple[torch.Tensor, torch.Tensor]:
+        edges = self.pixel_bin_edges
+        return ((edges[0][1:] + edges[0][:-1]) / 2, (edges[1][1:] + edges[1][:-1]) / 2)
+
+    def get_read_beam(self):
+        return self.__dict__.get("_read_beam")
+
+    def set_read_beam(self, value) -> None:
+        object.__setattr__(self, "_read_beam", value)
+        object.__setattr__(self, "_cached_reading", None)
+
+    @property
+    def reading(self) -> torch.Tensor:
+        """Image of the screen, ``(..., height, width)`` (screen.py:241-344)."""
+        cached = self.__dict__.get("_cached_reading")
+        if cached is not None:
+            return cached
+        read_beam = self.get_read_beam()
+        if read_beam is None:
+            image = self.misalignment.new_zeros(
+                (int(self.effective_resolution[1]), int(self.effective_resolution[0]))
+            )
+        else:
+            from . import diagnostics
+
+            image = diagnostics.screen_image(self, read_beam)
+        object.__setattr__(self, "_cached_reading", image)
+        return image
+
+    def track(self, incoming: Beam) -> Beam:
+        from . import diagnostics
+
+        return diagnostics.track_screen(self, incoming)
 
 
 class Aperture(_SimpleElement):

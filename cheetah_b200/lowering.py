@@ -73,7 +73,7 @@ class NonlinearRun:
 @dataclass
 class Barrier:
     element: object
-    kind: str  # "space_charge" or "unsupported"
+    kind: str  # "space_charge", "bpm", "screen" or "unsupported"
 
 
 class LatticeProgram:
@@ -415,6 +415,9 @@ def lower(elements, device: torch.device, target_shape: tuple = ()) -> LatticePr
         elif kind == "SpaceChargeKick":
             close_section()
             stages.append(Barrier(element, "space_charge"))
+        elif kind in ("BPM", "Screen"):  # active monitors record a reading between sections
+            close_section()
+            stages.append(Barrier(element, kind.lower()))
         else:
             close_section()
             stages.append(Barrier(element, "unsupported"))

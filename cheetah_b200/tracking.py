@@ -329,6 +329,15 @@ def _track_nonlinear_run(program, run, beam):
     return outgoing
 
 
+def _track_monitor(stage, beam):
+    """Active BPM / Screen between two sections (bpm.py:77-86, screen.py:187-239)."""
+    from . import diagnostics
+
+    if stage.kind == "bpm":
+        return diagnostics.track_bpm(stage.element, beam)
+    return diagnostics.track_screen(stage.element, beam)
+
+
 class BeamMoments:
     """What ``ParticleBeam.mu_*`` / ``sigma_*`` / ``num_particles_survived`` return on the
     outgoing beam, computed in the epilogue of the apply kernel (no (B, N, 7) array needed).
@@ -388,6 +397,8 @@ def track_moments(elements, incoming, cache_owner=None, keep_particles: bool = F
             from . import space_charge
 
             beam = space_charge.track(stage.element, beam)
+        elif stage.kind in ("bpm", "screen"):
+            beam = _track_monitor(stage, beam)
         else:
             raise NotImplementedError(
                 f"cheetah_b200: element {stage.element.name!r} is outside the accelerated hot path"
@@ -410,6 +421,12 @@ def _track_parameter_beam(program, beam):
             raise AssertionError(
                 "Second-order tracking is currently only supported for `ParticleBeam`."
             )
+        if isinstance(stage, lowering.Barrier) and stage.kind in ("bpm", "screen"):
+            beam = _track_monitor(stage, beam.__class__(
+                mu, cov, beam.energy, total_charge=beam.total_charge, s=s, species=beam.species,
+            ))
+            mu, cov, s = beam.mu, beam.cov, beam.s
+            continue
         if isinstance(stage, lowering.Barrier):
             if stage.kind == "space_charge":
                 raise AssertionError(
@@ -466,6 +483,8 @@ def track(elements, incoming, cache_owner=None):
             from . import space_charge
 
             beam = space_charge.track(stage.element, beam)
+        elif stage.kind in ("bpm", "screen"):
+            beam = _track_monitor(stage, beam)
         else:
             raise NotImplementedError(
                 f"cheetah_b200: element {stage.element.name!r} of type "

@@ -247,6 +247,25 @@ int ch_track_nonlinear(const ch_program* program, int32_t op_begin, int32_t op_e
                        int64_t n_particles, int64_t n_settings, void* particles_out,
                        int32_t dtype, void* stream);
 
+/* diagnostics -------------------------------------------------------------------------- */
+/* Image recorded by an active Screen for a ParticleBeam: Screen.reading
+ * (cheetah/accelerator/screen.py:241-344) with the read beam shifted by the screen misalignment
+ * (:199-215), weights |particle_charges| * survival, extent -+ resolution * pixel_size / 2
+ * (:137-146) and bins = resolution / binning.  method 0: 2-D cloud-in-cell deposit
+ * (cheetah/utils/cloud_in_cell.py:129-241); method 1: torch.histogramdd semantics on the given
+ * bin edges (edges_x [nx + 1], edges_y [ny + 1]: Screen.pixel_bin_edges, :148-166).  All arrays in
+ * the beam dtype; misalignment [B or 1][2] (stride 0 or 2), pixel_size [2].  image
+ * [B][resolution_y / binning][resolution_x / binning] (height, width) is zeroed here.         */
+int ch_screen_image(const void* particles, int64_t particle_stride,
+                    const void* charges, int64_t charge_stride,
+                    const void* survival, int64_t survival_stride,
+                    const void* misalignment, int64_t misalignment_stride,
+                    const void* pixel_size,
+                    int32_t resolution_x, int32_t resolution_y, int32_t binning, int32_t method,
+                    const void* edges_x, const void* edges_y,
+                    int64_t n_particles, int64_t n_beams, int32_t dtype,
+                    void* image, void* stream);
+
 /* space charge ----------------------------------------------------------------------- */
 /* One SpaceChargeKick (cheetah/accelerator/space_charge_kick.py:477-586) is the sequence
  *   ch_sc_beam_moments -> ch_sc_grid_params -> ch_sc_deposit -> ch_sc_green_function ->

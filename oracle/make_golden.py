@@ -669,7 +669,68 @@ def make_nonlinear() -> None:
           "cases")
 
 
+# --------------------------------------------------------------------------------------
+# 8. diagnostics: active Screen images and BPM readings
+# --------------------------------------------------------------------------------------
+def make_diagnostics() -> None:
+    arrays, meta = {}, {}
+    torch.manual_seed(21)
+    base = cheetah.ParticleBeam.from_parameters(
+        num_particles=6_000, sigma_x=torch.tensor(3e-4), sigma_y=torch.tensor(2e-4),
+        mu_x=torch.tensor(1e-4), mu_y=torch.tensor(-5e-5), total_charge=torch.tensor(1e-10),
+        dtype=torch.float64,
+    )
+    survival = (torch.rand(6_000, dtype=torch.float64) > 0.2).to(torch.float64) * torch.rand(
+        6_000, dtype=torch.float64)
+    base.survival_probabilities = survival
+    arrays.update(beam_arrays("incoming", base))
+    screens = {
+        "cic": dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5], method="cloud-in-cell"),
+        "cic_binned_misaligned": dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5], binning=2,
+                                      misalignment=[2e-4, -1e-4], method="cloud-in-cell"),
+        "cic_clipping": dict(resolution=(40, 30), pixel_size=[1e-5, 1e-5], method="cloud-in-cell"),
+        "histogram": dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5], method="histogram"),
+        "histogram_binned": dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5], binning=4,
+                                 misalignment=[2e-4, -1e-4], method="histogram"),
+    }
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        beam = base.to(dtype)
+        for name, kw in screens.items():
+            kwargs = {k: (torch.tensor(v, dtype=dtype) if isinstance(v, list) else v)
+                      for k, v in kw.items()}
+            screen = cheetah.Screen(is_active=True, name=name, dtype=dtype, **kwargs)
+            out = screen.track(beam)
+            assert torch.equal(out.particles, beam.particles)
+            arrays[f"screen.{name}.{tag}"] = np64(screen.reading)
+            meta[f"screen.{name}"] = kw
+        # vectorised beams (3 transverse offsets) on the cloud-in-cell screen
+        segment = cheetah.Segment([
+            cheetah.HorizontalCorrector(length=torch.tensor(0.1, dtype=dtype),
+                                        angle=torch.tensor([0.0, 1e-3, -2e-3], dtype=dtype)),
+            cheetah.Drift(length=torch.tensor(0.5, dtype=dtype)),
+            cheetah.BPM(is_active=True, name="bpm", misalignment=torch.tensor([1e-4, 2e-4], dtype=dtype)),
+            cheetah.Screen(is_active=True, name="screen", resolution=(96, 64),
+                           pixel_size=torch.tensor([2.5e-5, 3e-5], dtype=dtype), dtype=dtype),
+        ])
+        out = segment.track(beam)
+        arrays[f"segment.screen.{tag}"] = np64(segment.screen.reading)
+        arrays[f"segment.bpm.{tag}"] = np64(segment.bpm.reading)
+        arrays[f"segment.outgoing_shape.{tag}"] = np.asarray(out.particles.shape)
+        bpm = cheetah.BPM(is_active=True, misalignment=torch.tensor([0.1, 0.2], dtype=dtype))
+        bpm.track(beam)
+        arrays[f"bpm.{tag}"] = np64(bpm.reading)
+        blocking = cheetah.Screen(is_active=True, is_blocking=True, dtype=dtype)
+        arrays[f"blocking.survival.{tag}"] = np64(blocking.track(beam).survival_probabilities)
+    np.savez_compressed(OUT / "diagnostics.npz", **arrays)
+    with (OUT / "diagnostics.json").open("w") as f:
+        json.dump(meta, f, separators=(",", ":"))
+    print("diagnostics:", len(screens), "screens, sum", float(arrays["screen.cic.f64"].sum()))
+
+
 if __name__ == "__main__":
+    if "--only-diagnostics" in sys.argv:
+        make_diagnostics()
+        sys.exit(0)
     if "--only-cavity" in sys.argv:
         make_cavity()
         sys.exit(0)
@@ -683,5 +744,6 @@ if __name__ == "__main__":
     make_space_charge()
     make_cavity()
     make_nonlinear()
+    make_diagnostics()
     for path in sorted(OUT.iterdir()):
         print(f"{path.name:40s} {path.stat().st_size / 1024:8.1f} KiB")

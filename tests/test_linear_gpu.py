@@ -304,8 +304,13 @@ def test_errors_are_loud():
     beam = cb.ParticleBeam.from_parameters(num_particles=16, dtype=torch.float32)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cb.Drift(length=torch.tensor(1.0)).track(beam)
+    class Wiggler(cb.Element):  # an element type this backend does not know
+        @property
+        def is_skippable(self) -> bool:
+            return False
+
     with pytest.raises(NotImplementedError, match="outside the accelerated hot path"):
-        cb.Drift(length=torch.tensor(1.0, device=DEVICE), tracking_method="drift_kick_drift").track(
+        Wiggler(name="w").track(
             cb.ParticleBeam.from_parameters(num_particles=16, device=DEVICE, dtype=torch.float32)
         )
     with pytest.raises(ValueError, match="move the lattice"):
