@@ -33,6 +33,10 @@ def main() -> None:
     p.add_argument("--cells", type=int, default=50)
     p.add_argument("--grid", type=int, default=64)
     p.add_argument("--particles", type=int, default=1_000_000)
+    p.add_argument("--beams", type=int, default=1,
+                   help="independent beams tracked together (BASELINE configs[4]: 1024 beams "
+                        "over 8 GPUs = 128 per GPU); total charge linspace(1e-11, 1e-9)")
+    p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     args = p.parse_args()
 
@@ -46,9 +50,18 @@ def main() -> None:
     segment = workloads.product_segment(description, device, dtype)
     particles = workloads.parameters_beam_particles(n)
     charges = torch.full((n,), 1e-10 / n, dtype=dtype)
+    B = args.beams
+    if B == 1:
+        beam_particles, beam_charges = particles.to(device=device, dtype=dtype), charges.to(device)
+    else:  # per-beam particles (seed = beam index) and charges
+        beam_particles = torch.empty((B, n, 7), device=device, dtype=dtype)
+        for i in range(B):
+            beam_particles[i] = workloads.parameters_beam_particles(n, seed=i).to(device=device, dtype=dtype)
+        total = torch.linspace(1e-11, 1e-9, B, dtype=dtype)
+        beam_charges = (total.unsqueeze(-1) / n).expand(B, n).contiguous().to(device)
     beam = cb.ParticleBeam(
-        particles.to(device=device, dtype=dtype), torch.tensor(1e8, device=device, dtype=dtype),
-        particle_charges=charges.to(device), species=cb.Species("electron", device=device, dtype=dtype),
+        beam_particles, torch.tensor(1e8, device=device, dtype=dtype),
+        particle_charges=beam_charges, species=cb.Species("electron", device=device, dtype=dtype),
     )
     beam._unit_seventh = True
     n_elements, kicks = len(description), 2 * args.cells
@@ -67,8 +80,10 @@ def main() -> None:
         return a.elapsed_time(b) / steps, _capi.launch_count() - before
 
     ms, launches = timed(lambda: segment.track(beam), args.steps, args.warmup)
-    graphed = cb.GraphedTrack(segment, beam)
-    graph_ms, _ = timed(lambda: graphed.replay(), args.steps, 1)
+    graph_ms = None
+    if not args.no_graph:
+        graphed = cb.GraphedTrack(segment, beam)
+        graph_ms, _ = timed(lambda: graphed.replay(), args.steps, 1)
 
     # ---- per-kernel timing of ONE kick, stage by stage -------------------------------------
     lib = _capi.lib()
@@ -81,6 +96,8 @@ def main() -> None:
     stream = _capi.current_stream(device)
     code = _capi.CH_F32
     pp, q, w = beam.particles, beam.particle_charges, beam.survival_probabilities
+    ps, qs = (0, 0) if B == 1 else (n * 7, n)
+    out = out.reshape(B, n, 7)
     one = torch.tensor(1.0, device=device)
     three = torch.tensor(3.0, device=device)
     cells3 = grid ** 3
@@ -88,38 +105,40 @@ def main() -> None:
     stages = {
         "sc_moments_kernel (+grid params)": (
             lambda: lib.ch_sc_moments_and_params(
-                pp.data_ptr(), 0, w.data_ptr(), 0, n, 1, beam.energy.data_ptr(), 0, code,
+                pp.data_ptr(), ps, w.data_ptr(), 0, n, B, beam.energy.data_ptr(), 0, code,
                 beam.species.mass_eV.data_ptr(), code, one.data_ptr(), 0, code,
                 three.data_ptr(), 0, three.data_ptr(), 0, three.data_ptr(), 0, code,
                 grid, grid, grid, code, ws.stats.data_ptr(), ws.params.data_ptr(), stream),
-            n * 32, "hbm: 28 B row + 4 B survival per particle"),
+            B * n * 32, "hbm: 28 B row + 4 B survival per particle"),
         "sc_deposit_kernel": (
             lambda: lib.ch_sc_deposit(
-                pp.data_ptr(), 0, q.data_ptr(), 0, w.data_ptr(), 0, ws.params.data_ptr(), n, 1,
+                pp.data_ptr(), ps, q.data_ptr(), qs, w.data_ptr(), 0, ws.params.data_ptr(), n, B,
                 grid, grid, grid, code, ws.rho_split.data_ptr(), stream),
-            n * 36, "hbm: 28 B row + charge + survival per particle (atomics stay in L2)"),
+            B * n * 36, "hbm: 28 B row + charge + survival per particle (atomics stay in L2)"),
         "green lattice + 3 even FFT passes": (
-            lambda: (lib.ch_sc_green_function(ws.params.data_ptr(), 1, grid, grid, grid, code,
+            lambda: (lib.ch_sc_green_function(ws.params.data_ptr(), B, grid, grid, grid, code,
                                               ws.lattice.data_ptr(), None, stream),
-                     lib.ch_sc_green_spectrum(ws.lattice.data_ptr(), 1, grid, grid, grid, code,
+                     lib.ch_sc_green_spectrum(ws.lattice.data_ptr(), B, grid, grid, grid, code,
                                               ws.green_scratch.data_ptr(),
                                               ws.green_spectrum.data_ptr(), stream)),
-            (grid + 1) ** 3 * (8 + 8) + 4 * cells3 * 4, "L2-resident: lattice write+read, 3 passes"),
+            B * ((grid + 1) ** 3 * (8 + 8) + 4 * cells3 * 4),
+            "lattice write+read, 3 passes (L2-resident for one beam)"),
         "poisson: r2c z, y, fused x conv, inverse y, c2r z": (
             lambda: lib.ch_sc_poisson_solve(
-                ws.rho_split.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), 1,
+                ws.rho_split.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), B,
                 grid, grid, grid, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream),
-            int(spectrum_bytes * (0.25 + 0.5 + 0.5 + 1.0 + 0.5 + 0.5 + 0.25)) + cells3 * 12,
-            "L2-resident: spectrum passes touch 1/4 .. 1 of the (2n)^2 (n+1) complex array"),
+            B * (int(spectrum_bytes * (0.25 + 0.5 + 0.5 + 1.0 + 0.5 + 0.5 + 0.25)) + cells3 * 12),
+            "spectrum passes touch 1/4 .. 1 of the (2n)^2 (n+1) complex array (L2-resident for "
+            "one beam)"),
         "sc_field_kernel": (
-            lambda: lib.ch_sc_field(ws.phi.data_ptr(), ws.params.data_ptr(), 1, grid, grid, grid,
+            lambda: lib.ch_sc_field(ws.phi.data_ptr(), ws.params.data_ptr(), B, grid, grid, grid,
                                     code, ws.field.data_ptr(), stream),
-            cells3 * (4 + 32), "phi read + paired field write"),
+            B * cells3 * (4 + 32), "phi read + paired field write"),
         "sc_gather_kick_kernel": (
-            lambda: lib.ch_sc_gather_kick(pp.data_ptr(), 0, ws.field.data_ptr(),
-                                          ws.params.data_ptr(), n, 1, grid, grid, grid, code,
+            lambda: lib.ch_sc_gather_kick(pp.data_ptr(), ps, ws.field.data_ptr(),
+                                          ws.params.data_ptr(), n, B, grid, grid, grid, code,
                                           out.data_ptr(), None, stream),
-            n * 56, "hbm: 28 B row read + 28 B row written per particle (gathers hit L2)"),
+            B * n * 56, "hbm: 28 B row read + 28 B row written per particle (gathers hit L2)"),
     }
     peak = 6450.0
     peaks = REPO / "MEASURED_PEAKS.json"
@@ -127,7 +146,7 @@ def main() -> None:
         peak = float(json.loads(peaks.read_text())["hbm_gbs"])
     kernels = []
     for name, (fn, nbytes, note) in stages.items():
-        stage_ms, _ = timed(fn, 20, 3)
+        stage_ms, _ = timed(fn, 20 if B == 1 else 5, 3 if B == 1 else 1)
         kernels.append({
             "kernel": name, "us": stage_ms * 1e3, "algorithmic_bytes": nbytes,
             "achieved_gbs": nbytes / (stage_ms * 1e-3) / 1e9,
@@ -158,17 +177,20 @@ def main() -> None:
 
     line = {
         "metric": "particle-steps/sec (Segment.track, ParticleBeam)",
-        "value": n * n_elements / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": 1,
+        "value": B * n * n_elements / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "n/a", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"{args.cells} FODO cells x [Quadrupole, Drift/2, SpaceChargeKick({grid}^3), "
                         f"Drift/2] x 2 = {n_elements} elements, {kicks} kicks, {n} particles, "
-                        "total charge 1e-10 C, 1e8 eV -- BASELINE configs[3]",
-            "particles": n, "n_elements": n_elements, "kicks": kicks, "grid": grid,
+                        "total charge 1e-10 C, 1e8 eV -- BASELINE configs[3]"
+                        + ("" if B == 1 else f"; {B} independent beams with per-beam particles and "
+                           "charges (one GPU's share of BASELINE configs[4])"),
+            "particles": n, "beams": B, "n_elements": n_elements, "kicks": kicks, "grid": grid,
         },
-        "particle_kicks_per_s": n * kicks / (ms * 1e-3),
-        "graph_value": n * n_elements / (graph_ms * 1e-3), "graph_ms_per_step": graph_ms,
+        "particle_kicks_per_s": B * n * kicks / (ms * 1e-3),
+        "graph_value": None if graph_ms is None else B * n * n_elements / (graph_ms * 1e-3),
+        "graph_ms_per_step": graph_ms,
         "gpu_launches": launches,
         "roofline": {
             "kernel": dominant["kernel"], "bound": "hbm", "achieved": dominant["achieved_gbs"],

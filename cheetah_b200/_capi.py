@@ -34,7 +34,7 @@ OP_DKD_DIPOLE = 13
 OP_DKD_TDC = 14
 OP_SECOND_ORDER = 15
 NONLINEAR_OPS = (OP_DKD_DRIFT, OP_DKD_QUADRUPOLE, OP_DKD_DIPOLE, OP_DKD_TDC, OP_SECOND_ORDER)
-NL_HEADER = 8
+NL_HEADER = 12
 NL_MAX_OPS = 64
 
 RECORD_HEADER = 2

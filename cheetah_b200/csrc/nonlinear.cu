@@ -112,7 +112,10 @@ __device__ __forceinline__ double si2msi2divdiff(double a, double b) {  // :546-
 
 // ---- constant-block layouts ------------------------------------------------------------------
 // header (CH_NL_HEADER scalars per setting)
-enum { H_P0C = 0, H_MC2 = 1, H_E0 = 2, H_BETA0 = 3, H_MC2_E0_SQ = 4, H_LENGTH = 5, H_CHARGE = 6 };
+enum {
+  H_P0C = 0, H_MC2 = 1, H_E0 = 2, H_BETA0 = 3, H_MC2_E0_SQ = 4, H_LENGTH = 5, H_CHARGE = 6,
+  H_INV_P0C = 7, H_TWO_E0_OVER_P0C = 8
+};
 // drift_kick_drift ops
 enum { D_L = 0 };
 enum { Q_L = 0, Q_K1 = 1, Q_COS = 2, Q_SIN = 3, Q_XOFF = 4, Q_YOFF = 5, Q_STEP = 6 };
@@ -397,7 +400,9 @@ nonlinear_constants_kernel(Program prog, int32_t op_begin, int32_t n_ops, Scalar
     base[H_MC2_E0_SQ] = static_cast<double>((mc2 / E0) * (mc2 / E0));
     base[H_LENGTH] = static_cast<double>(total);
     base[H_CHARGE] = static_cast<double>(q);
-    base[7] = 0.0;
+    base[H_INV_P0C] = 1.0 / p0c;
+    base[H_TWO_E0_OVER_P0C] = 2.0 * E0 / p0c;
+    for (int i = H_TWO_E0_OVER_P0C + 1; i < CH_NL_HEADER; ++i) base[i] = 0.0;
   }
 }
 
@@ -419,32 +424,53 @@ __device__ __forceinline__ C sqrt_one(C x) {
 
 template <typename C>
 struct Beam0 {  // reference-particle constants of one setting
-  C p0c, mc2, E0, beta0, mc2_e0_sq;
+  C p0c, mc2, E0, beta0, mc2_e0_sq, inv_p0c, two_e0_over_p0c;
 };
 
-// particle state: transverse coordinates + either (tau, delta) or Bmad-X (z, pz)
+// particle state: transverse coordinates + either (tau, delta) or Bmad-X (z, pz).  In Bmad-X
+// mode the quantities that only depend on pz are carried along, so that a run of elements
+// evaluates them once per particle: iP = 1 / (1 + pz), rb = beta / beta0 - 1, inv_beta = 1 / beta
+// and the delta that corresponds to pz (for the way back).
 template <typename C>
 struct State {
   C x, px, y, py, l, d;
+  C iP, rb, inv_beta, delta;
 };
 
 // (tau, delta) -> (z, pz): bmadx.py:7-30 with p^2 - p0c^2 = delta p0c (2 E0 + delta p0c)
 template <typename C>
 __device__ __forceinline__ void to_bmad(State<C>& s, const Beam0<C>& r) {
   const C energy = r.E0 + s.d * r.p0c;
-  const C pz = sqrt_one(s.d * (C(2) * r.E0 + s.d * r.p0c) / r.p0c);
-  const C beta = (C(1) + pz) * r.p0c / energy;
-  s.l = -beta * s.l;
+  const C inv_energy = C(1) / energy;
+  const C pz = sqrt_one(s.d * (r.two_e0_over_p0c + s.d));
+  const C P = C(1) + pz;
+  const C m_over_e = r.mc2 * inv_energy;
+  s.iP = C(1) / P;
+  s.rb = sqrt_one(m_over_e * m_over_e * pz * (C(2) + pz));  // (beta/beta0)^2 - 1 -> beta/beta0 - 1
+  s.inv_beta = energy * s.iP * r.inv_p0c;
+  s.delta = s.d;
+  s.l = -(P * r.p0c * inv_energy) * s.l;
   s.d = pz;
 }
 
-// (z, pz) -> (tau, delta): bmadx.py:33-55 with E^2 - E0^2 = p0c^2 pz (2 + pz)
+// refresh the pz-dependent quantities after an element that changed pz (TDC)
 template <typename C>
-__device__ __forceinline__ void from_bmad(State<C>& s, const Beam0<C>& r) {
-  const C p = (C(1) + s.d) * r.p0c;
+__device__ __forceinline__ void refresh_from_pz(State<C>& s, const Beam0<C>& r) {
+  const C P = C(1) + s.d;
+  const C p = P * r.p0c;
   const C energy = sqrt_t(p * p + r.mc2 * r.mc2);
-  s.l = -s.l * energy / p;
-  s.d = r.p0c * s.d * (C(2) + s.d) / (energy + r.E0);
+  const C m_over_e = r.mc2 / energy;
+  s.iP = C(1) / P;
+  s.rb = sqrt_one(m_over_e * m_over_e * s.d * (C(2) + s.d));
+  s.inv_beta = energy / p;
+  s.delta = r.p0c * s.d * (C(2) + s.d) / (energy + r.E0);  // E^2 - E0^2 = p0c^2 pz (2 + pz)
+}
+
+// (z, pz) -> (tau, delta): bmadx.py:33-55
+template <typename C>
+__device__ __forceinline__ void from_bmad(State<C>& s) {
+  s.l = -s.l * s.inv_beta;
+  s.d = s.delta;
 }
 
 template <typename C>
@@ -466,36 +492,31 @@ __device__ __forceinline__ void offset_unset(State<C>& s, C cs, C sn, C x_off, C
   s.py = px * sn + py * cs;
 }
 
-// m^2 pz (2 + pz) / ((p0c P)^2 + m^2) = (beta / beta0)^2 - 1
+// exact drift (bmadx.py:271-302) with the cached 1 / P and beta / beta0 - 1:
+//   dz = L (sqrt_one((beta/beta0)^2 - 1) + sqrt_one(-Pxy2) / Pl),  sqrt_one(-Pxy2) = -Pxy2 / (Pl + 1)
 template <typename C>
-__device__ __forceinline__ C beta_ratio_sq_minus_one(C pz, const Beam0<C>& r) {
-  const C pc = r.p0c * (C(1) + pz);
-  return r.mc2 * r.mc2 * (C(2) * pz + pz * pz) / (pc * pc + r.mc2 * r.mc2);
-}
-
-// exact drift (bmadx.py:271-302)
-template <typename C>
-__device__ __forceinline__ void track_a_drift(State<C>& s, C L, const Beam0<C>& r) {
-  const C iP = C(1) / (C(1) + s.d);
-  const C Px = s.px * iP, Py = s.py * iP;
+__device__ __forceinline__ void track_a_drift(State<C>& s, C L) {
+  const C Px = s.px * s.iP, Py = s.py * s.iP;
   const C Pxy2 = Px * Px + Py * Py;
-  const C iPl = C(1) / sqrt_t(C(1) - Pxy2);
-  const C dz = L * (sqrt_one(beta_ratio_sq_minus_one(s.d, r)) + sqrt_one(-Pxy2) * iPl);
-  s.x += L * Px * iPl;
-  s.y += L * Py * iPl;
-  s.l += dz;
+  const C Pl = sqrt_t(C(1) - Pxy2);
+  const C t = C(1) / (Pl * (Pl + C(1)));
+  const C L_over_Pl = L * t * (Pl + C(1));
+  s.x += L_over_Pl * Px;
+  s.y += L_over_Pl * Py;
+  s.l += L * (s.rb - Pxy2 * t);
 }
 
-// bmadx.py:183-220; the high-|pz| branch ds (beta - beta0) / beta0 is evaluated as
-// ds (sqrt(1 + ((beta/beta0)^2 - 1)) - 1), which does not cancel
+// bmadx.py:183-220; the high-|pz| branch ds (beta - beta0) / beta0 is ds * rb, which does not
+// cancel
 template <typename C>
-__device__ __forceinline__ C low_energy_z_correction(C pz, C ds, const Beam0<C>& r) {
+__device__ __forceinline__ C low_energy_z_correction(const State<C>& s, C ds, const Beam0<C>& r) {
+  const C pz = s.d;
   const C evaluation = r.mc2 * (r.beta0 * pz) * (r.beta0 * pz);
   const C b2 = r.beta0 * r.beta0;
   if (evaluation < C(3e-7) * r.E0)
     return ds * pz * (C(1) - C(3) * (pz * b2) / C(2) +
                       pz * pz * b2 * (C(2) * b2 - r.mc2_e0_sq / C(2))) * r.mc2_e0_sq;
-  return ds * sqrt_one(beta_ratio_sq_minus_one(pz, r));
+  return ds * s.rb;
 }
 
 // one plane of bmadx.py:223-260 for the argument `k1` (kx^2 = -k1), step length l
@@ -504,7 +525,7 @@ struct QuadPlane {
   C a11, a12, a21, c1, c2, c3;
 };
 template <typename C>
-__device__ __forceinline__ QuadPlane<C> quadrupole_plane(C k1, C l, C rel_p) {
+__device__ __forceinline__ QuadPlane<C> quadrupole_plane(C k1, C l, C rel_p, C inv_rel_p) {
   C cx, sx;
   if (k1 < C(0)) {  // kx real: focusing
     const C k = sqrt_t(-k1);
@@ -521,11 +542,11 @@ __device__ __forceinline__ QuadPlane<C> quadrupole_plane(C k1, C l, C rel_p) {
   }
   QuadPlane<C> q;
   q.a11 = cx;
-  q.a12 = sx / rel_p;
+  q.a12 = sx * inv_rel_p;
   q.a21 = k1 * sx * rel_p;
-  q.c1 = k1 * (-cx * sx + l) / C(4);
-  q.c2 = -k1 * sx * sx / (C(2) * rel_p);
-  q.c3 = -(cx * sx + l) / (C(4) * rel_p * rel_p);
+  q.c1 = k1 * (-cx * sx + l) * C(0.25);
+  q.c2 = -k1 * sx * sx * C(0.5) * inv_rel_p;
+  q.c3 = -(cx * sx + l) * C(0.25) * inv_rel_p * inv_rel_p;
   return q;
 }
 
@@ -535,10 +556,10 @@ __device__ __forceinline__ void track_quadrupole(State<C>& s, const C* c, int nu
                                                  const Beam0<C>& r) {
   offset_set(s, c[Q_COS], c[Q_SIN], c[Q_XOFF], c[Q_YOFF]);
   const C rel_p = C(1) + s.d;
-  const C k1 = c[Q_K1] / rel_p;  // b1 / (L rel_p)
-  const QuadPlane<C> tx = quadrupole_plane(-k1, c[Q_STEP], rel_p);
-  const QuadPlane<C> ty = quadrupole_plane(k1, c[Q_STEP], rel_p);
-  const C dz_low = low_energy_z_correction(s.d, c[Q_STEP], r);
+  const C k1 = c[Q_K1] * s.iP;  // b1 / (L rel_p)
+  const QuadPlane<C> tx = quadrupole_plane(-k1, c[Q_STEP], rel_p, s.iP);
+  const QuadPlane<C> ty = quadrupole_plane(k1, c[Q_STEP], rel_p, s.iP);
+  const C dz_low = low_energy_z_correction(s, c[Q_STEP], r);
   for (int step = 0; step < num_steps; ++step) {
     s.l += tx.c1 * s.x * s.x + tx.c2 * s.x * s.px + tx.c3 * s.px * s.px +
            ty.c1 * s.y * s.y + ty.c2 * s.y * s.py + ty.c3 * s.py * s.py;
@@ -620,7 +641,8 @@ __device__ __forceinline__ void track_tdc(State<C>& st, const double* cc, const 
   State<double> s{st.x, st.px, st.y, st.py, st.l, st.d};
   const double cs = cc[T_COS], sn = cc[T_SIN], xo = cc[T_XOFF], yo = cc[T_YOFF];
   offset_set(s, cs, sn, xo, yo);
-  track_a_drift(s, cc[T_HALF], r);
+  refresh_from_pz(s, r);
+  track_a_drift(s, cc[T_HALF]);
   const double voltage = cc[T_V], k_rf = cc[T_KRF];
   const double pc_old = (1.0 + s.d) * r.p0c;
   const double E_old = sqrt(pc_old * pc_old + r.mc2 * r.mc2);
@@ -637,7 +659,8 @@ __device__ __forceinline__ void track_tdc(State<C>& st, const double* cc, const 
   const double E0 = sqrt(r.p0c * r.p0c + r.mc2 * r.mc2);
   s.d = (E_new - E0) * (E_new + E0) / (r.p0c * (pc + r.p0c));
   s.l = s.l * beta / beta_old;
-  track_a_drift(s, cc[T_HALF], r);
+  refresh_from_pz(s, r);
+  track_a_drift(s, cc[T_HALF]);
   offset_unset(s, cs, sn, xo, yo);
   st.x = static_cast<C>(s.x);
   st.px = static_cast<C>(s.px);
@@ -645,6 +668,10 @@ __device__ __forceinline__ void track_tdc(State<C>& st, const double* cc, const 
   st.py = static_cast<C>(s.py);
   st.l = static_cast<C>(s.l);
   st.d = static_cast<C>(s.d);
+  st.iP = static_cast<C>(s.iP);  // pz changed: hand the refreshed pz-dependent quantities back
+  st.rb = static_cast<C>(s.rb);
+  st.inv_beta = static_cast<C>(s.inv_beta);
+  st.delta = static_cast<C>(s.delta);
 }
 
 // element.py:195-225 with the frame changes of quadrupole.py:136-143 / dipole.py:417-426 applied
@@ -710,12 +737,16 @@ __global__ void __launch_bounds__(THREADS, (FP64_OPS || sizeof(T) == 8) ? 1 : 6)
 nonlinear_track_kernel(const TrackArgs<T> a) {
   constexpr int TP = P * THREADS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // stage: outgoing rows (read by the bulk store); in0 / in1: double-buffered incoming tiles, so
+  // that the tile of the NEXT setting is in flight while this one is computed
   T* stage = reinterpret_cast<T*>(smem_raw);
-  double* consts64 = reinterpret_cast<double*>(stage + TP * 7);
+  T* in0 = stage + TP * 7;
+  T* in1 = in0 + TP * 7;
+  double* consts64 = reinterpret_cast<double*>(in1 + TP * 7);
   const int n_consts = CH_NL_HEADER + a.n_ops * a.block;
   T* consts = reinterpret_cast<T*>(consts64 + n_consts);  // the same, rounded to the beam dtype
-  uint64_t* bar = reinterpret_cast<uint64_t*>(consts + (n_consts + 3) / 4 * 4);
-  int32_t* codes = reinterpret_cast<int32_t*>(bar + 1);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(consts + (n_consts + 3) / 4 * 4);  // bar[0..1]
+  int32_t* codes = reinterpret_cast<int32_t*>(bar + 2);
   int32_t* flags = codes + a.n_ops;
 
   const int tid = threadIdx.x;
@@ -724,6 +755,7 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
 
   if (a.bulk_in && tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < a.n_ops; i += THREADS) {
@@ -732,9 +764,27 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
   }
   __syncthreads();
 
+  auto tile_offset = [&](int64_t b) {
+    return (a.particle_index ? a.particle_index[b] : b) * a.particle_stride + n0 * 7;
+  };
+  // one elected thread asks the TMA engine for the tile at `offset` (bulk path only)
+  auto request = [&](int buf, int64_t offset) {
+    if (tid == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(count) * 7u * sizeof(T);
+      mbar_expect_tx(bar + buf, bytes);
+      bulk_load(buf ? in1 : in0, a.particles_in + offset, bytes, bar + buf);
+    }
+  };
+
   T p[P][7];
-  int64_t loaded = -1;
-  uint32_t phase = 0;
+  int64_t loaded = -1;     // offset of the tile held in registers
+  int64_t requested = -1;  // offset of the tile most recently requested (into in[buf])
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;             // buffer the next needed tile is (being) loaded into
+  if (a.bulk_in && blockIdx.y < a.n_settings) {
+    requested = tile_offset(blockIdx.y);
+    request(0, requested);
+  }
   for (int64_t b = blockIdx.y; b < a.n_settings; b += gridDim.y) {
     // the staging tile may still be read by the bulk store of the previous setting
     if (a.bulk_out && tid == 0) bulk_wait_read<0>();
@@ -746,24 +796,52 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
       consts64[i] = v;
       consts[i] = static_cast<T>(v);
     }
-    const int64_t p_off =
-        (a.particle_index ? a.particle_index[b] : b) * a.particle_stride + n0 * 7;
+    const int64_t p_off = tile_offset(b);
     if (p_off != loaded) {
-      cta_load_tile(stage, a.particles_in + p_off, count * 7, a.bulk_in != 0, bar, phase);
+      const T* tile;
+      if (a.bulk_in) {
+        // normally the tile was prefetched during the previous iteration; if not (the previous
+        // settings shared one tile), ask for it now.  Then prefetch the following tile into the
+        // other buffer (every thread finished reading it before the barrier at the top of this
+        // iteration).
+        if (requested != p_off) {
+          requested = p_off;
+          request(buf, p_off);
+        }
+        const int64_t b_next = b + gridDim.y;
+        const int cur = buf;
+        if (b_next < a.n_settings) {
+          const int64_t next_off = tile_offset(b_next);
+          if (next_off != p_off) {
+            requested = next_off;
+            buf ^= 1;
+            request(buf, next_off);
+          }
+        }
+        mbar_wait(bar + cur, phase[cur]);
+        phase[cur] ^= 1u;
+        tile = cur ? in1 : in0;
+      } else {
+        const T* src = a.particles_in + p_off;
+        for (int i = tid; i < count * 7; i += THREADS) in0[i] = src[i];
+        __syncthreads();
+        tile = in0;
+      }
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         const int local = tid + k * THREADS;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) p[k][j] = local < count ? stage[local * 7 + j] : T(0);
+        for (int j = 0; j < 7; ++j) p[k][j] = local < count ? tile[local * 7 + j] : T(0);
       }
       loaded = p_off;
     }
     __syncthreads();  // constants visible, tile consumed
 
     const Beam0<T> ref{consts[H_P0C], consts[H_MC2], consts[H_E0], consts[H_BETA0],
-                       consts[H_MC2_E0_SQ]};
+                       consts[H_MC2_E0_SQ], consts[H_INV_P0C], consts[H_TWO_E0_OVER_P0C]};
     const Beam0<double> ref64{consts64[H_P0C], consts64[H_MC2], consts64[H_E0],
-                              consts64[H_BETA0], consts64[H_MC2_E0_SQ]};
+                              consts64[H_BETA0], consts64[H_MC2_E0_SQ], consts64[H_INV_P0C],
+                              consts64[H_TWO_E0_OVER_P0C]};
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       State<T> s{p[k][0], p[k][1], p[k][2], p[k][3], p[k][4], p[k][5]};
@@ -775,11 +853,11 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
         if (code == CH_OP_IDENTITY) continue;
         const bool wants_bmad = code != CH_OP_SECOND_ORDER;
         if (wants_bmad && !bmad) to_bmad(s, ref);
-        if (!wants_bmad && bmad) from_bmad(s, ref);
+        if (!wants_bmad && bmad) from_bmad(s);
         bmad = wants_bmad;
         switch (code) {
           case CH_OP_DKD_DRIFT:
-            track_a_drift(s, c[D_L], ref);
+            track_a_drift(s, c[D_L]);
             break;
           case CH_OP_DKD_QUADRUPOLE:
             track_quadrupole(s, c, flags[op] > 0 ? flags[op] : 1, ref);
@@ -797,7 +875,7 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
             break;
         }
       }
-      if (bmad) from_bmad(s, ref);
+      if (bmad) from_bmad(s);
       T* row = stage + (tid + k * THREADS) * 7;
       row[0] = s.x;
       row[1] = s.px;
@@ -871,12 +949,15 @@ int launch_track(const ch_program* program, int32_t op_begin, int32_t op_end, co
   a.bulk_in = bulk_compatible<T>(particles_in, n_particles, particle_stride) ? 1 : 0;
   a.bulk_out = bulk_compatible<T>(particles_out, n_particles, n_particles * 7) ? 1 : 0;
   const int n_consts = CH_NL_HEADER + a.n_ops * a.block;
-  const size_t smem = sizeof(T) * (TP * 7 + (n_consts + 3) / 4 * 4) + sizeof(double) * n_consts +
-                      sizeof(uint64_t) + 2 * sizeof(int32_t) * a.n_ops;
+  const size_t smem = sizeof(T) * (3 * TP * 7 + (n_consts + 3) / 4 * 4) + sizeof(double) * n_consts +
+                      2 * sizeof(uint64_t) + 2 * sizeof(int32_t) * a.n_ops;
   const int64_t tiles = (n_particles + TP - 1) / TP;
   CH_REQUIRE(tiles <= 2147483647LL, "ch_track_nonlinear: too many particles");
-  dim3 grid(static_cast<unsigned>(tiles),
-            static_cast<unsigned>(n_settings < 65535 ? n_settings : 65535));
+  // enough CTAs for ~8 waves of 148 SMs x 6 resident CTAs; beyond that a CTA loops over settings
+  // (the beam tile stays in registers when it is shared, and is prefetched when it is not)
+  int64_t rows = (148 * 6 * 8 + tiles - 1) / tiles;
+  rows = rows < 1 ? 1 : (rows > n_settings ? n_settings : rows);
+  dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(rows < 65535 ? rows : 65535));
   bool fp64_ops = false;
   for (int32_t i = op_begin; i < op_end; ++i)
     fp64_ops |= program->opcodes_host[i] == CH_OP_DKD_DIPOLE ||

@@ -212,10 +212,11 @@ int ch_apply_maps_moments(const void* particles_in, int64_t particle_stride, con
  * setting) for the whole run.  Replaces Drift/Quadrupole/Dipole._track_drift_kick_drift,
  * TransverseDeflectingCavity._track_drift_kick_drift and Element._track_second_order (files
  * cited at the opcodes).  Per setting the constants are
- *   [CH_NL_HEADER]  p0c, mc^2, E0, beta0, (mc^2 / E0)^2, sum of the element lengths, charge, 0
+ *   [CH_NL_HEADER]  p0c, mc^2, E0, beta0, (mc^2 / E0)^2, sum of the element lengths, charge,
+ *                   1 / p0c, 2 E0 / p0c, 0, 0, 0
  *   then one block per op: CH_NL_BLOCK_SECOND_ORDER scalars if the run holds a second-order op,
  *   else CH_NL_BLOCK_DKD (ch_nonlinear_constants_len gives the total).                      */
-#define CH_NL_HEADER 8
+#define CH_NL_HEADER 12
 #define CH_NL_BLOCK_DKD 16
 #define CH_NL_BLOCK_SECOND_ORDER 64
 #define CH_NL_MAX_OPS 64
