@@ -307,7 +307,8 @@ def main() -> None:
         traffic = per_unit * per_rank * args.particles
         traffic_note = "ncu dram bytes at 256 settings, scaled per (particle, setting)"
     roofline = {
-        "kernel": "apply_maps_kernel<float,4,256,true> (ch_apply_maps)",
+        "kernel": "apply_maps_kernel<float, 4, 256, UNIT7=1, MOMENTS=0, WRITE=1, CAVITY=0> "
+                  "(ch_apply_maps)",
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
