@@ -199,6 +199,21 @@ SIGNATURES = {
             c_void_p, c_void_p, c_void_p,
         ],
     ),
+    "ch_sc_gather_kick_fused": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_int64, c_void_p, c_int64,
+            c_void_p, c_void_p,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int32,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32,
+            c_int32, c_int32, c_int32,
+            c_void_p, c_void_p,
+        ],
+    ),
 }
 
 MOMENTS = 20

@@ -638,6 +638,20 @@ struct Field4<double> {
   using type = double4;
 };
 
+// One z corner pair {E(i, j, k), E(i, j, k + 1)} of the paired field layout.  For float the pair
+// is one 32-byte sector and is fetched with ONE 256-bit load (LDG.E.256, sm_100+) instead of two
+// 128-bit ones: half the L1 wavefronts of the gather, which is bound by L1/L2 sector traffic.
+__device__ __forceinline__ void load_pair(const float4* pair, float4& lo, float4& hi) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y),
+                 "=f"(hi.z), "=f"(hi.w)
+               : "l"(pair));
+}
+__device__ __forceinline__ void load_pair(const double4* pair, double4& lo, double4& hi) {
+  lo = pair[0];
+  hi = pair[1];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 sc_field_kernel(const T* __restrict__ phi, const double* __restrict__ params, int nx, int ny,
@@ -673,17 +687,43 @@ sc_field_kernel(const T* __restrict__ phi, const double* __restrict__ params, in
 // ---------------------------------------------------------------------------------------
 // 7. gather + kick
 // ---------------------------------------------------------------------------------------
+// What the FUSED instantiation does on top of the kick, while the particles are in registers:
+//  * the linear section that follows the kick in the lattice (a skippable run without
+//    apertures): out = M . kicked, M = the 6x7 map of a ch_compose_maps record -- saves the
+//    separate ch_apply_maps pass (28 B read + 28 B written per particle);
+//  * the survival-weighted sums of the NEXT SpaceChargeKick (ch_sc_moments_and_params) on the
+//    outgoing coordinates, and, in the last CTA of a beam, its grid parameters -- saves the
+//    moments pass (32 B read per particle) and a launch.
 template <typename T>
+struct GatherFusion {
+  const T* records;       // null: no map
+  int64_t record_stride;  // 0: one record for all beams
+  const T* survival;      // weights of the fused moments (null: ones)
+  int64_t survival_stride;
+  double* next_stats;     // null: no fused moments
+  double* next_params;
+  GridInputs next_in;
+  int nnx, nny, nnz;
+};
+
+template <typename T, bool FUSED>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 3 : 1)
 sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_stride,
                       const typename Field4<T>::type* __restrict__ field,
                       const double* __restrict__ params, int64_t n_particles, int nx, int ny,
                       int nz, int bulk_in, int bulk_out, T* __restrict__ particles_out,
-                      T* __restrict__ forces_out) {
+                      T* __restrict__ forces_out, const GatherFusion<T> fusion) {
   constexpr int P = 4, THREADS = 256, TP = P * THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);
   __shared__ uint64_t bar;
+  __shared__ T map_s[FUSED ? 44 : 1];
+  __shared__ double partial[FUSED ? 8 : 1][8];
+  if constexpr (FUSED) {
+    if (fusion.records != nullptr && threadIdx.x < 42)
+      map_s[threadIdx.x] =
+          fusion.records[blockIdx.y * fusion.record_stride + CH_RECORD_HEADER + threadIdx.x];
+  }
   const int64_t b = blockIdx.y;
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
   const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
@@ -748,8 +788,8 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
         const int ix = min(max(base[0] + ox, 0), nx - 1);
         const int iy = min(max(base[1] + oy, 0), ny - 1);
         const F4* pair = grid + ((static_cast<int64_t>(ix) * ny + iy) * nz + cz) * 2;
-        lower[u][r] = pair[0];
-        upper[u][r] = from_first ? pair[0] : pair[1];
+        load_pair(pair, lower[u][r], upper[u][r]);
+        if (from_first) upper[u][r] = lower[u][r];
       }
     }
 #pragma unroll
@@ -767,6 +807,7 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
     }
   }
 
+  double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // fused moments of the outgoing particles
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     const int local = threadIdx.x + k * THREADS;
@@ -799,6 +840,39 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
     out[k][4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
     out[k][5] = static_cast<T>((gamma_new - gamma0) * inv_bg0);
     out[k][6] = p[6];
+    if constexpr (FUSED) {
+      if (fusion.records != nullptr) {  // particles @ tm.mT of the following linear section
+        T mapped[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          T acc = map_s[i * 7 + 6] * out[k][6];
+#pragma unroll
+          for (int j = 5; j >= 0; --j) acc = fma(map_s[i * 7 + j], out[k][j], acc);
+          mapped[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) out[k][i] = mapped[i];
+      }
+      if (fusion.next_stats != nullptr && local < count) {
+        // sums about the origin in fp64 (ch_sc_beam_moments uses a pilot particle; with fp64
+        // accumulators the origin is as good: relative error ~ 1e-16 (mean / sigma)^2)
+        const double wi = fusion.survival
+                              ? static_cast<double>(
+                                    fusion.survival[b * fusion.survival_stride + n0 + local])
+                              : 1.0;
+        const double dx = static_cast<double>(out[k][0]);
+        const double dy = static_cast<double>(out[k][2]);
+        const double dt = static_cast<double>(out[k][4]);
+        acc8[0] += wi;
+        acc8[1] = fma(wi, wi, acc8[1]);
+        acc8[2] = fma(wi, dx, acc8[2]);
+        acc8[3] = fma(wi, dy, acc8[3]);
+        acc8[4] = fma(wi, dt, acc8[4]);
+        acc8[5] = fma(wi * dx, dx, acc8[5]);
+        acc8[6] = fma(wi * dy, dy, acc8[6]);
+        acc8[7] = fma(wi * dt, dt, acc8[7]);
+      }
+    }
   }
   __syncthreads();  // everybody is done reading the input tile
 #pragma unroll
@@ -819,6 +893,36 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
   } else {
     __syncthreads();
     for (int i = threadIdx.x; i < count * 7; i += THREADS) dst[i] = tile[i];
+  }
+  if constexpr (FUSED) {
+    if (fusion.next_stats == nullptr) return;
+    double* stats = fusion.next_stats + b * CH_SC_STATS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double sum = warp_sum(acc8[k]);
+      if (lane == 0) partial[warp][k] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      double sum = 0.0;
+      for (int wi = 0; wi < 8; ++wi) sum += partial[wi][threadIdx.x];
+      atomicAdd(&stats[threadIdx.x], sum);
+    }
+    // last CTA of the beam: sums -> grid parameters of the next kick (as in sc_moments_kernel;
+    // stats[8..10], the pilot, stay 0 from the memset)
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      last = atomicAdd(&stats[11], 1.0) == static_cast<double>(gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+      double sums[CH_SC_STATS];
+      for (int i = 0; i < CH_SC_STATS; ++i) sums[i] = __ldcg(&stats[i]);
+      grid_params_for_beam<T>(sums, b, fusion.next_in, fusion.nnx, fusion.nny, fusion.nnz,
+                              fusion.next_params + b * CH_SC_PARAMS);
+    }
   }
 }
 
@@ -1200,6 +1304,34 @@ extern "C" int ch_sc_field(const void* phi, const double* params, int64_t n_beam
   return CH_OK;
 }
 
+namespace {
+template <typename T>
+int launch_gather(const void* particles_in, int64_t particle_stride, const void* field,
+                  const double* params, int64_t n_particles, int64_t n_beams, int nx, int ny,
+                  int nz, void* particles_out, void* forces_out,
+                  const ch::GatherFusion<T>* fusion, cudaStream_t s) {
+  using F4 = typename ch::Field4<T>::type;
+  dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(n_beams));
+  const int bulk_in = ch::bulk_compatible<T>(particles_in, n_particles, particle_stride);
+  const int bulk_out = ch::bulk_compatible<T>(particles_out, n_particles, n_particles * 7);
+  const size_t smem = 1024 * 7 * sizeof(T);
+  auto launch = [&](auto kernel, const ch::GatherFusion<T>& f) -> int {
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    kernel<<<grid, 256, smem, s>>>(static_cast<const T*>(particles_in), particle_stride,
+                                   static_cast<const F4*>(field), params, n_particles, nx, ny, nz,
+                                   bulk_in, bulk_out, static_cast<T*>(particles_out),
+                                   static_cast<T*>(forces_out), f);
+    return CH_OK;
+  };
+  const int status = fusion ? launch(ch::sc_gather_kick_kernel<T, true>, *fusion)
+                            : launch(ch::sc_gather_kick_kernel<T, false>, ch::GatherFusion<T>{});
+  if (status != CH_OK) return status;
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+}  // namespace
+
 extern "C" int ch_sc_gather_kick(const void* particles_in, int64_t particle_stride,
                                  const void* field, const double* params, int64_t n_particles,
                                  int64_t n_beams, int32_t nx, int32_t ny, int32_t nz,
@@ -1210,26 +1342,55 @@ extern "C" int ch_sc_gather_kick(const void* particles_in, int64_t particle_stri
              "ch_sc_gather_kick: bad arguments");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_gather_kick: bad grid (%d, %d, %d)", nx, ny, nz);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(n_beams));
-  if (dtype == CH_F32) {
-    const int bulk_in = ch::bulk_compatible<float>(particles_in, n_particles, particle_stride);
-    const int bulk_out = ch::bulk_compatible<float>(particles_out, n_particles, n_particles * 7);
-    ch::sc_gather_kick_kernel<float><<<grid, 256, 1024 * 7 * sizeof(float), s>>>(
-        static_cast<const float*>(particles_in), particle_stride,
-        static_cast<const float4*>(field), params, n_particles, nx, ny, nz, bulk_in, bulk_out,
-        static_cast<float*>(particles_out), static_cast<float*>(forces_out));
-  } else {
-    const int bulk_in = ch::bulk_compatible<double>(particles_in, n_particles, particle_stride);
-    const int bulk_out = ch::bulk_compatible<double>(particles_out, n_particles, n_particles * 7);
-    auto kernel = ch::sc_gather_kick_kernel<double>;
-    const size_t smem = 1024 * 7 * sizeof(double);
-    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
-    kernel<<<grid, 256, smem, s>>>(static_cast<const double*>(particles_in), particle_stride,
-                                static_cast<const double4*>(field), params, n_particles, nx, ny,
-                                nz, bulk_in, bulk_out, static_cast<double*>(particles_out),
-                                static_cast<double*>(forces_out));
+  if (dtype == CH_F32)
+    return launch_gather<float>(particles_in, particle_stride, field, params, n_particles, n_beams,
+                                nx, ny, nz, particles_out, forces_out, nullptr, s);
+  return launch_gather<double>(particles_in, particle_stride, field, params, n_particles, n_beams,
+                               nx, ny, nz, particles_out, forces_out, nullptr, s);
+}
+
+extern "C" int ch_sc_gather_kick_fused(
+    const void* particles_in, int64_t particle_stride, const void* field, const double* params,
+    int64_t n_particles, int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+    const void* records, int64_t record_stride, const void* survival, int64_t survival_stride,
+    double* next_stats, double* next_params, const void* energy, int64_t energy_stride,
+    int32_t energy_dtype, const void* mass_eV, int32_t mass_dtype, const void* next_effect_length,
+    int64_t next_length_stride, int32_t next_length_dtype, const void* next_extent_x,
+    int64_t next_extent_x_stride, const void* next_extent_y, int64_t next_extent_y_stride,
+    const void* next_extent_tau, int64_t next_extent_tau_stride, int32_t next_extent_dtype,
+    int32_t next_nx, int32_t next_ny, int32_t next_nz, void* particles_out, void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_gather_kick_fused");
+  CH_REQUIRE(particles_in && field && params && particles_out && n_particles > 0,
+             "ch_sc_gather_kick_fused: bad arguments");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_gather_kick_fused: bad grid (%d, %d, %d)", nx, ny, nz);
+  CH_REQUIRE(records != nullptr || next_stats != nullptr,
+             "ch_sc_gather_kick_fused: nothing to fuse (use ch_sc_gather_kick)");
+  if (next_stats != nullptr) {
+    CH_REQUIRE(next_params && energy && mass_eV && next_effect_length && next_extent_x &&
+                   next_extent_y && next_extent_tau,
+               "ch_sc_gather_kick_fused: NULL pointer among the next kick's inputs");
+    CH_REQUIRE(ch::grid_ok(next_nx, next_ny, next_nz),
+               "ch_sc_gather_kick_fused: bad next grid (%d, %d, %d)", next_nx, next_ny, next_nz);
   }
-  CH_LAUNCH_CHECK();
-  return CH_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (next_stats != nullptr)
+    CH_CUDA(cudaMemsetAsync(next_stats, 0, sizeof(double) * CH_SC_STATS * n_beams, s));
+  const ch::GridInputs in{{energy, energy_stride, energy_dtype},
+                          {mass_eV, 0, mass_dtype},
+                          {next_effect_length, next_length_stride, next_length_dtype},
+                          {next_extent_x, next_extent_x_stride, next_extent_dtype},
+                          {next_extent_y, next_extent_y_stride, next_extent_dtype},
+                          {next_extent_tau, next_extent_tau_stride, next_extent_dtype}};
+  if (dtype == CH_F32) {
+    const ch::GatherFusion<float> f{static_cast<const float*>(records), record_stride,
+                                    static_cast<const float*>(survival), survival_stride,
+                                    next_stats, next_params, in, next_nx, next_ny, next_nz};
+    return launch_gather<float>(particles_in, particle_stride, field, params, n_particles, n_beams,
+                                nx, ny, nz, particles_out, nullptr, &f, s);
+  }
+  const ch::GatherFusion<double> f{static_cast<const double*>(records), record_stride,
+                                   static_cast<const double*>(survival), survival_stride,
+                                   next_stats, next_params, in, next_nx, next_ny, next_nz};
+  return launch_gather<double>(particles_in, particle_stride, field, params, n_particles, n_beams,
+                               nx, ny, nz, particles_out, nullptr, &f, s);
 }

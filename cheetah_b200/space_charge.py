@@ -32,8 +32,24 @@ def _scalar_ref(tensor: torch.Tensor, vector_shape: tuple, dtype) -> tuple:
     return tensor, min(stride, 1)
 
 
+class Prepared:
+    """Grid parameters of a kick that the PREVIOUS kick's fused gather kernel already computed
+    (``ch_sc_gather_kick_fused``): the kick can skip its moments pass."""
+
+    def __init__(self, workspace, slot: int, element) -> None:
+        self.workspace, self.slot, self.element = workspace, slot, element
+
+
 class Workspace:
     """Scratch buffers of one kick (torch's caching allocator makes re-allocation cheap)."""
+
+    @property
+    def stats(self) -> torch.Tensor:
+        return self.stats_slots[self.slot]
+
+    @property
+    def params(self) -> torch.Tensor:
+        return self.params_slots[self.slot]
 
     def charge_grid(self) -> torch.Tensor:
         """Deposited charge per cell [B, nx, ny, nz] (merges the split rows)."""
@@ -44,8 +60,17 @@ class Workspace:
         nx, ny, nz = grid_shape
         cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
         spectrum = (n_beams, 2 * nx, 2 * ny, nz + 1)
-        self.stats = torch.empty((n_beams, _capi.SC_STATS), dtype=torch.float64, device=device)
-        self.params = torch.empty((n_beams, _capi.SC_PARAMS), dtype=torch.float64, device=device)
+        # two slots: the fused gather kernel of kick k writes the sums / grid parameters of kick
+        # k + 1 while it is still reading those of kick k
+        self.stats_slots = [
+            torch.empty((n_beams, _capi.SC_STATS), dtype=torch.float64, device=device)
+            for _ in range(2)
+        ]
+        self.params_slots = [
+            torch.empty((n_beams, _capi.SC_PARAMS), dtype=torch.float64, device=device)
+            for _ in range(2)
+        ]
+        self.slot = 0
         # split rows [.., 2, nz + 2] (see ch_sc_deposit); `charge_grid()` merges them
         self.rho_split = torch.empty((n_beams, nx, ny, 2, nz + 2), dtype=dtype, device=device)
         self.lattice = torch.empty(
@@ -87,8 +112,14 @@ def _workspace(n_beams: int, grid_shape: tuple, dtype, device) -> Workspace:
 
 
 def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, grid_shape,
-         want_intermediates: bool = False):
-    """Run one kick on already-broadcast inputs; returns (particles_out [B,N,7], workspace)."""
+         want_intermediates: bool = False, prepared: Prepared | None = None, element=None,
+         fuse_records=None, next_element=None):
+    """Run one kick on already-broadcast inputs; returns (particles_out [B,N,7], workspace).
+
+    ``prepared``: the grid parameters were computed by the previous kick (skip the moments pass).
+    ``fuse_records`` (``[1 or B, record_len]`` compose records): apply that linear map to the
+    kicked particles in the same pass.  ``next_element``: also compute the moments and grid
+    parameters of that following SpaceChargeKick; ``workspace.prepared_next`` is then set."""
     device, dtype = particles.device, particles.dtype
     lib = _capi.lib()
     code = _capi.dtype_code(dtype)
@@ -118,15 +149,23 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
     out = torch.empty((n_beams, n, 7), dtype=dtype, device=device)
     forces = torch.empty((n_beams, n, 3), dtype=dtype, device=device) if want_intermediates else None
     stream = _capi.current_stream(device)
+    ws.prepared_next = None
+    reuse = (
+        prepared is not None and prepared.workspace is ws and prepared.element is element
+        and element is not None
+    )
     with torch.cuda.device(device):
-        _capi.check(lib.ch_sc_moments_and_params(
-            p.data_ptr(), p_stride, w.data_ptr(), w_stride, n, n_beams,
-            e.data_ptr(), e_stride, _capi.dtype_code(e.dtype),
-            mass.data_ptr(), _capi.dtype_code(mass.dtype),
-            length.data_ptr(), l_stride, _capi.dtype_code(length.dtype),
-            ext[0][0].data_ptr(), ext[0][1], ext[1][0].data_ptr(), ext[1][1],
-            ext[2][0].data_ptr(), ext[2][1], code,
-            nx, ny, nz, code, ws.stats.data_ptr(), ws.params.data_ptr(), stream))
+        if reuse:
+            ws.slot = prepared.slot
+        else:
+            _capi.check(lib.ch_sc_moments_and_params(
+                p.data_ptr(), p_stride, w.data_ptr(), w_stride, n, n_beams,
+                e.data_ptr(), e_stride, _capi.dtype_code(e.dtype),
+                mass.data_ptr(), _capi.dtype_code(mass.dtype),
+                length.data_ptr(), l_stride, _capi.dtype_code(length.dtype),
+                ext[0][0].data_ptr(), ext[0][1], ext[1][0].data_ptr(), ext[1][1],
+                ext[2][0].data_ptr(), ext[2][1], code,
+                nx, ny, nz, code, ws.stats.data_ptr(), ws.params.data_ptr(), stream))
         # the Green-function chain only needs the grid parameters: it runs on a side stream
         # concurrently with the deposit and the first two FFT passes of the charge
         main = torch.cuda.current_stream(device)
@@ -156,15 +195,64 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
         _capi.check(lib.ch_sc_field(
             ws.phi.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
             ws.field.data_ptr(), stream))
-        _capi.check(lib.ch_sc_gather_kick(
-            p.data_ptr(), p_stride, ws.field.data_ptr(), ws.params.data_ptr(), n, n_beams,
-            nx, ny, nz, code, out.data_ptr(), _capi.ptr(forces), stream))
+        if fuse_records is None and next_element is None:
+            _capi.check(lib.ch_sc_gather_kick(
+                p.data_ptr(), p_stride, ws.field.data_ptr(), ws.params.data_ptr(), n, n_beams,
+                nx, ny, nz, code, out.data_ptr(), _capi.ptr(forces), stream))
+        else:
+            nxt = None
+            next_slot = 1 - ws.slot
+            if next_element is not None:
+                nlen, nl_stride = _scalar_ref(next_element.effect_length, vector_shape, dtype)
+                next = [
+                    _scalar_ref(x, vector_shape, dtype)
+                    for x in (next_element.grid_extent_x, next_element.grid_extent_y,
+                              next_element.grid_extent_tau)
+                ]
+                nxt = (nlen, nl_stride, next)
+            record_stride = 0
+            if fuse_records is not None and fuse_records.shape[0] > 1:
+                record_stride = fuse_records.shape[1]
+            _capi.check(lib.ch_sc_gather_kick_fused(
+                p.data_ptr(), p_stride, ws.field.data_ptr(), ws.params.data_ptr(), n, n_beams,
+                nx, ny, nz, code,
+                _capi.ptr(fuse_records), record_stride, w.data_ptr(), w_stride,
+                ws.stats_slots[next_slot].data_ptr() if nxt else None,
+                ws.params_slots[next_slot].data_ptr() if nxt else None,
+                e.data_ptr(), e_stride, _capi.dtype_code(e.dtype),
+                mass.data_ptr(), _capi.dtype_code(mass.dtype),
+                nxt[0].data_ptr() if nxt else None, nxt[1] if nxt else 0,
+                _capi.dtype_code(nxt[0].dtype) if nxt else code,
+                nxt[2][0][0].data_ptr() if nxt else None, nxt[2][0][1] if nxt else 0,
+                nxt[2][1][0].data_ptr() if nxt else None, nxt[2][1][1] if nxt else 0,
+                nxt[2][2][0].data_ptr() if nxt else None, nxt[2][2][1] if nxt else 0, code,
+                nx, ny, nz, out.data_ptr(), stream))
+            if nxt is not None:
+                ws.prepared_next = Prepared(ws, next_slot, next_element)
     ws.forces = forces
     return out.reshape(*vector_shape, n, 7), ws
 
 
+def kick_vector_shape(element, incoming) -> tuple:
+    """Vector shape one kick works on (space_charge_kick.py:493-528, without the (1,) helper)."""
+    return tuple(torch.broadcast_shapes(
+        incoming.particles.shape[:-2], incoming.energy.shape,
+        incoming.particle_charges.shape[:-1], incoming.survival_probabilities.shape[:-1],
+        element.effect_length.shape, element.grid_extent_x.shape, element.grid_extent_y.shape,
+        element.grid_extent_tau.shape,
+    ))
+
+
 def track(element, incoming):
     """``SpaceChargeKick.track`` (space_charge_kick.py:477-586)."""
+    return track_fused(element, incoming)[0]
+
+
+def track_fused(element, incoming, prepared: Prepared | None = None, fuse_records=None,
+                next_element=None):
+    """``SpaceChargeKick.track`` plus, optionally, the linear map of the following section and
+    the moments of the following kick in the same particle pass.  Returns (beam, Prepared|None);
+    the caller adds the section length to ``s`` when it passed ``fuse_records``."""
     assert type(incoming).__name__ == "ParticleBeam", (
         "SpaceChargeKick tracking is currently only supported for `ParticleBeam`."
     )
@@ -178,11 +266,12 @@ def track(element, incoming):
                 f"{name} of element {element.name!r} lives on {tensor.device} but the beam is on "
                 f"{particles.device}; move the lattice with `segment.to(device)` first"
             )
-    out, _ = kick(
+    out, ws = kick(
         particles, incoming.energy, incoming.particle_charges, incoming.survival_probabilities,
         incoming.species.mass_eV, element.effect_length,
         (element.grid_extent_x, element.grid_extent_y, element.grid_extent_tau),
-        element.grid_shape,
+        element.grid_shape, prepared=prepared, element=element, fuse_records=fuse_records,
+        next_element=next_element,
     )
     # the reference drops the (1,) helper dimension again when nothing is vectorised
     out_shape = torch.broadcast_shapes(
@@ -200,7 +289,7 @@ def track(element, incoming):
         outgoing._unit_seventh = getattr(incoming, "_unit_seventh", None)
     except Exception:
         pass
-    return outgoing
+    return outgoing, ws.prepared_next
 
 
 def cloud_in_cell_charge_deposition(positions, bins, extent=None, charges=None):

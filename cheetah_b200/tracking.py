@@ -329,6 +329,62 @@ def _track_nonlinear_run(program, run, beam):
     return outgoing
 
 
+# Set to False to run every stage as its own pass (tests compare the two paths).
+fuse_space_charge = True
+
+
+def _track_space_charge(program, stages: list, i: int, beam, prepared):
+    """SpaceChargeKick stage ``i`` with its neighbours fused into the gather pass when the lattice
+    allows it: the following linear section (skippable run, no apertures / cavity, one map per
+    beam) and the moments of the kick after that.  Returns (beam, prepared, stages consumed)."""
+    from . import space_charge
+
+    element = stages[i].element
+    section = records = next_element = None
+    if fuse_space_charge and type(beam).__name__ == "ParticleBeam":
+        vs = space_charge.kick_vector_shape(element, beam)
+        j = i + 1
+        if j < len(stages) and isinstance(stages[j], lowering.LinearSection):
+            candidate = stages[j]
+            vm = tuple(torch.broadcast_shapes(candidate.lattice_shape, beam.energy.shape))
+            if (candidate.has_maps and candidate.n_apertures == 0 and candidate.cavity is None
+                    and (math.prod(vm) == 1 or vm == vs)):
+                section = candidate
+                j += 1
+            else:
+                j = len(stages)  # the next kick sees particles we do not produce here
+        if j < len(stages) and isinstance(stages[j], lowering.Barrier) \
+                and stages[j].kind == "space_charge":
+            candidate = stages[j].element
+            shapes = [candidate.effect_length.shape, candidate.grid_extent_x.shape,
+                      candidate.grid_extent_y.shape, candidate.grid_extent_tau.shape]
+            if (tuple(candidate.grid_shape) == tuple(element.grid_shape)
+                    and tuple(torch.broadcast_shapes(vs, *shapes)) == vs
+                    and all(t.device == beam.particles.device for t in (
+                        candidate.effect_length, candidate.grid_extent_x,
+                        candidate.grid_extent_y, candidate.grid_extent_tau))):
+                next_element = candidate
+    new_s = None
+    if section is not None:
+        records, vm = _compose(program, section, beam.energy, beam.species, beam.particles.dtype)
+        new_s = beam.s + _section_length(records, vm, section.length_shape)
+    outgoing, prepared = space_charge.track_fused(
+        element, beam, prepared=prepared, fuse_records=records, next_element=next_element
+    )
+    if section is not None:
+        fused = outgoing.__class__(
+            outgoing.particles, outgoing.energy, particle_charges=outgoing.particle_charges,
+            survival_probabilities=outgoing.survival_probabilities, s=new_s,
+            species=outgoing.species.clone(),
+        )
+        try:
+            fused._unit_seventh = getattr(outgoing, "_unit_seventh", None)
+        except Exception:
+            pass
+        outgoing = fused
+    return outgoing, prepared, 1 if section is None else 2
+
+
 def _track_monitor(stage, beam):
     """Active BPM / Screen between two sections (bpm.py:77-86, screen.py:187-239)."""
     from . import diagnostics
@@ -474,15 +530,20 @@ def track(elements, incoming, cache_owner=None):
 
     program = _plan(elements, incoming.particles.device, tuple(incoming.energy.shape), cache_owner)
     beam = incoming
-    for stage in program.stages:
+    stages = program.stages
+    prepared = None  # grid parameters a kick already computed for the kick that follows it
+    i = 0
+    while i < len(stages):
+        stage = stages[i]
+        if isinstance(stage, lowering.Barrier) and stage.kind == "space_charge":
+            beam, prepared, consumed = _track_space_charge(program, stages, i, beam, prepared)
+            i += consumed
+            continue
+        prepared = None
         if isinstance(stage, lowering.LinearSection):
             beam = _track_linear_section(program, stage, beam)
         elif isinstance(stage, lowering.NonlinearRun):
             beam = _track_nonlinear_run(program, stage, beam)
-        elif stage.kind == "space_charge":
-            from . import space_charge
-
-            beam = space_charge.track(stage.element, beam)
         elif stage.kind in ("bpm", "screen"):
             beam = _track_monitor(stage, beam)
         else:
@@ -492,6 +553,7 @@ def track(elements, incoming, cache_owner=None):
                 f"{getattr(stage.element, 'tracking_method', None)!r}) is outside the accelerated "
                 "hot path of this build (SURVEY.md 8f)"
             )
+        i += 1
     if beam is incoming:  # empty lattice: still hand back a new beam object
         beam = incoming.__class__(
             incoming.particles, incoming.energy, particle_charges=incoming.particle_charges,

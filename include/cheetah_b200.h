@@ -395,6 +395,34 @@ int ch_sc_gather_kick(const void* particles_in, int64_t particle_stride,
                       int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                       void* particles_out, void* forces_out, void* stream);
 
+/* ch_sc_gather_kick with the neighbouring stages of the lattice fused in, while the particles are
+ * in registers (both parts optional, at least one must be given):
+ *  - records != NULL: the linear section that FOLLOWS the kick (a skippable run without apertures
+ *    or cavities): particles_out = M . kicked, M the 6x7 map of the ch_compose_maps record
+ *    records[b * record_stride] (stride 0 = one map for all beams).  Replaces one ch_apply_maps
+ *    pass (cheetah/accelerator/element.py:181-191).
+ *  - next_stats != NULL: the survival-weighted sums (about the origin) of the NEXT
+ *    SpaceChargeKick on the outgoing coordinates and, from the last CTA of each beam, its grid
+ *    parameters next_params -- what ch_sc_moments_and_params would compute in a separate pass
+ *    (space_charge_kick.py:531-550).  next_* describe that next kick; energy / mass as there.    */
+int ch_sc_gather_kick_fused(const void* particles_in, int64_t particle_stride,
+                            const void* field, const double* params,
+                            int64_t n_particles, int64_t n_beams,
+                            int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                            const void* records, int64_t record_stride,
+                            const void* survival, int64_t survival_stride,
+                            double* next_stats, double* next_params,
+                            const void* energy, int64_t energy_stride, int32_t energy_dtype,
+                            const void* mass_eV, int32_t mass_dtype,
+                            const void* next_effect_length, int64_t next_length_stride,
+                            int32_t next_length_dtype,
+                            const void* next_extent_x, int64_t next_extent_x_stride,
+                            const void* next_extent_y, int64_t next_extent_y_stride,
+                            const void* next_extent_tau, int64_t next_extent_tau_stride,
+                            int32_t next_extent_dtype,
+                            int32_t next_nx, int32_t next_ny, int32_t next_nz,
+                            void* particles_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

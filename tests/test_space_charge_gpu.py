@@ -192,3 +192,70 @@ def test_cloud_in_cell_matches_reference_and_histogram(dtype):
     outside = torch.tensor([[0.0, 1.0, 0.0], [5.0, 1.0, 0.0], [0.0, -1.0, 0.0], [0.5, 0.5, 1.0]], dtype=dtype)
     grid = cloud_in_cell_charge_deposition(outside.to(DEVICE), bins, extent.to(DEVICE))
     assert float(grid.sum()) == 2.0
+
+
+# ---- fused stages: kick + following linear section + moments of the next kick ------------------
+def _fodo_with_kicks(dtype, vector_k1=None, aperture=False, grid=(16, 16, 16)):
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE, dtype=dtype)  # noqa: E731
+    elements = []
+    for cell in range(2):
+        for sign in (1.0, -1.0):
+            k1 = t(sign * 4.2) if vector_k1 is None else t([sign * k for k in vector_k1])
+            elements += [
+                cb.Quadrupole(length=t(0.2), k1=k1),
+                cb.Drift(length=t(0.5)),
+                cb.SpaceChargeKick(effect_length=t(1.0), grid_shape=grid),
+                cb.Drift(length=t(0.5)),
+            ]
+            if aperture and sign > 0:
+                elements.append(cb.Aperture(x_max=t(5e-4), y_max=t(5e-4)))
+    return cb.Segment(elements)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", ["plain", "vector_beams", "vector_lattice", "aperture"])
+def test_fused_kick_pipeline_equals_the_stage_by_stage_one(case, dtype):
+    """ch_sc_gather_kick_fused (kick + next linear map + next kick's moments in one pass) against
+    the unfused stage sequence.  The only arithmetic difference is the reference point of the
+    moment sums (origin instead of a pilot particle), i.e. rounding of sigma."""
+    import cheetah_b200 as cb
+    from cheetah_b200 import _capi, tracking
+
+    torch.manual_seed(9)
+    kwargs = {}
+    if case in ("vector_beams", "vector_lattice"):
+        kwargs["total_charge"] = torch.tensor([1e-10, 3e-10, 5e-10])
+    beam = cb.ParticleBeam.from_parameters(
+        num_particles=20_000, energy=torch.tensor(5e7), device=DEVICE, dtype=dtype, **kwargs
+    )
+    if case == "vector_beams":  # per-beam particles
+        scale = torch.tensor([1.0, 1.1, 0.9], device=DEVICE, dtype=dtype).reshape(3, 1, 1)
+        particles = beam.particles.unsqueeze(0) * scale
+        particles[..., 6] = 1.0
+        beam = cb.ParticleBeam(particles, beam.energy, particle_charges=beam.particle_charges,
+                               species=beam.species)
+    segment = _fodo_with_kicks(
+        dtype, vector_k1=[4.2, 3.0, 5.0] if case == "vector_lattice" else None,
+        aperture=case == "aperture",
+    )
+    launches = []
+    results = []
+    for fuse in (False, True):
+        tracking.fuse_space_charge = fuse
+        try:
+            before = _capi.launch_count()
+            results.append(segment.track(beam))
+            torch.cuda.synchronize()
+            launches.append(_capi.launch_count() - before)
+        finally:
+            tracking.fuse_space_charge = True
+    unfused, fused = results
+    assert fused.particles.shape == unfused.particles.shape
+    assert launches[1] < launches[0]  # fewer passes over the particles
+    tol = 1e-9 if dtype == torch.float64 else 5e-5
+    scale = unfused.particles.abs().amax(dim=-2, keepdim=True).clamp_min(1e-30)
+    assert float(((fused.particles - unfused.particles).abs() / scale).max()) < tol
+    assert torch.equal(fused.survival_probabilities, unfused.survival_probabilities)
+    assert torch.allclose(fused.s, unfused.s)
