@@ -97,6 +97,18 @@ SIGNATURES = {
             c_int32, c_int32, c_void_p,
         ],
     ),
+    "ch_apply_maps_covariance": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_int64, c_int32, c_uint32,
+            c_int64, c_int64,
+            c_void_p, c_void_p, c_void_p,
+            c_int32, c_int32, c_void_p,
+        ],
+    ),
     "ch_nonlinear_constants_len": (c_int64, [c_void_p, c_int32, c_int32]),
     "ch_nonlinear_constants": (
         c_int32,
@@ -217,6 +229,7 @@ SIGNATURES = {
 }
 
 MOMENTS = 20
+MOMENTS_COV = 36
 SC_STATS = 12
 SC_PARAMS = 16
 

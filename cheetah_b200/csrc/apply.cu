@@ -46,6 +46,7 @@ struct ApplyArgs {
   int32_t bulk_out;  // particles_out tiles do
   double* moments_out;  // [n_settings][CH_MOMENTS] survival-weighted sums (MOMENTS kernels)
   int32_t has_cavity;   // the record ends with a CH_RECORD_CAVITY block
+  int32_t covariance;   // moments_out has CH_MOMENTS_COV entries per setting (full 6x6 sums)
 };
 
 template <typename T>
@@ -117,13 +118,14 @@ __device__ __forceinline__ bool inside(double v, double bound) { return fabs(v) 
 // the final map into the staging tile.  SPARSE drops the structurally-zero terms (flags).
 // With MOMENTS the outgoing coordinates are also accumulated into `acc` (see the kernel) about
 // `pilot`, the image of the beam's first particle under the same map.
-template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE, bool MOMENTS, bool WRITE,
+template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE, int MOMENTS, bool WRITE,
           bool CAVITY>
 __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
                                                 uint32_t elliptical_mask, const T (&p)[P][7],
                                                 T (&sv)[P], T* stage, int tid,
                                                 const T (&first_particle)[7], T (&pilot)[6],
-                                                float (&acc)[16], const T* cavity) {
+                                                float (&acc)[MOMENTS == 2 ? 32 : 16],
+                                                const T* cavity) {
   for (int ap = 0; ap < n_apertures; ++ap) {
     T q[16];
     load_coefficients(q, rec + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
@@ -240,10 +242,24 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
       acc[0] += w;
       acc[1] = fmaf(w, w, acc[1]);
 #pragma unroll
+      float d[6];
+#pragma unroll
       for (int i = 0; i < 6; ++i) {
-        const float d = static_cast<float>(out[i] - pilot[i]);
-        acc[2 + i] = fmaf(w, d, acc[2 + i]);
-        acc[8 + i] = fmaf(w * d, d, acc[8 + i]);
+        d[i] = static_cast<float>(out[i] - pilot[i]);
+        acc[2 + i] = fmaf(w, d[i], acc[2 + i]);
+        acc[8 + i] = fmaf(w * d[i], d[i], acc[8 + i]);
+      }
+      if constexpr (MOMENTS == 2) {  // the 15 off-diagonal second moments, (0,1), (0,2), ... (4,5)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float wd = w * d[i];
+#pragma unroll
+          for (int j = i + 1; j < 6; ++j) {
+            constexpr int kBase = 14;
+            const int slot = kBase + i * (11 - i) / 2 + (j - i - 1);
+            acc[slot] = fmaf(wd, d[j], acc[slot]);
+          }
+        }
       }
     }
   }
@@ -269,8 +285,25 @@ __device__ __forceinline__ float packed_warp_sum(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <typename T, int P, int THREADS, bool UNIT7, bool MOMENTS, bool WRITE, bool CAVITY>
-__global__ void __launch_bounds__(THREADS, sizeof(T) == 4 ? 3 : 1)
+// Same for 32 per-lane values (5 rounds, 31 shuffles): afterwards lane L holds the warp total of
+// value index L.
+__device__ __forceinline__ float packed_warp_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int round = 0; round < 5; ++round) {
+    const int offset = 16 >> round;  // 16, 8, 4, 2, 1 = number of values kept
+    const bool upper = (lane & offset) != 0;
+#pragma unroll
+    for (int i = 0; i < offset; ++i) {
+      const float send = upper ? v[i] : v[i + offset];
+      const float mine = upper ? v[i + offset] : v[i];
+      v[i] = mine + __shfl_xor_sync(0xffffffffu, send, offset);
+    }
+  }
+  return v[0];
+}
+
+template <typename T, int P, int THREADS, bool UNIT7, int MOMENTS, bool WRITE, bool CAVITY>
+__global__ void __launch_bounds__(THREADS, sizeof(T) == 4 ? (MOMENTS == 2 ? 2 : 3) : 1)
 apply_maps_kernel(const ApplyArgs<T> a) {
   constexpr int TP = P * THREADS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -303,16 +336,20 @@ apply_maps_kernel(const ApplyArgs<T> a) {
   // about a per-setting pilot (the image of particle 0), so that mu / sigma never need the
   // (B, N, 7) array in HBM (ParticleBeam.mu_* / sigma_*,
   // cheetah/particles/particle_beam.py:1699-1805, cheetah/utils/statistics.py:30-62)
-  __shared__ float partial[2][THREADS / 32][16];
+  constexpr int NACC = MOMENTS == 2 ? 32 : 16;           // per-lane accumulators
+  constexpr int NSUM = MOMENTS == 2 ? 29 : 14;           // of which are sums
+  constexpr int NOUT = MOMENTS == 2 ? CH_MOMENTS_COV : CH_MOMENTS;
+  __shared__ float partial[2][THREADS / 32][NACC];
   __shared__ T pilot_shared[2][8];
-  auto flush_moments = [&](int buf, int64_t b) {  // threads 0..19 after a barrier
-    if (tid < 14) {
+  auto flush_moments = [&](int buf, int64_t b) {  // threads 0..34 after a barrier
+    if (tid < NSUM) {
       double total = 0.0;
 #pragma unroll
       for (int wi = 0; wi < THREADS / 32; ++wi) total += static_cast<double>(partial[buf][wi][tid]);
-      atomicAdd(&a.moments_out[b * CH_MOMENTS + tid], total);
-    } else if (tid < 20 && blockIdx.x == 0) {
-      a.moments_out[b * CH_MOMENTS + tid] = static_cast<double>(pilot_shared[buf][tid - 14]);
+      // sums 0..13 keep their place, the pilot sits at 14..19, the off-diagonal sums follow
+      atomicAdd(&a.moments_out[b * NOUT + (tid < 14 ? tid : tid + 6)], total);
+    } else if (tid >= 32 && tid < 38 && blockIdx.x == 0) {
+      a.moments_out[b * NOUT + 14 + (tid - 32)] = static_cast<double>(pilot_shared[buf][tid - 32]);
     }
   };
 
@@ -405,9 +442,9 @@ apply_maps_kernel(const ApplyArgs<T> a) {
     constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
                                  CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
     T pilot[6];
-    float acc[16];
+    float acc[NACC];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
     if (MOMENTS) {  // lanes past the end of the beam must not count
 #pragma unroll
       for (int k = 0; k < P; ++k)
@@ -434,7 +471,9 @@ apply_maps_kernel(const ApplyArgs<T> a) {
       // the top of the next iteration
       const int lane = tid & 31;
       const float total = packed_warp_sum(acc, lane);
-      if ((lane & 1) == 0) {
+      if constexpr (MOMENTS == 2) {
+        partial[it & 1][tid >> 5][lane] = total;
+      } else if ((lane & 1) == 0) {
         const int index = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
                           ((lane >> 1) & 1);
         partial[it & 1][tid >> 5][index] = total;
@@ -488,11 +527,18 @@ int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t strea
     return args.has_cavity ? pick(unit, moments, write, std::true_type{})
                            : pick(unit, moments, write, std::false_type{});
   };
+  using M0 = std::integral_constant<int, 0>;
+  using M1 = std::integral_constant<int, 1>;
+  using M2 = std::integral_constant<int, 2>;
   auto with_outputs = [&](auto unit) -> int {
+    if (args.moments_out != nullptr && args.covariance) {
+      if (args.particles_out == nullptr) return with_cavity(unit, M2{}, std::false_type{});
+      return with_cavity(unit, M2{}, std::true_type{});
+    }
     if (args.moments_out != nullptr && args.particles_out == nullptr)
-      return with_cavity(unit, std::true_type{}, std::false_type{});
-    if (args.moments_out != nullptr) return with_cavity(unit, std::true_type{}, std::true_type{});
-    return with_cavity(unit, std::false_type{}, std::true_type{});
+      return with_cavity(unit, M1{}, std::false_type{});
+    if (args.moments_out != nullptr) return with_cavity(unit, M1{}, std::true_type{});
+    return with_cavity(unit, M0{}, std::true_type{});
   };
   const int status =
       unit_seventh ? with_outputs(std::true_type{}) : with_outputs(std::false_type{});
@@ -507,9 +553,11 @@ int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t
                 const void* records, int64_t record_stride, const int32_t* record_index,
                 int64_t record_len, int32_t n_apertures, uint32_t elliptical_mask,
                 int64_t n_particles, int64_t n_settings, void* particles_out, void* survival_out,
-                int32_t unit_seventh, double* moments_out, cudaStream_t stream) {
+                int32_t unit_seventh, double* moments_out, int32_t covariance,
+                cudaStream_t stream) {
   ApplyArgs<T> a;
   a.moments_out = moments_out;
+  a.covariance = covariance;
   a.particles_in = static_cast<const T*>(particles_in);
   a.survival_in = static_cast<const T*>(survival_in);
   a.records = static_cast<const T*>(records);
@@ -558,7 +606,7 @@ int apply_dispatch(const void* particles_in, int64_t particle_stride,
                    int64_t record_stride, const int32_t* record_index, int64_t record_len,
                    int32_t n_apertures, uint32_t elliptical_mask, int64_t n_particles,
                    int64_t n_settings, void* particles_out, void* survival_out, int32_t dtype,
-                   int32_t unit_seventh, double* moments_out, void* stream) {
+                   int32_t unit_seventh, double* moments_out, int32_t covariance, void* stream) {
   CH_REQUIRE(particles_in && records, "ch_apply_maps: NULL pointer argument");
   CH_REQUIRE(particles_out || moments_out, "ch_apply_maps: no output requested");
   CH_REQUIRE(n_particles > 0 && n_settings > 0, "ch_apply_maps: empty beam or batch");
@@ -573,18 +621,20 @@ int apply_dispatch(const void* particles_in, int64_t particle_stride,
   CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, "ch_apply_maps: bad dtype %d", dtype);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (moments_out != nullptr)
-    CH_CUDA(cudaMemsetAsync(moments_out, 0, sizeof(double) * CH_MOMENTS * n_settings, s));
+    CH_CUDA(cudaMemsetAsync(moments_out, 0,
+                            sizeof(double) * (covariance ? CH_MOMENTS_COV : CH_MOMENTS) * n_settings,
+                            s));
   if (dtype == CH_F32)
     return ch::apply_typed<float>(particles_in, particle_stride, particle_index, survival_in,
                                   survival_stride, survival_index, records, record_stride,
                                   record_index, record_len, n_apertures, elliptical_mask,
                                   n_particles, n_settings, particles_out, survival_out,
-                                  unit_seventh, moments_out, s);
+                                  unit_seventh, moments_out, covariance, s);
   return ch::apply_typed<double>(particles_in, particle_stride, particle_index, survival_in,
                                  survival_stride, survival_index, records, record_stride,
                                  record_index, record_len, n_apertures, elliptical_mask,
                                  n_particles, n_settings, particles_out, survival_out,
-                                 unit_seventh, moments_out, s);
+                                 unit_seventh, moments_out, covariance, s);
 }
 }  // namespace
 
@@ -600,7 +650,7 @@ extern "C" int ch_apply_maps(const void* particles_in, int64_t particle_stride,
   return apply_dispatch(particles_in, particle_stride, particle_index, survival_in,
                         survival_stride, survival_index, records, record_stride, record_index,
                         record_len, n_apertures, elliptical_mask, n_particles, n_settings,
-                        particles_out, survival_out, dtype, unit_seventh, nullptr, stream);
+                        particles_out, survival_out, dtype, unit_seventh, nullptr, 0, stream);
 }
 
 extern "C" int ch_apply_maps_moments(const void* particles_in, int64_t particle_stride,
@@ -616,5 +666,22 @@ extern "C" int ch_apply_maps_moments(const void* particles_in, int64_t particle_
   return apply_dispatch(particles_in, particle_stride, particle_index, survival_in,
                         survival_stride, survival_index, records, record_stride, record_index,
                         record_len, n_apertures, elliptical_mask, n_particles, n_settings,
-                        particles_out, survival_out, dtype, unit_seventh, moments_out, stream);
+                        particles_out, survival_out, dtype, unit_seventh, moments_out, 0, stream);
+}
+
+extern "C" int ch_apply_maps_covariance(const void* particles_in, int64_t particle_stride,
+                                        const int32_t* particle_index, const void* survival_in,
+                                        int64_t survival_stride, const int32_t* survival_index,
+                                        const void* records, int64_t record_stride,
+                                        const int32_t* record_index, int64_t record_len,
+                                        int32_t n_apertures, uint32_t elliptical_mask,
+                                        int64_t n_particles, int64_t n_settings,
+                                        void* particles_out, void* survival_out,
+                                        double* moments_out, int32_t dtype, int32_t unit_seventh,
+                                        void* stream) {
+  CH_REQUIRE(moments_out != nullptr, "ch_apply_maps_covariance: moments_out is NULL");
+  return apply_dispatch(particles_in, particle_stride, particle_index, survival_in,
+                        survival_stride, survival_index, records, record_stride, record_index,
+                        record_len, n_apertures, elliptical_mask, n_particles, n_settings,
+                        particles_out, survival_out, dtype, unit_seventh, moments_out, 1, stream);
 }

@@ -582,11 +582,14 @@ class Segment(Element):
 
         return tracking.track(list(self.elements), incoming, cache_owner=self)
 
-    def track_moments(self, incoming: Beam, keep_particles: bool = False):
-        """Outgoing-beam moments from the fused kernel epilogue (tracking.track_moments)."""
+    def track_moments(self, incoming: Beam, keep_particles: bool = False,
+                      covariance: bool = False):
+        """Outgoing-beam moments from the fused kernel epilogue (tracking.track_moments);
+        ``covariance=True`` adds the full 6x6 covariance matrix (``BeamMoments.cov``)."""
         from . import tracking
 
-        return tracking.track_moments(list(self.elements), incoming, self, keep_particles)
+        return tracking.track_moments(list(self.elements), incoming, self, keep_particles,
+                                      covariance)
 
     def __repr__(self) -> str:
         return f"Segment(elements={list(self.elements)!r}, name={self.name!r})"

@@ -143,7 +143,8 @@ def _unit_seventh(beam) -> bool:
     return flag
 
 
-def _track_linear_section(program, section, beam, moments: str | None = None):
+def _track_linear_section(program, section, beam, moments: str | None = None,
+                          covariance: bool = False):
     """One ``ch_compose_maps`` + one ``ch_apply_maps`` for a ParticleBeam.
 
     ``moments``: None (particles only), "with" (particles + fused moments) or "only" (the
@@ -180,8 +181,9 @@ def _track_linear_section(program, section, beam, moments: str | None = None):
     record_index = _index_table(vm, vo, device)
     out = None if moments == "only" else torch.empty((*vo, n, 7), dtype=dtype, device=device)
     sums = None
+    n_sums = _capi.MOMENTS_COV if covariance else _capi.MOMENTS
     if moments is not None:
-        sums = torch.empty((n_out, _capi.MOMENTS), dtype=torch.float64, device=device)
+        sums = torch.empty((n_out, n_sums), dtype=torch.float64, device=device)
 
     survival_in = beam.survival_probabilities
     survival_out = None
@@ -226,6 +228,8 @@ def _track_linear_section(program, section, beam, moments: str | None = None):
     with torch.cuda.device(device):
         if moments is None:
             _capi.check(_capi.lib().ch_apply_maps(*common, *tail))
+        elif covariance:
+            _capi.check(_capi.lib().ch_apply_maps_covariance(*common, sums.data_ptr(), *tail))
         else:
             _capi.check(_capi.lib().ch_apply_maps_moments(*common, sums.data_ptr(), *tail))
     if events is not None:
@@ -234,7 +238,7 @@ def _track_linear_section(program, section, beam, moments: str | None = None):
 
     observed = None
     if sums is not None:
-        observed = BeamMoments.from_sums(sums.reshape(*vo, _capi.MOMENTS), new_energy, new_s, dtype)
+        observed = BeamMoments.from_sums(sums.reshape(*vo, n_sums), new_energy, new_s, dtype)
     if moments == "only":
         return None, observed
 
@@ -403,10 +407,12 @@ class BeamMoments:
 
     names = ("x", "px", "y", "py", "tau", "p")
 
-    def __init__(self, mu, sigma, num_particles_survived, energy, s) -> None:
+    def __init__(self, mu, sigma, num_particles_survived, energy, s, cov=None) -> None:
         self.mu, self.sigma = mu, sigma
         self.num_particles_survived = num_particles_survived
         self.energy, self.s = energy, s
+        # (..., 6, 6) unbiased weighted covariance matrix (statistics.py:65-88) when requested
+        self.cov = cov
 
     @classmethod
     def from_sums(cls, sums: torch.Tensor, energy, s, dtype) -> "BeamMoments":
@@ -416,7 +422,17 @@ class BeamMoments:
         centred = s2 - s1.square() / s0.unsqueeze(-1)
         correction = (s0 - sww / s0).unsqueeze(-1)
         sigma = (centred.clamp_min(0.0) / correction).sqrt()
-        return cls(mu.to(dtype), sigma.to(dtype), s0.to(dtype), energy, s)
+        cov = None
+        if sums.shape[-1] == _capi.MOMENTS_COV:
+            rows, cols = torch.triu_indices(6, 6, offset=1, device=sums.device)
+            second = torch.diag_embed(s2)
+            second[..., rows, cols] = sums[..., 20:35]
+            second[..., cols, rows] = sums[..., 20:35]
+            cov = (
+                second - s1.unsqueeze(-1) * s1.unsqueeze(-2) / s0[..., None, None]
+            ) / correction.unsqueeze(-1)
+            cov = cov.to(dtype)
+        return cls(mu.to(dtype), sigma.to(dtype), s0.to(dtype), energy, s, cov)
 
     def __getattr__(self, name: str):
         for prefix, source in (("mu_", "mu"), ("sigma_", "sigma")):
@@ -428,7 +444,8 @@ class BeamMoments:
         return f"BeamMoments(mu={self.mu!r}, sigma={self.sigma!r})"
 
 
-def track_moments(elements, incoming, cache_owner=None, keep_particles: bool = False):
+def track_moments(elements, incoming, cache_owner=None, keep_particles: bool = False,
+                  covariance: bool = False):
     """Track ``incoming`` and return the first/second moments of the outgoing beam.
 
     The last linear section of the lattice computes them in the kernel epilogue; with
@@ -460,7 +477,8 @@ def track_moments(elements, incoming, cache_owner=None, keep_particles: bool = F
                 f"cheetah_b200: element {stage.element.name!r} is outside the accelerated hot path"
             )
     outgoing, observed = _track_linear_section(
-        program, stages[-1], beam, moments="with" if keep_particles else "only"
+        program, stages[-1], beam, moments="with" if keep_particles else "only",
+        covariance=covariance,
     )
     return (outgoing, observed) if keep_particles else observed
 

@@ -267,6 +267,21 @@ int ch_screen_image(const void* particles, int64_t particle_stride,
                     int64_t n_particles, int64_t n_beams, int32_t dtype,
                     void* image, void* stream);
 
+/* ch_apply_maps_moments with the full second-moment matrix: moments_out[b] has CH_MOMENTS_COV
+ * doubles, the first CH_MOMENTS as above, then [20 + k] = sum w (u_i - c_i)(u_j - c_j) for the 15
+ * pairs i < j in the order (0,1), (0,2), ..., (0,5), (1,2), ..., (4,5), [35] unused.  With
+ * cov_ij = (S_ij - S1_i S1_j / S0) / (S0 - sum w^2 / S0) this is
+ * unbiased_weighted_covariance_matrix (cheetah/utils/statistics.py:65-88) of the outgoing beam,
+ * i.e. ParticleBeam.as_parameter_beam's cov and the cov_xpx / cov_ypy / cov_taup properties.   */
+#define CH_MOMENTS_COV 36
+int ch_apply_maps_covariance(const void* particles_in, int64_t particle_stride, const int32_t* particle_index,
+                             const void* survival_in, int64_t survival_stride, const int32_t* survival_index,
+                             const void* records, int64_t record_stride, const int32_t* record_index,
+                             int64_t record_len, int32_t n_apertures, uint32_t elliptical_mask,
+                             int64_t n_particles, int64_t n_settings,
+                             void* particles_out, void* survival_out, double* moments_out,
+                             int32_t dtype, int32_t unit_seventh, void* stream);
+
 /* space charge ----------------------------------------------------------------------- */
 /* One SpaceChargeKick (cheetah/accelerator/space_charge_kick.py:477-586) is the sequence
  *   ch_sc_beam_moments -> ch_sc_grid_params -> ch_sc_deposit -> ch_sc_green_function ->

@@ -63,3 +63,49 @@ def test_track_moments_without_apertures_and_single_setting():
     assert float(observed.num_particles_survived) == 50_001
     assert ((observed.mu.double() - mu).abs() / sigma).max() < 2e-5
     assert ((observed.sigma.double() - sigma).abs() / sigma).max() < 2e-5
+
+
+def reference_covariance(out):
+    """unbiased_weighted_covariance_matrix (cheetah/utils/statistics.py:65-88) in float64."""
+    w = out.survival_probabilities.double()
+    if w.dim() < out.particles.dim() - 1:
+        w = w.expand(out.particles.shape[:-1])
+    u = out.particles.double()[..., :6]
+    normalized = w / w.sum(dim=-1, keepdim=True)
+    correction = 1 - normalized.square().sum(dim=-1)
+    centred = u - (u * normalized.unsqueeze(-1)).sum(dim=-2, keepdim=True)
+    return (normalized.unsqueeze(-1) * centred).mT @ centred / correction[..., None, None]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("keep", [False, True])
+def test_track_moments_with_full_covariance(dtype, keep):
+    """ch_apply_maps_covariance: the 6x6 covariance of the outgoing beam from the kernel epilogue
+    (a tilted quadrupole couples x and y, the dipole adds dispersion)."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE, dtype=dtype)  # noqa: E731
+    segment = cb.Segment([
+        cb.Quadrupole(length=t(0.2), k1=t([3.0, -2.0, 0.5]), tilt=t(0.3)),
+        cb.Drift(length=t(1.0)),
+        cb.Dipole(length=t(0.5), angle=t(0.2)),
+        cb.Aperture(x_max=t(4e-4), y_max=t(6e-4), shape="elliptical"),
+        cb.Drift(length=t(0.7)),
+    ])
+    torch.manual_seed(2)
+    beam = cb.ParticleBeam.from_parameters(num_particles=200_003, device=DEVICE, dtype=dtype)
+    out = segment.track(beam)
+    expected = reference_covariance(out)
+    result = segment.track_moments(beam, keep_particles=keep, covariance=True)
+    observed = result[1] if keep else result
+    assert observed.cov.shape == (3, 6, 6) and observed.cov.dtype == dtype
+    sigma = expected.diagonal(dim1=-2, dim2=-1).sqrt()
+    scale = sigma.unsqueeze(-1) * sigma.unsqueeze(-2)
+    tol = 3e-5 if dtype == torch.float32 else 1e-6  # fp32 per-tile partial sums in both cases
+    assert float(((observed.cov.double().cpu() - expected.cpu()).abs() / scale.cpu()).max()) < tol
+    assert torch.allclose(observed.cov, observed.cov.mT)
+    assert torch.allclose(observed.cov.diagonal(dim1=-2, dim2=-1).sqrt(), observed.sigma, rtol=1e-5)
+    plain = segment.track_moments(beam)
+    assert plain.cov is None and torch.allclose(plain.sigma, observed.sigma, rtol=1e-6)
+    if keep:
+        assert torch.equal(result[0].particles, out.particles)
