@@ -414,6 +414,45 @@ def main() -> None:
         del tracker
         torch.cuda.empty_cache()
 
+    # ---- BASELINE configs[1]: same lattice, one setting (README magnet values), B = 1 -----------
+    config2 = None
+    if rank == 0 and world == 1 and not args.no_observables:
+        import cheetah_b200 as cb
+
+        segment2 = workloads.product_segment(workloads.ares_config2(dtype), device, dtype)
+        for _ in range(3):
+            segment2.track(beam)
+        torch.cuda.synchronize()
+        c_start, c_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        c_start.record()
+        for _ in range(reps):
+            segment2.track(beam)
+        c_stop.record()
+        torch.cuda.synchronize()
+        eager_ms = c_start.elapsed_time(c_stop) / reps
+        graphed = cb.GraphedTrack(segment2, beam)
+        for _ in range(3):
+            graphed.replay()
+        torch.cuda.synchronize()
+        c_start.record()
+        for _ in range(reps):
+            graphed.replay()
+        c_stop.record()
+        torch.cuda.synchronize()
+        graph_ms = c_start.elapsed_time(c_stop) / reps
+        config2 = {
+            "workload": f"ARES Segment ({N_ELEMENTS} elements), {args.particles} particles, ONE "
+                        "setting (README magnet values), linear maps -- BASELINE configs[1]; the "
+                        "64 MB working set is L2-resident and the call is launch-latency bound",
+            "ms_per_step": eager_ms,
+            "value": args.particles * N_ELEMENTS / (eager_ms * 1e-3),
+            "graph_ms_per_step": graph_ms,
+            "graph_value": args.particles * N_ELEMENTS / (graph_ms * 1e-3),
+            "unit": UNIT,
+            "achieved_gbs_graph": args.particles * 64 / (graph_ms * 1e-3) / 1e9,
+        }
+
     # ---- CPU baseline (rank 0, single-GPU runs only) --------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -439,6 +478,7 @@ def main() -> None:
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "observables": observables,
+            "config2": config2,
             "gpu_launches": launches,
             "clocks": clocks,
             "particle_tracks_per_s": args.settings * args.particles / (ms_per_step * 1e-3),

@@ -62,16 +62,23 @@ __device__ __forceinline__ void fill_twiddles(double2* tw, int len) {
   }
 }
 
+// Thread mapping of every stage: the COLUMN index runs fastest over the threads (COLS = 16 or
+// 8 columns per tile), so the lanes of a half-warp hold the same butterfly of different columns.
+// With an odd column pitch (len + 1 for 16 columns; len + 2 for 8 columns, where a half-warp
+// covers two neighbouring butterflies) their 64-bit shared-memory accesses fall into distinct
+// banks for every span, and the twiddle factor is a broadcast.  (Mapping consecutive threads to
+// consecutive butterflies of ONE column -- the textbook layout -- gives 2- to 4-way bank
+// conflicts for spans below 32: ncu showed the passes 95 % L1/shared-bound.)
+//
 // One radix-2 DIF stage of span 2^span_log on all columns (no barrier).
-template <typename C>
-__device__ __forceinline__ void dif_stage(C* v, const C* tw, int len, int span_log, int columns,
-                                          int pitch) {
+template <int COLS, typename C>
+__device__ __forceinline__ void dif_stage(C* v, const C* tw, int len, int span_log, int pitch) {
   const int half_total = len >> 1;
   const int half = 1 << (span_log - 1);
   const int tw_step = len >> span_log;
-  for (int t = threadIdx.x; t < columns * half_total; t += blockDim.x) {
-    const int col = t / half_total;
-    const int j = t - col * half_total;
+  for (int t = threadIdx.x; t < COLS * half_total; t += blockDim.x) {
+    const int col = t % COLS;
+    const int j = t / COLS;
     const int pos = j & (half - 1);
     const int i0 = ((j >> (span_log - 1)) << span_log) + pos;
     C* base = v + col * pitch;
@@ -82,15 +89,14 @@ __device__ __forceinline__ void dif_stage(C* v, const C* tw, int len, int span_l
   }
 }
 
-template <typename C>
-__device__ __forceinline__ void dit_stage(C* v, const C* tw, int len, int span_log, int columns,
-                                          int pitch) {
+template <int COLS, typename C>
+__device__ __forceinline__ void dit_stage(C* v, const C* tw, int len, int span_log, int pitch) {
   const int half_total = len >> 1;
   const int half = 1 << (span_log - 1);
   const int tw_step = len >> span_log;
-  for (int t = threadIdx.x; t < columns * half_total; t += blockDim.x) {
-    const int col = t / half_total;
-    const int j = t - col * half_total;
+  for (int t = threadIdx.x; t < COLS * half_total; t += blockDim.x) {
+    const int col = t % COLS;
+    const int j = t / COLS;
     const int pos = j & (half - 1);
     const int i0 = ((j >> (span_log - 1)) << span_log) + pos;
     C* base = v + col * pitch;
@@ -107,17 +113,16 @@ __device__ __forceinline__ void dit_stage(C* v, const C* tw, int len, int span_l
 // through both stages in registers: half the shared-memory round trips and barriers of a
 // plain radix-2 loop with the identical data flow (the output order stays bit-reversed).
 // Ends with a __syncthreads().
-template <typename C>
-__device__ __forceinline__ void forward_dif(C* v, const C* tw, int len, int log2_len, int columns,
-                                            int pitch) {
+template <int COLS, typename C>
+__device__ __forceinline__ void forward_dif(C* v, const C* tw, int len, int log2_len, int pitch) {
   const int quarter_total = len >> 2;
   int s = log2_len;
   for (; s >= 2; s -= 2) {
     const int quarter = 1 << (s - 2);
     const int step_a = len >> s;
-    for (int t = threadIdx.x; t < columns * quarter_total; t += blockDim.x) {
-      const int col = t / quarter_total;
-      const int j = t - col * quarter_total;
+    for (int t = threadIdx.x; t < COLS * quarter_total; t += blockDim.x) {
+      const int col = t % COLS;
+      const int j = t / COLS;
       const int pos = j & (quarter - 1);
       const int i0 = ((j >> (s - 2)) << s) + pos;
       C* base = v + col * pitch;
@@ -134,29 +139,28 @@ __device__ __forceinline__ void forward_dif(C* v, const C* tw, int len, int log2
     __syncthreads();
   }
   if (s == 1) {
-    dif_stage(v, tw, len, 1, columns, pitch);
+    dif_stage<COLS>(v, tw, len, 1, pitch);
     __syncthreads();
   }
 }
 
 // Inverse DIT (unnormalised): bit-reversed input, natural-order output; mirror image of
 // forward_dif (stage pairs fused in registers).
-template <typename C>
-__device__ __forceinline__ void inverse_dit(C* v, const C* tw, int len, int log2_len, int columns,
-                                            int pitch) {
+template <int COLS, typename C>
+__device__ __forceinline__ void inverse_dit(C* v, const C* tw, int len, int log2_len, int pitch) {
   const int quarter_total = len >> 2;
   int s = 2;
   if (log2_len & 1) {
-    dit_stage(v, tw, len, 1, columns, pitch);
+    dit_stage<COLS>(v, tw, len, 1, pitch);
     __syncthreads();
     s = 3;
   }
   for (; s <= log2_len; s += 2) {
     const int quarter = 1 << (s - 2);
     const int step_a = len >> s;
-    for (int t = threadIdx.x; t < columns * quarter_total; t += blockDim.x) {
-      const int col = t / quarter_total;
-      const int j = t - col * quarter_total;
+    for (int t = threadIdx.x; t < COLS * quarter_total; t += blockDim.x) {
+      const int col = t % COLS;
+      const int j = t / COLS;
       const int pos = j & (quarter - 1);
       const int i0 = ((j >> (s - 2)) << s) + pos;
       C* base = v + col * pitch;

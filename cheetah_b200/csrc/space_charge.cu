@@ -384,7 +384,8 @@ fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int in_
   using C = typename fft::Complex<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* v = reinterpret_cast<C*>(smem_raw);
-  C* tw = v + kRowPairs * len;
+  const int pitch = len + 2;  // 8 columns: see the bank note in fft.cuh
+  C* tw = v + kRowPairs * pitch;
   const int64_t b = blockIdx.y;
   const int rows = in_x * in_y;
   const int kz = len / 2 + 1;
@@ -409,17 +410,17 @@ fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int in_
         value.y = split_offset ? row[i] + row[split_offset + i + 1] : row[i];
       }
     }
-    v[t] = value;
+    v[pair * pitch + i] = value;
   }
   __syncthreads();
-  fft::forward_dif(v, tw, len, log2_len, kRowPairs, len);
+  fft::forward_dif<kRowPairs>(v, tw, len, log2_len, pitch);
 
   for (int t = threadIdx.x; t < kRowPairs * kz; t += kFftThreads) {
     const int pair = t / kz, k = t - pair * kz;
     const int r0 = first_row + 2 * pair, r1 = r0 + 1;
     if (r0 >= rows) continue;
-    const C zk = v[pair * len + fft::bit_reverse(k, log2_len)];
-    const C zm = v[pair * len + fft::bit_reverse((len - k) & (len - 1), log2_len)];
+    const C zk = v[pair * pitch + fft::bit_reverse(k, log2_len)];
+    const C zm = v[pair * pitch + fft::bit_reverse((len - k) & (len - 1), log2_len)];
     // A = (Z[k] + conj Z[-k]) / 2, B = (Z[k] - conj Z[-k]) / (2i)
     const C a{T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y - zm.y)};
     const C bb{T(0.5) * (zk.y + zm.y), T(-0.5) * (zk.x - zm.x)};
@@ -442,7 +443,8 @@ fft_c2r_z_kernel(const typename fft::Complex<T>::type* __restrict__ in, int in_n
   using C = typename fft::Complex<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* v = reinterpret_cast<C*>(smem_raw);
-  C* tw = v + kRowPairs * len;
+  const int pitch = len + 2;
+  C* tw = v + kRowPairs * pitch;
   const int64_t b = blockIdx.y;
   const int rows = out_x * out_y;
   const int kz = len / 2 + 1;
@@ -471,15 +473,15 @@ fft_c2r_z_kernel(const typename fft::Complex<T>::type* __restrict__ in, int in_n
     }
     if (k == 0 || k == len / 2) a.y = bb.y = T(0);  // c2r ignores Im of DC / Nyquist
     // Z = A + i B
-    v[pair * len + fft::bit_reverse(k, log2_len)] = C{a.x - bb.y, a.y + bb.x};
+    v[pair * pitch + fft::bit_reverse(k, log2_len)] = C{a.x - bb.y, a.y + bb.x};
   }
   __syncthreads();
-  fft::inverse_dit(v, tw, len, log2_len, kRowPairs, len);
+  fft::inverse_dit<kRowPairs>(v, tw, len, log2_len, pitch);
 
   for (int t = threadIdx.x; t < kRowPairs * out_z; t += kFftThreads) {
     const int pair = t / out_z, i = t - pair * out_z;
     const int r0 = first_row + 2 * pair, r1 = r0 + 1;
-    const C z = v[pair * len + i];
+    const C z = v[pair * pitch + i];
     if (r0 < rows) dst[static_cast<int64_t>(r0) * out_z + i] = z.x * scale;
     if (r1 < rows) dst[static_cast<int64_t>(r1) * out_z + i] = z.y * scale;
   }
@@ -520,7 +522,7 @@ fft_strided_kernel(typename fft::Complex<T>::type* __restrict__ data,
   }
   __syncthreads();
 
-  if (MODE == 0 || MODE == 2) fft::forward_dif(v, tw, len, log2_len, kColumns, pitch);
+  if (MODE == 0 || MODE == 2) fft::forward_dif<kColumns>(v, tw, len, log2_len, pitch);
   if (MODE == 2) {
     const int64_t plane = static_cast<int64_t>(green_ny) * green_kz;
     const T* g0 = green + blockIdx.z * (len / 2 + 1) * plane;
@@ -540,7 +542,7 @@ fft_strided_kernel(typename fft::Complex<T>::type* __restrict__ data,
     }
     __syncthreads();
   }
-  if (MODE == 1 || MODE == 2) fft::inverse_dit(v, tw, len, log2_len, kColumns, pitch);
+  if (MODE == 1 || MODE == 2) fft::inverse_dit<kColumns>(v, tw, len, log2_len, pitch);
 
   const int n_store = (MODE == 0) ? len : out_len;
   for (int t = threadIdx.x; t < kColumns * n_store; t += kFftThreads) {
@@ -570,7 +572,7 @@ fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, in
   using C = typename fft::Complex<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* v = reinterpret_cast<C*>(smem_raw);
-  const int pitch = len + 1;
+  const int pitch = len + 2;  // 8 packed columns: see the bank note in fft.cuh
   constexpr int kPairs = kColumns / 2;
   C* tw = v + kPairs * pitch;
   const int c0 = blockIdx.x * kColumns;
@@ -610,7 +612,7 @@ fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, in
   }
   if (threadIdx.x < kPairs) v[threadIdx.x * pitch + n] = C{T(0), T(0)};
   __syncthreads();
-  fft::forward_dif(v, tw, len, log2_len, kPairs, pitch);
+  fft::forward_dif<kPairs>(v, tw, len, log2_len, pitch);
 
   T* dst = out + blockIdx.y * out_batch_stride;
   for (int t = threadIdx.x; t < kColumns * (n + 1); t += kFftThreads) {
@@ -962,7 +964,7 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
   using C = typename fft::Complex<T>::type;
   const int Kz = nz + 1;
   const unsigned nb = static_cast<unsigned>(B);
-  auto smem = [&](int len) { return sizeof(C) * ((kColumns / 2) * (len + 1) + len / 2); };
+  auto smem = [&](int len) { return sizeof(C) * ((kColumns / 2) * (len + 2) + len / 2); };
   const int64_t lattice_points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
   {  // z: rows (x, y) of the lattice difference -> s1[x][y][kz]
     auto k = fft_even_pass_kernel<T, true>;
@@ -1007,7 +1009,7 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
   const int Nx = 2 * nx, Ny = 2 * ny, Nz = 2 * nz, Kz = Nz / 2 + 1;
   const int lx = log2_exact(Nx), ly = log2_exact(Ny), lz = log2_exact(Nz);
   const int64_t spectrum = static_cast<int64_t>(Nx) * Ny * Kz;
-  auto z_smem = [&](int len) { return sizeof(C) * (kRowPairs * len + len / 2); };
+  auto z_smem = [&](int len) { return sizeof(C) * (kRowPairs * (len + 2) + len / 2); };
   auto s_smem = [&](int len) { return sizeof(C) * (kColumns * (len + 1) + len / 2); };
   const unsigned nb = static_cast<unsigned>(B);
 
