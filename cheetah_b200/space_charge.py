@@ -95,7 +95,8 @@ _side_streams: dict = {}
 def _side_stream(device) -> torch.cuda.Stream:
     stream = _side_streams.get(device)
     if stream is None:
-        stream = _side_streams[device] = torch.cuda.Stream(device)
+        # high priority: its (few, long-running) CTAs are placed before the deposit's
+        stream = _side_streams[device] = torch.cuda.Stream(device, priority=-1)
     return stream
 
 
