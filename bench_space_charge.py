@@ -113,7 +113,7 @@ def main() -> None:
         "sc_deposit_kernel": (
             lambda: lib.ch_sc_deposit(
                 pp.data_ptr(), ps, q.data_ptr(), qs, w.data_ptr(), 0, ws.params.data_ptr(), n, B,
-                grid, grid, grid, code, ws.rho_split.data_ptr(), stream),
+                grid, grid, grid, code, ws.rho_quad.data_ptr(), stream),
             B * n * 36, "hbm: 28 B row + charge + survival per particle (atomics stay in L2)"),
         "green lattice + 3 even FFT passes": (
             lambda: (lib.ch_sc_green_function(ws.params.data_ptr(), B, grid, grid, grid, code,
@@ -125,7 +125,7 @@ def main() -> None:
             "lattice write+read, 3 passes (L2-resident for one beam)"),
         "poisson: r2c z, y, fused x conv, inverse y, c2r z": (
             lambda: lib.ch_sc_poisson_solve(
-                ws.rho_split.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), B,
+                ws.rho_quad.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), B,
                 grid, grid, grid, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream),
             B * (int(spectrum_bytes * (0.25 + 0.5 + 0.5 + 1.0 + 0.5 + 0.5 + 0.25)) + cells3 * 12),
             "spectrum passes touch 1/4 .. 1 of the (2n)^2 (n+1) complex array (L2-resident for "

@@ -211,22 +211,42 @@ __device__ __forceinline__ void deposit_particle(T* __restrict__ grid, T x, T y,
       }
 }
 
-// Two adjacent cells along z in ONE L2 transaction (SASS REDG.E.ADD.F32x2): needs an 8-byte
-// aligned address, i.e. an even first index -- see the split-row layout below.
-__device__ __forceinline__ void add_pair(float* address, float a, float b) {
-  atomicAdd(reinterpret_cast<float2*>(address), make_float2(a, b));
+// Four cells (2 x 2 in y, z) in ONE L2 transaction (SASS REDG.E.ADD.F32x4): needs a 16-byte
+// aligned address -- see the quad-block layout below.  The L2 processes ~200 G reductions / s
+// whatever their width (tools/micro/red_vec.cu), so the count of reductions is what matters.
+__device__ __forceinline__ void add_quad(float* address, float a, float b, float c, float d) {
+  atomicAdd(reinterpret_cast<float4*>(address), make_float4(a, b, c, d));
 }
-__device__ __forceinline__ void add_pair(double* address, double a, double b) {
+__device__ __forceinline__ void add_quad(double* address, double a, double b, double c, double d) {
   atomicAdd(address, a);
   atomicAdd(address + 1, b);
+  atomicAdd(address + 2, c);
+  atomicAdd(address + 3, d);
 }
 
-// Space-charge deposit.  Each particle touches 4 (x, y) rows x 2 adjacent z cells.  The grid
-// is kept as SPLIT ROWS  rho[B][nx * ny][2][nz + 2]:  part 0 (A) receives the z pairs that
-// start at an even cell, part 1 (B) -- indexed by z + 1 -- those that start at an odd cell
-// (including -1), so every pair is 8-byte aligned and one vector RED serves two cells: 4 L2
-// atomics per particle instead of 8.  The logical grid is A[z] + B[z + 1]; the z pass of the
-// FFT sums the two parts while loading (ch_sc_poisson_solve).
+// Space-charge deposit.  Each particle touches 2 x-planes x (2 x 2) cells in (y, z).  The grid is
+// kept as QUAD BLOCKS  rho[B][nx][4][ny/2 + 1][nz/2 + 1][4]:  part p = 2 py + pz holds the 2 x 2
+// blocks whose lower corner (y0, z0) has parity (py, pz) (-1 counts as odd), block
+// ((y0 + py) / 2, (z0 + pz) / 2), entries (dy, dz) = (0,0), (0,1), (1,0), (1,1).  Every corner
+// quadruple is therefore contiguous and 16-byte aligned and ONE vector RED serves four cells:
+// 2 L2 reductions per particle instead of 8 scalar ones (4 with z pairs only).  The logical grid
+// is the sum of the four parts; the z pass of the FFT adds them while loading (quad_value).
+template <typename T>
+__device__ __forceinline__ T quad_value(const T* __restrict__ plane, int y, int z, int qy, int qz) {
+  // plane = rho[b][x]; the cell belongs to one block of each part
+  T sum = T(0);
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+    const int by = (y + py) >> 1, dy = (y + py) & 1;
+#pragma unroll
+    for (int pz = 0; pz < 2; ++pz) {
+      const int bz = (z + pz) >> 1, dz = (z + pz) & 1;
+      sum += plane[((static_cast<int64_t>(py * 2 + pz) * qy + by) * qz + bz) * 4 + dy * 2 + dz];
+    }
+  }
+  return sum;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 sc_deposit_kernel(const T* __restrict__ particles, int64_t particle_stride,
@@ -245,8 +265,9 @@ sc_deposit_kernel(const T* __restrict__ particles, int64_t particle_stride,
   const T minus_beta = -static_cast<T>(prm[7]);
   const T* q = charges + b * charge_stride;
   const T* w = survival ? survival + b * survival_stride : nullptr;
-  const int part = nz + 2, pitch = 2 * part;
-  T* grid = rho + b * static_cast<int64_t>(nx) * ny * pitch;
+  const int qy = ny / 2 + 1, qz = nz / 2 + 1;
+  const int64_t plane = static_cast<int64_t>(4) * qy * qz * 4;  // scalars per x plane
+  T* grid = rho + b * nx * plane;
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
   const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
 
@@ -269,22 +290,22 @@ sc_deposit_kernel(const T* __restrict__ particles, int64_t particle_stride,
     const T z = tile[local * 7 + 4] * minus_beta;
     const AxisDeposit<T> az = deposit_axis(z, lo[2], hi[2], nz);
     if (!(ax.inside && ay.inside && az.inside)) continue;  // charges * in_extent
-    // lower z index: in [-1, nz - 1] for a particle inside the extent (off-grid corners carry
-    // zero weight, so the clamp only guards against rounding at the very edge)
+    // lower corner indices: in [-1, n - 1] for a particle inside the extent (off-grid corners
+    // carry zero weight, so the clamps only guard against rounding at the very edge)
+    const int iy = min(max(ay.base, -1), ny - 1);
     const int iz = min(max(az.base, -1), nz - 1);
-    const int ix[2] = {ax.lo, ax.hi}, iy[2] = {ay.lo, ay.hi};
-    const T wx[2] = {ax.w_lo, ax.w_hi}, wy[2] = {ay.w_lo, ay.w_hi};
-    // pair start: even -> part A at z, odd (or -1) -> part B at z + 1
-    const int slot = (iz & 1) ? part + iz + 1 : iz;
+    const int py = iy & 1, pz = iz & 1;  // -1 & 1 == 1
+    const int64_t block =
+        ((static_cast<int64_t>(py * 2 + pz) * qy + ((iy + py) >> 1)) * qz + ((iz + pz) >> 1)) * 4;
+    const int ix[2] = {ax.lo, ax.hi};
+    const T wx[2] = {ax.w_lo, ax.w_hi};
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const T wxy = wx[a] * wy[c] * charge;
-        if (wxy != T(0))
-          add_pair(grid + static_cast<int64_t>(ix[a] * ny + iy[c]) * pitch + slot, wxy * az.w_lo,
-                   wxy * az.w_hi);
-      }
+    for (int a = 0; a < 2; ++a) {
+      if (wx[a] == T(0)) continue;
+      const T lower = wx[a] * ay.w_lo * charge, upper = wx[a] * ay.w_hi * charge;
+      add_quad(grid + ix[a] * plane + block, lower * az.w_lo, lower * az.w_hi, upper * az.w_lo,
+               upper * az.w_hi);
+    }
   }
 }
 
@@ -379,7 +400,7 @@ constexpr int kColumns = 16;   // strided passes: 16 adjacent columns per CTA
 template <typename T>
 __global__ void __launch_bounds__(kFftThreads)
 fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int in_pitch,
-                 int split_offset, int len, int log2_len, int out_nx, int out_ny,
+                 int quad, int len, int log2_len, int out_nx, int out_ny,
                  typename fft::Complex<T>::type* __restrict__ out) {
   using C = typename fft::Complex<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -390,9 +411,11 @@ fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int in_
   const int rows = in_x * in_y;
   const int kz = len / 2 + 1;
   const int first_row = blockIdx.x * 2 * kRowPairs;
-  // rows are `in_pitch` apart; with split_offset != 0 a row is stored as two parts (see
-  // sc_deposit_kernel) and the logical value is part A[i] + part B[i + 1]
-  const T* src = in + b * static_cast<int64_t>(rows) * in_pitch;
+  // plain rows are `in_pitch` apart; with quad != 0 the input is the quad-block charge grid of
+  // sc_deposit_kernel and a value is the sum of four partial grids (quad_value)
+  const int qy = in_y / 2 + 1, qz = in_z / 2 + 1;
+  const int64_t plane = static_cast<int64_t>(4) * qy * qz * 4;
+  const T* src = in + b * (quad ? in_x * plane : static_cast<int64_t>(rows) * in_pitch);
   C* dst = out + b * static_cast<int64_t>(out_nx) * out_ny * kz;
 
   fft::fill_twiddles(tw, len);
@@ -401,14 +424,12 @@ fft_r2c_z_kernel(const T* __restrict__ in, int in_x, int in_y, int in_z, int in_
     const int r0 = first_row + 2 * pair, r1 = r0 + 1;
     C value{T(0), T(0)};
     if (i < in_z) {
-      if (r0 < rows) {
-        const T* row = src + static_cast<int64_t>(r0) * in_pitch;
-        value.x = split_offset ? row[i] + row[split_offset + i + 1] : row[i];
-      }
-      if (r1 < rows) {
-        const T* row = src + static_cast<int64_t>(r1) * in_pitch;
-        value.y = split_offset ? row[i] + row[split_offset + i + 1] : row[i];
-      }
+      if (r0 < rows)
+        value.x = quad ? quad_value(src + (r0 / in_y) * plane, r0 % in_y, i, qy, qz)
+                       : src[static_cast<int64_t>(r0) * in_pitch + i];
+      if (r1 < rows)
+        value.y = quad ? quad_value(src + (r1 / in_y) * plane, r1 % in_y, i, qy, qz)
+                       : src[static_cast<int64_t>(r1) * in_pitch + i];
     }
     v[pair * pitch + i] = value;
   }
@@ -1018,8 +1039,7 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
     auto k = fft_r2c_z_kernel<T>;
     if (allow_smem(k, z_smem(Nz)) != CH_OK) return CH_ECUDA;
     dim3 grid((nx * ny + 2 * kRowPairs - 1) / (2 * kRowPairs), nb);
-    k<<<grid, kFftThreads, z_smem(Nz), stream>>>(rho, nx, ny, nz, 2 * (nz + 2), nz + 2, Nz, lz, Nx,
-                                                  Ny, rs);
+    k<<<grid, kFftThreads, z_smem(Nz), stream>>>(rho, nx, ny, nz, 0, 1, Nz, lz, Nx, Ny, rs);
     CH_LAUNCH_CHECK();
   }
   {
@@ -1180,7 +1200,7 @@ extern "C" int ch_sc_deposit(const void* particles, int64_t particle_stride, con
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_deposit: bad grid (%d, %d, %d)", nx, ny, nz);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t elem = dtype == CH_F32 ? 4 : 8;
-  CH_CUDA(cudaMemsetAsync(rho, 0, elem * nx * ny * 2 * (nz + 2) * n_beams, s));
+  CH_CUDA(cudaMemsetAsync(rho, 0, elem * nx * 16 * (ny / 2 + 1) * (nz / 2 + 1) * n_beams, s));
   dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(n_beams));
   if (dtype == CH_F32) {
     const int bulk = ch::bulk_compatible<float>(particles, n_particles, particle_stride);

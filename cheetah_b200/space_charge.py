@@ -52,9 +52,20 @@ class Workspace:
         return self.params_slots[self.slot]
 
     def charge_grid(self) -> torch.Tensor:
-        """Deposited charge per cell [B, nx, ny, nz] (merges the split rows)."""
-        nz = self.rho_split.shape[-1] - 2
-        return self.rho_split[..., 0, :nz] + self.rho_split[..., 1, 1 : nz + 1]
+        """Deposited charge per cell [B, nx, ny, nz] (sums the four quad-block parts, see
+        ch_sc_deposit)."""
+        quad = self.rho_quad  # [B, nx, 4, QY, QZ, 4]
+        n_beams, nx, _, qy, qz, _ = quad.shape
+        ny, nz = 2 * (qy - 1), 2 * (qz - 1)
+        blocks = quad.reshape(n_beams, nx, 2, 2, qy, qz, 2, 2)  # py, pz, by, bz, dy, dz
+        out = quad.new_zeros((n_beams, nx, ny + 3, nz + 3))  # index = cell + 1 (cells from -1)
+        for py in (0, 1):
+            for pz in (0, 1):
+                # block (by, bz) covers cells y = 2 by - py + dy, z = 2 bz - pz + dz
+                part = blocks[:, :, py, pz].permute(0, 1, 2, 4, 3, 5).reshape(
+                    n_beams, nx, 2 * qy, 2 * qz)
+                out[:, :, 1 - py : 1 - py + 2 * qy, 1 - pz : 1 - pz + 2 * qz] += part
+        return out[:, :, 1 : ny + 1, 1 : nz + 1]
 
     def __init__(self, n_beams: int, grid_shape: tuple, dtype, device) -> None:
         nx, ny, nz = grid_shape
@@ -71,8 +82,9 @@ class Workspace:
             for _ in range(2)
         ]
         self.slot = 0
-        # split rows [.., 2, nz + 2] (see ch_sc_deposit); `charge_grid()` merges them
-        self.rho_split = torch.empty((n_beams, nx, ny, 2, nz + 2), dtype=dtype, device=device)
+        # quad blocks (see ch_sc_deposit); `charge_grid()` sums the four parts
+        self.rho_quad = torch.empty(
+            (n_beams, nx, 4, ny // 2 + 1, nz // 2 + 1, 4), dtype=dtype, device=device)
         self.lattice = torch.empty(
             (n_beams, nx + 1, ny + 1, nz + 1), dtype=torch.float64, device=device
         )
@@ -188,10 +200,10 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
         joined.record(side)
         _capi.check(lib.ch_sc_deposit(
             p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
-            ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_split.data_ptr(), stream))
+            ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_quad.data_ptr(), stream))
         main.wait_event(joined)
         _capi.check(lib.ch_sc_poisson_solve(
-            ws.rho_split.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
+            ws.rho_quad.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
             nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))
         _capi.check(lib.ch_sc_field(
             ws.phi.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,

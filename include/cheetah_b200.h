@@ -342,10 +342,12 @@ int ch_sc_grid_params(const double* stats, int64_t n_beams,
  * spanning +-grid half-extent: _array_rho (space_charge_kick.py:125-146) ->
  * _cloud_in_cell_3d (cheetah/utils/cloud_in_cell.py:244-384; cell-centred, inclusive
  * extent test, clamped corners with zeroed weights).  rho is zeroed here and holds CHARGE per
- * cell (the 1/cell-volume factor is applied in ch_sc_poisson_solve) in SPLIT ROWS
- * rho[B][nx*ny][2][nz+2]: the two z-adjacent cells of a corner pair go to one 8-byte aligned
- * vector atomic -- part 0 at index z for pairs starting at an even cell, part 1 at index z+1
- * for pairs starting at an odd cell (or at -1).  Logical grid: rho[.][0][z] + rho[.][1][z+1]. */
+ * cell (the 1/cell-volume factor is applied in ch_sc_poisson_solve) in QUAD BLOCKS
+ * rho[B][nx][4][ny/2 + 1][nz/2 + 1][4]: part p = 2 py + pz holds the 2 x 2 (y, z) blocks whose
+ * lower corner (y0, z0) has parity (py, pz) (-1 counts as odd) at block ((y0 + py) / 2,
+ * (z0 + pz) / 2), entries (dy, dz) = (0,0), (0,1), (1,0), (1,1).  The four (y, z) corners of a
+ * particle are then one 16-byte aligned vector reduction (REDG.E.ADD.F32x4): 2 L2 reductions per
+ * particle.  Logical grid: the sum over the four parts (nx, ny, nz even).                      */
 int ch_sc_deposit(const void* particles, int64_t particle_stride,
                   const void* charges, int64_t charge_stride,
                   const void* survival, int64_t survival_stride,
@@ -384,7 +386,8 @@ int ch_sc_green_spectrum(const double* lattice, int64_t n_beams,
  * shared-memory FFT passes (no cuFFT): z real<->complex with two rows packed per transform,
  * y and x strided passes; zero padding is never materialised; the x pass fuses forward FFT,
  * the multiply by the compact Green spectrum and the inverse FFT.
- * rho: the split-row charge grid written by ch_sc_deposit (merged while loading);
+ * rho: the quad-block charge grid written by ch_sc_deposit (its four parts are summed while
+ * loading);
  * rho_spectrum: [B][2nx][2ny][nz+1] complex scratch.                                        */
 int ch_sc_poisson_solve(const void* rho, const void* green_spectrum, const double* params,
                         int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
