@@ -11,6 +11,8 @@
 // tiles; the charge histogram lives in L2 (a 64^3 fp32 grid is 1 MB) and is built with
 // fire-and-forget RED atomics (N/cells is ~4: privatising tiles would cost more than the
 // atomics they save); the 3-D convolution is three shared-memory FFT passes.
+#include <cstdlib>
+
 #include "ch_common.cuh"
 #include "fft.cuh"
 
@@ -1259,7 +1261,12 @@ extern "C" int ch_sc_green_function(const double* params, int64_t n_beams, int32
   // loop) leaves room for the deposit's CTAs on every SM, so the two overlap instead of queueing
   // behind each other (64 beams: 630 -> 611 ms per 100 kicks; capping the FFT passes of the
   // chain as well made them the critical path and was not kept).
-  const int64_t per_beam = (148 * 3 + n_beams - 1) / n_beams;
+  static const int ctas_per_sm = [] {
+    const char* v = getenv("CH_GREEN_CTAS_PER_SM");  // tuning knob
+    const int n = v ? atoi(v) : 3;
+    return n > 0 ? n : 3;
+  }();
+  const int64_t per_beam = (148 * ctas_per_sm + n_beams - 1) / n_beams;
   dim3 grid_a(ch::blocks_for(points, 256, per_beam < 1 ? 1 : per_beam),
               static_cast<unsigned>(n_beams));
   ch::sc_green_lattice_kernel<<<grid_a, 256, 0, s>>>(params, nx, ny, nz, lattice);
