@@ -144,3 +144,89 @@ def test_space_charge_odd_particle_count_and_survival_weighting():
         ours = out.particles.cpu().double() - beam_t["particles"].double() + particles
         err = ((ours - expected["particles"]).abs().amax(dim=0) / moved.clamp_min(1e-300))[[1, 3, 5]]
         assert (err < tol).all(), err
+
+
+# ---- non-linear tracking methods at full size ---------------------------
+def _column_error(a, b, reference):
+    scale = reference.abs().amax(dim=-2, keepdim=True).clamp_min(1e-30)
+    return float(((a - b).abs() / scale)[..., :6].max())
+
+
+def test_drift_kick_drift_round_trip_and_limits(beam):
+    """1e6 particles: the exact drift inverts under L -> -L, a k1 = 0 quadrupole and a zero-angle
+    dipole are exact drifts, an unpowered TDC is two half drifts, and a run of elements equals
+    tracking them one by one (tests/test_drift.py:43-69, test_dipole.py:153-175)."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE)  # noqa: E731
+    dkd = "drift_kick_drift"
+    there = cb.Drift(length=t(1.7), tracking_method=dkd).track(beam)
+    back = cb.Drift(length=t(-1.7), tracking_method=dkd).track(there)
+    assert _column_error(back.particles, beam.particles, beam.particles) < 5e-7
+    assert torch.equal(back.particles[..., 5], beam.particles[..., 5])  # delta untouched
+    drift = cb.Drift(length=t(0.8), tracking_method=dkd).track(beam)
+    quad = cb.Quadrupole(length=t(0.8), k1=t(0.0), num_steps=4, tracking_method=dkd).track(beam)
+    dipole = cb.Dipole(length=t(0.8), angle=t(0.0), tracking_method=dkd).track(beam)
+    tdc = cb.TransverseDeflectingCavity(length=t(0.8), voltage=t(0.0)).track(beam)
+    for other in (quad, dipole, tdc):
+        assert _column_error(other.particles, drift.particles, drift.particles) < 1e-6
+    # linear drift agrees to second order in the (small) angles
+    linear = cb.Drift(length=t(0.8)).track(beam)
+    assert _column_error(drift.particles[..., :4], linear.particles[..., :4],
+                         linear.particles[..., :4]) < 1e-4
+    elements = [
+        cb.Drift(length=t(0.3), tracking_method=dkd),
+        cb.Quadrupole(length=t(0.2), k1=t(4.0), num_steps=3, tracking_method=dkd),
+        cb.Marker(),
+        cb.Dipole(length=t(0.4), angle=t(0.05), tracking_method=dkd),
+        cb.Sextupole(length=t(0.1), k2=t(20.0)),
+        cb.Drift(length=t(0.3), tracking_method="second_order"),
+    ]
+    fused = cb.Segment(elements).track(beam)
+    step = beam
+    for element in elements:
+        step = element.track(step)
+    assert _column_error(fused.particles, step.particles, step.particles) < 2e-6
+    assert torch.allclose(fused.s, step.s)
+
+
+def test_second_order_reduces_to_linear_for_small_amplitudes(beam):
+    """Second-order maps = linear map + O(amplitude^2): shrinking the beam by 1e-3 leaves only
+    the linear part (sextupole.py:84-116, quadrupole.py:93-143)."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE)  # noqa: E731
+    small = workloads.product_beam(workloads.twiss_beam_particles(N), DEVICE, torch.float32)
+    small.particles[..., :6] *= 1e-3
+    for second, linear in (
+        (cb.Quadrupole(length=t(0.3), k1=t(5.0), tilt=t(0.2), tracking_method="second_order"),
+         cb.Quadrupole(length=t(0.3), k1=t(5.0), tilt=t(0.2))),
+        (cb.Sextupole(length=t(0.3), k2=t(50.0)), cb.Drift(length=t(0.3))),
+        (cb.Dipole(length=t(0.5), angle=t(0.1), tracking_method="second_order"),
+         cb.Dipole(length=t(0.5), angle=t(0.1))),
+    ):
+        a, b = second.track(small), linear.track(small)
+        assert _column_error(a.particles, b.particles, b.particles) < 5e-5
+
+
+def test_screen_conserves_the_surviving_charge_at_full_size():
+    """4 settings x 1e6 particles behind an aperture: every image sums to the charge that
+    survived and lies on the screen (screen.py:316-340)."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE)  # noqa: E731
+    torch.manual_seed(8)
+    beam = cb.ParticleBeam.from_parameters(num_particles=N, total_charge=torch.tensor(1e-9),
+                                           sigma_x=3e-4, sigma_y=2e-4, device=DEVICE)
+    segment = cb.Segment([
+        cb.Quadrupole(length=t(0.2), k1=t([0.0, 4.0, -4.0, 8.0])),
+        cb.Drift(length=t(1.0)),
+        cb.Aperture(x_max=t(4e-4), y_max=t(4e-4)),
+        cb.Screen(is_active=True, name="screen", resolution=(512, 512), pixel_size=t([4e-6, 4e-6])),
+    ])
+    out = segment.track(beam)
+    image = segment.screen.reading
+    assert tuple(image.shape) == (4, 512, 512)
+    on_screen = (out.particles[..., 0].abs() < 1.0e-3) & (out.particles[..., 2].abs() < 1.0e-3)
+    expected = (out.particle_charges.abs() * out.survival_probabilities * on_screen).double().sum(-1)
+    assert torch.allclose(image.double().sum(dim=(-2, -1)), expected, rtol=2e-4)
