@@ -25,6 +25,7 @@ from .elements import (  # noqa: F401
     Sextupole,
     Solenoid,
     SpaceChargeKick,
+    Superimposed,
     TransverseDeflectingCavity,
     Undulator,
     VerticalCorrector,

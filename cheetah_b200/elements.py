@@ -131,6 +131,28 @@ class Element(nn.Module):
     def forward(self, incoming: Beam) -> Beam:
         return self.track(incoming)
 
+    def split(self, resolution: torch.Tensor) -> list["Element"]:
+        """Slices no longer than ``resolution``; elements that cannot be split return
+        themselves (element.py:338-347)."""
+        return [self]
+
+    def _split_evenly(self, resolution: torch.Tensor, **fields) -> list["Element"]:
+        """``ceil(max|length| / resolution)`` equal slices with the other fields unchanged
+        (drift.py:160-172, quadrupole.py:261-278, solenoid.py:126-143)."""
+        num_splits = int((self.length.abs().max() / resolution).ceil().int())
+        extras = {key: getattr(self, key) for key in getattr(self, "plain_fields", {})}
+        if self.supported_tracking_methods and hasattr(self, "_tracking_method") and \
+                len(self.supported_tracking_methods) > 1:
+            extras["tracking_method"] = self.tracking_method
+        return [
+            self.__class__(
+                length=self.length / num_splits, **fields, **extras,
+                name=f"{self.name}_split_{i}", sanitize_name=False, metadata=self.metadata,
+                dtype=self.length.dtype, device=self.length.device,
+            )
+            for i in range(num_splits)
+        ]
+
     def __repr__(self) -> str:
         fields = ", ".join(f"{k}={getattr(self, k)!r}" for k in self.tensor_fields)
         return f"{self.__class__.__name__}({fields}, name={self.name!r})"
@@ -185,6 +207,9 @@ class Drift(_SimpleElement):
     def is_skippable(self) -> bool:
         return self.tracking_method == "linear"
 
+    def split(self, resolution: torch.Tensor) -> list[Element]:
+        return self._split_evenly(resolution)
+
 
 class Quadrupole(_SimpleElement):
     """Quadrupole magnet (cheetah/accelerator/quadrupole.py)."""
@@ -200,6 +225,10 @@ class Quadrupole(_SimpleElement):
     @property
     def is_active(self) -> bool:
         return bool((self.k1 != 0).any())
+
+    def split(self, resolution: torch.Tensor) -> list[Element]:
+        return self._split_evenly(resolution, k1=self.k1, misalignment=self.misalignment,
+                                  tilt=self.tilt)
 
 
 class Sextupole(_SimpleElement):
@@ -321,6 +350,9 @@ class Solenoid(_SimpleElement):
     @property
     def is_active(self) -> bool:
         return bool((self.k != 0).any())
+
+    def split(self, resolution: torch.Tensor) -> list[Element]:
+        return self._split_evenly(resolution, k=self.k, misalignment=self.misalignment)
 
 
 class Undulator(_SimpleElement):
@@ -514,6 +546,23 @@ class CustomTransferMap(Element):
         ).all(), "The seventh row of the transfer map must be [0, 0, 0, 0, 0, 0, 1]."
         self.register_buffer_or_parameter("predefined_transfer_map", predefined_transfer_map)
 
+    @classmethod
+    def from_merging_elements(cls, elements: list, incoming_beam: Beam) -> "CustomTransferMap":
+        """One map for a run of skippable elements (custom_transfer_map.py:60-109): the product
+        is formed on the device in fp64 by ``ch_compose_maps`` and rounded once."""
+        assert all(element.is_skippable for element in elements), (
+            "Combining the elements in a Segment that is not skippable will result in"
+            " incorrect tracking results."
+        )
+        from . import tracking
+
+        tm = tracking.first_order_transfer_map(
+            list(elements), incoming_beam.energy, incoming_beam.species
+        )
+        length = sum(element.length for element in elements)
+        name = "combined_" + "_".join(element.name for element in elements)
+        return cls(tm, length=length, name=name, sanitize_name=False)
+
 
 class SpaceChargeKick(_SimpleElement):
     """IGF space-charge kick (cheetah/accelerator/space_charge_kick.py)."""
@@ -526,6 +575,45 @@ class SpaceChargeKick(_SimpleElement):
     @property
     def is_skippable(self) -> bool:
         return False
+
+
+class Superimposed(Element):
+    """One zero-length element placed at the centre of another
+    (cheetah/accelerator/superimposed.py): lowered as [first half, element, second half]."""
+
+    def __init__(self, base_element: Element, superimposed_element: Element,
+                 name: str | None = None, sanitize_name: bool | None = None,
+                 metadata: dict | None = None, device=None, dtype=None) -> None:
+        super().__init__(name=name, sanitize_name=sanitize_name, metadata=metadata,
+                         device=device, dtype=dtype)
+        assert bool((superimposed_element.length == 0.0).all()), (
+            "The superimposed element must have zero length."
+        )
+        self.base_element = base_element
+        self.superimposed_element = superimposed_element
+        halves = base_element.split(base_element.length / 2.0)
+        assert len(halves) == 2, f"{type(base_element).__name__} cannot be split in two"
+        self._segment = Segment(
+            elements=[halves[0], superimposed_element, halves[1]], name=f"{self.name}_segment",
+            sanitize_name=sanitize_name,
+        )
+
+    def flattened(self) -> "Segment":
+        return self._segment.flattened()
+
+    @property
+    def is_skippable(self) -> bool:
+        return self._segment.is_skippable
+
+    @property
+    def length(self) -> torch.Tensor:
+        return self._segment.length
+
+    def first_order_transfer_map(self, energy: torch.Tensor, species: Species) -> torch.Tensor:
+        return self._segment.first_order_transfer_map(energy, species)
+
+    def track(self, incoming: Beam) -> Beam:
+        return self._segment.track(incoming)
 
 
 class Segment(Element):
@@ -569,6 +657,100 @@ class Segment(Element):
             else:
                 flat.append(element)
         return Segment(elements=flat, name=self.name, sanitize_name=False)
+
+    # ---- container helpers (segment.py:73-229, :576-656) ------------------------------------
+    @property
+    def element_names(self) -> list[str]:
+        return [element.name for element in self.elements]
+
+    def element_index(self, element_name: str) -> int:
+        try:
+            return self.element_names.index(element_name)
+        except ValueError:
+            raise ValueError(f"Element '{element_name}' not found in segment.")
+
+    def subcell(self, start: str | None = None, end: str | None = None,
+                include_start: bool = True, include_end: bool = True) -> "Segment":
+        """Elements from ``start`` to ``end`` (segment.py:94-141)."""
+        names = self.element_names
+        if start is not None and start not in names:
+            raise ValueError(f"Element {start} is not part of the segment.")
+        if end is not None and end not in names:
+            raise ValueError(f"Element {end} is not part of the segment.")
+        subcell = []
+        is_in_subcell = start is None
+        for element in self.elements:
+            if element.name == start:
+                is_in_subcell = True
+                if include_start:
+                    subcell.append(element)
+                continue
+            if element.name == end:
+                if include_end and is_in_subcell:
+                    subcell.append(element)
+                break
+            if is_in_subcell:
+                subcell.append(element)
+        return self.__class__(subcell)
+
+    def reversed(self) -> "Segment":
+        elements = [e.reversed() if isinstance(e, Segment) else e for e in self.elements][::-1]
+        return self.__class__(elements=elements, name=f"{self.name}_reversed", sanitize_name=False)
+
+    def partition_at(self, element_name: str, mode: str = "both") -> tuple:
+        """Split around a named element (segment.py:599-629)."""
+        index = self.element_index(element_name)
+        elements = list(self.elements)
+        pre = self.__class__(elements[: index + 1] if mode == "after" else elements[:index])
+        post = self.__class__(elements[index:] if mode == "before" else elements[index + 1 :])
+        return (pre, elements[index], post) if mode == "both" else (pre, post)
+
+    def transfer_maps_merged(self, incoming_beam: Beam, except_for: list[str] | None = None
+                             ) -> "Segment":
+        """Runs of skippable elements replaced by one ``CustomTransferMap`` each
+        (segment.py:179-229).  NOTE: ``Segment.track`` already merges every skippable run on the
+        device for each call (``ch_compose_maps``), so this only saves the composition launch."""
+        except_for = except_for or []
+        merged, run = [], []
+        beam = incoming_beam
+
+        def flush() -> None:
+            nonlocal beam, run
+            if len(run) == 1:
+                merged.append(run[0])
+                beam = run[0].track(beam)
+            elif len(run) > 1:
+                merged.append(CustomTransferMap.from_merging_elements(run, incoming_beam=beam))
+                beam = merged[-1].track(beam)
+            run = []
+
+        for element in self.elements:
+            if element.is_skippable and element.name not in except_for:
+                run.append(element)
+            else:
+                flush()
+                merged.append(element)
+                beam = element.track(beam)
+        if run:
+            merged.append(CustomTransferMap.from_merging_elements(run, incoming_beam=beam))
+        return self.__class__(elements=merged, name=self.name, sanitize_name=False)
+
+    def split(self, resolution: torch.Tensor) -> list[Element]:
+        return [part for element in self.elements for part in element.split(resolution)]
+
+    def beam_along_segment_generator(self, incoming: Beam, resolution=None):
+        """Beams at the end of every element, or of every slice no longer than ``resolution``
+        (segment.py:631-656)."""
+        if resolution is not None:
+            yield from self.__class__(
+                elements=self.split(torch.as_tensor(resolution)), name=f"{self.name}_split"
+            ).beam_along_segment_generator(incoming)
+            return
+        yield incoming
+        for element in self.elements:
+            outgoing = element.track(incoming)
+            yield outgoing
+            incoming = outgoing
 
     def first_order_transfer_map(self, energy: torch.Tensor, species: Species) -> torch.Tensor:
         if not self.is_skippable:

@@ -135,9 +135,21 @@ def make_consistency() -> None:
 
     lattices = {}
     rows = slice(None, None, ROW_STRIDE)
-    for (cls_name, label), kwargs in CONSISTENCY_CASES.items():
+    containers = {  # tests/conftest.py:100-102, :117-124
+        ("Segment", "default"): lambda: cheetah.Segment(
+            elements=[cheetah.Drift(length=torch.tensor(1.0))], name="default"),
+        ("Superimposed", "default"): lambda: cheetah.Superimposed(
+            base_element=cheetah.Quadrupole(length=torch.tensor(1.0), k1=torch.tensor(0.5)),
+            superimposed_element=cheetah.BPM(), name="default"),
+    }
+    cases = dict(CONSISTENCY_CASES)
+    cases.update({key: None for key in containers})
+    for (cls_name, label), kwargs in cases.items():
         key = f"{cls_name}_{label}"
-        element = getattr(cheetah, cls_name)(name=label, **kwargs).to(torch.float64)
+        if kwargs is None:
+            element = containers[(cls_name, label)]().to(torch.float64)
+        else:
+            element = getattr(cheetah, cls_name)(name=label, **kwargs).to(torch.float64)
         lattices[key] = lattice_io._to_json([lattice_io.describe(element)])
         folder = resources / "consistency_expected_outgoing"
         with (folder / f"{cls_name}_ParticleBeam_{label}.pkl").open("rb") as f:
@@ -159,7 +171,7 @@ def make_consistency() -> None:
     np.savez_compressed(OUT / "consistency.npz", **arrays)
     with (OUT / "consistency.json").open("w") as f:
         json.dump({"row_stride": ROW_STRIDE, "lattices": lattices}, f, separators=(",", ":"))
-    print("consistency:", len(CONSISTENCY_CASES), "cases")
+    print("consistency:", len(cases), "cases")
 
 
 # --------------------------------------------------------------------------------------
@@ -728,6 +740,9 @@ def make_diagnostics() -> None:
 
 
 if __name__ == "__main__":
+    if "--only-consistency" in sys.argv:
+        make_consistency()
+        sys.exit(0)
     if "--only-diagnostics" in sys.argv:
         make_diagnostics()
         sys.exit(0)

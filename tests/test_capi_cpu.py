@@ -178,3 +178,29 @@ def test_epoch_invalidation_on_attribute_assignment():
     before = lattice_epoch()
     quad.to(torch.float64)
     assert lattice_epoch() > before and quad.k1.dtype == torch.float64
+
+
+def test_segment_container_helpers_mirror_the_reference():
+    """segment.py:73-229, :599-629: names, index, subcell, reversed, partition_at."""
+    t = torch.tensor
+    segment = cb.Segment([
+        cb.Drift(length=t(1.0), name="d1"), cb.Quadrupole(length=t(0.2), k1=t(1.0), name="q1"),
+        cb.Marker(name="m"), cb.Drift(length=t(0.5), name="d2"),
+    ], name="cell")
+    assert segment.element_names == ["d1", "q1", "m", "d2"]
+    assert segment.element_index("q1") == 1
+    with pytest.raises(ValueError, match="not found in segment"):
+        segment.element_index("nope")
+    assert segment.subcell("q1", "m").element_names == ["q1", "m"]
+    assert segment.subcell(end="q1", include_end=False).element_names == ["d1"]
+    assert segment.subcell(start="m", include_start=False).element_names == ["d2"]
+    with pytest.raises(ValueError, match="not part of the segment"):
+        segment.subcell(start="nope")
+    assert segment.reversed().element_names == ["d2", "m", "q1", "d1"]
+    pre, element, post = segment.partition_at("q1")
+    assert pre.element_names == ["d1"] and element.name == "q1" and post.element_names == ["m", "d2"]
+    pre, post = segment.partition_at("q1", mode="before")
+    assert pre.element_names == ["d1"] and post.element_names == ["q1", "m", "d2"]
+    with pytest.raises(AssertionError, match="not skippable"):
+        cb.CustomTransferMap.from_merging_elements(
+            [cb.Drift(length=t(1.0), tracking_method="drift_kick_drift")], incoming_beam=None)

@@ -344,3 +344,72 @@ def test_active_cavity_against_reference_outputs(case, tag, dtype):
     assert torch.equal(
         out.survival_probabilities.cpu().double()[..., rows], truth["survival_probabilities"]
     )
+
+
+def test_transfer_maps_merged_and_beam_along_segment():
+    """Segment.transfer_maps_merged / CustomTransferMap.from_merging_elements /
+    beam_along_segment_generator (segment.py:179-229, :631-656, custom_transfer_map.py:60-109)."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE, dtype=torch.float64)  # noqa: E731
+    segment = cb.Segment([
+        cb.Drift(length=t(0.5), name="d1"),
+        cb.Quadrupole(length=t(0.2), k1=t(4.0), tilt=t(0.1), name="q1"),
+        cb.Drift(length=t(0.3), name="d2"),
+        cb.Aperture(x_max=t(3e-4), y_max=t(3e-4), name="a1"),
+        cb.HorizontalCorrector(length=t(0.1), angle=t(2e-4), name="h1"),
+        cb.Quadrupole(length=t(0.2), k1=t(-4.0), name="q2"),
+        cb.Drift(length=t(0.7), name="d3"),
+    ])
+    torch.manual_seed(1)
+    beam = cb.ParticleBeam.from_parameters(num_particles=20_000, device=DEVICE, dtype=torch.float64)
+    expected = segment.track(beam)
+    merged = segment.transfer_maps_merged(beam)
+    assert [type(e).__name__ for e in merged.elements] == [
+        "CustomTransferMap", "Aperture", "CustomTransferMap"]
+    assert merged.elements[0].name == "combined_d1_q1_d2"
+    assert torch.allclose(merged.elements[0].length, t(1.0))
+    out = merged.track(beam)
+    assert torch.allclose(out.particles, expected.particles, rtol=1e-12, atol=1e-18)
+    assert torch.equal(out.survival_probabilities, expected.survival_probabilities)
+    assert torch.allclose(out.s, expected.s)
+    kept = segment.transfer_maps_merged(beam, except_for=["q2"])
+    # like the reference, a trailing run is wrapped even when it holds a single element
+    assert [e.name for e in kept.elements] == ["combined_d1_q1_d2", "a1", "h1", "q2", "combined_d3"]
+    assert torch.allclose(kept.track(beam).particles, expected.particles, rtol=1e-12, atol=1e-18)
+    beams = list(segment.beam_along_segment_generator(beam))
+    assert len(beams) == len(segment.elements) + 1 and beams[0] is beam
+    assert torch.allclose(beams[-1].particles, expected.particles, rtol=1e-11, atol=1e-17)
+    assert torch.allclose(torch.stack([b.s for b in beams])[-1], expected.s)
+
+
+def test_superimposed_and_split_against_the_reference_pickle():
+    """cheetah/accelerator/superimposed.py: a BPM at the centre of a quadrupole (the reference's
+    Superimposed_ParticleBeam_default.pkl), and Segment.beam_along_segment_generator(resolution)."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE, dtype=torch.float64)  # noqa: E731
+    incoming = gu.product_beam(gu.beam_dict(CONSISTENCY, "incoming"), DEVICE, torch.float64)
+    element = cb.Superimposed(
+        base_element=cb.Quadrupole(length=t(1.0), k1=t(0.5)),
+        superimposed_element=cb.BPM(misalignment=t([0.0, 0.0])), name="default",
+    )
+    assert [type(e).__name__ for e in element.flattened().elements] == [
+        "Quadrupole", "BPM", "Quadrupole"]
+    out = element.track(incoming)
+    rows = slice(None, None, ROW_STRIDE)
+    expected = gu.beam_dict(CONSISTENCY, "Superimposed_default.expected")
+    assert torch.allclose(out.particles.cpu()[..., rows, :], expected["particles"])
+    assert torch.allclose(out.s.cpu(), expected["s"])
+    assert torch.allclose(
+        element.first_order_transfer_map(incoming.energy, incoming.species),
+        cb.Quadrupole(length=t(1.0), k1=t(0.5)).first_order_transfer_map(
+            incoming.energy, incoming.species), rtol=1e-12, atol=1e-15)
+    segment = cb.Segment([cb.Drift(length=t(1.0)), element, cb.Solenoid(length=t(0.5), k=t(0.3),
+                                                                        misalignment=t([0.0, 0.0]))])
+    beams = list(segment.beam_along_segment_generator(incoming, resolution=0.3))
+    # 4 drift slices + the Superimposed (not splittable, element.py:338-347) + 2 solenoid slices
+    assert len(beams) == 1 + 4 + 1 + 2
+    assert torch.allclose(beams[-1].particles, segment.track(incoming).particles,
+                          rtol=1e-10, atol=1e-16)
+    assert torch.allclose(beams[-1].s, t(2.5))
