@@ -1,18 +1,23 @@
 // Map composition: builds every first-order map of a lattice section from the vectorised
 // element parameters and multiplies them into the cumulative maps ch_apply_maps consumes.
 //
-// One CTA per lattice setting, two phases per chunk of <= 256 elements:
-//   A (all threads, one element each): read the element's parameters through the slot
-//     table and reduce them, in fp64 with closed real forms, to <= 16 coefficients
-//     (cos/sin-like terms, r56, edge kicks, tilt rotation, misalignment shifts).  This is
-//     where all memory latency and all transcendental math lives, fully parallel.
-//   B (8 lanes of warp 0): left-multiplying by an element map acts on the 7 columns of the
-//     cumulative map independently, so lane j owns column j (6 fp64 registers) and applies
-//     each element as 3-20 FMAs with coefficients broadcast from shared memory; lane 7
-//     accumulates the section length.  A drift costs 3 dependent FMAs per lane.
-// Cut points (apertures, section end) snapshot the cumulative map into the per-setting
-// record, rounded ONCE from fp64 to the beam dtype -- closer to the fp64 truth than the
+// One CTA (256 threads) per lattice setting; per chunk of <= 256 elements:
+//   A (one element per thread): read the element's parameters through the slot table and
+//     reduce them, in fp64 with closed real forms, to <= 16 coefficients (cos/sin-like terms,
+//     r56, edge kicks, tilt rotation, misalignment shifts).  All memory latency and all
+//     transcendental math lives here, fully parallel.
+//   B1 (32 groups of 8 lanes, 8 consecutive elements each): left-multiplying by an element map
+//     acts on the 7 columns of a map independently, so lane j of a group owns column j of the
+//     group's product (6 fp64 registers) and applies each element as 3-20 FMAs with
+//     coefficients broadcast from shared memory; lane 7 sums the lengths.  All groups run at
+//     once: 8 dependent steps instead of 256.
+//   B2 (7 lanes): the exclusive prefix over the <= 32 group products, again column-wise (36
+//     FMAs per lane and group, no communication between lanes).
+//   B3: cut points (apertures, an active cavity) recorded in B1 relative to their group are
+//     multiplied by the prefix of the groups before them and written to the record.
+// Snapshots are rounded ONCE from fp64 to the beam dtype -- closer to the fp64 truth than the
 // reference's chain of fp32 7x7 products (BASELINE.md section 2 noise-floor figures).
+// Latency for ARES (195 elements) at one setting: 46 us with the serial walk -> see DESIGN.md.
 //
 // Reference behaviour restated here (desy-ml/cheetah @ 60d1053):
 //   cheetah/track_methods.py:17-77      base_rmatrix (quadrupole / sector-bend body)
@@ -33,7 +38,10 @@ namespace {
 constexpr int kChunk = 256;      // elements per shared-memory chunk
 constexpr int kCoef = 16;        // fp64 coefficients per element
 constexpr int kLengthSlot = 15;  // coefficient index that always holds the element length
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
+constexpr int kGroup = 8;                  // elements per group (phase B1)
+constexpr int kGroups = kChunk / kGroup;   // 32 groups = 256 threads of 8 lanes
+constexpr int kMaxCuts = CH_MAX_APERTURES + 1;  // apertures + one active cavity per section
 constexpr uint32_t kAllFlags = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
                                CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
 
@@ -379,11 +387,101 @@ __device__ __forceinline__ double pack_flags<double>(uint32_t f) {
   return __longlong_as_double(static_cast<long long>(f));
 }
 
-__device__ __forceinline__ uint32_t and_over_group(uint32_t f) {
-  f &= __shfl_xor_sync(0xffu, f, 1);
-  f &= __shfl_xor_sync(0xffu, f, 2);
-  f &= __shfl_xor_sync(0xffu, f, 4);
-  return f;
+
+// Apply the map of one element to this lane's column (CH_OP_APERTURE and the snapshot part of
+// CH_OP_CAVITY are handled by the caller).  `one` is 1.0 on lane 6 (the affine column).
+__device__ __forceinline__ void apply_element_to_column(const Program& prog, int32_t op,
+                                                        int32_t code, const double* c, int64_t b,
+                                                        double* v, double one) {
+  switch (code) {
+    case CH_OP_DRIFT:
+    case CH_OP_CAVITY_OFF:
+      v[0] = fma(c[0], v[1], v[0]);
+      v[2] = fma(c[0], v[3], v[2]);
+      v[4] = fma(c[1], v[5], v[4]);
+      break;
+    case CH_OP_CORRECTOR:
+      v[0] = fma(c[0], v[1], v[0]);
+      v[2] = fma(c[0], v[3], v[2]);
+      v[4] = fma(c[1], v[5], v[4]);
+      v[1] = fma(c[2], one, v[1]);
+      v[3] = fma(c[3], one, v[3]);
+      break;
+    case CH_OP_QUADRUPOLE:
+      if (c[1] != 0.0 || c[0] != 1.0) rotate_column(v, c[0], c[1]);
+      v[0] = fma(c[2], one, v[0]);
+      v[2] = fma(c[3], one, v[2]);
+      apply_body_column(v, c, false);
+      if (c[1] != 0.0 || c[0] != 1.0) rotate_column(v, c[0], -c[1]);
+      v[0] = fma(c[13], one, v[0]);
+      v[2] = fma(c[14], one, v[2]);
+      break;
+    case CH_OP_DIPOLE:
+      if (c[1] != 0.0 || c[0] != 1.0) rotate_column(v, c[0], c[1]);
+      v[1] = fma(c[2], v[0], v[1]);
+      v[3] = fma(c[3], v[2], v[3]);
+      apply_body_column(v, c, true);
+      v[1] = fma(c[13], v[0], v[1]);
+      v[3] = fma(c[14], v[2], v[3]);
+      if (c[1] != 0.0 || c[0] != 1.0) rotate_column(v, c[0], -c[1]);
+      break;
+    case CH_OP_SOLENOID: {
+      v[0] = fma(-c[0], one, v[0]);
+      v[2] = fma(-c[1], one, v[2]);
+      v[4] = fma(c[8], v[5], v[4]);
+      const double r0 = v[0], r1 = v[1], r2 = v[2], r3 = v[3];
+      v[0] = c[2] * r0 + c[3] * r1 + c[4] * r2 + c[5] * r3;
+      v[1] = -c[6] * r0 + c[2] * r1 - c[7] * r2 + c[4] * r3;
+      v[2] = -c[4] * r0 - c[5] * r1 + c[2] * r2 + c[3] * r3;
+      v[3] = c[7] * r0 - c[4] * r1 - c[6] * r2 + c[2] * r3;
+      v[0] = fma(c[0], one, v[0]);
+      v[2] = fma(c[1], one, v[2]);
+      break;
+    }
+    case CH_OP_UNDULATOR:
+      v[4] = fma(c[0], v[5], v[4]);
+      mix(v[0], v[1], c[1], c[2], c[3], c[1]);
+      mix(v[2], v[3], c[4], c[5], c[6], c[4]);
+      break;
+    case CH_OP_CUSTOM_MAP: {
+      // dense user map: read straight from the parameter tensor (rare, latency-tolerant)
+      const ScalarRef ref = prog.slots[prog.slot_begin[op]];
+      double w[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double acc = one * load_scalar(ref.ptr, b * ref.stride + r * 7 + 6, ref.dtype);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          acc = fma(load_scalar(ref.ptr, b * ref.stride + r * 7 + k, ref.dtype), v[k], acc);
+        w[r] = acc;
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) v[r] = w[r];
+      break;
+    }
+    case CH_OP_CAVITY:
+      mix(v[0], v[1], c[0], c[1], c[2], c[3]);
+      mix(v[2], v[3], c[0], c[1], c[2], c[3]);
+      mix(v[4], v[5], c[4], c[5], c[6], c[7]);
+      break;
+    default:
+      break;
+  }
+}
+
+// w = G . v for one column v of a 7x7 affine map (row 6 of G is 0 0 0 0 0 0 1), G row-major 6x7
+// in shared memory; `one` is 1.0 for the affine column.
+__device__ __forceinline__ void left_multiply_column(const double* g, double* v, double one) {
+  double w[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double acc = g[r * 7 + 6] * one;
+#pragma unroll
+    for (int k = 5; k >= 0; --k) acc = fma(g[r * 7 + k], v[k], acc);
+    w[r] = acc;
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) v[r] = w[r];
 }
 
 template <typename T>
@@ -391,12 +489,21 @@ __global__ void __launch_bounds__(kThreads)
 compose_maps_kernel(Program prog, int32_t op_begin, int32_t op_end, ScalarRef energy,
                     ScalarRef mass, ScalarRef charge, int32_t n_apertures, T* __restrict__ records,
                     int64_t record_len) {
-  __shared__ double coef[kChunk][kCoef];
+  extern __shared__ __align__(16) unsigned char compose_smem[];
+  double (*coef)[kCoef] = reinterpret_cast<double (*)[kCoef]>(compose_smem);  // [kChunk][kCoef]
   __shared__ int32_t codes[kChunk];
+  __shared__ int32_t warp_cuts[kThreads / 32];
+  __shared__ double group_map[kGroups][44];       // 6x7 product of a group, [42] = its length
+  __shared__ double prefix_map[kGroups + 1][42];  // product of all groups BEFORE group g
+  __shared__ double cut_rows[kMaxCuts][2][8];     // two rows of the group-partial map at a cut
+  __shared__ int32_t cut_element[kMaxCuts];       // element index (in the chunk) of each cut
+  __shared__ int32_t n_cuts_shared;
+  __shared__ uint32_t flags_shared;
 
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
-  const int lane = tid;  // only meaningful for tid < 8
+  const int lane = tid & 7;     // column owned inside a group (7: length accumulator)
+  const int group = tid >> 3;
 
   Relativistic rel;
   const double mass_value = load_scalar(mass.ptr, 0, mass.dtype);
@@ -409,170 +516,163 @@ compose_maps_kernel(Program prog, int32_t op_begin, int32_t op_end, ScalarRef en
     rel.beta = sqrt(1.0 - rel.igamma2);
   }
 
-  double v[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) v[i] = (i == lane) ? 1.0 : 0.0;
-  const double one = (lane == 6) ? 1.0 : 0.0;
-  double total_length = 0.0;  // lane 7: s_out = s_in + sum of lengths (element.py:183)
-  uint32_t flags = kAllFlags;
-
   T* rec = records + b * record_len;
   T* aperture_rec = rec + CH_RECORD_HEADER + CH_RECORD_MAP;
+  T* cavity_rec = aperture_rec + n_apertures * CH_RECORD_APERTURE;
+  const double one = (lane == 6) ? 1.0 : 0.0;
+
+  // running product of everything before the current chunk, column `tid` held by thread tid < 7
+  double cum[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cum[i] = (i == tid) ? 1.0 : 0.0;
+  double total_length = 0.0;  // thread 7
+  int32_t apertures_done = 0;
+  if (tid == 0) flags_shared = kAllFlags;
 
   for (int32_t chunk = op_begin; chunk < op_end; chunk += kChunk) {
     const int32_t n = min(kChunk, op_end - chunk);
-    for (int32_t i = tid; i < n; i += kThreads) {
-      codes[i] = prog.opcodes[chunk + i];
-      element_coefficients(prog, chunk + i, b, rel, mass_value, charge_value, coef[i]);
+    // ---- A: coefficients; cut points in element order --------------------------------------
+    if (tid < n) {
+      codes[tid] = prog.opcodes[chunk + tid];
+      element_coefficients(prog, chunk + tid, b, rel, mass_value, charge_value, coef[tid]);
+    }
+    {  // ordered list of the cut elements: ballot inside a warp, prefix over the warp totals
+      const bool is_cut =
+          tid < n && (codes[tid] == CH_OP_APERTURE || codes[tid] == CH_OP_CAVITY);
+      const uint32_t mask = __ballot_sync(0xffffffffu, is_cut);
+      if ((tid & 31) == 0) warp_cuts[tid >> 5] = __popc(mask);
+      __syncthreads();
+      int32_t before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) {
+        const int32_t count = warp_cuts[w];
+        if (w < (tid >> 5)) before += count;
+        total += count;
+      }
+      if (is_cut) cut_element[before + __popc(mask & ((1u << (tid & 31)) - 1u))] = tid;
+      if (tid == 0) n_cuts_shared = total;
     }
     __syncthreads();
+    const int32_t n_cuts = n_cuts_shared;
 
-    if (tid < 8) {
-      for (int32_t i = 0; i < n; ++i) {
+    // ---- B1: product of each group of 8 elements, column per lane ---------------------------
+    {
+      double v[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) v[i] = (i == lane) ? 1.0 : 0.0;
+      double group_length = 0.0;
+      const int32_t first = group * kGroup;
+      int32_t cut = 0;  // ordinal of the next cut at or after `first`
+      while (cut < n_cuts && cut_element[cut] < first) ++cut;
+      for (int32_t i = first; i < min(first + kGroup, n); ++i) {
         const double* c = coef[i];
         const int32_t code = codes[i];
-        total_length += c[kLengthSlot];
-        switch (code) {
-          case CH_OP_DRIFT:
-          case CH_OP_CAVITY_OFF:
-            v[0] = fma(c[0], v[1], v[0]);
-            v[2] = fma(c[0], v[3], v[2]);
-            v[4] = fma(c[1], v[5], v[4]);
-            break;
-          case CH_OP_CORRECTOR:
-            v[0] = fma(c[0], v[1], v[0]);
-            v[2] = fma(c[0], v[3], v[2]);
-            v[4] = fma(c[1], v[5], v[4]);
-            v[1] = fma(c[2], one, v[1]);
-            v[3] = fma(c[3], one, v[3]);
-            break;
-          case CH_OP_QUADRUPOLE:
-            if (c[1] != 0.0 || c[0] != 1.0) rotate_column(v, c[0], c[1]);
-            v[0] = fma(c[2], one, v[0]);
-            v[2] = fma(c[3], one, v[2]);
-            apply_body_column(v, c, false);
-            if (c[1] != 0.0 || c[0] != 1.0) rotate_column(v, c[0], -c[1]);
-            v[0] = fma(c[13], one, v[0]);
-            v[2] = fma(c[14], one, v[2]);
-            break;
-          case CH_OP_DIPOLE:
-            if (c[1] != 0.0 || c[0] != 1.0) rotate_column(v, c[0], c[1]);
-            v[1] = fma(c[2], v[0], v[1]);
-            v[3] = fma(c[3], v[2], v[3]);
-            apply_body_column(v, c, true);
-            v[1] = fma(c[13], v[0], v[1]);
-            v[3] = fma(c[14], v[2], v[3]);
-            if (c[1] != 0.0 || c[0] != 1.0) rotate_column(v, c[0], -c[1]);
-            break;
-          case CH_OP_SOLENOID: {
-            v[0] = fma(-c[0], one, v[0]);
-            v[2] = fma(-c[1], one, v[2]);
-            v[4] = fma(c[8], v[5], v[4]);
-            const double r0 = v[0], r1 = v[1], r2 = v[2], r3 = v[3];
-            v[0] = c[2] * r0 + c[3] * r1 + c[4] * r2 + c[5] * r3;
-            v[1] = -c[6] * r0 + c[2] * r1 - c[7] * r2 + c[4] * r3;
-            v[2] = -c[4] * r0 - c[5] * r1 + c[2] * r2 + c[3] * r3;
-            v[3] = c[7] * r0 - c[4] * r1 - c[6] * r2 + c[2] * r3;
-            v[0] = fma(c[0], one, v[0]);
-            v[2] = fma(c[1], one, v[2]);
-            break;
+        group_length += c[kLengthSlot];
+        if (code == CH_OP_APERTURE || code == CH_OP_CAVITY) {
+          // rows (x, y) at an aperture, (tau, delta) at a cavity entrance, relative to the group
+          const int r0 = code == CH_OP_APERTURE ? 0 : 4, r1 = code == CH_OP_APERTURE ? 2 : 5;
+          if (lane < 7) {
+            cut_rows[cut][0][lane] = v[r0];
+            cut_rows[cut][1][lane] = v[r1];
           }
-          case CH_OP_UNDULATOR:
-            v[4] = fma(c[0], v[5], v[4]);
-            mix(v[0], v[1], c[1], c[2], c[3], c[1]);
-            mix(v[2], v[3], c[4], c[5], c[6], c[4]);
-            break;
-          case CH_OP_CUSTOM_MAP: {
-            // dense user map: read straight from the parameter tensor (rare, latency-tolerant)
-            const ScalarRef ref = prog.slots[prog.slot_begin[chunk + i]];
-            double w[6];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-              double acc = one * load_scalar(ref.ptr, b * ref.stride + r * 7 + 6, ref.dtype);
-#pragma unroll
-              for (int k = 0; k < 6; ++k)
-                acc = fma(load_scalar(ref.ptr, b * ref.stride + r * 7 + k, ref.dtype), v[k], acc);
-              w[r] = acc;
-            }
-#pragma unroll
-            for (int r = 0; r < 6; ++r) v[r] = w[r];
-            break;
-          }
-          case CH_OP_CAVITY: {
-            // snapshot the rows (tau, delta) at the cavity entrance + the non-linear tail
-            T* block = rec + CH_RECORD_HEADER + CH_RECORD_MAP + n_apertures * CH_RECORD_APERTURE;
-            if (lane < 7) {
-              block[lane] = static_cast<T>(v[4]);
-              block[7 + lane] = static_cast<T>(v[5]);
-            } else {
-              double sphi, cphi;
-              sincos(c[11], &sphi, &cphi);
-              block[14] = static_cast<T>(c[8]);
-              block[15] = static_cast<T>(c[9]);
-              block[16] = static_cast<T>(c[10]);
-              block[17] = static_cast<T>(sphi);
-              block[18] = static_cast<T>(cphi);
-              block[19] = static_cast<T>(c[12]);
-              block[20] = static_cast<T>(c[13]);
-              block[21] = static_cast<T>(c[14]);
-              block[22] = block[23] = T(0);
-            }
-            mix(v[0], v[1], c[0], c[1], c[2], c[3]);
-            mix(v[2], v[3], c[0], c[1], c[2], c[3]);
-            mix(v[4], v[5], c[4], c[5], c[6], c[7]);
-            break;
-          }
-          case CH_OP_APERTURE: {
-            uint32_t f = kAllFlags;
-            if (lane < 7) {
-              const T x = static_cast<T>(v[0]);
-              const T y = static_cast<T>(v[2]);
-              aperture_rec[lane] = x;
-              aperture_rec[7 + lane] = y;
-              if ((lane == 2 || lane == 3) && x != T(0)) f &= ~CH_FLAG_XY_UNCOUPLED;
-              if ((lane == 0 || lane == 1) && y != T(0)) f &= ~CH_FLAG_XY_UNCOUPLED;
-              if (lane == 4 && (x != T(0) || y != T(0))) f &= ~CH_FLAG_NO_TAU_COLUMN;
-              if (lane == 5 && y != T(0)) f &= ~CH_FLAG_NO_Y_DISPERSION;
-            } else {
-              aperture_rec[14] = static_cast<T>(c[0]);
-              aperture_rec[15] = static_cast<T>(c[1]);
-            }
-            flags &= f;
-            aperture_rec += CH_RECORD_APERTURE;
-            break;
-          }
-          default:
-            break;
+          ++cut;
         }
+        if (code != CH_OP_APERTURE) apply_element_to_column(prog, chunk + i, code, c, b, v, one);
+      }
+      if (lane < 7) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) group_map[group][r * 7 + lane] = v[r];
+      } else {
+        group_map[group][42] = group_length;
       }
     }
     __syncthreads();
+
+    // ---- B2: exclusive prefix over the groups (thread c < 7 owns column c) -------------------
+    const int32_t n_groups = (n + kGroup - 1) / kGroup;
+    if (tid < 7) {
+      const double one_c = (tid == 6) ? 1.0 : 0.0;
+      for (int32_t g = 0; g < n_groups; ++g) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) prefix_map[g][r * 7 + tid] = cum[r];
+        left_multiply_column(group_map[g], cum, one_c);
+      }
+    } else if (tid == 7) {
+      for (int32_t g = 0; g < n_groups; ++g) total_length += group_map[g][42];
+    }
+    __syncthreads();
+
+    // ---- B3: cut snapshots = (rows relative to the group) . (prefix of the groups before) ------
+    for (int32_t task = tid; task < n_cuts * 16; task += kThreads) {
+      const int32_t cut = task >> 4, slot = task & 15;
+      const int32_t element = cut_element[cut];
+      const int32_t code = codes[element];
+      const double* c = coef[element];
+      // aperture ordinal within the section: cuts of this chunk before it that are apertures
+      int32_t ordinal = apertures_done;
+      for (int32_t k = 0; k < cut; ++k) ordinal += codes[cut_element[k]] == CH_OP_APERTURE;
+      T* block = code == CH_OP_APERTURE ? aperture_rec + ordinal * CH_RECORD_APERTURE : cavity_rec;
+      if (slot < 14) {
+        const int row = slot / 7, col = slot - row * 7;
+        const double* p = cut_rows[cut][row];
+        const double* pre = prefix_map[element / kGroup];
+        double acc = (col == 6) ? p[6] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc = fma(p[k], pre[k * 7 + col], acc);
+        const T value = static_cast<T>(acc);
+        block[slot] = value;
+        if (code == CH_OP_APERTURE) {
+          uint32_t f = kAllFlags;
+          const bool is_x = row == 0;
+          if (is_x && (col == 2 || col == 3) && value != T(0)) f &= ~CH_FLAG_XY_UNCOUPLED;
+          if (!is_x && (col == 0 || col == 1) && value != T(0)) f &= ~CH_FLAG_XY_UNCOUPLED;
+          if (col == 4 && value != T(0)) f &= ~CH_FLAG_NO_TAU_COLUMN;
+          if (!is_x && col == 5 && value != T(0)) f &= ~CH_FLAG_NO_Y_DISPERSION;
+          if (f != kAllFlags) atomicAnd(&flags_shared, f);
+        }
+      } else if (code == CH_OP_APERTURE) {
+        block[slot] = static_cast<T>(c[slot - 14]);  // x_max, y_max
+      } else if (slot == 14) {  // cavity constants (cavity.py:113-220), see the record layout
+        double sphi, cphi;
+        sincos(c[11], &sphi, &cphi);
+        block[14] = static_cast<T>(c[8]);
+        block[15] = static_cast<T>(c[9]);
+        block[16] = static_cast<T>(c[10]);
+        block[17] = static_cast<T>(sphi);
+        block[18] = static_cast<T>(cphi);
+        block[19] = static_cast<T>(c[12]);
+        block[20] = static_cast<T>(c[13]);
+        block[21] = static_cast<T>(c[14]);
+        block[22] = block[23] = T(0);
+      }
+    }
+    for (int32_t k = 0; k < n_cuts; ++k) apertures_done += codes[cut_element[k]] == CH_OP_APERTURE;
+    __syncthreads();  // shared tables are rebuilt by the next chunk
   }
 
-  if (tid < 8) {
+  // ---- final map, flags, length ----------------------------------------------------------------
+  if (tid < 7) {
     uint32_t f = kAllFlags;
-    if (lane < 7) {
-      T w[6];
+    T w[6];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        w[r] = static_cast<T>(v[r]);
-        rec[CH_RECORD_HEADER + r * 7 + lane] = w[r];
-      }
-      const bool z01 = w[0] != T(0) || w[1] != T(0);
-      const bool z23 = w[2] != T(0) || w[3] != T(0);
-      if ((lane == 2 || lane == 3) && z01) f &= ~CH_FLAG_XY_UNCOUPLED;
-      if ((lane == 0 || lane == 1) && z23) f &= ~CH_FLAG_XY_UNCOUPLED;
-      if (lane == 4 && (z01 || z23 || w[5] != T(0))) f &= ~CH_FLAG_NO_TAU_COLUMN;
-      if (w[5] != ((lane == 5) ? T(1) : T(0))) f &= ~CH_FLAG_DELTA_IDENTITY;
-      if (lane == 5 && z23) f &= ~CH_FLAG_NO_Y_DISPERSION;
-      if ((lane == 2 || lane == 3) && w[4] != T(0)) f &= ~CH_FLAG_NO_Y_DISPERSION;
+    for (int r = 0; r < 6; ++r) {
+      w[r] = static_cast<T>(cum[r]);
+      rec[CH_RECORD_HEADER + r * 7 + tid] = w[r];
     }
-    flags = and_over_group(flags & f);
-    if (lane == 7) {
-      rec[0] = pack_flags<T>(flags);
-      rec[1] = static_cast<T>(total_length);
-    }
+    const bool z01 = w[0] != T(0) || w[1] != T(0);
+    const bool z23 = w[2] != T(0) || w[3] != T(0);
+    if ((tid == 2 || tid == 3) && z01) f &= ~CH_FLAG_XY_UNCOUPLED;
+    if ((tid == 0 || tid == 1) && z23) f &= ~CH_FLAG_XY_UNCOUPLED;
+    if (tid == 4 && (z01 || z23 || w[5] != T(0))) f &= ~CH_FLAG_NO_TAU_COLUMN;
+    if (w[5] != ((tid == 5) ? T(1) : T(0))) f &= ~CH_FLAG_DELTA_IDENTITY;
+    if (tid == 5 && z23) f &= ~CH_FLAG_NO_Y_DISPERSION;
+    if ((tid == 2 || tid == 3) && w[4] != T(0)) f &= ~CH_FLAG_NO_Y_DISPERSION;
+    if (f != kAllFlags) atomicAnd(&flags_shared, f);
+  } else if (tid == 7) {
+    rec[1] = static_cast<T>(total_length);
   }
+  __syncthreads();
+  if (tid == 0) rec[0] = pack_flags<T>(flags_shared);
 }
 
 }  // namespace
@@ -605,11 +705,16 @@ extern "C" int ch_compose_maps(const ch_program* program, int32_t op_begin, int3
       (extra % CH_RECORD_APERTURE == 0 ? extra : extra - CH_RECORD_CAVITY) / CH_RECORD_APERTURE);
   const unsigned blocks = static_cast<unsigned>(n_settings);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int smem = ch::kChunk * ch::kCoef * sizeof(double);  // + ~27 KB static: opt in above 48 KB
   if (record_dtype == CH_F32) {
-    ch::compose_maps_kernel<float><<<blocks, ch::kThreads, 0, s>>>(
+    CH_CUDA(cudaFuncSetAttribute(ch::compose_maps_kernel<float>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ch::compose_maps_kernel<float><<<blocks, ch::kThreads, smem, s>>>(
         prog, op_begin, op_end, e, m, q, n_apertures, static_cast<float*>(records), record_len);
   } else {
-    ch::compose_maps_kernel<double><<<blocks, ch::kThreads, 0, s>>>(
+    CH_CUDA(cudaFuncSetAttribute(ch::compose_maps_kernel<double>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ch::compose_maps_kernel<double><<<blocks, ch::kThreads, smem, s>>>(
         prog, op_begin, op_end, e, m, q, n_apertures, static_cast<double*>(records), record_len);
   }
   CH_LAUNCH_CHECK();
