@@ -272,7 +272,11 @@ def dtype_code(dtype: torch.dtype) -> int:
 
 
 def current_stream(device: torch.device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream on ``device`` (fast path, no Stream object)."""
+    index = device.index
+    if index is None:
+        index = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(index)
 
 
 def launch_count() -> int:

@@ -76,6 +76,23 @@ class ParticleBeam(Beam):
         # None = unknown; the tracker checks once whether particles[..., 6] == 1 and caches it
         self._unit_seventh: bool | None = None
 
+    @classmethod
+    def _from_tracking(cls, particles, energy, particle_charges, survival_probabilities, s,
+                       species, unit_seventh=None) -> "ParticleBeam":
+        """Constructor used by the tracker for outgoing beams: same object as ``__init__`` builds,
+        without its argument checks and ``register_buffer`` bookkeeping (~60 us per call)."""
+        beam = cls.__new__(cls)
+        nn.Module.__init__(beam)
+        beam._modules["species"] = species
+        buffers = beam._buffers
+        buffers["particles"] = particles
+        buffers["energy"] = energy
+        buffers["particle_charges"] = particle_charges
+        buffers["survival_probabilities"] = survival_probabilities
+        buffers["s"] = s
+        object.__setattr__(beam, "_unit_seventh", unit_seventh)
+        return beam
+
     # ---- set-up helpers (host-side convenience, not part of the accelerated path) --------
     @classmethod
     def from_distribution(

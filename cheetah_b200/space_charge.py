@@ -13,6 +13,7 @@ import math
 import torch
 
 from . import _capi
+from .tracking import _bshape, _new_beam
 
 
 def _flat(tensor: torch.Tensor, vector_shape: tuple, inner: tuple, dtype) -> tuple:
@@ -144,7 +145,7 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
                 f"{tuple(grid_shape)}"
             )
 
-    vector_shape = torch.broadcast_shapes(
+    vector_shape = _bshape(
         particles.shape[:-2], energy.shape, charges.shape[:-1], survival.shape[:-1],
         effect_length.shape, *(e.shape for e in extents), (1,),
     )
@@ -248,7 +249,7 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
 
 def kick_vector_shape(element, incoming) -> tuple:
     """Vector shape one kick works on (space_charge_kick.py:493-528, without the (1,) helper)."""
-    return tuple(torch.broadcast_shapes(
+    return tuple(_bshape(
         incoming.particles.shape[:-2], incoming.energy.shape,
         incoming.particle_charges.shape[:-1], incoming.survival_probabilities.shape[:-1],
         element.effect_length.shape, element.grid_extent_x.shape, element.grid_extent_y.shape,
@@ -287,21 +288,17 @@ def track_fused(element, incoming, prepared: Prepared | None = None, fuse_record
         next_element=next_element,
     )
     # the reference drops the (1,) helper dimension again when nothing is vectorised
-    out_shape = torch.broadcast_shapes(
+    out_shape = _bshape(
         particles.shape[:-2], incoming.energy.shape, incoming.particle_charges.shape[:-1],
         incoming.survival_probabilities.shape[:-1], element.effect_length.shape,
         element.grid_extent_x.shape, element.grid_extent_y.shape, element.grid_extent_tau.shape,
     )
     out = out.reshape(*out_shape, particles.shape[-2], 7)
-    outgoing = incoming.__class__(
-        out, incoming.energy, particle_charges=incoming.particle_charges,
-        survival_probabilities=incoming.survival_probabilities, s=incoming.s,
-        species=incoming.species,
+    outgoing = _new_beam(
+        incoming, out, incoming.energy, incoming.particle_charges,
+        incoming.survival_probabilities, incoming.s, incoming.species,
+        getattr(incoming, "_unit_seventh", None),
     )
-    try:
-        outgoing._unit_seventh = getattr(incoming, "_unit_seventh", None)
-    except Exception:
-        pass
     return outgoing, ws.prepared_next
 
 

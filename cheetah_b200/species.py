@@ -70,12 +70,14 @@ class Species(nn.Module):
         return self.num_elementary_charges * ELEMENTARY_CHARGE
 
     def clone(self) -> "Species":
-        """Copy of the species (device-side tensor clones only: CUDA-graph capturable)."""
+        """New ``Species`` object for an outgoing beam (element.py:190).  The two scalar tensors
+        are SHARED with the original instead of copied: nothing in this package modifies them in
+        place, and two device-side copies per tracked section are pure launch overhead."""
         copy = self.__class__.__new__(self.__class__)
         nn.Module.__init__(copy)
-        copy.name = self.name
-        copy.register_buffer("num_elementary_charges", self.num_elementary_charges.clone())
-        copy.register_buffer("mass_eV", self.mass_eV.clone())
+        object.__setattr__(copy, "name", self.name)
+        copy._buffers["num_elementary_charges"] = self._buffers["num_elementary_charges"]
+        copy._buffers["mass_eV"] = self._buffers["mass_eV"]
         return copy
 
     def __repr__(self) -> str:

@@ -23,6 +23,37 @@ from .beam import ParameterBeam, ParticleBeam
 apply_events: list | None = None
 
 
+def _bshape(*shapes) -> tuple:
+    """``torch.broadcast_shapes`` for the common cases without its per-call overhead."""
+    result = ()
+    for shape in shapes:
+        shape = tuple(shape)
+        if shape == result or not shape:
+            continue
+        if not result:
+            result = shape
+            continue
+        return tuple(torch.broadcast_shapes(*shapes))
+    return result
+
+
+def _new_beam(like, particles, energy, particle_charges, survival_probabilities, s, species,
+              unit_seventh=None):
+    """Outgoing beam of the same class as ``like`` (the reference's ParticleBeam or ours)."""
+    cls = like.__class__
+    fast = getattr(cls, "_from_tracking", None)
+    if fast is not None:
+        return fast(particles, energy, particle_charges, survival_probabilities, s, species,
+                    unit_seventh)
+    beam = cls(particles, energy, particle_charges=particle_charges,
+               survival_probabilities=survival_probabilities, s=s, species=species)
+    try:
+        beam._unit_seventh = unit_seventh
+    except Exception:
+        pass
+    return beam
+
+
 def _is_particle_beam(beam) -> bool:
     return type(beam).__name__ == "ParticleBeam"
 
@@ -73,7 +104,7 @@ def _compose(program, section, energy: torch.Tensor, species, dtype):
         element, gain_flag = section.cavity
         delta_energy = element.voltage * element.phase.deg2rad().cos() * charge * -1
         gain_flag.copy_((delta_energy > 0).any())
-    map_shape = tuple(torch.broadcast_shapes(section.lattice_shape, energy.shape))
+    map_shape = tuple(_bshape(section.lattice_shape, energy.shape))
     n_settings = math.prod(map_shape)
     if energy.dtype not in (torch.float32, torch.float64):
         energy = energy.to(dtype)
@@ -167,13 +198,11 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
         ).to(beam.energy.dtype)
 
     if not section.has_maps and section.n_apertures == 0 and moments is None:
-        return beam.__class__(
-            particles, beam.energy, particle_charges=beam.particle_charges,
-            survival_probabilities=beam.survival_probabilities, s=new_s,
-            species=beam.species.clone(),
-        )
+        return _new_beam(beam, particles, beam.energy, beam.particle_charges,
+                         beam.survival_probabilities, new_s, beam.species.clone(),
+                         getattr(beam, "_unit_seventh", None))
 
-    vo = tuple(torch.broadcast_shapes(vm, vp))
+    vo = tuple(_bshape(vm, vp))
     n_out = math.prod(vo)
     if not particles.is_contiguous():
         particles = particles.contiguous()
@@ -194,7 +223,7 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
             survival_in = survival_in.to(dtype).contiguous()
         # the kernel works on the full output batch; the reference's survival tensor only
         # carries the vector dims that reached the last aperture
-        vfull = tuple(torch.broadcast_shapes(vo, vs))
+        vfull = tuple(_bshape(vo, vs))
         if vfull != vo:
             raise NotImplementedError(
                 "survival_probabilities with vector dimensions beyond those of particles and "
@@ -212,7 +241,7 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
         # the sums are weighted with the survival probabilities even without apertures
         if survival_in.dtype != dtype or not survival_in.is_contiguous():
             survival_in = survival_in.to(dtype).contiguous()
-        if tuple(torch.broadcast_shapes(vo, vs)) != vo:
+        if tuple(_bshape(vo, vs)) != vo:
             raise NotImplementedError("survival_probabilities wider than particles and lattice")
         survival_index = _index_table(vs, vo, device)
     common = (
@@ -245,7 +274,7 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
     if survival_out is not None:
         # reference shape: broadcast(survival_in, particles vector dims, everything up to and
         # including the last aperture); later (post-aperture) vectorised elements do not widen it
-        keep = tuple(torch.broadcast_shapes(vs, vp, section.survival_shape, beam.energy.shape))
+        keep = tuple(_bshape(vs, vp, section.survival_shape, beam.energy.shape))
         if keep != vo:
             lead = len(vo) - len(keep)
             index = [0] * lead + [slice(None) if k > 1 else 0 for k in keep]
@@ -254,14 +283,8 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
     else:
         new_survival = beam.survival_probabilities
 
-    outgoing = beam.__class__(
-        out, new_energy, particle_charges=beam.particle_charges,
-        survival_probabilities=new_survival, s=new_s, species=beam.species.clone(),
-    )
-    try:
-        outgoing._unit_seventh = _unit_seventh(beam)
-    except Exception:
-        pass
+    outgoing = _new_beam(beam, out, new_energy, beam.particle_charges, new_survival, new_s,
+                         beam.species.clone(), _unit_seventh(beam))
     return outgoing if moments is None else (outgoing, observed)
 
 
@@ -278,7 +301,7 @@ def _track_nonlinear_run(program, run, beam):
     lib = _capi.lib()
     species = beam.species
     energy = beam.energy
-    vm = tuple(torch.broadcast_shapes(run.lattice_shape, energy.shape))
+    vm = tuple(_bshape(run.lattice_shape, energy.shape))
     n_settings = math.prod(vm)
     if energy.dtype not in (torch.float32, torch.float64):
         energy = energy.to(dtype)
@@ -303,7 +326,7 @@ def _track_nonlinear_run(program, run, beam):
             )
         )
         new_s = beam.s + _section_length(constants, vm, run.length_shape, column=5).to(beam.s.dtype)
-        vo = tuple(torch.broadcast_shapes(vm, vp))
+        vo = tuple(_bshape(vm, vp))
         if not particles.is_contiguous():
             particles = particles.contiguous()
         particle_index = _index_table(vp, vo, device)
@@ -322,15 +345,8 @@ def _track_nonlinear_run(program, run, beam):
         )
     # the reference hands back ref_energy = sqrt(p0c^2 + m^2) == energy up to rounding, the same
     # species object and the untouched charges / survival probabilities
-    outgoing = beam.__class__(
-        out, beam.energy, particle_charges=beam.particle_charges,
-        survival_probabilities=beam.survival_probabilities, s=new_s, species=species,
-    )
-    try:
-        outgoing._unit_seventh = _unit_seventh(beam)
-    except Exception:
-        pass
-    return outgoing
+    return _new_beam(beam, out, beam.energy, beam.particle_charges, beam.survival_probabilities,
+                     new_s, species, _unit_seventh(beam))
 
 
 # Set to False to run every stage as its own pass (tests compare the two paths).
@@ -350,7 +366,7 @@ def _track_space_charge(program, stages: list, i: int, beam, prepared):
         j = i + 1
         if j < len(stages) and isinstance(stages[j], lowering.LinearSection):
             candidate = stages[j]
-            vm = tuple(torch.broadcast_shapes(candidate.lattice_shape, beam.energy.shape))
+            vm = tuple(_bshape(candidate.lattice_shape, beam.energy.shape))
             if (candidate.has_maps and candidate.n_apertures == 0 and candidate.cavity is None
                     and (math.prod(vm) == 1 or vm == vs)):
                 section = candidate
@@ -363,7 +379,7 @@ def _track_space_charge(program, stages: list, i: int, beam, prepared):
             shapes = [candidate.effect_length.shape, candidate.grid_extent_x.shape,
                       candidate.grid_extent_y.shape, candidate.grid_extent_tau.shape]
             if (tuple(candidate.grid_shape) == tuple(element.grid_shape)
-                    and tuple(torch.broadcast_shapes(vs, *shapes)) == vs
+                    and tuple(_bshape(vs, *shapes)) == vs
                     and all(t.device == beam.particles.device for t in (
                         candidate.effect_length, candidate.grid_extent_x,
                         candidate.grid_extent_y, candidate.grid_extent_tau))):
@@ -376,16 +392,11 @@ def _track_space_charge(program, stages: list, i: int, beam, prepared):
         element, beam, prepared=prepared, fuse_records=records, next_element=next_element
     )
     if section is not None:
-        fused = outgoing.__class__(
-            outgoing.particles, outgoing.energy, particle_charges=outgoing.particle_charges,
-            survival_probabilities=outgoing.survival_probabilities, s=new_s,
-            species=outgoing.species.clone(),
+        outgoing = _new_beam(
+            outgoing, outgoing.particles, outgoing.energy, outgoing.particle_charges,
+            outgoing.survival_probabilities, new_s, outgoing.species.clone(),
+            getattr(outgoing, "_unit_seventh", None),
         )
-        try:
-            fused._unit_seventh = getattr(outgoing, "_unit_seventh", None)
-        except Exception:
-            pass
-        outgoing = fused
     return outgoing, prepared, 1 if section is None else 2
 
 
