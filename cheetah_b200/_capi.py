@@ -16,6 +16,7 @@ import torch
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcheetah_b200.so"
 
 CH_F32, CH_F64 = 0, 1
+ABI_VERSION = 2  # CH_ABI_VERSION of include/cheetah_b200.h
 
 OP_IDENTITY = 0
 OP_DRIFT = 1
@@ -249,6 +250,12 @@ def lib() -> ctypes.CDLL:
                 "`python -m cheetah_b200.build`; there is no CPU fallback."
             )
         handle = ctypes.CDLL(str(LIB_PATH))
+        handle.ch_abi_version.restype = c_int32
+        if handle.ch_abi_version() != ABI_VERSION:
+            raise RuntimeError(
+                f"cheetah_b200: {LIB_PATH} has ABI version {handle.ch_abi_version()}, the Python "
+                f"binding expects {ABI_VERSION}; rebuild it with `python -m cheetah_b200.build`"
+            )
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype = restype
@@ -277,6 +284,26 @@ def current_stream(device: torch.device) -> int:
     if index is None:
         index = torch.cuda.current_device()
     return torch._C._cuda_getCurrentRawStream(index)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device: torch.device):
+    """``torch.cuda.device(device)`` only when ``device`` is not already current (the context
+    manager costs ~8 us per use, as much as a whole C-ABI call)."""
+    index = device.index
+    if index is None or index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def launch_count() -> int:

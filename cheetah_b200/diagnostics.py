@@ -56,7 +56,7 @@ def beam_centroid(beam) -> tuple[torch.Tensor, torch.Tensor]:
     particles = particles.contiguous()
     survival = survival.to(dtype).contiguous()
     stats = torch.empty((n_beams, _capi.SC_STATS), dtype=torch.float64, device=device)
-    with torch.cuda.device(device):
+    with _capi.device_guard(device):
         _capi.check(_capi.lib().ch_sc_beam_moments(
             particles.data_ptr(), 0 if math.prod(vp) == 1 else n * 7,
             survival.data_ptr(), 0 if math.prod(vs) == 1 else n,
@@ -161,7 +161,7 @@ def screen_image(element, beam) -> torch.Tensor:
     if method == "histogram":
         edges_x, edges_y = (e.to(dtype).contiguous() for e in element.pixel_bin_edges)
     image = torch.empty((n_beams, ny, nx), dtype=dtype, device=device)
-    with torch.cuda.device(device):
+    with _capi.device_guard(device):
         _capi.check(_capi.lib().ch_screen_image(
             particles.data_ptr(), particle_stride, charges.data_ptr(), charge_stride,
             survival.data_ptr(), survival_stride, misalignment.data_ptr(), misalignment_stride,

@@ -138,7 +138,7 @@ class HostTracker:
             if done[buf] is not None:
                 compute.wait_event(done[buf])  # previous download of this device buffer
             out, surv = self.out_dev[buf], self.surv_dev[buf]
-            with torch.cuda.device(device):
+            with _capi.device_guard(device):
                 _capi.check(
                     lib.ch_apply_maps(
                         self.beam_dev.data_ptr(), 0, None,

@@ -116,7 +116,7 @@ class LatticeProgram:
         c_strides = (ctypes.c_int64 * max(n_slots, 1))(*strides)
         c_dtypes = (ctypes.c_int32 * max(n_slots, 1))(*dtypes)
         handle = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
+        with _capi.device_guard(self.device):
             _capi.check(
                 lib.ch_program_create(
                     opcodes, flags, slot_begin, n_ops, c_ptrs, c_strides, c_dtypes, n_slots,

@@ -168,7 +168,7 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
         prepared is not None and prepared.workspace is ws and prepared.element is element
         and element is not None
     )
-    with torch.cuda.device(device):
+    with _capi.device_guard(device):
         if reuse:
             ws.slot = prepared.slot
         else:
@@ -322,7 +322,7 @@ def cloud_in_cell_charge_deposition(positions, bins, extent=None, charges=None):
     if charges is not None:
         q = charges.to(dtype).expand(*vector_shape, n).reshape(n_beams, n).contiguous()
     grid = torch.empty((n_beams, *shape), dtype=dtype, device=device)
-    with torch.cuda.device(device):
+    with _capi.device_guard(device):
         _capi.check(_capi.lib().ch_cic_deposit3d(
             pos.data_ptr(), ext.data_ptr(), _capi.ptr(q), n, n_beams, *shape,
             _capi.dtype_code(dtype), grid.data_ptr(), _capi.current_stream(device)))

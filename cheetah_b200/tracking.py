@@ -115,7 +115,7 @@ def _compose(program, section, energy: torch.Tensor, species, dtype):
         energy_stride = 1
     rec_len = _capi.record_len(section.n_apertures, section.cavity is not None)
     records = torch.empty((n_settings, rec_len), dtype=dtype, device=device)
-    with torch.cuda.device(device):
+    with _capi.device_guard(device):
         _capi.check(
             _capi.lib().ch_compose_maps(
                 program.native, section.op_begin, section.op_end, n_settings,
@@ -254,7 +254,7 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
         n, n_out, _capi.ptr(out), _capi.ptr(survival_out),
     )
     tail = (_capi.dtype_code(dtype), int(_unit_seventh(beam)), _capi.current_stream(device))
-    with torch.cuda.device(device):
+    with _capi.device_guard(device):
         if moments is None:
             _capi.check(_capi.lib().ch_apply_maps(*common, *tail))
         elif covariance:
@@ -310,7 +310,7 @@ def _track_nonlinear_run(program, run, beam):
     else:
         energy = energy.expand(vm).contiguous()
         energy_stride = 1
-    with torch.cuda.device(device):
+    with _capi.device_guard(device):
         n_consts = int(lib.ch_nonlinear_constants_len(program.native, run.op_begin, run.op_end))
         if n_consts < 0:
             _capi.check(-1)

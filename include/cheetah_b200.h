@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define CH_ABI_VERSION 1
+/* 2: non-linear tracking, diagnostics, fused gather, quad-block charge grid (ch_sc_deposit) */
+#define CH_ABI_VERSION 2
 
 enum { CH_F32 = 0, CH_F64 = 1 };
 
