@@ -98,6 +98,14 @@ SIGNATURES = {
             c_int32, c_int32, c_void_p,
         ],
     ),
+    "ch_apply_maps_parameter": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+            c_void_p, c_int64, c_void_p,
+            c_int64, c_void_p, c_void_p, c_int32, c_void_p,
+        ],
+    ),
     "ch_apply_maps_covariance": (
         c_int32,
         [

@@ -685,3 +685,80 @@ extern "C" int ch_apply_maps_covariance(const void* particles_in, int64_t partic
                         record_len, n_apertures, elliptical_mask, n_particles, n_settings,
                         particles_out, survival_out, dtype, unit_seventh, moments_out, 1, stream);
 }
+
+// ---- ParameterBeam: mu' = M mu, cov' = M cov M^T (cheetah/accelerator/element.py:166-179) --------
+namespace ch {
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(64)
+apply_maps_parameter_kernel(const T* __restrict__ mu_in, int64_t mu_stride,
+                            const int32_t* __restrict__ mu_index, const T* __restrict__ cov_in,
+                            int64_t cov_stride, const T* __restrict__ records,
+                            int64_t record_stride, const int32_t* __restrict__ record_index,
+                            T* __restrict__ mu_out, T* __restrict__ cov_out) {
+  __shared__ double m[7][7], mu[7], cov[7][7], half[7][7];
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int64_t beam = mu_index ? mu_index[b] : b;
+  const T* rec = records + (record_index ? record_index[b] : b) * record_stride + CH_RECORD_HEADER;
+  if (tid < 49) {
+    const int i = tid / 7, j = tid - i * 7;
+    m[i][j] = i < 6 ? static_cast<double>(rec[i * 7 + j]) : (j == 6 ? 1.0 : 0.0);
+    cov[i][j] = static_cast<double>(cov_in[beam * cov_stride + tid]);
+  }
+  if (tid < 7) mu[tid] = static_cast<double>(mu_in[beam * mu_stride + tid]);
+  __syncthreads();
+  if (tid < 49) {  // half = M cov
+    const int i = tid / 7, j = tid - i * 7;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc = fma(m[i][k], cov[k][j], acc);
+    half[i][j] = acc;
+  }
+  __syncthreads();
+  if (tid < 49) {  // cov' = half M^T
+    const int i = tid / 7, j = tid - i * 7;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc = fma(half[i][k], m[j][k], acc);
+    cov_out[b * 49 + tid] = static_cast<T>(acc);
+  } else if (tid < 56) {
+    const int i = tid - 49;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc = fma(m[i][k], mu[k], acc);
+    mu_out[b * 7 + i] = static_cast<T>(acc);
+  }
+}
+
+}  // namespace
+}  // namespace ch
+
+extern "C" int ch_apply_maps_parameter(const void* mu_in, int64_t mu_stride,
+                                       const int32_t* mu_index, const void* cov_in,
+                                       int64_t cov_stride, const void* records,
+                                       int64_t record_stride, const int32_t* record_index,
+                                       int64_t n_settings, void* mu_out, void* cov_out,
+                                       int32_t dtype, void* stream) {
+  CH_REQUIRE(mu_in && cov_in && records && mu_out && cov_out,
+             "ch_apply_maps_parameter: NULL pointer argument");
+  CH_REQUIRE(n_settings > 0 && n_settings <= 2147483647LL,
+             "ch_apply_maps_parameter: n_settings must be in [1, 2^31)");
+  CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, "ch_apply_maps_parameter: bad dtype %d", dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>(n_settings);
+  if (dtype == CH_F32)
+    ch::apply_maps_parameter_kernel<float><<<blocks, 64, 0, s>>>(
+        static_cast<const float*>(mu_in), mu_stride, mu_index, static_cast<const float*>(cov_in),
+        cov_stride, static_cast<const float*>(records), record_stride, record_index,
+        static_cast<float*>(mu_out), static_cast<float*>(cov_out));
+  else
+    ch::apply_maps_parameter_kernel<double><<<blocks, 64, 0, s>>>(
+        static_cast<const double*>(mu_in), mu_stride, mu_index,
+        static_cast<const double*>(cov_in), cov_stride, static_cast<const double*>(records),
+        record_stride, record_index, static_cast<double*>(mu_out),
+        static_cast<double*>(cov_out));
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}

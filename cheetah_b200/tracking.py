@@ -532,9 +532,26 @@ def _track_parameter_beam(program, beam):
                 "cheetah_b200: an active Cavity is only accelerated for `ParticleBeam`"
             )
         records, vm = _compose(program, stage, beam.energy, beam.species, dtype)
-        tm = _maps_from_records(records, vm)
-        mu = (tm @ mu.unsqueeze(-1)).squeeze(-1)
-        cov = tm @ cov @ tm.mT
+        # mu' = M mu, cov' = M cov M^T on the device library (element.py:166-179)
+        device = mu.device
+        vb = tuple(_bshape(mu.shape[:-1], cov.shape[:-2]))
+        vo = tuple(_bshape(vm, vb))
+        n_out = math.prod(vo)
+        mu_c = mu.expand(*vb, 7).contiguous()
+        cov_c = cov.expand(*vb, 7, 7).contiguous()
+        beam_index = _index_table(vb, vo, device)
+        record_index = _index_table(vm, vo, device)
+        mu_out = torch.empty((*vo, 7), dtype=dtype, device=device)
+        cov_out = torch.empty((*vo, 7, 7), dtype=dtype, device=device)
+        with _capi.device_guard(device):
+            _capi.check(_capi.lib().ch_apply_maps_parameter(
+                mu_c.data_ptr(), 0 if math.prod(vb) == 1 else 7, _capi.ptr(beam_index),
+                cov_c.data_ptr(), 0 if math.prod(vb) == 1 else 49,
+                records.data_ptr(), 0 if math.prod(vm) == 1 else records.shape[1],
+                _capi.ptr(record_index), n_out, mu_out.data_ptr(), cov_out.data_ptr(),
+                _capi.dtype_code(dtype), _capi.current_stream(device),
+            ))
+        mu, cov = mu_out, cov_out
         s = s + _section_length(records, vm, stage.length_shape)
     return beam.__class__(
         mu, cov, beam.energy, total_charge=beam.total_charge, s=s, species=beam.species.clone()
