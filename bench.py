@@ -356,9 +356,11 @@ def main() -> None:
     if not args.no_e2e:
         host_description = workloads.ares_config3(args.settings, dtype, begin, end)
         import cheetah_b200 as cb
-        from oracle import lattice_io
+        from cheetah_b200 import lattice_description
 
-        host_segment = cb.Segment(elements=lattice_io.build(host_description, cb, dtype=dtype))
+        host_segment = cb.Segment(
+            elements=lattice_description.build(host_description, dtype=dtype)
+        )
         host_beam = cb.ParticleBeam(
             particles=particles.to(dtype), energy=torch.tensor(1e8, dtype=dtype),
             species=cb.Species("electron", dtype=dtype),

@@ -58,7 +58,7 @@ def main() -> None:
 
     import cheetah_b200 as cb
     from cheetah_b200 import _capi
-    from oracle import lattice_io
+    from cheetah_b200 import lattice_description
     from oracle import track_oracle as oracle
 
     device, dtype = torch.device("cuda", 0), torch.float32
@@ -119,7 +119,7 @@ def main() -> None:
     fused = {}
     for method in ("drift_kick_drift", "second_order"):
         description = fodo(method, 5, B, dtype)
-        segment = cb.Segment(lattice_io.build(description, cb, device=device, dtype=dtype))
+        segment = cb.Segment(lattice_description.build(description, device=device, dtype=dtype))
         ms, launches = timed(lambda: segment.track(shared))
         fused[method] = {
             "case": f"20-element {method} FODO line, shared beam, {B} settings x {n} particles",

@@ -2,8 +2,8 @@
 
 The ARES lattice comes from ``tests/golden/ares_lattice.json`` (the reference's
 ``docs/examples/ARESlatticeStage3v1_9.json`` converted by ``oracle/make_golden.py``: 195
-elements).  A workload is returned as a plain-dict lattice description (``oracle/lattice_io``
-format) plus beam parameters, and can be instantiated either as ``cheetah_b200`` objects on a
+elements).  A workload is returned as a plain-dict lattice description
+(``cheetah_b200/lattice_description.py`` format) plus beam parameters, and can be instantiated either as ``cheetah_b200`` objects on a
 CUDA device (the product) or kept as dicts for the CPU oracle (the baseline).
 
 Config 3 recipe (frozen; SURVEY.md 8d asks to tune the ranges once so that the mean survival
@@ -20,7 +20,7 @@ from pathlib import Path
 
 import torch
 
-from oracle import lattice_io
+from cheetah_b200 import lattice_description
 
 GOLDEN = Path(__file__).resolve().parent / "tests" / "golden"
 N_ELEMENTS_ARES = 195
@@ -44,7 +44,7 @@ def _set(description: list, name: str, attr: str, value) -> None:
 
 def ares_config2(dtype=torch.float32) -> list:
     """ARES, single setting, five EA magnets powered (BASELINE configs[1])."""
-    lattice = lattice_io.load(GOLDEN / "ares_lattice.json", dtype)
+    lattice = lattice_description.load(GOLDEN / "ares_lattice.json", dtype)
     for name, (attr, value) in CONFIG2_SETTINGS.items():
         _set(lattice, name, attr, torch.tensor(value, dtype=dtype))
     return lattice
@@ -58,7 +58,7 @@ def ares_config3(n_settings: int, dtype=torch.float32, begin: int = 0, end: int 
     the same settings.
     """
     end = n_settings if end is None else end
-    lattice = lattice_io.load(GOLDEN / "ares_lattice.json", dtype)
+    lattice = lattice_description.load(GOLDEN / "ares_lattice.json", dtype)
     g = torch.Generator().manual_seed(1)
     for element in lattice:
         if element["type"] == "Quadrupole":
@@ -89,7 +89,7 @@ def twiss_beam_particles(num_particles: int, seed: int = 0) -> torch.Tensor:
 def product_segment(description: list, device, dtype):
     import cheetah_b200 as cb
 
-    return cb.Segment(elements=lattice_io.build(description, cb, device=device, dtype=dtype))
+    return cb.Segment(elements=lattice_description.build(description, device=device, dtype=dtype))
 
 
 def product_beam(particles: torch.Tensor, device, dtype, energy: float = 1e8):
