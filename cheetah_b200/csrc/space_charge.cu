@@ -742,11 +742,11 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);
   __shared__ uint64_t bar;
-  __shared__ T map_s[FUSED ? 44 : 1];
+  __shared__ __align__(16) T map_s[FUSED ? 48 : 1];  // rows padded to 8 for 128-bit loads
   __shared__ double partial[FUSED ? 8 : 1][8];
   if constexpr (FUSED) {
     if (fusion.records != nullptr && threadIdx.x < 42)
-      map_s[threadIdx.x] =
+      map_s[(threadIdx.x / 7) * 8 + threadIdx.x % 7] =
           fusion.records[blockIdx.y * fusion.record_stride + CH_RECORD_HEADER + threadIdx.x];
   }
   const int64_t b = blockIdx.y;
@@ -772,7 +772,6 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
   const double mc = prm[15] * kEvToKg * kSpeedOfLight;  // mass * c in kg m / s
   const double bg0 = gamma0 * beta0, inv_bg0 = 1.0 / bg0, dt_over_mc = dt / mc;
 
-  T out[P][7];
   T force[P][3];
   // ---- trilinear gather on the node-centred grid (space_charge_kick.py:388-475), two
   // particles at a time so that their 16 sector loads are in flight together ------------
@@ -840,6 +839,7 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
 #pragma unroll
     for (int j = 0; j < 7; ++j) p[j] = (local < count) ? tile[local * 7 + j] : T(0);
     const T fx = force[k][0], fy = force[k][1], fz = force[k][2];
+    T row[7];  // outgoing particle; written back over the thread's own input row below
     if (forces_out != nullptr && local < count) {
       T* f = forces_out + (b * n_particles + n0 + local) * 3;
       f[0] = fx;
@@ -858,25 +858,40 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
     uy = fma(static_cast<double>(fy), dt_over_mc, uy);
     uz = fma(static_cast<double>(fz), dt_over_mc, uz);
     const double gamma_new = sqrt(1.0 + ux * ux + uy * uy + uz * uz);
-    out[k][0] = p[0];
-    out[k][1] = static_cast<T>(ux * inv_bg0);
-    out[k][2] = p[2];
-    out[k][3] = static_cast<T>(uy * inv_bg0);
-    out[k][4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
-    out[k][5] = static_cast<T>((gamma_new - gamma0) * inv_bg0);
-    out[k][6] = p[6];
+    row[0] = p[0];
+    row[1] = static_cast<T>(ux * inv_bg0);
+    row[2] = p[2];
+    row[3] = static_cast<T>(uy * inv_bg0);
+    row[4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
+    row[5] = static_cast<T>((gamma_new - gamma0) * inv_bg0);
+    row[6] = p[6];
     if constexpr (FUSED) {
       if (fusion.records != nullptr) {  // particles @ tm.mT of the following linear section
+        // the gather is bound by L1 / shared-memory traffic: fetch each map row with two
+        // (four for double) 128-bit loads instead of seven scalar ones
         T mapped[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          T acc = map_s[i * 7 + 6] * out[k][6];
+          T c[8];
+          if constexpr (sizeof(T) == 4) {
+            const float4 lo = reinterpret_cast<const float4*>(map_s)[i * 2];
+            const float4 hi = reinterpret_cast<const float4*>(map_s)[i * 2 + 1];
+            c[0] = lo.x, c[1] = lo.y, c[2] = lo.z, c[3] = lo.w;
+            c[4] = hi.x, c[5] = hi.y, c[6] = hi.z, c[7] = hi.w;
+          } else {
 #pragma unroll
-          for (int j = 5; j >= 0; --j) acc = fma(map_s[i * 7 + j], out[k][j], acc);
+            for (int h = 0; h < 4; ++h) {
+              const double2 v = reinterpret_cast<const double2*>(map_s)[i * 4 + h];
+              c[2 * h] = v.x, c[2 * h + 1] = v.y;
+            }
+          }
+          T acc = c[6] * row[6];
+#pragma unroll
+          for (int j = 5; j >= 0; --j) acc = fma(c[j], row[j], acc);
           mapped[i] = acc;
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) out[k][i] = mapped[i];
+        for (int i = 0; i < 6; ++i) row[i] = mapped[i];
       }
       if (fusion.next_stats != nullptr && local < count) {
         // sums about the origin in fp64 (ch_sc_beam_moments uses a pilot particle; with fp64
@@ -885,9 +900,9 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
                               ? static_cast<double>(
                                     fusion.survival[b * fusion.survival_stride + n0 + local])
                               : 1.0;
-        const double dx = static_cast<double>(out[k][0]);
-        const double dy = static_cast<double>(out[k][2]);
-        const double dt = static_cast<double>(out[k][4]);
+        const double dx = static_cast<double>(row[0]);
+        const double dy = static_cast<double>(row[2]);
+        const double dt = static_cast<double>(row[4]);
         acc8[0] += wi;
         acc8[1] = fma(wi, wi, acc8[1]);
         acc8[2] = fma(wi, dx, acc8[2]);
@@ -898,13 +913,10 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
         acc8[7] = fma(wi * dt, dt, acc8[7]);
       }
     }
-  }
-  __syncthreads();  // everybody is done reading the input tile
+    // a row of the tile is only ever touched by the thread that owns the particle, so the
+    // outgoing row can replace the incoming one right away (no block-wide staging of all rows)
 #pragma unroll
-  for (int k = 0; k < P; ++k) {
-    const int local = threadIdx.x + k * THREADS;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) tile[local * 7 + j] = out[k][j];
+    for (int j = 0; j < 7; ++j) tile[local * 7 + j] = row[j];
   }
   T* dst = particles_out + (b * n_particles + n0) * 7;
   if (bulk_out) {
@@ -934,6 +946,11 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
       for (int wi = 0; wi < 8; ++wi) sum += partial[wi][threadIdx.x];
       atomicAdd(&stats[threadIdx.x], sum);
     }
+    // With many CTAs per beam the caller derives the grid parameters in a separate tiny launch
+    // (next_params == NULL here): the reductions above are fire-and-forget, whereas the
+    // fence + ticket round trip below would keep every CTA's slot idle for ~2 us at its end
+    // (measured: +25 % on a 64-beam gather).  With few CTAs the last one does it in place.
+    if (fusion.next_params == nullptr) return;
     // last CTA of the beam: sums -> grid parameters of the next kick (as in sc_moments_kernel;
     // stats[8..10], the pilot, stay 0 from the memset)
     __shared__ bool last;
@@ -1417,16 +1434,32 @@ extern "C" int ch_sc_gather_kick_fused(
                           {next_extent_x, next_extent_x_stride, next_extent_dtype},
                           {next_extent_y, next_extent_y_stride, next_extent_dtype},
                           {next_extent_tau, next_extent_tau_stride, next_extent_dtype}};
+  // several waves of CTAs: grid parameters in a follow-up launch instead of a last-CTA epilogue
+  const int64_t ctas = ((n_particles + 1023) / 1024) * n_beams;
+  const bool separate_params = next_stats != nullptr && ctas > 148 * 3 * 4;
+  double* in_kernel_params = separate_params ? nullptr : next_params;
+  int status;
   if (dtype == CH_F32) {
     const ch::GatherFusion<float> f{static_cast<const float*>(records), record_stride,
                                     static_cast<const float*>(survival), survival_stride,
-                                    next_stats, next_params, in, next_nx, next_ny, next_nz};
-    return launch_gather<float>(particles_in, particle_stride, field, params, n_particles, n_beams,
-                                nx, ny, nz, particles_out, nullptr, &f, s);
+                                    next_stats, in_kernel_params, in, next_nx, next_ny, next_nz};
+    status = launch_gather<float>(particles_in, particle_stride, field, params, n_particles,
+                                  n_beams, nx, ny, nz, particles_out, nullptr, &f, s);
+  } else {
+    const ch::GatherFusion<double> f{static_cast<const double*>(records), record_stride,
+                                     static_cast<const double*>(survival), survival_stride,
+                                     next_stats, in_kernel_params, in, next_nx, next_ny, next_nz};
+    status = launch_gather<double>(particles_in, particle_stride, field, params, n_particles,
+                                   n_beams, nx, ny, nz, particles_out, nullptr, &f, s);
   }
-  const ch::GatherFusion<double> f{static_cast<const double*>(records), record_stride,
-                                   static_cast<const double*>(survival), survival_stride,
-                                   next_stats, next_params, in, next_nx, next_ny, next_nz};
-  return launch_gather<double>(particles_in, particle_stride, field, params, n_particles, n_beams,
-                               nx, ny, nz, particles_out, nullptr, &f, s);
+  if (status != CH_OK || !separate_params) return status;
+  const unsigned blocks = static_cast<unsigned>((n_beams + 127) / 128);
+  if (dtype == CH_F32)
+    ch::sc_grid_params_kernel<float><<<blocks, 128, 0, s>>>(next_stats, n_beams, in, next_nx,
+                                                            next_ny, next_nz, next_params);
+  else
+    ch::sc_grid_params_kernel<double><<<blocks, 128, 0, s>>>(next_stats, n_beams, in, next_nx,
+                                                             next_ny, next_nz, next_params);
+  CH_LAUNCH_CHECK();
+  return CH_OK;
 }
