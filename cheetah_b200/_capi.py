@@ -103,7 +103,7 @@ SIGNATURES = {
         [
             c_void_p, c_int64, c_void_p, c_void_p, c_int64,
             c_void_p, c_int64, c_void_p,
-            c_int64, c_void_p, c_void_p, c_int32, c_void_p,
+            c_int32, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
         ],
     ),
     "ch_apply_maps_covariance": (

@@ -696,8 +696,10 @@ apply_maps_parameter_kernel(const T* __restrict__ mu_in, int64_t mu_stride,
                             const int32_t* __restrict__ mu_index, const T* __restrict__ cov_in,
                             int64_t cov_stride, const T* __restrict__ records,
                             int64_t record_stride, const int32_t* __restrict__ record_index,
-                            T* __restrict__ mu_out, T* __restrict__ cov_out) {
+                            int32_t cavity_offset, T* __restrict__ mu_out,
+                            T* __restrict__ cov_out) {
   __shared__ double m[7][7], mu[7], cov[7][7], half[7][7];
+  __shared__ double entrance[2][7], entrance_cov[2][7];
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
   const int64_t beam = mu_index ? mu_index[b] : b;
@@ -730,6 +732,47 @@ apply_maps_parameter_kernel(const T* __restrict__ mu_in, int64_t mu_stride,
     for (int k = 0; k < 7; ++k) acc = fma(m[i][k], mu[k], acc);
     mu_out[b * 7 + i] = static_cast<T>(acc);
   }
+  if (cavity_offset < 0) return;
+  // Active cavity at the end of the section, ParameterBeam branch of Cavity.track
+  // (cavity.py:129-135, :203-217): the longitudinal entries are replaced by expressions in the
+  // moments at the cavity ENTRANCE, i.e. under the rows (tau, delta) of the map up to there.
+  const T* cav = rec - CH_RECORD_HEADER + cavity_offset;
+  __syncthreads();  // the plain results above are written
+  if (tid < 14) entrance[tid / 7][tid % 7] = static_cast<double>(cav[tid]);
+  __syncthreads();
+  if (tid < 14) {  // entrance_cov[r] = row_r . cov
+    const int r = tid / 7, j = tid % 7;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc = fma(entrance[r][k], cov[k][j], acc);
+    entrance_cov[r][j] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tau = 0.0, delta = 0.0, c44 = 0.0, c45 = 0.0, c55 = 0.0;
+    for (int k = 0; k < 7; ++k) {
+      tau = fma(entrance[0][k], mu[k], tau);
+      delta = fma(entrance[1][k], mu[k], delta);
+      c44 = fma(entrance_cov[0][k], entrance[0][k], c44);
+      c45 = fma(entrance_cov[0][k], entrance[1][k], c45);
+      c55 = fma(entrance_cov[1][k], entrance[1][k], c55);
+    }
+    const double a = cav[14], bv = cav[15], b0k = cav[16], sphi = cav[17], cphi = cav[18];
+    const double t566 = cav[19], t556 = cav[20], t555 = cav[21];
+    double se, ce;
+    sincos(tau * b0k, &se, &ce);
+    const double dcos = cphi * ce + sphi * se - cphi;  // cos(phi - tau b0 k) - cos(phi)
+    mu_out[b * 7 + 5] = static_cast<T>(a * delta + bv * dcos);
+    double m4 = 0.0;
+    for (int k = 0; k < 7; ++k) m4 = fma(m[4][k], mu[k], m4);
+    mu_out[b * 7 + 4] = static_cast<T>(m4 + t566 * delta * delta + t556 * tau * delta +
+                                       t555 * tau * tau);
+    const double longitudinal = t566 * c55 * c55 + t556 * c45 * c55 + t555 * c44 * c44;
+    cov_out[b * 49 + 4 * 7 + 4] = static_cast<T>(longitudinal);
+    cov_out[b * 49 + 4 * 7 + 5] = static_cast<T>(longitudinal);
+    cov_out[b * 49 + 5 * 7 + 4] = static_cast<T>(longitudinal);
+    cov_out[b * 49 + 5 * 7 + 5] = static_cast<T>(c55);
+  }
 }
 
 }  // namespace
@@ -739,8 +782,8 @@ extern "C" int ch_apply_maps_parameter(const void* mu_in, int64_t mu_stride,
                                        const int32_t* mu_index, const void* cov_in,
                                        int64_t cov_stride, const void* records,
                                        int64_t record_stride, const int32_t* record_index,
-                                       int64_t n_settings, void* mu_out, void* cov_out,
-                                       int32_t dtype, void* stream) {
+                                       int32_t cavity_offset, int64_t n_settings, void* mu_out,
+                                       void* cov_out, int32_t dtype, void* stream) {
   CH_REQUIRE(mu_in && cov_in && records && mu_out && cov_out,
              "ch_apply_maps_parameter: NULL pointer argument");
   CH_REQUIRE(n_settings > 0 && n_settings <= 2147483647LL,
@@ -752,12 +795,12 @@ extern "C" int ch_apply_maps_parameter(const void* mu_in, int64_t mu_stride,
     ch::apply_maps_parameter_kernel<float><<<blocks, 64, 0, s>>>(
         static_cast<const float*>(mu_in), mu_stride, mu_index, static_cast<const float*>(cov_in),
         cov_stride, static_cast<const float*>(records), record_stride, record_index,
-        static_cast<float*>(mu_out), static_cast<float*>(cov_out));
+        cavity_offset, static_cast<float*>(mu_out), static_cast<float*>(cov_out));
   else
     ch::apply_maps_parameter_kernel<double><<<blocks, 64, 0, s>>>(
         static_cast<const double*>(mu_in), mu_stride, mu_index,
         static_cast<const double*>(cov_in), cov_stride, static_cast<const double*>(records),
-        record_stride, record_index, static_cast<double*>(mu_out),
+        record_stride, record_index, cavity_offset, static_cast<double*>(mu_out),
         static_cast<double*>(cov_out));
   CH_LAUNCH_CHECK();
   return CH_OK;

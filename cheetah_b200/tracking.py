@@ -496,7 +496,7 @@ def track_moments(elements, incoming, cache_owner=None, keep_particles: bool = F
 
 def _track_parameter_beam(program, beam):
     """tm @ mu, tm @ cov @ tm^T with the composed maps (element.py:166-179)."""
-    mu, cov, s = beam.mu, beam.cov, beam.s
+    mu, cov, s, energy = beam.mu, beam.cov, beam.s, beam.energy
     for stage in program.stages:
         if isinstance(stage, lowering.NonlinearRun):
             if "drift_kick_drift" in stage.methods:
@@ -508,7 +508,7 @@ def _track_parameter_beam(program, beam):
             )
         if isinstance(stage, lowering.Barrier) and stage.kind in ("bpm", "screen"):
             beam = _track_monitor(stage, beam.__class__(
-                mu, cov, beam.energy, total_charge=beam.total_charge, s=s, species=beam.species,
+                mu, cov, energy, total_charge=beam.total_charge, s=s, species=beam.species,
             ))
             mu, cov, s = beam.mu, beam.cov, beam.s
             continue
@@ -527,11 +527,10 @@ def _track_parameter_beam(program, beam):
                 _physics_warning(), stacklevel=3,
             )
         dtype = mu.dtype
+        records, vm = _compose(program, stage, energy, beam.species, dtype)
+        cavity_offset = -1
         if stage.cavity is not None:
-            raise NotImplementedError(
-                "cheetah_b200: an active Cavity is only accelerated for `ParticleBeam`"
-            )
-        records, vm = _compose(program, stage, beam.energy, beam.species, dtype)
+            cavity_offset = _capi.record_len(stage.n_apertures, False)
         # mu' = M mu, cov' = M cov M^T on the device library (element.py:166-179)
         device = mu.device
         vb = tuple(_bshape(mu.shape[:-1], cov.shape[:-2]))
@@ -548,13 +547,19 @@ def _track_parameter_beam(program, beam):
                 mu_c.data_ptr(), 0 if math.prod(vb) == 1 else 7, _capi.ptr(beam_index),
                 cov_c.data_ptr(), 0 if math.prod(vb) == 1 else 49,
                 records.data_ptr(), 0 if math.prod(vm) == 1 else records.shape[1],
-                _capi.ptr(record_index), n_out, mu_out.data_ptr(), cov_out.data_ptr(),
-                _capi.dtype_code(dtype), _capi.current_stream(device),
+                _capi.ptr(record_index), cavity_offset, n_out, mu_out.data_ptr(),
+                cov_out.data_ptr(), _capi.dtype_code(dtype), _capi.current_stream(device),
             ))
         mu, cov = mu_out, cov_out
+        if stage.cavity is not None:
+            cavity = stage.cavity[0]
+            energy = energy + (
+                cavity.voltage * cavity.phase.deg2rad().cos()
+                * beam.species.num_elementary_charges * -1
+            ).to(energy.dtype)
         s = s + _section_length(records, vm, stage.length_shape)
     return beam.__class__(
-        mu, cov, beam.energy, total_charge=beam.total_charge, s=s, species=beam.species.clone()
+        mu, cov, energy, total_charge=beam.total_charge, s=s, species=beam.species.clone()
     )
 
 

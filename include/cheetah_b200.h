@@ -192,12 +192,15 @@ int ch_apply_maps(const void* particles_in, int64_t particle_stride, const int32
 /* ParameterBeam tracking through one linear section (cheetah/accelerator/element.py:166-179):
  *   mu_out[b] = M_b mu_in[midx(b)],  cov_out[b] = M_b cov_in[midx(b)] M_b^T
  * with M_b the 7x7 map of records[ridx(b)] (products accumulated in fp64); mu [..][7],
- * cov [..][7][7]; index / stride conventions as in ch_apply_maps (mu_index serves both).      */
+ * cov [..][7][7]; index / stride conventions as in ch_apply_maps (mu_index serves both).
+ * cavity_offset: position of the CH_RECORD_CAVITY block inside a record when the section ends with
+ * an active cavity (CH_RECORD_LEN(n_apertures)), else -1; with it the longitudinal entries follow
+ * the ParameterBeam branch of Cavity.track (cavity.py:129-135, :203-217).                       */
 int ch_apply_maps_parameter(const void* mu_in, int64_t mu_stride, const int32_t* mu_index,
                             const void* cov_in, int64_t cov_stride,
                             const void* records, int64_t record_stride, const int32_t* record_index,
-                            int64_t n_settings, void* mu_out, void* cov_out,
-                            int32_t dtype, void* stream);
+                            int32_t cavity_offset, int64_t n_settings,
+                            void* mu_out, void* cov_out, int32_t dtype, void* stream);
 
 /* ch_apply_maps with a fused observables epilogue: additionally
  * accumulates, per setting, the survival-weighted sums that ParticleBeam.mu_* / sigma_*

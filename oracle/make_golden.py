@@ -445,6 +445,9 @@ def make_cavity() -> None:
         dtype=torch.float64,
     )
     arrays.update(beam_arrays("incoming", base))
+    parameter_base = base.as_parameter_beam()
+    arrays["incoming.mu"] = np64(parameter_base.mu)
+    arrays["incoming.cov"] = np64(parameter_base.cov)
     cases = {
         "standing": dict(length=1.0377, voltage=2.0e7, phase=-20.0, frequency=1.3e9,
                          cavity_type="standing_wave"),
@@ -464,6 +467,10 @@ def make_cavity() -> None:
             cavity = cheetah.Cavity(name=name, dtype=dtype, **kwargs)
             out = cavity.track(beam)
             arrays.update(beam_arrays(f"{name}.{tag}", out, rows))
+            parameter_out = cavity.track(parameter_base.to(dtype))  # ParameterBeam branch
+            arrays[f"{name}.{tag}.mu"] = np64(parameter_out.mu)
+            arrays[f"{name}.{tag}.cov"] = np64(parameter_out.cov)
+            arrays[f"{name}.{tag}.parameter_energy"] = np64(parameter_out.energy)
             if tag == "f64":
                 descriptions[name] = lattice_io._to_json([lattice_io.describe(cavity)])
         t = lambda v: torch.tensor(v, dtype=dtype)  # noqa: E731
@@ -480,6 +487,12 @@ def make_cavity() -> None:
         ])
         out = segment.track(beam)
         arrays.update(beam_arrays(f"segment.{tag}", out, rows))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # aperture on a ParameterBeam
+            parameter_out = segment.track(parameter_base.to(dtype))
+        arrays[f"segment.{tag}.mu"] = np64(parameter_out.mu)
+        arrays[f"segment.{tag}.cov"] = np64(parameter_out.cov)
+        arrays[f"segment.{tag}.parameter_energy"] = np64(parameter_out.energy)
         if tag == "f64":
             descriptions["segment"] = lattice_io._to_json(lattice_io.describe(segment)["elements"])
             print("cavity segment: energy", out.energy.item(), "survival",

@@ -546,6 +546,83 @@ def track_cavity(el: dict, beam: dict) -> dict:
     return _with(beam, particles=out, energy=outgoing_energy, s=beam["s"] + length)
 
 
+def track_parameter_beam(elements: list, mu, cov, energy, mass_eV, num_elementary_charges=-1.0):
+    """``Segment.track`` for a ParameterBeam (element.py:166-179, cavity.py:100-251): linear maps
+    on (mu, cov); an active cavity adds its special updates of the longitudinal entries.
+    Returns (mu, cov, energy)."""
+    run: list = []
+
+    def flush():
+        nonlocal mu, cov, run
+        for el in run:
+            tm = first_order_map(el, energy, mass_eV, num_elementary_charges)
+            mu = (tm @ mu.unsqueeze(-1)).squeeze(-1)
+            cov = tm @ cov @ tm.mT
+        run = []
+
+    for el in flatten(elements):
+        if is_skippable(el) or el["type"] == "Aperture":  # apertures ignore ParameterBeams
+            if el["type"] != "Aperture":
+                run.append(el)
+            continue
+        flush()
+        assert el["type"] == "Cavity", el["type"]
+        length = _get(el, "length", mu)
+        voltage = _get(el, "voltage", mu)
+        phi = _get(el, "phase", mu).deg2rad()
+        frequency = _get(el, "frequency", mu)
+        gamma0, igamma2, beta0 = relativistic_factors(energy, mass_eV)
+        tm = _cavity_map(el, energy, mass_eV, num_elementary_charges)
+        out_mu = (tm @ mu.unsqueeze(-1)).squeeze(-1)
+        out_cov = tm @ cov @ tm.mT
+        delta_energy = voltage * phi.cos() * num_elementary_charges * -1
+        T566 = 1.5 * length * igamma2 / beta0.pow(3)
+        T556 = length.new_zeros(())
+        T555 = length.new_zeros(())
+        k = 2.0 * torch.pi * frequency / SPEED_OF_LIGHT
+        outgoing_energy = energy + delta_energy
+        gamma1, _, beta1 = relativistic_factors(outgoing_energy, mass_eV)
+        out_mu[..., 5] = mu[..., 5] * energy * beta0 / (outgoing_energy * beta1) + voltage * beta0 / (
+            outgoing_energy * beta1
+        ) * ((-mu[..., 4] * beta0 * k + phi).cos() - phi.cos())
+        out_cov[..., 5, 5] = cov[..., 5, 5]
+        dgamma = voltage / mass_eV
+        if (delta_energy > 0).any():
+            T566 = (
+                length * (beta0.pow(3) * gamma0.pow(3) - beta1.pow(3) * gamma1.pow(3))
+                / (2.0 * beta0 * beta1.pow(3) * gamma0 * (gamma0 - gamma1) * gamma1.pow(3))
+            )
+            T556 = (
+                beta0 * k * length * dgamma * gamma0
+                * (beta1.pow(3) * gamma1.pow(3) + beta0 * (gamma0 - gamma1.pow(3))) * phi.sin()
+                / (beta1.pow(3) * gamma1.pow(3) * (gamma0 - gamma1).square())
+            )
+            T555 = (
+                beta0.square() * k.square() * length * dgamma / 2.0
+                * (
+                    dgamma
+                    * (2.0 * gamma0 * gamma1.pow(3) * (beta0 * beta1.pow(3) - 1.0)
+                       + gamma0.square() + 3.0 * gamma1.square() - 2.0)
+                    / (beta1.pow(3) * gamma1.pow(3) * (gamma0 - gamma1).pow(3)) * phi.sin().square()
+                    - (gamma1 * gamma0 * (beta1 * beta0 - 1.0) + 1.0)
+                    / (beta1 * gamma1 * (gamma0 - gamma1).square()) * phi.cos()
+                )
+            )
+        out_mu[..., 4] = out_mu[..., 4] + (
+            T566 * mu[..., 5].square() + T556 * mu[..., 4] * mu[..., 5] + T555 * mu[..., 4].square()
+        )
+        longitudinal = (
+            T566 * cov[..., 5, 5].square() + T556 * cov[..., 4, 5] * cov[..., 5, 5]
+            + T555 * cov[..., 4, 4].square()
+        )
+        out_cov[..., 4, 4] = longitudinal
+        out_cov[..., 4, 5] = longitudinal
+        out_cov[..., 5, 4] = longitudinal
+        mu, cov, energy = out_mu, out_cov, outgoing_energy
+    flush()
+    return mu, cov, energy
+
+
 # --------------------------------------------------------------------------------------
 # Space charge
 # --------------------------------------------------------------------------------------

@@ -413,3 +413,40 @@ def test_superimposed_and_split_against_the_reference_pickle():
     assert torch.allclose(beams[-1].particles, segment.track(incoming).particles,
                           rtol=1e-10, atol=1e-16)
     assert torch.allclose(beams[-1].s, t(2.5))
+
+
+@pytest.mark.parametrize("tag,dtype", [("f64", torch.float64), ("f32", torch.float32)])
+@pytest.mark.parametrize("case", ["standing", "traveling", "decelerating", "vectorised", "segment"])
+def test_active_cavity_parameter_beam(case, tag, dtype):
+    """ParameterBeam branch of Cavity.track (cavity.py:108-110, :129-135, :203-217) in
+    ch_apply_maps_parameter, against the unmodified reference."""
+    import warnings
+
+    import cheetah_b200 as cb
+
+    from .test_oracle_golden import CAVITY, cavity_lattices
+
+    lattice = cavity_lattices(dtype)[case]
+    incoming = gu.beam_dict(CAVITY, "incoming", dtype)
+    to = lambda a: gu.tensor(a, dtype).to(DEVICE)  # noqa: E731
+    beam = cb.ParameterBeam(
+        mu=to(CAVITY["incoming.mu"]), cov=to(CAVITY["incoming.cov"]),
+        energy=incoming["energy"].to(DEVICE),
+        species=cb.Species("electron", device=DEVICE, dtype=dtype),
+    )
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # the segment holds an aperture
+        out = gu.product_segment(lattice, DEVICE, dtype).track(beam)
+    truth_mu = gu.tensor(CAVITY[f"{case}.f64.mu"])
+    truth_cov = gu.tensor(CAVITY[f"{case}.f64.cov"])
+    assert out.mu.shape == truth_mu.shape and out.cov.shape == truth_cov.shape
+    rtol = 1e-9 if dtype == torch.float64 else 2e-5
+    scale_mu = truth_mu.abs().amax(dim=-1, keepdim=True)
+    assert float(((out.mu.cpu().double() - truth_mu).abs() / scale_mu).max()) < rtol
+    sigma = truth_cov.diagonal(dim1=-2, dim2=-1).abs().sqrt()
+    scale_cov = (sigma.unsqueeze(-1) * sigma.unsqueeze(-2)).clamp_min(1e-300)
+    assert float(((out.cov.cpu().double() - truth_cov).abs() / scale_cov)[..., :6, :6].max()) < (
+        1e-8 if dtype == torch.float64 else 2e-4)
+    assert torch.allclose(out.energy.cpu().double(),
+                          gu.tensor(CAVITY[f"{case}.f64.parameter_energy"]),
+                          rtol=1e-12 if dtype == torch.float64 else 1e-6)
