@@ -192,6 +192,14 @@ SIGNATURES = {
             c_void_p, c_void_p,
         ],
     ),
+    "ch_cic_deposit": (
+        c_int32,
+        [
+            c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p,
+        ],
+    ),
     "ch_sc_green_function": (
         c_int32,
         [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],

@@ -329,6 +329,41 @@ cic_deposit3d_kernel(const T* __restrict__ positions, const T* __restrict__ exte
                      ny, nz);
 }
 
+// 1-D and 2-D general deposits (cloud_in_cell.py:67-241): same per-axis rule, 2 / 4 corners.
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+cic_deposit_low_kernel(const T* __restrict__ positions, const T* __restrict__ extent,
+                       const T* __restrict__ charges, int64_t n_particles, int nx, int ny,
+                       T* __restrict__ out) {
+  const int64_t b = blockIdx.y;
+  const T* e = extent + b * 2 * D;
+  const T* p = positions + b * n_particles * D;
+  const T* q = charges ? charges + b * n_particles : nullptr;
+  T* grid = out + b * static_cast<int64_t>(nx) * (D == 2 ? ny : 1);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_particles;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const T charge = q ? q[i] : T(1);
+    const AxisDeposit<T> ax = deposit_axis(p[i * D], e[0], e[1], nx);
+    if (D == 1) {
+      if (!ax.inside) continue;
+      if (ax.w_lo != T(0)) atomicAdd(&grid[ax.lo], charge * ax.w_lo);
+      if (ax.w_hi != T(0)) atomicAdd(&grid[ax.hi], charge * ax.w_hi);
+    } else {
+      const AxisDeposit<T> ay = deposit_axis(p[i * D + 1], e[2], e[3], ny);
+      if (!(ax.inside && ay.inside)) continue;
+      const int ix[2] = {ax.lo, ax.hi}, iy[2] = {ay.lo, ay.hi};
+      const T wx[2] = {ax.w_lo, ax.w_hi}, wy[2] = {ay.w_lo, ay.w_hi};
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const T w = wx[a] * wy[c];
+          if (w != T(0)) atomicAdd(&grid[ix[a] * ny + iy[c]], charge * w);
+        }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // 4. integrated Green function
 // ---------------------------------------------------------------------------------------
@@ -1261,6 +1296,38 @@ extern "C" int ch_cic_deposit3d(const void* positions, const void* extent, const
         static_cast<const double*>(positions), static_cast<const double*>(extent),
         static_cast<const double*>(charges), n_particles, nx, ny, nz,
         static_cast<double*>(grid_out));
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_cic_deposit(const void* positions, const void* extent, const void* charges,
+                              int64_t n_particles, int64_t n_beams, int32_t dims, int32_t nx,
+                              int32_t ny, int32_t nz, int32_t dtype, void* grid_out,
+                              void* stream) {
+  CH_SC_COMMON_CHECKS("ch_cic_deposit");
+  CH_REQUIRE(dims >= 1 && dims <= 3, "ch_cic_deposit: dims must be 1, 2 or 3, got %d", dims);
+  if (dims == 3)
+    return ch_cic_deposit3d(positions, extent, charges, n_particles, n_beams, nx, ny, nz, dtype,
+                            grid_out, stream);
+  CH_REQUIRE(positions && extent && grid_out && n_particles > 0, "ch_cic_deposit: bad arguments");
+  CH_REQUIRE(nx > 0 && (dims == 1 || ny > 0), "ch_cic_deposit: bad grid (%d, %d)", nx, ny);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t elem = dtype == CH_F32 ? 4 : 8;
+  const int64_t cells = static_cast<int64_t>(nx) * (dims == 2 ? ny : 1);
+  CH_CUDA(cudaMemsetAsync(grid_out, 0, elem * cells * n_beams, s));
+  dim3 grid(ch::blocks_for(n_particles, 256), static_cast<unsigned>(n_beams));
+  auto launch = [&](auto zero) {
+    using T = decltype(zero);
+    if (dims == 1)
+      ch::cic_deposit_low_kernel<T, 1><<<grid, 256, 0, s>>>(
+          static_cast<const T*>(positions), static_cast<const T*>(extent),
+          static_cast<const T*>(charges), n_particles, nx, 1, static_cast<T*>(grid_out));
+    else
+      ch::cic_deposit_low_kernel<T, 2><<<grid, 256, 0, s>>>(
+          static_cast<const T*>(positions), static_cast<const T*>(extent),
+          static_cast<const T*>(charges), n_particles, nx, ny, static_cast<T*>(grid_out));
+  };
+  if (dtype == CH_F32) launch(0.0f); else launch(0.0);
   CH_LAUNCH_CHECK();
   return CH_OK;
 }

@@ -303,27 +303,32 @@ def track_fused(element, incoming, prepared: Prepared | None = None, fuse_record
 
 
 def cloud_in_cell_charge_deposition(positions, bins, extent=None, charges=None):
-    """3-D cloud-in-cell deposit with the signature of cheetah/utils/cloud_in_cell.py:8-13."""
-    if positions.shape[-1] != 3:
-        raise NotImplementedError("cheetah_b200 accelerates the 3-D deposit only (SURVEY.md 8f)")
+    """Cloud-in-cell deposit with the signature of cheetah/utils/cloud_in_cell.py:8-64 for 1, 2
+    or 3 position dimensions: ``positions (..., N, d)`` -> ``(..., *bins)``."""
+    dims = positions.shape[-1]
+    if dims not in (1, 2, 3):
+        raise NotImplementedError(
+            "cheetah_b200 accelerates cloud-in-cell deposits in 1, 2 and 3 dimensions"
+        )
     if not positions.is_cuda:
         raise RuntimeError("cheetah_b200: positions must be on a CUDA device (no CPU fallback)")
     dtype, device = positions.dtype, positions.device
-    shape = [bins] * 3 if isinstance(bins, int) else list(bins)
-    assert len(shape) == 3, "Number of bin values must match number of position dimensions."
+    shape = [bins] * dims if isinstance(bins, int) else list(bins)
+    assert len(shape) == dims, "Number of bin values must match number of position dimensions."
     if extent is None:
         extent = torch.stack([positions.amin(dim=-2), positions.amax(dim=-2)], dim=-1)
     vector_shape = tuple(positions.shape[:-2])
     n = positions.shape[-2]
     n_beams = max(1, math.prod(vector_shape))
-    pos = positions.reshape(n_beams, n, 3).contiguous()
-    ext = extent.to(dtype).expand(*vector_shape, 3, 2).reshape(n_beams, 3, 2).contiguous()
+    pos = positions.reshape(n_beams, n, dims).contiguous()
+    ext = extent.to(dtype).expand(*vector_shape, dims, 2).reshape(n_beams, dims, 2).contiguous()
     q = None
     if charges is not None:
         q = charges.to(dtype).expand(*vector_shape, n).reshape(n_beams, n).contiguous()
     grid = torch.empty((n_beams, *shape), dtype=dtype, device=device)
+    padded = shape + [1] * (3 - dims)
     with _capi.device_guard(device):
-        _capi.check(_capi.lib().ch_cic_deposit3d(
-            pos.data_ptr(), ext.data_ptr(), _capi.ptr(q), n, n_beams, *shape,
+        _capi.check(_capi.lib().ch_cic_deposit(
+            pos.data_ptr(), ext.data_ptr(), _capi.ptr(q), n, n_beams, dims, *padded,
             _capi.dtype_code(dtype), grid.data_ptr(), _capi.current_stream(device)))
     return grid.reshape(*vector_shape, *shape)

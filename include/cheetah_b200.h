@@ -377,6 +377,14 @@ int ch_cic_deposit3d(const void* positions, const void* extent, const void* char
                      int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                      void* grid, void* stream);
 
+/* The same for 1, 2 or 3 position dimensions (`dims`; the 1-D / 2-D specialisations,
+ * cheetah/utils/cloud_in_cell.py:67-241): positions [B][N][dims], extent [B][dims][2], grid
+ * [B][nx (* ny (* nz))]; unused bin counts are ignored.                                         */
+int ch_cic_deposit(const void* positions, const void* extent, const void* charges,
+                   int64_t n_particles, int64_t n_beams, int32_t dims,
+                   int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                   void* grid, void* stream);
+
 /* Integrated Green function: _integrated_potential + _integrated_green_function
  * (space_charge_kick.py:103-123, :163-291).  The antiderivative is evaluated ONCE per
  * half-shifted lattice point in fp64 (lattice [B][(nx+1)(ny+1)(nz+1)] doubles; the reference

@@ -318,6 +318,12 @@ def make_cloud_in_cell() -> None:
             positions.to(dtype), bins, extent.to(dtype), charges.to(dtype)
         )
         arrays[f"grid.{tag}"] = np64(grid)
+        for dims in (1, 2):  # the 1-D and 2-D specialisations (cloud_in_cell.py:67-241)
+            grid = cloud_in_cell_charge_deposition(
+                positions[..., :dims].to(dtype), bins[:dims], extent[..., :dims, :].to(dtype),
+                charges.to(dtype),
+            )
+            arrays[f"grid{dims}d.{tag}"] = np64(grid)
     np.savez_compressed(OUT / "cloud_in_cell.npz", **arrays)
     print("cloud_in_cell: done")
 
@@ -753,6 +759,9 @@ def make_diagnostics() -> None:
 
 
 if __name__ == "__main__":
+    if "--only-cic" in sys.argv:
+        make_cloud_in_cell()
+        sys.exit(0)
     if "--only-consistency" in sys.argv:
         make_consistency()
         sys.exit(0)

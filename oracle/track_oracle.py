@@ -682,6 +682,43 @@ def from_xyz_pxpypz(xp, energy, mass_eV) -> torch.Tensor:
     return out
 
 
+def cic_deposit_nd(positions, bins, extent, charges) -> torch.Tensor:
+    """1-, 2- or 3-D cloud-in-cell deposit (cheetah/utils/cloud_in_cell.py:67-384; the three
+    specialisations share the per-axis rule): positions (..., N, d), extent (..., d, 2),
+    charges (..., N) -> (..., *bins)."""
+    dims = positions.shape[-1]
+    nbins = [int(n) for n in bins]
+    vector_shape = positions.shape[:-2]
+    total = 1
+    for n in nbins:
+        total *= n
+    grid = positions.new_zeros(*vector_shape, total)
+    inside = torch.ones_like(charges, dtype=torch.bool)
+    corners = []
+    for d in range(dims):
+        p = positions[..., d]
+        left, right = extent[..., d, 0].unsqueeze(-1), extent[..., d, 1].unsqueeze(-1)
+        inside = inside & (p >= left) & (p <= right)
+        q = (p - left) / ((right - left) / nbins[d]) - 0.5
+        base = q.floor().long()
+        frac = q - base
+        corners.append([
+            (base.clamp(0, nbins[d] - 1), (1.0 - frac) * ((base >= 0) & (base < nbins[d]))),
+            ((base + 1).clamp(0, nbins[d] - 1), frac * ((base + 1 >= 0) & (base + 1 < nbins[d]))),
+        ])
+    masked = charges * inside
+    import itertools
+
+    for choice in itertools.product((0, 1), repeat=dims):
+        index = torch.zeros_like(corners[0][0][0])
+        weight = masked
+        for d, c in enumerate(choice):
+            index = index * nbins[d] + corners[d][c][0]
+            weight = weight * corners[d][c][1]
+        grid.scatter_add_(dim=-1, index=index, src=weight)
+    return grid.reshape(*vector_shape, *nbins)
+
+
 def cic_deposit_3d(positions, bins, extent, charges) -> torch.Tensor:
     """3-D cloud-in-cell deposit (cheetah/utils/cloud_in_cell.py:244-384).
 

@@ -194,6 +194,44 @@ def test_cloud_in_cell_matches_reference_and_histogram(dtype):
     assert float(grid.sum()) == 2.0
 
 
+@pytest.mark.parametrize("dims", [1, 2])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_cloud_in_cell_1d_and_2d(dims, dtype):
+    """cloud_in_cell_charge_deposition for 1 and 2 position dimensions (cloud_in_cell.py:67-241):
+    reference outputs, exact histogram at bin centres, missing extent / charges, exact total."""
+    from cheetah_b200.space_charge import cloud_in_cell_charge_deposition
+
+    data = gu.load_npz("cloud_in_cell.npz")
+    tag = "f64" if dtype == torch.float64 else "f32"
+    bins = tuple(int(b) for b in data["bins"])[:dims]
+    grid = cloud_in_cell_charge_deposition(
+        gu.tensor(data["positions"], dtype)[..., :dims].to(DEVICE), bins,
+        gu.tensor(data["extent"], dtype)[..., :dims, :].to(DEVICE),
+        gu.tensor(data["charges"], dtype).to(DEVICE),
+    )
+    expected = gu.tensor(data[f"grid{dims}d.{tag}"], dtype)
+    assert grid.shape == expected.shape
+    assert rel_err(grid, expected) < (1e-13 if dtype == torch.float64 else 2e-6)
+
+    g = torch.Generator().manual_seed(1)
+    bins = (8, 16)[:dims]
+    idx = torch.stack([torch.randint(0, b, (4000,), generator=g) for b in bins], dim=-1)
+    extent = torch.tensor([[-1.0, 1.0], [0.0, 4.0]], dtype=dtype)[:dims]
+    width = (extent[:, 1] - extent[:, 0]) / torch.tensor(bins, dtype=dtype)
+    positions = extent[:, 0] + (idx.to(dtype) + 0.5) * width
+    hist = torch.histogramdd(positions.double(), bins=list(bins),
+                             range=extent.double().flatten().tolist()).hist
+    grid = cloud_in_cell_charge_deposition(positions.to(DEVICE), bins, extent.to(DEVICE))
+    assert torch.equal(grid.cpu().double(), hist)
+    # extent inferred from the positions, integer bin count (cloud_in_cell.py:31-38)
+    inferred = cloud_in_cell_charge_deposition(positions.to(DEVICE), 8)
+    assert tuple(inferred.shape) == (8,) * dims
+    span = torch.stack([positions.amin(dim=-2), positions.amax(dim=-2)], dim=-1)
+    expected = oracle.cic_deposit_nd(positions, (8,) * dims, span, torch.ones(4000, dtype=dtype))
+    # ~500 float32 additions per bin in a different order than scatter_add_
+    assert rel_err(inferred, expected) < (1e-13 if dtype == torch.float64 else 2e-5)
+
+
 # ---- fused stages: kick + following linear section + moments of the next kick ------------------
 def _fodo_with_kicks(dtype, vector_k1=None, aperture=False, grid=(16, 16, 16)):
     import cheetah_b200 as cb
