@@ -658,6 +658,17 @@ class Segment(Element):
                 flat.append(element)
         return Segment(elements=flat, name=self.name, sanitize_name=False)
 
+    @classmethod
+    def from_lattice_json(cls, filepath, name: str | None = None, device=None, dtype=None
+                          ) -> "Segment":
+        """Load the reference's LatticeJSON format (segment.py:370-384)."""
+        from . import latticejson
+
+        segment = latticejson.load_segment(filepath, device=device, dtype=dtype)
+        if name is not None:
+            segment.name = name
+        return segment
+
     # ---- container helpers (segment.py:73-229, :576-656) ------------------------------------
     @property
     def element_names(self) -> list[str]:

@@ -204,3 +204,50 @@ def test_segment_container_helpers_mirror_the_reference():
     with pytest.raises(AssertionError, match="not skippable"):
         cb.CustomTransferMap.from_merging_elements(
             [cb.Drift(length=t(1.0), tracking_method="drift_kick_drift")], incoming_beam=None)
+
+
+def test_from_lattice_json_reads_the_reference_format(tmp_path):
+    """Segment.from_lattice_json (segment.py:370-384, latticejson.py:156-260)."""
+    import json
+    from pathlib import Path
+
+    lattice = {
+        "version": "cheetah-0.7", "title": "test", "info": "", "root": "cell",
+        "elements": {
+            "d1": ["Drift", {"length": 0.5, "tracking_method": "linear"}],
+            "q1": ["Quadrupole", {"length": 0.2, "k1": [1.0, -2.0], "misalignment": [0.0, 1e-4],
+                                  "tilt": 0.1, "num_steps": 3, "tracking_method": "drift_kick_drift",
+                                  "metadata": {"pv": "Q1:K1"}}],
+            "a1": ["Aperture", {"x_max": 1e-3, "y_max": 2e-3, "shape": "elliptical",
+                                "is_active": True}],
+            "s1": ["Screen", {"resolution": [64, 48], "pixel_size": [1e-5, 2e-5], "binning": 2,
+                              "method": "histogram", "is_active": False}],
+            "bpm": ["BPM", {"is_active": False}],
+            "sup": ["Superimposed", {"base_element": "q1", "superimposed_element": "bpm"}],
+        },
+        "lattices": {"cell": ["d1", "inner", "s1"], "inner": ["q1", "a1", "sup"]},
+    }
+    path = tmp_path / "lattice.json"
+    path.write_text(json.dumps(lattice))
+    segment = cb.Segment.from_lattice_json(path, dtype=torch.float64)
+    assert segment.name == "cell" and [e.name for e in segment.elements] == ["d1", "inner", "s1"]
+    inner = segment.elements[1]
+    assert isinstance(inner, cb.Segment) and inner.q1.tracking_method == "drift_kick_drift"
+    assert inner.q1.k1.dtype == torch.float64 and inner.q1.k1.tolist() == [1.0, -2.0]
+    assert inner.q1.num_steps == 3 and inner.q1.metadata == {"pv": "Q1:K1"}
+    assert inner.a1.shape == "elliptical" and float(inner.a1.y_max) == 2e-3
+    assert segment.s1.resolution == (64, 48) and segment.s1.method == "histogram"
+    assert isinstance(inner.sup, cb.Superimposed) and len(inner.sup.flattened().elements) == 3
+    assert torch.allclose(segment.length, torch.tensor(0.5 + 0.2 + 0.2, dtype=torch.float64))
+
+    ares = Path("/root/reference/docs/examples/ARESlatticeStage3v1_9.json")
+    if ares.exists():  # only in the build container; the GPU box has the converted fixture
+        from tests import golden_utils as gu
+
+        loaded = cb.Segment.from_lattice_json(ares).flattened().elements
+        golden = gu.ares_lattice(torch.float32)
+        assert [type(e).__name__ for e in loaded] == [d["type"] for d in golden]
+        assert [e.name for e in loaded] == [d["name"] for d in golden]
+        for element, description in zip(loaded, golden):
+            if "length" in description:
+                assert torch.equal(element.length, description["length"])
