@@ -52,6 +52,9 @@ class LinearSection:
     lattice_shape: tuple = ()          # broadcast vector shape of all parameters
     length_shape: tuple = ()           # ... of the length parameters only
     survival_shape: tuple = ()         # ... of everything up to and including the last aperture
+    map_shape: tuple = ()              # ... of the parameters of the non-aperture ops only
+    n_map_ops: int = 0                 # non-aperture ops (identity elements included)
+    maps_before_last_aperture: bool = False
     has_maps: bool = False             # any non-identity op
     apertures: list = field(default_factory=list)
     cavity: object = None              # active Cavity closing the section (element, gain flag)
@@ -430,19 +433,30 @@ def _finish_section(section: LinearSection, ops: list, device, target_shape, wat
     shapes, length_shapes = [tuple(target_shape)], []
     survival_shape: tuple = ()
     running: tuple = ()
+    map_shape: tuple = ()
+    n_map_ops, maps_before_last_aperture = 0, False
     for op in ops[section.op_begin : section.op_end]:
         for slot in op.slots:
             _check_tensor(slot.tensor, device, f"parameter of element {op.element.name!r}")
             shapes.append(slot.vector_shape)
             running = torch.broadcast_shapes(running, slot.vector_shape)
+            if op.opcode != _capi.OP_APERTURE:
+                map_shape = torch.broadcast_shapes(map_shape, slot.vector_shape)
             if slot.is_length:
                 length_shapes.append(slot.vector_shape)
         if op.opcode == _capi.OP_APERTURE:
             survival_shape = running
+            maps_before_last_aperture = n_map_ops > 0
+        else:
+            n_map_ops += 1
     full = tuple(torch.broadcast_shapes(*shapes))
     section.lattice_shape = full
     section.length_shape = tuple(torch.broadcast_shapes(*length_shapes)) if length_shapes else ()
     section.survival_shape = tuple(survival_shape)
+    if isinstance(section, LinearSection):
+        section.map_shape = tuple(map_shape)
+        section.n_map_ops = n_map_ops
+        section.maps_before_last_aperture = maps_before_last_aperture
 
     for op in ops[section.op_begin : section.op_end]:
         resolved = []

@@ -198,6 +198,10 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
         ).to(beam.energy.dtype)
 
     if not section.has_maps and section.n_apertures == 0 and moments is None:
+        # identity elements only: the reference still multiplies by eye(7).repeat(energy.shape)
+        widened = tuple(_bshape(vp, beam.energy.shape))
+        if widened != vp:
+            particles = particles.expand(*widened, n, 7)
         return _new_beam(beam, particles, beam.energy, beam.particle_charges,
                          beam.survival_probabilities, new_s, beam.species.clone(),
                          getattr(beam, "_unit_seventh", None))
@@ -271,17 +275,30 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
     if moments == "only":
         return None, observed
 
+    def narrowed(tensor, keep: tuple, inner: tuple):
+        """The kernel works on the full broadcast batch ``vo``; the reference's tensors only
+        carry the vector dims of what actually shaped them."""
+        if keep == vo:
+            return tensor
+        lead = len(vo) - len(keep)
+        padded = (1,) * (len(vo) - lead - len(keep)) + keep
+        index = [0] * lead + [slice(None) if k == v else 0 for k, v in zip(padded, vo[lead:])]
+        return tensor[tuple(index)].reshape(*keep, *inner)
+
+    energy_shape = tuple(beam.energy.shape)
     if survival_out is not None:
         # reference shape: broadcast(survival_in, particles vector dims, everything up to and
-        # including the last aperture); later (post-aperture) vectorised elements do not widen it
-        keep = tuple(_bshape(vs, vp, section.survival_shape, beam.energy.shape))
-        if keep != vo:
-            lead = len(vo) - len(keep)
-            index = [0] * lead + [slice(None) if k > 1 else 0 for k in keep]
-            survival_out = survival_out[tuple(index)].reshape(*keep, n)
-        new_survival = survival_out
+        # including the last aperture); later (post-aperture) vectorised elements do not widen
+        # it, and the beam energy only enters through a map in front of the aperture
+        keep = tuple(_bshape(vs, vp, section.survival_shape,
+                             energy_shape if section.maps_before_last_aperture else ()))
+        new_survival = narrowed(survival_out, keep, (n,))
     else:
         new_survival = beam.survival_probabilities
+    if out is not None:
+        # particles: vectorised aperture limits do not widen them (aperture.py:108-132)
+        keep = tuple(_bshape(vp, section.map_shape, energy_shape if section.n_map_ops else ()))
+        out = narrowed(out, keep, (n, 7))
 
     outgoing = _new_beam(beam, out, new_energy, beam.particle_charges, new_survival, new_s,
                          beam.species.clone(), _unit_seventh(beam))
