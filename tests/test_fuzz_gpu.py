@@ -92,3 +92,127 @@ def test_random_vectorised_lattices(seed):
     assert tuple(out.s.shape) == tuple(expected["s"].shape)
     assert torch.allclose(out.s.cpu(), expected["s"], rtol=1e-12)
     assert tuple(out.energy.shape) == tuple(expected["energy"].shape)
+
+
+def random_mixed_lattice(seed: int) -> tuple[list, tuple]:
+    """Linear, drift_kick_drift and second_order elements, markers and apertures."""
+    g = torch.Generator().manual_seed(7000 + seed)
+    pick = lambda: SHAPES[int(torch.randint(0, len(SHAPES), (1,), generator=g))]  # noqa: E731
+    choice = lambda options: options[int(torch.randint(0, len(options), (1,), generator=g))]  # noqa: E731
+    lattice = []
+    for i in range(int(torch.randint(3, 10, (1,), generator=g))):
+        kind = choice(["Drift", "Drift", "Quadrupole", "Quadrupole", "Dipole", "Sextupole",
+                       "TransverseDeflectingCavity", "Marker", "Aperture", "HorizontalCorrector"])
+        el = {"type": kind, "name": f"e{i}"}
+        if kind not in ("Marker", "Aperture"):
+            el["length"] = _vector(g, 0.1, 0.8, pick())
+        if kind == "Drift":
+            el["tracking_method"] = choice(["linear", "drift_kick_drift", "second_order"])
+        elif kind == "Quadrupole":
+            el["k1"] = _vector(g, -6.0, 6.0, pick())
+            el["tilt"] = _vector(g, -0.3, 0.3, pick())
+            el["misalignment"] = _vector(g, -1e-4, 1e-4, (*pick(), 2))
+            el["tracking_method"] = choice(["linear", "drift_kick_drift", "second_order"])
+            el["num_steps"] = int(torch.randint(1, 5, (1,), generator=g))
+        elif kind == "Dipole":
+            el["angle"] = _vector(g, 0.05, 0.3, pick())
+            el["dipole_e1"] = _vector(g, -0.1, 0.1, pick())
+            el["dipole_e2"] = _vector(g, -0.1, 0.1, ())
+            el["tilt"] = _vector(g, -0.2, 0.2, pick())
+            el["fringe_integral"] = _vector(g, 0.0, 0.5, ())
+            el["gap"] = _vector(g, 0.0, 0.05, ())
+            el["tracking_method"] = choice(["linear", "drift_kick_drift", "second_order"])
+            el["fringe_at"] = choice(["both", "entrance", "exit", "neither"])
+        elif kind == "Sextupole":
+            el["k2"] = _vector(g, -30.0, 30.0, pick())
+            el["tilt"] = _vector(g, -0.3, 0.3, ())
+            el["misalignment"] = _vector(g, -1e-4, 1e-4, (2,))
+            el["tracking_method"] = choice(["linear", "second_order"])
+        elif kind == "TransverseDeflectingCavity":
+            el["voltage"] = _vector(g, -5e6, 5e6, pick())
+            el["phase"] = _vector(g, 0.0, 1.0, pick())
+            el["frequency"] = _vector(g, 1e9, 3e9, ())
+            el["tilt"] = _vector(g, -0.2, 0.2, ())
+            el["misalignment"] = _vector(g, -1e-4, 1e-4, (2,))
+        elif kind == "HorizontalCorrector":
+            el["angle"] = _vector(g, -1e-4, 1e-4, pick())
+        elif kind == "Aperture":
+            el["x_max"] = _vector(g, 2e-4, 8e-4, pick())
+            el["y_max"] = _vector(g, 2e-4, 8e-4, ())
+            el["shape"] = choice(["rectangular", "elliptical"])
+            el["is_active"] = True
+        lattice.append(el)
+    beam_shape = choice([(), (), (3,), (2, 3)])
+    return lattice, beam_shape
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_lattices_with_nonlinear_elements(seed):
+    lattice, beam_shape = random_mixed_lattice(seed)
+    g = torch.Generator().manual_seed(9000 + seed)
+    n = 193
+    sigma = torch.tensor([2e-4, 3e-5, 2e-4, 3e-5, 1e-4, 1e-3], dtype=torch.float64)
+    particles = torch.randn((*beam_shape, n, 7), generator=g, dtype=torch.float64)
+    particles[..., :6] *= sigma
+    particles[..., 6] = 1.0
+    energy = _vector(g, 5e7, 2e8, ())
+    beam = oracle.make_beam(particles, energy)
+    expected = oracle.track(lattice, beam)
+    if not torch.isfinite(expected["particles"]).all():
+        pytest.skip("random optics blew the beam up (transverse momentum > total momentum)")
+    out = gu.product_segment(lattice, DEVICE, torch.float64).track(
+        gu.product_beam(beam, DEVICE, torch.float64))
+    assert tuple(out.particles.shape) == tuple(expected["particles"].shape), (
+        out.particles.shape, expected["particles"].shape)
+    assert gu.column_scaled_error(out.particles, expected["particles"]) < 1e-9
+    assert tuple(out.survival_probabilities.shape) == tuple(expected["survival_probabilities"].shape)
+    assert torch.equal(out.survival_probabilities.cpu(), expected["survival_probabilities"])
+    assert tuple(out.s.shape) == tuple(expected["s"].shape)
+    assert torch.allclose(out.s.cpu(), expected["s"], rtol=1e-12)
+    assert torch.allclose(out.energy.cpu(), expected["energy"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_space_charge_lattices(seed):
+    """FODO-like lines with SpaceChargeKicks and randomly vectorised beams / charges / lengths /
+    quadrupole strengths (the fused kick + linear section + next-moments path included)."""
+    g = torch.Generator().manual_seed(300 + seed)
+    choice = lambda options: options[int(torch.randint(0, len(options), (1,), generator=g))]  # noqa: E731
+    batch = choice([(), (2,), (3,)])
+    vec = lambda low, high: _vector(g, low, high, choice([(), batch]))  # noqa: E731
+    grid = choice([(8, 8, 8), (16, 16, 16), (8, 16, 8)])
+    lattice = []
+    for i in range(int(torch.randint(1, 4, (1,), generator=g))):
+        lattice += [
+            {"type": "Quadrupole", "name": f"q{i}", "length": _vector(g, 0.1, 0.3, ()),
+             "k1": vec(-4.0, 4.0)},
+            {"type": "Drift", "name": f"d{i}a", "length": vec(0.2, 0.6)},
+            {"type": "SpaceChargeKick", "name": f"sc{i}", "effect_length": vec(0.5, 1.5),
+             "grid_shape": list(grid)},
+        ]
+        if choice([True, False]):
+            lattice.append({"type": "Drift", "name": f"d{i}b", "length": _vector(g, 0.2, 0.6, ())})
+        if choice([True, False, False]):
+            lattice.append({"type": "Aperture", "name": f"a{i}", "x_max": _vector(g, 3e-4, 6e-4, ()),
+                            "y_max": _vector(g, 3e-4, 6e-4, ()), "shape": "rectangular",
+                            "is_active": True})
+    n = 3000
+    beam_shape = choice([(), batch])
+    sigma = torch.tensor([2e-4, 3e-5, 2e-4, 3e-5, 1e-4, 1e-3], dtype=torch.float64)
+    particles = torch.randn((*beam_shape, n, 7), generator=g, dtype=torch.float64)
+    particles[..., :6] *= sigma
+    particles[..., 6] = 1.0
+    charge_shape = choice([(), batch])
+    charges = -_vector(g, 1e-10, 1e-9, (*charge_shape, 1)).expand(*charge_shape, n) / n
+    beam = oracle.make_beam(particles, torch.tensor(5e7, dtype=torch.float64),
+                            particle_charges=charges.contiguous())
+    expected = oracle.track(lattice, beam)
+    out = gu.product_segment(lattice, DEVICE, torch.float64).track(
+        gu.product_beam(beam, DEVICE, torch.float64))
+    assert tuple(out.particles.shape) == tuple(expected["particles"].shape), (
+        out.particles.shape, expected["particles"].shape)
+    assert gu.column_scaled_error(out.particles, expected["particles"]) < 1e-8
+    assert tuple(out.survival_probabilities.shape) == tuple(expected["survival_probabilities"].shape)
+    mismatches = int((out.survival_probabilities.cpu() != expected["survival_probabilities"]).sum())
+    assert mismatches == 0
+    assert torch.allclose(out.s.cpu(), expected["s"], rtol=1e-12)
