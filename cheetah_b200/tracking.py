@@ -275,16 +275,6 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
     if moments == "only":
         return None, observed
 
-    def narrowed(tensor, keep: tuple, inner: tuple):
-        """The kernel works on the full broadcast batch ``vo``; the reference's tensors only
-        carry the vector dims of what actually shaped them."""
-        if keep == vo:
-            return tensor
-        lead = len(vo) - len(keep)
-        padded = (1,) * (len(vo) - lead - len(keep)) + keep
-        index = [0] * lead + [slice(None) if k == v else 0 for k, v in zip(padded, vo[lead:])]
-        return tensor[tuple(index)].reshape(*keep, *inner)
-
     energy_shape = tuple(beam.energy.shape)
     if survival_out is not None:
         # reference shape: broadcast(survival_in, particles vector dims, everything up to and
@@ -292,17 +282,27 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
         # it, and the beam energy only enters through a map in front of the aperture
         keep = tuple(_bshape(vs, vp, section.survival_shape,
                              energy_shape if section.maps_before_last_aperture else ()))
-        new_survival = narrowed(survival_out, keep, (n,))
+        new_survival = _narrowed(survival_out, vo, keep, (n,))
     else:
         new_survival = beam.survival_probabilities
     if out is not None:
         # particles: vectorised aperture limits do not widen them (aperture.py:108-132)
         keep = tuple(_bshape(vp, section.map_shape, energy_shape if section.n_map_ops else ()))
-        out = narrowed(out, keep, (n, 7))
+        out = _narrowed(out, vo, keep, (n, 7))
 
     outgoing = _new_beam(beam, out, new_energy, beam.particle_charges, new_survival, new_s,
                          beam.species.clone(), _unit_seventh(beam))
     return outgoing if moments is None else (outgoing, observed)
+
+
+def _narrowed(tensor, vo: tuple, keep: tuple, inner: tuple):
+    """The kernels work on the full broadcast batch ``vo``; the reference's tensors only carry
+    the vector dims of what actually shaped them."""
+    if keep == vo:
+        return tensor
+    lead = len(vo) - len(keep)
+    index = [0] * lead + [slice(None) if k == v else 0 for k, v in zip(keep, vo[lead:])]
+    return tensor[tuple(index)].reshape(*keep, *inner)
 
 
 def _track_nonlinear_run(program, run, beam):
@@ -567,7 +567,9 @@ def _track_parameter_beam(program, beam):
                 _capi.ptr(record_index), cavity_offset, n_out, mu_out.data_ptr(),
                 cov_out.data_ptr(), _capi.dtype_code(dtype), _capi.current_stream(device),
             ))
-        mu, cov = mu_out, cov_out
+        # vectorised aperture limits do not shape a ParameterBeam (aperture.py:108-113)
+        keep = tuple(_bshape(vb, stage.map_shape, tuple(energy.shape) if stage.n_map_ops else ()))
+        mu, cov = _narrowed(mu_out, vo, keep, (7,)), _narrowed(cov_out, vo, keep, (7, 7))
         if stage.cavity is not None:
             cavity = stage.cavity[0]
             energy = energy + (

@@ -216,3 +216,63 @@ def test_random_space_charge_lattices(seed):
     mismatches = int((out.survival_probabilities.cpu() != expected["survival_probabilities"]).sum())
     assert mismatches == 0
     assert torch.allclose(out.s.cpu(), expected["s"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_random_vectorised_lattices_float32(seed):
+    """The same random lattices in float32 against the float64 oracle on float32-rounded inputs:
+    3e-6 x column maximum; survival may differ for a particle within float32 rounding of an
+    aperture edge (at most 2 of 257 x settings here, none in practice)."""
+    from oracle import lattice_io
+
+    lattice, beam_shape = random_lattice(seed)
+    g = torch.Generator().manual_seed(1000 + seed)
+    n = 257
+    sigma = torch.tensor([2e-4, 3e-5, 2e-4, 3e-5, 1e-4, 1e-3], dtype=torch.float64)
+    particles = torch.randn((*beam_shape, n, 7), generator=g, dtype=torch.float64)
+    particles[..., :6] *= sigma
+    particles[..., 6] = 1.0
+    energy = _vector(g, 5e7, 2e8, ())
+    beam = oracle.make_beam(particles, energy)
+    lattice32 = lattice_io.cast(lattice_io.cast(lattice, torch.float32), torch.float64)
+    beam32 = {k: v.to(torch.float32).to(torch.float64) for k, v in beam.items()}
+    expected = oracle.track(lattice32, beam32)
+    out = gu.product_segment(lattice, DEVICE, torch.float32).track(
+        gu.product_beam(beam, DEVICE, torch.float32))
+    assert out.particles.dtype == torch.float32
+    assert tuple(out.particles.shape) == tuple(expected["particles"].shape)
+    assert gu.column_scaled_error(out.particles, expected["particles"]) < 3e-6
+    flips = int((out.survival_probabilities.cpu().double() != expected["survival_probabilities"]).sum())
+    assert flips <= 2, flips
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_random_lattices_parameter_beam(seed):
+    """ParameterBeam through random vectorised linear lattices (ch_apply_maps_parameter)."""
+    import warnings
+
+    import cheetah_b200 as cb
+
+    lattice, _ = random_lattice(seed)
+    g = torch.Generator().manual_seed(2000 + seed)
+    sigma = torch.tensor([2e-4, 3e-5, 2e-4, 3e-5, 1e-4, 1e-3, 0.0], dtype=torch.float64)
+    mixing = torch.eye(7, dtype=torch.float64) + 0.1 * torch.randn(7, 7, generator=g, dtype=torch.float64)
+    mixing[6], mixing[:, 6] = 0.0, 0.0
+    cov = mixing @ torch.diag(sigma.square()) @ mixing.T
+    mu = torch.cat([torch.randn(6, generator=g, dtype=torch.float64) * sigma[:6],
+                    torch.ones(1, dtype=torch.float64)])
+    energy = _vector(g, 5e7, 2e8, [(), (3,)][seed % 2])
+    mass = torch.tensor(oracle.ELECTRON_MASS_EV, dtype=torch.float64)
+    exp_mu, exp_cov, _ = oracle.track_parameter_beam(lattice, mu, cov, energy, mass)
+    beam = cb.ParameterBeam(mu.to(DEVICE), cov.to(DEVICE), energy.to(DEVICE),
+                            species=cb.Species("electron", device=DEVICE, dtype=torch.float64))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # apertures are ignored for ParameterBeams
+        out = gu.product_segment(lattice, DEVICE, torch.float64).track(beam)
+    assert tuple(out.mu.shape) == tuple(exp_mu.shape), (out.mu.shape, exp_mu.shape)
+    assert tuple(out.cov.shape) == tuple(exp_cov.shape)
+    scale = exp_mu.abs().amax(dim=-1, keepdim=True).clamp_min(1e-300)
+    assert float(((out.mu.cpu() - exp_mu).abs() / scale).max()) < 1e-9
+    diag = exp_cov.diagonal(dim1=-2, dim2=-1).abs().sqrt()
+    cscale = (diag.unsqueeze(-1) * diag.unsqueeze(-2))[..., :6, :6].clamp_min(1e-300)
+    assert float(((out.cov.cpu() - exp_cov).abs()[..., :6, :6] / cscale).max()) < 1e-8
