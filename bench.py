@@ -341,7 +341,8 @@ def main() -> None:
         o_ms = float(t[0]) / args.steps
         observables = {
             "what": "Segment.track_moments: mu, sigma (6 each) and surviving-particle count per "
-                    "setting from the apply kernel's epilogue; outgoing particles never written",
+                    "setting from observe_maps_kernel (packed FFMA2 pairs); outgoing particles never "
+                    "written",
             "value": args.settings * args.particles * N_ELEMENTS / (o_ms * 1e-3),
             "unit": UNIT,
             "ms_per_step": o_ms,

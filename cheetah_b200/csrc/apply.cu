@@ -503,6 +503,380 @@ apply_maps_kernel(const ApplyArgs<T> a) {
   if (a.bulk_out && tid == 0) bulk_wait<0>();
 }
 
+// ---- observables only, float32: packed-pair arithmetic ------------------------------------------
+// With nothing to write, Segment.track_moments is bound by the FP32 pipe, not by HBM: per
+// (particle, setting) ~66 multiply-adds (3 apertures, the map, 12 weighted sums) and the shared
+// beam stays in registers.  On sm_100 a 3-register FFMA issues every second cycle per SM
+// sub-partition; the packed FFMA2 / FADD2 / FMUL2 forms do two lanes' worth of work in the same
+// slot (the scalar kernel measured 21.2 ms for ARES x 1e6 particles x 4096 settings, i.e. the
+// scalar issue limit).  This kernel therefore keeps two particles per 64-bit register pair:
+// P = 8 particles per thread as 4 pairs, every coefficient of the record duplicated in shared
+// memory so that one broadcast LDS.128 delivers two ready-made (c, c) operands.  The chains are
+// the same fma sequences as in process_setting, so aperture masks are bit-identical to the
+// particle-writing kernel's.
+using f2 = float2;
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+
+// `n` duplicated coefficients (n even) from shared memory, two per 128-bit word
+template <int N>
+__device__ __forceinline__ void load_pairs(f2 (&dst)[N], const f2* src) {
+  static_assert(N % 2 == 0, "whole 128-bit words");
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    dst[2 * i] = f2{v.x, v.y};
+    dst[2 * i + 1] = f2{v.z, v.w};
+  }
+}
+
+template <bool UNIT7>
+__device__ __forceinline__ f2 affine_row2(const f2* c, const f2 (&p)[7]) {
+  f2 acc = UNIT7 ? c[6] : mul2(c[6], p[6]);
+#pragma unroll
+  for (int j = 5; j >= 0; --j) acc = fma2(c[j], p[j], acc);
+  return acc;
+}
+
+template <int PAIRS, bool UNIT7, bool SPARSE, int MOMENTS>
+__device__ __forceinline__ void observe_setting(const f2* rec2, int n_apertures,
+                                                uint32_t elliptical_mask,
+                                                const f2 (&p)[PAIRS][7], f2 (&sv)[PAIRS],
+                                                const float (&first_particle)[7],
+                                                float (&pilot)[6],
+                                                f2 (&acc)[MOMENTS == 2 ? 29 : 14]) {
+#pragma unroll 1
+  for (int ap = 0; ap < n_apertures; ++ap) {
+    f2 q[16];
+    load_pairs(q, rec2 + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
+    const float x_max = q[14].x, y_max = q[15].x;
+    f2 x[PAIRS], y[PAIRS];
+#pragma unroll
+    for (int k = 0; k < PAIRS; ++k) {
+      if constexpr (SPARSE) {
+        x[k] = fma2(q[0], p[k][0],
+                    fma2(q[1], p[k][1], fma2(q[5], p[k][5], UNIT7 ? q[6] : mul2(q[6], p[k][6]))));
+        y[k] = fma2(q[9], p[k][2], fma2(q[10], p[k][3], UNIT7 ? q[13] : mul2(q[13], p[k][6])));
+      } else {
+        x[k] = affine_row2<UNIT7>(q, p[k]);
+        y[k] = affine_row2<UNIT7>(q + 7, p[k]);
+      }
+    }
+    // one uniform branch per aperture; inside, predicates are combined without short-circuit
+    // jumps (2 FSETP + 1 FSEL per particle)
+    if ((elliptical_mask >> ap) & 1u) {
+      const float xx = mul_rn(x_max, x_max), yy = mul_rn(y_max, y_max);
+#pragma unroll
+      for (int k = 0; k < PAIRS; ++k) {
+        const bool lo = add_rn(div_rn(mul_rn(x[k].x, x[k].x), xx),
+                               div_rn(mul_rn(y[k].x, y[k].x), yy)) <= 1.0f;
+        const bool hi = add_rn(div_rn(mul_rn(x[k].y, x[k].y), xx),
+                               div_rn(mul_rn(y[k].y, y[k].y), yy)) <= 1.0f;
+        sv[k].x = lo ? sv[k].x : 0.0f;
+        sv[k].y = hi ? sv[k].y : 0.0f;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < PAIRS; ++k) {
+        const bool lo = inside(x[k].x, x_max) & inside(y[k].x, y_max);
+        const bool hi = inside(x[k].y, x_max) & inside(y[k].y, y_max);
+        sv[k].x = lo ? sv[k].x : 0.0f;
+        sv[k].y = hi ? sv[k].y : 0.0f;
+      }
+    }
+  }
+
+  f2 c[44];
+  load_pairs(c, rec2);
+  const f2* m = c + CH_RECORD_HEADER;
+  // pilot: image of the beam's particle 0 (scalar, same chains as process_setting), from the
+  // low halves of the coefficient pairs
+  {
+    const float w = UNIT7 ? 1.0f : first_particle[6];
+    const float(&in)[7] = first_particle;
+    if constexpr (SPARSE) {
+      auto constant = [&](int i) { return UNIT7 ? m[i * 7 + 6].x : m[i * 7 + 6].x * w; };
+      pilot[0] = fmaf(m[0].x, in[0], fmaf(m[1].x, in[1], fmaf(m[5].x, in[5], constant(0))));
+      pilot[1] = fmaf(m[7].x, in[0], fmaf(m[8].x, in[1], fmaf(m[12].x, in[5], constant(1))));
+      pilot[2] = fmaf(m[16].x, in[2], fmaf(m[17].x, in[3], constant(2)));
+      pilot[3] = fmaf(m[23].x, in[2], fmaf(m[24].x, in[3], constant(3)));
+      pilot[4] = fmaf(m[28].x, in[0],
+                      fmaf(m[29].x, in[1],
+                           fmaf(m[32].x, in[4], fmaf(m[33].x, in[5], constant(4)))));
+      pilot[5] = in[5];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float acc1 = UNIT7 ? m[i * 7 + 6].x : m[i * 7 + 6].x * w;
+#pragma unroll
+        for (int j = 5; j >= 0; --j) acc1 = fmaf(m[i * 7 + j].x, in[j], acc1);
+        pilot[i] = acc1;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) {
+    f2 out[6];
+    if constexpr (SPARSE) {
+      auto constant = [&](int i) { return UNIT7 ? m[i * 7 + 6] : mul2(m[i * 7 + 6], p[k][6]); };
+      out[0] = fma2(m[0], p[k][0], fma2(m[1], p[k][1], fma2(m[5], p[k][5], constant(0))));
+      out[1] = fma2(m[7], p[k][0], fma2(m[8], p[k][1], fma2(m[12], p[k][5], constant(1))));
+      out[2] = fma2(m[16], p[k][2], fma2(m[17], p[k][3], constant(2)));
+      out[3] = fma2(m[23], p[k][2], fma2(m[24], p[k][3], constant(3)));
+      out[4] = fma2(m[28], p[k][0],
+                    fma2(m[29], p[k][1],
+                         fma2(m[32], p[k][4], fma2(m[33], p[k][5], constant(4)))));
+      out[5] = p[k][5];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) out[i] = affine_row2<UNIT7>(m + i * 7, p[k]);
+    }
+    const f2 w = sv[k];
+    acc[0] = add2(acc[0], w);
+    acc[1] = fma2(w, w, acc[1]);
+    f2 d[6], wd[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      d[i] = add2(out[i], f2{-pilot[i], -pilot[i]});
+      wd[i] = mul2(w, d[i]);
+      acc[2 + i] = add2(acc[2 + i], wd[i]);
+      acc[8 + i] = fma2(wd[i], d[i], acc[8 + i]);
+    }
+    if constexpr (MOMENTS == 2) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) {
+          const int slot = 14 + i * (11 - i) / 2 + (j - i - 1);
+          acc[slot] = fma2(wd[i], d[j], acc[slot]);
+        }
+    }
+  }
+}
+
+template <int P, int THREADS, bool UNIT7, int MOMENTS>
+__global__ void __launch_bounds__(THREADS, MOMENTS == 2 ? 2 : 4)
+observe_maps_kernel(const ApplyArgs<float> a) {
+  static_assert(P % 2 == 0, "particles are processed in pairs");
+  constexpr int PAIRS = P / 2;
+  constexpr int TP = P * THREADS;
+  constexpr int NACC = MOMENTS == 2 ? 32 : 16;
+  constexpr int NSUM = MOMENTS == 2 ? 29 : 14;
+  constexpr int NOUT = MOMENTS == 2 ? CH_MOMENTS_COV : CH_MOMENTS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  const int rec_pitch = (a.record_len + 3) & ~3;  // keeps every buffer 16-byte aligned
+  f2* pairs0 = reinterpret_cast<f2*>(tile + TP * 7);
+  f2* pairs1 = pairs0 + rec_pitch;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(pairs1 + rec_pitch);
+  __shared__ float partial[2][THREADS / 32][NACC];
+  __shared__ float pilot_shared[2][8];
+
+  const int tid = threadIdx.x;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
+  const int count = static_cast<int>(min(static_cast<int64_t>(TP), a.n_particles - n0));
+  const int64_t b_begin = static_cast<int64_t>(blockIdx.y) * a.settings_per_cta;
+  const int64_t b_end = min(a.n_settings, b_begin + a.settings_per_cta);
+
+  if (a.bulk_in && tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  // The next setting's record and beam / survival offsets are FETCHED into registers before the
+  // arithmetic of the current setting and COMMITTED to shared memory after it, so that their L2
+  // latency is covered by ~250 packed instructions instead of stalling every warp once per setting.
+  constexpr int kFetch = 2;  // record entries per thread held in registers (the rest is copied)
+  float fetched[kFetch];
+  const bool beam_moves = a.particle_stride != 0;
+  const bool survival_moves = a.survival_in != nullptr && a.survival_stride != 0;
+  int64_t next_p_off = n0 * 7, next_s_off = n0;
+  auto fetch = [&](int64_t b) {
+    const float* src =
+        a.records + (a.record_index ? a.record_index[b] : b) * a.record_stride;
+#pragma unroll
+    for (int r = 0; r < kFetch; ++r) {
+      const int i = tid + r * THREADS;
+      fetched[r] = i < a.record_len ? src[i] : 0.0f;
+    }
+    // a shared beam / shared (or absent) incoming survival has one offset for every setting
+    if (beam_moves)
+      next_p_off = (a.particle_index ? a.particle_index[b] : b) * a.particle_stride + n0 * 7;
+    if (survival_moves)
+      next_s_off = (a.survival_index ? a.survival_index[b] : b) * a.survival_stride + n0;
+  };
+  auto commit = [&](f2* pairs, int64_t b) {
+#pragma unroll
+    for (int r = 0; r < kFetch; ++r) {
+      const int i = tid + r * THREADS;
+      if (i < a.record_len) pairs[i] = f2{fetched[r], fetched[r]};
+    }
+    if (a.record_len > kFetch * THREADS) {  // more than 13 apertures
+      const float* src =
+          a.records + (a.record_index ? a.record_index[b] : b) * a.record_stride;
+      for (int i = tid + kFetch * THREADS; i < a.record_len; i += THREADS) {
+        const float v = src[i];
+        pairs[i] = f2{v, v};
+      }
+    }
+  };
+  auto flush_moments = [&](int buf, int64_t b) {
+    if (tid < NSUM) {
+      double total = 0.0;
+#pragma unroll
+      for (int wi = 0; wi < THREADS / 32; ++wi) total += static_cast<double>(partial[buf][wi][tid]);
+      atomicAdd(&a.moments_out[b * NOUT + (tid < 14 ? tid : tid + 6)], total);
+    } else if (tid >= 32 && tid < 38 && blockIdx.x == 0) {
+      a.moments_out[b * NOUT + 14 + (tid - 32)] = static_cast<double>(pilot_shared[buf][tid - 32]);
+    }
+  };
+
+  fetch(b_begin);
+  commit(pairs0, b_begin);
+  __syncthreads();
+
+  f2 p[PAIRS][7];
+  float first[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) first[j] = 0.0f;
+  f2 sv_in[PAIRS];
+#pragma unroll
+  for (int k = 0; k < PAIRS; ++k) sv_in[k] = f2{1.0f, 1.0f};
+  int64_t loaded_particles = -1, loaded_survival = -1;
+  uint32_t phase = 0;
+
+  for (int64_t b = b_begin; b < b_end; ++b) {
+    const int it = static_cast<int>(b - b_begin);
+    const f2* rec2 = (it & 1) ? pairs1 : pairs0;
+    __syncthreads();  // this setting's record is complete; partial[(it - 1) & 1] is too
+    if (it > 0) flush_moments((it - 1) & 1, b - 1);
+
+    const int64_t p_off = next_p_off;
+    if (p_off != loaded_particles) {
+      const float* src = a.particles_in + p_off;
+      if (a.bulk_in) {
+        if (tid == 0) {
+          const uint32_t bytes = static_cast<uint32_t>(count) * 7u * sizeof(float);
+          mbar_expect_tx(bar, bytes);
+          bulk_load(tile, src, bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+      } else {
+        for (int i = tid; i < count * 7; i += THREADS) tile[i] = src[i];
+        __syncthreads();
+      }
+#pragma unroll
+      for (int k = 0; k < PAIRS; ++k) {
+        const int lo = tid + (2 * k) * THREADS, hi = lo + THREADS;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          p[k][j].x = lo < count ? tile[lo * 7 + j] : 0.0f;
+          p[k][j].y = hi < count ? tile[hi * 7 + j] : 0.0f;
+        }
+      }
+      const float* head = a.particles_in + (p_off - n0 * 7);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) first[j] = head[j];
+      loaded_particles = p_off;
+      __syncthreads();  // registers filled before the tile is loaded again
+    }
+    const int64_t s_off = next_s_off;
+    if (s_off != loaded_survival) {
+#pragma unroll
+      for (int k = 0; k < PAIRS; ++k) {
+        const int lo = tid + (2 * k) * THREADS, hi = lo + THREADS;
+        // lanes past the end of the beam must not count
+        sv_in[k].x = lo < count ? (a.survival_in ? a.survival_in[s_off + lo] : 1.0f) : 0.0f;
+        sv_in[k].y = hi < count ? (a.survival_in ? a.survival_in[s_off + hi] : 1.0f) : 0.0f;
+      }
+      loaded_survival = s_off;
+    }
+
+    if (b + 1 < b_end) fetch(b + 1);
+
+    f2 sv[PAIRS];
+#pragma unroll
+    for (int k = 0; k < PAIRS; ++k) sv[k] = sv_in[k];
+    const uint32_t flags = record_flags(rec2[0].x);
+    constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
+                                 CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
+    float pilot[6];
+    f2 acc2[NSUM];
+#pragma unroll
+    for (int i = 0; i < NSUM; ++i) acc2[i] = f2{0.0f, 0.0f};
+    if ((flags & kSparse) == kSparse)
+      observe_setting<PAIRS, UNIT7, true, MOMENTS>(rec2, a.n_apertures, a.elliptical_mask, p,
+                                                    sv, first, pilot, acc2);
+    else
+      observe_setting<PAIRS, UNIT7, false, MOMENTS>(rec2, a.n_apertures, a.elliptical_mask,
+                                                     p, sv, first, pilot, acc2);
+    if (b + 1 < b_end) commit((it & 1) ? pairs0 : pairs1, b + 1);
+    if (a.survival_out != nullptr) {
+      float* dst = a.survival_out + b * a.n_particles + n0;
+#pragma unroll
+      for (int k = 0; k < PAIRS; ++k) {
+        const int lo = tid + (2 * k) * THREADS, hi = lo + THREADS;
+        if (lo < count) dst[lo] = sv[k].x;
+        if (hi < count) dst[hi] = sv[k].y;
+      }
+    }
+    // fold the two halves, then the packed butterfly over the warp (a shared-memory transpose
+    // instead of the shuffle tree executed fewer instructions but was not faster: the kernel
+    // is bound by dependent-issue latency at 4 warps per scheduler, not by instruction count)
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NSUM; ++i) acc[i] = acc2[i].x + acc2[i].y;
+    const int lane = tid & 31;
+    const float total = packed_warp_sum(acc, lane);
+    if constexpr (MOMENTS == 2) {
+      partial[it & 1][tid >> 5][lane] = total;
+    } else if ((lane & 1) == 0) {
+      const int index = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                        ((lane >> 1) & 1);
+      partial[it & 1][tid >> 5][index] = total;
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) pilot_shared[it & 1][i] = pilot[i];
+    }
+  }
+  if (b_end > b_begin) {
+    __syncthreads();
+    flush_moments(static_cast<int>((b_end - b_begin - 1) & 1), b_end - 1);
+  }
+}
+
+constexpr int kObserveP = 8, kObserveThreads = 128;
+
+int launch_observe(const ApplyArgs<float>& args, bool unit_seventh, cudaStream_t stream) {
+  constexpr int TP = kObserveP * kObserveThreads;
+  const size_t rec_pitch = (static_cast<size_t>(args.record_len) + 3) & ~size_t(3);
+  const size_t smem = sizeof(float) * (TP * 7 + 4 * rec_pitch) + sizeof(uint64_t);
+  const int64_t tiles = (args.n_particles + TP - 1) / TP;
+  const int64_t chunks = (args.n_settings + args.settings_per_cta - 1) / args.settings_per_cta;
+  CH_REQUIRE(tiles <= 2147483647LL && chunks <= 65535, "ch_apply_maps_moments: grid too large");
+  dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(chunks));
+  auto launch = [&](auto kernel) -> int {
+    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    kernel<<<grid, kObserveThreads, smem, stream>>>(args);
+    return CH_OK;
+  };
+  int status;
+  if (args.covariance)
+    status = unit_seventh ? launch(observe_maps_kernel<kObserveP, kObserveThreads, true, 2>)
+                          : launch(observe_maps_kernel<kObserveP, kObserveThreads, false, 2>);
+  else
+    status = unit_seventh ? launch(observe_maps_kernel<kObserveP, kObserveThreads, true, 1>)
+                          : launch(observe_maps_kernel<kObserveP, kObserveThreads, false, 1>);
+  if (status != CH_OK) return status;
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
 template <typename T, int P, int THREADS>
 int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t stream) {
   constexpr int TP = P * THREADS;
@@ -593,6 +967,12 @@ int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t
   int64_t per_cta = 64;
   while (per_cta > 1 && tiles * ((n_settings + per_cta - 1) / per_cta) < 148 * 16) per_cta /= 2;
   a.settings_per_cta = static_cast<int32_t>(per_cta);
+  if constexpr (sizeof(T) == 4) {
+    static_assert(kObserveP * kObserveThreads == P * THREADS, "same tiling for both kernels");
+    // observables only (no cavity tail): the packed-pair kernel
+    if (moments_out != nullptr && particles_out == nullptr && !a.has_cavity)
+      return launch_observe(a, unit_seventh != 0, stream);
+  }
   return launch_apply<T, P, THREADS>(a, unit_seventh != 0, stream);
 }
 

@@ -210,7 +210,8 @@ int ch_apply_maps_parameter(const void* mu_in, int64_t mu_stride, const int32_t*
  *   [8+i] = sum w (u_i - c_i)^2, [14+i] = c_i               (w = outgoing survival)
  * so mu_i = c_i + S1_i / S0 and var_i = (S2_i - S1_i^2 / S0) / (S0 - sum w^2 / S0).
  * particles_out and survival_out may be NULL: then nothing but the 20 doubles per setting
- * leaves the SM (no (B, N, 7) array in HBM).  moments_out is zeroed here.                  */
+ * leaves the SM (no (B, N, 7) array in HBM); float32 sections without a cavity tail then run the
+ * packed-pair kernel (observe_maps_kernel, two particles per FFMA2).  moments_out is zeroed here. */
 #define CH_MOMENTS 20
 int ch_apply_maps_moments(const void* particles_in, int64_t particle_stride, const int32_t* particle_index,
                           const void* survival_in, int64_t survival_stride, const int32_t* survival_index,

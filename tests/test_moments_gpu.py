@@ -46,7 +46,11 @@ def test_track_moments_matches_moments_of_tracked_beam(n, settings):
     kept, observed2 = segment.track_moments(beam, keep_particles=True)
     assert torch.equal(kept.particles, out.particles)
     assert torch.equal(kept.survival_probabilities, out.survival_probabilities)
-    assert torch.equal(observed2.mu, observed.mu)
+    # particles + moments and moments only are different kernels (scalar / packed pairs): same
+    # sums in a different order
+    assert ((observed2.mu.double() - observed.mu.double()).abs() / scale).max() < 2e-6
+    assert ((observed2.sigma.double() - observed.sigma.double()).abs() / scale).max() < 2e-6
+    assert torch.equal(observed2.num_particles_survived, observed.num_particles_survived)
 
 
 def test_track_moments_without_apertures_and_single_setting():
