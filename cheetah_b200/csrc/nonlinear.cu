@@ -674,41 +674,116 @@ __device__ __forceinline__ void track_tdc(State<C>& st, const double* cc, const 
   st.delta = static_cast<C>(s.delta);
 }
 
-// element.py:195-225 with the frame changes of quadrupole.py:136-143 / dipole.py:417-426 applied
-// to the particle instead of being folded into T: q = entry(p), t = R q + T q q, out = exit(t)
+// Elements [A, B) of a 16-byte aligned coefficient block through 128-bit shared-memory loads (all
+// lanes read the same address: one broadcast wavefront per load).  Scalar loads of the 58
+// second-order coefficients were 31 % of the executed instructions and 55 % of the stall samples
+// of a second_order run.
 template <typename C>
-__device__ __forceinline__ void track_second_order(State<C>& s, const C* c) {
-  const C cs = c[S_COS], sn = c[S_SIN];
-  C x = s.x * cs + s.y * sn + c[S_OX];
-  C y = -s.x * sn + s.y * cs + c[S_OY];
-  C px = s.px * cs + s.py * sn;
-  C py = -s.px * sn + s.py * cs;
-  px += c[S_KX1] * x;
-  py += c[S_KY1] * y;
-  const C tau = s.l, dl = s.d;
-  const C* r = c + S_R;
-  const C* t = c + S_T;
-  const C xx = x * x, xp = x * px, pp = px * px, xd = x * dl, pd = px * dl, dd = dl * dl;
-  const C yy = y * y, yq = y * py, qq = py * py;
-  const C xy = x * y, xq = x * py, py_ = px * y, pq = px * py, yd = y * dl, qd = py * dl;
-  C ox = r[R_CX] * x + r[R_SX] * px + r[R_05] * dl + t[T000] * xx + t[T001] * xp + t[T011] * pp +
-         t[T005] * xd + t[T015] * pd + t[T055] * dd + t[T022] * yy + t[T023] * yq + t[T033] * qq;
-  C opx = r[R_10] * x + r[R_CX] * px + r[R_15] * dl + t[T100] * xx + t[T101] * xp + t[T111] * pp +
-          t[T105] * xd + t[T115] * pd + t[T155] * dd + t[T122] * yy + t[T123] * yq + t[T133] * qq;
-  C oy = r[R_CY] * y + r[R_SY] * py + t[T202] * xy + t[T203] * xq + t[T212] * py_ + t[T213] * pq +
-         t[T225] * yd + t[T235] * qd;
-  C opy = r[R_32] * y + r[R_CY] * py + t[T302] * xy + t[T303] * xq + t[T312] * py_ +
-          t[T313] * pq + t[T325] * yd + t[T335] * qd;
-  const C otau = tau + r[R_15] * x + r[R_05] * px + r[R_56] * dl + t[T400] * xx + t[T401] * xp +
-                 t[T411] * pp + t[T405] * xd + t[T415] * pd + t[T455] * dd + t[T422] * yy +
-                 t[T423] * yq + t[T433] * qq;
-  opx += c[S_KX2] * ox;
-  opy += c[S_KY2] * oy;
-  s.x = ox * cs - oy * sn + c[S_MX];
-  s.y = ox * sn + oy * cs + c[S_MY];
-  s.px = opx * cs - opy * sn;
-  s.py = opx * sn + opy * cs;
-  s.l = otau;
+struct Wide;
+template <>
+struct Wide<float> {
+  using type = float4;
+  static constexpr int lanes = 4;
+};
+template <>
+struct Wide<double> {
+  using type = double2;
+  static constexpr int lanes = 2;
+};
+template <int A, int B, typename C>
+__device__ __forceinline__ void load_span(C (&dst)[B - A], const C* c) {
+  using V = typename Wide<C>::type;
+  constexpr int L = Wide<C>::lanes;
+#pragma unroll
+  for (int w = A / L; w <= (B - 1) / L; ++w) {
+    const V v = reinterpret_cast<const V*>(c)[w];
+    C e[4];
+    if constexpr (L == 4) {
+      e[0] = v.x, e[1] = v.y, e[2] = v.z, e[3] = v.w;
+    } else {
+      e[0] = v.x, e[1] = v.y, e[2] = C(0), e[3] = C(0);
+    }
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int index = w * L + i;
+      if (index >= A && index < B) dst[index - A] = e[i];
+    }
+  }
+}
+
+// element.py:195-225 with the frame changes of quadrupole.py:136-143 / dipole.py:417-426 applied
+// to the particle instead of being folded into T: q = entry(p), t = R q + T q q, out = exit(t).
+// The thread's P particles go through the element together, so every coefficient row is loaded
+// once (T rows: 0..8, 9..17, 18..23, 24..29, 30..38 of the enum above).
+template <typename C, int P>
+__device__ __forceinline__ void track_second_order(State<C> (&s)[P], const C* c) {
+  C h[S_T];  // frame, kicks and R
+  load_span<0, S_T>(h, c);
+  const C cs = h[S_COS], sn = h[S_SIN];
+  const C* r = h + S_R;
+  C x[P], y[P], px[P], py[P], dl[P];
+  C xx[P], xp[P], pp[P], xd[P], pd[P], dd[P], yy[P], yq[P], qq[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    x[k] = s[k].x * cs + s[k].y * sn + h[S_OX];
+    y[k] = -s[k].x * sn + s[k].y * cs + h[S_OY];
+    px[k] = s[k].px * cs + s[k].py * sn;
+    py[k] = -s[k].px * sn + s[k].py * cs;
+    px[k] += h[S_KX1] * x[k];
+    py[k] += h[S_KY1] * y[k];
+    dl[k] = s[k].d;
+    xx[k] = x[k] * x[k], xp[k] = x[k] * px[k], pp[k] = px[k] * px[k];
+    xd[k] = x[k] * dl[k], pd[k] = px[k] * dl[k], dd[k] = dl[k] * dl[k];
+    yy[k] = y[k] * y[k], yq[k] = y[k] * py[k], qq[k] = py[k] * py[k];
+  }
+  // the three rows with the same nine products: x, px, tau
+  C ox[P], opx[P];
+  {
+    C t[9];
+    load_span<S_T + T000, S_T + T000 + 9>(t, c);
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      ox[k] = r[R_CX] * x[k] + r[R_SX] * px[k] + r[R_05] * dl[k] + t[0] * xx[k] + t[1] * xp[k] +
+              t[2] * pp[k] + t[3] * xd[k] + t[4] * pd[k] + t[5] * dd[k] + t[6] * yy[k] +
+              t[7] * yq[k] + t[8] * qq[k];
+  }
+  {
+    C t[9];
+    load_span<S_T + T100, S_T + T100 + 9>(t, c);
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      opx[k] = r[R_10] * x[k] + r[R_CX] * px[k] + r[R_15] * dl[k] + t[0] * xx[k] + t[1] * xp[k] +
+               t[2] * pp[k] + t[3] * xd[k] + t[4] * pd[k] + t[5] * dd[k] + t[6] * yy[k] +
+               t[7] * yq[k] + t[8] * qq[k];
+  }
+  {
+    C t[9];
+    load_span<S_T + T400, S_T + T400 + 9>(t, c);
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      s[k].l = s[k].l + r[R_15] * x[k] + r[R_05] * px[k] + r[R_56] * dl[k] + t[0] * xx[k] +
+               t[1] * xp[k] + t[2] * pp[k] + t[3] * xd[k] + t[4] * pd[k] + t[5] * dd[k] +
+               t[6] * yy[k] + t[7] * yq[k] + t[8] * qq[k];
+  }
+  // the two vertical rows share six mixed products
+  C t2[6], t3[6];
+  load_span<S_T + T202, S_T + T202 + 6>(t2, c);
+  load_span<S_T + T302, S_T + T302 + 6>(t3, c);
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const C xy = x[k] * y[k], xq = x[k] * py[k], py_ = px[k] * y[k], pq = px[k] * py[k];
+    const C yd = y[k] * dl[k], qd = py[k] * dl[k];
+    const C oy = r[R_CY] * y[k] + r[R_SY] * py[k] + t2[0] * xy + t2[1] * xq + t2[2] * py_ +
+                 t2[3] * pq + t2[4] * yd + t2[5] * qd;
+    C opy = r[R_32] * y[k] + r[R_CY] * py[k] + t3[0] * xy + t3[1] * xq + t3[2] * py_ +
+            t3[3] * pq + t3[4] * yd + t3[5] * qd;
+    const C opx_k = opx[k] + h[S_KX2] * ox[k];
+    opy += h[S_KY2] * oy;
+    s[k].x = ox[k] * cs - oy * sn + h[S_MX];
+    s[k].y = ox[k] * sn + oy * cs + h[S_MY];
+    s[k].px = opx_k * cs - opy * sn;
+    s[k].py = opx_k * sn + opy * cs;
+  }
 }
 
 template <typename T>
@@ -842,47 +917,73 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
     const Beam0<double> ref64{consts64[H_P0C], consts64[H_MC2], consts64[H_E0],
                               consts64[H_BETA0], consts64[H_MC2_E0_SQ], consts64[H_INV_P0C],
                               consts64[H_TWO_E0_OVER_P0C]};
+    // ops outer, the thread's P particles inner: opcode dispatch, flags and coefficient loads are
+    // paid once per op instead of once per (op, particle)
+    State<T> s[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      State<T> s{p[k][0], p[k][1], p[k][2], p[k][3], p[k][4], p[k][5]};
-      bool bmad = false;  // representation of (s.l, s.d): uniform over the CTA
-      for (int op = 0; op < a.n_ops; ++op) {
-        const int code = codes[op];
-        const T* c = consts + CH_NL_HEADER + op * a.block;
-        const double* c64 = consts64 + CH_NL_HEADER + op * a.block;
-        if (code == CH_OP_IDENTITY) continue;
-        const bool wants_bmad = code != CH_OP_SECOND_ORDER;
-        if (wants_bmad && !bmad) to_bmad(s, ref);
-        if (!wants_bmad && bmad) from_bmad(s);
-        bmad = wants_bmad;
-        switch (code) {
-          case CH_OP_DKD_DRIFT:
-            track_a_drift(s, c[D_L]);
-            break;
-          case CH_OP_DKD_QUADRUPOLE:
-            track_quadrupole(s, c, flags[op] > 0 ? flags[op] : 1, ref);
-            break;
-          case CH_OP_DKD_DIPOLE:
-            if constexpr (FP64_OPS) track_dipole(s, c64, flags[op], ref64);
-            break;
-          case CH_OP_DKD_TDC:
-            if constexpr (FP64_OPS) track_tdc(s, c64, ref64);
-            break;
-          case CH_OP_SECOND_ORDER:
-            track_second_order(s, c);
-            break;
-          default:
-            break;
-        }
+      s[k].x = p[k][0], s[k].px = p[k][1], s[k].y = p[k][2], s[k].py = p[k][3];
+      s[k].l = p[k][4], s[k].d = p[k][5];
+      s[k].iP = s[k].rb = s[k].inv_beta = s[k].delta = T(0);
+    }
+    bool bmad = false;  // representation of (s.l, s.d): uniform over the CTA
+    for (int op = 0; op < a.n_ops; ++op) {
+      const int code = codes[op];
+      const T* c = consts + CH_NL_HEADER + op * a.block;
+      const double* c64 = consts64 + CH_NL_HEADER + op * a.block;
+      if (code == CH_OP_IDENTITY) continue;
+      const bool wants_bmad = code != CH_OP_SECOND_ORDER;
+      if (wants_bmad && !bmad) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) to_bmad(s[k], ref);
       }
-      if (bmad) from_bmad(s);
+      if (!wants_bmad && bmad) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) from_bmad(s[k]);
+      }
+      bmad = wants_bmad;
+      switch (code) {
+        case CH_OP_DKD_DRIFT: {
+          const T length = c[D_L];
+#pragma unroll
+          for (int k = 0; k < P; ++k) track_a_drift(s[k], length);
+          break;
+        }
+        case CH_OP_DKD_QUADRUPOLE: {
+          const int steps = flags[op] > 0 ? flags[op] : 1;
+#pragma unroll
+          for (int k = 0; k < P; ++k) track_quadrupole(s[k], c, steps, ref);
+          break;
+        }
+        case CH_OP_DKD_DIPOLE:
+          if constexpr (FP64_OPS) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) track_dipole(s[k], c64, flags[op], ref64);
+          }
+          break;
+        case CH_OP_DKD_TDC:
+          if constexpr (FP64_OPS) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) track_tdc(s[k], c64, ref64);
+          }
+          break;
+        case CH_OP_SECOND_ORDER:
+          track_second_order(s, c);
+          break;
+        default:
+          break;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      if (bmad) from_bmad(s[k]);
       T* row = stage + (tid + k * THREADS) * 7;
-      row[0] = s.x;
-      row[1] = s.px;
-      row[2] = s.y;
-      row[3] = s.py;
-      row[4] = s.l;
-      row[5] = s.d;
+      row[0] = s[k].x;
+      row[1] = s[k].px;
+      row[2] = s[k].y;
+      row[3] = s[k].py;
+      row[4] = s[k].l;
+      row[5] = s[k].d;
       row[6] = p[k][6];
     }
 

@@ -18,6 +18,25 @@ def main():
     species = cb.Species("electron", device=device, dtype=dtype)
     batched = cb.ParticleBeam(particles.expand(B, n, 7).contiguous(), t(1e8), species=species)
     shared = cb.ParticleBeam(particles, t(1e8), species=species)
+    if len(sys.argv) > 3:  # fused 20-element line: drift_kick_drift or second_order
+        import bench_nonlinear
+        from cheetah_b200 import lattice_description
+        method = sys.argv[3]
+        description = bench_nonlinear.fodo(method, 5, B, dtype)
+        segment = cb.Segment(lattice_description.build(description, device=device, dtype=dtype))
+        for _ in range(3):
+            segment.track(shared)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            segment.track(shared)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        print(f"{method} x 20 elements, {B} settings x {n}: {ms:.3f} ms, "
+              f"{B * n * 20 / ms / 1e6:.1f} G particle-steps/s")
+        return
     cases = {
         "drift_dkd": cb.Segment([cb.Drift(length=t(1.0), tracking_method="drift_kick_drift")]),
         "quad_second_order": cb.Segment([cb.Quadrupole(length=t(0.2), k1=t(4.2),
