@@ -156,3 +156,35 @@ def test_long_run_is_split_and_matches_single_elements():
         step = element.track(step)
     assert torch.allclose(fused.particles, step.particles, rtol=1e-10, atol=1e-16)
     assert torch.allclose(fused.s, step.s)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("k1,length,num_steps", [
+    (4.2, 0.2, 5),      # |k1| step^2 = 0.0067: power series
+    (-35.0, 0.5, 2),    # 2.19: series, just inside the switch-over
+    (35.0, 0.5, 2),
+    (40.0, 0.5, 2),     # 2.5: closed forms (cosh / sinh, cos / sin)
+    (-120.0, 0.6, 1),   # 43: closed forms, k l = 6.6 rad
+    (0.0, 0.3, 3),      # k1 = 0: a drift
+])
+def test_drift_kick_drift_quadrupole_series_and_closed_forms(k1, length, num_steps, dtype):
+    """quadrupole_plane evaluates cos / cosh and sin / sinh by a power series in k1 l^2 for
+    |k1 l^2| <= 2.25 and by the closed forms (quadrupole.py:168-251, bmadx.py:223-260) above;
+    both against the oracle, with vectorised k1 straddling the switch-over."""
+    g = torch.Generator().manual_seed(11)
+    n = 4000
+    particles = torch.randn(n, 7, generator=g, dtype=torch.float64)
+    particles[:, :6] *= torch.tensor([3e-4, 4e-5, 3e-4, 4e-5, 1e-4, 2e-2], dtype=torch.float64)
+    particles[:, 6] = 1.0
+    k1s = torch.tensor([k1, 0.97 * k1, 1.06 * k1], dtype=torch.float64)
+    lattice = [{"type": "Quadrupole", "name": "q", "length": torch.tensor(length, dtype=torch.float64),
+                "k1": k1s, "num_steps": num_steps, "tracking_method": "drift_kick_drift"}]
+    beam = oracle.make_beam(particles, torch.tensor(6e6, dtype=torch.float64))
+    if dtype == torch.float32:
+        lattice = lattice_io.cast(lattice_io.cast(lattice, torch.float32), torch.float64)
+        beam = {k: v.to(torch.float32).to(torch.float64) for k, v in beam.items()}
+    expected = oracle.track(lattice, beam)
+    out = gu.product_segment(lattice, DEVICE, dtype).track(gu.product_beam(beam, DEVICE, dtype))
+    assert tuple(out.particles.shape) == (3, n, 7)
+    tolerance = 1e-11 if dtype == torch.float64 else F32_TOL
+    assert gu.column_scaled_error(out.particles, expected["particles"]) < tolerance
