@@ -703,6 +703,20 @@ __device__ __forceinline__ void track_tdc(State<C>& st, const double* cc, const 
   st.delta = static_cast<C>(s.delta);
 }
 
+// The two fp64 bodies are several hundred instructions each: called (not inlined) once per
+// particle, so that the P particles of a thread do not multiply the code size and the register
+// pressure of the FP64_OPS instantiation.
+template <typename C>
+__device__ __noinline__ void track_dipole_call(State<C>& st, const double* cc, int flags,
+                                               const Beam0<double>& r) {
+  track_dipole(st, cc, flags, r);
+}
+template <typename C>
+__device__ __noinline__ void track_tdc_call(State<C>& st, const double* cc,
+                                            const Beam0<double>& r) {
+  track_tdc(st, cc, r);
+}
+
 // Elements [A, B) of a 16-byte aligned coefficient block through 128-bit shared-memory loads (all
 // lanes read the same address: one broadcast wavefront per load).  Scalar loads of the 58
 // second-order coefficients were 31 % of the executed instructions and 55 % of the stall samples
@@ -987,13 +1001,13 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
         case CH_OP_DKD_DIPOLE:
           if constexpr (FP64_OPS) {
 #pragma unroll
-            for (int k = 0; k < P; ++k) track_dipole(s[k], c64, flags[op], ref64);
+            for (int k = 0; k < P; ++k) track_dipole_call(s[k], c64, flags[op], ref64);
           }
           break;
         case CH_OP_DKD_TDC:
           if constexpr (FP64_OPS) {
 #pragma unroll
-            for (int k = 0; k < P; ++k) track_tdc(s[k], c64, ref64);
+            for (int k = 0; k < P; ++k) track_tdc_call(s[k], c64, ref64);
           }
           break;
         case CH_OP_SECOND_ORDER:
