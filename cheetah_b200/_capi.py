@@ -8,7 +8,7 @@ g.build()"`` or ``python -m cheetah_b200.build``).
 from __future__ import annotations
 
 import ctypes
-from ctypes import POINTER, c_char_p, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import c_double, POINTER, c_char_p, c_int32, c_int64, c_uint32, c_void_p
 from pathlib import Path
 
 import torch
@@ -145,6 +145,21 @@ SIGNATURES = {
             c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
             c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
             c_int64, c_int64, c_int32, c_void_p, c_void_p,
+        ],
+    ),
+    "ch_screen_kde": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+            c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+            c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+        ],
+    ),
+    "ch_screen_gaussian": (
+        c_int32,
+        [
+            c_void_p, c_void_p, c_void_p, c_double, c_double, c_int32, c_double, c_double,
+            c_int32, c_int32, c_void_p, c_void_p,
         ],
     ),
     "ch_sc_beam_moments": (

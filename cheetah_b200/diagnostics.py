@@ -114,17 +114,9 @@ def track_screen(element, incoming):
 
 def screen_image(element, beam) -> torch.Tensor:
     """``Screen.reading`` for a ParticleBeam: ``(..., height, width)`` (screen.py:296-340)."""
-    if type(beam).__name__ != "ParticleBeam":
-        raise NotImplementedError(
-            "cheetah_b200 computes Screen readings for `ParticleBeam` only (the reference's "
-            "`ParameterBeam` image is an analytic Gaussian, outside the hot path)"
-        )
+    if type(beam).__name__ == "ParameterBeam":
+        return _parameter_beam_image(element, beam)
     method = element.method
-    if method == "kde":
-        raise NotImplementedError(
-            "cheetah_b200: Screen method 'kde' is outside the accelerated hot path; use "
-            "'cloud-in-cell' (the reference's default) or 'histogram'"
-        )
     particles = beam.particles
     device, dtype = particles.device, particles.dtype
     charges, survival = beam.particle_charges, beam.survival_probabilities
@@ -161,6 +153,26 @@ def screen_image(element, beam) -> torch.Tensor:
     if method == "histogram":
         edges_x, edges_y = (e.to(dtype).contiguous() for e in element.pixel_bin_edges)
     image = torch.empty((n_beams, ny, nx), dtype=dtype, device=device)
+    if method == "kde":
+        # Gaussian kernel density estimate on the pixel centres (screen.py:312-326, kde.py:160-204)
+        centers_x, centers_y = (c.to(dtype).contiguous() for c in element.pixel_bin_centers)
+        bandwidth = element.kde_bandwidth
+        if bandwidth is None:
+            bandwidth = element.pixel_size[0]
+        bandwidth = torch.as_tensor(bandwidth, dtype=dtype, device=device)
+        if bandwidth.dim() != 0:
+            raise ValueError(f"Input sigma must be a of the shape (1,). Got {bandwidth.shape}")
+        bandwidth = bandwidth.reshape(1).contiguous()
+        totals = torch.empty(n_beams, dtype=torch.float64, device=device)
+        with _capi.device_guard(device):
+            _capi.check(_capi.lib().ch_screen_kde(
+                particles.data_ptr(), particle_stride, charges.data_ptr(), charge_stride,
+                survival.data_ptr(), survival_stride, misalignment.data_ptr(),
+                misalignment_stride, centers_x.data_ptr(), nx, centers_y.data_ptr(), ny,
+                bandwidth.data_ptr(), n, n_beams, _capi.dtype_code(dtype), image.data_ptr(),
+                totals.data_ptr(), _capi.current_stream(device),
+            ))
+        return image.reshape(*vo, ny, nx)
     with _capi.device_guard(device):
         _capi.check(_capi.lib().ch_screen_image(
             particles.data_ptr(), particle_stride, charges.data_ptr(), charge_stride,
@@ -170,3 +182,33 @@ def screen_image(element, beam) -> torch.Tensor:
             n, n_beams, _capi.dtype_code(dtype), image.data_ptr(), _capi.current_stream(device),
         ))
     return image.reshape(*vo, ny, nx)
+
+
+def _parameter_beam_image(element, beam) -> torch.Tensor:
+    """``Screen.reading`` for a ParameterBeam: the bivariate normal density of (x, y) on the pixel
+    grid ``arange(left, right, step)`` (screen.py:251-289, ``ch_screen_gaussian``).  The read beam
+    is shifted by the misalignment (:187-198)."""
+    if torch.numel(beam.mu[..., 0]) > 1:
+        raise NotImplementedError(
+            "`Screen` does not support vectorization of `ParameterBeam`. Please use "
+            "`ParticleBeam` instead. If this is a feature you would like to see, please open an "
+            "issue on GitHub."
+        )
+    device, dtype = beam.mu.device, beam.mu.dtype
+    mu = beam.mu.reshape(7).contiguous()
+    cov = beam.cov.reshape(7, 7).to(dtype).contiguous()
+    misalignment = element.misalignment.to(dtype).reshape(2).contiguous()
+    # torch.arange(left, right, step) with tensor bounds: ceil((right - left) / step) points in
+    # double, float32 values (the kernel reproduces the rounding); needs the bounds on the host
+    extent = [float(v) for v in element.extent.to(dtype)]
+    steps = [float(v) for v in (element.pixel_size.to(dtype) * int(element.binning))]
+    nx = max(0, math.ceil((extent[1] - extent[0]) / steps[0]))
+    ny = max(0, math.ceil((extent[3] - extent[2]) / steps[1]))
+    image = torch.empty((ny, nx), dtype=dtype, device=device)
+    with _capi.device_guard(device):
+        _capi.check(_capi.lib().ch_screen_gaussian(
+            mu.data_ptr(), cov.data_ptr(), misalignment.data_ptr(), extent[0], steps[0], nx,
+            extent[2], steps[1], ny, _capi.dtype_code(dtype), image.data_ptr(),
+            _capi.current_stream(device),
+        ))
+    return image

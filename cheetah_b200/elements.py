@@ -429,7 +429,8 @@ class BPM(_SimpleElement):
 
 class Screen(_SimpleElement):
     """Diagnostic screen (cheetah/accelerator/screen.py): when active it remembers the passing
-    beam and renders ``reading`` (height, width) lazily with ``ch_screen_image``."""
+    beam and renders ``reading`` (height, width) lazily with ``ch_screen_image``
+    (cloud-in-cell, histogram), ``ch_screen_kde`` or, for a ParameterBeam, ``ch_screen_gaussian``."""
 
     tensor_fields = {"pixel_size": (1e-3, 1e-3), "misalignment": (0.0, 0.0)}
     plain_fields = {
@@ -446,7 +447,8 @@ class Screen(_SimpleElement):
             assert value in ["histogram", "kde", "cloud-in-cell"], (
                 f"Invalid method {value}. Must be 'histogram', 'kde', or 'cloud-in-cell'."
             )
-        if name in ("resolution", "binning", "method", "pixel_size", "misalignment"):
+        if name in ("resolution", "binning", "method", "pixel_size", "misalignment",
+                    "kde_bandwidth"):
             object.__setattr__(self, "_cached_reading", None)
         super().__setattr__(name, value)
 

@@ -282,6 +282,33 @@ int ch_screen_image(const void* particles, int64_t particle_stride,
                     int64_t n_particles, int64_t n_beams, int32_t dtype,
                     void* image, void* stream);
 
+/* Screen.reading with method="kde" (screen.py:312-326 -> cheetah/utils/kde.py:160-204): Gaussian
+ * kernel density image on the pixel centres centers_x [nx], centers_y [ny]
+ * (Screen.pixel_bin_centers, screen.py:168-174; uniformly spaced) with bandwidth[0] (device scalar,
+ * Screen.kde_bandwidth), weights |particle_charges| * survival on the x factor only, kernel values
+ * clamped to the smallest normal number, image normalised by (its sum + 1e-10).  Every particle is
+ * spread over the pixels within 7 (float32) / 8 (float64) bandwidths, beyond which the kernel is
+ * below the rounding of the sums.  totals: [B] doubles (zeroed here; the un-normalised sums on
+ * return).  image [B][ny][nx] (height, width); other conventions as ch_screen_image.             */
+int ch_screen_kde(const void* particles, int64_t particle_stride,
+                  const void* charges, int64_t charge_stride,
+                  const void* survival, int64_t survival_stride,
+                  const void* misalignment, int64_t misalignment_stride,
+                  const void* centers_x, int32_t nx, const void* centers_y, int32_t ny,
+                  const void* bandwidth, int64_t n_particles, int64_t n_beams, int32_t dtype,
+                  void* image, double* totals, void* stream);
+
+/* Screen.reading for a (non-vectorised) ParameterBeam (screen.py:251-289): the bivariate normal
+ * density of (x, y) ~ N((mu[0], mu[2]) - misalignment, cov[{0,2}][{0,2}]) at the grid points
+ * float32(left + i * step_x), float32(bottom + j * step_y) -- torch.arange(left, right, step) with
+ * tensor bounds yields float32 points computed in double, whatever the screen dtype; the caller
+ * passes nx = ceil((right - left) / step_x) likewise.  mu [7], cov [7][7], misalignment [2] in the
+ * beam dtype; image [ny][nx].                                                                  */
+int ch_screen_gaussian(const void* mu, const void* cov, const void* misalignment,
+                       double left, double step_x, int32_t nx,
+                       double bottom, double step_y, int32_t ny,
+                       int32_t dtype, void* image, void* stream);
+
 /* ch_apply_maps_moments with the full second-moment matrix: moments_out[b] has CH_MOMENTS_COV
  * doubles, the first CH_MOMENTS as above, then [20 + k] = sum w (u_i - c_i)(u_j - c_j) for the 15
  * pairs i < j in the order (0,1), (0,2), ..., (0,5), (1,2), ..., (4,5), [35] unused.  With

@@ -723,11 +723,16 @@ def make_diagnostics() -> None:
         "histogram": dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5], method="histogram"),
         "histogram_binned": dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5], binning=4,
                                  misalignment=[2e-4, -1e-4], method="histogram"),
+        "kde": dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5], method="kde"),
+        "kde_binned_bandwidth": dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5], binning=2,
+                                     misalignment=[2e-4, -1e-4], method="kde",
+                                     kde_bandwidth=8e-5),
+        "kde_clipping": dict(resolution=(40, 30), pixel_size=[1e-5, 1e-5], method="kde"),
     }
     for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
         beam = base.to(dtype)
         for name, kw in screens.items():
-            kwargs = {k: (torch.tensor(v, dtype=dtype) if isinstance(v, list) else v)
+            kwargs = {k: (torch.tensor(v, dtype=dtype) if isinstance(v, (list, float)) else v)
                       for k, v in kw.items()}
             screen = cheetah.Screen(is_active=True, name=name, dtype=dtype, **kwargs)
             out = screen.track(beam)
@@ -744,12 +749,30 @@ def make_diagnostics() -> None:
                            pixel_size=torch.tensor([2.5e-5, 3e-5], dtype=dtype), dtype=dtype),
         ])
         out = segment.track(beam)
+        kde_screen = cheetah.Screen(is_active=True, name="kde_screen", resolution=(96, 64),
+                                    pixel_size=torch.tensor([2.5e-5, 3e-5], dtype=dtype),
+                                    method="kde", dtype=dtype)
+        kde_screen.track(out)  # vectorised read beam (3 settings)
+        arrays[f"segment.kde_screen.{tag}"] = np64(kde_screen.reading)
         arrays[f"segment.screen.{tag}"] = np64(segment.screen.reading)
         arrays[f"segment.bpm.{tag}"] = np64(segment.bpm.reading)
         arrays[f"segment.outgoing_shape.{tag}"] = np.asarray(out.particles.shape)
         bpm = cheetah.BPM(is_active=True, misalignment=torch.tensor([0.1, 0.2], dtype=dtype))
         bpm.track(beam)
         arrays[f"bpm.{tag}"] = np64(bpm.reading)
+        # ParameterBeam on a screen: analytic bivariate normal on the pixel grid
+        parameter_beam = beam.as_parameter_beam()
+        for name, kw in (("gaussian", dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5])),
+                         ("gaussian_binned", dict(resolution=(96, 64), pixel_size=[2.5e-5, 3e-5],
+                                                  binning=2, misalignment=[2e-4, -1e-4]))):
+            kwargs = {k: (torch.tensor(v, dtype=dtype) if isinstance(v, list) else v)
+                      for k, v in kw.items()}
+            screen = cheetah.Screen(is_active=True, name=name, dtype=dtype, **kwargs)
+            screen.track(parameter_beam)
+            arrays[f"screen.{name}.{tag}"] = np64(screen.reading)
+            meta[f"screen.{name}"] = kw
+        arrays[f"parameter_beam.mu.{tag}"] = np64(parameter_beam.mu)
+        arrays[f"parameter_beam.cov.{tag}"] = np64(parameter_beam.cov)
         blocking = cheetah.Screen(is_active=True, is_blocking=True, dtype=dtype)
         arrays[f"blocking.survival.{tag}"] = np64(blocking.track(beam).survival_probabilities)
     np.savez_compressed(OUT / "diagnostics.npz", **arrays)

@@ -16,6 +16,8 @@ with (gu.GOLDEN / "diagnostics.json").open() as f:
     SCREENS = {k.split(".", 1)[1]: v for k, v in json.load(f).items()}
 
 TAGS = [("f64", torch.float64), ("f32", torch.float32)]
+PARTICLE_SCREENS = sorted(k for k in SCREENS if not k.startswith("gaussian"))
+GAUSSIAN_SCREENS = sorted(k for k in SCREENS if k.startswith("gaussian"))
 
 
 def segment_lattice(dtype) -> list:
@@ -27,7 +29,7 @@ def segment_lattice(dtype) -> list:
 
 
 @pytest.mark.parametrize("tag,dtype", TAGS)
-@pytest.mark.parametrize("name", sorted(SCREENS))
+@pytest.mark.parametrize("name", PARTICLE_SCREENS)
 def test_screen_images(name, tag, dtype):
     beam = gu.beam_dict(ARRAYS, "incoming", dtype)
     image = diag.screen_reading(SCREENS[name], beam)
@@ -56,3 +58,30 @@ def test_bpm_and_vectorised_segment(tag, dtype):
     assert image.shape == expected.shape == (3, 64, 96)
     assert torch.allclose(image, expected, rtol=1e-10 if dtype == torch.float64 else 2e-3,
                           atol=float(expected.max()) * (1e-12 if dtype == torch.float64 else 2e-3))
+
+
+@pytest.mark.parametrize("tag,dtype", TAGS)
+@pytest.mark.parametrize("name", GAUSSIAN_SCREENS)
+def test_parameter_beam_images(name, tag, dtype):
+    """Analytic bivariate-normal image of a ParameterBeam (screen.py:251-289)."""
+    mu = gu.tensor(ARRAYS[f"parameter_beam.mu.{tag}"], dtype)
+    cov = gu.tensor(ARRAYS[f"parameter_beam.cov.{tag}"], dtype)
+    image = diag.parameter_beam_image(SCREENS[name], mu, cov)
+    expected = gu.tensor(ARRAYS[f"screen.{name}.{tag}"], dtype)
+    assert image.shape == expected.shape
+    assert torch.allclose(image, expected, rtol=1e-9 if dtype == torch.float64 else 2e-4,
+                          atol=float(expected.max()) * (1e-12 if dtype == torch.float64 else 1e-5))
+
+
+@pytest.mark.parametrize("tag,dtype", TAGS)
+def test_vectorised_kde_screen(tag, dtype):
+    """method="kde" is the reference's vectorised Screen (tests/test_vectorized.py:305-352)."""
+    beam = gu.beam_dict(ARRAYS, "incoming", dtype)
+    out = oracle.track(segment_lattice(dtype), beam)
+    image = diag.screen_reading(
+        {"resolution": (96, 64), "pixel_size": (2.5e-5, 3e-5), "method": "kde"}, out)
+    expected = gu.tensor(ARRAYS[f"segment.kde_screen.{tag}"], dtype)
+    assert image.shape == expected.shape == (3, 64, 96)
+    assert torch.allclose(image, expected, rtol=1e-9 if dtype == torch.float64 else 2e-3,
+                          atol=float(expected.max()) * (1e-12 if dtype == torch.float64 else 2e-4))
+    assert torch.allclose(image.sum(dim=(-2, -1)), torch.ones(3, dtype=dtype), atol=1e-4)
