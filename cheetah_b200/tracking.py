@@ -511,6 +511,31 @@ def track_moments(elements, incoming, cache_owner=None, keep_particles: bool = F
     return (outgoing, observed) if keep_particles else observed
 
 
+class _IdentityLattice:
+    """A one-marker lattice with its own plan cache: lets the moments kernel observe a beam as it
+    is (``ParticleBeam.second_moments``)."""
+
+    def __init__(self) -> None:
+        from .elements import Marker
+
+        self.elements = [Marker(name="beam_moments")]
+        self._plan_cache = None
+
+
+_identity_lattice: _IdentityLattice | None = None
+
+
+def beam_moments(beam) -> BeamMoments:
+    """Survival-weighted mean, sigma and full 6 x 6 covariance of ``beam`` itself: one pass of
+    the covariance kernel with the identity map (``ParticleBeam.mu_* / sigma_* / cov_*``,
+    particle_beam.py:1699-1943; ``unbiased_weighted_covariance_matrix``, statistics.py:65-88)."""
+    global _identity_lattice
+    if _identity_lattice is None:
+        _identity_lattice = _IdentityLattice()
+    return track_moments(_identity_lattice.elements, beam, cache_owner=_identity_lattice,
+                         covariance=True)
+
+
 def _track_parameter_beam(program, beam):
     """tm @ mu, tm @ cov @ tm^T with the composed maps (element.py:166-179)."""
     mu, cov, s, energy = beam.mu, beam.cov, beam.s, beam.energy

@@ -781,6 +781,77 @@ def make_diagnostics() -> None:
     print("diagnostics:", len(screens), "screens, sum", float(arrays["screen.cic.f64"].sum()))
 
 
+SCALAR_PROPERTIES = (
+    [f"mu_{c}" for c in ("x", "px", "y", "py", "tau", "p")]
+    + [f"sigma_{c}" for c in ("x", "px", "y", "py", "tau", "p")]
+    + ["cov_xpx", "cov_ypy", "cov_taup", "cov_xp", "cov_pxp", "cov_yp", "cov_pyp", "cov_xy",
+       "cov_xpy", "cov_xtau", "cov_pxy", "cov_pxpy", "cov_pxtau", "cov_ytau", "cov_pytau",
+       "emittance_x", "emittance_y", "projected_emittance_x", "projected_emittance_y",
+       "normalized_emittance_x", "normalized_emittance_y", "beta_x", "beta_y", "alpha_x",
+       "alpha_y", "dispersion_x", "dispersion_px", "dispersion_y", "dispersion_py",
+       "relativistic_gamma", "relativistic_beta", "p0c", "total_charge"]
+)
+
+
+def make_beam_properties() -> None:
+    """Derived beam quantities of the reference (beam.py:262-557, particle_beam.py:1034-1346,
+    :1699-1951, parameter_beam.py:62-760) for the host-side beam mirror."""
+    arrays = {}
+    torch.manual_seed(33)
+    mixing = torch.eye(6, dtype=torch.float64) + 0.3 * torch.randn(6, 6, dtype=torch.float64)
+    sigma = torch.tensor([3e-4, 4e-5, 2e-4, 3e-5, 1e-4, 2e-3], dtype=torch.float64)
+    phase_space = (torch.randn(4000, 6, dtype=torch.float64) @ mixing.T) * sigma + sigma * 0.3
+    particles = torch.cat([phase_space, torch.ones(4000, 1, dtype=torch.float64)], dim=-1)
+    survival = (torch.rand(4000, dtype=torch.float64) > 0.15) * torch.rand(4000, dtype=torch.float64)
+    charges = torch.rand(4000, dtype=torch.float64) * 1e-14
+    beam = cheetah.ParticleBeam(particles, torch.tensor(6.3e7, dtype=torch.float64),
+                                particle_charges=charges, survival_probabilities=survival,
+                                dtype=torch.float64)
+    arrays.update(beam_arrays("incoming", beam))
+    for name in SCALAR_PROPERTIES:
+        arrays[f"particle.{name}"] = np64(getattr(beam, name))
+    arrays["particle.energies"] = np64(beam.energies)
+    arrays["particle.momenta"] = np64(beam.momenta)
+    arrays["particle.xyz_pxpypz"] = np64(beam.to_xyz_pxpypz())
+    round_trip = cheetah.ParticleBeam.from_xyz_pxpypz(beam.to_xyz_pxpypz(), beam.energy,
+                                                      dtype=torch.float64)
+    arrays["particle.round_trip"] = np64(round_trip.particles)
+    moved = beam.transformed_to(mu_x=torch.tensor(1e-3, dtype=torch.float64),
+                                sigma_py=torch.tensor(5e-5, dtype=torch.float64),
+                                total_charge=torch.tensor(3e-11, dtype=torch.float64))
+    arrays["particle.transformed.particles"] = np64(moved.particles)
+    arrays["particle.transformed.charges"] = np64(moved.particle_charges)
+    parameter = beam.as_parameter_beam()
+    arrays["parameter.mu"] = np64(parameter.mu)
+    arrays["parameter.cov"] = np64(parameter.cov)
+    for name in SCALAR_PROPERTIES:
+        arrays[f"parameter.{name}"] = np64(getattr(parameter, name))
+    twiss = cheetah.ParameterBeam.from_twiss(
+        beta_x=torch.tensor([1.0, 2.5], dtype=torch.float64),
+        alpha_x=torch.tensor(-0.7, dtype=torch.float64),
+        emittance_x=torch.tensor(3e-9, dtype=torch.float64),
+        beta_y=torch.tensor(4.0, dtype=torch.float64),
+        alpha_y=torch.tensor([0.2, 0.0], dtype=torch.float64),
+        emittance_y=torch.tensor(2e-9, dtype=torch.float64),
+        sigma_tau=torch.tensor(1e-4, dtype=torch.float64),
+        sigma_p=torch.tensor(1e-3, dtype=torch.float64),
+        cov_taup=torch.tensor(2e-8, dtype=torch.float64),
+        dispersion_x=torch.tensor(0.03, dtype=torch.float64),
+        dispersion_py=torch.tensor(-0.02, dtype=torch.float64),
+        energy=torch.tensor(1.2e8, dtype=torch.float64), dtype=torch.float64,
+    )
+    arrays["twiss.mu"] = np64(twiss.mu)
+    arrays["twiss.cov"] = np64(twiss.cov)
+    for name in SCALAR_PROPERTIES:
+        arrays[f"twiss.{name}"] = np64(getattr(twiss, name))
+    changed = twiss.transformed_to(sigma_x=torch.tensor(2e-4, dtype=torch.float64),
+                                   mu_y=torch.tensor(1e-4, dtype=torch.float64))
+    arrays["twiss.transformed.mu"] = np64(changed.mu)
+    arrays["twiss.transformed.cov"] = np64(changed.cov)
+    np.savez_compressed(OUT / "beam_properties.npz", **arrays)
+    print("beam properties:", len(arrays), "arrays, emittance_x", float(arrays["particle.emittance_x"]))
+
+
 if __name__ == "__main__":
     if "--only-cic" in sys.argv:
         make_cloud_in_cell()
@@ -797,6 +868,9 @@ if __name__ == "__main__":
     if "--only-nonlinear" in sys.argv:
         make_nonlinear()
         sys.exit(0)
+    if "--only-beam-properties" in sys.argv:
+        make_beam_properties()
+        sys.exit(0)
     make_consistency()
     make_ares()
     make_aperture()
@@ -805,5 +879,6 @@ if __name__ == "__main__":
     make_cavity()
     make_nonlinear()
     make_diagnostics()
+    make_beam_properties()
     for path in sorted(OUT.iterdir()):
         print(f"{path.name:40s} {path.stat().st_size / 1024:8.1f} KiB")
