@@ -131,6 +131,20 @@ class Element(nn.Module):
     def forward(self, incoming: Beam) -> Beam:
         return self.track(incoming)
 
+    def clone(self) -> "Element":
+        """Copy of the element that does not share memory with it (element.py:323-336)."""
+        import copy
+
+        fields = {key: getattr(self, key).clone() for key in getattr(self, "tensor_fields", {})}
+        extras = {key: copy.deepcopy(getattr(self, key))
+                  for key in getattr(self, "plain_fields", {})}
+        extras = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in extras.items()}
+        if self.supported_tracking_methods and hasattr(self, "_tracking_method") and \
+                len(self.supported_tracking_methods) > 1:
+            extras["tracking_method"] = self.tracking_method
+        return self.__class__(**fields, **extras, name=self.name, sanitize_name=False,
+                              metadata=copy.deepcopy(self.metadata))
+
     def split(self, resolution: torch.Tensor) -> list["Element"]:
         """Slices no longer than ``resolution``; elements that cannot be split return
         themselves (element.py:338-347)."""
@@ -548,6 +562,13 @@ class CustomTransferMap(Element):
         ).all(), "The seventh row of the transfer map must be [0, 0, 0, 0, 0, 0, 1]."
         self.register_buffer_or_parameter("predefined_transfer_map", predefined_transfer_map)
 
+    def clone(self) -> "CustomTransferMap":
+        import copy
+
+        return self.__class__(self.predefined_transfer_map.clone(), length=self.length.clone(),
+                              name=self.name, sanitize_name=False,
+                              metadata=copy.deepcopy(self.metadata))
+
     @classmethod
     def from_merging_elements(cls, elements: list, incoming_beam: Beam) -> "CustomTransferMap":
         """One map for a run of skippable elements (custom_transfer_map.py:60-109): the product
@@ -602,6 +623,13 @@ class Superimposed(Element):
 
     def flattened(self) -> "Segment":
         return self._segment.flattened()
+
+    def clone(self) -> "Superimposed":
+        import copy
+
+        return self.__class__(self.base_element.clone(), self.superimposed_element.clone(),
+                              name=self.name, sanitize_name=False,
+                              metadata=copy.deepcopy(self.metadata))
 
     @property
     def is_skippable(self) -> bool:
@@ -750,6 +778,70 @@ class Segment(Element):
 
     def split(self, resolution: torch.Tensor) -> list[Element]:
         return [part for element in self.elements for part in element.split(resolution)]
+
+    def clone(self) -> "Segment":
+        """Deep copy: every element cloned (segment.py, element.py:323-336)."""
+        import copy
+
+        return self.__class__([element.clone() for element in self.elements], name=self.name,
+                              sanitize_name=False, metadata=copy.deepcopy(self.metadata))
+
+    # ---- the reference's lattice simplifications (segment.py:231-330).  The composer already
+    # folds markers, inactive monitors and zero-strength magnets into one map, so these do not
+    # change the cost of a track() here; they are kept because user code calls them.
+    def _filtered(self, keep) -> "Segment":
+        return self.__class__(elements=[e for e in self.elements if keep(e)], name=self.name,
+                              sanitize_name=False)
+
+    def without_inactive_markers(self, except_for: list[str] | None = None) -> "Segment":
+        except_for = except_for or []
+        return self._filtered(lambda e: not isinstance(e, Marker) or e.name in except_for)
+
+    def without_inactive_zero_length_elements(self, except_for: list[str] | None = None
+                                              ) -> "Segment":
+        except_for = except_for or []
+        return self._filtered(
+            lambda e: bool((e.length != 0.0).any()) or bool(getattr(e, "is_active", False))
+            or e.name in except_for
+        )
+
+    def inactive_elements_as_drifts(self, except_for: list[str] | None = None) -> "Segment":
+        except_for = except_for or []
+
+        def converted(element):
+            if bool(getattr(element, "is_active", False)) or bool((element.length == 0.0).all()) \
+                    or element.name in except_for:
+                return element
+            return Drift(element.length, name=element.name, sanitize_name=False)
+
+        return self.__class__(elements=[converted(e) for e in self.elements],
+                              name=f"{self.name}_inactive_as_drifts", sanitize_name=False)
+
+    def set_attrs_on_every_element(self, filter_type=None, is_recursive: bool = True,
+                                   **kwargs) -> None:
+        """Set attributes on every element (of ``filter_type``), descending into nested
+        segments (segment.py:605-629)."""
+        for element in self.elements:
+            if filter_type is None or isinstance(element, filter_type):
+                for key, value in kwargs.items():
+                    setattr(element, key, value)
+            elif is_recursive and isinstance(element, Segment):
+                element.set_attrs_on_every_element(filter_type, is_recursive=True, **kwargs)
+
+    def get_beam_attrs_along_segment(self, attr_names, incoming: Beam, resolution=None):
+        """Beam attributes at the end of every element (or slice), stacked along a new
+        dimension in front of the attribute's own ones (segment.py:658-701)."""
+        names = attr_names if isinstance(attr_names, tuple) else (attr_names,)
+        inner = {"particles": 2, "particle_charges": 1, "survival_probabilities": 1, "x": 1,
+                 "px": 1, "y": 1, "py": 1, "tau": 1, "p": 1, "mu": 1, "cov": 2, "energies": 1,
+                 "momenta": 1}
+        beams = list(self.beam_along_segment_generator(incoming, resolution=resolution))
+        results = tuple(
+            torch.stack(torch.broadcast_tensors(*[getattr(beam, name) for beam in beams]),
+                        dim=-(inner.get(name, 0) + 1))
+            for name in names
+        )
+        return results if isinstance(attr_names, tuple) else results[0]
 
     def beam_along_segment_generator(self, incoming: Beam, resolution=None):
         """Beams at the end of every element, or of every slice no longer than ``resolution``

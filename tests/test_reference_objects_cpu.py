@@ -75,3 +75,41 @@ def test_reference_space_charge_and_superimposed_lower(cheetah):
     assert len(program.ops) == 5  # two half quadrupoles + BPM, the bend, the cavity
     dipole = program.ops[3]
     assert torch.allclose(dipole.resolved[3][0], t(0.15))  # e1 = rbend_e1 + angle / 2
+
+
+def test_clone_and_lattice_simplifications():
+    """Element / Segment.clone (element.py:323-336) and the reference's lattice simplifications
+    (segment.py:231-330), host-side only."""
+    import cheetah_b200 as cb
+
+    t = torch.tensor
+    quad = cb.Quadrupole(length=t(0.2), k1=t([1.0, -2.0]), tilt=t(0.1), num_steps=3,
+                         tracking_method="drift_kick_drift", name="q1")
+    copy = quad.clone()
+    assert copy is not quad and copy.name == "q1" and copy.num_steps == 3
+    assert copy.tracking_method == "drift_kick_drift"
+    assert torch.equal(copy.k1, quad.k1) and copy.k1.data_ptr() != quad.k1.data_ptr()
+    segment = cb.Segment([
+        cb.Drift(length=t(0.5), name="d1"), cb.Marker(name="m1"), quad,
+        cb.BPM(name="bpm_off"), cb.BPM(name="bpm_on", is_active=True),
+        cb.Screen(name="screen_off"), cb.Cavity(length=t(1.0), voltage=t(0.0), name="cav_off"),
+        cb.Segment([cb.Marker(name="inner_marker"), cb.HorizontalCorrector(length=t(0.1), name="hc")],
+                   name="inner"),
+    ], name="line")
+    cloned = segment.clone()
+    assert [e.name for e in cloned.elements] == [e.name for e in segment.elements]
+    assert cloned.q1 is not segment.q1 and torch.equal(cloned.q1.k1, segment.q1.k1)
+    assert [e.name for e in segment.without_inactive_markers().elements] == [
+        "d1", "q1", "bpm_off", "bpm_on", "screen_off", "cav_off", "inner"]
+    assert [e.name for e in segment.without_inactive_markers(except_for=["m1"]).elements][1] == "m1"
+    assert [e.name for e in segment.without_inactive_zero_length_elements().elements] == [
+        "d1", "q1", "bpm_on", "cav_off", "inner"]
+    as_drifts = segment.inactive_elements_as_drifts(except_for=["q1"])
+    kinds = {e.name: type(e).__name__ for e in as_drifts.elements}
+    assert kinds["q1"] == "Quadrupole" and kinds["cav_off"] == "Drift" and kinds["d1"] == "Drift"
+    assert kinds["bpm_on"] == "BPM" and kinds["m1"] == "Marker"
+    assert torch.equal(as_drifts.length, segment.length)
+    segment.set_attrs_on_every_element(cb.BPM, is_active=True)
+    assert segment.bpm_off.is_active
+    segment.set_attrs_on_every_element(cb.HorizontalCorrector, angle=t(1e-3))
+    assert abs(float(segment.inner.hc.angle) - 1e-3) < 1e-9
