@@ -49,3 +49,39 @@ def shard_segment(segment, n_settings: int, rank: int, world_size: int):
             elif name == "misalignment" and tensor.dim() == 2 and tensor.shape[0] == n_settings:
                 setattr(element, name, tensor[begin:end].contiguous())
     return begin, end
+
+
+def gather_settings(tensor: torch.Tensor, n_settings: int) -> torch.Tensor:
+    """All ranks' slices of a per-setting tensor ``(shard, ...)`` -> ``(n_settings, ...)`` on
+    every rank.  Shards differ by at most one setting (``shard_bounds``), so each is padded to
+    the largest one for the collective and trimmed afterwards.  Meant for REDUCED observables
+    (a few numbers per setting); the tracked particles ``(B, N, 7)`` are never gathered
+    (SURVEY.md 8e)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tensor
+    world = dist.get_world_size()
+    largest = -(-n_settings // world)
+    padded = tensor.new_zeros((largest, *tensor.shape[1:]))
+    padded[: tensor.shape[0]] = tensor
+    pieces = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(pieces, padded.contiguous())
+    sizes = [end - begin for begin, end in (shard_bounds(n_settings, r, world) for r in range(world))]
+    return torch.cat([piece[:size] for piece, size in zip(pieces, sizes)], dim=0)
+
+
+def gather_moments(observed, n_settings: int):
+    """``BeamMoments`` of this rank's settings -> ``BeamMoments`` of the whole batch on every rank
+    (mu, sigma, survivors, covariance: at most 49 numbers per setting)."""
+    from .tracking import BeamMoments
+
+    def gather(tensor, inner_dims: int):
+        # scalars shared by all settings (a common energy or s) are replicated, not gathered
+        if tensor is None or tensor.dim() <= inner_dims:
+            return tensor
+        return gather_settings(tensor, n_settings)
+
+    return BeamMoments(
+        gather(observed.mu, 1), gather(observed.sigma, 1),
+        gather(observed.num_particles_survived, 0), gather(observed.energy, 0),
+        gather(observed.s, 0), cov=gather(observed.cov, 2),
+    )

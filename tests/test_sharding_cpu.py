@@ -81,3 +81,45 @@ def test_two_ranks_shard_settings_and_share_the_beam():
     full = workloads.ares_config3(10, torch.float32)
     k1_full = next(e for e in full if e["name"] == "AREAMQZM1")["k1"]
     assert torch.equal(results[0]["k1"], k1_full)
+
+
+def _gather_worker(rank: int, world: int, port: int, results) -> None:
+    sys.path.insert(0, str(REPO))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cheetah_b200 import sharding
+    from cheetah_b200.tracking import BeamMoments
+
+    n_settings = 5  # 3 + 2: unequal shards
+    begin, end = sharding.shard_bounds(n_settings, rank, world)
+    index = torch.arange(begin, end, dtype=torch.float64)
+    mine = BeamMoments(
+        mu=index[:, None] + torch.arange(6, dtype=torch.float64) * 0.1,
+        sigma=(index[:, None] + 1.0).expand(-1, 6).contiguous(),
+        num_particles_survived=index * 100.0, energy=torch.tensor(1e8, dtype=torch.float64),
+        s=index * 0.5, cov=index[:, None, None] * torch.eye(6, dtype=torch.float64),
+    )
+    whole = sharding.gather_moments(mine, n_settings)
+    results[rank] = {"mu": whole.mu, "sigma": whole.sigma, "survived": whole.num_particles_survived,
+                     "s": whole.s, "cov": whole.cov, "energy": whole.energy}
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gather_reduced_observables():
+    """The only data-path collective the design allows: a final gather of per-setting moments
+    (never the particles), with unequal shard sizes."""
+    world = 2
+    manager = mp.Manager()
+    results = manager.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_gather_worker, args=(world, port, results), nprocs=world, join=True)
+    index = torch.arange(5, dtype=torch.float64)
+    for rank in range(world):
+        got = results[rank]
+        assert torch.equal(got["mu"], index[:, None] + torch.arange(6, dtype=torch.float64) * 0.1)
+        assert torch.equal(got["sigma"], (index[:, None] + 1.0).expand(-1, 6))
+        assert torch.equal(got["survived"], index * 100.0)
+        assert torch.equal(got["s"], index * 0.5)
+        assert torch.equal(got["cov"], index[:, None, None] * torch.eye(6, dtype=torch.float64))
+        assert got["energy"].dim() == 0
