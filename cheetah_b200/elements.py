@@ -123,6 +123,23 @@ class Element(nn.Module):
 
         return tracking.first_order_transfer_map([self], energy, species)
 
+    def transfer_map(self, energy: torch.Tensor, species: Species) -> torch.Tensor:
+        """Deprecated alias of ``first_order_transfer_map`` (element.py:67-102)."""
+        warnings.warn(
+            "The `transfer_map` method is deprecated and will be removed in a future version. "
+            "Use `first_order_transfer_map` instead.", DeprecationWarning, stacklevel=2,
+        )
+        return self.first_order_transfer_map(energy, species)
+
+    @property
+    def defining_features(self) -> list[str]:
+        """Names of the attributes that define the element (element.py:300-313)."""
+        return ["name", *getattr(self, "tensor_fields", {}), *getattr(self, "plain_fields", {})]
+
+    @property
+    def defining_tensors(self) -> list[str]:
+        return [f for f in self.defining_features if isinstance(getattr(self, f), torch.Tensor)]
+
     def track(self, incoming: Beam) -> Beam:
         from . import tracking
 
