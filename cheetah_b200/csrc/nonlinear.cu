@@ -666,41 +666,34 @@ __device__ __forceinline__ void track_dipole(State<C>& st, const double* cc, int
 
 // transverse_deflecting_cavity.py:122-209 in fp64
 template <typename C>
-__device__ __forceinline__ void track_tdc(State<C>& st, const double* cc, const Beam0<double>& r) {
-  State<double> s{st.x, st.px, st.y, st.py, st.l, st.d};
-  const double cs = cc[T_COS], sn = cc[T_SIN], xo = cc[T_XOFF], yo = cc[T_YOFF];
-  offset_set(s, cs, sn, xo, yo);
-  refresh_from_pz(s, r);
-  track_a_drift(s, cc[T_HALF]);
-  const double voltage = cc[T_V], k_rf = cc[T_KRF];
-  const double pc_old = (1.0 + s.d) * r.p0c;
-  const double E_old = sqrt(pc_old * pc_old + r.mc2 * r.mc2);
-  const double beta_old = pc_old / E_old;
-  // phase = 2 pi (phase0 - t f) with t = -z / (beta c)
-  const double phase = cc[T_PHASE] + k_rf * s.l / beta_old;
-  double sp, cp;
-  sincos(phase, &sp, &cp);
-  s.px += voltage * sp;
-  const double E_new = E_old + voltage * cp * k_rf * s.x * r.p0c;
-  const double pc = sqrt(E_new * E_new - r.mc2 * r.mc2);
-  const double beta = pc / E_new;
-  // pz = (pc - p0c) / p0c with pc^2 - p0c^2 = (E_new - E0)(E_new + E0)
-  const double E0 = sqrt(r.p0c * r.p0c + r.mc2 * r.mc2);
-  s.d = (E_new - E0) * (E_new + E0) / (r.p0c * (pc + r.p0c));
-  s.l = s.l * beta / beta_old;
-  refresh_from_pz(s, r);
-  track_a_drift(s, cc[T_HALF]);
-  offset_unset(s, cs, sn, xo, yo);
-  st.x = static_cast<C>(s.x);
-  st.px = static_cast<C>(s.px);
-  st.y = static_cast<C>(s.y);
-  st.py = static_cast<C>(s.py);
-  st.l = static_cast<C>(s.l);
-  st.d = static_cast<C>(s.d);
-  st.iP = static_cast<C>(s.iP);  // pz changed: hand the refreshed pz-dependent quantities back
-  st.rb = static_cast<C>(s.rb);
-  st.inv_beta = static_cast<C>(s.inv_beta);
-  st.delta = static_cast<C>(s.delta);
+__device__ __forceinline__ void track_tdc(State<C>& st, const C* c, const double* cc,
+                                          const Beam0<C>& rc, const Beam0<double>& r) {
+  // frame change and the two half drifts in the beam dtype, like a Drift op (the cached
+  // pz-dependent quantities are valid on entry and refreshed after the kick); only the kick,
+  // whose energy change is a 1e-5 correction on E, is evaluated in fp64
+  offset_set(st, c[T_COS], c[T_SIN], c[T_XOFF], c[T_YOFF]);
+  track_a_drift(st, c[T_HALF]);
+  {
+    const double x = st.x, z = st.l, pz = st.d;
+    const double voltage = cc[T_V], k_rf = cc[T_KRF];
+    const double pc_old = (1.0 + pz) * r.p0c;
+    const double E_old = sqrt(pc_old * pc_old + r.mc2 * r.mc2);
+    const double beta_old = pc_old / E_old;
+    // phase = 2 pi (phase0 - t f) with t = -z / (beta c)
+    const double phase = cc[T_PHASE] + k_rf * z / beta_old;
+    double sp, cp;
+    sincos(phase, &sp, &cp);
+    const double E_new = E_old + voltage * cp * k_rf * x * r.p0c;
+    const double pc = sqrt(E_new * E_new - r.mc2 * r.mc2);
+    const double beta = pc / E_new;
+    // pz = (pc - p0c) / p0c with pc^2 - p0c^2 = (E_new - E0)(E_new + E0)
+    st.px = static_cast<C>(static_cast<double>(st.px) + voltage * sp);
+    st.d = static_cast<C>((E_new - r.E0) * (E_new + r.E0) / (r.p0c * (pc + r.p0c)));
+    st.l = static_cast<C>(z * beta / beta_old);
+  }
+  refresh_from_pz(st, rc);
+  track_a_drift(st, c[T_HALF]);
+  offset_unset(st, c[T_COS], c[T_SIN], c[T_XOFF], c[T_YOFF]);
 }
 
 // The two fp64 bodies are several hundred instructions each: called (not inlined) once per
@@ -712,9 +705,9 @@ __device__ __noinline__ void track_dipole_call(State<C>& st, const double* cc, i
   track_dipole(st, cc, flags, r);
 }
 template <typename C>
-__device__ __noinline__ void track_tdc_call(State<C>& st, const double* cc,
-                                            const Beam0<double>& r) {
-  track_tdc(st, cc, r);
+__device__ __noinline__ void track_tdc_call(State<C>& st, const C* c, const double* cc,
+                                            const Beam0<C>& rc, const Beam0<double>& r) {
+  track_tdc(st, c, cc, rc, r);
 }
 
 // Elements [A, B) of a 16-byte aligned coefficient block through 128-bit shared-memory loads (all
@@ -1007,7 +1000,7 @@ nonlinear_track_kernel(const TrackArgs<T> a) {
         case CH_OP_DKD_TDC:
           if constexpr (FP64_OPS) {
 #pragma unroll
-            for (int k = 0; k < P; ++k) track_tdc_call(s[k], c64, ref64);
+            for (int k = 0; k < P; ++k) track_tdc_call(s[k], c, c64, ref, ref64);
           }
           break;
         case CH_OP_SECOND_ORDER:
