@@ -645,8 +645,7 @@ __device__ __forceinline__ void track_dipole(State<C>& st, const double* cc, int
     const double mc2 = rr.mc2, p0c = rr.p0c;
     const double P = p0c * (1.0 + pz);
     const double E = sqrt(P * P + mc2 * mc2);
-    const double E0 = sqrt(p0c * p0c + mc2 * mc2);
-    const double beta = P / E, beta0 = p0c / E0;
+    const double beta = P / E, beta0 = rr.beta0;  // beta0 = p0c / E0 from the constants header
     s.x = x2;
     s.px = px_norm * sin(angle + phi1 - theta_p);
     s.y = s.y + s.py * Lp / px_norm;
