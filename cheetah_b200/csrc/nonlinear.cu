@@ -513,10 +513,11 @@ __device__ __forceinline__ C low_energy_z_correction(const State<C>& s, C ds, co
   const C pz = s.d;
   const C evaluation = r.mc2 * (r.beta0 * pz) * (r.beta0 * pz);
   const C b2 = r.beta0 * r.beta0;
-  if (evaluation < C(3e-7) * r.E0)
-    return ds * pz * (C(1) - C(3) * (pz * b2) / C(2) +
-                      pz * pz * b2 * (C(2) * b2 - r.mc2_e0_sq / C(2))) * r.mc2_e0_sq;
-  return ds * s.rb;
+  // both forms are a handful of multiply-adds: evaluated unconditionally and selected, so the
+  // warp does not diverge on a per-particle comparison
+  const C low = ds * pz * (C(1) - C(3) * (pz * b2) / C(2) +
+                           pz * pz * b2 * (C(2) * b2 - r.mc2_e0_sq / C(2))) * r.mc2_e0_sq;
+  return evaluation < C(3e-7) * r.E0 ? low : ds * s.rb;
 }
 
 // one plane of bmadx.py:223-260 for the argument `k1` (kx^2 = -k1), step length l
@@ -556,18 +557,23 @@ template <typename C>
 __device__ __forceinline__ QuadPlane<C> quadrupole_plane(C k1, C l, C rel_p, C inv_rel_p) {
   C cx, sx;
   const C w = k1 * l * l;
-  if (w <= C(2.25) && w >= C(-2.25)) {
-    series_cos_sin(w, cx, sx);
-    sx *= l;
-  } else if (k1 < C(0)) {  // kx real: focusing
-    const C k = sqrt_t(-k1);
-    C sn;
-    sincos_t(k * l, sn, cx);
-    sx = sn / k;
-  } else {
-    const C k = sqrt_t(k1);
-    cx = cosh_t(k * l);
-    sx = sinh_t(k * l) / k;
+  // the series is evaluated unconditionally; one warp-uniform test (every lane reaches this
+  // point) skips the closed forms when all 32 particles are inside its range -- the normal case
+  const bool in_range = w <= C(2.25) && w >= C(-2.25);
+  series_cos_sin(w, cx, sx);
+  sx *= l;
+  if (!__all_sync(0xffffffffu, in_range)) {  // rare: some lane needs a closed form
+    if (!in_range) {
+      const C k = sqrt_t(k1 < C(0) ? -k1 : k1);
+      if (k1 < C(0)) {  // kx real: focusing
+        C sn;
+        sincos_t(k * l, sn, cx);
+        sx = sn / k;
+      } else {
+        cx = cosh_t(k * l);
+        sx = sinh_t(k * l) / k;
+      }
+    }
   }
   QuadPlane<C> q;
   q.a11 = cx;
@@ -590,8 +596,9 @@ __device__ __forceinline__ void track_quadrupole(State<C>& s, const C* c, int nu
   const QuadPlane<C> ty = quadrupole_plane(k1, c[Q_STEP], rel_p, s.iP);
   const C dz_low = low_energy_z_correction(s, c[Q_STEP], r);
   for (int step = 0; step < num_steps; ++step) {
-    s.l += tx.c1 * s.x * s.x + tx.c2 * s.x * s.px + tx.c3 * s.px * s.px +
-           ty.c1 * s.y * s.y + ty.c2 * s.y * s.py + ty.c3 * s.py * s.py;
+    // c1 u^2 + c2 u pu + c3 pu^2 per plane as u (c1 u + c2 pu) + (c3 pu) pu: 5 instead of 8 ops
+    s.l += s.x * (tx.c1 * s.x + tx.c2 * s.px) + (tx.c3 * s.px) * s.px +
+           s.y * (ty.c1 * s.y + ty.c2 * s.py) + (ty.c3 * s.py) * s.py;
     const C x = s.x, y = s.y;
     s.x = tx.a11 * x + tx.a12 * s.px;
     s.px = tx.a21 * x + tx.a11 * s.px;

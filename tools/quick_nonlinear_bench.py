@@ -18,7 +18,7 @@ def main():
     species = cb.Species("electron", device=device, dtype=dtype)
     batched = cb.ParticleBeam(particles.expand(B, n, 7).contiguous(), t(1e8), species=species)
     shared = cb.ParticleBeam(particles, t(1e8), species=species)
-    if len(sys.argv) > 3:  # fused 20-element line: drift_kick_drift or second_order
+    if len(sys.argv) > 3 and sys.argv[3] in ("drift_kick_drift", "second_order"):  # fused line
         import bench_nonlinear
         from cheetah_b200 import lattice_description
         method = sys.argv[3]
@@ -43,7 +43,11 @@ def main():
                                                        tracking_method="second_order")]),
         "dipole_dkd": cb.Segment([cb.Dipole(length=t(0.5), angle=t(0.2),
                                             tracking_method="drift_kick_drift")]),
+        "quad_dkd": cb.Segment([cb.Quadrupole(length=t(0.2), k1=t(4.2), num_steps=5,
+                                              tracking_method="drift_kick_drift")]),
     }
+    if len(sys.argv) > 3:  # one single-element case by name
+        cases = {sys.argv[3]: cases[sys.argv[3]]}
     for name, segment in cases.items():
         for _ in range(3):
             out = segment.track(batched)
