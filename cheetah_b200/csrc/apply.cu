@@ -114,6 +114,12 @@ __device__ __forceinline__ uint32_t record_flags(double header) {
 __device__ __forceinline__ bool inside(float v, float bound) { return fabsf(v) < bound; }
 __device__ __forceinline__ bool inside(double v, double bound) { return fabs(v) < bound; }
 
+// accumulator type of the fused moments: the beam dtype (float32 partial sums per thread about the
+// pilot for float32 beams, fp64 for float64 beams -- the reference's golden dtype); fp64 across
+// threads and tiles in both cases
+template <typename T>
+using Acc = T;
+
 // One lattice setting for this thread's P particles: survival masks at every aperture, then
 // the final map into the staging tile.  SPARSE drops the structurally-zero terms (flags).
 // With MOMENTS the outgoing coordinates are also accumulated into `acc` (see the kernel) about
@@ -124,7 +130,7 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
                                                 uint32_t elliptical_mask, const T (&p)[P][7],
                                                 T (&sv)[P], T* stage, int tid,
                                                 const T (&first_particle)[7], T (&pilot)[6],
-                                                float (&acc)[MOMENTS == 2 ? 32 : 16],
+                                                Acc<T> (&acc)[MOMENTS == 2 ? 32 : 16],
                                                 const T* cavity) {
   for (int ap = 0; ap < n_apertures; ++ap) {
     T q[16];
@@ -238,26 +244,25 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
     }
     if constexpr (MOMENTS) {
       // survival-weighted fp32 sums about the pilot (no cancellation); tail lanes carry w = 0
-      const float w = static_cast<float>(sv[k]);
+      const Acc<T> w = sv[k];
       acc[0] += w;
-      acc[1] = fmaf(w, w, acc[1]);
-#pragma unroll
-      float d[6];
+      acc[1] = fma_t(w, w, acc[1]);
+      Acc<T> d[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        d[i] = static_cast<float>(out[i] - pilot[i]);
-        acc[2 + i] = fmaf(w, d[i], acc[2 + i]);
-        acc[8 + i] = fmaf(w * d[i], d[i], acc[8 + i]);
+        d[i] = out[i] - pilot[i];
+        acc[2 + i] = fma_t(w, d[i], acc[2 + i]);
+        acc[8 + i] = fma_t(w * d[i], d[i], acc[8 + i]);
       }
       if constexpr (MOMENTS == 2) {  // the 15 off-diagonal second moments, (0,1), (0,2), ... (4,5)
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          const float wd = w * d[i];
+          const Acc<T> wd = w * d[i];
 #pragma unroll
           for (int j = i + 1; j < 6; ++j) {
             constexpr int kBase = 14;
             const int slot = kBase + i * (11 - i) / 2 + (j - i - 1);
-            acc[slot] = fmaf(wd, d[j], acc[slot]);
+            acc[slot] = fma_t(wd, d[j], acc[slot]);
           }
         }
       }
@@ -269,7 +274,8 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
 // round halves the number of values a lane is responsible for.  Afterwards lane L (L even)
 // holds the warp total of value index ((L >> 4) & 1) * 8 + ((L >> 3) & 1) * 4 +
 // ((L >> 2) & 1) * 2 + ((L >> 1) & 1).
-__device__ __forceinline__ float packed_warp_sum(float (&v)[16], int lane) {
+template <typename A>
+__device__ __forceinline__ A packed_warp_sum(A (&v)[16], int lane) {
 #pragma unroll
   for (int round = 0; round < 4; ++round) {
     const int offset = 16 >> round;      // 16, 8, 4, 2
@@ -277,8 +283,8 @@ __device__ __forceinline__ float packed_warp_sum(float (&v)[16], int lane) {
     const bool upper = (lane & offset) != 0;
 #pragma unroll
     for (int i = 0; i < keep; ++i) {
-      const float send = upper ? v[i] : v[i + keep];
-      const float mine = upper ? v[i + keep] : v[i];
+      const A send = upper ? v[i] : v[i + keep];
+      const A mine = upper ? v[i + keep] : v[i];
       v[i] = mine + __shfl_xor_sync(0xffffffffu, send, offset);
     }
   }
@@ -287,15 +293,16 @@ __device__ __forceinline__ float packed_warp_sum(float (&v)[16], int lane) {
 
 // Same for 32 per-lane values (5 rounds, 31 shuffles): afterwards lane L holds the warp total of
 // value index L.
-__device__ __forceinline__ float packed_warp_sum(float (&v)[32], int lane) {
+template <typename A>
+__device__ __forceinline__ A packed_warp_sum(A (&v)[32], int lane) {
 #pragma unroll
   for (int round = 0; round < 5; ++round) {
     const int offset = 16 >> round;  // 16, 8, 4, 2, 1 = number of values kept
     const bool upper = (lane & offset) != 0;
 #pragma unroll
     for (int i = 0; i < offset; ++i) {
-      const float send = upper ? v[i] : v[i + offset];
-      const float mine = upper ? v[i + offset] : v[i];
+      const A send = upper ? v[i] : v[i + offset];
+      const A mine = upper ? v[i + offset] : v[i];
       v[i] = mine + __shfl_xor_sync(0xffffffffu, send, offset);
     }
   }
@@ -339,7 +346,7 @@ apply_maps_kernel(const ApplyArgs<T> a) {
   constexpr int NACC = MOMENTS == 2 ? 32 : 16;           // per-lane accumulators
   constexpr int NSUM = MOMENTS == 2 ? 29 : 14;           // of which are sums
   constexpr int NOUT = MOMENTS == 2 ? CH_MOMENTS_COV : CH_MOMENTS;
-  __shared__ float partial[2][THREADS / 32][NACC];
+  __shared__ Acc<T> partial[2][THREADS / 32][NACC];
   __shared__ T pilot_shared[2][8];
   auto flush_moments = [&](int buf, int64_t b) {  // threads 0..34 after a barrier
     if (tid < NSUM) {
@@ -442,9 +449,9 @@ apply_maps_kernel(const ApplyArgs<T> a) {
     constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
                                  CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
     T pilot[6];
-    float acc[NACC];
+    Acc<T> acc[NACC];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
+    for (int i = 0; i < NACC; ++i) acc[i] = Acc<T>(0);
     if (MOMENTS) {  // lanes past the end of the beam must not count
 #pragma unroll
       for (int k = 0; k < P; ++k)
@@ -470,7 +477,7 @@ apply_maps_kernel(const ApplyArgs<T> a) {
       // packed warp reduction, then one fp64 atomic per (tile, setting, statistic) issued at
       // the top of the next iteration
       const int lane = tid & 31;
-      const float total = packed_warp_sum(acc, lane);
+      const Acc<T> total = packed_warp_sum(acc, lane);
       if constexpr (MOMENTS == 2) {
         partial[it & 1][tid >> 5][lane] = total;
       } else if ((lane & 1) == 0) {
