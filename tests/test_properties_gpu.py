@@ -230,3 +230,55 @@ def test_screen_conserves_the_surviving_charge_at_full_size():
     on_screen = (out.particles[..., 0].abs() < 1.0e-3) & (out.particles[..., 2].abs() < 1.0e-3)
     expected = (out.particle_charges.abs() * out.survival_probabilities * on_screen).double().sum(-1)
     assert torch.allclose(image.double().sum(dim=(-2, -1)), expected, rtol=2e-4)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1023, 1025])
+def test_tiny_and_ragged_beams(n):
+    """One to a few particles and tile-boundary sizes through every kernel family against the
+    oracle / closed formulas (ragged last tiles, single-particle statistics)."""
+    import cheetah_b200 as cb
+    from oracle import diagnostics_oracle as diag
+    from oracle import track_oracle as oracle
+    from . import golden_utils as gu
+
+    g = torch.Generator().manual_seed(n)
+    particles = torch.randn(n, 7, generator=g, dtype=torch.float64) * 1e-4
+    particles[:, 6] = 1.0
+    t = lambda v: torch.tensor(v, device="cuda", dtype=torch.float64)  # noqa: E731
+    lattice = [
+        {"type": "Quadrupole", "name": "q", "length": torch.tensor(0.2, dtype=torch.float64),
+         "k1": torch.tensor([3.0, -2.0], dtype=torch.float64)},
+        {"type": "Aperture", "name": "a", "x_max": torch.tensor(1.5e-4, dtype=torch.float64),
+         "y_max": torch.tensor(2e-4, dtype=torch.float64), "shape": "rectangular", "is_active": True},
+        {"type": "Drift", "name": "d", "length": torch.tensor(1.0, dtype=torch.float64)},
+    ]
+    beam = oracle.make_beam(particles, torch.tensor(1e8, dtype=torch.float64))
+    expected = oracle.track(lattice, beam)
+    segment = gu.product_segment(lattice, "cuda", torch.float64)
+    product = gu.product_beam(beam, "cuda", torch.float64)
+    out = segment.track(product)
+    assert tuple(out.particles.shape) == (2, n, 7)
+    assert torch.allclose(out.particles.cpu(), expected["particles"], rtol=1e-11, atol=1e-18)
+    assert torch.equal(out.survival_probabilities.cpu(), expected["survival_probabilities"])
+    observed = segment.track_moments(product, covariance=True)
+    survivors = expected["survival_probabilities"].sum(dim=-1)
+    assert torch.equal(observed.num_particles_survived.cpu(), survivors)
+    w = expected["survival_probabilities"]
+    mean = (expected["particles"][..., 0] * w).sum(-1) / w.sum(-1)
+    ok = survivors > 0
+    assert torch.allclose(observed.mu[..., 0].cpu()[ok], mean[ok], rtol=1e-10, atol=1e-18)
+    # non-linear run and a screen on the same beam
+    nonlinear = [{"type": "Drift", "name": "d", "length": torch.tensor(0.7, dtype=torch.float64),
+                  "tracking_method": "drift_kick_drift"},
+                 {"type": "Sextupole", "name": "s", "length": torch.tensor(0.1, dtype=torch.float64),
+                  "k2": torch.tensor(20.0, dtype=torch.float64), "tracking_method": "second_order"}]
+    got = gu.product_segment(nonlinear, "cuda", torch.float64).track(product)
+    assert gu.column_scaled_error(got.particles, oracle.track(nonlinear, beam)["particles"]) < 1e-11
+    for method in ("cloud-in-cell", "histogram", "kde"):
+        screen = cb.Screen(is_active=True, resolution=(40, 30), method=method,
+                           pixel_size=t([2e-5, 2e-5]))
+        screen.track(product)
+        spec = {"resolution": (40, 30), "pixel_size": (2e-5, 2e-5), "method": method}
+        reference = diag.screen_reading(spec, beam)
+        image = screen.reading.cpu()
+        assert float((image - reference).abs().max()) <= 1e-9 * float(reference.max()) + 1e-300
