@@ -27,12 +27,6 @@ COVARIANCES = {
 }
 
 
-def _tensor(value, like: torch.Tensor | None = None, **factory_kwargs) -> torch.Tensor:
-    if isinstance(value, torch.Tensor):
-        return value
-    return torch.tensor(float(value), **factory_kwargs)
-
-
 class Beam(nn.Module):
     """Quantities derived from the first and second moments (cheetah/particles/beam.py:262-557);
     subclasses provide ``mu_*``, ``sigma_*`` and ``_covariance(i, j)``."""

@@ -15,7 +15,6 @@ import warnings
 import torch
 
 from . import _capi, lowering
-from .beam import ParameterBeam, ParticleBeam
 
 
 # When set to a list, every ch_apply_maps launch appends a (start, stop) CUDA-event pair
