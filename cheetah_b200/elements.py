@@ -123,6 +123,13 @@ class Element(nn.Module):
 
         return tracking.first_order_transfer_map([self], energy, species)
 
+    def second_order_transfer_map(self, energy: torch.Tensor, species: Species) -> torch.Tensor:
+        """Dense ``T_ijk`` with the first-order map in ``T[:, 6, :]`` (element.py:134-147) for the
+        elements that support ``tracking_method="second_order"``."""
+        from . import tracking
+
+        return tracking.second_order_transfer_map(self, energy, species)
+
     def transfer_map(self, energy: torch.Tensor, species: Species) -> torch.Tensor:
         """Deprecated alias of ``first_order_transfer_map`` (element.py:67-102)."""
         warnings.warn(
@@ -333,6 +340,16 @@ class RBend(Dipole):
             fringe_at=fringe_at, fringe_type=fringe_type, tracking_method=tracking_method,
             name=name, sanitize_name=sanitize_name, metadata=metadata, **factory_kwargs,
         )
+
+    def clone(self) -> "RBend":
+        import copy
+
+        fields = {key: getattr(self, key).clone() for key in self.tensor_fields
+                  if key not in ("dipole_e1", "dipole_e2")}
+        extras = {key: copy.deepcopy(getattr(self, key)) for key in self.plain_fields}
+        return self.__class__(**fields, **extras, rbend_e1=self.rbend_e1, rbend_e2=self.rbend_e2,
+                              tracking_method=self.tracking_method, name=self.name,
+                              sanitize_name=False, metadata=copy.deepcopy(self.metadata))
 
     @property
     def rbend_e1(self) -> torch.Tensor:

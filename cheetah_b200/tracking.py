@@ -365,6 +365,87 @@ def _track_nonlinear_run(program, run, beam):
                      new_s, species, _unit_seventh(beam))
 
 
+# Layout of a SECOND_ORDER block of the constants table (include/cheetah_b200.h,
+# "second-order block"): frame, edge kicks, the nine distinct entries of the body R and the 39
+# non-zero T_ijk in the order of track_methods.py:147-279.
+_SO_COS, _SO_SIN, _SO_OX, _SO_OY, _SO_KX1, _SO_KY1, _SO_KX2, _SO_KY2, _SO_MX, _SO_MY = range(10)
+_SO_R, _SO_T = 10, 19
+_SO_R_PLACES = {0: [(0, 0), (1, 1)], 1: [(0, 1)], 2: [(1, 0)], 3: [(2, 2), (3, 3)], 4: [(2, 3)],
+                5: [(3, 2)], 6: [(0, 5), (4, 1)], 7: [(1, 5), (4, 0)], 8: [(4, 5)]}
+_SO_T_PLACES = [
+    (0, 0, 0), (0, 0, 1), (0, 1, 1), (0, 0, 5), (0, 1, 5), (0, 5, 5), (0, 2, 2), (0, 2, 3), (0, 3, 3),
+    (1, 0, 0), (1, 0, 1), (1, 1, 1), (1, 0, 5), (1, 1, 5), (1, 5, 5), (1, 2, 2), (1, 2, 3), (1, 3, 3),
+    (2, 0, 2), (2, 0, 3), (2, 1, 2), (2, 1, 3), (2, 2, 5), (2, 3, 5),
+    (3, 0, 2), (3, 0, 3), (3, 1, 2), (3, 1, 3), (3, 2, 5), (3, 3, 5),
+    (4, 0, 0), (4, 0, 1), (4, 1, 1), (4, 0, 5), (4, 1, 5), (4, 5, 5), (4, 2, 2), (4, 2, 3), (4, 3, 3),
+]
+
+
+def second_order_transfer_map(element, energy: torch.Tensor, species) -> torch.Tensor:
+    """Dense ``T (..., 7, 7, 7)`` of ``out_i = sum_jk T_ijk in_j in_k`` with the first-order map in
+    ``T[:, 6, :]`` and the element's frame changes folded in, as the reference returns it
+    (drift.py:68-82, quadrupole.py:113-144, sextupole.py:91-116, dipole.py:397-428).
+
+    The coefficients come from ``ch_nonlinear_constants`` (fp64, the same table the tracking
+    kernel applies in sparse form); only the scatter into the dense tensor and the contraction
+    with the 7 x 7 entry / exit frames -- a few hundred numbers per setting -- are torch ops."""
+    if "second_order" not in element.supported_tracking_methods:
+        raise NotImplementedError
+    _require_cuda(energy, "energy")
+    twin = element.clone()
+    twin.tracking_method = "second_order"
+    device, dtype = energy.device, element.length.dtype
+    program = lowering.lower([twin], device, tuple(energy.shape))
+    run = program.stages[0]
+    assert isinstance(run, lowering.NonlinearRun)
+    vm = tuple(_bshape(run.lattice_shape, energy.shape))
+    n_settings = math.prod(vm)
+    lib = _capi.lib()
+    if energy.dtype not in (torch.float32, torch.float64):
+        energy = energy.to(dtype)
+    energy_c = energy if energy.numel() == 1 else energy.expand(vm).contiguous()
+    with _capi.device_guard(device):
+        n_consts = int(lib.ch_nonlinear_constants_len(program.native, run.op_begin, run.op_end))
+        table = torch.empty((n_settings, n_consts), dtype=torch.float64, device=device)
+        mass_eV, charge = species.mass_eV, species.num_elementary_charges
+        _capi.check(lib.ch_nonlinear_constants(
+            program.native, run.op_begin, run.op_end, n_settings, energy_c.data_ptr(),
+            0 if energy_c.numel() == 1 else 1, _capi.dtype_code(energy_c.dtype),
+            mass_eV.data_ptr(), _capi.dtype_code(mass_eV.dtype),
+            charge.data_ptr(), _capi.dtype_code(charge.dtype),
+            table.data_ptr(), _capi.current_stream(device),
+        ))
+    c = table[:, _capi.NL_HEADER:]
+    eye = torch.eye(7, dtype=torch.float64, device=device).expand(n_settings, 7, 7)
+    body = torch.zeros((n_settings, 7, 7, 7), dtype=torch.float64, device=device)
+    for k, (i, j, l) in enumerate(_SO_T_PLACES):
+        body[:, i, j, l] = c[:, _SO_T + k]
+    first = eye.clone()
+    for k, places in _SO_R_PLACES.items():
+        for i, j in places:
+            first[:, i, j] = c[:, _SO_R + k]
+    body[:, :, 6, :] = first
+    cs, sn = c[:, _SO_COS], c[:, _SO_SIN]
+    entry, leave = eye.clone(), eye.clone()
+    # entry: rotate into the element frame (+ offset), then the entrance edge kick
+    entry[:, 0, 0], entry[:, 0, 2], entry[:, 0, 6] = cs, sn, c[:, _SO_OX]
+    entry[:, 2, 0], entry[:, 2, 2], entry[:, 2, 6] = -sn, cs, c[:, _SO_OY]
+    entry[:, 1, 1], entry[:, 1, 3] = cs, sn
+    entry[:, 3, 1], entry[:, 3, 3] = -sn, cs
+    entry[:, 1, :] = entry[:, 1, :] + c[:, _SO_KX1, None] * entry[:, 0, :]
+    entry[:, 3, :] = entry[:, 3, :] + c[:, _SO_KY1, None] * entry[:, 2, :]
+    # exit: the exit edge kick, then rotate back (+ offset)
+    kick = eye.clone()
+    kick[:, 1, 0], kick[:, 3, 2] = c[:, _SO_KX2], c[:, _SO_KY2]
+    leave[:, 0, 0], leave[:, 0, 2], leave[:, 0, 6] = cs, -sn, c[:, _SO_MX]
+    leave[:, 2, 0], leave[:, 2, 2], leave[:, 2, 6] = sn, cs, c[:, _SO_MY]
+    leave[:, 1, 1], leave[:, 1, 3] = cs, -sn
+    leave[:, 3, 1], leave[:, 3, 3] = sn, cs
+    leave = leave @ kick
+    dense = torch.einsum("bij,bjkl,bkn,blm->binm", leave, body, entry, entry)
+    return dense.reshape(*vm, 7, 7, 7).to(dtype)
+
+
 # Set to False to run every stage as its own pass (tests compare the two paths).
 fuse_space_charge = True
 

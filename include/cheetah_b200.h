@@ -230,7 +230,13 @@ int ch_apply_maps_moments(const void* particles_in, int64_t particle_stride, con
  *   [CH_NL_HEADER]  p0c, mc^2, E0, beta0, (mc^2 / E0)^2, sum of the element lengths, charge,
  *                   1 / p0c, 2 E0 / p0c, 0, 0, 0
  *   then one block per op: CH_NL_BLOCK_SECOND_ORDER scalars if the run holds a second-order op,
- *   else CH_NL_BLOCK_DKD (ch_nonlinear_constants_len gives the total).                      */
+ *   else CH_NL_BLOCK_DKD (ch_nonlinear_constants_len gives the total).
+ * Second-order block (what Element.second_order_transfer_map, element.py:134-147, is assembled
+ * from on the host): [0] cos tilt, [1] sin tilt, [2..3] entry offsets, [4..5] entrance edge kicks
+ * (px += k x, py += k y), [6..7] exit edge kicks, [8..9] exit offsets, [10..18] the body's
+ * R: cx, sx, R10, cy, sy, R32, R05 (= R41), R15 (= R40), R45, [19..57] T_ijk in the order
+ * 000 001 011 005 015 055 022 023 033 | 100 101 111 105 115 155 122 123 133 | 202 203 212 213
+ * 225 235 | 302 303 312 313 325 335 | 400 401 411 405 415 455 422 423 433 (track_methods.py:147-279). */
 #define CH_NL_HEADER 12
 #define CH_NL_BLOCK_DKD 16
 #define CH_NL_BLOCK_SECOND_ORDER 64

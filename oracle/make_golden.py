@@ -852,6 +852,31 @@ def make_beam_properties() -> None:
     print("beam properties:", len(arrays), "arrays, emittance_x", float(arrays["particle.emittance_x"]))
 
 
+def make_second_order_maps() -> None:
+    """Dense second-order transfer maps of the reference (element.py:134-147 and the per-class
+    assemblies) for Element.second_order_transfer_map."""
+    arrays = {}
+    t = lambda v: torch.tensor(v, dtype=torch.float64)  # noqa: E731
+    energy = t([6.3e7, 1.2e8])
+    species = cheetah.Species("electron", dtype=torch.float64)
+    elements = {
+        "drift": cheetah.Drift(length=t(0.7), dtype=torch.float64),
+        "quadrupole": cheetah.Quadrupole(length=t(0.2), k1=t([4.2, -3.1]), tilt=t(0.3),
+                                         misalignment=t([2e-4, -1e-4]), dtype=torch.float64),
+        "sextupole": cheetah.Sextupole(length=t(0.15), k2=t(25.0), tilt=t(-0.2),
+                                       misalignment=t([1e-4, 3e-4]), dtype=torch.float64),
+        "dipole": cheetah.Dipole(length=t(0.5), angle=t(0.2), k1=t(0.4), dipole_e1=t(0.05),
+                                 dipole_e2=t(0.08), tilt=t(0.1), fringe_integral=t(0.5),
+                                 fringe_integral_exit=t(0.4), gap=t(0.03), dtype=torch.float64),
+        "rbend": cheetah.RBend(length=t(0.4), angle=t(-0.15), fringe_integral=t(0.3), gap=t(0.02),
+                               dtype=torch.float64),
+    }
+    for name, element in elements.items():
+        arrays[name] = np64(element.second_order_transfer_map(energy, species))
+    np.savez_compressed(OUT / "second_order_maps.npz", **arrays)
+    print("second-order maps:", {k: v.shape for k, v in arrays.items()})
+
+
 if __name__ == "__main__":
     if "--only-cic" in sys.argv:
         make_cloud_in_cell()
@@ -868,6 +893,9 @@ if __name__ == "__main__":
     if "--only-nonlinear" in sys.argv:
         make_nonlinear()
         sys.exit(0)
+    if "--only-second-order-maps" in sys.argv:
+        make_second_order_maps()
+        sys.exit(0)
     if "--only-beam-properties" in sys.argv:
         make_beam_properties()
         sys.exit(0)
@@ -880,5 +908,6 @@ if __name__ == "__main__":
     make_nonlinear()
     make_diagnostics()
     make_beam_properties()
+    make_second_order_maps()
     for path in sorted(OUT.iterdir()):
         print(f"{path.name:40s} {path.stat().st_size / 1024:8.1f} KiB")

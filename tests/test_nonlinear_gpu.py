@@ -188,3 +188,26 @@ def test_drift_kick_drift_quadrupole_series_and_closed_forms(k1, length, num_ste
     assert tuple(out.particles.shape) == (3, n, 7)
     tolerance = 1e-11 if dtype == torch.float64 else F32_TOL
     assert gu.column_scaled_error(out.particles, expected["particles"]) < tolerance
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", ["drift", "quadrupole", "sextupole", "dipole", "rbend"])
+def test_dense_second_order_transfer_map(name, dtype):
+    """``Element.second_order_transfer_map``: the fp64 coefficient table of
+    ``ch_nonlinear_constants`` scattered into the reference's dense (7, 7, 7) layout with the
+    frames folded in, against tensors from the unmodified reference."""
+    import cheetah_b200 as cb
+
+    from .test_nonlinear_oracle import SECOND_ORDER_MAPS, second_order_element
+
+    element = gu.product_segment([second_order_element(name)], DEVICE, dtype).elements[0]
+    energy = torch.tensor([6.3e7, 1.2e8], device=DEVICE, dtype=dtype)
+    got = element.second_order_transfer_map(energy, cb.Species("electron", device=DEVICE, dtype=dtype))
+    expected = gu.tensor(SECOND_ORDER_MAPS[name])
+    assert got.dtype == dtype and tuple(got.shape) == (2, 7, 7, 7)
+    error = (got.cpu().double() - expected).abs()
+    # entry by entry, relative to the largest coefficient that shares its output row
+    scale = expected.abs().amax(dim=(-2, -1), keepdim=True).clamp_min(1e-300)
+    assert float((error / scale).max()) < (1e-10 if dtype == torch.float64 else 2e-6)
+    with pytest.raises(NotImplementedError):
+        cb.Marker().second_order_transfer_map(energy, cb.Species("electron", device=DEVICE, dtype=dtype))

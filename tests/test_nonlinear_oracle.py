@@ -56,3 +56,36 @@ def test_fresh_reference_outputs_float64(case):
     )
     assert torch.allclose(out["energy"], expected["energy"], rtol=1e-14)
     assert torch.allclose(out["s"], expected["s"])
+
+
+SECOND_ORDER_MAPS = gu.load_npz("second_order_maps.npz")
+SECOND_ORDER_ELEMENTS = {
+    "drift": {"type": "Drift", "length": 0.7},
+    "quadrupole": {"type": "Quadrupole", "length": 0.2, "k1": [4.2, -3.1], "tilt": 0.3,
+                   "misalignment": [2e-4, -1e-4]},
+    "sextupole": {"type": "Sextupole", "length": 0.15, "k2": 25.0, "tilt": -0.2,
+                  "misalignment": [1e-4, 3e-4]},
+    "dipole": {"type": "Dipole", "length": 0.5, "angle": 0.2, "k1": 0.4, "dipole_e1": 0.05,
+               "dipole_e2": 0.08, "tilt": 0.1, "fringe_integral": 0.5, "fringe_integral_exit": 0.4,
+               "gap": 0.03},
+    "rbend": {"type": "RBend", "length": 0.4, "angle": -0.15, "fringe_integral": 0.3, "gap": 0.02},
+}
+
+
+def second_order_element(name: str) -> dict:
+    return {k: (torch.tensor(v, dtype=torch.float64) if not isinstance(v, str) else v)
+            for k, v in SECOND_ORDER_ELEMENTS[name].items()} | {"name": name}
+
+
+@pytest.mark.parametrize("name", sorted(SECOND_ORDER_ELEMENTS))
+def test_dense_second_order_maps_match_the_reference(name):
+    """``Element.second_order_transfer_map`` (element.py:134-147 and the per-class assemblies):
+    the oracle's dense T against tensors computed by the unmodified reference."""
+    from oracle import nonlinear_oracle
+
+    energy = torch.tensor([6.3e7, 1.2e8], dtype=torch.float64)
+    mass = torch.tensor(510998.95069, dtype=torch.float64)
+    got = nonlinear_oracle.second_order_map(second_order_element(name), energy, mass)
+    expected = gu.tensor(SECOND_ORDER_MAPS[name])
+    assert got.shape == expected.shape == (2, 7, 7, 7)
+    assert torch.allclose(got, expected, rtol=1e-10, atol=1e-13 * float(expected.abs().max()))
