@@ -155,6 +155,26 @@ class Element(nn.Module):
     def forward(self, incoming: Beam) -> Beam:
         return self.track(incoming)
 
+    def merge(self, other: "Element") -> "Element | None":
+        """Merged element if ``self`` followed by ``other`` can be expressed as one element of the
+        same type, else ``None`` (element.py:349-358; implemented by Drift, Quadrupole, Sextupole,
+        Solenoid and Segment)."""
+        return None
+
+    def _merged(self, other: "Element", **fields) -> "Element":
+        import os
+
+        prefix = os.path.commonprefix([self.name, other.name])  # utils/names.py:17-38
+        extras = {}
+        if len(self.supported_tracking_methods) > 1:
+            extras["tracking_method"] = self.tracking_method
+        return self.__class__(
+            length=self.length + other.length, **fields, **extras,
+            name=prefix if prefix else f"{self.name}_{other.name}", sanitize_name=False,
+            metadata={**other.metadata, **self.metadata},
+            dtype=self.length.dtype, device=self.length.device,
+        )
+
     def clone(self) -> "Element":
         """Copy of the element that does not share memory with it (element.py:323-336)."""
         import copy
@@ -248,6 +268,11 @@ class Drift(_SimpleElement):
     def split(self, resolution: torch.Tensor) -> list[Element]:
         return self._split_evenly(resolution)
 
+    def merge(self, other: "Drift") -> "Drift | None":
+        if self.tracking_method != other.tracking_method:  # drift.py:175-187
+            return None
+        return self._merged(other)
+
 
 class Quadrupole(_SimpleElement):
     """Quadrupole magnet (cheetah/accelerator/quadrupole.py)."""
@@ -268,6 +293,18 @@ class Quadrupole(_SimpleElement):
         return self._split_evenly(resolution, k1=self.k1, misalignment=self.misalignment,
                                   tilt=self.tilt)
 
+    def merge(self, other: "Quadrupole") -> "Quadrupole | None":
+        """Length-weighted k1, summed ``num_steps`` (quadrupole.py:280-301)."""
+        if not (self.tracking_method == other.tracking_method
+                and self.misalignment.equal(other.misalignment) and self.tilt.equal(other.tilt)):
+            return None
+        return self._merged(
+            other,
+            k1=(self.k1 * self.length + other.k1 * other.length) / (self.length + other.length),
+            misalignment=self.misalignment, tilt=self.tilt,
+            num_steps=self.num_steps + other.num_steps,
+        )
+
 
 class Sextupole(_SimpleElement):
     """Sextupole magnet; linear tracking is a drift (cheetah/accelerator/sextupole.py:84-88)."""
@@ -278,6 +315,12 @@ class Sextupole(_SimpleElement):
     @property
     def is_skippable(self) -> bool:
         return self.tracking_method == "linear"
+
+    def merge(self, other: "Sextupole") -> "Sextupole | None":
+        if not (self.tracking_method == other.tracking_method and self.k2.equal(other.k2)
+                and self.misalignment.equal(other.misalignment) and self.tilt.equal(other.tilt)):
+            return None  # sextupole.py:133-152
+        return self._merged(other, k2=self.k2, misalignment=self.misalignment, tilt=self.tilt)
 
 
 class Dipole(_SimpleElement):
@@ -398,6 +441,15 @@ class Solenoid(_SimpleElement):
     @property
     def is_active(self) -> bool:
         return bool((self.k != 0).any())
+
+    def merge(self, other: "Solenoid") -> "Solenoid | None":
+        if not self.misalignment.equal(other.misalignment):  # solenoid.py:143-157
+            return None
+        return self._merged(
+            other,
+            k=(self.k * self.length + other.k * other.length) / (self.length + other.length),
+            misalignment=self.misalignment,
+        )
 
     def split(self, resolution: torch.Tensor) -> list[Element]:
         return self._split_evenly(resolution, k=self.k, misalignment=self.misalignment)
@@ -823,6 +875,36 @@ class Segment(Element):
     # ---- the reference's lattice simplifications (segment.py:231-330).  The composer already
     # folds markers, inactive monitors and zero-strength magnets into one map, so these do not
     # change the cost of a track() here; they are kept because user code calls them.
+    def merge(self, other: "Segment") -> "Segment":
+        import os
+
+        prefix = os.path.commonprefix([self.name, other.name])  # segment.py:591-597
+        return self.__class__(elements=list(self.elements) + list(other.elements),
+                              name=prefix if prefix else f"{self.name}_{other.name}",
+                              sanitize_name=False, metadata={**other.metadata, **self.metadata})
+
+    def with_consecutive_elements_merged(self, except_for: list[str] | None = None) -> "Segment":
+        """Consecutive mergeable elements of the same type combined into one
+        (segment.py:326-367).  The fused composer makes this unnecessary for speed here."""
+        import copy
+
+        except_for = except_for or []
+        merged, current = [], self.elements[0]
+        for following in list(self.elements)[1:]:
+            if current.name not in except_for:
+                if type(current) is Segment:
+                    current = current.with_consecutive_elements_merged(except_for=except_for)
+                elif type(current) is type(following) and following.name not in except_for:
+                    combined = current.merge(following)
+                    if combined is not None:
+                        current = combined
+                        continue
+            merged.append(current)
+            current = following
+        merged.append(current)
+        return self.__class__(elements=merged, name=self.name, sanitize_name=False,
+                              metadata=copy.deepcopy(self.metadata))
+
     def _filtered(self, keep) -> "Segment":
         return self.__class__(elements=[e for e in self.elements if keep(e)], name=self.name,
                               sanitize_name=False)

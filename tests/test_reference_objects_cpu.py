@@ -113,3 +113,35 @@ def test_clone_and_lattice_simplifications():
     assert segment.bpm_off.is_active
     segment.set_attrs_on_every_element(cb.HorizontalCorrector, angle=t(1e-3))
     assert abs(float(segment.inner.hc.angle) - 1e-3) < 1e-9
+
+
+def test_merging_consecutive_elements():
+    """Element.merge / Segment.with_consecutive_elements_merged (drift.py:175-187,
+    quadrupole.py:280-301, sextupole.py:133-152, solenoid.py:143-157, segment.py:326-367)."""
+    import cheetah_b200 as cb
+
+    t = torch.tensor
+    segment = cb.Segment([
+        cb.Drift(length=t(0.5), name="D1"), cb.Drift(length=t(0.25), name="D2"),
+        cb.Quadrupole(length=t(0.1), k1=t(2.0), name="Q_in", num_steps=2),
+        cb.Quadrupole(length=t(0.3), k1=t(4.0), name="Q_out", num_steps=3),
+        cb.Quadrupole(length=t(0.3), k1=t(4.0), tilt=t(0.1), name="QT"),
+        cb.Sextupole(length=t(0.1), k2=t(3.0), name="S1"), cb.Sextupole(length=t(0.1), k2=t(3.0), name="S2"),
+        cb.Sextupole(length=t(0.1), k2=t(4.0), name="S3"),
+        cb.Solenoid(length=t(0.2), k=t(1.0), name="sol_a"), cb.Solenoid(length=t(0.2), k=t(3.0), name="sol_b"),
+        cb.Drift(length=t(0.1), name="D3"), cb.Drift(length=t(0.1), name="keep"),
+    ], name="line")
+    merged = segment.with_consecutive_elements_merged(except_for=["keep"])
+    assert [e.name for e in merged.elements] == ["D", "Q_", "QT", "S", "S3", "sol_", "D3", "keep"]
+    assert torch.isclose(merged.length, segment.length)
+    assert torch.isclose(merged.Q_.k1, t(3.5)) and merged.Q_.num_steps == 5
+    assert torch.isclose(merged.sol_.k, t(2.0))
+    assert torch.isclose(merged.D.length, t(0.75))
+    # different tracking methods or frames do not merge
+    a = cb.Drift(length=t(0.1), tracking_method="drift_kick_drift")
+    assert a.merge(cb.Drift(length=t(0.1))) is None
+    assert a.merge(cb.Drift(length=t(0.2), tracking_method="drift_kick_drift")).tracking_method == \
+        "drift_kick_drift"
+    assert cb.Marker().merge(cb.Marker()) is None
+    both = cb.Segment([a], name="cell_1").merge(cb.Segment([cb.Marker(name="m")], name="cell_2"))
+    assert both.name == "cell_" and len(both.elements) == 2
