@@ -270,6 +270,76 @@ class ParticleBeam(Beam):
             device=device, dtype=dtype, generator=generator,
         )
 
+    @classmethod
+    def uniform_3d_ellipsoid(cls, num_particles: int = 100_000, radius_x=1e-3, radius_y=1e-3,
+                             radius_tau=1e-3, sigma_px=4e-6, sigma_py=4e-6, sigma_p=2e-3,
+                             energy=None, total_charge=None, s=None, species=None, device=None,
+                             dtype=None, generator: torch.Generator | None = None
+                             ) -> "ParticleBeam":
+        """Waterbag beam: positions uniform inside an ellipsoid, Gaussian uncorrelated momenta
+        (particle_beam.py:563-666; the space-charge expansion test of the reference starts from
+        it)."""
+        beam = cls.from_parameters(
+            num_particles, sigma_x=radius_x, sigma_px=sigma_px, sigma_y=radius_y,
+            sigma_py=sigma_py, sigma_tau=radius_tau, sigma_p=sigma_p, energy=energy,
+            total_charge=total_charge, s=s, species=species, device=device, dtype=dtype,
+            generator=generator,
+        )
+        uniform = torch.rand(3, num_particles, dtype=torch.float64, generator=generator)
+        r = uniform[0].pow(1 / 3)                   # uniform in the volume of the unit sphere
+        theta = (2 * uniform[1] - 1).arccos()
+        phi = uniform[2] * 2 * torch.pi
+        unit = torch.stack([r * theta.sin() * phi.cos(), r * theta.sin() * phi.sin(),
+                            r * theta.cos()])
+        radii = [float(radius_x), float(radius_y), float(radius_tau)]
+        for column, radius, values in zip((0, 2, 4), radii, unit):
+            beam.particles[..., column] = (values * radius).to(beam.particles)
+        return beam
+
+    @classmethod
+    def make_linspaced(cls, num_particles: int = 10, energy=None, total_charge=None, s=None,
+                       species=None, device=None, dtype=None, **moments) -> "ParticleBeam":
+        """``num_particles`` particles evenly spaced from ``mu - sigma`` to ``mu + sigma`` in every
+        coordinate; ``mu_*`` / ``sigma_*`` by keyword, tensors of broadcastable shapes
+        (particle_beam.py:668-803)."""
+        factory_kwargs = {"device": device, "dtype": dtype}
+        defaults = {"sigma_x": 175e-9, "sigma_px": 2e-7, "sigma_y": 175e-9, "sigma_py": 2e-7,
+                    "sigma_tau": 1e-6, "sigma_p": 1e-6}
+        for name in moments:
+            assert name in {f"{k}_{c}" for k in ("mu", "sigma") for c in COORDINATES}, (
+                f"unknown beam parameter {name!r}"
+            )
+        value = lambda name: torch.as_tensor(  # noqa: E731
+            moments[name] if moments.get(name) is not None else defaults.get(name, 0.0),
+            **factory_kwargs)
+        species = species if species is not None else Species("electron", **factory_kwargs)
+        energy = energy if energy is not None else torch.tensor(1e8, **factory_kwargs)
+        total_charge = torch.as_tensor(
+            total_charge if total_charge is not None else species.charge_coulomb * num_particles,
+            **factory_kwargs)
+        charges = (torch.ones((*total_charge.shape, num_particles), **factory_kwargs)
+                   * total_charge.unsqueeze(-1) / num_particles)
+        centres = [value(f"mu_{c}") for c in COORDINATES]
+        widths = [value(f"sigma_{c}") for c in COORDINATES]
+        vector_shape = torch.broadcast_shapes(*[t.shape for t in centres + widths])
+        particles = torch.ones((*vector_shape, num_particles, 7), **factory_kwargs)
+        steps = torch.linspace(-1.0, 1.0, num_particles, **factory_kwargs)
+        for i, (mu, sigma) in enumerate(zip(centres, widths)):
+            particles[..., i] = mu.unsqueeze(-1) + sigma.unsqueeze(-1) * steps
+        return cls(particles, energy, particle_charges=charges, s=s, species=species,
+                   device=device, dtype=dtype)
+
+    def linspaced(self, num_particles: int) -> "ParticleBeam":
+        """Evenly spaced beam with this beam's centres, sigmas, energy and total charge
+        (particle_beam.py:1180-1210)."""
+        moments = {f"{k}_{c}": getattr(self, f"{k}_{c}") for k in ("mu", "sigma")
+                   for c in COORDINATES}
+        return self.make_linspaced(
+            num_particles, energy=self.energy, total_charge=self.total_charge, s=self.s,
+            species=self.species, device=self.particles.device, dtype=self.particles.dtype,
+            **moments,
+        )
+
     # ---- views and moments -----------------------------------------------------------------
     @property
     def num_particles(self) -> int:

@@ -143,3 +143,29 @@ def test_particle_beam_properties_from_the_covariance_kernel(dtype):
                       survival_probabilities=beam.survival_probabilities, species=beam.species)
     assert tuple(wide.second_moments()[1].shape) == (3, 6, 6)
     assert tuple(wide.emittance_x.shape) == (3,)
+
+
+def test_waterbag_and_linspaced_generators():
+    """uniform_3d_ellipsoid (particle_beam.py:563-666: uniform density inside the ellipsoid, so
+    sigma = radius / sqrt(5)) and make_linspaced / linspaced (:668-803, :1180-1210)."""
+    import cheetah_b200 as cb
+
+    beam = cb.ParticleBeam.uniform_3d_ellipsoid(
+        num_particles=200_000, radius_x=1e-3, radius_y=2e-3, radius_tau=5e-4, sigma_px=1e-5,
+        dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    inside = (beam.x / 1e-3) ** 2 + (beam.y / 2e-3) ** 2 + (beam.tau / 5e-4) ** 2
+    assert float(inside.max()) <= 1.0 + 1e-12
+    for name, radius in (("sigma_x", 1e-3), ("sigma_y", 2e-3), ("sigma_tau", 5e-4)):
+        assert abs(float(getattr(beam, name)) / (radius / 5 ** 0.5) - 1.0) < 1e-2
+    assert abs(float(beam.sigma_px) / 1e-5 - 1.0) < 1e-2
+    t = lambda v: torch.tensor(v, dtype=torch.float64)  # noqa: E731
+    line = cb.ParticleBeam.make_linspaced(num_particles=5, mu_x=t([0.0, 1e-3]), sigma_x=t(2e-4),
+                                          sigma_p=t(1e-3), dtype=torch.float64)
+    assert tuple(line.particles.shape) == (2, 5, 7)
+    assert torch.allclose(line.x[1], t([8e-4, 9e-4, 1e-3, 1.1e-3, 1.2e-3]))
+    assert torch.allclose(line.p[0], t([-1e-3, -5e-4, 0.0, 5e-4, 1e-3]))
+    assert torch.equal(line.particles[..., 6], torch.ones(2, 5, dtype=torch.float64))
+    again = particle_beam().linspaced(11)
+    assert again.num_particles == 11
+    assert torch.isclose(again.mu_x, particle_beam().mu_x, rtol=1e-9)
+    assert torch.isclose(again.total_charge, particle_beam().total_charge, rtol=1e-9)
