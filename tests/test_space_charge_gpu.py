@@ -297,3 +297,39 @@ def test_fused_kick_pipeline_equals_the_stage_by_stage_one(case, dtype):
     assert float(((fused.particles - unfused.particles).abs() / scale).max()) < tol
     assert torch.equal(fused.survival_probabilities, unfused.survival_probabilities)
     assert torch.allclose(fused.s, unfused.s)
+
+
+@pytest.mark.parametrize("energy", [2.5e8, 1e6], ids=["ultra-relativistic", "non-relativistic"])
+def test_cold_uniform_bunch_doubles_in_size(energy):
+    """Known-answer test of the reference (tests/test_space_charge_kick.py:14-69; free expansion
+    of a cold uniform bunch): after the drift length
+    L = beta gamma kappa sqrt(R0^3 / (N r_e)), kappa = 1 + sqrt(2)/4 ln(3 + 2 sqrt(2)), with three
+    space-charge kicks, all three beam sizes have doubled within 2 %."""
+    import math
+
+    import cheetah_b200 as cb
+
+    r0, total_charge = 1e-3, 1e-8
+    electron_radius = 2.8179403205e-15
+    gamma = energy / 510998.95069
+    beta = math.sqrt(1 - 1 / gamma ** 2)
+    incoming = cb.ParticleBeam.uniform_3d_ellipsoid(
+        num_particles=100_000, radius_x=r0, radius_y=r0, radius_tau=r0 / gamma / beta,
+        sigma_px=1e-15, sigma_py=1e-15, sigma_p=1e-15, energy=torch.tensor(energy),
+        total_charge=torch.tensor(total_charge), device=DEVICE, dtype=torch.float32,
+        generator=torch.Generator().manual_seed(2),
+    )
+    kappa = 1 + math.sqrt(2) / 4 * math.log(3 + 2 * math.sqrt(2))
+    n_electrons = total_charge / 1.602176634e-19
+    length = beta * gamma * kappa * math.sqrt(r0 ** 3 / (n_electrons * electron_radius))
+    t = lambda v: torch.tensor(v, device=DEVICE, dtype=torch.float32)  # noqa: E731
+    segment = cb.Segment([
+        cb.Drift(length=t(length / 6)), cb.SpaceChargeKick(effect_length=t(length / 3)),
+        cb.Drift(length=t(length / 3)), cb.SpaceChargeKick(effect_length=t(length / 3)),
+        cb.Drift(length=t(length / 3)), cb.SpaceChargeKick(effect_length=t(length / 3)),
+        cb.Drift(length=t(length / 6)),
+    ])
+    outgoing = segment.track(incoming)
+    for name in ("sigma_x", "sigma_y", "sigma_tau"):
+        ratio = float(getattr(outgoing, name) / getattr(incoming, name))
+        assert abs(ratio / 2.0 - 1.0) < 2e-2, (name, ratio)
