@@ -451,3 +451,30 @@ def test_active_cavity_parameter_beam(case, tag, dtype):
     assert torch.allclose(out.energy.cpu().double(),
                           gu.tensor(CAVITY[f"{case}.f64.parameter_energy"]),
                           rtol=1e-12 if dtype == torch.float64 else 1e-6)
+
+
+@pytest.mark.parametrize("shape,expected", [("elliptical", [0.0235, 0.42, 0.552]),
+                                            ("rectangular", [0.029, 0.495, 0.629])])
+def test_vectorised_aperture_survival_fractions(shape, expected):
+    """Known-answer test of the reference (tests/test_vectorized.py:461-504): a Gaussian beam
+    (sigma_px = 2e-4, sigma_py = 1e-4) through Drift(0.5) - Aperture(x_max (3, 1), y_max 2e-4) -
+    Drift(0.5) with two beam energies: broadcast shapes and the surviving fractions to 5e-3."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE)  # noqa: E731
+    incoming = cb.ParticleBeam.from_parameters(
+        num_particles=100_000, sigma_px=2e-4, sigma_py=1e-4, energy=t([154e6, 14e9]),
+        device=DEVICE, generator=torch.Generator().manual_seed(7),
+    )
+    segment = cb.Segment([
+        cb.Drift(length=t(0.5)),
+        cb.Aperture(x_max=t([[1e-5], [2e-4], [3e-4]]), y_max=t(2e-4), shape=shape),
+        cb.Drift(length=t(0.5)),
+    ])
+    outgoing = segment.track(incoming)
+    assert tuple(outgoing.particles.shape) == (2, 100_000, 7)
+    assert tuple(outgoing.energy.shape) == (2,)
+    assert tuple(outgoing.particle_charges.shape) == (100_000,)
+    assert tuple(outgoing.survival_probabilities.shape) == (3, 2, 100_000)
+    fractions = outgoing.survival_probabilities.mean(dim=-1)[:, 0].cpu()
+    assert torch.allclose(fractions, torch.tensor(expected), atol=5e-3), fractions
