@@ -141,7 +141,10 @@ class Element(nn.Module):
     @property
     def defining_features(self) -> list[str]:
         """Names of the attributes that define the element (element.py:300-313)."""
-        return ["name", *getattr(self, "tensor_fields", {}), *getattr(self, "plain_fields", {})]
+        features = ["name", *getattr(self, "tensor_fields", {}), *getattr(self, "plain_fields", {})]
+        if len(self.supported_tracking_methods) > 1:
+            features.append("tracking_method")
+        return features
 
     @property
     def defining_tensors(self) -> list[str]:
@@ -648,6 +651,10 @@ class CustomTransferMap(Element):
         ).all(), "The seventh row of the transfer map must be [0, 0, 0, 0, 0, 0, 1]."
         self.register_buffer_or_parameter("predefined_transfer_map", predefined_transfer_map)
 
+    @property
+    def defining_features(self) -> list[str]:
+        return ["name", "predefined_transfer_map", "length"]
+
     def clone(self) -> "CustomTransferMap":
         import copy
 
@@ -709,6 +716,10 @@ class Superimposed(Element):
 
     def flattened(self) -> "Segment":
         return self._segment.flattened()
+
+    @property
+    def defining_features(self) -> list[str]:
+        return ["name", "base_element", "superimposed_element"]
 
     def clone(self) -> "Superimposed":
         import copy
@@ -784,6 +795,13 @@ class Segment(Element):
         if name is not None:
             segment.name = name
         return segment
+
+    def to_lattice_json(self, filepath, title: str | None = None,
+                        info: str = "This is a placeholder lattice description") -> None:
+        """Save in the reference's LatticeJSON format (segment.py:386-396)."""
+        from . import latticejson
+
+        latticejson.save_segment(self, filepath, title=title, info=info)
 
     # ---- container helpers (segment.py:73-229, :576-656) ------------------------------------
     @property

@@ -145,3 +145,58 @@ def test_merging_consecutive_elements():
     assert cb.Marker().merge(cb.Marker()) is None
     both = cb.Segment([a], name="cell_1").merge(cb.Segment([cb.Marker(name="m")], name="cell_2"))
     assert both.name == "cell_" and len(both.elements) == 2
+
+
+def _sample_lattice():
+    import cheetah_b200 as cb
+
+    t = torch.tensor
+    return cb.Segment([
+        cb.Drift(length=t(0.5), name="d1", tracking_method="drift_kick_drift"),
+        cb.Quadrupole(length=t(0.2), k1=t([1.0, -2.0]), tilt=t(0.1), misalignment=t([1e-4, 0.0]),
+                      num_steps=3, name="q1"),
+        cb.Dipole(length=t(0.4), angle=t(0.1), dipole_e1=t(0.02), fringe_integral=t(0.5), gap=t(0.03),
+                  fringe_at="entrance", name="b1"),
+        cb.Segment([cb.Marker(name="m1"), cb.HorizontalCorrector(length=t(0.1), angle=t(1e-3), name="h1")],
+                   name="inner"),
+        cb.Aperture(x_max=t(1e-3), y_max=t(2e-3), shape="elliptical", name="a1"),
+        cb.Screen(resolution=(64, 48), pixel_size=t([1e-5, 2e-5]), binning=2, method="kde",
+                  is_active=True, name="s1"),
+        cb.SpaceChargeKick(effect_length=t(0.3), grid_shape=(16, 16, 8), name="sc1"),
+        cb.Superimposed(cb.Drift(length=t(1.0), name="long_drift"), cb.Marker(name="mid"), name="sup1"),
+    ], name="line")
+
+
+def test_lattice_json_round_trip(tmp_path):
+    """Segment.to_lattice_json / from_lattice_json (segment.py:370-396, latticejson.py)."""
+    import cheetah_b200 as cb
+
+    segment = _sample_lattice()
+    path = tmp_path / "line.json"
+    segment.to_lattice_json(path, title="test lattice")
+    loaded = cb.Segment.from_lattice_json(path)
+    assert loaded.name == "line"
+    assert [type(e).__name__ for e in loaded.elements] == [type(e).__name__ for e in segment.elements]
+    assert [e.name for e in loaded.elements] == [e.name for e in segment.elements]
+    assert loaded.d1.tracking_method == "drift_kick_drift"
+    assert torch.equal(loaded.q1.k1, segment.q1.k1) and loaded.q1.num_steps == 3
+    assert loaded.b1.fringe_at == "entrance" and torch.equal(loaded.b1.dipole_e1, segment.b1.dipole_e1)
+    assert [e.name for e in loaded.inner.elements] == ["m1", "h1"]
+    assert loaded.a1.shape == "elliptical" and float(loaded.a1.y_max) == pytest.approx(2e-3)
+    assert tuple(loaded.s1.resolution) == (64, 48) and loaded.s1.method == "kde" and loaded.s1.is_active
+    assert tuple(loaded.sc1.grid_shape) == (16, 16, 8)
+    assert type(loaded.sup1.superimposed_element).__name__ == "Marker"
+    assert torch.isclose(loaded.length, segment.length)
+
+
+def test_the_reference_reads_our_lattice_json(tmp_path):
+    """The file we write loads in the unmodified reference (skipped where it is not installed)."""
+    cheetah = pytest.importorskip("cheetah")
+    segment = _sample_lattice()
+    path = tmp_path / "line.json"
+    segment.to_lattice_json(path)
+    theirs = cheetah.Segment.from_lattice_json(str(path))
+    assert [type(e).__name__ for e in theirs.elements] == [type(e).__name__ for e in segment.elements]
+    assert torch.equal(theirs.q1.k1, segment.q1.k1)
+    assert theirs.d1.tracking_method == "drift_kick_drift"
+    assert torch.isclose(theirs.length, segment.length)
