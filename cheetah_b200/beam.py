@@ -170,11 +170,13 @@ class ParticleBeam(Beam):
         dtype: torch.dtype | None = None,
         generator: torch.Generator | None = None,
     ) -> "ParticleBeam":
-        """Gaussian beam with mean ``mu (6,)`` and covariance ``cov (6, 6)``.
+        """Gaussian beam with mean ``mu (..., 6)`` and covariance ``cov (..., 6, 6)``.
 
-        Unlike the reference (particle_beam.py:357-431) the sample moments are not matched
-        to (mu, cov) exactly; samples are drawn through a Cholesky factor.
-        """
+        As in the reference (particle_beam.py:357-431, ``match_distribution_moments``,
+        utils/statistics.py:91-150) ONE standard-normal sample ``(N, 6)`` is whitened to exactly
+        zero mean and unit covariance and then mapped by the Cholesky factor of every target
+        covariance, so the sample moments of every vector entry equal ``(mu, cov)`` exactly.  The
+        sampling runs in float64 on the host (``generator`` for reproducibility)."""
         dtype = dtype if dtype is not None else torch.get_default_dtype()
         factory_kwargs = {"device": device, "dtype": dtype}
         species = species if species is not None else Species("electron", **factory_kwargs)
@@ -187,12 +189,23 @@ class ParticleBeam(Beam):
             * total_charge.unsqueeze(-1)
             / num_particles
         )
-        factor = torch.linalg.cholesky(
-            cov.to(torch.float64).cpu() + 1e-300 * torch.eye(6, dtype=torch.float64)
-        )
+        mu64 = torch.as_tensor(mu).detach().to("cpu", torch.float64)
+        cov64 = torch.as_tensor(cov).detach().to("cpu", torch.float64)
         standard = torch.randn(num_particles, 6, dtype=torch.float64, generator=generator)
-        samples = standard @ factor.mT + mu.to(torch.float64).cpu()
-        particles = torch.cat([samples, torch.ones(num_particles, 1, dtype=torch.float64)], dim=-1)
+        if num_particles > 6:  # whiten the sample (needs a non-singular sample covariance)
+            centred = standard - standard.mean(dim=0, keepdim=True)
+            sample_factor = torch.linalg.cholesky(centred.mT @ centred / (num_particles - 1))
+            standard = torch.linalg.solve_triangular(sample_factor, centred.mT, upper=False).mT
+        factor, info = torch.linalg.cholesky_ex(cov64)
+        if bool((info != 0).any()):  # semi-definite target (a zero sigma): symmetric square root
+            values, vectors = torch.linalg.eigh(cov64)
+            factor = vectors * values.clamp_min(0.0).sqrt().unsqueeze(-2)
+        vector_shape = torch.broadcast_shapes(mu64.shape[:-1], cov64.shape[:-2])
+        samples = (
+            standard @ factor.expand(*vector_shape, 6, 6).mT
+            + mu64.expand(*vector_shape, 6).unsqueeze(-2)
+        )
+        particles = torch.cat([samples, torch.ones_like(samples[..., :1])], dim=-1)
         beam = cls(
             particles.to(**factory_kwargs),
             energy.to(**factory_kwargs),
@@ -221,20 +234,25 @@ class ParticleBeam(Beam):
         generator: torch.Generator | None = None,
         **other_covariances,
     ) -> "ParticleBeam":
-        """Defaults follow particle_beam.py:199-216; the other twelve ``cov_*`` of
-        particle_beam.py:109-140 are accepted by keyword."""
-        f = lambda v: float(v)  # noqa: E731
-        mu = torch.tensor([f(mu_x), f(mu_px), f(mu_y), f(mu_py), f(mu_tau), f(mu_p)], dtype=torch.float64)
-        cov = torch.zeros(6, 6, dtype=torch.float64)
-        for i, sigma in enumerate((sigma_x, sigma_px, sigma_y, sigma_py, sigma_tau, sigma_p)):
-            cov[i, i] = f(sigma) ** 2
-        cov[0, 1] = cov[1, 0] = f(cov_xpx)
-        cov[2, 3] = cov[3, 2] = f(cov_ypy)
-        cov[4, 5] = cov[5, 4] = f(cov_taup)
+        """Defaults follow particle_beam.py:199-216; numbers or tensors of mutually broadcastable
+        shapes (a vectorised beam); the other twelve ``cov_*`` of particle_beam.py:109-140 are
+        accepted by keyword."""
+        t = lambda v: torch.as_tensor(v if v is not None else 0.0).detach().to(  # noqa: E731
+            "cpu", torch.float64)
+        means = [t(v) for v in (mu_x, mu_px, mu_y, mu_py, mu_tau, mu_p)]
+        sigmas = [t(v) for v in (sigma_x, sigma_px, sigma_y, sigma_py, sigma_tau, sigma_p)]
+        covariances = {"cov_xpx": t(cov_xpx), "cov_ypy": t(cov_ypy), "cov_taup": t(cov_taup)}
         for name, value in other_covariances.items():
             assert name in COVARIANCES, f"unknown beam parameter {name!r}"
+            covariances[name] = t(value)
+        mu = torch.stack(torch.broadcast_tensors(*means), dim=-1)
+        shape = torch.broadcast_shapes(*[v.shape for v in sigmas + list(covariances.values())])
+        cov = torch.zeros((*shape, 6, 6), dtype=torch.float64)
+        for i, sigma in enumerate(sigmas):
+            cov[..., i, i] = sigma.square()
+        for name, value in covariances.items():
             i, j = COVARIANCES[name]
-            cov[i, j] = cov[j, i] = f(value)
+            cov[..., i, j] = cov[..., j, i] = value
         return cls.from_distribution(
             mu, cov, num_particles, energy, total_charge, s, species, device, dtype, generator
         )
@@ -246,6 +264,7 @@ class ParticleBeam(Beam):
         beta_x=0.0, alpha_x=0.0, emittance_x=7.1971891e-13,
         beta_y=0.0, alpha_y=0.0, emittance_y=7.1971891e-13,
         sigma_tau=1e-6, sigma_p=1e-6, cov_taup=0.0,
+        dispersion_x=0.0, dispersion_px=0.0, dispersion_y=0.0, dispersion_py=0.0,
         energy: torch.Tensor | None = None,
         total_charge: torch.Tensor | None = None,
         s: torch.Tensor | None = None,
@@ -254,18 +273,26 @@ class ParticleBeam(Beam):
         dtype: torch.dtype | None = None,
         generator: torch.Generator | None = None,
     ) -> "ParticleBeam":
-        """Twiss -> second moments as in particle_beam.py:499-533 (no dispersion terms)."""
-        f = lambda v: float(v)  # noqa: E731
+        """Twiss and dispersion functions -> second moments as in particle_beam.py:434-561."""
+        t = lambda v: torch.as_tensor(v).detach().to("cpu", torch.float64)  # noqa: E731
+        beta_x, alpha_x, emittance_x = t(beta_x), t(alpha_x), t(emittance_x)
+        beta_y, alpha_y, emittance_y = t(beta_y), t(alpha_y), t(emittance_y)
+        sigma_p = t(sigma_p)
+        dx, dpx, dy, dpy = t(dispersion_x), t(dispersion_px), t(dispersion_y), t(dispersion_py)
+        assert (beta_x > 0).all(), "Beta function in x direction must be larger than 0 everywhere."
+        assert (beta_y > 0).all(), "Beta function in y direction must be larger than 0 everywhere."
+        p2 = sigma_p.square()
         return cls.from_parameters(
             num_particles,
-            sigma_x=(f(beta_x) * f(emittance_x)) ** 0.5,
-            sigma_px=(f(emittance_x) * (1 + f(alpha_x) ** 2) / f(beta_x)) ** 0.5,
-            sigma_y=(f(beta_y) * f(emittance_y)) ** 0.5,
-            sigma_py=(f(emittance_y) * (1 + f(alpha_y) ** 2) / f(beta_y)) ** 0.5,
+            sigma_x=(emittance_x * beta_x + dx.square() * p2).sqrt(),
+            sigma_px=(emittance_x * (1 + alpha_x.square()) / beta_x + dpx.square() * p2).sqrt(),
+            sigma_y=(emittance_y * beta_y + dy.square() * p2).sqrt(),
+            sigma_py=(emittance_y * (1 + alpha_y.square()) / beta_y + dpy.square() * p2).sqrt(),
             sigma_tau=sigma_tau, sigma_p=sigma_p,
-            cov_xpx=-f(emittance_x) * f(alpha_x),
-            cov_ypy=-f(emittance_y) * f(alpha_y),
+            cov_xpx=-emittance_x * alpha_x + dx * dpx * p2,
+            cov_ypy=-emittance_y * alpha_y + dy * dpy * p2,
             cov_taup=cov_taup,
+            cov_xp=dx * p2, cov_pxp=dpx * p2, cov_yp=dy * p2, cov_pyp=dpy * p2,
             energy=energy, total_charge=total_charge, s=s, species=species,
             device=device, dtype=dtype, generator=generator,
         )

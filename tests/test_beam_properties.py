@@ -169,3 +169,36 @@ def test_waterbag_and_linspaced_generators():
     assert again.num_particles == 11
     assert torch.isclose(again.mu_x, particle_beam().mu_x, rtol=1e-9)
     assert torch.isclose(again.total_charge, particle_beam().total_charge, rtol=1e-9)
+
+
+def test_generated_beams_have_exactly_the_requested_moments():
+    """from_parameters / from_twiss / from_distribution whiten one shared sample and map it per
+    vector entry (particle_beam.py:357-431, statistics.py:91-150): sample moments equal the
+    targets to rounding, for vectorised parameters too."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, dtype=torch.float64)  # noqa: E731
+    g = torch.Generator().manual_seed(0)
+    beam = cb.ParticleBeam.from_parameters(
+        num_particles=10_000, mu_y=3e-5, sigma_x=t([1e-4, 2e-4]), sigma_px=t(3e-5), cov_xpx=1e-10,
+        cov_xp=t([[1e-8], [2e-8], [0.0]]), dtype=torch.float64, generator=g)
+    assert tuple(beam.particles.shape) == (3, 2, 10_000, 7)
+    assert torch.allclose(beam.sigma_x, t([1e-4, 2e-4]).expand(3, 2), rtol=1e-10)
+    assert torch.allclose(beam.cov_xpx, t(1e-10).expand(3, 2), rtol=1e-9)
+    assert torch.allclose(beam.cov_xp, t([[1e-8], [2e-8], [0.0]]).expand(3, 2), rtol=1e-9, atol=1e-20)
+    assert torch.allclose(beam.mu_y, t(3e-5).expand(3, 2), rtol=1e-10)
+    assert torch.allclose(beam.mu_x, torch.zeros(3, 2, dtype=torch.float64), atol=1e-18)
+    twiss = cb.ParticleBeam.from_twiss(
+        num_particles=5000, beta_x=3.14, alpha_x=-0.5, beta_y=t([42.0, 10.0]), dispersion_x=0.1,
+        sigma_p=1e-3, dtype=torch.float64, generator=g)
+    # (the dispersive part of sigma_x^2 is 4000 x the betatron part here: the dispersion-corrected
+    # quantities subtract nearly equal numbers)
+    assert torch.allclose(twiss.beta_x, t(3.14).expand(2), rtol=1e-6)
+    assert torch.allclose(twiss.alpha_x, t(-0.5).expand(2), rtol=1e-6)
+    assert torch.allclose(twiss.beta_y, t([42.0, 10.0]), rtol=1e-8)
+    assert torch.allclose(twiss.dispersion_x, t(0.1).expand(2), rtol=1e-8)
+    assert torch.allclose(twiss.emittance_x, t(7.1971891e-13).expand(2), rtol=1e-6)
+    cold = cb.ParticleBeam.from_parameters(num_particles=1000, sigma_p=0.0, generator=g)
+    assert float(cold.sigma_p) == 0.0 and float(cold.sigma_x) == pytest.approx(175e-6, rel=1e-5)
+    with pytest.raises(AssertionError, match="Beta function in x"):
+        cb.ParticleBeam.from_twiss(num_particles=10)
