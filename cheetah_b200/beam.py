@@ -709,6 +709,16 @@ class ParameterBeam(Beam):
             self.species, self.mu.device, self.mu.dtype, generator,
         )
 
+    def linspaced(self, num_particles: int) -> ParticleBeam:
+        """ParticleBeam of evenly spaced particles with this beam's centres and sigmas
+        (parameter_beam.py:610-640)."""
+        moments = {f"{k}_{c}": getattr(self, f"{k}_{c}") for k in ("mu", "sigma")
+                   for c in COORDINATES}
+        return ParticleBeam.make_linspaced(
+            num_particles, energy=self.energy, total_charge=self.total_charge, s=self.s,
+            species=self.species, device=self.mu.device, dtype=self.mu.dtype, **moments,
+        )
+
     def _covariance(self, i: int, j: int) -> torch.Tensor:
         return self.cov[..., i, j]
 
