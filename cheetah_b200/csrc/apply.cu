@@ -16,6 +16,11 @@
 // row layout.  Two staging tiles overlap the bulk store of setting b with the math of b+1.
 // HBM traffic per (particle, setting): 28 B + 4 B written, the shared beam is read once per
 // CTA.  No tensor cores: K = 7 is far below any MMA tile.
+//
+// Kernels in this file: apply_maps_kernel (particles out, optionally with the fused moments /
+// covariance epilogue and the cavity tail), observe_maps_kernel (float32 observables only: the
+// same tiling on packed FFMA2 pairs, nothing written but 20 / 36 sums per setting) and
+// apply_maps_parameter_kernel (ParameterBeam: mu' = M mu, cov' = M cov M^T).
 #include <type_traits>
 
 #include "ch_common.cuh"
