@@ -86,6 +86,18 @@ SIGNATURES = {
             c_int32, c_int32, c_void_p,
         ],
     ),
+    "ch_apply_maps_compact": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_void_p, c_int64, c_void_p,
+            c_int64, c_int32, c_uint32,
+            c_int64, c_int64,
+            c_void_p, c_void_p, c_void_p,
+            c_int32, c_void_p,
+        ],
+    ),
     "ch_apply_maps_moments": (
         c_int32,
         [

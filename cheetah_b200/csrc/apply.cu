@@ -52,6 +52,10 @@ struct ApplyArgs {
   double* moments_out;  // [n_settings][CH_MOMENTS] survival-weighted sums (MOMENTS kernels)
   int32_t has_cavity;   // the record ends with a CH_RECORD_CAVITY block
   int32_t covariance;   // moments_out has CH_MOMENTS_COV entries per setting (full 6x6 sums)
+  // COMPACT kernels (ch_apply_maps_compact): particles_out holds 6 coordinates per row and
+  // the survival mask may be written as one byte per particle instead of a T
+  int32_t compact;
+  uint8_t* survival_u8;
 };
 
 template <typename T>
@@ -130,7 +134,7 @@ using Acc = T;
 // With MOMENTS the outgoing coordinates are also accumulated into `acc` (see the kernel) about
 // `pilot`, the image of the beam's first particle under the same map.
 template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE, int MOMENTS, bool WRITE,
-          bool CAVITY>
+          bool CAVITY, int ROW = 7>
 __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
                                                 uint32_t elliptical_mask, const T (&p)[P][7],
                                                 T (&sv)[P], T* stage, int tid,
@@ -206,7 +210,7 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
     // plain path (the headline kernel): rows go straight to the staging tile
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      T* row = stage + (tid + k * THREADS) * 7;
+      T* row = stage + (tid + k * THREADS) * ROW;
       if constexpr (SPARSE) {
         const T w = UNIT7 ? T(1) : p[k][6];
         auto constant = [&](int i) { return UNIT7 ? m[i * 7 + 6] : m[i * 7 + 6] * w; };
@@ -222,7 +226,7 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
 #pragma unroll
         for (int i = 0; i < 6; ++i) row[i] = affine_row<T, UNIT7>(m + i * 7, p[k]);
       }
-      row[6] = UNIT7 ? T(1) : p[k][6];
+      if constexpr (ROW == 7) row[6] = UNIT7 ? T(1) : p[k][6];
       if constexpr (CAVITY) {
         T r4 = row[4], r5;
         cavity_tail(p[k], r4, r5);
@@ -314,10 +318,15 @@ __device__ __forceinline__ A packed_warp_sum(A (&v)[32], int lane) {
   return v[0];
 }
 
-template <typename T, int P, int THREADS, bool UNIT7, int MOMENTS, bool WRITE, bool CAVITY>
+template <typename T, int P, int THREADS, bool UNIT7, int MOMENTS, bool WRITE, bool CAVITY,
+          bool COMPACT = false>
 __global__ void __launch_bounds__(THREADS, sizeof(T) == 4 ? (MOMENTS == 2 ? 2 : 3) : 1)
 apply_maps_kernel(const ApplyArgs<T> a) {
   constexpr int TP = P * THREADS;
+  // COMPACT (host-bound output, ch_apply_maps_compact): the seventh column is known to be 1 and
+  // is not written -- 24-byte rows -- and the survival mask can leave as one byte per particle
+  constexpr int ROW = COMPACT ? 6 : 7;
+  static_assert(!COMPACT || (UNIT7 && MOMENTS == 0 && WRITE), "compact output: plain path only");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* stage0 = reinterpret_cast<T*>(smem_raw);
   T* stage1 = stage0 + TP * 7;
@@ -426,7 +435,7 @@ apply_maps_kernel(const ApplyArgs<T> a) {
       loaded_particles = p_off;
       __syncthreads();  // everyone has its registers before the tile is overwritten
     }
-    if (a.survival_out != nullptr || MOMENTS) {
+    if (a.survival_out != nullptr || MOMENTS || (COMPACT && a.survival_u8 != nullptr)) {
       const int64_t s_off =
           (a.survival_index ? a.survival_index[b] : b) * a.survival_stride + n0;
       if (s_off != loaded_survival) {
@@ -465,11 +474,21 @@ apply_maps_kernel(const ApplyArgs<T> a) {
     const T* cavity =
         rec + CH_RECORD_HEADER + CH_RECORD_MAP + a.n_apertures * CH_RECORD_APERTURE;
     if ((flags & kSparse) == kSparse)
-      process_setting<T, P, THREADS, UNIT7, true, MOMENTS, WRITE, CAVITY>(
+      process_setting<T, P, THREADS, UNIT7, true, MOMENTS, WRITE, CAVITY, ROW>(
           rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc, cavity);
     else
-      process_setting<T, P, THREADS, UNIT7, false, MOMENTS, WRITE, CAVITY>(
+      process_setting<T, P, THREADS, UNIT7, false, MOMENTS, WRITE, CAVITY, ROW>(
           rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc, cavity);
+    if constexpr (COMPACT) {
+      if (a.survival_u8 != nullptr) {
+        uint8_t* dst = a.survival_u8 + b * a.n_particles + n0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const int local = tid + k * THREADS;
+          if (local < count) dst[local] = sv[k] != T(0) ? 1 : 0;
+        }
+      }
+    }
     if (a.survival_out != nullptr) {
       T* dst = a.survival_out + b * a.n_particles + n0;
 #pragma unroll
@@ -495,17 +514,17 @@ apply_maps_kernel(const ApplyArgs<T> a) {
 
     // ---- hand the finished tile to the TMA engine (or copy it out cooperatively) -------
     if (!WRITE) continue;  // observables only: nothing leaves the SM
-    T* out = a.particles_out + (b * a.n_particles + n0) * 7;
+    T* out = a.particles_out + (b * a.n_particles + n0) * ROW;
     if (a.bulk_out) {
       fence_async_shared();
       __syncthreads();
       if (tid == 0) {
-        bulk_store(out, stage, static_cast<uint32_t>(count) * 7u * sizeof(T));
+        bulk_store(out, stage, static_cast<uint32_t>(count) * ROW * sizeof(T));
         bulk_commit();
       }
     } else {
       __syncthreads();
-      for (int i = tid; i < count * 7; i += THREADS) out[i] = stage[i];
+      for (int i = tid; i < count * ROW; i += THREADS) out[i] = stage[i];
     }
   }
   if (MOMENTS && b_end > b_begin) {
@@ -928,8 +947,11 @@ int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t strea
     if (args.moments_out != nullptr) return with_cavity(unit, M1{}, std::true_type{});
     return with_cavity(unit, M0{}, std::true_type{});
   };
-  const int status =
-      unit_seventh ? with_outputs(std::true_type{}) : with_outputs(std::false_type{});
+  int status;
+  if (args.compact)
+    status = launch(apply_maps_kernel<T, P, THREADS, true, 0, true, false, true>);
+  else
+    status = unit_seventh ? with_outputs(std::true_type{}) : with_outputs(std::false_type{});
   if (status != CH_OK) return status;
   CH_LAUNCH_CHECK();
   return CH_OK;
@@ -942,8 +964,10 @@ int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t
                 int64_t record_len, int32_t n_apertures, uint32_t elliptical_mask,
                 int64_t n_particles, int64_t n_settings, void* particles_out, void* survival_out,
                 int32_t unit_seventh, double* moments_out, int32_t covariance,
-                cudaStream_t stream) {
+                cudaStream_t stream, uint8_t* survival_u8 = nullptr, bool compact = false) {
   ApplyArgs<T> a;
+  a.compact = compact ? 1 : 0;
+  a.survival_u8 = survival_u8;
   a.moments_out = moments_out;
   a.covariance = covariance;
   a.particles_in = static_cast<const T*>(particles_in);
@@ -965,14 +989,15 @@ int apply_typed(const void* particles_in, int64_t particle_stride, const int32_t
   a.elliptical_mask = elliptical_mask;
 
   // cp.async.bulk needs 16-byte aligned addresses and sizes for every tile
-  const size_t row_bytes = 7 * sizeof(T);
-  auto tiles_aligned = [&](const void* base, int64_t batch_stride_elems) {
+  auto tiles_aligned = [&](const void* base, int64_t batch_stride_elems, int row = 7) {
     return reinterpret_cast<uintptr_t>(base) % 16 == 0 &&
-           (static_cast<size_t>(n_particles) * row_bytes) % 16 == 0 &&
+           (static_cast<size_t>(n_particles) * row * sizeof(T)) % 16 == 0 &&
            (static_cast<size_t>(batch_stride_elems) * sizeof(T)) % 16 == 0;
   };
+  const int row_out = compact ? 6 : 7;
   a.bulk_in = tiles_aligned(particles_in, particle_stride) ? 1 : 0;
-  a.bulk_out = (particles_out != nullptr && tiles_aligned(particles_out, n_particles * 7)) ? 1 : 0;
+  a.bulk_out = (particles_out != nullptr &&
+                tiles_aligned(particles_out, n_particles * row_out, row_out)) ? 1 : 0;
 
   // settings per CTA: amortise the tile load over many settings but keep >= ~8 waves of CTAs
   constexpr int P = sizeof(T) == 4 ? 4 : 2;
@@ -1045,6 +1070,42 @@ extern "C" int ch_apply_maps(const void* particles_in, int64_t particle_stride,
                         survival_stride, survival_index, records, record_stride, record_index,
                         record_len, n_apertures, elliptical_mask, n_particles, n_settings,
                         particles_out, survival_out, dtype, unit_seventh, nullptr, 0, stream);
+}
+
+extern "C" int ch_apply_maps_compact(const void* particles_in, int64_t particle_stride,
+                                     const int32_t* particle_index, const void* survival_in,
+                                     int64_t survival_stride, const int32_t* survival_index,
+                                     const void* records, int64_t record_stride,
+                                     const int32_t* record_index, int64_t record_len,
+                                     int32_t n_apertures, uint32_t elliptical_mask,
+                                     int64_t n_particles, int64_t n_settings, void* coordinates_out,
+                                     void* survival_out, uint8_t* survival_mask_out, int32_t dtype,
+                                     void* stream) {
+  CH_REQUIRE(particles_in && records && coordinates_out,
+             "ch_apply_maps_compact: NULL pointer argument");
+  CH_REQUIRE(n_particles > 0 && n_settings > 0, "ch_apply_maps_compact: empty beam or batch");
+  CH_REQUIRE(n_apertures >= 0 && n_apertures <= CH_MAX_APERTURES,
+             "ch_apply_maps_compact: n_apertures %d outside [0, %d]", n_apertures,
+             CH_MAX_APERTURES);
+  CH_REQUIRE(record_len == CH_RECORD_LEN(n_apertures),
+             "ch_apply_maps_compact: record_len %lld does not match %d apertures (sections ending "
+             "in an active cavity are not supported)",
+             static_cast<long long>(record_len), n_apertures);
+  CH_REQUIRE(n_apertures == 0 || survival_out != nullptr || survival_mask_out != nullptr,
+             "ch_apply_maps_compact: a survival output is required when apertures are present");
+  CH_REQUIRE(dtype == CH_F32 || dtype == CH_F64, "ch_apply_maps_compact: bad dtype %d", dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == CH_F32)
+    return ch::apply_typed<float>(particles_in, particle_stride, particle_index, survival_in,
+                                  survival_stride, survival_index, records, record_stride,
+                                  record_index, record_len, n_apertures, elliptical_mask,
+                                  n_particles, n_settings, coordinates_out, survival_out, 1,
+                                  nullptr, 0, s, survival_mask_out, true);
+  return ch::apply_typed<double>(particles_in, particle_stride, particle_index, survival_in,
+                                 survival_stride, survival_index, records, record_stride,
+                                 record_index, record_len, n_apertures, elliptical_mask,
+                                 n_particles, n_settings, coordinates_out, survival_out, 1,
+                                 nullptr, 0, s, survival_mask_out, true);
 }
 
 extern "C" int ch_apply_maps_moments(const void* particles_in, int64_t particle_stride,

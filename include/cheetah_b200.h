@@ -189,6 +189,23 @@ int ch_apply_maps(const void* particles_in, int64_t particle_stride, const int32
                   void* particles_out, void* survival_out,
                   int32_t dtype, int32_t unit_seventh, void* stream);
 
+/* ch_apply_maps for results that are about to cross PCIe (the host-buffer path, host.py): the
+ * seventh phase-space column is the constant 1 of cheetah/particles/particle_beam.py:60-106 and is
+ * not written -- coordinates_out is [n_settings][n_particles][6] (24 instead of 28 bytes per row
+ * for float32) -- and the survival probabilities can leave as a byte mask
+ * survival_mask_out[n_settings][n_particles] in {0, 1} (exact whenever survival_in is NULL or holds
+ * only zeros and ones, as after any chain of Aperture.track calls on a fresh beam,
+ * aperture.py:108-132) instead of / next to survival_out in the beam dtype: 25 B per (particle,
+ * setting) instead of 32.  Requires particles_in[..., 6] == 1 and a section without a cavity tail;
+ * either survival output may be NULL. */
+int ch_apply_maps_compact(const void* particles_in, int64_t particle_stride, const int32_t* particle_index,
+                          const void* survival_in, int64_t survival_stride, const int32_t* survival_index,
+                          const void* records, int64_t record_stride, const int32_t* record_index,
+                          int64_t record_len, int32_t n_apertures, uint32_t elliptical_mask,
+                          int64_t n_particles, int64_t n_settings,
+                          void* coordinates_out, void* survival_out, uint8_t* survival_mask_out,
+                          int32_t dtype, void* stream);
+
 /* ParameterBeam tracking through one linear section (cheetah/accelerator/element.py:166-179):
  *   mu_out[b] = M_b mu_in[midx(b)],  cov_out[b] = M_b cov_in[midx(b)] M_b^T
  * with M_b the 7x7 map of records[ridx(b)] (products accumulated in fp64); mu [..][7],

@@ -73,6 +73,37 @@ def ares_config3(n_settings: int, dtype=torch.float32, begin: int = 0, end: int 
     return lattice
 
 
+def ares_config3_dense(n_settings: int, dtype=torch.float32, begin: int = 0,
+                       end: int | None = None) -> list:
+    """Config 3 with x-y coupling: both gun solenoids powered (k = 0.5 / -0.4 1/m) and the
+    quadrupole AREAMQZM2 tilted by 0.3 rad, so that none of the sparsity flags of the apply kernel
+    holds and every setting takes its generic 72-multiply-add branch (solenoid.py:74-116,
+    track_methods.py:345-382)."""
+    lattice = ares_config3(n_settings, dtype, begin, end)
+    _set(lattice, "ARLIMSOG1A", "k", torch.tensor(0.5, dtype=dtype))
+    _set(lattice, "ARLIMSOG1B", "k", torch.tensor(-0.4, dtype=dtype))
+    _set(lattice, "AREAMQZM2", "tilt", torch.tensor(0.3, dtype=dtype))
+    return lattice
+
+
+def ares_survey_ranges(n_settings: int, dtype=torch.float32, x_max: float = 0.5) -> list:
+    """The ranges SURVEY 8d first proposed -- k1 ~ U(-30, 30) 1/m^2, corrector angles ~
+    U(-1e-3, 1e-3) rad, seed 1 -- with the two apertures opened to `x_max` instead of narrowing
+    the ranges: strongly over-focused settings with large map entries (a parity case, not the
+    bench workload)."""
+    lattice = lattice_description.load(GOLDEN / "ares_lattice.json", dtype)
+    g = torch.Generator().manual_seed(1)
+    for element in lattice:
+        if element["type"] == "Quadrupole":
+            element["k1"] = ((torch.rand(n_settings, generator=g) * 2 - 1) * 30.0).to(dtype)
+        elif element["type"] in ("HorizontalCorrector", "VerticalCorrector"):
+            element["angle"] = ((torch.rand(n_settings, generator=g) * 2 - 1) * 1e-3).to(dtype)
+    for name in ("ARLISLHG1", "ARBCSLHB1"):
+        _set(lattice, name, "x_max", torch.tensor(x_max, dtype=dtype))
+        _set(lattice, name, "y_max", torch.tensor(x_max, dtype=dtype))
+    return lattice
+
+
 def twiss_beam_particles(num_particles: int, seed: int = 0) -> torch.Tensor:
     """(N, 7) float64 particles of the README beam (beta_x 3.14, beta_y 42, defaults of
     particle_beam.py:464-504), generated on the CPU so that every rank and the CPU baseline
