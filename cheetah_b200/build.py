@@ -31,6 +31,19 @@ def _object(src: Path) -> Path:
     return OBJECTS / (src.stem + ".o")
 
 
+def _includes(path: Path, seen: set | None = None) -> list[Path]:
+    """Headers of this repository that ``path`` includes, transitively (quoted includes only)."""
+    import re
+
+    seen = set() if seen is None else seen
+    for name in re.findall(r'^\s*#include\s+"([^"]+)"', path.read_text(), flags=re.M):
+        for candidate in (path.parent / name, ROOT.parent / "include" / name):
+            if candidate.exists() and candidate not in seen:
+                seen.add(candidate)
+                _includes(candidate, seen)
+    return sorted(seen)
+
+
 def _stale(target: Path, deps: list[Path]) -> bool:
     if not target.exists():
         return True
@@ -56,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return OUTPUT
     OBJECTS.mkdir(parents=True, exist_ok=True)
     todo = [src for src in SOURCES
-            if force or _stale(_object(src), [src, *HEADERS, Path(__file__)])]
+            if force or _stale(_object(src), [src, *_includes(src), Path(__file__)])]
     with ThreadPoolExecutor(max_workers=min(len(todo) or 1, os.cpu_count() or 1)) as pool:
         logs = list(pool.map(lambda src: _compile(src, verbose), todo))
     if verbose:

@@ -12,9 +12,11 @@
 // fire-and-forget RED atomics (N/cells is ~4: privatising tiles would cost more than the
 // atomics they save); the 3-D convolution is three shared-memory FFT passes.
 #include <cstdlib>
+#include <type_traits>
 
 #include "ch_common.cuh"
 #include "fft.cuh"
+#include "fft_regs.cuh"
 
 namespace ch {
 namespace {
@@ -367,7 +369,50 @@ cic_deposit_low_kernel(const T* __restrict__ positions, const T* __restrict__ ex
 // ---------------------------------------------------------------------------------------
 // 4. integrated Green function
 // ---------------------------------------------------------------------------------------
-// Antiderivative of 1/r (space_charge_kick.py:103-123), fp64.
+// Antiderivative F of 1/r (space_charge_kick.py:103-123), fp64, in a form that costs a quarter of
+// the reference's expression (3 atan + 3 asinh + 4 sqrt, ~970 fp64 instructions per point):
+//   * the Green function is the 8-corner signed difference of F over a cell (:195-236), which
+//     annihilates every term that does not depend on all three coordinates.  With
+//     asinh(x / rho) = log(x + r) - log(rho) the three rho terms are such terms, and so is the
+//     (pi/4) x^2 left over when the third arctangent is replaced through
+//     atan(xy/(tr)) + atan(xt/(yr)) + atan(yt/(xr)) = pi/2  (x, y, t > 0).  What remains is
+//       F^ = (x^2 - t^2)/2 atan(xy/(tr)) + (x^2 - y^2)/2 atan(xt/(yr))
+//            + y t log(x + r) + x t log(y + r) + x y log(t + r):
+//     one sqrt, one division, two atan, three log.
+//   * F is odd in each coordinate and the lattice point with index 0 sits at -1/2 cell.  The
+//     dropped terms D = d1(y,t) + d2(x,t) + d3(x,y) + d4(x) keep cancelling across that plane only
+//     if they are continued as functions of their own arguments, so lattice = F - D with the true
+//     odd F gives, with s = sx sy st, the corrections (s - sy st) d1 + ... + (s - 1) d4 on the
+//     index-0 planes (O(n^2) points).
+//   * coordinates are taken in units of the grid diagonal R: the dropped logarithms then vanish
+//     where the differences cancel most (far cells), and the rounding error of the differences
+//     stays at the level of the reference's own fp64 expression (2e-9 of a far-corner value at
+//     64^3, measured against 80-bit arithmetic; 8e-10 for the reference form).
+// lattice[i][j][k] = R^2 F^(|i - 1/2| cx, |j - 1/2| cy, |k - 1/2| ct) (+ corrections), c = cell / R.
+__device__ __forceinline__ double igf_lattice_value(int i, int j, int k, double cx, double cy,
+                                                    double ct) {
+  const double x = fabs(i - 0.5) * cx, y = fabs(j - 0.5) * cy, t = fabs(k - 0.5) * ct;
+  const double x2 = x * x, y2 = y * y, t2 = t * t;
+  const double r = sqrt(x2 + y2 + t2);
+  const double inv = 1.0 / (y * t * r);
+  const double a1 = atan(x * y2 * inv);  // atan(x y / (t r))
+  const double a2 = atan(x * t2 * inv);  // atan(x t / (y r))
+  double f = 0.5 * (x2 - t2) * a1 + 0.5 * (x2 - y2) * a2 + y * t * log(x + r) +
+             x * t * log(y + r) + x * y * log(t + r);
+  if (i == 0 || j == 0 || k == 0) {
+    const double sx = i == 0 ? -1.0 : 1.0, sy = j == 0 ? -1.0 : 1.0, st = k == 0 ? -1.0 : 1.0;
+    const double s = sx * sy * st;
+    f *= s;
+    if (i == 0) f += sy * st * y * t * log(y2 + t2);  // (s - sy st) d1, d1 = -1/2 y t log(y2 + t2)
+    if (j == 0) f += sx * st * x * t * log(x2 + t2);
+    if (k == 0) f += sx * sy * x * y * log(x2 + y2);
+    f -= (s - 1.0) * (0.25 * kPi) * x2;               // (s - 1) d4, d4 = -(pi/4) x^2
+  }
+  return f;
+}
+
+// The reference's expression, kept for the parity tests of the new form (ch_sc_green_function
+// with CH_GREEN_REFERENCE_FORM=1 in the environment).
 __device__ __forceinline__ double igf_antiderivative(double x, double y, double t) {
   const double r = sqrt(x * x + y * y + t * t);
   return -0.5 * t * t * atan(x * y / (t * r)) - 0.5 * y * y * atan(x * t / (y * r)) -
@@ -375,13 +420,19 @@ __device__ __forceinline__ double igf_antiderivative(double x, double y, double 
          x * t * asinh(y / sqrt(x * x + t * t)) + x * y * asinh(t / sqrt(x * x + y * y));
 }
 
-// lattice[i][j][k] = F((i - 1/2) dx, (j - 1/2) dy, (k - 1/2) dt), 0 <= i <= nx, ...
+// lattice[i][j][k] = F((i - 1/2) dx, (j - 1/2) dy, (k - 1/2) dt), 0 <= i <= nx, ...  (up to terms
+// the 8-corner difference annihilates, see above)
+template <bool REFERENCE_FORM>
 __global__ void __launch_bounds__(256)
 sc_green_lattice_kernel(const double* __restrict__ params, int nx, int ny, int nz,
                         double* __restrict__ lattice) {
   const int64_t b = blockIdx.y;
   const double* prm = params + b * CH_SC_PARAMS;
   const double dx = prm[3], dy = prm[4], dt = prm[5] * prm[6];  // only d_tau is scaled by gamma
+  const double ex = nx * dx, ey = ny * dy, et = nz * dt;
+  const double diagonal2 = ex * ex + ey * ey + et * et;
+  const double inv_diagonal = rsqrt(diagonal2);
+  const double cx = dx * inv_diagonal, cy = dy * inv_diagonal, ct = dt * inv_diagonal;
   const int64_t total = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
   double* out = lattice + b * total;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -389,7 +440,10 @@ sc_green_lattice_kernel(const double* __restrict__ params, int nx, int ny, int n
     const int k = static_cast<int>(idx % (nz + 1));
     const int j = static_cast<int>((idx / (nz + 1)) % (ny + 1));
     const int i = static_cast<int>(idx / (static_cast<int64_t>(nz + 1) * (ny + 1)));
-    out[idx] = igf_antiderivative((i - 0.5) * dx, (j - 0.5) * dy, (k - 0.5) * dt);
+    if (REFERENCE_FORM)
+      out[idx] = igf_antiderivative((i - 0.5) * dx, (j - 0.5) * dy, (k - 0.5) * dt);
+    else
+      out[idx] = diagonal2 * igf_lattice_value(i, j, k, cx, cy, ct);
   }
 }
 
@@ -680,6 +734,265 @@ fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, in
     const int col = c0 + c;
     const int outer = col / inner_count, inner = col - outer * inner_count;
     const C z = v[(c >> 1) * pitch + fft::bit_reverse(k, log2_len)];
+    dst[outer * out_outer_stride + inner + k * out_axis_stride] = (c & 1) ? z.y : z.x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 5b. the same passes on the register-resident FFT core (fft_regs.cuh): float, lengths 32 .. 256
+// ---------------------------------------------------------------------------------------
+// Thread layout of every kernel: 16 columns (or packed row pairs) x N2 = LEN / 16 threads, the
+// column index in the low four bits of threadIdx.x -- so the 16 lanes of a half-warp touch 16
+// adjacent columns in global memory (128 contiguous bytes) and 16 different banks of the
+// exchange buffer (odd column pitch).
+using fftr::C;
+
+template <int LEN>
+struct FftrShared {
+  C exchange[16 * fftr::Plan<LEN>::PITCH];
+  C twiddles[LEN];
+};
+
+// Strided complex pass (MODE as in fft_strided_kernel): columns go global -> registers ->
+// global; the only shared-memory traffic is the one exchange inside each transform.
+template <int LEN, int MODE>
+__global__ void __launch_bounds__(16 * fftr::Plan<LEN>::N2)
+fftr_strided_kernel(C* __restrict__ data, const float* __restrict__ green, int green_ny,
+                    int green_kz, int in_len, int out_len, int64_t axis_stride, int inner_count,
+                    int64_t outer_stride, int64_t batch_stride) {
+  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH;
+  __shared__ FftrShared<LEN> sh;
+  const int c = threadIdx.x & 15, n2 = threadIdx.x >> 4;
+  const int inner = blockIdx.x * 16 + c;
+  const bool live = inner < inner_count;
+  C* col = data + blockIdx.z * batch_stride + blockIdx.y * outer_stride + inner;
+  fftr::fill_twiddles<LEN>(sh.twiddles);
+  C v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const int n = N2 * n1 + n2;
+    v[n1] = (live && n < in_len) ? col[n * axis_stride] : C{0.0f, 0.0f};
+  }
+  __syncthreads();
+  C* column = sh.exchange + c * PITCH;
+  if (MODE == 0 || MODE == 2) fftr::transform<LEN, false>(v, column, n2, sh.twiddles);
+  if (MODE == 2) {
+    // the spectrum of the mirrored Green array is real and even in every index: compact storage
+    const int64_t plane = static_cast<int64_t>(green_ny) * green_kz;
+    const float* g0 = green + blockIdx.z * (LEN / 2 + 1) * plane;
+    const int full_ny = 2 * (green_ny - 1);
+    const int ky = live ? inner / green_kz : 0, kz = live ? inner - ky * green_kz : 0;
+    const int ky_even = ky <= full_ny / 2 ? ky : full_ny - ky;
+    const float* g1 = g0 + ky_even * green_kz + kz;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int kx = n2 + N2 * j;
+      const int kx_even = kx <= LEN / 2 ? kx : LEN - kx;
+      const float g = g1[kx_even * plane];
+      v[j].x *= g;
+      v[j].y *= g;
+    }
+    __syncthreads();  // every gather of the forward transform is done: the buffer is free
+  }
+  if (MODE == 1 || MODE == 2) fftr::transform<LEN, true>(v, column, n2, sh.twiddles);
+  const int n_store = (MODE == 0) ? LEN : out_len;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int k = n2 + N2 * j;
+    if (live && k < n_store) col[k * axis_stride] = v[j];
+  }
+}
+
+// z pass, real -> complex: 16 packed row pairs per CTA (semantics of fft_r2c_z_kernel).
+template <int LEN>
+__global__ void __launch_bounds__(16 * fftr::Plan<LEN>::N2)
+fftr_r2c_z_kernel(const float* __restrict__ in, int in_x, int in_y, int in_z, int in_pitch, int quad,
+                  int out_nx, int out_ny, C* __restrict__ out) {
+  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH, THREADS = 16 * N2;
+  __shared__ FftrShared<LEN> sh;
+  const int p = threadIdx.x & 15, n2 = threadIdx.x >> 4;
+  const int64_t b = blockIdx.y;
+  const int rows = in_x * in_y;
+  constexpr int kz = LEN / 2 + 1;
+  const int first_row = blockIdx.x * 32;
+  const int qy = in_y / 2 + 1, qz = in_z / 2 + 1;
+  const int64_t plane = static_cast<int64_t>(4) * qy * qz * 4;
+  const float* src = in + b * (quad ? in_x * plane : static_cast<int64_t>(rows) * in_pitch);
+  C* dst = out + b * static_cast<int64_t>(out_nx) * out_ny * kz;
+
+  fftr::fill_twiddles<LEN>(sh.twiddles);
+  // stage the 32 rows with the z index running over the lanes (contiguous global reads)
+  for (int t = threadIdx.x; t < 16 * in_z; t += THREADS) {
+    const int pair = t / in_z, i = t - pair * in_z;
+    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
+    C value{0.0f, 0.0f};
+    if (r0 < rows)
+      value.x = quad ? quad_value(src + (r0 / in_y) * plane, r0 % in_y, i, qy, qz)
+                     : src[static_cast<int64_t>(r0) * in_pitch + i];
+    if (r1 < rows)
+      value.y = quad ? quad_value(src + (r1 / in_y) * plane, r1 % in_y, i, qy, qz)
+                     : src[static_cast<int64_t>(r1) * in_pitch + i];
+    sh.exchange[pair * PITCH + i] = value;
+  }
+  __syncthreads();
+  C* column = sh.exchange + p * PITCH;
+  C v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const int n = N2 * n1 + n2;
+    v[n1] = n < in_z ? column[n] : C{0.0f, 0.0f};
+  }
+  __syncthreads();
+  fftr::transform<LEN, false>(v, column, n2, sh.twiddles);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) column[n2 + N2 * j] = v[j];
+  __syncthreads();
+  // separate the two real rows: A = (Z[k] + conj Z[-k]) / 2, B = (Z[k] - conj Z[-k]) / (2i)
+  for (int t = threadIdx.x; t < 16 * kz; t += THREADS) {
+    const int pair = t / kz, k = t - pair * kz;
+    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
+    if (r0 >= rows) continue;
+    const C zk = sh.exchange[pair * PITCH + k];
+    const C zm = sh.exchange[pair * PITCH + ((LEN - k) & (LEN - 1))];
+    const C a{0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)};
+    const C bb{0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x)};
+    const int x0 = r0 / in_y, y0 = r0 - x0 * in_y;
+    dst[(static_cast<int64_t>(x0) * out_ny + y0) * kz + k] = a;
+    if (r1 < rows) {
+      const int x1 = r1 / in_y, y1 = r1 - x1 * in_y;
+      dst[(static_cast<int64_t>(x1) * out_ny + y1) * kz + k] = bb;
+    }
+  }
+}
+
+// z pass, complex -> real (semantics of fft_c2r_z_kernel).
+template <int LEN>
+__global__ void __launch_bounds__(16 * fftr::Plan<LEN>::N2)
+fftr_c2r_z_kernel(const C* __restrict__ in, int in_nx, int in_ny, int out_x, int out_y, int out_z,
+                  const double* __restrict__ params, double norm, float* __restrict__ out) {
+  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH, THREADS = 16 * N2;
+  __shared__ FftrShared<LEN> sh;
+  const int p = threadIdx.x & 15, n2 = threadIdx.x >> 4;
+  const int64_t b = blockIdx.y;
+  const int rows = out_x * out_y;
+  constexpr int kz = LEN / 2 + 1;
+  const int first_row = blockIdx.x * 32;
+  const C* src = in + b * static_cast<int64_t>(in_nx) * in_ny * kz;
+  float* dst = out + b * static_cast<int64_t>(rows) * out_z;
+  const float scale = static_cast<float>(params[b * CH_SC_PARAMS + 9] * norm);
+
+  fftr::fill_twiddles<LEN>(sh.twiddles);
+  for (int t = threadIdx.x; t < 16 * kz; t += THREADS) {
+    const int pair = t / kz, k = t - pair * kz;
+    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
+    C a{0.0f, 0.0f}, bb{0.0f, 0.0f};
+    if (r0 < rows) {
+      const int x0 = r0 / out_y, y0 = r0 - x0 * out_y;
+      a = src[(static_cast<int64_t>(x0) * in_ny + y0) * kz + k];
+    }
+    if (r1 < rows) {
+      const int x1 = r1 / out_y, y1 = r1 - x1 * out_y;
+      bb = src[(static_cast<int64_t>(x1) * in_ny + y1) * kz + k];
+    }
+    if (k == 0 || k == LEN / 2) a.y = bb.y = 0.0f;  // c2r ignores Im of DC / Nyquist
+    // Z = A + i B; the upper half from the Hermitian symmetry of A and B
+    sh.exchange[pair * PITCH + k] = C{a.x - bb.y, a.y + bb.x};
+    if (k > 0 && k < LEN / 2) sh.exchange[pair * PITCH + LEN - k] = C{a.x + bb.y, bb.x - a.y};
+  }
+  __syncthreads();
+  C* column = sh.exchange + p * PITCH;
+  C v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = column[N2 * n1 + n2];
+  __syncthreads();
+  fftr::transform<LEN, true>(v, column, n2, sh.twiddles);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) column[n2 + N2 * j] = v[j];
+  __syncthreads();
+  for (int t = threadIdx.x; t < 16 * out_z; t += THREADS) {
+    const int pair = t / out_z, i = t - pair * out_z;
+    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
+    const C z = sh.exchange[pair * PITCH + i];
+    if (r0 < rows) dst[static_cast<int64_t>(r0) * out_z + i] = z.x * scale;
+    if (r1 < rows) dst[static_cast<int64_t>(r1) * out_z + i] = z.y * scale;
+  }
+}
+
+// Real-even pass of the Green function (semantics of fft_even_pass_kernel): 32 columns = 16
+// packed pairs per CTA; the column g[0..n) stands for g[0..n), 0 ..., g[n-1..1] of length LEN.
+template <int LEN, bool FROM_LATTICE>
+__global__ void __launch_bounds__(16 * fftr::Plan<LEN>::N2)
+fftr_even_pass_kernel(const void* __restrict__ in, float* __restrict__ out, int n,
+                      int total_columns, int inner_count, int64_t in_outer_stride,
+                      int64_t in_axis_stride, int64_t in_batch_stride, int64_t out_outer_stride,
+                      int64_t out_axis_stride, int64_t out_batch_stride, int lattice_ny,
+                      int lattice_nz) {
+  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH, THREADS = 16 * N2;
+  constexpr int kCols = 32;
+  __shared__ FftrShared<LEN> sh;
+  const int p = threadIdx.x & 15, n2 = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * kCols;
+  const int columns = min(kCols, total_columns - c0);
+  const bool axis_contiguous = in_axis_stride == 1;
+
+  fftr::fill_twiddles<LEN>(sh.twiddles);
+  // positions n .. LEN - n stay zero (plane n of the reference's doubled array, and the padding
+  // when LEN exceeds 2 n)
+  for (int t = threadIdx.x; t < 16 * (LEN - 2 * n + 1); t += THREADS) {
+    const int pair = t / (LEN - 2 * n + 1), i = n + (t - pair * (LEN - 2 * n + 1));
+    sh.exchange[pair * PITCH + i] = C{0.0f, 0.0f};
+  }
+  for (int t = threadIdx.x; t < kCols * n; t += THREADS) {
+    // fastest index follows the contiguous direction of the input
+    const int c = axis_contiguous ? t / n : t % kCols;
+    const int i = axis_contiguous ? t - c * n : t / kCols;
+    float value = 0.0f;
+    if (c < columns) {
+      const int col = c0 + c;
+      const int outer = col / inner_count, inner = col - outer * inner_count;
+      if (FROM_LATTICE) {
+        const double* f = static_cast<const double*>(in) + blockIdx.y * in_batch_stride;
+        const int x = outer / lattice_ny, y = outer - x * lattice_ny;
+        const int sy = lattice_nz + 1, sx = (lattice_ny + 1) * (lattice_nz + 1);
+        const double* q = f + static_cast<int64_t>(x) * sx + y * sy + i;
+        value = static_cast<float>(q[sx + sy + 1] - q[sy + 1] - q[sx + 1] - q[sx + sy] + q[sx] +
+                                   q[sy] + q[1] - q[0]);
+      } else {
+        const float* src = static_cast<const float*>(in) + blockIdx.y * in_batch_stride;
+        value = src[outer * in_outer_stride + inner + i * in_axis_stride];
+      }
+    }
+    C* column = sh.exchange + (c >> 1) * PITCH;
+    if (c & 1) {
+      column[i].y = value;
+      if (i > 0) column[LEN - i].y = value;
+    } else {
+      column[i].x = value;
+      if (i > 0) column[LEN - i].x = value;
+    }
+  }
+  __syncthreads();
+  C* column = sh.exchange + p * PITCH;
+  C v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = column[N2 * n1 + n2];
+  __syncthreads();
+  fftr::transform<LEN, false>(v, column, n2, sh.twiddles);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) column[n2 + N2 * j] = v[j];
+  __syncthreads();
+  float* dst = out + blockIdx.y * out_batch_stride;
+  constexpr int n_out = LEN / 2 + 1;
+  for (int t = threadIdx.x; t < kCols * n_out; t += THREADS) {
+    const int c = axis_contiguous ? t / n_out : t % kCols;
+    const int k = axis_contiguous ? t - c * n_out : t / kCols;
+    if (c >= columns) continue;
+    const int col = c0 + c;
+    const int outer = col / inner_count, inner = col - outer * inner_count;
+    const C z = sh.exchange[(c >> 1) * PITCH + k];
     dst[outer * out_outer_stride + inner + k * out_axis_stride] = (c & 1) ? z.y : z.x;
   }
 }
@@ -1033,6 +1346,28 @@ unsigned blocks_for(int64_t work, int threads, int64_t cap = 148 * 16) {
 
 // Compact Green spectrum [B][nx+1][ny+1][nz+1] from the antiderivative lattice: three even
 // passes through two scratch arrays s1 [B][nx][ny][nz+1], s2 [B][nx][ny+1][nz+1].
+// LEN -> std::integral_constant for the register-FFT kernels; false when LEN is not covered
+template <typename F>
+bool fftr_dispatch(int len, F&& f) {
+  switch (len) {
+    case 32: f(std::integral_constant<int, 32>{}); return true;
+    case 64: f(std::integral_constant<int, 64>{}); return true;
+    case 128: f(std::integral_constant<int, 128>{}); return true;
+    case 256: f(std::integral_constant<int, 256>{}); return true;
+    default: return false;
+  }
+}
+bool fftr_covers(int len) { return len == 32 || len == 64 || len == 128 || len == 256; }
+bool fftr_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("CH_FFT_SHARED_ONLY");  // test knob: force the fft.cuh passes
+    return !(v != nullptr && atoi(v) != 0);
+  }();
+  return on;
+}
+
+// Compact Green spectrum [B][nx+1][ny+1][nz+1] from the antiderivative lattice: three even
+// passes through two scratch arrays s1 [B][nx][ny][nz+1], s2 [B][nx][ny+1][nz+1].
 template <typename T>
 int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* s1, T* s2,
                    T* spectrum, cudaStream_t stream) {
@@ -1041,36 +1376,76 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
   const unsigned nb = static_cast<unsigned>(B);
   auto smem = [&](int len) { return sizeof(C) * ((kColumns / 2) * (len + 2) + len / 2); };
   const int64_t lattice_points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
+  constexpr bool kFloat = std::is_same<T, float>::value;
+  const bool regs = kFloat && fftr_enabled() && fftr_covers(2 * nx) && fftr_covers(2 * ny) &&
+                    fftr_covers(2 * nz);
   {  // z: rows (x, y) of the lattice difference -> s1[x][y][kz]
-    auto k = fft_even_pass_kernel<T, true>;
-    if (allow_smem(k, smem(2 * nz)) != CH_OK) return CH_ECUDA;
     const int columns = nx * ny;
-    dim3 grid((columns + kColumns - 1) / kColumns, nb);
-    k<<<grid, kFftThreads, smem(2 * nz), stream>>>(
-        lattice, s1, nz, 2 * nz, log2_exact(2 * nz), columns, 1, 0, 1, lattice_points, Kz, 1,
-        static_cast<int64_t>(nx) * ny * Kz, ny, nz);
+    if (regs) {
+      if constexpr (kFloat) {
+        fftr_dispatch(2 * nz, [&](auto L) {
+          constexpr int LEN = decltype(L)::value;
+          dim3 grid((columns + 31) / 32, nb);
+          fftr_even_pass_kernel<LEN, true><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
+              lattice, s1, nz, columns, 1, 0, 1, lattice_points, Kz, 1,
+              static_cast<int64_t>(nx) * ny * Kz, ny, nz);
+        });
+      }
+    } else {
+      auto k = fft_even_pass_kernel<T, true>;
+      if (allow_smem(k, smem(2 * nz)) != CH_OK) return CH_ECUDA;
+      dim3 grid((columns + kColumns - 1) / kColumns, nb);
+      k<<<grid, kFftThreads, smem(2 * nz), stream>>>(
+          lattice, s1, nz, 2 * nz, log2_exact(2 * nz), columns, 1, 0, 1, lattice_points, Kz, 1,
+          static_cast<int64_t>(nx) * ny * Kz, ny, nz);
+    }
     CH_LAUNCH_CHECK();
   }
   {  // y: columns (x, kz) -> s2[x][ky][kz]
-    auto k = fft_even_pass_kernel<T, false>;
-    if (allow_smem(k, smem(2 * ny)) != CH_OK) return CH_ECUDA;
     const int columns = nx * Kz;
-    dim3 grid((columns + kColumns - 1) / kColumns, nb);
-    k<<<grid, kFftThreads, smem(2 * ny), stream>>>(
-        s1, s2, ny, 2 * ny, log2_exact(2 * ny), columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
-        static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
-        static_cast<int64_t>(nx) * (ny + 1) * Kz, 0, 0);
+    if (regs) {
+      if constexpr (kFloat) {
+        fftr_dispatch(2 * ny, [&](auto L) {
+          constexpr int LEN = decltype(L)::value;
+          dim3 grid((columns + 31) / 32, nb);
+          fftr_even_pass_kernel<LEN, false><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
+              s1, s2, ny, columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
+              static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
+              static_cast<int64_t>(nx) * (ny + 1) * Kz, 0, 0);
+        });
+      }
+    } else {
+      auto k = fft_even_pass_kernel<T, false>;
+      if (allow_smem(k, smem(2 * ny)) != CH_OK) return CH_ECUDA;
+      dim3 grid((columns + kColumns - 1) / kColumns, nb);
+      k<<<grid, kFftThreads, smem(2 * ny), stream>>>(
+          s1, s2, ny, 2 * ny, log2_exact(2 * ny), columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
+          static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
+          static_cast<int64_t>(nx) * (ny + 1) * Kz, 0, 0);
+    }
     CH_LAUNCH_CHECK();
   }
   {  // x: columns (ky, kz) -> spectrum[kx][ky][kz]
-    auto k = fft_even_pass_kernel<T, false>;
-    if (allow_smem(k, smem(2 * nx)) != CH_OK) return CH_ECUDA;
     const int columns = (ny + 1) * Kz;
-    dim3 grid((columns + kColumns - 1) / kColumns, nb);
-    k<<<grid, kFftThreads, smem(2 * nx), stream>>>(
-        s2, spectrum, nx, 2 * nx, log2_exact(2 * nx), columns, columns, 0, columns,
-        static_cast<int64_t>(nx) * columns, 0, columns, static_cast<int64_t>(nx + 1) * columns, 0,
-        0);
+    if (regs) {
+      if constexpr (kFloat) {
+        fftr_dispatch(2 * nx, [&](auto L) {
+          constexpr int LEN = decltype(L)::value;
+          dim3 grid((columns + 31) / 32, nb);
+          fftr_even_pass_kernel<LEN, false><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
+              s2, spectrum, nx, columns, columns, 0, columns, static_cast<int64_t>(nx) * columns,
+              0, columns, static_cast<int64_t>(nx + 1) * columns, 0, 0);
+        });
+      }
+    } else {
+      auto k = fft_even_pass_kernel<T, false>;
+      if (allow_smem(k, smem(2 * nx)) != CH_OK) return CH_ECUDA;
+      dim3 grid((columns + kColumns - 1) / kColumns, nb);
+      k<<<grid, kFftThreads, smem(2 * nx), stream>>>(
+          s2, spectrum, nx, 2 * nx, log2_exact(2 * nx), columns, columns, 0, columns,
+          static_cast<int64_t>(nx) * columns, 0, columns, static_cast<int64_t>(nx + 1) * columns, 0,
+          0);
+    }
     CH_LAUNCH_CHECK();
   }
   return CH_OK;
@@ -1087,6 +1462,50 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
   auto z_smem = [&](int len) { return sizeof(C) * (kRowPairs * (len + 2) + len / 2); };
   auto s_smem = [&](int len) { return sizeof(C) * (kColumns * (len + 1) + len / 2); };
   const unsigned nb = static_cast<unsigned>(B);
+  const double norm = 1.0 / (4.0 * kPi * kEpsilon0) / (static_cast<double>(Nx) * Ny * Nz);
+  constexpr bool kFloat = std::is_same<T, float>::value;
+  if constexpr (kFloat) {
+    if (fftr_enabled() && fftr_covers(Nx) && fftr_covers(Ny) && fftr_covers(Nz)) {
+      // ---- register-FFT passes: rho z, y; fused x convolution; inverse y, z ----------------
+      fftr_dispatch(Nz, [&](auto L) {
+        constexpr int LEN = decltype(L)::value;
+        dim3 grid((nx * ny + 31) / 32, nb);
+        fftr_r2c_z_kernel<LEN><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(rho, nx, ny, nz, 0,
+                                                                               1, Nx, Ny, rs);
+      });
+      CH_LAUNCH_CHECK();
+      fftr_dispatch(Ny, [&](auto L) {
+        constexpr int LEN = decltype(L)::value;
+        dim3 grid((Kz + 15) / 16, nx, nb);
+        fftr_strided_kernel<LEN, 0><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
+            rs, nullptr, 0, 0, ny, Ny, Kz, Kz, static_cast<int64_t>(Ny) * Kz, spectrum);
+      });
+      CH_LAUNCH_CHECK();
+      fftr_dispatch(Nx, [&](auto L) {
+        constexpr int LEN = decltype(L)::value;
+        const int inner = Ny * Kz;
+        dim3 grid((inner + 15) / 16, 1, nb);
+        fftr_strided_kernel<LEN, 2><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
+            rs, green_spectrum_compact, ny + 1, Kz, nx, nx, inner, inner, 0, spectrum);
+      });
+      CH_LAUNCH_CHECK();
+      fftr_dispatch(Ny, [&](auto L) {
+        constexpr int LEN = decltype(L)::value;
+        dim3 grid((Kz + 15) / 16, nx, nb);
+        fftr_strided_kernel<LEN, 1><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
+            rs, nullptr, 0, 0, Ny, ny, Kz, Kz, static_cast<int64_t>(Ny) * Kz, spectrum);
+      });
+      CH_LAUNCH_CHECK();
+      fftr_dispatch(Nz, [&](auto L) {
+        constexpr int LEN = decltype(L)::value;
+        dim3 grid((nx * ny + 31) / 32, nb);
+        fftr_c2r_z_kernel<LEN><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
+            rs, Nx, Ny, nx, ny, nz, params, norm, phi);
+      });
+      CH_LAUNCH_CHECK();
+      return CH_OK;
+    }
+  }
 
   // ---- rho: z (zero-padded rows of the physical octant), then y ------------------------
   {
@@ -1127,7 +1546,6 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
     auto k = fft_c2r_z_kernel<T>;
     if (allow_smem(k, z_smem(Nz)) != CH_OK) return CH_ECUDA;
     dim3 grid((nx * ny + 2 * kRowPairs - 1) / (2 * kRowPairs), nb);
-    const double norm = 1.0 / (4.0 * kPi * kEpsilon0) / (static_cast<double>(Nx) * Ny * Nz);
     k<<<grid, kFftThreads, z_smem(Nz), stream>>>(rs, Nx, Ny, Nz, lz, nx, ny, nz, params, norm, phi);
     CH_LAUNCH_CHECK();
   }
@@ -1353,7 +1771,14 @@ extern "C" int ch_sc_green_function(const double* params, int64_t n_beams, int32
   const int64_t per_beam = (148 * ctas_per_sm + n_beams - 1) / n_beams;
   dim3 grid_a(ch::blocks_for(points, 256, per_beam < 1 ? 1 : per_beam),
               static_cast<unsigned>(n_beams));
-  ch::sc_green_lattice_kernel<<<grid_a, 256, 0, s>>>(params, nx, ny, nz, lattice);
+  static const bool reference_form = [] {
+    const char* v = getenv("CH_GREEN_REFERENCE_FORM");  // test knob: the reference's expression
+    return v != nullptr && atoi(v) != 0;
+  }();
+  if (reference_form)
+    ch::sc_green_lattice_kernel<true><<<grid_a, 256, 0, s>>>(params, nx, ny, nz, lattice);
+  else
+    ch::sc_green_lattice_kernel<false><<<grid_a, 256, 0, s>>>(params, nx, ny, nz, lattice);
   CH_LAUNCH_CHECK();
   if (green == nullptr) return CH_OK;  // the solver only needs the lattice
   dim3 grid_b(ch::blocks_for(static_cast<int64_t>(8) * nx * ny * nz, 256, 148 * 32),

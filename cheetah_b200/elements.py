@@ -45,6 +45,49 @@ def _bump_epoch() -> None:
     _lattice_epoch += 1
 
 
+def lattice_signature(elements) -> tuple:
+    """Identity and per-element edit counter of every (flattened) element: what a cached lowering
+    of ``elements`` is valid for.  The global epoch is only the cheap first test; this tells a
+    real edit of THIS lattice from attribute traffic on unrelated elements (clones, other
+    segments) and sees structural edits (removed, inserted or reordered elements)."""
+    from .lowering import flatten
+
+    return tuple((id(e), e.__dict__.get("_epoch", 0)) for e in flatten(elements))
+
+
+class ElementList(nn.ModuleList):
+    """``nn.ModuleList`` whose structural edits (``del seg.elements[1]``, ``insert``, ``append``,
+    item assignment ...) bump the lattice epoch, so that cached lowerings are re-validated."""
+
+    def __setitem__(self, idx, module):
+        _bump_epoch()
+        return super().__setitem__(idx, module)
+
+    def __delitem__(self, idx):
+        _bump_epoch()
+        return super().__delitem__(idx)
+
+    def __iadd__(self, modules):
+        _bump_epoch()
+        return super().__iadd__(modules)
+
+    def insert(self, index, module):
+        _bump_epoch()
+        return super().insert(index, module)
+
+    def append(self, module):
+        _bump_epoch()
+        return super().append(module)
+
+    def extend(self, modules):
+        _bump_epoch()
+        return super().extend(modules)
+
+    def pop(self, key):
+        _bump_epoch()
+        return super().pop(key)
+
+
 class Element(nn.Module):
     """Base class of all lattice elements."""
 
@@ -88,10 +131,12 @@ class Element(nn.Module):
 
     def __setattr__(self, name: str, value: Any) -> None:
         _bump_epoch()
+        object.__setattr__(self, "_epoch", self.__dict__.get("_epoch", 0) + 1)
         super().__setattr__(name, value)
 
     def _apply(self, fn, *args, **kwargs):
         _bump_epoch()
+        object.__setattr__(self, "_epoch", self.__dict__.get("_epoch", 0) + 1)
         return super()._apply(fn, *args, **kwargs)
 
     # ---- tracking-method hook (element.py:231-259) ---------------------------------------
@@ -749,7 +794,7 @@ class Segment(Element):
     def __init__(self, elements: list[Element], name: str | None = None,
                  sanitize_name: bool | None = None, metadata: dict | None = None) -> None:
         super().__init__(name=name, sanitize_name=sanitize_name, metadata=metadata)
-        self.elements = nn.ModuleList(elements)
+        self.elements = ElementList(elements)
         for element in elements:  # `segment.<element name>` access (segment.py:60-70)
             if element.name.isidentifier() and not hasattr(self, element.name):
                 object.__setattr__(self, "_alias_" + element.name, element)

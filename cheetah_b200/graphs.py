@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import torch
 
-from .elements import lattice_epoch
+from .elements import lattice_epoch, lattice_signature
 
 
 class GraphedTrack:
@@ -31,24 +31,52 @@ class GraphedTrack:
         torch.cuda.current_stream(device).wait_stream(stream)
         torch.cuda.synchronize(device)
         self.epoch = lattice_epoch()
+        self.signature = lattice_signature([segment])
+        self.unit_seventh = bool(getattr(self.static_in, "_unit_seventh", False))
+        from .lowering import flatten
+
+        self.screens = [e for e in flatten([segment]) if type(e).__name__ == "Screen"]
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = segment.track(self.static_in)
-        if lattice_epoch() != self.epoch:
+        if lattice_signature([segment]) != self.signature:
             raise RuntimeError("the lattice changed while it was being captured")
+        self.epoch = lattice_epoch()
 
     def replay(self, beam=None):
         """Track ``beam`` (or the captured input again); returns the graph-owned outgoing beam."""
         if lattice_epoch() != self.epoch:
-            raise RuntimeError(
-                "an element attribute was re-assigned since capture; build a new GraphedTrack "
-                "(in-place updates of parameter tensors do not need this)"
-            )
+            # something was (re)assigned somewhere: only edits of THIS lattice invalidate the graph
+            if lattice_signature([self.segment]) != self.signature:
+                raise RuntimeError(
+                    "an element attribute of this lattice was re-assigned since capture; build a "
+                    "new GraphedTrack (in-place updates of parameter tensors do not need this)"
+                )
+            self.epoch = lattice_epoch()
         if beam is not None and beam is not self.static_in:
+            if self.unit_seventh:
+                # the captured kernels add column 6 of the map instead of multiplying by the
+                # seventh coordinate: the new beam must satisfy that too
+                flag = getattr(beam, "_unit_seventh", None)
+                if flag is None:
+                    flag = bool((beam.particles[..., 6] == 1).all())
+                if not flag:
+                    raise ValueError(
+                        "this graph was captured for beams with particles[..., 6] == 1; build a "
+                        "new GraphedTrack for a beam whose seventh coordinate is not 1"
+                    )
             self.static_in.particles.copy_(beam.particles)
             self.static_in.energy.copy_(beam.energy)
             self.static_in.particle_charges.copy_(beam.particle_charges)
             self.static_in.survival_probabilities.copy_(beam.survival_probabilities)
             self.static_in.s.copy_(beam.s)
         self.graph.replay()
+        self._invalidate_screen_readings()
         return self.static_out
+
+    def _invalidate_screen_readings(self) -> None:
+        """Active screens share the graph-owned beam buffers: an image rendered from an earlier
+        replay must not be served for this one."""
+        for element in self.screens:
+            if element.__dict__.get("_cached_reading") is not None:
+                object.__setattr__(element, "_cached_reading", None)

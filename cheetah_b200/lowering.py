@@ -318,6 +318,7 @@ def lower(elements, device: torch.device, target_shape: tuple = ()) -> LatticePr
     stages: list = []
     watched: list = []
     section: LinearSection | None = None
+    target_shape = tuple(target_shape)
 
     def open_section() -> LinearSection:
         nonlocal section
@@ -415,6 +416,11 @@ def lower(elements, device: torch.device, target_shape: tuple = ()) -> LatticePr
             )
             sec.cavity = (element, gain_flag)
             close_section()
+            # the outgoing energy is energy + voltage cos(phase) q (cavity.py:122): every later
+            # section sees an energy that also carries the cavity's vector dimensions, and its
+            # slot strides must be resolved against that wider batch
+            target_shape = tuple(torch.broadcast_shapes(
+                tuple(target_shape), tuple(element.voltage.shape), tuple(element.phase.shape)))
         elif kind == "SpaceChargeKick":
             close_section()
             stages.append(Barrier(element, "space_charge"))

@@ -70,17 +70,28 @@ def _require_cuda(tensor: torch.Tensor, what: str) -> None:
 
 
 def _plan(elements, device: torch.device, target_shape: tuple, cache_owner=None):
-    """Lowered program for ``elements``, cached on ``cache_owner`` (a Segment) while no element
-    attribute changes (the epoch) and no value-dependent decision goes stale."""
-    from .elements import lattice_epoch
+    """Lowered program for ``elements``, cached on ``cache_owner`` (a Segment).
 
-    key = (lattice_epoch(), device, tuple(target_shape))
+    Fast test: nothing anywhere was edited (global epoch) and no value-dependent decision went
+    stale.  When the epoch moved, the cached program is kept if THIS lattice still consists of the
+    same element objects in the same order with unchanged edit counters (``lattice_signature``):
+    attribute traffic on unrelated elements does not force a re-lowering, while removed, inserted
+    or reordered elements do."""
+    from .elements import lattice_epoch, lattice_signature
+
+    epoch = lattice_epoch()
+    key = (device, tuple(target_shape))
     cache = getattr(cache_owner, "_plan_cache", None) if cache_owner is not None else None
-    if cache is not None and cache[0] == key and not cache[1].is_stale():
-        return cache[1]
+    if cache is not None and cache[0] == key and not cache[2].is_stale():
+        if cache[1] == epoch:
+            return cache[2]
+        if cache[3] == lattice_signature(elements):
+            object.__setattr__(cache_owner, "_plan_cache", (key, epoch, cache[2], cache[3]))
+            return cache[2]
     program = lowering.lower(elements, device, target_shape)
     if cache_owner is not None and hasattr(cache_owner, "_plan_cache"):
-        object.__setattr__(cache_owner, "_plan_cache", (key, program))
+        object.__setattr__(cache_owner, "_plan_cache",
+                           (key, epoch, program, lattice_signature(elements)))
     return program
 
 
