@@ -161,5 +161,42 @@ __device__ __forceinline__ void transform(C (&v)[16], C* column, int n2, const C
 }
 #endif
 
+// Layout B of the exchange, for passes along the CONTIGUOUS axis: there the N2 threads of a
+// transform are adjacent lanes (n2 in the low bits of threadIdx.x), so that a warp reads N2
+// consecutive elements of each of its 32 / N2 rows straight from global memory.  The exchange
+// word of (n2, k1) then sits at k1 (N2 + 1) + n2 and columns are PITCH_B = 16 (N2 + 1) + N2
+// words apart (= N2 mod 16): scatter (fixed k1) and gather (lane u reads word
+// (u + N2 m)(N2 + 1) + s) are both bank-conflict free for N2 = 2, 4, 8, 16.
+template <int LEN>
+struct PlanB {
+  static constexpr int N2 = LEN / 16;
+  static constexpr int PITCH = 16 * (N2 + 1) + N2;
+};
+template <int LEN, bool INV>
+CH_HD void transform_scatter_b(C (&v)[16], C* column, int n2, const C* tw) {
+  constexpr int N2 = Plan<LEN>::N2;
+  pass1<LEN, INV>(v, n2, tw);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) column[k1 * (N2 + 1) + n2] = v[k1];
+}
+template <int LEN, bool INV>
+CH_HD void transform_gather_b(C (&v)[16], const C* column, int n2) {
+  constexpr int N2 = Plan<LEN>::N2, M = Plan<LEN>::M;
+  C z[16];
+#pragma unroll
+  for (int m = 0; m < M; ++m)
+#pragma unroll
+    for (int s = 0; s < N2; ++s) z[m * N2 + s] = column[(n2 + N2 * m) * (N2 + 1) + s];
+  pass2<LEN, INV>(z, v);
+}
+#ifdef __CUDACC__
+template <int LEN, bool INV>
+__device__ __forceinline__ void transform_b(C (&v)[16], C* column, int n2, const C* tw) {
+  transform_scatter_b<LEN, INV>(v, column, n2, tw);
+  __syncthreads();
+  transform_gather_b<LEN, INV>(v, column, n2);
+}
+#endif
+
 }  // namespace fftr
 }  // namespace ch

@@ -741,29 +741,79 @@ fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, in
 // ---------------------------------------------------------------------------------------
 // 5b. the same passes on the register-resident FFT core (fft_regs.cuh): float, lengths 32 .. 256
 // ---------------------------------------------------------------------------------------
-// Thread layout of every kernel: 16 columns (or packed row pairs) x N2 = LEN / 16 threads, the
-// column index in the low four bits of threadIdx.x -- so the 16 lanes of a half-warp touch 16
-// adjacent columns in global memory (128 contiguous bytes) and 16 different banks of the
-// exchange buffer (odd column pitch).
+// Every pass moves its data global -> registers -> global; shared memory only carries the one
+// exchange inside a transform (plus the pairing of mirrored / packed elements where a pass needs
+// it).  Two thread layouts:
+//   A, passes along a STRIDED axis: COLS adjacent columns per CTA, c = tid % COLS in the low bits
+//      (a half-warp touches 16 adjacent columns = 128 contiguous bytes), n2 = tid / COLS;
+//   B, passes along the CONTIGUOUS axis: n2 = tid % N2 in the low bits (a warp reads N2
+//      consecutive elements of each of its rows), row pair = tid / N2.
+// COLS / ROWS = 16 in general and 8 for launches that would not fill the GPU otherwise.
 using fftr::C;
 
-template <int LEN>
-struct FftrShared {
-  C exchange[16 * fftr::Plan<LEN>::PITCH];
+// rho[B][nx][ny][nz] = sum of the four quad-block parts of sc_deposit_kernel: one thread per
+// 2 x 2 (y, z) quad reads the nine 16-byte blocks that overlap it.
+__global__ void __launch_bounds__(256)
+sc_quad_sum_kernel(const float* __restrict__ quad, int nx, int ny, int nz, float* __restrict__ rho) {
+  const int qy = ny / 2 + 1, qz = nz / 2 + 1;
+  const int hy = (ny + 1) / 2, hz = (nz + 1) / 2;
+  const int64_t b = blockIdx.y;
+  const int64_t quads = static_cast<int64_t>(nx) * hy * hz;
+  const int64_t part = static_cast<int64_t>(qy) * qz;  // float4 blocks per part
+  const float4* base = reinterpret_cast<const float4*>(quad) + b * nx * 4 * part;
+  float* out = rho + b * static_cast<int64_t>(nx) * ny * nz;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < quads;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int Z = static_cast<int>(idx % hz);
+    const int Y = static_cast<int>((idx / hz) % hy);
+    const int x = static_cast<int>(idx / (static_cast<int64_t>(hz) * hy));
+    const float4* p00 = base + (static_cast<int64_t>(x) * 4 + 0) * part + Y * qz + Z;
+    const float4* p01 = p00 + part;
+    const float4* p10 = p01 + part;
+    const float4* p11 = p10 + part;
+    // (the +1 neighbours of the last quad of an odd-sized axis carry no charge: clamp them)
+    const int nz1 = Z + 1 < qz ? 1 : 0, ny1 = Y + 1 < qy ? qz : 0;
+    const float4 a = p00[0];
+    const float4 b0 = p01[0], b1 = p01[nz1];
+    const float4 c0 = p10[0], c1 = p10[ny1];
+    const float4 d00 = p11[0], d01 = p11[nz1], d10 = p11[ny1], d11 = p11[ny1 + nz1];
+    const int y0 = 2 * Y, z0 = 2 * Z;
+    float* row0 = out + (static_cast<int64_t>(x) * ny + y0) * nz + z0;
+    const float v00 = a.x + b0.y + c0.z + d00.w;
+    const float v01 = a.y + b1.x + c0.w + d01.z;
+    const float v10 = a.z + b0.w + c1.x + d10.y;
+    const float v11 = a.w + b1.z + c1.y + d11.x;
+    const bool z1 = z0 + 1 < nz, y1 = y0 + 1 < ny;
+    row0[0] = v00;
+    if (z1) row0[1] = v01;
+    if (y1) {
+      row0[nz] = v10;
+      if (z1) row0[nz + 1] = v11;
+    }
+  }
+}
+
+template <int LEN, int COLS>
+struct FftrSharedA {
+  C exchange[COLS * fftr::Plan<LEN>::PITCH];
+  C twiddles[LEN];
+};
+template <int LEN, int ROWS>
+struct FftrSharedB {
+  C exchange[ROWS * fftr::PlanB<LEN>::PITCH];
   C twiddles[LEN];
 };
 
-// Strided complex pass (MODE as in fft_strided_kernel): columns go global -> registers ->
-// global; the only shared-memory traffic is the one exchange inside each transform.
-template <int LEN, int MODE>
-__global__ void __launch_bounds__(16 * fftr::Plan<LEN>::N2)
+// Strided complex pass (MODE as in fft_strided_kernel).
+template <int LEN, int MODE, int COLS>
+__global__ void __launch_bounds__(COLS * fftr::Plan<LEN>::N2)
 fftr_strided_kernel(C* __restrict__ data, const float* __restrict__ green, int green_ny,
                     int green_kz, int in_len, int out_len, int64_t axis_stride, int inner_count,
                     int64_t outer_stride, int64_t batch_stride) {
   constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH;
-  __shared__ FftrShared<LEN> sh;
-  const int c = threadIdx.x & 15, n2 = threadIdx.x >> 4;
-  const int inner = blockIdx.x * 16 + c;
+  __shared__ FftrSharedA<LEN, COLS> sh;
+  const int c = threadIdx.x % COLS, n2 = threadIdx.x / COLS;
+  const int inner = blockIdx.x * COLS + c;
   const bool live = inner < inner_count;
   C* col = data + blockIdx.z * batch_stride + blockIdx.y * outer_stride + inner;
   fftr::fill_twiddles<LEN>(sh.twiddles);
@@ -803,197 +853,206 @@ fftr_strided_kernel(C* __restrict__ data, const float* __restrict__ green, int g
   }
 }
 
-// z pass, real -> complex: 16 packed row pairs per CTA (semantics of fft_r2c_z_kernel).
-template <int LEN>
-__global__ void __launch_bounds__(16 * fftr::Plan<LEN>::N2)
-fftr_r2c_z_kernel(const float* __restrict__ in, int in_x, int in_y, int in_z, int in_pitch, int quad,
-                  int out_nx, int out_ny, C* __restrict__ out) {
-  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH, THREADS = 16 * N2;
-  __shared__ FftrShared<LEN> sh;
-  const int p = threadIdx.x & 15, n2 = threadIdx.x >> 4;
-  const int64_t b = blockIdx.y;
-  const int rows = in_x * in_y;
-  constexpr int kz = LEN / 2 + 1;
-  const int first_row = blockIdx.x * 32;
-  const int qy = in_y / 2 + 1, qz = in_z / 2 + 1;
-  const int64_t plane = static_cast<int64_t>(4) * qy * qz * 4;
-  const float* src = in + b * (quad ? in_x * plane : static_cast<int64_t>(rows) * in_pitch);
-  C* dst = out + b * static_cast<int64_t>(out_nx) * out_ny * kz;
-
+// Real-even pass of the Green function along a strided axis (the y and x passes of
+// green_spectrum): two adjacent real columns packed as one complex transform.  The column
+// g[0..n) stands for g[0..n), 0 ..., g[n-1..1] of length LEN; outputs k = 0 .. LEN / 2 (real).
+template <int LEN, int COLS>
+__global__ void __launch_bounds__(COLS * fftr::Plan<LEN>::N2)
+fftr_even_strided_kernel(const float* __restrict__ in, float* __restrict__ out, int n,
+                         int total_columns, int inner_count, int64_t in_outer_stride,
+                         int64_t in_axis_stride, int64_t in_batch_stride,
+                         int64_t out_outer_stride, int64_t out_axis_stride,
+                         int64_t out_batch_stride) {
+  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH;
+  __shared__ FftrSharedA<LEN, COLS> sh;
+  const int p = threadIdx.x % COLS, n2 = threadIdx.x / COLS;
+  const int col_a = blockIdx.x * 2 * COLS + 2 * p, col_b = col_a + 1;
+  const bool live_a = col_a < total_columns, live_b = col_b < total_columns;
+  const int outer_a = col_a / inner_count, inner_a = col_a - outer_a * inner_count;
+  const int outer_b = col_b / inner_count, inner_b = col_b - outer_b * inner_count;
+  const float* src = in + blockIdx.y * in_batch_stride;
+  const float* src_a = src + outer_a * in_outer_stride + inner_a;
+  const float* src_b = src + outer_b * in_outer_stride + inner_b;
   fftr::fill_twiddles<LEN>(sh.twiddles);
-  // stage the 32 rows with the z index running over the lanes (contiguous global reads)
-  for (int t = threadIdx.x; t < 16 * in_z; t += THREADS) {
-    const int pair = t / in_z, i = t - pair * in_z;
-    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
-    C value{0.0f, 0.0f};
-    if (r0 < rows)
-      value.x = quad ? quad_value(src + (r0 / in_y) * plane, r0 % in_y, i, qy, qz)
-                     : src[static_cast<int64_t>(r0) * in_pitch + i];
-    if (r1 < rows)
-      value.y = quad ? quad_value(src + (r1 / in_y) * plane, r1 % in_y, i, qy, qz)
-                     : src[static_cast<int64_t>(r1) * in_pitch + i];
-    sh.exchange[pair * PITCH + i] = value;
+  C v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const int pos = N2 * n1 + n2;
+    const int i = pos < n ? pos : (pos > LEN - n ? LEN - pos : -1);  // even extension
+    v[n1] = C{(live_a && i >= 0) ? src_a[i * in_axis_stride] : 0.0f,
+              (live_b && i >= 0) ? src_b[i * in_axis_stride] : 0.0f};
   }
   __syncthreads();
-  C* column = sh.exchange + p * PITCH;
+  fftr::transform<LEN, false>(v, sh.exchange + p * PITCH, n2, sh.twiddles);
+  float* dst = out + blockIdx.y * out_batch_stride;
+  float* dst_a = dst + outer_a * out_outer_stride + inner_a;
+  float* dst_b = dst + outer_b * out_outer_stride + inner_b;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int k = n2 + N2 * j;
+    if (k <= LEN / 2) {
+      if (live_a) dst_a[k * out_axis_stride] = v[j].x;
+      if (live_b) dst_b[k * out_axis_stride] = v[j].y;
+    }
+  }
+}
+
+// Real-even z pass of the Green function straight from the antiderivative lattice: the input
+// of column (x, y) is the 8-corner difference (:195-236) at z = 0 .. nz - 1, evaluated once per
+// element by the thread that owns it and handed to the owner of its mirror image through
+// shared memory.  out: s1[(x ny + y)][LEN / 2 + 1].
+template <int LEN, int ROWS>
+__global__ void __launch_bounds__(ROWS * fftr::Plan<LEN>::N2)
+fftr_even_z_kernel(const double* __restrict__ lattice, float* __restrict__ out, int nx, int ny,
+                   int nz) {
+  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::PlanB<LEN>::PITCH, KZ = LEN / 2 + 1;
+  static_assert(PITCH >= LEN / 2, "the mirror copy borrows a column of the exchange buffer");
+  __shared__ FftrSharedB<LEN, ROWS> sh;
+  const int n2 = threadIdx.x % N2, pr = threadIdx.x / N2;
+  C* mirror = sh.exchange + pr * PITCH;  // own elements, read back by the owner of the mirror image
+  const int total = nx * ny;
+  const int col_a = (blockIdx.x * ROWS + pr) * 2, col_b = col_a + 1;
+  const bool live_a = col_a < total, live_b = col_b < total;
+  const int64_t points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
+  const double* f = lattice + blockIdx.y * points;
+  const int sy = nz + 1, sx = (ny + 1) * (nz + 1);
+  auto corner = [&](int col) {
+    const int x = col / ny, y = col - x * ny;
+    return f + static_cast<int64_t>(x) * sx + y * sy;
+  };
+  const double* qa = corner(live_a ? col_a : 0);
+  const double* qb = corner(live_b ? col_b : 0);
+  auto difference = [&](const double* q) {
+    return static_cast<float>(q[sx + sy + 1] - q[sy + 1] - q[sx + 1] - q[sx + sy] + q[sx] +
+                              q[sy] + q[1] - q[0]);
+  };
+  fftr::fill_twiddles<LEN>(sh.twiddles);
+  C v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const int pos = N2 * n1 + n2;
+    v[n1] = C{0.0f, 0.0f};
+    if (pos < nz) {
+      v[n1] = C{live_a ? difference(qa + pos) : 0.0f, live_b ? difference(qb + pos) : 0.0f};
+      mirror[pos] = v[n1];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const int pos = N2 * n1 + n2;
+    if (pos > LEN - nz) v[n1] = mirror[LEN - pos];
+  }
+  __syncthreads();  // the exchange of the transform overwrites the mirror copy
+  fftr::transform_b<LEN, false>(v, sh.exchange + pr * PITCH, n2, sh.twiddles);
+  float* dst = out + blockIdx.y * static_cast<int64_t>(total) * KZ;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int k = n2 + N2 * j;
+    if (k < KZ) {
+      if (live_a) dst[static_cast<int64_t>(col_a) * KZ + k] = v[j].x;
+      if (live_b) dst[static_cast<int64_t>(col_b) * KZ + k] = v[j].y;
+    }
+  }
+}
+
+// z pass, real -> complex, on plain rows rho[rows][in_z] (sc_quad_sum_kernel): two rows packed
+// per transform; out: [B][out_nx][out_ny][LEN / 2 + 1], rows (x < in_x, y < in_y).
+template <int LEN, int ROWS>
+__global__ void __launch_bounds__(ROWS * fftr::Plan<LEN>::N2)
+fftr_r2c_z_kernel(const float* __restrict__ in, int in_x, int in_y, int in_z, int out_nx,
+                  int out_ny, C* __restrict__ out) {
+  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::PlanB<LEN>::PITCH, KZ = LEN / 2 + 1;
+  constexpr int THREADS = ROWS * N2;
+  static_assert(PITCH >= LEN, "the natural-order copy reuses a column of the exchange buffer");
+  __shared__ FftrSharedB<LEN, ROWS> sh;
+  const int n2 = threadIdx.x % N2, pr = threadIdx.x / N2;
+  const int64_t b = blockIdx.y;
+  const int rows = in_x * in_y;
+  const int first_row = blockIdx.x * 2 * ROWS;
+  const int r0 = first_row + 2 * pr, r1 = r0 + 1;
+  const float* src = in + b * static_cast<int64_t>(rows) * in_z;
+  const float* row0 = src + static_cast<int64_t>(r0) * in_z;
+  const float* row1 = src + static_cast<int64_t>(r1) * in_z;
+  C* dst = out + b * static_cast<int64_t>(out_nx) * out_ny * KZ;
+
+  fftr::fill_twiddles<LEN>(sh.twiddles);
   C v[16];
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) {
     const int n = N2 * n1 + n2;
-    v[n1] = n < in_z ? column[n] : C{0.0f, 0.0f};
+    v[n1] = C{(r0 < rows && n < in_z) ? row0[n] : 0.0f, (r1 < rows && n < in_z) ? row1[n] : 0.0f};
   }
   __syncthreads();
-  fftr::transform<LEN, false>(v, column, n2, sh.twiddles);
+  C* column = sh.exchange + pr * PITCH;
+  fftr::transform_b<LEN, false>(v, column, n2, sh.twiddles);
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 16; ++j) column[n2 + N2 * j] = v[j];
   __syncthreads();
   // separate the two real rows: A = (Z[k] + conj Z[-k]) / 2, B = (Z[k] - conj Z[-k]) / (2i)
-  for (int t = threadIdx.x; t < 16 * kz; t += THREADS) {
-    const int pair = t / kz, k = t - pair * kz;
-    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
-    if (r0 >= rows) continue;
+  for (int t = threadIdx.x; t < ROWS * KZ; t += THREADS) {
+    const int pair = t / KZ, k = t - pair * KZ;
+    const int a0 = first_row + 2 * pair, a1 = a0 + 1;
+    if (a0 >= rows) continue;
     const C zk = sh.exchange[pair * PITCH + k];
     const C zm = sh.exchange[pair * PITCH + ((LEN - k) & (LEN - 1))];
     const C a{0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y)};
     const C bb{0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x)};
-    const int x0 = r0 / in_y, y0 = r0 - x0 * in_y;
-    dst[(static_cast<int64_t>(x0) * out_ny + y0) * kz + k] = a;
-    if (r1 < rows) {
-      const int x1 = r1 / in_y, y1 = r1 - x1 * in_y;
-      dst[(static_cast<int64_t>(x1) * out_ny + y1) * kz + k] = bb;
+    const int x0 = a0 / in_y, y0 = a0 - x0 * in_y;
+    dst[(static_cast<int64_t>(x0) * out_ny + y0) * KZ + k] = a;
+    if (a1 < rows) {
+      const int x1 = a1 / in_y, y1 = a1 - x1 * in_y;
+      dst[(static_cast<int64_t>(x1) * out_ny + y1) * KZ + k] = bb;
     }
   }
 }
 
-// z pass, complex -> real (semantics of fft_c2r_z_kernel).
-template <int LEN>
-__global__ void __launch_bounds__(16 * fftr::Plan<LEN>::N2)
+// z pass, complex -> real (semantics of fft_c2r_z_kernel): spectrum rows in, the first out_z
+// samples of each inverse transform out, both straight from / to global memory.
+template <int LEN, int ROWS>
+__global__ void __launch_bounds__(ROWS * fftr::Plan<LEN>::N2)
 fftr_c2r_z_kernel(const C* __restrict__ in, int in_nx, int in_ny, int out_x, int out_y, int out_z,
                   const double* __restrict__ params, double norm, float* __restrict__ out) {
-  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH, THREADS = 16 * N2;
-  __shared__ FftrShared<LEN> sh;
-  const int p = threadIdx.x & 15, n2 = threadIdx.x >> 4;
+  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::PlanB<LEN>::PITCH, KZ = LEN / 2 + 1;
+  __shared__ FftrSharedB<LEN, ROWS> sh;
+  const int n2 = threadIdx.x % N2, pr = threadIdx.x / N2;
   const int64_t b = blockIdx.y;
   const int rows = out_x * out_y;
-  constexpr int kz = LEN / 2 + 1;
-  const int first_row = blockIdx.x * 32;
-  const C* src = in + b * static_cast<int64_t>(in_nx) * in_ny * kz;
+  const int r0 = (blockIdx.x * ROWS + pr) * 2, r1 = r0 + 1;
+  const bool live0 = r0 < rows, live1 = r1 < rows;
+  const C* src = in + b * static_cast<int64_t>(in_nx) * in_ny * KZ;
+  const int x0 = live0 ? r0 / out_y : 0, y0 = live0 ? r0 - x0 * out_y : 0;
+  const int x1 = live1 ? r1 / out_y : 0, y1 = live1 ? r1 - x1 * out_y : 0;
+  const C* row_a = src + (static_cast<int64_t>(x0) * in_ny + y0) * KZ;
+  const C* row_b = src + (static_cast<int64_t>(x1) * in_ny + y1) * KZ;
   float* dst = out + b * static_cast<int64_t>(rows) * out_z;
   const float scale = static_cast<float>(params[b * CH_SC_PARAMS + 9] * norm);
 
   fftr::fill_twiddles<LEN>(sh.twiddles);
-  for (int t = threadIdx.x; t < 16 * kz; t += THREADS) {
-    const int pair = t / kz, k = t - pair * kz;
-    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
-    C a{0.0f, 0.0f}, bb{0.0f, 0.0f};
-    if (r0 < rows) {
-      const int x0 = r0 / out_y, y0 = r0 - x0 * out_y;
-      a = src[(static_cast<int64_t>(x0) * in_ny + y0) * kz + k];
-    }
-    if (r1 < rows) {
-      const int x1 = r1 / out_y, y1 = r1 - x1 * out_y;
-      bb = src[(static_cast<int64_t>(x1) * in_ny + y1) * kz + k];
+  C v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const int k = N2 * n1 + n2;
+    const int kk = k <= LEN / 2 ? k : LEN - k;  // Hermitian partner for the upper half
+    C a = live0 ? row_a[kk] : C{0.0f, 0.0f};
+    C bb = live1 ? row_b[kk] : C{0.0f, 0.0f};
+    if (k > LEN / 2) {  // conj for the mirrored half
+      a.y = -a.y;
+      bb.y = -bb.y;
     }
     if (k == 0 || k == LEN / 2) a.y = bb.y = 0.0f;  // c2r ignores Im of DC / Nyquist
-    // Z = A + i B; the upper half from the Hermitian symmetry of A and B
-    sh.exchange[pair * PITCH + k] = C{a.x - bb.y, a.y + bb.x};
-    if (k > 0 && k < LEN / 2) sh.exchange[pair * PITCH + LEN - k] = C{a.x + bb.y, bb.x - a.y};
+    v[n1] = C{a.x - bb.y, a.y + bb.x};             // Z = A + i B
   }
   __syncthreads();
-  C* column = sh.exchange + p * PITCH;
-  C v[16];
+  fftr::transform_b<LEN, true>(v, sh.exchange + pr * PITCH, n2, sh.twiddles);
 #pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) v[n1] = column[N2 * n1 + n2];
-  __syncthreads();
-  fftr::transform<LEN, true>(v, column, n2, sh.twiddles);
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 16; ++j) column[n2 + N2 * j] = v[j];
-  __syncthreads();
-  for (int t = threadIdx.x; t < 16 * out_z; t += THREADS) {
-    const int pair = t / out_z, i = t - pair * out_z;
-    const int r0 = first_row + 2 * pair, r1 = r0 + 1;
-    const C z = sh.exchange[pair * PITCH + i];
-    if (r0 < rows) dst[static_cast<int64_t>(r0) * out_z + i] = z.x * scale;
-    if (r1 < rows) dst[static_cast<int64_t>(r1) * out_z + i] = z.y * scale;
-  }
-}
-
-// Real-even pass of the Green function (semantics of fft_even_pass_kernel): 32 columns = 16
-// packed pairs per CTA; the column g[0..n) stands for g[0..n), 0 ..., g[n-1..1] of length LEN.
-template <int LEN, bool FROM_LATTICE>
-__global__ void __launch_bounds__(16 * fftr::Plan<LEN>::N2)
-fftr_even_pass_kernel(const void* __restrict__ in, float* __restrict__ out, int n,
-                      int total_columns, int inner_count, int64_t in_outer_stride,
-                      int64_t in_axis_stride, int64_t in_batch_stride, int64_t out_outer_stride,
-                      int64_t out_axis_stride, int64_t out_batch_stride, int lattice_ny,
-                      int lattice_nz) {
-  constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::Plan<LEN>::PITCH, THREADS = 16 * N2;
-  constexpr int kCols = 32;
-  __shared__ FftrShared<LEN> sh;
-  const int p = threadIdx.x & 15, n2 = threadIdx.x >> 4;
-  const int c0 = blockIdx.x * kCols;
-  const int columns = min(kCols, total_columns - c0);
-  const bool axis_contiguous = in_axis_stride == 1;
-
-  fftr::fill_twiddles<LEN>(sh.twiddles);
-  // positions n .. LEN - n stay zero (plane n of the reference's doubled array, and the padding
-  // when LEN exceeds 2 n)
-  for (int t = threadIdx.x; t < 16 * (LEN - 2 * n + 1); t += THREADS) {
-    const int pair = t / (LEN - 2 * n + 1), i = n + (t - pair * (LEN - 2 * n + 1));
-    sh.exchange[pair * PITCH + i] = C{0.0f, 0.0f};
-  }
-  for (int t = threadIdx.x; t < kCols * n; t += THREADS) {
-    // fastest index follows the contiguous direction of the input
-    const int c = axis_contiguous ? t / n : t % kCols;
-    const int i = axis_contiguous ? t - c * n : t / kCols;
-    float value = 0.0f;
-    if (c < columns) {
-      const int col = c0 + c;
-      const int outer = col / inner_count, inner = col - outer * inner_count;
-      if (FROM_LATTICE) {
-        const double* f = static_cast<const double*>(in) + blockIdx.y * in_batch_stride;
-        const int x = outer / lattice_ny, y = outer - x * lattice_ny;
-        const int sy = lattice_nz + 1, sx = (lattice_ny + 1) * (lattice_nz + 1);
-        const double* q = f + static_cast<int64_t>(x) * sx + y * sy + i;
-        value = static_cast<float>(q[sx + sy + 1] - q[sy + 1] - q[sx + 1] - q[sx + sy] + q[sx] +
-                                   q[sy] + q[1] - q[0]);
-      } else {
-        const float* src = static_cast<const float*>(in) + blockIdx.y * in_batch_stride;
-        value = src[outer * in_outer_stride + inner + i * in_axis_stride];
-      }
+  for (int j = 0; j < 16; ++j) {
+    const int i = n2 + N2 * j;
+    if (i < out_z) {
+      if (live0) dst[static_cast<int64_t>(r0) * out_z + i] = v[j].x * scale;
+      if (live1) dst[static_cast<int64_t>(r1) * out_z + i] = v[j].y * scale;
     }
-    C* column = sh.exchange + (c >> 1) * PITCH;
-    if (c & 1) {
-      column[i].y = value;
-      if (i > 0) column[LEN - i].y = value;
-    } else {
-      column[i].x = value;
-      if (i > 0) column[LEN - i].x = value;
-    }
-  }
-  __syncthreads();
-  C* column = sh.exchange + p * PITCH;
-  C v[16];
-#pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) v[n1] = column[N2 * n1 + n2];
-  __syncthreads();
-  fftr::transform<LEN, false>(v, column, n2, sh.twiddles);
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 16; ++j) column[n2 + N2 * j] = v[j];
-  __syncthreads();
-  float* dst = out + blockIdx.y * out_batch_stride;
-  constexpr int n_out = LEN / 2 + 1;
-  for (int t = threadIdx.x; t < kCols * n_out; t += THREADS) {
-    const int c = axis_contiguous ? t / n_out : t % kCols;
-    const int k = axis_contiguous ? t - c * n_out : t / kCols;
-    if (c >= columns) continue;
-    const int col = c0 + c;
-    const int outer = col / inner_count, inner = col - outer * inner_count;
-    const C z = sh.exchange[(c >> 1) * PITCH + k];
-    dst[outer * out_outer_stride + inner + k * out_axis_stride] = (c & 1) ? z.y : z.x;
   }
 }
 
@@ -1317,6 +1376,332 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
 }
 
 // ---------------------------------------------------------------------------------------
+// 6b / 7b. float32: field "bricks" and the gather that reads them
+// ---------------------------------------------------------------------------------------
+// The trilinear gather needs the field at the 8 nodes around a particle.  With a node array every
+// particle of a warp touches 4 scattered 32-byte sectors per load instruction and the kernel is
+// bound by L1 wavefronts (one per distinct 128-byte line per instruction, ~6 cycles per particle
+// and SM).  Bricks put everything one particle needs side by side:
+//   brick[b][cx][cy][cz] = float[3][8]   (96 bytes)   E_component[s] at node (cx + dx, cy + dy,
+//   cz + dz), corner index q = 4 dx + 2 dy + dz, zero for nodes beyond the grid,
+// and the gather gives each particle four adjacent lanes: lane s < 3 fetches the 32-byte sector of
+// component s with ONE 256-bit load and contracts it with the 8 trilinear weights -- 3 sectors in
+// at most two lines per particle instead of 4 sectors in 4 lines, no cross-lane reduction.
+constexpr int kBrickFloats = 24;
+
+// One CTA: one x plane of cells, kBrickRows rows of y, all z.  The node fields of the 2 x
+// (rows + 1) x (nz + 1) nodes it needs are computed once into shared memory (central differences
+// of phi, zero on the boundary nodes and beyond the grid: space_charge_kick.py:324-365), then
+// written out as bricks with consecutive lanes on consecutive 16-byte pieces.
+constexpr int kBrickRows = 4;
+
+__global__ void __launch_bounds__(256)
+sc_field_brick_kernel(const float* __restrict__ phi, const double* __restrict__ params, int nx,
+                      int ny, int nz, float* __restrict__ bricks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* nodes = reinterpret_cast<float*>(smem_raw);  // [3][2][kBrickRows + 1][nz + 1]
+  const int64_t b = blockIdx.z;
+  const int cx = blockIdx.y, y0 = blockIdx.x * kBrickRows;
+  const double* prm = params + b * CH_SC_PARAMS;
+  const int64_t total = static_cast<int64_t>(nx) * ny * nz;
+  const float* f = phi + b * total;
+  // reference: (phi[i+1] - phi[i-1]) * (0.5 * inv_cell), then * (-igamma2), in the beam dtype
+  const float hx = 0.5f * (1.0f / static_cast<float>(prm[3]));
+  const float hy = 0.5f * (1.0f / static_cast<float>(prm[4]));
+  const float hz = 0.5f * (1.0f / static_cast<float>(prm[5]));
+  const float scale = -static_cast<float>(prm[10]);
+  const int pz = nz + 1, py = kBrickRows + 1;
+  const int node_count = 2 * py * pz;
+  for (int t = threadIdx.x; t < node_count; t += blockDim.x) {
+    const int k = t % pz, j = (t / pz) % py, a = t / (pz * py);
+    const int i = cx + a, jj = y0 + j;
+    float ex = 0.0f, ey = 0.0f, ez = 0.0f;
+    if (i < nx && jj < ny && k < nz) {
+      const int64_t idx = (static_cast<int64_t>(i) * ny + jj) * nz + k;
+      if (i > 0 && i < nx - 1) ex = scale * ((f[idx + ny * nz] - f[idx - ny * nz]) * hx);
+      if (jj > 0 && jj < ny - 1) ey = scale * ((f[idx + nz] - f[idx - nz]) * hy);
+      if (k > 0 && k < nz - 1) ez = scale * ((f[idx + 1] - f[idx - 1]) * hz);
+    }
+    nodes[t] = ex;
+    nodes[node_count + t] = ey;
+    nodes[2 * node_count + t] = ez;
+  }
+  __syncthreads();
+  // item = (row, cz, component s, half h): 4 corner values = one 16-byte store; consecutive items
+  // are consecutive in memory
+  const int rows = min(kBrickRows, ny - y0);
+  float* out = bricks + (b * total + (static_cast<int64_t>(cx) * ny + y0) * nz) * kBrickFloats;
+  const int items = rows * nz * 6;
+  for (int t = threadIdx.x; t < items; t += blockDim.x) {
+    const int h = t & 1, s = (t >> 1) % 3, cell = t / 6;
+    const int cz = cell % nz, r = cell / nz;
+    // half h holds corners q = 4 h + (2 dy + dz): dx = h
+    const float* src = nodes + s * node_count + (h * py + r) * pz + cz;
+    const float4 v = make_float4(src[0], src[1], src[pz], src[pz + 1]);
+    reinterpret_cast<float4*>(out)[t] = v;
+  }
+}
+
+// Gather + kick on bricks (see sc_gather_kick_kernel for what FUSED adds).  Three phases over the
+// CTA's tile of 1024 particles:
+//   A  one thread per particle: brick index and the six corner weights per axis -> shared memory
+//   B  four lanes per particle: component s of the force from one 256-bit load
+//   K  one thread per particle: momentum kick in float32 difference form, the optional map of the
+//      following linear section, the optional moments of the next kick, outgoing row
+// The kick: with u = P / (m c), u_x = px bg0, gamma = g0 (1 + delta b0), du = F dt / (m c):
+//   px' = px + du_x / bg0,  gamma'^2 - gamma^2 = 2 u . du + |du|^2
+//   delta' = delta + (2 u . du + |du|^2) / ((gamma' + gamma) bg0)
+// -- the same algebra as ParticleBeam.to_xyz_pxpypz / from_xyz_pxpypz around P += F dt
+// (particle_beam.py:1262-1346, space_charge_kick.py:557-565) written for the CHANGE of each
+// coordinate, so nothing cancels and float32 carries the kick to ~1e-7 of itself (the reference's
+// float32 version squares SI momenta of 1e-20 kg m/s into the subnormal range).
+struct BrickAux {  // per particle, stride 7 words (bank-conflict free like the particle rows)
+  int offset;      // brick index (cx ny + cy) nz + cz, -1: dead slot
+  float w[6];      // wx_lo, wx_hi, wy_lo, wy_hi, wz_lo, wz_hi (zero for corners off the grid)
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(256, 3)
+sc_gather_kick_brick_kernel(const float* __restrict__ particles_in, int64_t particle_stride,
+                            const float* __restrict__ bricks, const double* __restrict__ params,
+                            int64_t n_particles, int nx, int ny, int nz, int bulk_in, int bulk_out,
+                            float* __restrict__ particles_out, float* __restrict__ forces_out,
+                            const GatherFusion<float> fusion) {
+  constexpr int P = 4, THREADS = 256, TP = P * THREADS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);            // [TP][7]
+  float* aux = tile + TP * 7;                                  // [TP][7]
+  float* forces = aux + TP * 7;                                // [TP][3]
+  __shared__ uint64_t bar;
+  __shared__ __align__(16) float map_s[FUSED ? 48 : 1];  // rows padded to 8 for 128-bit loads
+  __shared__ double partial[FUSED ? 8 : 1][8];
+  if constexpr (FUSED) {
+    if (fusion.records != nullptr && threadIdx.x < 42)
+      map_s[(threadIdx.x / 7) * 8 + threadIdx.x % 7] =
+          fusion.records[blockIdx.y * fusion.record_stride + CH_RECORD_HEADER + threadIdx.x];
+  }
+  const int64_t b = blockIdx.y;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
+  const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
+  const double* prm = params + b * CH_SC_PARAMS;
+  const float* grid = bricks + b * static_cast<int64_t>(nx) * ny * nz * kBrickFloats;
+
+  if (bulk_in && threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  cta_load_tile(tile, particles_in + b * particle_stride + n0 * 7, count * 7, bulk_in != 0, &bar,
+                phase);
+
+  // per-beam constants; grid geometry in the beam dtype (as the reference computes it)
+  const float gd[3] = {static_cast<float>(prm[0]), static_cast<float>(prm[1]),
+                       static_cast<float>(prm[2])};
+  const float cell[3] = {static_cast<float>(prm[3]), static_cast<float>(prm[4]),
+                         static_cast<float>(prm[5])};
+  const int n[3] = {nx, ny, nz};
+  const float gamma0 = static_cast<float>(prm[6]), beta0 = static_cast<float>(prm[7]);
+  const double mc = prm[15] * kEvToKg * kSpeedOfLight;  // mass * c in kg m / s
+  const float bg0 = static_cast<float>(prm[6] * prm[7]);
+  const float inv_bg0 = static_cast<float>(1.0 / (prm[6] * prm[7]));
+  // forces carry the elementary charge; du = F dt / (m c)
+  const float du_per_field = static_cast<float>(kElementaryCharge * prm[8] / mc);
+
+  // ---- A: node-centred corner indices and weights (space_charge_kick.py:388-433) -----------
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int local = threadIdx.x + k * THREADS;
+    const bool live = local < count;
+    const float pos[3] = {live ? tile[local * 7 + 0] : 0.0f, live ? tile[local * 7 + 2] : 0.0f,
+                          (live ? tile[local * 7 + 4] : 0.0f) * -beta0};
+    int index[3];
+    float w[6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float norm = (pos[d] + gd[d]) / cell[d];
+      const float fl = floorf(norm);
+      const float lim = static_cast<float>(n[d] + 1);
+      const int base = static_cast<int>(fminf(fmaxf(fl, -lim), lim));
+      float w_lo = 1.0f - fabsf(norm - fl);  // 1 - |normalised - corner|  (:411-413)
+      float w_hi = 1.0f - fabsf(norm - (fl + 1.0f));
+      // corners outside the grid contribute nothing (valid_mask, :425-433)
+      if (base < 0 || base >= n[d]) w_lo = 0.0f;
+      if (base + 1 < 0 || base + 1 >= n[d]) w_hi = 0.0f;
+      // brick `index` holds nodes index and index + 1: for base == -1 node 0 is its lower corner
+      const bool shifted = base == -1;
+      index[d] = min(max(base, 0), n[d] - 1);
+      w[2 * d] = shifted ? w_hi : w_lo;
+      w[2 * d + 1] = shifted ? 0.0f : w_hi;
+    }
+    float* slot = aux + local * 7;
+    slot[0] = __int_as_float(live ? (index[0] * ny + index[1]) * nz + index[2] : -1);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) slot[1 + i] = w[i];
+  }
+  __syncthreads();
+
+  // ---- B: four lanes per particle, lane s < 3 gathers force component s ---------------------
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, s = lane & 3;
+    constexpr int kPerWarp = TP / (THREADS / 32);  // 128 particles per warp, 8 per step
+    constexpr int kUnroll = 4;
+#pragma unroll 1
+    for (int step = 0; step < kPerWarp / 8; step += kUnroll) {
+      float e[kUnroll][8];
+      int local[kUnroll];
+      bool active[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        local[u] = warp * kPerWarp + (step + u) * 8 + g;
+        const int offset = __float_as_int(aux[local[u] * 7]);
+        active[u] = s < 3 && offset >= 0;
+        const float* src = grid + static_cast<int64_t>(active[u] ? offset : 0) * kBrickFloats +
+                           (s < 3 ? s : 0) * 8;
+        if (active[u]) {
+          asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=f"(e[u][0]), "=f"(e[u][1]), "=f"(e[u][2]), "=f"(e[u][3]),
+                         "=f"(e[u][4]), "=f"(e[u][5]), "=f"(e[u][6]), "=f"(e[u][7])
+                       : "l"(src));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) e[u][q] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const float* w = aux + local[u] * 7 + 1;
+        const float xy00 = w[0] * w[2], xy01 = w[0] * w[3], xy10 = w[1] * w[2], xy11 = w[1] * w[3];
+        const float zl = w[4], zh = w[5];
+        float acc = (xy00 * zl) * e[u][0];
+        acc = fmaf(xy00 * zh, e[u][1], acc);
+        acc = fmaf(xy01 * zl, e[u][2], acc);
+        acc = fmaf(xy01 * zh, e[u][3], acc);
+        acc = fmaf(xy10 * zl, e[u][4], acc);
+        acc = fmaf(xy10 * zh, e[u][5], acc);
+        acc = fmaf(xy11 * zl, e[u][6], acc);
+        acc = fmaf(xy11 * zh, e[u][7], acc);
+        if (s < 3) forces[local[u] * 3 + s] = acc;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- K: kick, optional map and moments, outgoing rows --------------------------------------
+  double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // fused moments of the outgoing particles
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int local = threadIdx.x + k * THREADS;
+    float p[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) p[j] = (local < count) ? tile[local * 7 + j] : 0.0f;
+    const float ex = forces[local * 3 + 0], ey = forces[local * 3 + 1], ez = forces[local * 3 + 2];
+    if (forces_out != nullptr && local < count) {
+      float* f = forces_out + (b * n_particles + n0 + local) * 3;
+      f[0] = ex * static_cast<float>(kElementaryCharge);
+      f[1] = ey * static_cast<float>(kElementaryCharge);
+      f[2] = ez * static_cast<float>(kElementaryCharge);
+    }
+    const float dux = ex * du_per_field, duy = ey * du_per_field, duz = ez * du_per_field;
+    const float ux = p[1] * bg0, uy = p[3] * bg0;
+    const float gamma = fmaf(p[5], bg0, gamma0);  // g0 (1 + delta b0)
+    const float uz = sqrtf(fmaxf(fmaf(gamma, gamma, -1.0f) - ux * ux - uy * uy, 0.0f));
+    const float dg2 = 2.0f * (ux * dux + uy * duy + uz * duz) + (dux * dux + duy * duy + duz * duz);
+    const float gamma_new = sqrtf(fmaf(gamma, gamma, dg2));
+    float row[7];
+    row[0] = p[0];
+    row[1] = fmaf(dux, inv_bg0, p[1]);
+    row[2] = p[2];
+    row[3] = fmaf(duy, inv_bg0, p[3]);
+    row[4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
+    row[5] = p[5] + dg2 / ((gamma_new + gamma) * bg0);
+    row[6] = p[6];
+    if constexpr (FUSED) {
+      if (fusion.records != nullptr) {  // particles @ tm.mT of the following linear section
+        float mapped[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float4 lo = reinterpret_cast<const float4*>(map_s)[i * 2];
+          const float4 hi = reinterpret_cast<const float4*>(map_s)[i * 2 + 1];
+          float a = hi.z * row[6];
+          a = fmaf(hi.y, row[5], a);
+          a = fmaf(hi.x, row[4], a);
+          a = fmaf(lo.w, row[3], a);
+          a = fmaf(lo.z, row[2], a);
+          a = fmaf(lo.y, row[1], a);
+          a = fmaf(lo.x, row[0], a);
+          mapped[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) row[i] = mapped[i];
+      }
+      if (fusion.next_stats != nullptr && local < count) {
+        const double wi = fusion.survival
+                              ? static_cast<double>(
+                                    fusion.survival[b * fusion.survival_stride + n0 + local])
+                              : 1.0;
+        const double dx = static_cast<double>(row[0]);
+        const double dy = static_cast<double>(row[2]);
+        const double dt = static_cast<double>(row[4]);
+        acc8[0] += wi;
+        acc8[1] = fma(wi, wi, acc8[1]);
+        acc8[2] = fma(wi, dx, acc8[2]);
+        acc8[3] = fma(wi, dy, acc8[3]);
+        acc8[4] = fma(wi, dt, acc8[4]);
+        acc8[5] = fma(wi * dx, dx, acc8[5]);
+        acc8[6] = fma(wi * dy, dy, acc8[6]);
+        acc8[7] = fma(wi * dt, dt, acc8[7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) tile[local * 7 + j] = row[j];
+  }
+  float* dst = particles_out + (b * n_particles + n0) * 7;
+  if (bulk_out) {
+    fence_async_shared();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_store(dst, tile, static_cast<uint32_t>(count) * 7u * sizeof(float));
+      bulk_commit();
+      bulk_wait<0>();
+    }
+  } else {
+    __syncthreads();
+    for (int i = threadIdx.x; i < count * 7; i += THREADS) dst[i] = tile[i];
+  }
+  if constexpr (FUSED) {
+    if (fusion.next_stats == nullptr) return;
+    double* stats = fusion.next_stats + b * CH_SC_STATS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double sum = warp_sum(acc8[k]);
+      if (lane == 0) partial[warp][k] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      double sum = 0.0;
+      for (int wi = 0; wi < 8; ++wi) sum += partial[wi][threadIdx.x];
+      atomicAdd(&stats[threadIdx.x], sum);
+    }
+    if (fusion.next_params == nullptr) return;
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      last = atomicAdd(&stats[11], 1.0) == static_cast<double>(gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+      double sums[CH_SC_STATS];
+      for (int i = 0; i < CH_SC_STATS; ++i) sums[i] = __ldcg(&stats[i]);
+      grid_params_for_beam<float>(sums, b, fusion.next_in, fusion.nnx, fusion.nny, fusion.nnz,
+                                  fusion.next_params + b * CH_SC_PARAMS);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------------------
 int log2_exact(int v) {
@@ -1357,6 +1742,14 @@ bool fftr_dispatch(int len, F&& f) {
     default: return false;
   }
 }
+// 16 columns (row pairs) per CTA, 8 when the launch would not give every SM two CTAs otherwise
+template <typename F>
+void fftr_tile(int64_t units, F&& f) {
+  if ((units + 15) / 16 >= 2 * 148)
+    f(std::integral_constant<int, 16>{});
+  else
+    f(std::integral_constant<int, 8>{});
+}
 bool fftr_covers(int len) { return len == 32 || len == 64 || len == 128 || len == 256; }
 bool fftr_enabled() {
   static const bool on = [] {
@@ -1385,10 +1778,12 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
       if constexpr (kFloat) {
         fftr_dispatch(2 * nz, [&](auto L) {
           constexpr int LEN = decltype(L)::value;
-          dim3 grid((columns + 31) / 32, nb);
-          fftr_even_pass_kernel<LEN, true><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
-              lattice, s1, nz, columns, 1, 0, 1, lattice_points, Kz, 1,
-              static_cast<int64_t>(nx) * ny * Kz, ny, nz);
+          fftr_tile((static_cast<int64_t>(columns) + 1) / 2 * B, [&](auto R) {
+            constexpr int ROWS = decltype(R)::value;
+            dim3 grid((columns + 2 * ROWS - 1) / (2 * ROWS), nb);
+            fftr_even_z_kernel<LEN, ROWS><<<grid, ROWS * fftr::Plan<LEN>::N2, 0, stream>>>(
+                lattice, s1, nx, ny, nz);
+          });
         });
       }
     } else {
@@ -1407,11 +1802,14 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
       if constexpr (kFloat) {
         fftr_dispatch(2 * ny, [&](auto L) {
           constexpr int LEN = decltype(L)::value;
-          dim3 grid((columns + 31) / 32, nb);
-          fftr_even_pass_kernel<LEN, false><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
-              s1, s2, ny, columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
-              static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
-              static_cast<int64_t>(nx) * (ny + 1) * Kz, 0, 0);
+          fftr_tile((static_cast<int64_t>(columns) + 1) / 2 * B, [&](auto R) {
+            constexpr int COLS = decltype(R)::value;
+            dim3 grid((columns + 2 * COLS - 1) / (2 * COLS), nb);
+            fftr_even_strided_kernel<LEN, COLS><<<grid, COLS * fftr::Plan<LEN>::N2, 0, stream>>>(
+                s1, s2, ny, columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
+                static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
+                static_cast<int64_t>(nx) * (ny + 1) * Kz);
+          });
         });
       }
     } else {
@@ -1431,10 +1829,14 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
       if constexpr (kFloat) {
         fftr_dispatch(2 * nx, [&](auto L) {
           constexpr int LEN = decltype(L)::value;
-          dim3 grid((columns + 31) / 32, nb);
-          fftr_even_pass_kernel<LEN, false><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
-              s2, spectrum, nx, columns, columns, 0, columns, static_cast<int64_t>(nx) * columns,
-              0, columns, static_cast<int64_t>(nx + 1) * columns, 0, 0);
+          fftr_tile((static_cast<int64_t>(columns) + 1) / 2 * B, [&](auto R) {
+            constexpr int COLS = decltype(R)::value;
+            dim3 grid((columns + 2 * COLS - 1) / (2 * COLS), nb);
+            fftr_even_strided_kernel<LEN, COLS><<<grid, COLS * fftr::Plan<LEN>::N2, 0, stream>>>(
+                s2, spectrum, nx, columns, columns, 0, columns,
+                static_cast<int64_t>(nx) * columns, 0, columns,
+                static_cast<int64_t>(nx + 1) * columns);
+          });
         });
       }
     } else {
@@ -1467,40 +1869,63 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
   if constexpr (kFloat) {
     if (fftr_enabled() && fftr_covers(Nx) && fftr_covers(Ny) && fftr_covers(Nz)) {
       // ---- register-FFT passes: rho z, y; fused x convolution; inverse y, z ----------------
+      // plain charge rows first (phi is free until the last pass writes it)
+      {
+        const int64_t quads = static_cast<int64_t>(nx) * ((ny + 1) / 2) * ((nz + 1) / 2);
+        dim3 grid(blocks_for(quads, 256), nb);
+        sc_quad_sum_kernel<<<grid, 256, 0, stream>>>(rho, nx, ny, nz, phi);
+        CH_LAUNCH_CHECK();
+      }
+      const int64_t row_pairs = (static_cast<int64_t>(nx) * ny + 1) / 2 * B;
       fftr_dispatch(Nz, [&](auto L) {
         constexpr int LEN = decltype(L)::value;
-        dim3 grid((nx * ny + 31) / 32, nb);
-        fftr_r2c_z_kernel<LEN><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(rho, nx, ny, nz, 0,
-                                                                               1, Nx, Ny, rs);
+        fftr_tile(row_pairs, [&](auto R) {
+          constexpr int ROWS = decltype(R)::value;
+          dim3 grid((nx * ny + 2 * ROWS - 1) / (2 * ROWS), nb);
+          fftr_r2c_z_kernel<LEN, ROWS><<<grid, ROWS * fftr::Plan<LEN>::N2, 0, stream>>>(
+              phi, nx, ny, nz, Nx, Ny, rs);
+        });
       });
       CH_LAUNCH_CHECK();
       fftr_dispatch(Ny, [&](auto L) {
         constexpr int LEN = decltype(L)::value;
-        dim3 grid((Kz + 15) / 16, nx, nb);
-        fftr_strided_kernel<LEN, 0><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
-            rs, nullptr, 0, 0, ny, Ny, Kz, Kz, static_cast<int64_t>(Ny) * Kz, spectrum);
+        fftr_tile(static_cast<int64_t>(Kz) * nx * B, [&](auto R) {
+          constexpr int COLS = decltype(R)::value;
+          dim3 grid((Kz + COLS - 1) / COLS, nx, nb);
+          fftr_strided_kernel<LEN, 0, COLS><<<grid, COLS * fftr::Plan<LEN>::N2, 0, stream>>>(
+              rs, nullptr, 0, 0, ny, Ny, Kz, Kz, static_cast<int64_t>(Ny) * Kz, spectrum);
+        });
       });
       CH_LAUNCH_CHECK();
       fftr_dispatch(Nx, [&](auto L) {
         constexpr int LEN = decltype(L)::value;
         const int inner = Ny * Kz;
-        dim3 grid((inner + 15) / 16, 1, nb);
-        fftr_strided_kernel<LEN, 2><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
-            rs, green_spectrum_compact, ny + 1, Kz, nx, nx, inner, inner, 0, spectrum);
+        fftr_tile(static_cast<int64_t>(inner) * B, [&](auto R) {
+          constexpr int COLS = decltype(R)::value;
+          dim3 grid((inner + COLS - 1) / COLS, 1, nb);
+          fftr_strided_kernel<LEN, 2, COLS><<<grid, COLS * fftr::Plan<LEN>::N2, 0, stream>>>(
+              rs, green_spectrum_compact, ny + 1, Kz, nx, nx, inner, inner, 0, spectrum);
+        });
       });
       CH_LAUNCH_CHECK();
       fftr_dispatch(Ny, [&](auto L) {
         constexpr int LEN = decltype(L)::value;
-        dim3 grid((Kz + 15) / 16, nx, nb);
-        fftr_strided_kernel<LEN, 1><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
-            rs, nullptr, 0, 0, Ny, ny, Kz, Kz, static_cast<int64_t>(Ny) * Kz, spectrum);
+        fftr_tile(static_cast<int64_t>(Kz) * nx * B, [&](auto R) {
+          constexpr int COLS = decltype(R)::value;
+          dim3 grid((Kz + COLS - 1) / COLS, nx, nb);
+          fftr_strided_kernel<LEN, 1, COLS><<<grid, COLS * fftr::Plan<LEN>::N2, 0, stream>>>(
+              rs, nullptr, 0, 0, Ny, ny, Kz, Kz, static_cast<int64_t>(Ny) * Kz, spectrum);
+        });
       });
       CH_LAUNCH_CHECK();
       fftr_dispatch(Nz, [&](auto L) {
         constexpr int LEN = decltype(L)::value;
-        dim3 grid((nx * ny + 31) / 32, nb);
-        fftr_c2r_z_kernel<LEN><<<grid, 16 * fftr::Plan<LEN>::N2, 0, stream>>>(
-            rs, Nx, Ny, nx, ny, nz, params, norm, phi);
+        fftr_tile(row_pairs, [&](auto R) {
+          constexpr int ROWS = decltype(R)::value;
+          dim3 grid((nx * ny + 2 * ROWS - 1) / (2 * ROWS), nb);
+          fftr_c2r_z_kernel<LEN, ROWS><<<grid, ROWS * fftr::Plan<LEN>::N2, 0, stream>>>(
+              rs, Nx, Ny, nx, ny, nz, params, norm, phi);
+        });
       });
       CH_LAUNCH_CHECK();
       return CH_OK;

@@ -9,10 +9,10 @@
 
 using ch::fftr::C;
 
-template <int LEN, bool INV>
+template <int LEN, bool INV, bool LAYOUT_B = false>
 double check() {
   constexpr int N2 = ch::fftr::Plan<LEN>::N2;
-  std::vector<C> tw(LEN), column(ch::fftr::Plan<LEN>::PITCH);
+  std::vector<C> tw(LEN), column(LAYOUT_B ? ch::fftr::PlanB<LEN>::PITCH : ch::fftr::Plan<LEN>::PITCH);
   for (int k = 0; k < LEN; ++k)
     tw[k] = C{static_cast<float>(std::cos(-2.0 * M_PI * k / LEN)),
               static_cast<float>(std::sin(-2.0 * M_PI * k / LEN))};
@@ -31,12 +31,14 @@ double check() {
     C v[16];
     for (int n1 = 0; n1 < 16; ++n1)
       v[n1] = C{static_cast<float>(x[N2 * n1 + n2].real()), static_cast<float>(x[N2 * n1 + n2].imag())};
-    ch::fftr::transform_scatter<LEN, INV>(v, column.data(), n2, tw.data());
+    if (LAYOUT_B) ch::fftr::transform_scatter_b<LEN, INV>(v, column.data(), n2, tw.data());
+    else ch::fftr::transform_scatter<LEN, INV>(v, column.data(), n2, tw.data());
   }
   double worst = 0, scale = 0;
   for (int n2 = 0; n2 < N2; ++n2) {
     C v[16];
-    ch::fftr::transform_gather<LEN, INV>(v, column.data(), n2);
+    if (LAYOUT_B) ch::fftr::transform_gather_b<LEN, INV>(v, column.data(), n2);
+    else ch::fftr::transform_gather<LEN, INV>(v, column.data(), n2);
     for (int j = 0; j < 16; ++j) {
       const auto t = truth[n2 + N2 * j];
       worst = std::fmax(worst, std::abs(std::complex<double>(v[j].x, v[j].y) - t));
@@ -48,7 +50,9 @@ double check() {
 
 int main() {
   double errs[] = {check<32, false>(),  check<32, true>(),  check<64, false>(),  check<64, true>(),
-                   check<128, false>(), check<128, true>(), check<256, false>(), check<256, true>()};
+                   check<128, false>(), check<128, true>(), check<256, false>(), check<256, true>(),
+                   check<32, false, true>(), check<64, true, true>(), check<128, false, true>(),
+                   check<128, true, true>(), check<256, false, true>()};
   int bad = 0;
   for (double e : errs) {
     std::printf("%.3e\n", e);
