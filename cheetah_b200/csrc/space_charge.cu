@@ -1238,7 +1238,9 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
     }
   }
 
-  double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // fused moments of the outgoing particles
+  // fused moments of the outgoing particles: per-thread sums over its P particles in the beam
+  // dtype, fp64 across threads and CTAs
+  T acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     const int local = threadIdx.x + k * THREADS;
@@ -1254,24 +1256,51 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
       f[2] = fz;
     }
 
-    // ---- Cheetah -> SI, kick, SI -> Cheetah in fp64 (particle_beam.py:1262-1346) -------
-    // momenta in units of m c (u = P / (m c)): P_x = px p0, p0 / (m c) = gamma0 beta0;
-    // |u|^2 = gamma^2 - 1.  Two square roots and no division per particle.
-    const double gamma = gamma0 * (1.0 + static_cast<double>(p[5]) * beta0);
-    double ux = static_cast<double>(p[1]) * bg0;
-    double uy = static_cast<double>(p[3]) * bg0;
-    double uz = sqrt(gamma * gamma - 1.0 - ux * ux - uy * uy);
-    ux = fma(static_cast<double>(fx), dt_over_mc, ux);
-    uy = fma(static_cast<double>(fy), dt_over_mc, uy);
-    uz = fma(static_cast<double>(fz), dt_over_mc, uz);
-    const double gamma_new = sqrt(1.0 + ux * ux + uy * uy + uz * uz);
-    row[0] = p[0];
-    row[1] = static_cast<T>(ux * inv_bg0);
-    row[2] = p[2];
-    row[3] = static_cast<T>(uy * inv_bg0);
-    row[4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
-    row[5] = static_cast<T>((gamma_new - gamma0) * inv_bg0);
-    row[6] = p[6];
+    if constexpr (sizeof(T) == 4) {
+      // ---- float32: the kick in difference form.  With u = P / (m c): u_x = px bg0,
+      // gamma = g0 (1 + delta b0), du = F dt / (m c):
+      //   px' = px + du_x / bg0,   gamma'^2 - gamma^2 = 2 u . du + |du|^2,
+      //   delta' = delta + (2 u . du + |du|^2) / ((gamma' + gamma) bg0)
+      // -- the algebra of ParticleBeam.to_xyz_pxpypz / from_xyz_pxpypz around P += F dt
+      // (particle_beam.py:1262-1346, space_charge_kick.py:557-565) written for the CHANGE of each
+      // coordinate: nothing cancels, so float32 carries the kick to ~1e-7 of itself (the
+      // reference's float32 version squares SI momenta of 1e-20 kg m/s into the subnormal range,
+      // SURVEY 7.3; the fp64 evaluation used before cost ~100 issue slots per particle more)
+      const float bg = static_cast<float>(bg0), inv_bg = static_cast<float>(inv_bg0);
+      const float du_scale = static_cast<float>(dt_over_mc);
+      const float dux = fx * du_scale, duy = fy * du_scale, duz = fz * du_scale;
+      const float ux = p[1] * bg, uy = p[3] * bg;
+      const float gam = fmaf(p[5], bg, static_cast<float>(gamma0));
+      const float uz = sqrtf(fmaxf(fmaf(gam, gam, -1.0f) - ux * ux - uy * uy, 0.0f));
+      const float dg2 = 2.0f * (ux * dux + uy * duy + uz * duz) +
+                        (dux * dux + duy * duy + duz * duz);
+      const float gam_new = sqrtf(fmaf(gam, gam, dg2));
+      row[0] = p[0];
+      row[1] = fmaf(dux, inv_bg, p[1]);
+      row[2] = p[2];
+      row[3] = fmaf(duy, inv_bg, p[3]);
+      row[4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
+      row[5] = p[5] + dg2 / ((gam_new + gam) * bg);
+      row[6] = p[6];
+    } else {
+      // ---- float64: Cheetah -> SI, kick, SI -> Cheetah (particle_beam.py:1262-1346) in units
+      // of m c (u = P / (m c)): P_x = px p0, p0 / (m c) = gamma0 beta0; |u|^2 = gamma^2 - 1.
+      const double gamma = gamma0 * (1.0 + static_cast<double>(p[5]) * beta0);
+      double ux = static_cast<double>(p[1]) * bg0;
+      double uy = static_cast<double>(p[3]) * bg0;
+      double uz = sqrt(gamma * gamma - 1.0 - ux * ux - uy * uy);
+      ux = fma(static_cast<double>(fx), dt_over_mc, ux);
+      uy = fma(static_cast<double>(fy), dt_over_mc, uy);
+      uz = fma(static_cast<double>(fz), dt_over_mc, uz);
+      const double gamma_new = sqrt(1.0 + ux * ux + uy * uy + uz * uz);
+      row[0] = p[0];
+      row[1] = static_cast<T>(ux * inv_bg0);
+      row[2] = p[2];
+      row[3] = static_cast<T>(uy * inv_bg0);
+      row[4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
+      row[5] = static_cast<T>((gamma_new - gamma0) * inv_bg0);
+      row[6] = p[6];
+    }
     if constexpr (FUSED) {
       if (fusion.records != nullptr) {  // particles @ tm.mT of the following linear section
         // the gather is bound by L1 / shared-memory traffic: fetch each map row with two
@@ -1301,15 +1330,12 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
         for (int i = 0; i < 6; ++i) row[i] = mapped[i];
       }
       if (fusion.next_stats != nullptr && local < count) {
-        // sums about the origin in fp64 (ch_sc_beam_moments uses a pilot particle; with fp64
-        // accumulators the origin is as good: relative error ~ 1e-16 (mean / sigma)^2)
-        const double wi = fusion.survival
-                              ? static_cast<double>(
-                                    fusion.survival[b * fusion.survival_stride + n0 + local])
-                              : 1.0;
-        const double dx = static_cast<double>(row[0]);
-        const double dy = static_cast<double>(row[2]);
-        const double dt = static_cast<double>(row[4]);
+        // sums about the origin (ch_sc_beam_moments uses a pilot particle): four terms per thread
+        // in the beam dtype, then fp64 -- the rounding of the partial sums averages out over the
+        // ~N / 4 threads of a beam (relative error of the variance ~1e-10 (mean / sigma)^2)
+        const T wi = fusion.survival ? fusion.survival[b * fusion.survival_stride + n0 + local]
+                                     : T(1);
+        const T dx = row[0], dy = row[2], dt = row[4];
         acc8[0] += wi;
         acc8[1] = fma(wi, wi, acc8[1]);
         acc8[2] = fma(wi, dx, acc8[2]);
@@ -1344,7 +1370,7 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const double sum = warp_sum(acc8[k]);
+      const double sum = warp_sum(static_cast<double>(acc8[k]));
       if (lane == 0) partial[warp][k] = sum;
     }
     __syncthreads();
@@ -1371,332 +1397,6 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
       for (int i = 0; i < CH_SC_STATS; ++i) sums[i] = __ldcg(&stats[i]);
       grid_params_for_beam<T>(sums, b, fusion.next_in, fusion.nnx, fusion.nny, fusion.nnz,
                               fusion.next_params + b * CH_SC_PARAMS);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// 6b / 7b. float32: field "bricks" and the gather that reads them
-// ---------------------------------------------------------------------------------------
-// The trilinear gather needs the field at the 8 nodes around a particle.  With a node array every
-// particle of a warp touches 4 scattered 32-byte sectors per load instruction and the kernel is
-// bound by L1 wavefronts (one per distinct 128-byte line per instruction, ~6 cycles per particle
-// and SM).  Bricks put everything one particle needs side by side:
-//   brick[b][cx][cy][cz] = float[3][8]   (96 bytes)   E_component[s] at node (cx + dx, cy + dy,
-//   cz + dz), corner index q = 4 dx + 2 dy + dz, zero for nodes beyond the grid,
-// and the gather gives each particle four adjacent lanes: lane s < 3 fetches the 32-byte sector of
-// component s with ONE 256-bit load and contracts it with the 8 trilinear weights -- 3 sectors in
-// at most two lines per particle instead of 4 sectors in 4 lines, no cross-lane reduction.
-constexpr int kBrickFloats = 24;
-
-// One CTA: one x plane of cells, kBrickRows rows of y, all z.  The node fields of the 2 x
-// (rows + 1) x (nz + 1) nodes it needs are computed once into shared memory (central differences
-// of phi, zero on the boundary nodes and beyond the grid: space_charge_kick.py:324-365), then
-// written out as bricks with consecutive lanes on consecutive 16-byte pieces.
-constexpr int kBrickRows = 4;
-
-__global__ void __launch_bounds__(256)
-sc_field_brick_kernel(const float* __restrict__ phi, const double* __restrict__ params, int nx,
-                      int ny, int nz, float* __restrict__ bricks) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* nodes = reinterpret_cast<float*>(smem_raw);  // [3][2][kBrickRows + 1][nz + 1]
-  const int64_t b = blockIdx.z;
-  const int cx = blockIdx.y, y0 = blockIdx.x * kBrickRows;
-  const double* prm = params + b * CH_SC_PARAMS;
-  const int64_t total = static_cast<int64_t>(nx) * ny * nz;
-  const float* f = phi + b * total;
-  // reference: (phi[i+1] - phi[i-1]) * (0.5 * inv_cell), then * (-igamma2), in the beam dtype
-  const float hx = 0.5f * (1.0f / static_cast<float>(prm[3]));
-  const float hy = 0.5f * (1.0f / static_cast<float>(prm[4]));
-  const float hz = 0.5f * (1.0f / static_cast<float>(prm[5]));
-  const float scale = -static_cast<float>(prm[10]);
-  const int pz = nz + 1, py = kBrickRows + 1;
-  const int node_count = 2 * py * pz;
-  for (int t = threadIdx.x; t < node_count; t += blockDim.x) {
-    const int k = t % pz, j = (t / pz) % py, a = t / (pz * py);
-    const int i = cx + a, jj = y0 + j;
-    float ex = 0.0f, ey = 0.0f, ez = 0.0f;
-    if (i < nx && jj < ny && k < nz) {
-      const int64_t idx = (static_cast<int64_t>(i) * ny + jj) * nz + k;
-      if (i > 0 && i < nx - 1) ex = scale * ((f[idx + ny * nz] - f[idx - ny * nz]) * hx);
-      if (jj > 0 && jj < ny - 1) ey = scale * ((f[idx + nz] - f[idx - nz]) * hy);
-      if (k > 0 && k < nz - 1) ez = scale * ((f[idx + 1] - f[idx - 1]) * hz);
-    }
-    nodes[t] = ex;
-    nodes[node_count + t] = ey;
-    nodes[2 * node_count + t] = ez;
-  }
-  __syncthreads();
-  // item = (row, cz, component s, half h): 4 corner values = one 16-byte store; consecutive items
-  // are consecutive in memory
-  const int rows = min(kBrickRows, ny - y0);
-  float* out = bricks + (b * total + (static_cast<int64_t>(cx) * ny + y0) * nz) * kBrickFloats;
-  const int items = rows * nz * 6;
-  for (int t = threadIdx.x; t < items; t += blockDim.x) {
-    const int h = t & 1, s = (t >> 1) % 3, cell = t / 6;
-    const int cz = cell % nz, r = cell / nz;
-    // half h holds corners q = 4 h + (2 dy + dz): dx = h
-    const float* src = nodes + s * node_count + (h * py + r) * pz + cz;
-    const float4 v = make_float4(src[0], src[1], src[pz], src[pz + 1]);
-    reinterpret_cast<float4*>(out)[t] = v;
-  }
-}
-
-// Gather + kick on bricks (see sc_gather_kick_kernel for what FUSED adds).  Three phases over the
-// CTA's tile of 1024 particles:
-//   A  one thread per particle: brick index and the six corner weights per axis -> shared memory
-//   B  four lanes per particle: component s of the force from one 256-bit load
-//   K  one thread per particle: momentum kick in float32 difference form, the optional map of the
-//      following linear section, the optional moments of the next kick, outgoing row
-// The kick: with u = P / (m c), u_x = px bg0, gamma = g0 (1 + delta b0), du = F dt / (m c):
-//   px' = px + du_x / bg0,  gamma'^2 - gamma^2 = 2 u . du + |du|^2
-//   delta' = delta + (2 u . du + |du|^2) / ((gamma' + gamma) bg0)
-// -- the same algebra as ParticleBeam.to_xyz_pxpypz / from_xyz_pxpypz around P += F dt
-// (particle_beam.py:1262-1346, space_charge_kick.py:557-565) written for the CHANGE of each
-// coordinate, so nothing cancels and float32 carries the kick to ~1e-7 of itself (the reference's
-// float32 version squares SI momenta of 1e-20 kg m/s into the subnormal range).
-struct BrickAux {  // per particle, stride 7 words (bank-conflict free like the particle rows)
-  int offset;      // brick index (cx ny + cy) nz + cz, -1: dead slot
-  float w[6];      // wx_lo, wx_hi, wy_lo, wy_hi, wz_lo, wz_hi (zero for corners off the grid)
-};
-
-template <bool FUSED>
-__global__ void __launch_bounds__(256, 3)
-sc_gather_kick_brick_kernel(const float* __restrict__ particles_in, int64_t particle_stride,
-                            const float* __restrict__ bricks, const double* __restrict__ params,
-                            int64_t n_particles, int nx, int ny, int nz, int bulk_in, int bulk_out,
-                            float* __restrict__ particles_out, float* __restrict__ forces_out,
-                            const GatherFusion<float> fusion) {
-  constexpr int P = 4, THREADS = 256, TP = P * THREADS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);            // [TP][7]
-  float* aux = tile + TP * 7;                                  // [TP][7]
-  float* forces = aux + TP * 7;                                // [TP][3]
-  __shared__ uint64_t bar;
-  __shared__ __align__(16) float map_s[FUSED ? 48 : 1];  // rows padded to 8 for 128-bit loads
-  __shared__ double partial[FUSED ? 8 : 1][8];
-  if constexpr (FUSED) {
-    if (fusion.records != nullptr && threadIdx.x < 42)
-      map_s[(threadIdx.x / 7) * 8 + threadIdx.x % 7] =
-          fusion.records[blockIdx.y * fusion.record_stride + CH_RECORD_HEADER + threadIdx.x];
-  }
-  const int64_t b = blockIdx.y;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
-  const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
-  const double* prm = params + b * CH_SC_PARAMS;
-  const float* grid = bricks + b * static_cast<int64_t>(nx) * ny * nz * kBrickFloats;
-
-  if (bulk_in && threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  uint32_t phase = 0;
-  cta_load_tile(tile, particles_in + b * particle_stride + n0 * 7, count * 7, bulk_in != 0, &bar,
-                phase);
-
-  // per-beam constants; grid geometry in the beam dtype (as the reference computes it)
-  const float gd[3] = {static_cast<float>(prm[0]), static_cast<float>(prm[1]),
-                       static_cast<float>(prm[2])};
-  const float cell[3] = {static_cast<float>(prm[3]), static_cast<float>(prm[4]),
-                         static_cast<float>(prm[5])};
-  const int n[3] = {nx, ny, nz};
-  const float gamma0 = static_cast<float>(prm[6]), beta0 = static_cast<float>(prm[7]);
-  const double mc = prm[15] * kEvToKg * kSpeedOfLight;  // mass * c in kg m / s
-  const float bg0 = static_cast<float>(prm[6] * prm[7]);
-  const float inv_bg0 = static_cast<float>(1.0 / (prm[6] * prm[7]));
-  // forces carry the elementary charge; du = F dt / (m c)
-  const float du_per_field = static_cast<float>(kElementaryCharge * prm[8] / mc);
-
-  // ---- A: node-centred corner indices and weights (space_charge_kick.py:388-433) -----------
-#pragma unroll
-  for (int k = 0; k < P; ++k) {
-    const int local = threadIdx.x + k * THREADS;
-    const bool live = local < count;
-    const float pos[3] = {live ? tile[local * 7 + 0] : 0.0f, live ? tile[local * 7 + 2] : 0.0f,
-                          (live ? tile[local * 7 + 4] : 0.0f) * -beta0};
-    int index[3];
-    float w[6];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float norm = (pos[d] + gd[d]) / cell[d];
-      const float fl = floorf(norm);
-      const float lim = static_cast<float>(n[d] + 1);
-      const int base = static_cast<int>(fminf(fmaxf(fl, -lim), lim));
-      float w_lo = 1.0f - fabsf(norm - fl);  // 1 - |normalised - corner|  (:411-413)
-      float w_hi = 1.0f - fabsf(norm - (fl + 1.0f));
-      // corners outside the grid contribute nothing (valid_mask, :425-433)
-      if (base < 0 || base >= n[d]) w_lo = 0.0f;
-      if (base + 1 < 0 || base + 1 >= n[d]) w_hi = 0.0f;
-      // brick `index` holds nodes index and index + 1: for base == -1 node 0 is its lower corner
-      const bool shifted = base == -1;
-      index[d] = min(max(base, 0), n[d] - 1);
-      w[2 * d] = shifted ? w_hi : w_lo;
-      w[2 * d + 1] = shifted ? 0.0f : w_hi;
-    }
-    float* slot = aux + local * 7;
-    slot[0] = __int_as_float(live ? (index[0] * ny + index[1]) * nz + index[2] : -1);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) slot[1 + i] = w[i];
-  }
-  __syncthreads();
-
-  // ---- B: four lanes per particle, lane s < 3 gathers force component s ---------------------
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, s = lane & 3;
-    constexpr int kPerWarp = TP / (THREADS / 32);  // 128 particles per warp, 8 per step
-    constexpr int kUnroll = 4;
-#pragma unroll 1
-    for (int step = 0; step < kPerWarp / 8; step += kUnroll) {
-      float e[kUnroll][8];
-      int local[kUnroll];
-      bool active[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        local[u] = warp * kPerWarp + (step + u) * 8 + g;
-        const int offset = __float_as_int(aux[local[u] * 7]);
-        active[u] = s < 3 && offset >= 0;
-        const float* src = grid + static_cast<int64_t>(active[u] ? offset : 0) * kBrickFloats +
-                           (s < 3 ? s : 0) * 8;
-        if (active[u]) {
-          asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=f"(e[u][0]), "=f"(e[u][1]), "=f"(e[u][2]), "=f"(e[u][3]),
-                         "=f"(e[u][4]), "=f"(e[u][5]), "=f"(e[u][6]), "=f"(e[u][7])
-                       : "l"(src));
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) e[u][q] = 0.0f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const float* w = aux + local[u] * 7 + 1;
-        const float xy00 = w[0] * w[2], xy01 = w[0] * w[3], xy10 = w[1] * w[2], xy11 = w[1] * w[3];
-        const float zl = w[4], zh = w[5];
-        float acc = (xy00 * zl) * e[u][0];
-        acc = fmaf(xy00 * zh, e[u][1], acc);
-        acc = fmaf(xy01 * zl, e[u][2], acc);
-        acc = fmaf(xy01 * zh, e[u][3], acc);
-        acc = fmaf(xy10 * zl, e[u][4], acc);
-        acc = fmaf(xy10 * zh, e[u][5], acc);
-        acc = fmaf(xy11 * zl, e[u][6], acc);
-        acc = fmaf(xy11 * zh, e[u][7], acc);
-        if (s < 3) forces[local[u] * 3 + s] = acc;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- K: kick, optional map and moments, outgoing rows --------------------------------------
-  double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // fused moments of the outgoing particles
-#pragma unroll
-  for (int k = 0; k < P; ++k) {
-    const int local = threadIdx.x + k * THREADS;
-    float p[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) p[j] = (local < count) ? tile[local * 7 + j] : 0.0f;
-    const float ex = forces[local * 3 + 0], ey = forces[local * 3 + 1], ez = forces[local * 3 + 2];
-    if (forces_out != nullptr && local < count) {
-      float* f = forces_out + (b * n_particles + n0 + local) * 3;
-      f[0] = ex * static_cast<float>(kElementaryCharge);
-      f[1] = ey * static_cast<float>(kElementaryCharge);
-      f[2] = ez * static_cast<float>(kElementaryCharge);
-    }
-    const float dux = ex * du_per_field, duy = ey * du_per_field, duz = ez * du_per_field;
-    const float ux = p[1] * bg0, uy = p[3] * bg0;
-    const float gamma = fmaf(p[5], bg0, gamma0);  // g0 (1 + delta b0)
-    const float uz = sqrtf(fmaxf(fmaf(gamma, gamma, -1.0f) - ux * ux - uy * uy, 0.0f));
-    const float dg2 = 2.0f * (ux * dux + uy * duy + uz * duz) + (dux * dux + duy * duy + duz * duz);
-    const float gamma_new = sqrtf(fmaf(gamma, gamma, dg2));
-    float row[7];
-    row[0] = p[0];
-    row[1] = fmaf(dux, inv_bg0, p[1]);
-    row[2] = p[2];
-    row[3] = fmaf(duy, inv_bg0, p[3]);
-    row[4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
-    row[5] = p[5] + dg2 / ((gamma_new + gamma) * bg0);
-    row[6] = p[6];
-    if constexpr (FUSED) {
-      if (fusion.records != nullptr) {  // particles @ tm.mT of the following linear section
-        float mapped[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const float4 lo = reinterpret_cast<const float4*>(map_s)[i * 2];
-          const float4 hi = reinterpret_cast<const float4*>(map_s)[i * 2 + 1];
-          float a = hi.z * row[6];
-          a = fmaf(hi.y, row[5], a);
-          a = fmaf(hi.x, row[4], a);
-          a = fmaf(lo.w, row[3], a);
-          a = fmaf(lo.z, row[2], a);
-          a = fmaf(lo.y, row[1], a);
-          a = fmaf(lo.x, row[0], a);
-          mapped[i] = a;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) row[i] = mapped[i];
-      }
-      if (fusion.next_stats != nullptr && local < count) {
-        const double wi = fusion.survival
-                              ? static_cast<double>(
-                                    fusion.survival[b * fusion.survival_stride + n0 + local])
-                              : 1.0;
-        const double dx = static_cast<double>(row[0]);
-        const double dy = static_cast<double>(row[2]);
-        const double dt = static_cast<double>(row[4]);
-        acc8[0] += wi;
-        acc8[1] = fma(wi, wi, acc8[1]);
-        acc8[2] = fma(wi, dx, acc8[2]);
-        acc8[3] = fma(wi, dy, acc8[3]);
-        acc8[4] = fma(wi, dt, acc8[4]);
-        acc8[5] = fma(wi * dx, dx, acc8[5]);
-        acc8[6] = fma(wi * dy, dy, acc8[6]);
-        acc8[7] = fma(wi * dt, dt, acc8[7]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 7; ++j) tile[local * 7 + j] = row[j];
-  }
-  float* dst = particles_out + (b * n_particles + n0) * 7;
-  if (bulk_out) {
-    fence_async_shared();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      bulk_store(dst, tile, static_cast<uint32_t>(count) * 7u * sizeof(float));
-      bulk_commit();
-      bulk_wait<0>();
-    }
-  } else {
-    __syncthreads();
-    for (int i = threadIdx.x; i < count * 7; i += THREADS) dst[i] = tile[i];
-  }
-  if constexpr (FUSED) {
-    if (fusion.next_stats == nullptr) return;
-    double* stats = fusion.next_stats + b * CH_SC_STATS;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const double sum = warp_sum(acc8[k]);
-      if (lane == 0) partial[warp][k] = sum;
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-      double sum = 0.0;
-      for (int wi = 0; wi < 8; ++wi) sum += partial[wi][threadIdx.x];
-      atomicAdd(&stats[threadIdx.x], sum);
-    }
-    if (fusion.next_params == nullptr) return;
-    __shared__ bool last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0)
-      last = atomicAdd(&stats[11], 1.0) == static_cast<double>(gridDim.x - 1);
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-      double sums[CH_SC_STATS];
-      for (int i = 0; i < CH_SC_STATS; ++i) sums[i] = __ldcg(&stats[i]);
-      grid_params_for_beam<float>(sums, b, fusion.next_in, fusion.nnx, fusion.nny, fusion.nnz,
-                                  fusion.next_params + b * CH_SC_PARAMS);
     }
   }
 }
@@ -2184,14 +1884,15 @@ extern "C" int ch_sc_green_function(const double* params, int64_t n_beams, int32
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
   // The lattice kernel is bound by fp64 transcendentals and runs on a side stream next to the
-  // deposit, which is bound by L2 atomics.  Capping it at ~3 resident CTAs per SM (grid-stride
-  // loop) leaves room for the deposit's CTAs on every SM, so the two overlap instead of queueing
-  // behind each other (64 beams: 630 -> 611 ms per 100 kicks; capping the FFT passes of the
-  // chain as well made them the critical path and was not kept).
+  // deposit, which is bound by L2 reduction requests.  Capping it at ~1 resident CTA per SM
+  // (grid-stride loop) leaves the SM's registers and thread slots to the deposit's CTAs, so the
+  // two overlap instead of queueing behind each other (128 beams, 100 kicks: 878 ms with 3 CTAs
+  // per SM, 847 ms with 1; capping the FFT passes of the chain as well made them the critical
+  // path and was not kept).
   static const int ctas_per_sm = [] {
     const char* v = getenv("CH_GREEN_CTAS_PER_SM");  // tuning knob
-    const int n = v ? atoi(v) : 3;
-    return n > 0 ? n : 3;
+    const int n = v ? atoi(v) : 1;
+    return n > 0 ? n : 1;
   }();
   const int64_t per_beam = (148 * ctas_per_sm + n_beams - 1) / n_beams;
   dim3 grid_a(ch::blocks_for(points, 256, per_beam < 1 ? 1 : per_beam),
