@@ -126,7 +126,8 @@ def stage_table(beam, grid: int, reps: int | None = None) -> list[dict]:
             "sc_green_lattice_kernel + 3 x fft_even_pass_kernel",
             lambda: (lib.ch_sc_green_function(ws.params.data_ptr(), B, grid, grid, grid, code,
                                               ws.lattice.data_ptr(), None, stream),
-                     lib.ch_sc_green_spectrum(ws.lattice.data_ptr(), B, grid, grid, grid, code,
+                     lib.ch_sc_green_spectrum(ws.lattice.data_ptr(), ws.params.data_ptr(), B, grid, grid,
+                                              grid, code,
                                               ws.green_scratch.data_ptr(),
                                               ws.green_spectrum.data_ptr(), stream)),
             B * ((grid + 1) ** 3 * (8 + 8) + 4 * cells3 * 4),
@@ -139,15 +140,18 @@ def stage_table(beam, grid: int, reps: int | None = None) -> list[dict]:
             B * (int(spectrum_bytes * (0.25 + 0.5 + 0.5 + 1.0 + 0.5 + 0.5 + 0.25)) + cells3 * 12),
             "the passes touch 1/4 .. 1 of the (2n)^2 (n+1) complex spectrum, read + write"),
         "field": (
-            "sc_field_kernel",
-            lambda: lib.ch_sc_field(ws.phi.data_ptr(), ws.params.data_ptr(), B, grid, grid, grid,
-                                    code, ws.field.data_ptr(), stream),
-            B * cells3 * (4 + 32), "phi read + z-paired field write"),
+            "sc_field_brick_kernel" if ws.bricks else "sc_field_kernel",
+            lambda: (lib.ch_sc_field_bricks if ws.bricks else lib.ch_sc_field)(
+                ws.phi.data_ptr(), ws.params.data_ptr(), B, grid, grid, grid, code,
+                ws.field.data_ptr(), stream),
+            B * cells3 * (4 + (96 if ws.bricks else 32)),
+            "phi read + 96-byte bricks written" if ws.bricks else "phi read + z-paired field write"),
         "gather": (
-            "sc_gather_kick_kernel",
-            lambda: lib.ch_sc_gather_kick(pp.data_ptr(), ps, ws.field.data_ptr(),
-                                          ws.params.data_ptr(), n, B, grid, grid, grid, code,
-                                          out.data_ptr(), None, stream),
+            "sc_gather_brick_kernel" if ws.bricks else "sc_gather_kick_kernel",
+            lambda: lib.ch_sc_gather_kick(
+                pp.data_ptr(), ps, ws.field.data_ptr(),
+                _capi.SC_FIELD_BRICKS if ws.bricks else _capi.SC_FIELD_NODES,
+                ws.params.data_ptr(), n, B, grid, grid, grid, code, out.data_ptr(), None, stream),
             B * n * 56, "28 B row read + 28 B row written per particle (gathers hit L1/L2)"),
     }
     peak, _ = hbm_peak()

@@ -16,7 +16,7 @@ import torch
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcheetah_b200.so"
 
 CH_F32, CH_F64 = 0, 1
-ABI_VERSION = 2  # CH_ABI_VERSION of include/cheetah_b200.h
+ABI_VERSION = 3  # CH_ABI_VERSION of include/cheetah_b200.h
 
 OP_IDENTITY = 0
 OP_DRIFT = 1
@@ -233,7 +233,8 @@ SIGNATURES = {
     ),
     "ch_sc_green_spectrum": (
         c_int32,
-        [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+         c_void_p],
     ),
     "ch_sc_poisson_solve": (
         c_int32,
@@ -247,10 +248,14 @@ SIGNATURES = {
         c_int32,
         [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p],
     ),
+    "ch_sc_field_bricks": (
+        c_int32,
+        [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p],
+    ),
     "ch_sc_gather_kick": (
         c_int32,
         [
-            c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+            c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_int64,
             c_int32, c_int32, c_int32, c_int32,
             c_void_p, c_void_p, c_void_p,
         ],
@@ -258,7 +263,7 @@ SIGNATURES = {
     "ch_sc_gather_kick_fused": (
         c_int32,
         [
-            c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+            c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_int64,
             c_int32, c_int32, c_int32, c_int32,
             c_void_p, c_int64, c_void_p, c_int64,
             c_void_p, c_void_p,
@@ -275,7 +280,9 @@ SIGNATURES = {
 MOMENTS = 20
 MOMENTS_COV = 36
 SC_STATS = 12
-SC_PARAMS = 16
+SC_PARAMS = 24
+SC_FIELD_NODES = 0
+SC_FIELD_BRICKS = 1
 
 _lib = None
 

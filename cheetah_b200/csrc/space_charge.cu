@@ -11,6 +11,8 @@
 // tiles; the charge histogram lives in L2 (a 64^3 fp32 grid is 1 MB) and is built with
 // fire-and-forget RED atomics (N/cells is ~4: privatising tiles would cost more than the
 // atomics they save); the 3-D convolution is three shared-memory FFT passes.
+#include <math_constants.h>
+
 #include <cstdlib>
 #include <type_traits>
 
@@ -71,6 +73,14 @@ __device__ void grid_params_for_beam(const double* s, int64_t b, const GridInput
   out[10] = gamma != 0.0 ? 1.0 / (gamma * gamma) : 0.0;
   out[14] = sum_w;
   out[15] = mass;
+  // constants of the float32 gather (sc_gather_brick_kernel): u = P / (m c) per unit of px,
+  // du per unit of field (du = e E dt / (m c)) and the reciprocal cell sizes in the beam dtype
+  const double mc = mass * kEvToKg * kSpeedOfLight;
+  out[16] = gamma * beta;
+  out[17] = gamma * beta != 0.0 ? 1.0 / (gamma * beta) : 0.0;
+  out[18] = kElementaryCharge * out[8] / mc;
+  for (int d = 0; d < 3; ++d) out[19 + d] = static_cast<double>(T(1) / static_cast<T>(out[3 + d]));
+  out[22] = out[23] = 0.0;
 }
 
 template <typename T>
@@ -280,6 +290,15 @@ sc_deposit_kernel(const T* __restrict__ particles, int64_t particle_stride,
     fence_mbar_init();
   }
   __syncthreads();
+  // charges and survival probabilities of this thread's particles: issued before the wait for
+  // the tile, so that their DRAM latency overlaps the copy instead of stalling every iteration
+  T weight[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int local = threadIdx.x + k * THREADS;
+    weight[k] = local < count ? q[n0 + local] : T(0);
+    if (w != nullptr && local < count) weight[k] *= w[n0 + local];
+  }
   uint32_t phase = 0;
   cta_load_tile(tile, particles + b * particle_stride + n0 * 7, count * 7, bulk_in != 0, &bar,
                 phase);
@@ -287,7 +306,7 @@ sc_deposit_kernel(const T* __restrict__ particles, int64_t particle_stride,
   for (int k = 0; k < P; ++k) {
     const int local = threadIdx.x + k * THREADS;
     if (local >= count) continue;
-    const T charge = w ? q[n0 + local] * w[n0 + local] : q[n0 + local];
+    const T charge = weight[k];
     // positions are (x, y, z = -beta tau): particle_beam.py:1335
     const AxisDeposit<T> ax = deposit_axis(tile[local * 7 + 0], lo[0], hi[0], nx);
     const AxisDeposit<T> ay = deposit_axis(tile[local * 7 + 2], lo[1], hi[1], ny);
@@ -420,30 +439,98 @@ __device__ __forceinline__ double igf_antiderivative(double x, double y, double 
          x * t * asinh(y / sqrt(x * x + t * t)) + x * y * asinh(t / sqrt(x * x + y * y));
 }
 
+// Far field.  Beyond a few cells the integral of 1/r over a cell is its Taylor series about the cell
+// centre; odd orders vanish and, with t_a = x_a / r, e_a = h_a / r,
+//   G = (V / r) [1 + 1/24 sum_a e_a^2 (3 t_a^2 - 1)
+//                  + 1/1920 sum_a e_a^4 (105 t_a^4 - 90 t_a^2 + 9)
+//                  + 1/576 sum_{a<b} e_a^2 e_b^2 (105 t_a^2 t_b^2 - 15 (t_a^2 + t_b^2) + 3)] + O(e^6)
+// (derivatives of 1/r: d^n/dx^n = (-1)^n n! P_n(x / r) / r^(n+1)).  For r >= kFarRatio h_max the
+// truncation error is < 5e-8 of the value (tools/dev/igf_far_field.py, against 50-digit
+// arithmetic) -- below float32 resolution -- at ~60 fp64 operations instead of the ~1000 of an
+// exact antiderivative corner.  Float32 beams use it (the spectrum is float32 anyway); float64
+// beams keep the exact 8-corner difference everywhere.  With 9:1 cells (BASELINE configs[3]) 87 %
+// of the lattice is far field.
+constexpr double kFarRatio = 6.0;
+
+struct GreenGeometry {
+  double dx, dy, dt;  // cell sizes, d_tau scaled by gamma (space_charge_kick.py:185-189)
+  double near_r2;     // points with |r|^2 below this use the exact difference (inf: all)
+};
+
+__device__ __forceinline__ GreenGeometry green_geometry(const double* prm, bool far_field) {
+  GreenGeometry g;
+  g.dx = prm[3];
+  g.dy = prm[4];
+  g.dt = prm[5] * prm[6];
+  const double h = fmax(g.dx, fmax(g.dy, g.dt)) * kFarRatio;
+  g.near_r2 = far_field ? h * h : CUDART_INF;
+  return g;
+}
+
+// `slack` > 1 widens the near region: the lattice kernel computes slightly more points than the
+// consumers ask for, so a borderline point can never be read without having been written.
+__device__ __forceinline__ bool green_is_near(const GreenGeometry& g, int i, int j, int k,
+                                              double slack = 1.0) {
+  const double x = i * g.dx, y = j * g.dy, t = k * g.dt;
+  return x * x + y * y + t * t < g.near_r2 * slack;
+}
+
+__device__ __forceinline__ double igf_far_field(const GreenGeometry& g, int i, int j, int k) {
+  const double x2 = (i * g.dx) * (i * g.dx), y2 = (j * g.dy) * (j * g.dy),
+               t2 = (k * g.dt) * (k * g.dt);
+  const double inv_r2 = 1.0 / (x2 + y2 + t2);
+  const double tx = x2 * inv_r2, ty = y2 * inv_r2, tt = t2 * inv_r2;
+  const double ex = g.dx * g.dx * inv_r2, ey = g.dy * g.dy * inv_r2, et = g.dt * g.dt * inv_r2;
+  const double s2 = ex * (3.0 * tx - 1.0) + ey * (3.0 * ty - 1.0) + et * (3.0 * tt - 1.0);
+  const double s4a = ex * ex * ((105.0 * tx - 90.0) * tx + 9.0) +
+                     ey * ey * ((105.0 * ty - 90.0) * ty + 9.0) +
+                     et * et * ((105.0 * tt - 90.0) * tt + 9.0);
+  const double s4b = ex * ey * (105.0 * tx * ty - 15.0 * (tx + ty) + 3.0) +
+                     ex * et * (105.0 * tx * tt - 15.0 * (tx + tt) + 3.0) +
+                     ey * et * (105.0 * ty * tt - 15.0 * (ty + tt) + 3.0);
+  return g.dx * g.dy * g.dt * sqrt(inv_r2) *
+         (1.0 + s2 * (1.0 / 24.0) + s4a * (1.0 / 1920.0) + s4b * (1.0 / 576.0));
+}
+
+// Green function value at grid point (i, j, k): far field, or the 8-corner signed difference of
+// the antiderivative lattice (:195-236); `corner` = &lattice[i][j][k].
+__device__ __forceinline__ double green_value(const GreenGeometry& g, const double* corner, int sx,
+                                              int sy, int i, int j, int k) {
+  if (!green_is_near(g, i, j, k)) return igf_far_field(g, i, j, k);
+  return corner[sx + sy + 1] - corner[sy + 1] - corner[sx + 1] - corner[sx + sy] + corner[sx] +
+         corner[sy] + corner[1] - corner[0];
+}
+
 // lattice[i][j][k] = F((i - 1/2) dx, (j - 1/2) dy, (k - 1/2) dt), 0 <= i <= nx, ...  (up to terms
 // the 8-corner difference annihilates, see above)
 template <bool REFERENCE_FORM>
 __global__ void __launch_bounds__(256)
-sc_green_lattice_kernel(const double* __restrict__ params, int nx, int ny, int nz,
+sc_green_lattice_kernel(const double* __restrict__ params, int nx, int ny, int nz, int far_field,
                         double* __restrict__ lattice) {
   const int64_t b = blockIdx.y;
   const double* prm = params + b * CH_SC_PARAMS;
-  const double dx = prm[3], dy = prm[4], dt = prm[5] * prm[6];  // only d_tau is scaled by gamma
+  const GreenGeometry g = green_geometry(prm, far_field != 0);
+  const double dx = g.dx, dy = g.dy, dt = g.dt;
   const double ex = nx * dx, ey = ny * dy, et = nz * dt;
   const double diagonal2 = ex * ex + ey * ey + et * et;
   const double inv_diagonal = rsqrt(diagonal2);
   const double cx = dx * inv_diagonal, cy = dy * inv_diagonal, ct = dt * inv_diagonal;
   const int64_t total = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
   double* out = lattice + b * total;
+  // Threads run along y (the lattice is [i][j][k], k contiguous): the near region is a prefix
+  // of every y row, so warps are either busy or skip at once.  Lattice point (i, j, k) is a corner
+  // of the grid points (i-1..i, j-1..j, k-1..k); it is needed when the innermost of them is near.
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(idx % (nz + 1));
-    const int j = static_cast<int>((idx / (nz + 1)) % (ny + 1));
-    const int i = static_cast<int>(idx / (static_cast<int64_t>(nz + 1) * (ny + 1)));
+    const int j = static_cast<int>(idx % (ny + 1));
+    const int k = static_cast<int>((idx / (ny + 1)) % (nz + 1));
+    const int i = static_cast<int>(idx / (static_cast<int64_t>(ny + 1) * (nz + 1)));
+    if (!green_is_near(g, max(i - 1, 0), max(j - 1, 0), max(k - 1, 0), 1.02)) continue;
+    const int64_t at = (static_cast<int64_t>(i) * (ny + 1) + j) * (nz + 1) + k;
     if (REFERENCE_FORM)
-      out[idx] = igf_antiderivative((i - 0.5) * dx, (j - 0.5) * dy, (k - 0.5) * dt);
+      out[at] = igf_antiderivative((i - 0.5) * dx, (j - 0.5) * dy, (k - 0.5) * dt);
     else
-      out[idx] = diagonal2 * igf_lattice_value(i, j, k, cx, cy, ct);
+      out[at] = diagonal2 * igf_lattice_value(i, j, k, cx, cy, ct);
   }
 }
 
@@ -451,9 +538,10 @@ sc_green_lattice_kernel(const double* __restrict__ params, int nx, int ny, int n
 // (:247-289); the planes with index n stay zero.
 template <typename T>
 __global__ void __launch_bounds__(256)
-sc_green_mirror_kernel(const double* __restrict__ lattice, int nx, int ny, int nz,
-                       T* __restrict__ green) {
+sc_green_mirror_kernel(const double* __restrict__ lattice, const double* __restrict__ params,
+                       int nx, int ny, int nz, int far_field, T* __restrict__ green) {
   const int64_t b = blockIdx.y;
+  const GreenGeometry g = green_geometry(params + b * CH_SC_PARAMS, far_field != 0);
   const int64_t total = static_cast<int64_t>(8) * nx * ny * nz;
   const double* f = lattice + b * static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
   T* out = green + b * total;
@@ -470,10 +558,7 @@ sc_green_mirror_kernel(const double* __restrict__ lattice, int nx, int ny, int n
     const int i = i2 < nx ? i2 : 2 * nx - i2;
     const int j = j2 < ny ? j2 : 2 * ny - j2;
     const int k = k2 < nz ? k2 : 2 * nz - k2;
-    const double* c = f + i * sx + j * sy + k;
-    const double g = c[sx + sy + 1] - c[sy + 1] - c[sx + 1] - c[sx + sy] + c[sx] + c[sy] + c[1] -
-                     c[0];
-    out[idx] = static_cast<T>(g);
+    out[idx] = static_cast<T>(green_value(g, f + i * sx + j * sy + k, sx, sy, i, j, k));
   }
 }
 
@@ -680,7 +765,7 @@ fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, in
                      int log2_len, int total_columns, int inner_count, int64_t in_outer_stride,
                      int64_t in_axis_stride, int64_t in_batch_stride, int64_t out_outer_stride,
                      int64_t out_axis_stride, int64_t out_batch_stride, int lattice_ny,
-                     int lattice_nz) {
+                     int lattice_nz, const double* __restrict__ params, int far_field) {
   using C = typename fft::Complex<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* v = reinterpret_cast<C*>(smem_raw);
@@ -690,6 +775,8 @@ fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, in
   const int c0 = blockIdx.x * kColumns;
   const int columns = min(kColumns, total_columns - c0);
   const bool axis_contiguous = in_axis_stride == 1;
+  GreenGeometry geometry{};
+  if (FROM_LATTICE) geometry = green_geometry(params + blockIdx.y * CH_SC_PARAMS, far_field != 0);
 
   fft::fill_twiddles(tw, len);
   for (int t = threadIdx.x; t < kColumns * n; t += kFftThreads) {
@@ -705,8 +792,7 @@ fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, in
         const int x = outer / lattice_ny, y = outer - x * lattice_ny;
         const int sy = lattice_nz + 1, sx = (lattice_ny + 1) * (lattice_nz + 1);
         const double* q = f + static_cast<int64_t>(x) * sx + y * sy + i;
-        value = static_cast<T>(q[sx + sy + 1] - q[sy + 1] - q[sx + 1] - q[sx + sy] + q[sx] +
-                               q[sy] + q[1] - q[0]);
+        value = static_cast<T>(green_value(geometry, q, sx, sy, x, y, i));
       } else {
         const T* src = static_cast<const T*>(in) + blockIdx.y * in_batch_stride;
         value = src[outer * in_outer_stride + inner + i * in_axis_stride];
@@ -903,8 +989,8 @@ fftr_even_strided_kernel(const float* __restrict__ in, float* __restrict__ out, 
 // shared memory.  out: s1[(x ny + y)][LEN / 2 + 1].
 template <int LEN, int ROWS>
 __global__ void __launch_bounds__(ROWS * fftr::Plan<LEN>::N2)
-fftr_even_z_kernel(const double* __restrict__ lattice, float* __restrict__ out, int nx, int ny,
-                   int nz) {
+fftr_even_z_kernel(const double* __restrict__ lattice, const double* __restrict__ params,
+                   int far_field, float* __restrict__ out, int nx, int ny, int nz) {
   constexpr int N2 = fftr::Plan<LEN>::N2, PITCH = fftr::PlanB<LEN>::PITCH, KZ = LEN / 2 + 1;
   static_assert(PITCH >= LEN / 2, "the mirror copy borrows a column of the exchange buffer");
   __shared__ FftrSharedB<LEN, ROWS> sh;
@@ -916,16 +1002,11 @@ fftr_even_z_kernel(const double* __restrict__ lattice, float* __restrict__ out, 
   const int64_t points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
   const double* f = lattice + blockIdx.y * points;
   const int sy = nz + 1, sx = (ny + 1) * (nz + 1);
-  auto corner = [&](int col) {
-    const int x = col / ny, y = col - x * ny;
-    return f + static_cast<int64_t>(x) * sx + y * sy;
-  };
-  const double* qa = corner(live_a ? col_a : 0);
-  const double* qb = corner(live_b ? col_b : 0);
-  auto difference = [&](const double* q) {
-    return static_cast<float>(q[sx + sy + 1] - q[sy + 1] - q[sx + 1] - q[sx + sy] + q[sx] +
-                              q[sy] + q[1] - q[0]);
-  };
+  const GreenGeometry geometry = green_geometry(params + blockIdx.y * CH_SC_PARAMS, far_field != 0);
+  const int xa = (live_a ? col_a : 0) / ny, ya = (live_a ? col_a : 0) - xa * ny;
+  const int xb = (live_b ? col_b : 0) / ny, yb = (live_b ? col_b : 0) - xb * ny;
+  const double* qa = f + static_cast<int64_t>(xa) * sx + ya * sy;
+  const double* qb = f + static_cast<int64_t>(xb) * sx + yb * sy;
   fftr::fill_twiddles<LEN>(sh.twiddles);
   C v[16];
 #pragma unroll
@@ -933,7 +1014,10 @@ fftr_even_z_kernel(const double* __restrict__ lattice, float* __restrict__ out, 
     const int pos = N2 * n1 + n2;
     v[n1] = C{0.0f, 0.0f};
     if (pos < nz) {
-      v[n1] = C{live_a ? difference(qa + pos) : 0.0f, live_b ? difference(qb + pos) : 0.0f};
+      v[n1] = C{live_a ? static_cast<float>(green_value(geometry, qa + pos, sx, sy, xa, ya, pos))
+                       : 0.0f,
+                live_b ? static_cast<float>(green_value(geometry, qb + pos, sx, sy, xb, yb, pos))
+                       : 0.0f};
       mirror[pos] = v[n1];
     }
   }
@@ -1402,6 +1486,326 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
 }
 
 // ---------------------------------------------------------------------------------------
+// 6b / 7b. float32: field bricks and the quad-cooperative gather
+// ---------------------------------------------------------------------------------------
+// ncu on sc_gather_kick_kernel<float> (profiles/r02_gather_nodes_deposit_ncu_full.txt): 514 instructions per
+// particle at 45 % issue utilisation with the L1 data stage 71 % busy -- every particle pulls four
+// 32-byte sectors out of four different 128-byte lines, one thread waits for all of them, and half
+// of the instructions are index arithmetic, clamps and predicates.  This pair of kernels changes
+// the data layout and the thread mapping:
+//   brick[b][cx][cy][cz] = float[3][8]  (96 bytes): E_component[s] at the eight nodes
+//   (cx + dx, cy + dy, cz + dz), corner q = 4 dx + 2 dy + dz, zero for nodes beyond the grid --
+//   everything one particle needs, contiguous: 3 sectors in 1.5 lines on average;
+//   the four lanes of a quad take turns: in turn t the quad serves the particle owned by its lane
+//   t, lane s < 3 fetching the sector of component s with ONE 256-bit load and contracting it
+//   with the eight trilinear weights (broadcast from the owner with shuffles), so one load
+//   instruction of a warp covers 8 particles in 8-16 lines instead of 32 particles in 32 lines.
+constexpr int kBrickFloats = 24;
+constexpr int kBrickRows = 8;
+
+// One CTA: one x plane of cells, kBrickRows rows of y, all z.  The node fields of the
+// 2 x (rows + 1) x (nz + 1) nodes it needs are computed once into shared memory (central
+// differences of phi, zero on the boundary nodes and beyond the grid:
+// space_charge_kick.py:324-365), then written out as bricks, consecutive lanes on consecutive
+// 16-byte pieces.
+__global__ void __launch_bounds__(256)
+sc_field_brick_kernel(const float* __restrict__ phi, const double* __restrict__ params, int nx,
+                      int ny, int nz, float* __restrict__ bricks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* nodes = reinterpret_cast<float*>(smem_raw);  // [3][2][kBrickRows + 1][nz + 1]
+  const int64_t b = blockIdx.z;
+  const int cx = blockIdx.y, y0 = blockIdx.x * kBrickRows;
+  const double* prm = params + b * CH_SC_PARAMS;
+  const int64_t total = static_cast<int64_t>(nx) * ny * nz;
+  const float* f = phi + b * total;
+  // reference: (phi[i+1] - phi[i-1]) * (0.5 * inv_cell), then * (-igamma2), in the beam dtype
+  const float hx = 0.5f * (1.0f / static_cast<float>(prm[3]));
+  const float hy = 0.5f * (1.0f / static_cast<float>(prm[4]));
+  const float hz = 0.5f * (1.0f / static_cast<float>(prm[5]));
+  const float scale = -static_cast<float>(prm[10]);
+  const int pz = nz + 1, py = kBrickRows + 1;
+  const int node_count = 2 * py * pz;
+  const int plane = ny * nz;
+  for (int t = threadIdx.x; t < node_count; t += blockDim.x) {
+    const int k = t % pz, j = (t / pz) % py, a = t / (pz * py);
+    const int i = cx + a, jj = y0 + j;
+    float ex = 0.0f, ey = 0.0f, ez = 0.0f;
+    if (i < nx && jj < ny && k < nz) {
+      const int idx = (i * ny + jj) * nz + k;
+      if (i > 0 && i < nx - 1) ex = scale * ((f[idx + plane] - f[idx - plane]) * hx);
+      if (jj > 0 && jj < ny - 1) ey = scale * ((f[idx + nz] - f[idx - nz]) * hy);
+      if (k > 0 && k < nz - 1) ez = scale * ((f[idx + 1] - f[idx - 1]) * hz);
+    }
+    nodes[t] = ex;
+    nodes[node_count + t] = ey;
+    nodes[2 * node_count + t] = ez;
+  }
+  __syncthreads();
+  // item = (row, cz, component s, half h): 4 corner values = one 16-byte store; consecutive items
+  // are consecutive in memory.  Half h holds corners q = 4 h + (2 dy + dz): dx = h.
+  const int rows = min(kBrickRows, ny - y0);
+  float4* out = reinterpret_cast<float4*>(
+      bricks + (b * total + (static_cast<int64_t>(cx) * ny + y0) * nz) * kBrickFloats);
+  const int items = rows * nz * 6;
+  for (int t = threadIdx.x; t < items; t += blockDim.x) {
+    const int cell = t / 6, sub = t - cell * 6;
+    const int h = sub & 1, comp = sub >> 1;
+    const int r = cell / nz, cz = cell - r * nz;
+    const float* src = nodes + comp * node_count + (h * py + r) * pz + cz;
+    out[t] = make_float4(src[0], src[1], src[pz], src[pz + 1]);
+  }
+}
+
+// One axis of the node-centred corner search (space_charge_kick.py:388-433) for the brick
+// layout: the cell index whose brick holds both corners and the two weights.  The normalised
+// position is (pos + half_extent) * (1 / cell) -- the reference divides; the product differs by
+// an ulp at most, which can move a particle that sits on a node into the neighbouring cell, where
+// the (continuous) trilinear weights give the same force to rounding.
+__device__ __forceinline__ int brick_axis(float pos, float half_extent, float inv_cell, int n,
+                                          float& w0, float& w1) {
+  const float norm = (pos + half_extent) * inv_cell;
+  const float fl = floorf(norm);
+  const int base = __float2int_rd(norm);             // saturates for far-away particles
+  const float w_lo = 1.0f - (norm - fl);             // 1 - |normalised - corner|  (:411-413)
+  const float w_hi = 1.0f - ((fl + 1.0f) - norm);
+  // corners outside the grid contribute nothing (valid_mask, :425-433)
+  const bool lo_ok = static_cast<unsigned>(base) < static_cast<unsigned>(n);
+  const bool hi_ok = static_cast<unsigned>(base + 1) < static_cast<unsigned>(n);
+  // brick c holds nodes c and c + 1 (node n: zeros); for base == -1 node 0 is the UPPER corner:
+  // brick 0 with that weight in the lower slot
+  const bool shifted = base == -1;
+  w0 = shifted ? w_hi : (lo_ok ? w_lo : 0.0f);
+  w1 = (hi_ok && !shifted) ? w_hi : 0.0f;
+  return min(max(base, 0), n - 1);
+}
+
+// 256-bit load of one brick sector, predicated.  Lanes without work (the fourth lane of a quad,
+// dead particle slots) skip the load and compute on whatever the registers hold: their results
+// are never read.
+__device__ __forceinline__ void load_sector(const float* src, bool active, float (&e)[8]) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %9, 0;\n"
+      "@p ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+      "}\n"
+      : "=f"(e[0]), "=f"(e[1]), "=f"(e[2]), "=f"(e[3]), "=f"(e[4]), "=f"(e[5]), "=f"(e[6]),
+        "=f"(e[7])
+      : "l"(src), "r"(static_cast<int>(active)));
+}
+
+// Gather + kick on bricks (see sc_gather_kick_kernel for what FUSED adds).  The kick is the
+// float32 difference form of that kernel.
+template <bool FUSED>
+__global__ void __launch_bounds__(256, 3)
+sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_stride,
+                       const float* __restrict__ bricks, const double* __restrict__ params,
+                       int64_t n_particles, int nx, int ny, int nz, int bulk_in, int bulk_out,
+                       float* __restrict__ particles_out, float* __restrict__ forces_out,
+                       const GatherFusion<float> fusion) {
+  constexpr int P = 4, THREADS = 256, TP = P * THREADS;
+  constexpr unsigned kFull = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);  // [TP][7]
+  __shared__ uint64_t bar;
+  __shared__ __align__(16) float map_s[FUSED ? 48 : 1];  // rows padded to 8 for 128-bit loads
+  __shared__ double partial[FUSED ? 8 : 1][8];
+  if constexpr (FUSED) {
+    if (fusion.records != nullptr && threadIdx.x < 42)
+      map_s[(threadIdx.x / 7) * 8 + threadIdx.x % 7] =
+          fusion.records[blockIdx.y * fusion.record_stride + CH_RECORD_HEADER + threadIdx.x];
+  }
+  const int64_t b = blockIdx.y;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
+  const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
+  const double* prm = params + b * CH_SC_PARAMS;
+  const float* grid = bricks + b * static_cast<int64_t>(nx) * ny * nz * kBrickFloats;
+
+  if (bulk_in && threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  // per-beam constants (the loads overlap the tile copy); geometry in the beam dtype
+  const float gdx = static_cast<float>(prm[0]), gdy = static_cast<float>(prm[1]),
+              gdz = static_cast<float>(prm[2]);
+  const float icx = static_cast<float>(prm[19]), icy = static_cast<float>(prm[20]),
+              icz = static_cast<float>(prm[21]);
+  const float minus_beta = -static_cast<float>(prm[7]), gamma0 = static_cast<float>(prm[6]);
+  const float bg = static_cast<float>(prm[16]), inv_bg = static_cast<float>(prm[17]);
+  const float du_per_field = static_cast<float>(prm[18]);
+  // weights of the fused moments: fetched now, their DRAM latency overlaps the tile copy
+  float survival[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    survival[k] = 1.0f;
+    if constexpr (FUSED) {
+      const int local = threadIdx.x + k * THREADS;
+      if (fusion.next_stats != nullptr && fusion.survival != nullptr && local < count)
+        survival[k] = fusion.survival[b * fusion.survival_stride + n0 + local];
+    }
+  }
+  cta_load_tile(tile, particles_in + b * particle_stride + n0 * 7, count * 7, bulk_in != 0, &bar,
+                phase);
+
+  const int lane = threadIdx.x & 31;
+  const int quad = lane & ~3, s = lane & 3;
+  const int sector = (s < 3 ? s : 0) * 8;
+  float acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // fused moments of the outgoing particles
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int local = threadIdx.x + k * THREADS;
+    const bool live = local < count;
+    float* mine = tile + local * 7;
+    // ---- own particle: brick index and corner weights ----------------------------------------
+    float w[6];
+    int cell;
+    {
+      const int ix = brick_axis(live ? mine[0] : 0.0f, gdx, icx, nx, w[0], w[1]);
+      const int iy = brick_axis(live ? mine[2] : 0.0f, gdy, icy, ny, w[2], w[3]);
+      const int iz = brick_axis((live ? mine[4] : 0.0f) * minus_beta, gdz, icz, nz, w[4], w[5]);
+      cell = live ? (ix * ny + iy) * nz + iz : -1;
+    }
+    // ---- the quad serves its four particles in turn ------------------------------------------
+    float e[4][8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int o = __shfl_sync(kFull, cell, quad + t);
+      // (a grid has at most 256^3 cells: the float offset fits 32 bits)
+      load_sector(grid + (static_cast<unsigned>(max(o, 0)) * kBrickFloats + sector),
+                  s < 3 && o >= 0, e[t]);
+    }
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float ax0 = __shfl_sync(kFull, w[0], quad + t), ax1 = __shfl_sync(kFull, w[1], quad + t);
+      const float ay0 = __shfl_sync(kFull, w[2], quad + t), ay1 = __shfl_sync(kFull, w[3], quad + t);
+      const float az0 = __shfl_sync(kFull, w[4], quad + t), az1 = __shfl_sync(kFull, w[5], quad + t);
+      // corner q = 4 dx + 2 dy + dz
+      const float xy00 = ax0 * ay0, xy01 = ax0 * ay1, xy10 = ax1 * ay0, xy11 = ax1 * ay1;
+      float acc = xy00 * fmaf(az1, e[t][1], az0 * e[t][0]);
+      acc = fmaf(xy01, fmaf(az1, e[t][3], az0 * e[t][2]), acc);
+      acc = fmaf(xy10, fmaf(az1, e[t][5], az0 * e[t][4]), acc);
+      acc = fmaf(xy11, fmaf(az1, e[t][7], az0 * e[t][6]), acc);
+      // lane s of the quad now holds field component s at the particle of lane t
+      const float vx = __shfl_sync(kFull, acc, quad + 0);
+      const float vy = __shfl_sync(kFull, acc, quad + 1);
+      const float vz = __shfl_sync(kFull, acc, quad + 2);
+      if (t == s) {
+        fx = vx;
+        fy = vy;
+        fz = vz;
+      }
+    }
+    // ---- own particle: kick (difference form, see sc_gather_kick_kernel), map, moments -------
+    float p[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) p[j] = live ? mine[j] : 0.0f;
+    if (forces_out != nullptr && live) {
+      float* f = forces_out + (b * n_particles + n0 + local) * 3;
+      f[0] = fx * static_cast<float>(kElementaryCharge);
+      f[1] = fy * static_cast<float>(kElementaryCharge);
+      f[2] = fz * static_cast<float>(kElementaryCharge);
+    }
+    const float dux = fx * du_per_field, duy = fy * du_per_field, duz = fz * du_per_field;
+    const float ux = p[1] * bg, uy = p[3] * bg;
+    const float gam = fmaf(p[5], bg, gamma0);  // g0 (1 + delta b0)
+    const float uz = sqrtf(fmaxf(fmaf(gam, gam, -1.0f) - ux * ux - uy * uy, 0.0f));
+    const float dg2 =
+        2.0f * (ux * dux + uy * duy + uz * duz) + (dux * dux + duy * duy + duz * duz);
+    const float gam_new = sqrtf(fmaf(gam, gam, dg2));
+    float row[7];
+    row[0] = p[0];
+    row[1] = fmaf(dux, inv_bg, p[1]);
+    row[2] = p[2];
+    row[3] = fmaf(duy, inv_bg, p[3]);
+    row[4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
+    row[5] = p[5] + dg2 / ((gam_new + gam) * bg);
+    row[6] = p[6];
+    if constexpr (FUSED) {
+      if (fusion.records != nullptr) {  // particles @ tm.mT of the following linear section
+        float mapped[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float4 lo = reinterpret_cast<const float4*>(map_s)[i * 2];
+          const float4 hi = reinterpret_cast<const float4*>(map_s)[i * 2 + 1];
+          float a = hi.z * row[6];
+          a = fmaf(hi.y, row[5], a);
+          a = fmaf(hi.x, row[4], a);
+          a = fmaf(lo.w, row[3], a);
+          a = fmaf(lo.z, row[2], a);
+          a = fmaf(lo.y, row[1], a);
+          a = fmaf(lo.x, row[0], a);
+          mapped[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) row[i] = mapped[i];
+      }
+      if (fusion.next_stats != nullptr && live) {
+        const float wi = survival[k];
+        const float dx = row[0], dy = row[2], dt = row[4];
+        acc8[0] += wi;
+        acc8[1] = fmaf(wi, wi, acc8[1]);
+        acc8[2] = fmaf(wi, dx, acc8[2]);
+        acc8[3] = fmaf(wi, dy, acc8[3]);
+        acc8[4] = fmaf(wi, dt, acc8[4]);
+        acc8[5] = fmaf(wi * dx, dx, acc8[5]);
+        acc8[6] = fmaf(wi * dy, dy, acc8[6]);
+        acc8[7] = fmaf(wi * dt, dt, acc8[7]);
+      }
+    }
+    // a row of the tile is only ever touched by the thread that owns the particle
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) mine[j] = row[j];
+    }
+  }
+  float* dst = particles_out + (b * n_particles + n0) * 7;
+  if (bulk_out) {
+    fence_async_shared();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_store(dst, tile, static_cast<uint32_t>(count) * 7u * sizeof(float));
+      bulk_commit();
+      bulk_wait<0>();
+    }
+  } else {
+    __syncthreads();
+    for (int i = threadIdx.x; i < count * 7; i += THREADS) dst[i] = tile[i];
+  }
+  if constexpr (FUSED) {
+    if (fusion.next_stats == nullptr) return;
+    double* stats = fusion.next_stats + b * CH_SC_STATS;
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double sum = warp_sum(static_cast<double>(acc8[k]));
+      if (lane == 0) partial[warp][k] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      double sum = 0.0;
+      for (int wi = 0; wi < 8; ++wi) sum += partial[wi][threadIdx.x];
+      atomicAdd(&stats[threadIdx.x], sum);
+    }
+    if (fusion.next_params == nullptr) return;  // see sc_gather_kick_kernel
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      last = atomicAdd(&stats[11], 1.0) == static_cast<double>(gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+      double sums[CH_SC_STATS];
+      for (int i = 0; i < CH_SC_STATS; ++i) sums[i] = __ldcg(&stats[i]);
+      grid_params_for_beam<float>(sums, b, fusion.next_in, fusion.nnx, fusion.nny, fusion.nnz,
+                                  fusion.next_params + b * CH_SC_PARAMS);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------------------
 int log2_exact(int v) {
@@ -1450,6 +1854,22 @@ void fftr_tile(int64_t units, F&& f) {
   else
     f(std::integral_constant<int, 8>{});
 }
+// Test knobs: CH_GREEN_REFERENCE_FORM=1 evaluates the reference's antiderivative expression,
+// CH_GREEN_NO_FAR_FIELD=1 the exact 8-corner difference everywhere.
+bool green_reference_form() {
+  static const bool on = [] {
+    const char* v = getenv("CH_GREEN_REFERENCE_FORM");
+    return v != nullptr && atoi(v) != 0;
+  }();
+  return on;
+}
+int green_far_field(int dtype) {
+  static const bool off = [] {
+    const char* v = getenv("CH_GREEN_NO_FAR_FIELD");
+    return v != nullptr && atoi(v) != 0;
+  }();
+  return (dtype == CH_F32 && !off && !green_reference_form()) ? 1 : 0;
+}
 bool fftr_covers(int len) { return len == 32 || len == 64 || len == 128 || len == 256; }
 bool fftr_enabled() {
   static const bool on = [] {
@@ -1462,8 +1882,8 @@ bool fftr_enabled() {
 // Compact Green spectrum [B][nx+1][ny+1][nz+1] from the antiderivative lattice: three even
 // passes through two scratch arrays s1 [B][nx][ny][nz+1], s2 [B][nx][ny+1][nz+1].
 template <typename T>
-int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* s1, T* s2,
-                   T* spectrum, cudaStream_t stream) {
+int green_spectrum(const double* lattice, const double* params, int far_field, int64_t B, int nx,
+                   int ny, int nz, T* s1, T* s2, T* spectrum, cudaStream_t stream) {
   using C = typename fft::Complex<T>::type;
   const int Kz = nz + 1;
   const unsigned nb = static_cast<unsigned>(B);
@@ -1482,7 +1902,7 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
             constexpr int ROWS = decltype(R)::value;
             dim3 grid((columns + 2 * ROWS - 1) / (2 * ROWS), nb);
             fftr_even_z_kernel<LEN, ROWS><<<grid, ROWS * fftr::Plan<LEN>::N2, 0, stream>>>(
-                lattice, s1, nx, ny, nz);
+                lattice, params, far_field, s1, nx, ny, nz);
           });
         });
       }
@@ -1492,7 +1912,7 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
       dim3 grid((columns + kColumns - 1) / kColumns, nb);
       k<<<grid, kFftThreads, smem(2 * nz), stream>>>(
           lattice, s1, nz, 2 * nz, log2_exact(2 * nz), columns, 1, 0, 1, lattice_points, Kz, 1,
-          static_cast<int64_t>(nx) * ny * Kz, ny, nz);
+          static_cast<int64_t>(nx) * ny * Kz, ny, nz, params, far_field);
     }
     CH_LAUNCH_CHECK();
   }
@@ -1519,7 +1939,7 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
       k<<<grid, kFftThreads, smem(2 * ny), stream>>>(
           s1, s2, ny, 2 * ny, log2_exact(2 * ny), columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
           static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
-          static_cast<int64_t>(nx) * (ny + 1) * Kz, 0, 0);
+          static_cast<int64_t>(nx) * (ny + 1) * Kz, 0, 0, nullptr, 0);
     }
     CH_LAUNCH_CHECK();
   }
@@ -1546,7 +1966,7 @@ int green_spectrum(const double* lattice, int64_t B, int nx, int ny, int nz, T* 
       k<<<grid, kFftThreads, smem(2 * nx), stream>>>(
           s2, spectrum, nx, 2 * nx, log2_exact(2 * nx), columns, columns, 0, columns,
           static_cast<int64_t>(nx) * columns, 0, columns, static_cast<int64_t>(nx + 1) * columns, 0,
-          0);
+          0, nullptr, 0);
     }
     CH_LAUNCH_CHECK();
   }
@@ -1897,44 +2317,44 @@ extern "C" int ch_sc_green_function(const double* params, int64_t n_beams, int32
   const int64_t per_beam = (148 * ctas_per_sm + n_beams - 1) / n_beams;
   dim3 grid_a(ch::blocks_for(points, 256, per_beam < 1 ? 1 : per_beam),
               static_cast<unsigned>(n_beams));
-  static const bool reference_form = [] {
-    const char* v = getenv("CH_GREEN_REFERENCE_FORM");  // test knob: the reference's expression
-    return v != nullptr && atoi(v) != 0;
-  }();
-  if (reference_form)
-    ch::sc_green_lattice_kernel<true><<<grid_a, 256, 0, s>>>(params, nx, ny, nz, lattice);
+  const int far_field = ch::green_far_field(dtype);
+  if (ch::green_reference_form())
+    ch::sc_green_lattice_kernel<true><<<grid_a, 256, 0, s>>>(params, nx, ny, nz, far_field,
+                                                              lattice);
   else
-    ch::sc_green_lattice_kernel<false><<<grid_a, 256, 0, s>>>(params, nx, ny, nz, lattice);
+    ch::sc_green_lattice_kernel<false><<<grid_a, 256, 0, s>>>(params, nx, ny, nz, far_field,
+                                                               lattice);
   CH_LAUNCH_CHECK();
   if (green == nullptr) return CH_OK;  // the solver only needs the lattice
   dim3 grid_b(ch::blocks_for(static_cast<int64_t>(8) * nx * ny * nz, 256, 148 * 32),
               static_cast<unsigned>(n_beams));
   if (dtype == CH_F32)
-    ch::sc_green_mirror_kernel<float><<<grid_b, 256, 0, s>>>(lattice, nx, ny, nz,
-                                                             static_cast<float*>(green));
+    ch::sc_green_mirror_kernel<float><<<grid_b, 256, 0, s>>>(lattice, params, nx, ny, nz,
+                                                             far_field, static_cast<float*>(green));
   else
-    ch::sc_green_mirror_kernel<double><<<grid_b, 256, 0, s>>>(lattice, nx, ny, nz,
-                                                              static_cast<double*>(green));
+    ch::sc_green_mirror_kernel<double><<<grid_b, 256, 0, s>>>(
+        lattice, params, nx, ny, nz, far_field, static_cast<double*>(green));
   CH_LAUNCH_CHECK();
   return CH_OK;
 }
 
-extern "C" int ch_sc_green_spectrum(const double* lattice, int64_t n_beams, int32_t nx, int32_t ny,
-                                    int32_t nz, int32_t dtype, void* scratch, void* spectrum,
-                                    void* stream) {
+extern "C" int ch_sc_green_spectrum(const double* lattice, const double* params, int64_t n_beams,
+                                    int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                                    void* scratch, void* spectrum, void* stream) {
   CH_SC_COMMON_CHECKS("ch_sc_green_spectrum");
-  CH_REQUIRE(lattice && scratch && spectrum, "ch_sc_green_spectrum: NULL pointer argument");
+  CH_REQUIRE(lattice && params && scratch && spectrum,
+             "ch_sc_green_spectrum: NULL pointer argument");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_green_spectrum: bad grid (%d, %d, %d)", nx, ny, nz);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t s1 = n_beams * static_cast<int64_t>(nx) * ny * (nz + 1);
   if (dtype == CH_F32) {
     float* base = static_cast<float*>(scratch);
-    return ch::green_spectrum<float>(lattice, n_beams, nx, ny, nz, base, base + s1,
-                                     static_cast<float*>(spectrum), s);
+    return ch::green_spectrum<float>(lattice, params, ch::green_far_field(dtype), n_beams, nx, ny,
+                                     nz, base, base + s1, static_cast<float*>(spectrum), s);
   }
   double* base = static_cast<double*>(scratch);
-  return ch::green_spectrum<double>(lattice, n_beams, nx, ny, nz, base, base + s1,
-                                    static_cast<double*>(spectrum), s);
+  return ch::green_spectrum<double>(lattice, params, ch::green_far_field(dtype), n_beams, nx, ny,
+                                    nz, base, base + s1, static_cast<double*>(spectrum), s);
 }
 
 extern "C" int ch_sc_poisson_solve(const void* rho, const void* green_spectrum,
@@ -1975,17 +2395,50 @@ extern "C" int ch_sc_field(const void* phi, const double* params, int64_t n_beam
   return CH_OK;
 }
 
+extern "C" int ch_sc_field_bricks(const void* phi, const double* params, int64_t n_beams,
+                                  int32_t nx, int32_t ny, int32_t nz, int32_t dtype, void* bricks,
+                                  void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_field_bricks");
+  CH_REQUIRE(dtype == CH_F32, "ch_sc_field_bricks: float32 only (float64 uses ch_sc_field)");
+  CH_REQUIRE(phi && params && bricks, "ch_sc_field_bricks: NULL pointer argument");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_field_bricks: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = sizeof(float) * 3 * 2 * (ch::kBrickRows + 1) * (nz + 1);
+  if (ch::allow_smem(ch::sc_field_brick_kernel, smem) != CH_OK) return CH_ECUDA;
+  dim3 grid((ny + ch::kBrickRows - 1) / ch::kBrickRows, nx, static_cast<unsigned>(n_beams));
+  ch::sc_field_brick_kernel<<<grid, 256, smem, s>>>(static_cast<const float*>(phi), params, nx, ny,
+                                                    nz, static_cast<float*>(bricks));
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
 namespace {
 template <typename T>
 int launch_gather(const void* particles_in, int64_t particle_stride, const void* field,
-                  const double* params, int64_t n_particles, int64_t n_beams, int nx, int ny,
-                  int nz, void* particles_out, void* forces_out,
+                  int field_layout, const double* params, int64_t n_particles, int64_t n_beams,
+                  int nx, int ny, int nz, void* particles_out, void* forces_out,
                   const ch::GatherFusion<T>* fusion, cudaStream_t s) {
   using F4 = typename ch::Field4<T>::type;
   dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(n_beams));
   const int bulk_in = ch::bulk_compatible<T>(particles_in, n_particles, particle_stride);
   const int bulk_out = ch::bulk_compatible<T>(particles_out, n_particles, n_particles * 7);
   const size_t smem = 1024 * 7 * sizeof(T);
+  if constexpr (std::is_same<T, float>::value) {
+    if (field_layout == CH_SC_FIELD_BRICKS) {
+      auto launch_bricks = [&](auto kernel, const ch::GatherFusion<float>& f) -> int {
+        kernel<<<grid, 256, smem, s>>>(static_cast<const float*>(particles_in), particle_stride,
+                                       static_cast<const float*>(field), params, n_particles, nx,
+                                       ny, nz, bulk_in, bulk_out,
+                                       static_cast<float*>(particles_out),
+                                       static_cast<float*>(forces_out), f);
+        return CH_OK;
+      };
+      fusion ? launch_bricks(ch::sc_gather_brick_kernel<true>, *fusion)
+             : launch_bricks(ch::sc_gather_brick_kernel<false>, ch::GatherFusion<float>{});
+      CH_LAUNCH_CHECK();
+      return CH_OK;
+    }
+  }
   auto launch = [&](auto kernel, const ch::GatherFusion<T>& f) -> int {
     CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
@@ -2003,26 +2456,34 @@ int launch_gather(const void* particles_in, int64_t particle_stride, const void*
 }
 }  // namespace
 
+#define CH_SC_LAYOUT_CHECK(fn)                                                              \
+  CH_REQUIRE(field_layout == CH_SC_FIELD_NODES ||                                            \
+                 (field_layout == CH_SC_FIELD_BRICKS && dtype == CH_F32),                    \
+             fn ": field_layout %d not available for dtype %d", field_layout, dtype)
+
 extern "C" int ch_sc_gather_kick(const void* particles_in, int64_t particle_stride,
-                                 const void* field, const double* params, int64_t n_particles,
-                                 int64_t n_beams, int32_t nx, int32_t ny, int32_t nz,
-                                 int32_t dtype, void* particles_out, void* forces_out,
+                                 const void* field, int32_t field_layout, const double* params,
+                                 int64_t n_particles, int64_t n_beams, int32_t nx, int32_t ny,
+                                 int32_t nz, int32_t dtype, void* particles_out, void* forces_out,
                                  void* stream) {
   CH_SC_COMMON_CHECKS("ch_sc_gather_kick");
   CH_REQUIRE(particles_in && field && params && particles_out && n_particles > 0,
              "ch_sc_gather_kick: bad arguments");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_gather_kick: bad grid (%d, %d, %d)", nx, ny, nz);
+  CH_SC_LAYOUT_CHECK("ch_sc_gather_kick");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == CH_F32)
-    return launch_gather<float>(particles_in, particle_stride, field, params, n_particles, n_beams,
-                                nx, ny, nz, particles_out, forces_out, nullptr, s);
-  return launch_gather<double>(particles_in, particle_stride, field, params, n_particles, n_beams,
-                               nx, ny, nz, particles_out, forces_out, nullptr, s);
+    return launch_gather<float>(particles_in, particle_stride, field, field_layout, params,
+                                n_particles, n_beams, nx, ny, nz, particles_out, forces_out,
+                                nullptr, s);
+  return launch_gather<double>(particles_in, particle_stride, field, field_layout, params,
+                               n_particles, n_beams, nx, ny, nz, particles_out, forces_out,
+                               nullptr, s);
 }
 
 extern "C" int ch_sc_gather_kick_fused(
-    const void* particles_in, int64_t particle_stride, const void* field, const double* params,
-    int64_t n_particles, int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+    const void* particles_in, int64_t particle_stride, const void* field, int32_t field_layout,
+    const double* params, int64_t n_particles, int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
     const void* records, int64_t record_stride, const void* survival, int64_t survival_stride,
     double* next_stats, double* next_params, const void* energy, int64_t energy_stride,
     int32_t energy_dtype, const void* mass_eV, int32_t mass_dtype, const void* next_effect_length,
@@ -2034,6 +2495,7 @@ extern "C" int ch_sc_gather_kick_fused(
   CH_REQUIRE(particles_in && field && params && particles_out && n_particles > 0,
              "ch_sc_gather_kick_fused: bad arguments");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_gather_kick_fused: bad grid (%d, %d, %d)", nx, ny, nz);
+  CH_SC_LAYOUT_CHECK("ch_sc_gather_kick_fused");
   CH_REQUIRE(records != nullptr || next_stats != nullptr,
              "ch_sc_gather_kick_fused: nothing to fuse (use ch_sc_gather_kick)");
   if (next_stats != nullptr) {
@@ -2061,14 +2523,15 @@ extern "C" int ch_sc_gather_kick_fused(
     const ch::GatherFusion<float> f{static_cast<const float*>(records), record_stride,
                                     static_cast<const float*>(survival), survival_stride,
                                     next_stats, in_kernel_params, in, next_nx, next_ny, next_nz};
-    status = launch_gather<float>(particles_in, particle_stride, field, params, n_particles,
-                                  n_beams, nx, ny, nz, particles_out, nullptr, &f, s);
+    status = launch_gather<float>(particles_in, particle_stride, field, field_layout, params,
+                                  n_particles, n_beams, nx, ny, nz, particles_out, nullptr, &f, s);
   } else {
     const ch::GatherFusion<double> f{static_cast<const double*>(records), record_stride,
                                      static_cast<const double*>(survival), survival_stride,
                                      next_stats, in_kernel_params, in, next_nx, next_ny, next_nz};
-    status = launch_gather<double>(particles_in, particle_stride, field, params, n_particles,
-                                   n_beams, nx, ny, nz, particles_out, nullptr, &f, s);
+    status = launch_gather<double>(particles_in, particle_stride, field, field_layout, params,
+                                   n_particles, n_beams, nx, ny, nz, particles_out, nullptr, &f,
+                                   s);
   }
   if (status != CH_OK || !separate_params) return status;
   const unsigned blocks = static_cast<unsigned>((n_beams + 127) / 128);

@@ -98,8 +98,17 @@ class Workspace:
         )
         self.rho_spectrum = torch.empty(spectrum, dtype=cdtype, device=device)
         self.phi = torch.empty((n_beams, nx, ny, nz), dtype=dtype, device=device)
-        self.field = torch.empty((n_beams, nx, ny, nz, 2, 4), dtype=dtype, device=device)
+        # float32: "bricks" (all 8 corners of a cell side by side, ch_sc_field_bricks);
+        # float64: z corner pairs per node (ch_sc_field)
+        self.bricks = dtype == torch.float32 and use_field_bricks
+        if self.bricks:
+            self.field = torch.empty((n_beams, nx, ny, nz, 3, 8), dtype=dtype, device=device)
+        else:
+            self.field = torch.empty((n_beams, nx, ny, nz, 2, 4), dtype=dtype, device=device)
 
+
+# Set to False to gather from the node layout with float32 beams as well (tests compare both).
+use_field_bricks = True
 
 _workspace_cache: dict = {}
 _side_streams: dict = {}
@@ -116,7 +125,8 @@ def _side_stream(device) -> torch.cuda.Stream:
 def _workspace(n_beams: int, grid_shape: tuple, dtype, device) -> Workspace:
     """One cached workspace per (batch, grid, dtype, device, stream): kicks on a stream are
     ordered, so the scratch of the previous kick is free when the next one starts."""
-    key = (n_beams, tuple(grid_shape), dtype, device, torch.cuda.current_stream(device).cuda_stream)
+    key = (n_beams, tuple(grid_shape), dtype, device,
+           torch.cuda.current_stream(device).cuda_stream, use_field_bricks)
     ws = _workspace_cache.get(key)
     if ws is None:
         if len(_workspace_cache) >= 4:
@@ -195,7 +205,8 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
             ws.params.data_ptr(), n_beams, nx, ny, nz, code, ws.lattice.data_ptr(),
             _capi.ptr(ws.green), side.cuda_stream))
         _capi.check(lib.ch_sc_green_spectrum(
-            ws.lattice.data_ptr(), n_beams, nx, ny, nz, code, ws.green_scratch.data_ptr(),
+            ws.lattice.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
+            ws.green_scratch.data_ptr(),
             ws.green_spectrum.data_ptr(), side.cuda_stream))
         joined = torch.cuda.Event()
         joined.record(side)
@@ -206,12 +217,15 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
         _capi.check(lib.ch_sc_poisson_solve(
             ws.rho_quad.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
             nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))
-        _capi.check(lib.ch_sc_field(
+        field_kernel = lib.ch_sc_field_bricks if ws.bricks else lib.ch_sc_field
+        layout = _capi.SC_FIELD_BRICKS if ws.bricks else _capi.SC_FIELD_NODES
+        _capi.check(field_kernel(
             ws.phi.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
             ws.field.data_ptr(), stream))
         if fuse_records is None and next_element is None:
             _capi.check(lib.ch_sc_gather_kick(
-                p.data_ptr(), p_stride, ws.field.data_ptr(), ws.params.data_ptr(), n, n_beams,
+                p.data_ptr(), p_stride, ws.field.data_ptr(), layout, ws.params.data_ptr(), n,
+                n_beams,
                 nx, ny, nz, code, out.data_ptr(), _capi.ptr(forces), stream))
         else:
             nxt = None
@@ -228,7 +242,8 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
             if fuse_records is not None and fuse_records.shape[0] > 1:
                 record_stride = fuse_records.shape[1]
             _capi.check(lib.ch_sc_gather_kick_fused(
-                p.data_ptr(), p_stride, ws.field.data_ptr(), ws.params.data_ptr(), n, n_beams,
+                p.data_ptr(), p_stride, ws.field.data_ptr(), layout, ws.params.data_ptr(), n,
+                n_beams,
                 nx, ny, nz, code,
                 _capi.ptr(fuse_records), record_stride, w.data_ptr(), w_stride,
                 ws.stats_slots[next_slot].data_ptr() if nxt else None,

@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 /* 2: non-linear tracking, diagnostics, fused gather, quad-block charge grid (ch_sc_deposit) */
-#define CH_ABI_VERSION 2
+#define CH_ABI_VERSION 3
 
 enum { CH_F32 = 0, CH_F64 = 1 };
 
@@ -364,7 +364,17 @@ int ch_apply_maps_covariance(const void* particles_in, int64_t particle_stride, 
  * Grid sizes nx, ny, nz must be powers of two in [4, 256] (the doubled FFT length <= 512).
  * Batch strides are in elements per beam; 0 shares one array among all beams.           */
 #define CH_SC_STATS 12
-#define CH_SC_PARAMS 16
+#define CH_SC_PARAMS 24
+/* params 16-23 (derived, written with the rest): 16 gamma beta, 17 1 / (gamma beta),
+ * 18 e dt / (m c) (momentum change in units of m c per unit of field), 19-21 1 / cell size in
+ * the beam dtype, 22-23 reserved.                                                           */
+
+/* Layout of the field array read by ch_sc_gather_kick*:
+ *   CH_SC_FIELD_NODES   ch_sc_field:        [B][nx*ny*nz][2][4], z corner pairs (any dtype)
+ *   CH_SC_FIELD_BRICKS  ch_sc_field_bricks: [B][nx*ny*nz][3][8], all 8 corners of a cell side by
+ *                       side (float32 only)                                                  */
+#define CH_SC_FIELD_NODES 0
+#define CH_SC_FIELD_BRICKS 1
 
 /* Survival-weighted sums for the unbiased weighted standard deviations of x, y, tau:
  * ParticleBeam.sigma_{x,y,tau} (cheetah/particles/particle_beam.py:1709-1717, :1761-1765,
@@ -441,7 +451,10 @@ int ch_cic_deposit(const void* positions, const void* extent, const void* charge
  * half-shifted lattice point in fp64 (lattice [B][(nx+1)(ny+1)(nz+1)] doubles; the reference
  * evaluates it 8 n^3 times).  If `green` is not NULL the differenced, mirrored array
  * [B][2nx][2ny][2nz] of the reference is also written (plane n of every axis zero) -- used by
- * the parity tests; the solver itself only needs the lattice.  d_tau is scaled by gamma.   */
+ * the parity tests; the solver itself only needs the lattice.  d_tau is scaled by gamma.
+ * float32 beams: lattice points further than 6 x the largest cell size from the origin are not
+ * written -- their Green function is the 4th-order far-field series of the cell integral
+ * (truncation < 5e-8, below float32 resolution), evaluated by the consumers of the lattice. */
 int ch_sc_green_function(const double* params, int64_t n_beams,
                          int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                          double* lattice, void* green, void* stream);
@@ -449,8 +462,9 @@ int ch_sc_green_function(const double* params, int64_t n_beams,
 /* rfftn of the mirrored Green array without ever building it: the array is even in every axis,
  * so its spectrum is real and even and is stored compactly as spectrum [B][nx+1][ny+1][nz+1]
  * (3 passes of packed real-even FFTs, ~4x less work than a general rfftn).
- * scratch: B * (nx*ny*(nz+1) + nx*(ny+1)*(nz+1)) scalars of the beam dtype.                 */
-int ch_sc_green_spectrum(const double* lattice, int64_t n_beams,
+ * scratch: B * (nx*ny*(nz+1) + nx*(ny+1)*(nz+1)) scalars of the beam dtype.  `params` as given
+ * to ch_sc_green_function (cell sizes decide where the far-field series applies).            */
+int ch_sc_green_spectrum(const double* lattice, const double* params, int64_t n_beams,
                          int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                          void* scratch, void* spectrum, void* stream);
 
@@ -473,15 +487,25 @@ int ch_sc_poisson_solve(const void* rho, const void* green_spectrum, const doubl
 int ch_sc_field(const void* phi, const double* params, int64_t n_beams,
                 int32_t nx, int32_t ny, int32_t nz, int32_t dtype, void* field, void* stream);
 
+/* The same field as "bricks" (float32 only): bricks [B][nx][ny][nz][3][8] holds, per cell
+ * (cx, cy, cz), component s of the field at the eight nodes (cx + dx, cy + dy, cz + dz), corner
+ * index 4 dx + 2 dy + dz, zero for nodes beyond the grid: the 96 bytes one particle of that cell
+ * gathers, contiguous (3 sectors in 1-2 cache lines instead of 4 sectors in 4 lines).       */
+int ch_sc_field_bricks(const void* phi, const double* params, int64_t n_beams,
+                       int32_t nx, int32_t ny, int32_t nz, int32_t dtype, void* bricks,
+                       void* stream);
+
 /* Node-centred trilinear gather of the field at the 8 surrounding grid points x elementary
  * charge (_compute_forces, space_charge_kick.py:367-475), momentum kick P += F dt
  * (:557-565) and both coordinate conversions ParticleBeam.to_xyz_pxpypz /
  * from_xyz_pxpypz (cheetah/particles/particle_beam.py:1262-1346), fused: one read and one
- * write of the particles.  The SI round trip is evaluated in fp64 (the reference's fp32
- * version squares momenta of 1e-20 kg m/s into the subnormal range).
+ * write of the particles.  float64 beams evaluate the SI round trip as the reference does;
+ * float32 beams use the algebraically equal difference form (the change of each coordinate;
+ * the reference's fp32 version squares momenta of 1e-20 kg m/s into the subnormal range,
+ * SURVEY.md 7.3).  `field` / `field_layout`: see CH_SC_FIELD_*.
  * forces_out (optional, [B][N][3]) receives the interpolated forces for tests.          */
 int ch_sc_gather_kick(const void* particles_in, int64_t particle_stride,
-                      const void* field, const double* params,
+                      const void* field, int32_t field_layout, const double* params,
                       int64_t n_particles, int64_t n_beams,
                       int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                       void* particles_out, void* forces_out, void* stream);
@@ -497,7 +521,7 @@ int ch_sc_gather_kick(const void* particles_in, int64_t particle_stride,
  *    parameters next_params -- what ch_sc_moments_and_params would compute in a separate pass
  *    (space_charge_kick.py:531-550).  next_* describe that next kick; energy / mass as there.    */
 int ch_sc_gather_kick_fused(const void* particles_in, int64_t particle_stride,
-                            const void* field, const double* params,
+                            const void* field, int32_t field_layout, const double* params,
                             int64_t n_particles, int64_t n_beams,
                             int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                             const void* records, int64_t record_stride,

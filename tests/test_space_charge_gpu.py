@@ -333,3 +333,87 @@ def test_cold_uniform_bunch_doubles_in_size(energy):
     for name in ("sigma_x", "sigma_y", "sigma_tau"):
         ratio = float(getattr(outgoing, name) / getattr(incoming, name))
         assert abs(ratio / 2.0 - 1.0) < 2e-2, (name, ratio)
+
+
+@pytest.mark.parametrize("grid", [(16, 16, 16), (32, 8, 64)])
+def test_brick_gather_equals_node_gather(grid):
+    """float32: ch_sc_field_bricks + the quad-cooperative gather against ch_sc_field + the
+    one-thread-per-particle gather (same trilinear weights and node fields; the sums run in a
+    different order), including particles outside the grid and on its boundary cells."""
+    from cheetah_b200 import space_charge
+
+    torch.manual_seed(4)
+    dtype = torch.float32
+    n = 30_011  # ragged last tile
+    sigma = torch.tensor([2e-4, 3e-6, 1e-4, 5e-6, 1e-5, 1e-3], dtype=dtype)
+    particles = torch.randn((2, n, 7), dtype=dtype) * torch.cat([sigma, torch.ones(1)])
+    particles[..., 6] = 1.0
+    particles[0, :64, 0] *= 5.0  # far outside the 3-sigma grid
+    to = lambda t: t.to(DEVICE)  # noqa: E731
+    args = (
+        to(particles), torch.tensor(4e7, dtype=dtype, device=DEVICE),
+        torch.full((2, n), 1e-10 / n, dtype=dtype, device=DEVICE),
+        torch.ones((2, n), dtype=dtype, device=DEVICE),
+        torch.tensor(510998.95, dtype=dtype, device=DEVICE),
+        torch.tensor(0.4, dtype=dtype, device=DEVICE),
+        tuple(torch.tensor(3.0, dtype=dtype, device=DEVICE) for _ in range(3)), grid,
+    )
+    results = {}
+    for bricks in (True, False):
+        space_charge.use_field_bricks = bricks
+        try:
+            out, ws = space_charge.kick(*args, want_intermediates=True)
+            torch.cuda.synchronize()
+            assert ws.bricks == bricks
+            results[bricks] = (out.clone(), ws.forces.clone())
+        finally:
+            space_charge.use_field_bricks = True
+    force_scale = results[False][1].abs().max()
+    assert float((results[True][1] - results[False][1]).abs().max() / force_scale) < 5e-6
+    kick_nodes = results[False][0] - to(particles)
+    kick_bricks = results[True][0] - to(particles)
+    for col in (1, 3, 5):
+        scale = kick_nodes[..., col].abs().max()
+        assert float((kick_bricks[..., col] - kick_nodes[..., col]).abs().max() / scale) < 1e-5
+    for col in (0, 2, 4, 6):
+        assert torch.equal(results[True][0][..., col], to(particles)[..., col])
+
+
+def test_far_field_green_function_matches_the_exact_one(monkeypatch):
+    """float32 beams take the Green function of far cells from the 4th-order series of the cell
+    integral; compare the mirrored array with the one built from exact 8-corner differences
+    (float64 beam, same geometry)."""
+    from cheetah_b200 import space_charge
+
+    torch.manual_seed(5)
+    n = 20_000
+    grid = (32, 32, 32)
+    greens = {}
+    sigma = torch.tensor([2e-4, 3e-6, 1.5e-4, 5e-6, 8e-6, 1e-3], dtype=torch.float64)
+    particles = torch.randn((n, 7), dtype=torch.float64) * torch.cat([sigma, torch.ones(1)])
+    particles[..., 6] = 1.0
+    for dtype in (torch.float32, torch.float64):
+        out, ws = space_charge.kick(
+            particles.to(DEVICE, dtype), torch.tensor(1e8, dtype=dtype, device=DEVICE),
+            torch.full((n,), 1e-10 / n, dtype=dtype, device=DEVICE),
+            torch.ones((n,), dtype=dtype, device=DEVICE),
+            torch.tensor(510998.95, dtype=dtype, device=DEVICE),
+            torch.tensor(1.0, dtype=dtype, device=DEVICE),
+            tuple(torch.tensor(3.0, dtype=dtype, device=DEVICE) for _ in range(3)), grid,
+            want_intermediates=True,
+        )
+        torch.cuda.synchronize()
+        greens[dtype] = ws.green.double().cpu()
+        cells = ws.params[0, 3:6].cpu()
+    # the two beams have (almost) the same sigma, hence the same cells up to float32 rounding:
+    # compare point by point relative to the local value (the far field is much smaller than G[0])
+    exact, approx = greens[torch.float64], greens[torch.float32]
+    mask = exact != 0
+    rel = ((approx - exact).abs() / exact.abs().clamp_min(1e-300))[mask]
+    assert float(rel.max()) < 5e-6, float(rel.max())  # sigma rounding dominates (1e-6)
+    # aspect ratio of this beam: most of the lattice must have been far field
+    gamma = 1e8 / 510998.95
+    h = torch.tensor([float(cells[0]), float(cells[1]), float(cells[2]) * gamma])
+    idx = torch.stack(torch.meshgrid(*(torch.arange(32.0),) * 3, indexing="ij"), dim=-1)
+    far = ((idx * h) ** 2).sum(-1) >= (6.0 * h.max()) ** 2
+    assert float(far.float().mean()) > 0.5
