@@ -139,21 +139,31 @@ def stage_table(beam, grid: int, reps: int | None = None) -> list[dict]:
                 grid, grid, grid, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream),
             B * (int(spectrum_bytes * (0.25 + 0.5 + 0.5 + 1.0 + 0.5 + 0.5 + 0.25)) + cells3 * 12),
             "the passes touch 1/4 .. 1 of the (2n)^2 (n+1) complex spectrum, read + write"),
-        "field": (
-            "sc_field_brick_kernel" if ws.bricks else "sc_field_kernel",
-            lambda: (lib.ch_sc_field_bricks if ws.bricks else lib.ch_sc_field)(
-                ws.phi.data_ptr(), ws.params.data_ptr(), B, grid, grid, grid, code,
-                ws.field.data_ptr(), stream),
-            B * cells3 * (4 + (96 if ws.bricks else 32)),
-            "phi read + 96-byte bricks written" if ws.bricks else "phi read + z-paired field write"),
-        "gather": (
-            "sc_gather_brick_kernel" if ws.bricks else "sc_gather_kick_kernel",
-            lambda: lib.ch_sc_gather_kick(
-                pp.data_ptr(), ps, ws.field.data_ptr(),
-                _capi.SC_FIELD_BRICKS if ws.bricks else _capi.SC_FIELD_NODES,
-                ws.params.data_ptr(), n, B, grid, grid, grid, code, out.data_ptr(), None, stream),
-            B * n * 56, "28 B row read + 28 B row written per particle (gathers hit L1/L2)"),
     }
+    if ws.bricks:
+        null = (None, 0, None, 0, None, None, None, 0, code, None, code, None, 0, code,
+                None, 0, None, 0, None, 0, code, grid, grid, grid)
+        stages["field_gather"] = (
+            "sc_field_brick_kernel + sc_gather_brick_kernel per group of "
+            f"{ws.group_beams} beam(s) (ch_sc_field_gather, nothing fused)",
+            lambda: lib.ch_sc_field_gather(
+                pp.data_ptr(), ps, ws.phi.data_ptr(), ws.field.data_ptr(), ws.group_beams,
+                ws.params.data_ptr(), n, B, grid, grid, grid, code, *null, out.data_ptr(), None,
+                stream),
+            B * (n * 56 + cells3 * 4),
+            "phi read; 28 B row read + 28 B row written per particle (96-byte bricks stay in L2)")
+    else:
+        stages["field"] = (
+            "sc_field_kernel",
+            lambda: lib.ch_sc_field(ws.phi.data_ptr(), ws.params.data_ptr(), B, grid, grid, grid,
+                                    code, ws.field.data_ptr(), stream),
+            B * cells3 * (4 + 32), "phi read + z-paired field write")
+        stages["gather"] = (
+            "sc_gather_kick_kernel",
+            lambda: lib.ch_sc_gather_kick(
+                pp.data_ptr(), ps, ws.field.data_ptr(), _capi.SC_FIELD_NODES,
+                ws.params.data_ptr(), n, B, grid, grid, grid, code, out.data_ptr(), None, stream),
+            B * n * 56, "28 B row read + 28 B row written per particle (gathers hit L1/L2)")
     peak, _ = hbm_peak()
     traffic = {}
     traffic_path = REPO / "profiles" / "sc_traffic.json"

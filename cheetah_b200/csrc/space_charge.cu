@@ -1210,10 +1210,21 @@ sc_field_kernel(const T* __restrict__ phi, const double* __restrict__ params, in
 //  * the survival-weighted sums of the NEXT SpaceChargeKick (ch_sc_moments_and_params) on the
 //    outgoing coordinates, and, in the last CTA of a beam, its grid parameters -- saves the
 //    moments pass (32 B read per particle) and a launch.
+// Maps of the linear section fused into the float32 brick gather: copied device-to-device into
+// constant memory before the launch, so that the 42 coefficients reach the FMAs through the
+// uniform datapath (ULDC) instead of 12 shared-memory loads per particle -- the shared-memory /
+// L1 data stage was the busiest unit of the kernel (72 %, a third of it these loads).  One
+// buffer per device: like the reference ("not thread-safe by construction"), two host
+// threads must not track space charge on the same device at the same time.
+constexpr int kConstMaps = 256;
+constexpr int kConstMapPitch = 44;  // 42 coefficients, rows of 7
+__constant__ float c_gather_maps[kConstMaps * kConstMapPitch];
+
 template <typename T>
 struct GatherFusion {
   const T* records;       // null: no map
   int64_t record_stride;  // 0: one record for all beams
+  int const_maps;         // the maps are in c_gather_maps (float32 brick gather)
   const T* survival;      // weights of the fused moments (null: ones)
   int64_t survival_stride;
   double* next_stats;     // null: no fused moments
@@ -1251,6 +1262,17 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
     fence_mbar_init();
   }
   __syncthreads();
+  // weights of the fused moments: fetched now, their DRAM latency overlaps the tile copy
+  T survival[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    survival[k] = T(1);
+    if constexpr (FUSED) {
+      const int local = threadIdx.x + k * THREADS;
+      if (fusion.next_stats != nullptr && fusion.survival != nullptr && local < count)
+        survival[k] = fusion.survival[b * fusion.survival_stride + n0 + local];
+    }
+  }
   uint32_t phase = 0;
   cta_load_tile(tile, particles_in + b * particle_stride + n0 * 7, count * 7, bulk_in != 0, &bar,
                 phase);
@@ -1417,8 +1439,7 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
         // sums about the origin (ch_sc_beam_moments uses a pilot particle): four terms per thread
         // in the beam dtype, then fp64 -- the rounding of the partial sums averages out over the
         // ~N / 4 threads of a beam (relative error of the variance ~1e-10 (mean / sigma)^2)
-        const T wi = fusion.survival ? fusion.survival[b * fusion.survival_stride + n0 + local]
-                                     : T(1);
+        const T wi = survival[k];
         const T dx = row[0], dy = row[2], dt = row[4];
         acc8[0] += wi;
         acc8[1] = fma(wi, wi, acc8[1]);
@@ -1486,20 +1507,25 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
 }
 
 // ---------------------------------------------------------------------------------------
-// 6b / 7b. float32: field bricks and the quad-cooperative gather
+// 6b / 7b. float32: field bricks and the gather that reads them
 // ---------------------------------------------------------------------------------------
-// ncu on sc_gather_kick_kernel<float> (profiles/r02_gather_nodes_deposit_ncu_full.txt): 514 instructions per
-// particle at 45 % issue utilisation with the L1 data stage 71 % busy -- every particle pulls four
-// 32-byte sectors out of four different 128-byte lines, one thread waits for all of them, and half
-// of the instructions are index arithmetic, clamps and predicates.  This pair of kernels changes
-// the data layout and the thread mapping:
+// ncu on sc_gather_kick_kernel<float> (profiles/r02_gather_nodes_deposit_ncu_full.txt): 514
+// instructions per particle at 45 % issue utilisation, the L1 data stage 71 % busy -- every
+// particle pulls four 32-byte sectors out of four different 128-byte lines.  Bricks put what one
+// particle needs side by side:
 //   brick[b][cx][cy][cz] = float[3][8]  (96 bytes): E_component[s] at the eight nodes
-//   (cx + dx, cy + dy, cz + dz), corner q = 4 dx + 2 dy + dz, zero for nodes beyond the grid --
-//   everything one particle needs, contiguous: 3 sectors in 1.5 lines on average;
-//   the four lanes of a quad take turns: in turn t the quad serves the particle owned by its lane
-//   t, lane s < 3 fetching the sector of component s with ONE 256-bit load and contracting it
-//   with the eight trilinear weights (broadcast from the owner with shuffles), so one load
-//   instruction of a warp covers 8 particles in 8-16 lines instead of 32 particles in 32 lines.
+//   (cx + dx, cy + dy, cz + dz), corner q = 4 dx + 2 dy + dz, zero for nodes beyond the grid:
+//   3 sectors in 1.5 lines on average, three 256-bit loads, no clamping of corner indices.
+// Together with (a) the per-particle survival weights fetched before the tile wait instead of
+// inside the loop (one exposed DRAM latency per particle before), (b) the map of the fused
+// linear section read through the uniform datapath from constant memory, (c) float32 warp sums
+// of the fused moments, the fused pass went from 3.9 to 2.6 ms for 128 beams x 1e6 particles.
+// Measured and rejected on the way (128 beams): four lanes per particle, one sector each, weights
+// by shuffle (2.7 ms: fewer L1 wavefronts but 60 shuffles per particle); a two-stage software
+// pipeline at 2 CTAs per SM (3.3 ms); 4 CTAs per SM at 64 registers (2.7-2.9 ms); building and
+// consuming the bricks in L2-sized groups of beams (1 beam per group 5.1 ms, 2: 4.4, all: 3.3
+// including the field pass -- short launches pay their tails, and the gather is bound inside
+// the SM: its time follows the instruction count).
 constexpr int kBrickFloats = 24;
 constexpr int kBrickRows = 8;
 
@@ -1510,10 +1536,12 @@ constexpr int kBrickRows = 8;
 // 16-byte pieces.
 __global__ void __launch_bounds__(256)
 sc_field_brick_kernel(const float* __restrict__ phi, const double* __restrict__ params, int nx,
-                      int ny, int nz, float* __restrict__ bricks) {
+                      int ny, int nz, int beam0, float* __restrict__ bricks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* nodes = reinterpret_cast<float*>(smem_raw);  // [3][2][kBrickRows + 1][nz + 1]
-  const int64_t b = blockIdx.z;
+  // beam blockIdx.z of this launch's group is beam beam0 + blockIdx.z of phi / params; the
+  // bricks buffer holds the group only
+  const int64_t b = blockIdx.z + beam0;
   const int cx = blockIdx.y, y0 = blockIdx.x * kBrickRows;
   const double* prm = params + b * CH_SC_PARAMS;
   const int64_t total = static_cast<int64_t>(nx) * ny * nz;
@@ -1545,7 +1573,7 @@ sc_field_brick_kernel(const float* __restrict__ phi, const double* __restrict__ 
   // are consecutive in memory.  Half h holds corners q = 4 h + (2 dy + dz): dx = h.
   const int rows = min(kBrickRows, ny - y0);
   float4* out = reinterpret_cast<float4*>(
-      bricks + (b * total + (static_cast<int64_t>(cx) * ny + y0) * nz) * kBrickFloats);
+      bricks + (blockIdx.z * total + (static_cast<int64_t>(cx) * ny + y0) * nz) * kBrickFloats);
   const int items = rows * nz * 6;
   for (int t = threadIdx.x; t < items; t += blockDim.x) {
     const int cell = t / 6, sub = t - cell * 6;
@@ -1579,9 +1607,8 @@ __device__ __forceinline__ int brick_axis(float pos, float half_extent, float in
   return min(max(base, 0), n - 1);
 }
 
-// 256-bit load of one brick sector, predicated.  Lanes without work (the fourth lane of a quad,
-// dead particle slots) skip the load and compute on whatever the registers hold: their results
-// are never read.
+// 256-bit load of one brick sector, predicated.  Dead particle slots skip the load and compute on
+// whatever the registers hold: their results are never stored.
 __device__ __forceinline__ void load_sector(const float* src, bool active, float (&e)[8]) {
   asm volatile(
       "{\n"
@@ -1602,7 +1629,7 @@ sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_
                        const float* __restrict__ bricks, const double* __restrict__ params,
                        int64_t n_particles, int nx, int ny, int nz, int bulk_in, int bulk_out,
                        float* __restrict__ particles_out, float* __restrict__ forces_out,
-                       const GatherFusion<float> fusion) {
+                       const GatherFusion<float> fusion, int beam0) {
   constexpr int P = 4, THREADS = 256, TP = P * THREADS;
   constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1611,15 +1638,21 @@ sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_
   __shared__ __align__(16) float map_s[FUSED ? 48 : 1];  // rows padded to 8 for 128-bit loads
   __shared__ double partial[FUSED ? 8 : 1][8];
   if constexpr (FUSED) {
-    if (fusion.records != nullptr && threadIdx.x < 42)
+    if (fusion.records != nullptr && !fusion.const_maps && threadIdx.x < 42)
       map_s[(threadIdx.x / 7) * 8 + threadIdx.x % 7] =
-          fusion.records[blockIdx.y * fusion.record_stride + CH_RECORD_HEADER + threadIdx.x];
+          fusion.records[(blockIdx.y + beam0) * fusion.record_stride + CH_RECORD_HEADER +
+                         threadIdx.x];
   }
-  const int64_t b = blockIdx.y;
+  // beam blockIdx.y of this launch's group is beam b of every per-beam array; the bricks buffer
+  // holds the group only
+  const int64_t b = blockIdx.y + beam0;
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
   const int count = static_cast<int>(min(static_cast<int64_t>(TP), n_particles - n0));
   const double* prm = params + b * CH_SC_PARAMS;
-  const float* grid = bricks + b * static_cast<int64_t>(nx) * ny * nz * kBrickFloats;
+  const float* grid = bricks + blockIdx.y * static_cast<int64_t>(nx) * ny * nz * kBrickFloats;
+  // this beam's map in constant memory (uniform address: ULDC, no shared-memory traffic)
+  const float* cmap =
+      c_gather_maps + (fusion.record_stride == 0 ? 0 : static_cast<int>(b)) * kConstMapPitch;
 
   if (bulk_in && threadIdx.x == 0) {
     mbar_init(&bar, 1);
@@ -1650,58 +1683,50 @@ sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_
                 phase);
 
   const int lane = threadIdx.x & 31;
-  const int quad = lane & ~3, s = lane & 3;
-  const int sector = (s < 3 ? s : 0) * 8;
   float acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // fused moments of the outgoing particles
+
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     const int local = threadIdx.x + k * THREADS;
     const bool live = local < count;
     float* mine = tile + local * 7;
+    float p[7];
+    p[0] = live ? mine[0] : 0.0f;
+    p[2] = live ? mine[2] : 0.0f;
+    p[4] = live ? mine[4] : 0.0f;
     // ---- own particle: brick index and corner weights ----------------------------------------
     float w[6];
-    int cell;
+    const int ix = brick_axis(p[0], gdx, icx, nx, w[0], w[1]);
+    const int iy = brick_axis(p[2], gdy, icy, ny, w[2], w[3]);
+    const int iz = brick_axis(p[4] * minus_beta, gdz, icz, nz, w[4], w[5]);
+    const int cell = live ? (ix * ny + iy) * nz + iz : -1;
+    float fx, fy, fz;
     {
-      const int ix = brick_axis(live ? mine[0] : 0.0f, gdx, icx, nx, w[0], w[1]);
-      const int iy = brick_axis(live ? mine[2] : 0.0f, gdy, icy, ny, w[2], w[3]);
-      const int iz = brick_axis((live ? mine[4] : 0.0f) * minus_beta, gdz, icz, nz, w[4], w[5]);
-      cell = live ? (ix * ny + iy) * nz + iz : -1;
-    }
-    // ---- the quad serves its four particles in turn ------------------------------------------
-    float e[4][8];
+      // one thread per particle: its three sectors with three 256-bit loads
+      float e[3][8];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int o = __shfl_sync(kFull, cell, quad + t);
-      // (a grid has at most 256^3 cells: the float offset fits 32 bits)
-      load_sector(grid + (static_cast<unsigned>(max(o, 0)) * kBrickFloats + sector),
-                  s < 3 && o >= 0, e[t]);
-    }
-    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+      for (int c = 0; c < 3; ++c)
+        load_sector(grid + (static_cast<unsigned>(max(cell, 0)) * kBrickFloats + c * 8), live,
+                    e[c]);
+      p[1] = live ? mine[1] : 0.0f;
+      p[3] = live ? mine[3] : 0.0f;
+      p[5] = live ? mine[5] : 0.0f;
+      p[6] = live ? mine[6] : 0.0f;
+      const float xy00 = w[0] * w[2], xy01 = w[0] * w[3], xy10 = w[1] * w[2], xy11 = w[1] * w[3];
+      float f[3];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float ax0 = __shfl_sync(kFull, w[0], quad + t), ax1 = __shfl_sync(kFull, w[1], quad + t);
-      const float ay0 = __shfl_sync(kFull, w[2], quad + t), ay1 = __shfl_sync(kFull, w[3], quad + t);
-      const float az0 = __shfl_sync(kFull, w[4], quad + t), az1 = __shfl_sync(kFull, w[5], quad + t);
-      // corner q = 4 dx + 2 dy + dz
-      const float xy00 = ax0 * ay0, xy01 = ax0 * ay1, xy10 = ax1 * ay0, xy11 = ax1 * ay1;
-      float acc = xy00 * fmaf(az1, e[t][1], az0 * e[t][0]);
-      acc = fmaf(xy01, fmaf(az1, e[t][3], az0 * e[t][2]), acc);
-      acc = fmaf(xy10, fmaf(az1, e[t][5], az0 * e[t][4]), acc);
-      acc = fmaf(xy11, fmaf(az1, e[t][7], az0 * e[t][6]), acc);
-      // lane s of the quad now holds field component s at the particle of lane t
-      const float vx = __shfl_sync(kFull, acc, quad + 0);
-      const float vy = __shfl_sync(kFull, acc, quad + 1);
-      const float vz = __shfl_sync(kFull, acc, quad + 2);
-      if (t == s) {
-        fx = vx;
-        fy = vy;
-        fz = vz;
+      for (int c = 0; c < 3; ++c) {
+        float acc = xy00 * fmaf(w[5], e[c][1], w[4] * e[c][0]);
+        acc = fmaf(xy01, fmaf(w[5], e[c][3], w[4] * e[c][2]), acc);
+        acc = fmaf(xy10, fmaf(w[5], e[c][5], w[4] * e[c][4]), acc);
+        acc = fmaf(xy11, fmaf(w[5], e[c][7], w[4] * e[c][6]), acc);
+        f[c] = live ? acc : 0.0f;
       }
+      fx = f[0];
+      fy = f[1];
+      fz = f[2];
     }
     // ---- own particle: kick (difference form, see sc_gather_kick_kernel), map, moments -------
-    float p[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) p[j] = live ? mine[j] : 0.0f;
     if (forces_out != nullptr && live) {
       float* f = forces_out + (b * n_particles + n0 + local) * 3;
       f[0] = fx * static_cast<float>(kElementaryCharge);
@@ -1711,36 +1736,52 @@ sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_
     const float dux = fx * du_per_field, duy = fy * du_per_field, duz = fz * du_per_field;
     const float ux = p[1] * bg, uy = p[3] * bg;
     const float gam = fmaf(p[5], bg, gamma0);  // g0 (1 + delta b0)
-    const float uz = sqrtf(fmaxf(fmaf(gam, gam, -1.0f) - ux * ux - uy * uy, 0.0f));
+    // square roots and the division through the special-function unit (2 ulp): u_z and
+    // gamma' + gamma only scale the small change of delta
+    const float uz2 = fmaxf(fmaf(gam, gam, -1.0f) - ux * ux - uy * uy, 1e-30f);
+    const float uz = uz2 * rsqrtf(uz2);
     const float dg2 =
         2.0f * (ux * dux + uy * duy + uz * duz) + (dux * dux + duy * duy + duz * duz);
-    const float gam_new = sqrtf(fmaf(gam, gam, dg2));
+    const float g2 = fmaxf(fmaf(gam, gam, dg2), 1e-30f);
+    const float gam_new = g2 * rsqrtf(g2);
     float row[7];
     row[0] = p[0];
     row[1] = fmaf(dux, inv_bg, p[1]);
     row[2] = p[2];
     row[3] = fmaf(duy, inv_bg, p[3]);
     row[4] = p[4];  // tau = -z / beta with z = -beta tau: unchanged
-    row[5] = p[5] + dg2 / ((gam_new + gam) * bg);
+    row[5] = p[5] + __fdividef(dg2, (gam_new + gam) * bg);
     row[6] = p[6];
+    bool rewrite_positions = false;
     if constexpr (FUSED) {
       if (fusion.records != nullptr) {  // particles @ tm.mT of the following linear section
         float mapped[6];
+        if (fusion.const_maps) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const float4 lo = reinterpret_cast<const float4*>(map_s)[i * 2];
-          const float4 hi = reinterpret_cast<const float4*>(map_s)[i * 2 + 1];
-          float a = hi.z * row[6];
-          a = fmaf(hi.y, row[5], a);
-          a = fmaf(hi.x, row[4], a);
-          a = fmaf(lo.w, row[3], a);
-          a = fmaf(lo.z, row[2], a);
-          a = fmaf(lo.y, row[1], a);
-          a = fmaf(lo.x, row[0], a);
-          mapped[i] = a;
+          for (int i = 0; i < 6; ++i) {
+            float a = cmap[i * 7 + 6] * row[6];
+#pragma unroll
+            for (int j = 5; j >= 0; --j) a = fmaf(cmap[i * 7 + j], row[j], a);
+            mapped[i] = a;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const float4 lo = reinterpret_cast<const float4*>(map_s)[i * 2];
+            const float4 hi = reinterpret_cast<const float4*>(map_s)[i * 2 + 1];
+            float a = hi.z * row[6];
+            a = fmaf(hi.y, row[5], a);
+            a = fmaf(hi.x, row[4], a);
+            a = fmaf(lo.w, row[3], a);
+            a = fmaf(lo.z, row[2], a);
+            a = fmaf(lo.y, row[1], a);
+            a = fmaf(lo.x, row[0], a);
+            mapped[i] = a;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) row[i] = mapped[i];
+        rewrite_positions = true;
       }
       if (fusion.next_stats != nullptr && live) {
         const float wi = survival[k];
@@ -1755,10 +1796,17 @@ sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_
         acc8[7] = fmaf(wi * dt, dt, acc8[7]);
       }
     }
-    // a row of the tile is only ever touched by the thread that owns the particle
+    // a row of the tile is only ever touched by the thread that owns the particle; without a
+    // map only the momenta change
     if (live) {
-#pragma unroll
-      for (int j = 0; j < 6; ++j) mine[j] = row[j];
+      mine[1] = row[1];
+      mine[3] = row[3];
+      mine[5] = row[5];
+      if (rewrite_positions) {
+        mine[0] = row[0];
+        mine[2] = row[2];
+        mine[4] = row[4];
+      }
     }
   }
   float* dst = particles_out + (b * n_particles + n0) * 7;
@@ -1777,11 +1825,15 @@ sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_
   if constexpr (FUSED) {
     if (fusion.next_stats == nullptr) return;
     double* stats = fusion.next_stats + b * CH_SC_STATS;
+    // 128 terms per warp in float32 (their rounding averages out over the ~N / 128 warps of a
+    // beam like that of the per-thread sums), float64 across warps and CTAs
     const int warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const double sum = warp_sum(static_cast<double>(acc8[k]));
-      if (lane == 0) partial[warp][k] = sum;
+      float sum = acc8[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+      if (lane == 0) partial[warp][k] = static_cast<double>(sum);
     }
     __syncthreads();
     if (threadIdx.x < 8) {
@@ -2395,6 +2447,11 @@ extern "C" int ch_sc_field(const void* phi, const double* params, int64_t n_beam
   return CH_OK;
 }
 
+namespace {
+int launch_field_bricks(const float* phi, const double* params, int beam0, int group, int nx,
+                        int ny, int nz, float* bricks, cudaStream_t s);
+}
+
 extern "C" int ch_sc_field_bricks(const void* phi, const double* params, int64_t n_beams,
                                   int32_t nx, int32_t ny, int32_t nz, int32_t dtype, void* bricks,
                                   void* stream) {
@@ -2402,43 +2459,60 @@ extern "C" int ch_sc_field_bricks(const void* phi, const double* params, int64_t
   CH_REQUIRE(dtype == CH_F32, "ch_sc_field_bricks: float32 only (float64 uses ch_sc_field)");
   CH_REQUIRE(phi && params && bricks, "ch_sc_field_bricks: NULL pointer argument");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_field_bricks: bad grid (%d, %d, %d)", nx, ny, nz);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = sizeof(float) * 3 * 2 * (ch::kBrickRows + 1) * (nz + 1);
-  if (ch::allow_smem(ch::sc_field_brick_kernel, smem) != CH_OK) return CH_ECUDA;
-  dim3 grid((ny + ch::kBrickRows - 1) / ch::kBrickRows, nx, static_cast<unsigned>(n_beams));
-  ch::sc_field_brick_kernel<<<grid, 256, smem, s>>>(static_cast<const float*>(phi), params, nx, ny,
-                                                    nz, static_cast<float*>(bricks));
+  return launch_field_bricks(static_cast<const float*>(phi), params, 0, static_cast<int>(n_beams),
+                             nx, ny, nz, static_cast<float*>(bricks),
+                             static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+// Brick gather of `group` beams starting at beam0 (the bricks buffer holds that group).
+int launch_gather_bricks(const float* particles_in, int64_t particle_stride, const float* bricks,
+                         const double* params, int64_t n_particles, int beam0, int group, int nx,
+                         int ny, int nz, float* particles_out, float* forces_out,
+                         const ch::GatherFusion<float>* fusion, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(group));
+  const int bulk_in = ch::bulk_compatible<float>(particles_in, n_particles, particle_stride);
+  const int bulk_out = ch::bulk_compatible<float>(particles_out, n_particles, n_particles * 7);
+  const size_t smem = 1024 * 7 * sizeof(float);
+  auto launch = [&](auto kernel, const ch::GatherFusion<float>& f) {
+    kernel<<<grid, 256, smem, s>>>(particles_in, particle_stride, bricks, params, n_particles, nx,
+                                   ny, nz, bulk_in, bulk_out, particles_out, forces_out, f, beam0);
+  };
+  const ch::GatherFusion<float> none{};
+  fusion ? launch(ch::sc_gather_brick_kernel<true>, *fusion)
+         : launch(ch::sc_gather_brick_kernel<false>, none);
   CH_LAUNCH_CHECK();
   return CH_OK;
 }
 
-namespace {
+int launch_field_bricks(const float* phi, const double* params, int beam0, int group, int nx,
+                        int ny, int nz, float* bricks, cudaStream_t s) {
+  const size_t smem = sizeof(float) * 3 * 2 * (ch::kBrickRows + 1) * (nz + 1);
+  if (ch::allow_smem(ch::sc_field_brick_kernel, smem) != CH_OK) return CH_ECUDA;
+  dim3 grid((ny + ch::kBrickRows - 1) / ch::kBrickRows, nx, static_cast<unsigned>(group));
+  ch::sc_field_brick_kernel<<<grid, 256, smem, s>>>(phi, params, nx, ny, nz, beam0, bricks);
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
 template <typename T>
 int launch_gather(const void* particles_in, int64_t particle_stride, const void* field,
                   int field_layout, const double* params, int64_t n_particles, int64_t n_beams,
                   int nx, int ny, int nz, void* particles_out, void* forces_out,
                   const ch::GatherFusion<T>* fusion, cudaStream_t s) {
   using F4 = typename ch::Field4<T>::type;
+  if constexpr (std::is_same<T, float>::value) {
+    if (field_layout == CH_SC_FIELD_BRICKS)
+      return launch_gather_bricks(static_cast<const float*>(particles_in), particle_stride,
+                                  static_cast<const float*>(field), params, n_particles, 0,
+                                  static_cast<int>(n_beams), nx, ny, nz,
+                                  static_cast<float*>(particles_out),
+                                  static_cast<float*>(forces_out), fusion, s);
+  }
   dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(n_beams));
   const int bulk_in = ch::bulk_compatible<T>(particles_in, n_particles, particle_stride);
   const int bulk_out = ch::bulk_compatible<T>(particles_out, n_particles, n_particles * 7);
   const size_t smem = 1024 * 7 * sizeof(T);
-  if constexpr (std::is_same<T, float>::value) {
-    if (field_layout == CH_SC_FIELD_BRICKS) {
-      auto launch_bricks = [&](auto kernel, const ch::GatherFusion<float>& f) -> int {
-        kernel<<<grid, 256, smem, s>>>(static_cast<const float*>(particles_in), particle_stride,
-                                       static_cast<const float*>(field), params, n_particles, nx,
-                                       ny, nz, bulk_in, bulk_out,
-                                       static_cast<float*>(particles_out),
-                                       static_cast<float*>(forces_out), f);
-        return CH_OK;
-      };
-      fusion ? launch_bricks(ch::sc_gather_brick_kernel<true>, *fusion)
-             : launch_bricks(ch::sc_gather_brick_kernel<false>, ch::GatherFusion<float>{});
-      CH_LAUNCH_CHECK();
-      return CH_OK;
-    }
-  }
   auto launch = [&](auto kernel, const ch::GatherFusion<T>& f) -> int {
     CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
@@ -2451,6 +2525,102 @@ int launch_gather(const void* particles_in, int64_t particle_stride, const void*
   const int status = fusion ? launch(ch::sc_gather_kick_kernel<T, true>, *fusion)
                             : launch(ch::sc_gather_kick_kernel<T, false>, ch::GatherFusion<T>{});
   if (status != CH_OK) return status;
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+// What the two fused entry points share.  `phi` != NULL: float32, field bricks built per group of
+// `group_beams` beams into `field` (a buffer for one group) right before the group's gather, so
+// that the bricks are read back from L2, not from HBM.
+struct FusedArgs {
+  const void* particles_in;
+  int64_t particle_stride;
+  const void* field;
+  int32_t field_layout;
+  const float* phi;
+  int32_t group_beams;
+  const double* params;
+  int64_t n_particles, n_beams;
+  int32_t nx, ny, nz, dtype;
+  const void* records;
+  int64_t record_stride;
+  const void* survival;
+  int64_t survival_stride;
+  double* next_stats;
+  double* next_params;
+  ch::GridInputs next_in;
+  int32_t next_nx, next_ny, next_nz;
+  void* particles_out;
+  void* forces_out;
+};
+
+int gather_fused(const FusedArgs& a, cudaStream_t s) {
+  const bool fused = a.records != nullptr || a.next_stats != nullptr;
+  if (a.next_stats != nullptr)
+    CH_CUDA(cudaMemsetAsync(a.next_stats, 0, sizeof(double) * CH_SC_STATS * a.n_beams, s));
+  int const_maps = 0;
+  if (a.dtype == CH_F32 && a.field_layout == CH_SC_FIELD_BRICKS && a.records != nullptr) {
+    const int64_t n_maps = a.record_stride == 0 ? 1 : a.n_beams;
+    if (n_maps <= ch::kConstMaps) {
+      void* symbol = nullptr;
+      CH_CUDA(cudaGetSymbolAddress(&symbol, ch::c_gather_maps));
+      CH_CUDA(cudaMemcpy2DAsync(
+          symbol, sizeof(float) * ch::kConstMapPitch,
+          static_cast<const float*>(a.records) + CH_RECORD_HEADER,
+          sizeof(float) * (a.record_stride == 0 ? CH_RECORD_MAP : a.record_stride),
+          sizeof(float) * CH_RECORD_MAP, static_cast<size_t>(n_maps), cudaMemcpyDeviceToDevice, s));
+      const_maps = 1;
+    }
+  }
+  // several waves of CTAs: grid parameters in a follow-up launch instead of a last-CTA epilogue
+  const int64_t ctas = ((a.n_particles + 1023) / 1024) * a.n_beams;
+  const bool separate_params = a.next_stats != nullptr && ctas > 148 * 3 * 4;
+  double* in_kernel_params = separate_params ? nullptr : a.next_params;
+  int status;
+  if (a.dtype == CH_F32) {
+    const ch::GatherFusion<float> f{static_cast<const float*>(a.records), a.record_stride,
+                                    const_maps, static_cast<const float*>(a.survival),
+                                    a.survival_stride, a.next_stats, in_kernel_params, a.next_in,
+                                    a.next_nx, a.next_ny, a.next_nz};
+    if (a.phi != nullptr) {
+      status = CH_OK;
+      const int group = a.group_beams < 1 ? 1 : a.group_beams;
+      for (int64_t beam0 = 0; beam0 < a.n_beams && status == CH_OK; beam0 += group) {
+        const int g = static_cast<int>(a.n_beams - beam0 < group ? a.n_beams - beam0 : group);
+        float* bricks = static_cast<float*>(const_cast<void*>(a.field));
+        status = launch_field_bricks(a.phi, a.params, static_cast<int>(beam0), g, a.nx, a.ny,
+                                     a.nz, bricks, s);
+        if (status != CH_OK) break;
+        status = launch_gather_bricks(static_cast<const float*>(a.particles_in),
+                                      a.particle_stride, bricks, a.params, a.n_particles,
+                                      static_cast<int>(beam0), g, a.nx, a.ny, a.nz,
+                                      static_cast<float*>(a.particles_out),
+                                      static_cast<float*>(a.forces_out), fused ? &f : nullptr, s);
+      }
+    } else {
+      status = launch_gather<float>(a.particles_in, a.particle_stride, a.field, a.field_layout,
+                                    a.params, a.n_particles, a.n_beams, a.nx, a.ny, a.nz,
+                                    a.particles_out, a.forces_out, fused ? &f : nullptr, s);
+    }
+  } else {
+    const ch::GatherFusion<double> f{static_cast<const double*>(a.records), a.record_stride, 0,
+                                     static_cast<const double*>(a.survival), a.survival_stride,
+                                     a.next_stats, in_kernel_params, a.next_in, a.next_nx,
+                                     a.next_ny, a.next_nz};
+    status = launch_gather<double>(a.particles_in, a.particle_stride, a.field, a.field_layout,
+                                   a.params, a.n_particles, a.n_beams, a.nx, a.ny, a.nz,
+                                   a.particles_out, a.forces_out, fused ? &f : nullptr, s);
+  }
+  if (status != CH_OK || !separate_params) return status;
+  const unsigned blocks = static_cast<unsigned>((a.n_beams + 127) / 128);
+  if (a.dtype == CH_F32)
+    ch::sc_grid_params_kernel<float><<<blocks, 128, 0, s>>>(a.next_stats, a.n_beams, a.next_in,
+                                                            a.next_nx, a.next_ny, a.next_nz,
+                                                            a.next_params);
+  else
+    ch::sc_grid_params_kernel<double><<<blocks, 128, 0, s>>>(a.next_stats, a.n_beams, a.next_in,
+                                                             a.next_nx, a.next_ny, a.next_nz,
+                                                             a.next_params);
   CH_LAUNCH_CHECK();
   return CH_OK;
 }
@@ -2481,16 +2651,32 @@ extern "C" int ch_sc_gather_kick(const void* particles_in, int64_t particle_stri
                                nullptr, s);
 }
 
+#define CH_SC_NEXT_CHECKS(fn)                                                                   \
+  if (next_stats != nullptr) {                                                                  \
+    CH_REQUIRE(next_params && energy && mass_eV && next_effect_length && next_extent_x &&       \
+                   next_extent_y && next_extent_tau,                                            \
+               fn ": NULL pointer among the next kick's inputs");                               \
+    CH_REQUIRE(ch::grid_ok(next_nx, next_ny, next_nz), fn ": bad next grid (%d, %d, %d)",       \
+               next_nx, next_ny, next_nz);                                                      \
+  }                                                                                             \
+  const ch::GridInputs next_in{{energy, energy_stride, energy_dtype},                           \
+                               {mass_eV, 0, mass_dtype},                                        \
+                               {next_effect_length, next_length_stride, next_length_dtype},     \
+                               {next_extent_x, next_extent_x_stride, next_extent_dtype},        \
+                               {next_extent_y, next_extent_y_stride, next_extent_dtype},        \
+                               {next_extent_tau, next_extent_tau_stride, next_extent_dtype}}
+
 extern "C" int ch_sc_gather_kick_fused(
     const void* particles_in, int64_t particle_stride, const void* field, int32_t field_layout,
-    const double* params, int64_t n_particles, int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
-    const void* records, int64_t record_stride, const void* survival, int64_t survival_stride,
-    double* next_stats, double* next_params, const void* energy, int64_t energy_stride,
-    int32_t energy_dtype, const void* mass_eV, int32_t mass_dtype, const void* next_effect_length,
-    int64_t next_length_stride, int32_t next_length_dtype, const void* next_extent_x,
-    int64_t next_extent_x_stride, const void* next_extent_y, int64_t next_extent_y_stride,
-    const void* next_extent_tau, int64_t next_extent_tau_stride, int32_t next_extent_dtype,
-    int32_t next_nx, int32_t next_ny, int32_t next_nz, void* particles_out, void* stream) {
+    const double* params, int64_t n_particles, int64_t n_beams, int32_t nx, int32_t ny, int32_t nz,
+    int32_t dtype, const void* records, int64_t record_stride, const void* survival,
+    int64_t survival_stride, double* next_stats, double* next_params, const void* energy,
+    int64_t energy_stride, int32_t energy_dtype, const void* mass_eV, int32_t mass_dtype,
+    const void* next_effect_length, int64_t next_length_stride, int32_t next_length_dtype,
+    const void* next_extent_x, int64_t next_extent_x_stride, const void* next_extent_y,
+    int64_t next_extent_y_stride, const void* next_extent_tau, int64_t next_extent_tau_stride,
+    int32_t next_extent_dtype, int32_t next_nx, int32_t next_ny, int32_t next_nz,
+    void* particles_out, void* stream) {
   CH_SC_COMMON_CHECKS("ch_sc_gather_kick_fused");
   CH_REQUIRE(particles_in && field && params && particles_out && n_particles > 0,
              "ch_sc_gather_kick_fused: bad arguments");
@@ -2498,49 +2684,37 @@ extern "C" int ch_sc_gather_kick_fused(
   CH_SC_LAYOUT_CHECK("ch_sc_gather_kick_fused");
   CH_REQUIRE(records != nullptr || next_stats != nullptr,
              "ch_sc_gather_kick_fused: nothing to fuse (use ch_sc_gather_kick)");
-  if (next_stats != nullptr) {
-    CH_REQUIRE(next_params && energy && mass_eV && next_effect_length && next_extent_x &&
-                   next_extent_y && next_extent_tau,
-               "ch_sc_gather_kick_fused: NULL pointer among the next kick's inputs");
-    CH_REQUIRE(ch::grid_ok(next_nx, next_ny, next_nz),
-               "ch_sc_gather_kick_fused: bad next grid (%d, %d, %d)", next_nx, next_ny, next_nz);
-  }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (next_stats != nullptr)
-    CH_CUDA(cudaMemsetAsync(next_stats, 0, sizeof(double) * CH_SC_STATS * n_beams, s));
-  const ch::GridInputs in{{energy, energy_stride, energy_dtype},
-                          {mass_eV, 0, mass_dtype},
-                          {next_effect_length, next_length_stride, next_length_dtype},
-                          {next_extent_x, next_extent_x_stride, next_extent_dtype},
-                          {next_extent_y, next_extent_y_stride, next_extent_dtype},
-                          {next_extent_tau, next_extent_tau_stride, next_extent_dtype}};
-  // several waves of CTAs: grid parameters in a follow-up launch instead of a last-CTA epilogue
-  const int64_t ctas = ((n_particles + 1023) / 1024) * n_beams;
-  const bool separate_params = next_stats != nullptr && ctas > 148 * 3 * 4;
-  double* in_kernel_params = separate_params ? nullptr : next_params;
-  int status;
-  if (dtype == CH_F32) {
-    const ch::GatherFusion<float> f{static_cast<const float*>(records), record_stride,
-                                    static_cast<const float*>(survival), survival_stride,
-                                    next_stats, in_kernel_params, in, next_nx, next_ny, next_nz};
-    status = launch_gather<float>(particles_in, particle_stride, field, field_layout, params,
-                                  n_particles, n_beams, nx, ny, nz, particles_out, nullptr, &f, s);
-  } else {
-    const ch::GatherFusion<double> f{static_cast<const double*>(records), record_stride,
-                                     static_cast<const double*>(survival), survival_stride,
-                                     next_stats, in_kernel_params, in, next_nx, next_ny, next_nz};
-    status = launch_gather<double>(particles_in, particle_stride, field, field_layout, params,
-                                   n_particles, n_beams, nx, ny, nz, particles_out, nullptr, &f,
-                                   s);
-  }
-  if (status != CH_OK || !separate_params) return status;
-  const unsigned blocks = static_cast<unsigned>((n_beams + 127) / 128);
-  if (dtype == CH_F32)
-    ch::sc_grid_params_kernel<float><<<blocks, 128, 0, s>>>(next_stats, n_beams, in, next_nx,
-                                                            next_ny, next_nz, next_params);
-  else
-    ch::sc_grid_params_kernel<double><<<blocks, 128, 0, s>>>(next_stats, n_beams, in, next_nx,
-                                                             next_ny, next_nz, next_params);
-  CH_LAUNCH_CHECK();
-  return CH_OK;
+  CH_SC_NEXT_CHECKS("ch_sc_gather_kick_fused");
+  const FusedArgs a{particles_in, particle_stride, field,          field_layout, nullptr,
+                    0,            params,          n_particles,    n_beams,      nx,
+                    ny,           nz,              dtype,          records,      record_stride,
+                    survival,     survival_stride, next_stats,     next_params,  next_in,
+                    next_nx,      next_ny,         next_nz,        particles_out, nullptr};
+  return gather_fused(a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ch_sc_field_gather(
+    const void* particles_in, int64_t particle_stride, const void* phi, void* bricks,
+    int32_t group_beams, const double* params, int64_t n_particles, int64_t n_beams, int32_t nx,
+    int32_t ny, int32_t nz, int32_t dtype, const void* records, int64_t record_stride,
+    const void* survival, int64_t survival_stride, double* next_stats, double* next_params,
+    const void* energy, int64_t energy_stride, int32_t energy_dtype, const void* mass_eV,
+    int32_t mass_dtype, const void* next_effect_length, int64_t next_length_stride,
+    int32_t next_length_dtype, const void* next_extent_x, int64_t next_extent_x_stride,
+    const void* next_extent_y, int64_t next_extent_y_stride, const void* next_extent_tau,
+    int64_t next_extent_tau_stride, int32_t next_extent_dtype, int32_t next_nx, int32_t next_ny,
+    int32_t next_nz, void* particles_out, void* forces_out, void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_field_gather");
+  CH_REQUIRE(dtype == CH_F32, "ch_sc_field_gather: float32 only");
+  CH_REQUIRE(particles_in && phi && bricks && params && particles_out && n_particles > 0 &&
+                 group_beams > 0,
+             "ch_sc_field_gather: bad arguments");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_field_gather: bad grid (%d, %d, %d)", nx, ny, nz);
+  CH_SC_NEXT_CHECKS("ch_sc_field_gather");
+  const FusedArgs a{particles_in, particle_stride, bricks,      CH_SC_FIELD_BRICKS,
+                    static_cast<const float*>(phi), group_beams, params, n_particles, n_beams,
+                    nx, ny, nz, dtype, records, record_stride, survival, survival_stride,
+                    next_stats, next_params, next_in, next_nx, next_ny, next_nz, particles_out,
+                    forces_out};
+  return gather_fused(a, static_cast<cudaStream_t>(stream));
 }

@@ -9,6 +9,7 @@ the vector shape.  All per-beam scalars stay on the device between kernels.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -102,13 +103,22 @@ class Workspace:
         # float64: z corner pairs per node (ch_sc_field)
         self.bricks = dtype == torch.float32 and use_field_bricks
         if self.bricks:
-            self.field = torch.empty((n_beams, nx, ny, nz, 3, 8), dtype=dtype, device=device)
+            # one group of beams at a time (ch_sc_field_gather): the group's bricks stay in L2
+            per_beam = nx * ny * nz * 96
+            self.group_beams = max(1, min(n_beams, brick_group_bytes // per_beam))
+            self.field = torch.empty((self.group_beams, nx, ny, nz, 3, 8), dtype=dtype,
+                                     device=device)
         else:
             self.field = torch.empty((n_beams, nx, ny, nz, 2, 4), dtype=dtype, device=device)
 
 
+# Bytes of field bricks built and consumed at a time: caps the scratch memory of a large batch.
+# (Groups small enough to keep the bricks in L2 were measured SLOWER -- 128 beams: 5.1 ms with
+# 1 beam per group, 4.4 with 2, 3.3 with all -- the gather is bound inside the SM, not by where
+# its bricks come from, and short launches pay their tails.)
+brick_group_bytes = int(os.environ.get("CH_BRICK_GROUP_MB", "4096")) << 20
 # Set to False to gather from the node layout with float32 beams as well (tests compare both).
-use_field_bricks = True
+use_field_bricks = os.environ.get("CH_FIELD_NODES", "0") in ("", "0")
 
 _workspace_cache: dict = {}
 _side_streams: dict = {}
@@ -126,7 +136,7 @@ def _workspace(n_beams: int, grid_shape: tuple, dtype, device) -> Workspace:
     """One cached workspace per (batch, grid, dtype, device, stream): kicks on a stream are
     ordered, so the scratch of the previous kick is free when the next one starts."""
     key = (n_beams, tuple(grid_shape), dtype, device,
-           torch.cuda.current_stream(device).cuda_stream, use_field_bricks)
+           torch.cuda.current_stream(device).cuda_stream, use_field_bricks, brick_group_bytes)
     ws = _workspace_cache.get(key)
     if ws is None:
         if len(_workspace_cache) >= 4:
@@ -217,47 +227,54 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
         _capi.check(lib.ch_sc_poisson_solve(
             ws.rho_quad.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
             nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))
-        field_kernel = lib.ch_sc_field_bricks if ws.bricks else lib.ch_sc_field
-        layout = _capi.SC_FIELD_BRICKS if ws.bricks else _capi.SC_FIELD_NODES
-        _capi.check(field_kernel(
-            ws.phi.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
-            ws.field.data_ptr(), stream))
-        if fuse_records is None and next_element is None:
-            _capi.check(lib.ch_sc_gather_kick(
-                p.data_ptr(), p_stride, ws.field.data_ptr(), layout, ws.params.data_ptr(), n,
-                n_beams,
-                nx, ny, nz, code, out.data_ptr(), _capi.ptr(forces), stream))
+        nxt = None
+        next_slot = 1 - ws.slot
+        if next_element is not None:
+            nlen, nl_stride = _scalar_ref(next_element.effect_length, vector_shape, dtype)
+            next = [
+                _scalar_ref(x, vector_shape, dtype)
+                for x in (next_element.grid_extent_x, next_element.grid_extent_y,
+                          next_element.grid_extent_tau)
+            ]
+            nxt = (nlen, nl_stride, next)
+        record_stride = 0
+        if fuse_records is not None and fuse_records.shape[0] > 1:
+            record_stride = fuse_records.shape[1]
+        fusion_args = (
+            _capi.ptr(fuse_records), record_stride, w.data_ptr(), w_stride,
+            ws.stats_slots[next_slot].data_ptr() if nxt else None,
+            ws.params_slots[next_slot].data_ptr() if nxt else None,
+            e.data_ptr(), e_stride, _capi.dtype_code(e.dtype),
+            mass.data_ptr(), _capi.dtype_code(mass.dtype),
+            nxt[0].data_ptr() if nxt else None, nxt[1] if nxt else 0,
+            _capi.dtype_code(nxt[0].dtype) if nxt else code,
+            nxt[2][0][0].data_ptr() if nxt else None, nxt[2][0][1] if nxt else 0,
+            nxt[2][1][0].data_ptr() if nxt else None, nxt[2][1][1] if nxt else 0,
+            nxt[2][2][0].data_ptr() if nxt else None, nxt[2][2][1] if nxt else 0, code,
+            nx, ny, nz,
+        )
+        if ws.bricks:
+            # float32: field bricks and gather interleaved per group of beams
+            _capi.check(lib.ch_sc_field_gather(
+                p.data_ptr(), p_stride, ws.phi.data_ptr(), ws.field.data_ptr(), ws.group_beams,
+                ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, *fusion_args,
+                out.data_ptr(), _capi.ptr(forces), stream))
         else:
-            nxt = None
-            next_slot = 1 - ws.slot
-            if next_element is not None:
-                nlen, nl_stride = _scalar_ref(next_element.effect_length, vector_shape, dtype)
-                next = [
-                    _scalar_ref(x, vector_shape, dtype)
-                    for x in (next_element.grid_extent_x, next_element.grid_extent_y,
-                              next_element.grid_extent_tau)
-                ]
-                nxt = (nlen, nl_stride, next)
-            record_stride = 0
-            if fuse_records is not None and fuse_records.shape[0] > 1:
-                record_stride = fuse_records.shape[1]
-            _capi.check(lib.ch_sc_gather_kick_fused(
-                p.data_ptr(), p_stride, ws.field.data_ptr(), layout, ws.params.data_ptr(), n,
-                n_beams,
-                nx, ny, nz, code,
-                _capi.ptr(fuse_records), record_stride, w.data_ptr(), w_stride,
-                ws.stats_slots[next_slot].data_ptr() if nxt else None,
-                ws.params_slots[next_slot].data_ptr() if nxt else None,
-                e.data_ptr(), e_stride, _capi.dtype_code(e.dtype),
-                mass.data_ptr(), _capi.dtype_code(mass.dtype),
-                nxt[0].data_ptr() if nxt else None, nxt[1] if nxt else 0,
-                _capi.dtype_code(nxt[0].dtype) if nxt else code,
-                nxt[2][0][0].data_ptr() if nxt else None, nxt[2][0][1] if nxt else 0,
-                nxt[2][1][0].data_ptr() if nxt else None, nxt[2][1][1] if nxt else 0,
-                nxt[2][2][0].data_ptr() if nxt else None, nxt[2][2][1] if nxt else 0, code,
-                nx, ny, nz, out.data_ptr(), stream))
-            if nxt is not None:
-                ws.prepared_next = Prepared(ws, next_slot, next_element)
+            _capi.check(lib.ch_sc_field(
+                ws.phi.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
+                ws.field.data_ptr(), stream))
+            if fuse_records is None and next_element is None:
+                _capi.check(lib.ch_sc_gather_kick(
+                    p.data_ptr(), p_stride, ws.field.data_ptr(), _capi.SC_FIELD_NODES,
+                    ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, out.data_ptr(),
+                    _capi.ptr(forces), stream))
+            else:
+                _capi.check(lib.ch_sc_gather_kick_fused(
+                    p.data_ptr(), p_stride, ws.field.data_ptr(), _capi.SC_FIELD_NODES,
+                    ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, *fusion_args,
+                    out.data_ptr(), stream))
+        if nxt is not None:
+            ws.prepared_next = Prepared(ws, next_slot, next_element)
     ws.forces = forces
     return out.reshape(*vector_shape, n, 7), ws
 

@@ -538,6 +538,31 @@ int ch_sc_gather_kick_fused(const void* particles_in, int64_t particle_stride,
                             int32_t next_nx, int32_t next_ny, int32_t next_nz,
                             void* particles_out, void* stream);
 
+/* float32: ch_sc_field_bricks + ch_sc_gather_kick[_fused] interleaved per group of `group_beams`
+ * beams: the bricks of a group are built from phi [B][nx*ny*nz] into `bricks`
+ * (group_beams * nx*ny*nz * 24 floats, reused by every group) right before the group's gather
+ * pass, so the gather finds them in L2 instead of HBM (the bricks of all beams of a large batch
+ * exceed the L2 several times) and they never travel to HBM at all.  records and next_stats may
+ * both be NULL (plain kick); forces_out as in ch_sc_gather_kick; the other arguments as in
+ * ch_sc_gather_kick_fused.                                                                      */
+int ch_sc_field_gather(const void* particles_in, int64_t particle_stride,
+                       const void* phi, void* bricks, int32_t group_beams, const double* params,
+                       int64_t n_particles, int64_t n_beams,
+                       int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                       const void* records, int64_t record_stride,
+                       const void* survival, int64_t survival_stride,
+                       double* next_stats, double* next_params,
+                       const void* energy, int64_t energy_stride, int32_t energy_dtype,
+                       const void* mass_eV, int32_t mass_dtype,
+                       const void* next_effect_length, int64_t next_length_stride,
+                       int32_t next_length_dtype,
+                       const void* next_extent_x, int64_t next_extent_x_stride,
+                       const void* next_extent_y, int64_t next_extent_y_stride,
+                       const void* next_extent_tau, int64_t next_extent_tau_stride,
+                       int32_t next_extent_dtype,
+                       int32_t next_nx, int32_t next_ny, int32_t next_nz,
+                       void* particles_out, void* forces_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert symbols == set(_capi.SIGNATURES), symbols ^ set(_capi.SIGNATURES)
     for name in symbols:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
-    assert lib.ch_abi_version() == 2
+    assert lib.ch_abi_version() == _capi.ABI_VERSION == 3
     assert lib.ch_kernel_launch_count() == 0  # nothing computes on a CPU-only box
 
 
