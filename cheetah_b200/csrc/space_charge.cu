@@ -808,14 +808,18 @@ fft_even_pass_kernel(const void* __restrict__ in, T* __restrict__ out, int n, in
       if (i > 0) column[len - i].x = value;
     }
   }
-  if (threadIdx.x < kPairs) v[threadIdx.x * pitch + n] = C{T(0), T(0)};
+  // positions n .. len - n are zero (position n alone when len == 2 n)
+  const int gap = len - 2 * n + 1;
+  for (int t = threadIdx.x; t < kPairs * gap; t += kFftThreads)
+    v[(t / gap) * pitch + n + t % gap] = C{T(0), T(0)};
   __syncthreads();
   fft::forward_dif<kPairs>(v, tw, len, log2_len, pitch);
 
   T* dst = out + blockIdx.y * out_batch_stride;
-  for (int t = threadIdx.x; t < kColumns * (n + 1); t += kFftThreads) {
-    const int c = axis_contiguous ? t / (n + 1) : t % kColumns;
-    const int k = axis_contiguous ? t - c * (n + 1) : t / kColumns;
+  const int n_out = len / 2 + 1;
+  for (int t = threadIdx.x; t < kColumns * n_out; t += kFftThreads) {
+    const int c = axis_contiguous ? t / n_out : t % kColumns;
+    const int k = axis_contiguous ? t - c * n_out : t / kColumns;
     if (c >= columns) continue;
     const int col = c0 + c;
     const int outer = col / inner_count, inner = col - outer * inner_count;
@@ -1866,10 +1870,19 @@ int log2_exact(int v) {
   return ((1 << l) == v) ? l : -1;
 }
 
+// Any grid size in [2, 256] per axis.  The convolution with the Green function is aperiodic, so
+// the padded transform length only has to be >= 2 n - 1: the next power of two >= 2 n (>= 8),
+// which is 2 n itself for the power-of-two grids of the benchmarks.
 bool grid_ok(int nx, int ny, int nz) {
   for (int v : {nx, ny, nz})
-    if (v < 4 || v > 256 || log2_exact(v) < 0) return false;
+    if (v < 2 || v > 256) return false;
   return true;
+}
+
+int fft_len(int n) {
+  int len = 8;
+  while (len < 2 * n) len *= 2;
+  return len;
 }
 
 template <typename K>
@@ -1931,24 +1944,25 @@ bool fftr_enabled() {
   return on;
 }
 
-// Compact Green spectrum [B][nx+1][ny+1][nz+1] from the antiderivative lattice: three even
-// passes through two scratch arrays s1 [B][nx][ny][nz+1], s2 [B][nx][ny+1][nz+1].
+// Compact Green spectrum [B][Kx][Ky][Kz] (K = fft_len / 2 + 1) from the antiderivative lattice:
+// three even passes through two scratch arrays s1 [B][nx][ny][Kz], s2 [B][nx][Ky][Kz].
 template <typename T>
 int green_spectrum(const double* lattice, const double* params, int far_field, int64_t B, int nx,
                    int ny, int nz, T* s1, T* s2, T* spectrum, cudaStream_t stream) {
   using C = typename fft::Complex<T>::type;
-  const int Kz = nz + 1;
+  const int Lx = fft_len(nx), Ly = fft_len(ny), Lz = fft_len(nz);
+  const int Kx = Lx / 2 + 1, Ky = Ly / 2 + 1, Kz = Lz / 2 + 1;
   const unsigned nb = static_cast<unsigned>(B);
   auto smem = [&](int len) { return sizeof(C) * ((kColumns / 2) * (len + 2) + len / 2); };
   const int64_t lattice_points = static_cast<int64_t>(nx + 1) * (ny + 1) * (nz + 1);
   constexpr bool kFloat = std::is_same<T, float>::value;
-  const bool regs = kFloat && fftr_enabled() && fftr_covers(2 * nx) && fftr_covers(2 * ny) &&
-                    fftr_covers(2 * nz);
+  const bool regs = kFloat && fftr_enabled() && fftr_covers(Lx) && fftr_covers(Ly) &&
+                    fftr_covers(Lz);
   {  // z: rows (x, y) of the lattice difference -> s1[x][y][kz]
     const int columns = nx * ny;
     if (regs) {
       if constexpr (kFloat) {
-        fftr_dispatch(2 * nz, [&](auto L) {
+        fftr_dispatch(Lz, [&](auto L) {
           constexpr int LEN = decltype(L)::value;
           fftr_tile((static_cast<int64_t>(columns) + 1) / 2 * B, [&](auto R) {
             constexpr int ROWS = decltype(R)::value;
@@ -1960,10 +1974,10 @@ int green_spectrum(const double* lattice, const double* params, int far_field, i
       }
     } else {
       auto k = fft_even_pass_kernel<T, true>;
-      if (allow_smem(k, smem(2 * nz)) != CH_OK) return CH_ECUDA;
+      if (allow_smem(k, smem(Lz)) != CH_OK) return CH_ECUDA;
       dim3 grid((columns + kColumns - 1) / kColumns, nb);
-      k<<<grid, kFftThreads, smem(2 * nz), stream>>>(
-          lattice, s1, nz, 2 * nz, log2_exact(2 * nz), columns, 1, 0, 1, lattice_points, Kz, 1,
+      k<<<grid, kFftThreads, smem(Lz), stream>>>(
+          lattice, s1, nz, Lz, log2_exact(Lz), columns, 1, 0, 1, lattice_points, Kz, 1,
           static_cast<int64_t>(nx) * ny * Kz, ny, nz, params, far_field);
     }
     CH_LAUNCH_CHECK();
@@ -1972,34 +1986,34 @@ int green_spectrum(const double* lattice, const double* params, int far_field, i
     const int columns = nx * Kz;
     if (regs) {
       if constexpr (kFloat) {
-        fftr_dispatch(2 * ny, [&](auto L) {
+        fftr_dispatch(Ly, [&](auto L) {
           constexpr int LEN = decltype(L)::value;
           fftr_tile((static_cast<int64_t>(columns) + 1) / 2 * B, [&](auto R) {
             constexpr int COLS = decltype(R)::value;
             dim3 grid((columns + 2 * COLS - 1) / (2 * COLS), nb);
             fftr_even_strided_kernel<LEN, COLS><<<grid, COLS * fftr::Plan<LEN>::N2, 0, stream>>>(
                 s1, s2, ny, columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
-                static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
-                static_cast<int64_t>(nx) * (ny + 1) * Kz);
+                static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(Ky) * Kz, Kz,
+                static_cast<int64_t>(nx) * Ky * Kz);
           });
         });
       }
     } else {
       auto k = fft_even_pass_kernel<T, false>;
-      if (allow_smem(k, smem(2 * ny)) != CH_OK) return CH_ECUDA;
+      if (allow_smem(k, smem(Ly)) != CH_OK) return CH_ECUDA;
       dim3 grid((columns + kColumns - 1) / kColumns, nb);
-      k<<<grid, kFftThreads, smem(2 * ny), stream>>>(
-          s1, s2, ny, 2 * ny, log2_exact(2 * ny), columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
-          static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(ny + 1) * Kz, Kz,
-          static_cast<int64_t>(nx) * (ny + 1) * Kz, 0, 0, nullptr, 0);
+      k<<<grid, kFftThreads, smem(Ly), stream>>>(
+          s1, s2, ny, Ly, log2_exact(Ly), columns, Kz, static_cast<int64_t>(ny) * Kz, Kz,
+          static_cast<int64_t>(nx) * ny * Kz, static_cast<int64_t>(Ky) * Kz, Kz,
+          static_cast<int64_t>(nx) * Ky * Kz, 0, 0, nullptr, 0);
     }
     CH_LAUNCH_CHECK();
   }
   {  // x: columns (ky, kz) -> spectrum[kx][ky][kz]
-    const int columns = (ny + 1) * Kz;
+    const int columns = Ky * Kz;
     if (regs) {
       if constexpr (kFloat) {
-        fftr_dispatch(2 * nx, [&](auto L) {
+        fftr_dispatch(Lx, [&](auto L) {
           constexpr int LEN = decltype(L)::value;
           fftr_tile((static_cast<int64_t>(columns) + 1) / 2 * B, [&](auto R) {
             constexpr int COLS = decltype(R)::value;
@@ -2007,17 +2021,17 @@ int green_spectrum(const double* lattice, const double* params, int far_field, i
             fftr_even_strided_kernel<LEN, COLS><<<grid, COLS * fftr::Plan<LEN>::N2, 0, stream>>>(
                 s2, spectrum, nx, columns, columns, 0, columns,
                 static_cast<int64_t>(nx) * columns, 0, columns,
-                static_cast<int64_t>(nx + 1) * columns);
+                static_cast<int64_t>(Kx) * columns);
           });
         });
       }
     } else {
       auto k = fft_even_pass_kernel<T, false>;
-      if (allow_smem(k, smem(2 * nx)) != CH_OK) return CH_ECUDA;
+      if (allow_smem(k, smem(Lx)) != CH_OK) return CH_ECUDA;
       dim3 grid((columns + kColumns - 1) / kColumns, nb);
-      k<<<grid, kFftThreads, smem(2 * nx), stream>>>(
-          s2, spectrum, nx, 2 * nx, log2_exact(2 * nx), columns, columns, 0, columns,
-          static_cast<int64_t>(nx) * columns, 0, columns, static_cast<int64_t>(nx + 1) * columns, 0,
+      k<<<grid, kFftThreads, smem(Lx), stream>>>(
+          s2, spectrum, nx, Lx, log2_exact(Lx), columns, columns, 0, columns,
+          static_cast<int64_t>(nx) * columns, 0, columns, static_cast<int64_t>(Kx) * columns, 0,
           0, nullptr, 0);
     }
     CH_LAUNCH_CHECK();
@@ -2030,7 +2044,7 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
                   int nx, int ny, int nz, typename fft::Complex<T>::type* rs, T* phi,
                   cudaStream_t stream) {
   using C = typename fft::Complex<T>::type;
-  const int Nx = 2 * nx, Ny = 2 * ny, Nz = 2 * nz, Kz = Nz / 2 + 1;
+  const int Nx = fft_len(nx), Ny = fft_len(ny), Nz = fft_len(nz), Kz = Nz / 2 + 1;
   const int lx = log2_exact(Nx), ly = log2_exact(Ny), lz = log2_exact(Nz);
   const int64_t spectrum = static_cast<int64_t>(Nx) * Ny * Kz;
   auto z_smem = [&](int len) { return sizeof(C) * (kRowPairs * (len + 2) + len / 2); };
@@ -2076,7 +2090,7 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
           constexpr int COLS = decltype(R)::value;
           dim3 grid((inner + COLS - 1) / COLS, 1, nb);
           fftr_strided_kernel<LEN, 2, COLS><<<grid, COLS * fftr::Plan<LEN>::N2, 0, stream>>>(
-              rs, green_spectrum_compact, ny + 1, Kz, nx, nx, inner, inner, 0, spectrum);
+              rs, green_spectrum_compact, Ny / 2 + 1, Kz, nx, nx, inner, inner, 0, spectrum);
         });
       });
       CH_LAUNCH_CHECK();
@@ -2126,7 +2140,8 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
     if (allow_smem(k, s_smem(Nx)) != CH_OK) return CH_ECUDA;
     const int inner = Ny * Kz;
     dim3 grid((inner + kColumns - 1) / kColumns, 1, nb);
-    k<<<grid, kFftThreads, s_smem(Nx), stream>>>(rs, green_spectrum_compact, ny + 1, Kz, Nx, lx,
+    k<<<grid, kFftThreads, s_smem(Nx), stream>>>(rs, green_spectrum_compact, Ny / 2 + 1, Kz, Nx,
+                                                  lx,
                                                   nx, nx, inner, inner, 0, spectrum);
     CH_LAUNCH_CHECK();
   }
@@ -2185,7 +2200,7 @@ extern "C" int ch_sc_moments_and_params(
   CH_REQUIRE(energy && mass_eV && effect_length && extent_x && extent_y && extent_tau && params,
              "ch_sc_moments_and_params: NULL pointer argument");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz),
-             "ch_sc_moments_and_params: grid (%d, %d, %d) must be powers of two in [4, 256]", nx,
+             "ch_sc_moments_and_params: grid sizes (%d, %d, %d) must be in [2, 256]", nx,
              ny, nz);
   ch::GridInputs in{{energy, energy_stride, energy_dtype},
                     {mass_eV, 0, mass_dtype},
@@ -2241,7 +2256,7 @@ extern "C" int ch_sc_grid_params(const double* stats, int64_t n_beams, const voi
                  params,
              "ch_sc_grid_params: NULL pointer argument");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz),
-             "ch_sc_grid_params: grid (%d, %d, %d) must be powers of two in [4, 256]", nx, ny, nz);
+             "ch_sc_grid_params: grid sizes (%d, %d, %d) must be in [2, 256]", nx, ny, nz);
   ch::GridInputs in{{energy, energy_stride, energy_dtype},
                     {mass_eV, 0, mass_dtype},
                     {effect_length, length_stride, length_dtype},
@@ -2398,7 +2413,7 @@ extern "C" int ch_sc_green_spectrum(const double* lattice, const double* params,
              "ch_sc_green_spectrum: NULL pointer argument");
   CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_green_spectrum: bad grid (%d, %d, %d)", nx, ny, nz);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t s1 = n_beams * static_cast<int64_t>(nx) * ny * (nz + 1);
+  const int64_t s1 = n_beams * static_cast<int64_t>(nx) * ny * (ch::fft_len(nz) / 2 + 1);
   if (dtype == CH_F32) {
     float* base = static_cast<float*>(scratch);
     return ch::green_spectrum<float>(lattice, params, ch::green_far_field(dtype), n_beams, nx, ny,

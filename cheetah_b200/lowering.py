@@ -300,7 +300,7 @@ def _check_tensor(tensor: torch.Tensor, device: torch.device, what: str) -> None
             f"{what} lives on {tensor.device} but the beam is on {device}; move the lattice with "
             "`segment.to(device)` first"
         )
-    if tensor.requires_grad:
+    if tensor.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError(
             f"{what} requires grad: the CUDA path is forward-only; differentiable tracking is the "
             "reference implementation's job (SURVEY.md 2, row 12)"

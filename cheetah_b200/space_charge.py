@@ -29,6 +29,14 @@ def _flat(tensor: torch.Tensor, vector_shape: tuple, inner: tuple, dtype) -> tup
     return tensor.contiguous(), math.prod(inner)
 
 
+def fft_len(n: int) -> int:
+    """Padded transform length of a grid axis with ``n`` cells: the next power of two >= 2 n."""
+    length = 8
+    while length < 2 * n:
+        length *= 2
+    return length
+
+
 def _scalar_ref(tensor: torch.Tensor, vector_shape: tuple, dtype) -> tuple:
     tensor, stride = _flat(tensor, vector_shape, (), dtype)
     return tensor, min(stride, 1)
@@ -72,7 +80,10 @@ class Workspace:
     def __init__(self, n_beams: int, grid_shape: tuple, dtype, device) -> None:
         nx, ny, nz = grid_shape
         cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
-        spectrum = (n_beams, 2 * nx, 2 * ny, nz + 1)
+        # FFT length per axis: the next power of two >= 2 n (include/cheetah_b200.h)
+        lx, ly, lz = (fft_len(v) for v in (nx, ny, nz))
+        kx, ky, kz = lx // 2 + 1, ly // 2 + 1, lz // 2 + 1
+        spectrum = (n_beams, lx, ly, kz)
         # two slots: the fused gather kernel of kick k writes the sums / grid parameters of kick
         # k + 1 while it is still reading those of kick k
         self.stats_slots = [
@@ -92,11 +103,9 @@ class Workspace:
         )
         self.green = None  # the mirrored (2n)^3 array is only built for the parity tests
         self.green_scratch = torch.empty(
-            (n_beams * (nx * ny * (nz + 1) + nx * (ny + 1) * (nz + 1)),), dtype=dtype, device=device
+            (n_beams * (nx * ny * kz + nx * ky * kz),), dtype=dtype, device=device
         )
-        self.green_spectrum = torch.empty(
-            (n_beams, nx + 1, ny + 1, nz + 1), dtype=dtype, device=device
-        )
+        self.green_spectrum = torch.empty((n_beams, kx, ky, kz), dtype=dtype, device=device)
         self.rho_spectrum = torch.empty(spectrum, dtype=cdtype, device=device)
         self.phi = torch.empty((n_beams, nx, ny, nz), dtype=dtype, device=device)
         # float32: "bricks" (all 8 corners of a cell side by side, ch_sc_field_bricks);
@@ -159,9 +168,9 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
     code = _capi.dtype_code(dtype)
     nx, ny, nz = (int(v) for v in grid_shape)
     for v in (nx, ny, nz):
-        if v < 4 or v > 256 or v & (v - 1):
+        if v < 2 or v > 256:
             raise NotImplementedError(
-                f"cheetah_b200 SpaceChargeKick needs power-of-two grid sizes in [4, 256], got "
+                f"cheetah_b200 SpaceChargeKick supports grid sizes in [2, 256], got "
                 f"{tuple(grid_shape)}"
             )
 

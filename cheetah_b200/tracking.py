@@ -217,6 +217,11 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
                          getattr(beam, "_unit_seventh", None))
 
     vo = tuple(_bshape(vm, vp))
+    vs = tuple(beam.survival_probabilities.shape[:-1])
+    if section.n_apertures or moments is not None:
+        # survival probabilities may carry vector dims of their own (tests/test_vectorized.py:
+        # 339-371): the kernel then runs on the wider batch and the particles are narrowed again
+        vo = tuple(_bshape(vo, vs))
     n_out = math.prod(vo)
     if not particles.is_contiguous():
         particles = particles.contiguous()
@@ -231,18 +236,11 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
     survival_in = beam.survival_probabilities
     survival_out = None
     survival_index = None
-    vs = tuple(survival_in.shape[:-1])
     if section.n_apertures:
         if survival_in.dtype != dtype or not survival_in.is_contiguous():
             survival_in = survival_in.to(dtype).contiguous()
         # the kernel works on the full output batch; the reference's survival tensor only
         # carries the vector dims that reached the last aperture
-        vfull = tuple(_bshape(vo, vs))
-        if vfull != vo:
-            raise NotImplementedError(
-                "survival_probabilities with vector dimensions beyond those of particles and "
-                "lattice are not supported"
-            )
         survival_index = _index_table(vs, vo, device)
         if moments != "only":
             survival_out = torch.empty((*vo, n), dtype=dtype, device=device)
@@ -255,8 +253,6 @@ def _track_linear_section(program, section, beam, moments: str | None = None,
         # the sums are weighted with the survival probabilities even without apertures
         if survival_in.dtype != dtype or not survival_in.is_contiguous():
             survival_in = survival_in.to(dtype).contiguous()
-        if tuple(_bshape(vo, vs)) != vo:
-            raise NotImplementedError("survival_probabilities wider than particles and lattice")
         survival_index = _index_table(vs, vo, device)
     common = (
         particles.data_ptr(), 0 if math.prod(vp) == 1 else n * 7, _capi.ptr(particle_index),
@@ -715,6 +711,17 @@ def track(elements, incoming, cache_owner=None):
     _require_cuda(incoming.particles, "ParticleBeam")
 
     program = _plan(elements, incoming.particles.device, tuple(incoming.energy.shape), cache_owner)
+    return track_program(program, incoming)
+
+
+def track_program(program, incoming):
+    """Run an already lowered ``program`` on ``incoming`` (the stage loop of ``track``)."""
+    if _is_parameter_beam(incoming):
+        _require_cuda(incoming.mu, "ParameterBeam")
+        return _track_parameter_beam(program, incoming)
+    if not _is_particle_beam(incoming):
+        raise TypeError(f"Parameter incoming is of invalid type {type(incoming)}")
+    _require_cuda(incoming.particles, "ParticleBeam")
     beam = incoming
     stages = program.stages
     prepared = None  # grid parameters a kick already computed for the kick that follows it

@@ -361,7 +361,9 @@ int ch_apply_maps_covariance(const void* particles_in, int64_t particle_stride, 
  *                             6 gamma, 7 beta, 8 dt = L / (c beta), 9 1 / cell volume,
  *                             10 1 / gamma^2 (0 if gamma == 0), 11-13 sigma x, y, tau,
  *                             14 sum w, 15 mass in eV
- * Grid sizes nx, ny, nz must be powers of two in [4, 256] (the doubled FFT length <= 512).
+ * Grid sizes nx, ny, nz: any value in [2, 256].  The FFT length of an axis is L = the next power
+ * of two >= 2 n (>= 8; the convolution is aperiodic, so any padding >= 2 n - 1 gives the same
+ * potential), K = L / 2 + 1 its number of non-redundant frequencies.
  * Batch strides are in elements per beam; 0 shares one array among all beams.           */
 #define CH_SC_STATS 12
 #define CH_SC_PARAMS 24
@@ -460,9 +462,9 @@ int ch_sc_green_function(const double* params, int64_t n_beams,
                          double* lattice, void* green, void* stream);
 
 /* rfftn of the mirrored Green array without ever building it: the array is even in every axis,
- * so its spectrum is real and even and is stored compactly as spectrum [B][nx+1][ny+1][nz+1]
+ * so its spectrum is real and even and is stored compactly as spectrum [B][Kx][Ky][Kz]
  * (3 passes of packed real-even FFTs, ~4x less work than a general rfftn).
- * scratch: B * (nx*ny*(nz+1) + nx*(ny+1)*(nz+1)) scalars of the beam dtype.  `params` as given
+ * scratch: B * (nx*ny*Kz + nx*Ky*Kz) scalars of the beam dtype.  `params` as given
  * to ch_sc_green_function (cell sizes decide where the far-field series applies).            */
 int ch_sc_green_spectrum(const double* lattice, const double* params, int64_t n_beams,
                          int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
@@ -475,7 +477,7 @@ int ch_sc_green_spectrum(const double* lattice, const double* params, int64_t n_
  * the multiply by the compact Green spectrum and the inverse FFT.
  * rho: the quad-block charge grid written by ch_sc_deposit (its four parts are summed while
  * loading);
- * rho_spectrum: [B][2nx][2ny][nz+1] complex scratch.                                        */
+ * rho_spectrum: [B][Lx][Ly][Kz] complex scratch.                                        */
 int ch_sc_poisson_solve(const void* rho, const void* green_spectrum, const double* params,
                         int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                         void* rho_spectrum, void* phi, void* stream);

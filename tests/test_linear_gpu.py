@@ -478,3 +478,35 @@ def test_vectorised_aperture_survival_fractions(shape, expected):
     assert tuple(outgoing.survival_probabilities.shape) == (3, 2, 100_000)
     fractions = outgoing.survival_probabilities.mean(dim=-1)[:, 0].cpu()
     assert torch.allclose(fractions, torch.tensor(expected), atol=5e-3), fractions
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_incoming_survival_with_vector_dims_of_its_own(dtype):
+    """``survival_probabilities`` may carry vector dimensions that neither the particles nor the
+    lattice have (reference contract: tests/test_vectorized.py:339-371, :488-491 -- the survival
+    of the outgoing beam is the broadcast of everything, the particles keep their own shape)."""
+    from oracle import lattice_io
+
+    n = 3000
+    g = torch.Generator().manual_seed(3)
+    particles = torch.randn(n, 7, generator=g, dtype=torch.float64) * 1e-3
+    particles[..., 6] = 1.0
+    survival = torch.rand(3, 1, n, generator=g, dtype=torch.float64)
+    lattice = [
+        {"type": "Drift", "name": "d1", "length": torch.tensor(0.4)},
+        {"type": "Quadrupole", "name": "q", "length": torch.tensor(0.2),
+         "k1": torch.tensor([2.0, -3.0])},
+        {"type": "Aperture", "name": "a", "x_max": torch.tensor(1.1e-3),
+         "y_max": torch.tensor(9e-4), "shape": "elliptical"},
+        {"type": "Drift", "name": "d2", "length": torch.tensor(0.3)},
+    ]
+    lattice = lattice_io.cast(lattice, dtype)
+    beam = oracle.make_beam(particles.to(dtype), torch.tensor(1e8, dtype=dtype),
+                            survival_probabilities=survival.to(dtype))
+    expected = oracle.track(lattice, beam)
+    out = gu.product_segment(lattice, DEVICE, dtype).track(gu.product_beam(beam, DEVICE, dtype))
+    assert out.particles.shape == expected["particles"].shape == (2, n, 7)
+    assert out.survival_probabilities.shape == expected["survival_probabilities"].shape == (3, 2, n)
+    assert torch.equal(out.survival_probabilities.cpu(), expected["survival_probabilities"])
+    err = gu.column_scaled_error(out.particles, expected["particles"])
+    assert err < (1e-12 if dtype == torch.float64 else 2e-6)
