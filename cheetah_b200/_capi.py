@@ -190,6 +190,18 @@ SIGNATURES = {
             c_void_p, c_void_p, c_void_p,
         ],
     ),
+    "ch_sc_moments_and_params_deterministic": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int32,
+            c_void_p, c_int64, c_int32,
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p, c_void_p, c_void_p,
+        ],
+    ),
     "ch_sc_grid_params": (
         c_int32,
         [
@@ -209,6 +221,23 @@ SIGNATURES = {
             c_void_p, c_int64, c_int64,
             c_int32, c_int32, c_int32, c_int32,
             c_void_p, c_void_p,
+        ],
+    ),
+    "ch_sc_deposit_deterministic": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+            c_void_p, c_int64, c_int64,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p, c_void_p,
+        ],
+    ),
+    "ch_cic_deposit_deterministic": (
+        c_int32,
+        [
+            c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p, c_void_p,
         ],
     ),
     "ch_cic_deposit3d": (

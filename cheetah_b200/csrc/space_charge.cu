@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256)
 sc_moments_kernel(const T* __restrict__ particles, int64_t particle_stride,
                   const T* __restrict__ survival, int64_t survival_stride, int64_t n_particles,
                   int bulk_in, double* __restrict__ stats, GridInputs in, int nx, int ny, int nz,
-                  double* __restrict__ params) {
+                  double* __restrict__ params, double* __restrict__ partials) {
   constexpr int P = 4, THREADS = 256, TP = P * THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);
@@ -150,14 +150,18 @@ sc_moments_kernel(const T* __restrict__ particles, int64_t particle_stride,
   if (threadIdx.x < 8) {
     double s = 0.0;
     for (int wi = 0; wi < 8; ++wi) s += partial[wi][threadIdx.x];
-    atomicAdd(&stats[b * CH_SC_STATS + threadIdx.x], s);
+    // deterministic mode: the CTA sums are parked and added in CTA order by the last CTA
+    if (partials != nullptr)
+      partials[(b * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = s;
+    else
+      atomicAdd(&stats[b * CH_SC_STATS + threadIdx.x], s);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     stats[b * CH_SC_STATS + 8] = x0;
     stats[b * CH_SC_STATS + 9] = y0;
     stats[b * CH_SC_STATS + 10] = t0;
   }
-  if (params == nullptr) return;
+  if (params == nullptr && partials == nullptr) return;
   // the last CTA of this beam to finish turns the sums into the grid parameters, so the
   // chain needs no separate launch (threadfence-reduction pattern; stats[11] is the ticket)
   __shared__ bool last;
@@ -166,7 +170,17 @@ sc_moments_kernel(const T* __restrict__ particles, int64_t particle_stride,
   if (threadIdx.x == 0)
     last = atomicAdd(&stats[b * CH_SC_STATS + 11], 1.0) == static_cast<double>(gridDim.x - 1);
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last && partials != nullptr) {
+    if (threadIdx.x < 8) {
+      double s = 0.0;
+      for (unsigned c = 0; c < gridDim.x; ++c)
+        s += __ldcg(&partials[(b * gridDim.x + c) * 8 + threadIdx.x]);
+      stats[b * CH_SC_STATS + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+  }
+  if (last && threadIdx.x == 0 && params != nullptr) {
     double sums[CH_SC_STATS];
     for (int i = 0; i < CH_SC_STATS; ++i) sums[i] = __ldcg(&stats[b * CH_SC_STATS + i]);
     grid_params_for_beam<T>(sums, b, in, nx, ny, nz, params + b * CH_SC_PARAMS);
@@ -383,6 +397,182 @@ cic_deposit_low_kernel(const T* __restrict__ positions, const T* __restrict__ ex
         }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// 3b. deterministic deposits (the reference's scatter_add_ is order-dependent on
+// CUDA and its tests only ask torch for determinism, tests/conftest.py:204)
+// ---------------------------------------------------------------------------------------
+// Float atomics make a histogram depend on the order in which the hardware retires them.  The
+// deterministic variants accumulate in 64-bit FIXED POINT instead: integer addition is
+// associative, so any order gives the same bits.  Scale per beam: 2^(61 - ceil(log2 N)) /
+// max |q_i| (found by a first pass with an integer atomicMax on the bit pattern), i.e. no sum
+// of N contributions can overflow and one unit is ~2^-41 of the largest particle charge --
+// finer than the float32 (and float64 after 1e6 additions) rounding of the atomic version.
+// scratch per beam: cells int64 + 1 uint64.
+struct FixedGrid {
+  unsigned long long* cells;
+  double scale;
+  __device__ __forceinline__ void add(int64_t index, double value) const {
+    atomicAdd(cells + index, static_cast<unsigned long long>(__double2ll_rn(value * scale)));
+  }
+};
+
+__device__ __forceinline__ double fixed_scale(unsigned long long max_bits, int64_t n_particles) {
+  const double max_abs = __longlong_as_double(static_cast<long long>(max_bits));
+  int shift = 61;
+  for (int64_t n = n_particles; n > 0; n >>= 1) --shift;
+  return max_abs > 0.0 ? ldexp(1.0, shift) / max_abs : 0.0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cic_max_charge_kernel(const T* __restrict__ charges, int64_t charge_stride,
+                      const T* __restrict__ survival, int64_t survival_stride,
+                      int64_t n_particles, unsigned long long* __restrict__ max_bits) {
+  const int64_t b = blockIdx.y;
+  const T* q = charges ? charges + b * charge_stride : nullptr;
+  const T* w = survival ? survival + b * survival_stride : nullptr;
+  double local = 0.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_particles;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    T v = q ? q[i] : T(1);
+    if (w) v *= w[i];
+    local = fmax(local, fabs(static_cast<double>(v)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local = fmax(local, __shfl_xor_sync(0xffffffffu, local, o));
+  // non-negative doubles order like their bit patterns
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(max_bits + b, static_cast<unsigned long long>(__double_as_longlong(local)));
+}
+
+// Space-charge deposit into the fixed-point grid [B][nx][ny][nz]: the arithmetic of
+// sc_deposit_kernel up to the accumulation.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sc_deposit_fixed_kernel(const T* __restrict__ particles, int64_t particle_stride,
+                        const T* __restrict__ charges, int64_t charge_stride,
+                        const T* __restrict__ survival, int64_t survival_stride,
+                        const double* __restrict__ params, int64_t n_particles, int nx, int ny,
+                        int nz, const unsigned long long* __restrict__ max_bits,
+                        unsigned long long* __restrict__ fixed) {
+  const int64_t b = blockIdx.y;
+  const double* prm = params + b * CH_SC_PARAMS;
+  const T lo[3] = {-static_cast<T>(prm[0]), -static_cast<T>(prm[1]), -static_cast<T>(prm[2])};
+  const T hi[3] = {static_cast<T>(prm[0]), static_cast<T>(prm[1]), static_cast<T>(prm[2])};
+  const T minus_beta = -static_cast<T>(prm[7]);
+  const T* p = particles + b * particle_stride;
+  const T* q = charges + b * charge_stride;
+  const T* w = survival ? survival + b * survival_stride : nullptr;
+  const FixedGrid grid{fixed + b * static_cast<int64_t>(nx) * ny * nz,
+                       fixed_scale(max_bits[b], n_particles)};
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_particles;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const T charge = w ? q[i] * w[i] : q[i];
+    const AxisDeposit<T> ax = deposit_axis(p[i * 7 + 0], lo[0], hi[0], nx);
+    const AxisDeposit<T> ay = deposit_axis(p[i * 7 + 2], lo[1], hi[1], ny);
+    const AxisDeposit<T> az = deposit_axis(p[i * 7 + 4] * minus_beta, lo[2], hi[2], nz);
+    if (!(ax.inside && ay.inside && az.inside)) continue;  // charges * in_extent
+    const int ix[2] = {ax.lo, ax.hi}, iy[2] = {ay.lo, ay.hi}, iz[2] = {az.lo, az.hi};
+    const T wx[2] = {ax.w_lo, ax.w_hi}, wy[2] = {ay.w_lo, ay.w_hi}, wz[2] = {az.w_lo, az.w_hi};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const T row = wx[a] * wy[c] * charge;  // as sc_deposit_kernel: (wx wy q) wz
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const T value = row * wz[d];
+          if (value != T(0))
+            grid.add((static_cast<int64_t>(ix[a]) * ny + iy[c]) * nz + iz[d],
+                     static_cast<double>(value));
+        }
+      }
+  }
+}
+
+// fixed point -> the quad-block charge grid of sc_deposit_kernel: every cell (y, z) appears once
+// in part 0 (blocks with even lower corners); the other three parts stay zero.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sc_fixed_to_quad_kernel(const unsigned long long* __restrict__ fixed,
+                        const unsigned long long* __restrict__ max_bits, int64_t n_particles,
+                        int nx, int ny, int nz, T* __restrict__ rho) {
+  const int64_t b = blockIdx.y;
+  const int64_t cells = static_cast<int64_t>(nx) * ny * nz;
+  const double scale = fixed_scale(max_bits[b], n_particles);
+  const double inverse = scale > 0.0 ? 1.0 / scale : 0.0;
+  const int qy = ny / 2 + 1, qz = nz / 2 + 1;
+  const int64_t plane = static_cast<int64_t>(4) * qy * qz * 4;
+  T* out = rho + b * nx * plane;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < cells;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int z = static_cast<int>(idx % nz), y = static_cast<int>((idx / nz) % ny);
+    const int x = static_cast<int>(idx / (static_cast<int64_t>(nz) * ny));
+    const double value = static_cast<double>(static_cast<long long>(fixed[b * cells + idx])) * inverse;
+    out[x * plane + (static_cast<int64_t>(y >> 1) * qz + (z >> 1)) * 4 + (y & 1) * 2 + (z & 1)] =
+        static_cast<T>(value);
+  }
+}
+
+// General 1-, 2- and 3-D deposits into a fixed-point grid (per-axis rule of deposit_axis).
+template <typename T>
+__global__ void __launch_bounds__(256)
+cic_deposit_fixed_kernel(const T* __restrict__ positions, const T* __restrict__ extent,
+                         const T* __restrict__ charges, int64_t n_particles, int dims, int nx,
+                         int ny, int nz, const unsigned long long* __restrict__ max_bits,
+                         unsigned long long* __restrict__ fixed) {
+  const int64_t b = blockIdx.y;
+  const T* e = extent + b * 2 * dims;
+  const T* p = positions + b * n_particles * dims;
+  const T* q = charges ? charges + b * n_particles : nullptr;
+  const int n[3] = {nx, dims > 1 ? ny : 1, dims > 2 ? nz : 1};
+  const FixedGrid grid{fixed + b * static_cast<int64_t>(n[0]) * n[1] * n[2],
+                       fixed_scale(max_bits[b], n_particles)};
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_particles;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    AxisDeposit<T> axis[3];
+    bool inside = true;
+    for (int d = 0; d < 3; ++d) {
+      if (d < dims) {
+        axis[d] = deposit_axis(p[i * dims + d], e[2 * d], e[2 * d + 1], n[d]);
+        inside = inside && axis[d].inside;
+      } else {
+        axis[d].lo = axis[d].hi = 0;
+        axis[d].w_lo = T(1);
+        axis[d].w_hi = T(0);
+      }
+    }
+    if (!inside) continue;
+    const T charge = q ? q[i] : T(1);
+    for (int a = 0; a < 2; ++a)
+      for (int c = 0; c < 2; ++c)
+        for (int d = 0; d < 2; ++d) {
+          // the order of the products follows the atomic kernels: wx wy wz, then the charge
+          T weight = a ? axis[0].w_hi : axis[0].w_lo;
+          if (dims > 1) weight *= c ? axis[1].w_hi : axis[1].w_lo;
+          if (dims > 2) weight *= d ? axis[2].w_hi : axis[2].w_lo;
+          if ((dims < 2 && c) || (dims < 3 && d) || weight == T(0)) continue;
+          const int64_t cell = (static_cast<int64_t>(a ? axis[0].hi : axis[0].lo) * n[1] +
+                                (c ? axis[1].hi : axis[1].lo)) * n[2] + (d ? axis[2].hi : axis[2].lo);
+          grid.add(cell, static_cast<double>(charge * weight));
+        }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cic_fixed_to_grid_kernel(const unsigned long long* __restrict__ fixed,
+                         const unsigned long long* __restrict__ max_bits, int64_t n_particles,
+                         int64_t cells, T* __restrict__ out) {
+  const int64_t b = blockIdx.y;
+  const double scale = fixed_scale(max_bits[b], n_particles);
+  const double inverse = scale > 0.0 ? 1.0 / scale : 0.0;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < cells;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[b * cells + idx] = static_cast<T>(
+        static_cast<double>(static_cast<long long>(fixed[b * cells + idx])) * inverse);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2178,7 +2368,7 @@ namespace {
 int launch_moments(const void* particles, int64_t particle_stride, const void* survival,
                    int64_t survival_stride, int64_t n_particles, int64_t n_beams, int32_t dtype,
                    double* stats, const ch::GridInputs& inputs, int nx, int ny, int nz,
-                   double* params, void* stream);
+                   double* params, void* stream, double* partials = nullptr);
 }
 
 extern "C" int ch_sc_beam_moments(const void* particles, int64_t particle_stride,
@@ -2212,11 +2402,35 @@ extern "C" int ch_sc_moments_and_params(
                         dtype, stats, in, nx, ny, nz, params, stream);
 }
 
+extern "C" int ch_sc_moments_and_params_deterministic(
+    const void* particles, int64_t particle_stride, const void* survival, int64_t survival_stride,
+    int64_t n_particles, int64_t n_beams, const void* energy, int64_t energy_stride,
+    int32_t energy_dtype, const void* mass_eV, int32_t mass_dtype, const void* effect_length,
+    int64_t length_stride, int32_t length_dtype, const void* extent_x, int64_t extent_x_stride,
+    const void* extent_y, int64_t extent_y_stride, const void* extent_tau,
+    int64_t extent_tau_stride, int32_t extent_dtype, int32_t nx, int32_t ny, int32_t nz,
+    int32_t dtype, double* partials, double* stats, double* params, void* stream) {
+  CH_REQUIRE(energy && mass_eV && effect_length && extent_x && extent_y && extent_tau && params &&
+                 partials,
+             "ch_sc_moments_and_params_deterministic: NULL pointer argument");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz),
+             "ch_sc_moments_and_params_deterministic: grid sizes (%d, %d, %d) must be in [2, 256]",
+             nx, ny, nz);
+  ch::GridInputs in{{energy, energy_stride, energy_dtype},
+                    {mass_eV, 0, mass_dtype},
+                    {effect_length, length_stride, length_dtype},
+                    {extent_x, extent_x_stride, extent_dtype},
+                    {extent_y, extent_y_stride, extent_dtype},
+                    {extent_tau, extent_tau_stride, extent_dtype}};
+  return launch_moments(particles, particle_stride, survival, survival_stride, n_particles, n_beams,
+                        dtype, stats, in, nx, ny, nz, params, stream, partials);
+}
+
 namespace {
 int launch_moments(const void* particles, int64_t particle_stride, const void* survival,
                    int64_t survival_stride, int64_t n_particles, int64_t n_beams, int32_t dtype,
                    double* stats, const ch::GridInputs& inputs, int nx, int ny, int nz,
-                   double* params, void* stream) {
+                   double* params, void* stream, double* partials) {
   CH_SC_COMMON_CHECKS("ch_sc_beam_moments");
   CH_REQUIRE(particles && stats && n_particles > 0, "ch_sc_beam_moments: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -2226,7 +2440,7 @@ int launch_moments(const void* particles, int64_t particle_stride, const void* s
     const int bulk = ch::bulk_compatible<float>(particles, n_particles, particle_stride);
     ch::sc_moments_kernel<float><<<grid, 256, 1024 * 7 * sizeof(float), s>>>(
         static_cast<const float*>(particles), particle_stride, static_cast<const float*>(survival),
-        survival_stride, n_particles, bulk, stats, inputs, nx, ny, nz, params);
+        survival_stride, n_particles, bulk, stats, inputs, nx, ny, nz, params, partials);
   } else {
     const int bulk = ch::bulk_compatible<double>(particles, n_particles, particle_stride);
     auto kernel = ch::sc_moments_kernel<double>;
@@ -2235,7 +2449,7 @@ int launch_moments(const void* particles, int64_t particle_stride, const void* s
                                  static_cast<int>(smem)));
     kernel<<<grid, 256, smem, s>>>(static_cast<const double*>(particles), particle_stride,
                                    static_cast<const double*>(survival), survival_stride,
-                                   n_particles, bulk, stats, inputs, nx, ny, nz, params);
+                                   n_particles, bulk, stats, inputs, nx, ny, nz, params, partials);
   }
   CH_LAUNCH_CHECK();
   return CH_OK;
@@ -2358,6 +2572,79 @@ extern "C" int ch_cic_deposit(const void* positions, const void* extent, const v
           static_cast<const T*>(charges), n_particles, nx, ny, static_cast<T*>(grid_out));
   };
   if (dtype == CH_F32) launch(0.0f); else launch(0.0);
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_sc_deposit_deterministic(
+    const void* particles, int64_t particle_stride, const void* charges, int64_t charge_stride,
+    const void* survival, int64_t survival_stride, const double* params, int64_t n_particles,
+    int64_t n_beams, int32_t nx, int32_t ny, int32_t nz, int32_t dtype, void* scratch, void* rho,
+    void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_deposit_deterministic");
+  CH_REQUIRE(particles && charges && params && rho && scratch && n_particles > 0,
+             "ch_sc_deposit_deterministic: bad arguments");
+  CH_REQUIRE(ch::grid_ok(nx, ny, nz), "ch_sc_deposit_deterministic: bad grid (%d, %d, %d)", nx, ny,
+             nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t elem = dtype == CH_F32 ? 4 : 8;
+  const int64_t cells = static_cast<int64_t>(nx) * ny * nz;
+  auto* fixed = static_cast<unsigned long long*>(scratch);
+  unsigned long long* max_bits = fixed + n_beams * cells;
+  CH_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * n_beams * (cells + 1), s));
+  CH_CUDA(cudaMemsetAsync(rho, 0, elem * nx * 16 * (ny / 2 + 1) * (nz / 2 + 1) * n_beams, s));
+  dim3 grid(ch::blocks_for(n_particles, 256), static_cast<unsigned>(n_beams));
+  dim3 cell_grid(ch::blocks_for(cells, 256), static_cast<unsigned>(n_beams));
+  auto run = [&](auto zero) {
+    using T = decltype(zero);
+    ch::cic_max_charge_kernel<T><<<grid, 256, 0, s>>>(
+        static_cast<const T*>(charges), charge_stride, static_cast<const T*>(survival),
+        survival_stride, n_particles, max_bits);
+    ch::count_launch();
+    ch::sc_deposit_fixed_kernel<T><<<grid, 256, 0, s>>>(
+        static_cast<const T*>(particles), particle_stride, static_cast<const T*>(charges),
+        charge_stride, static_cast<const T*>(survival), survival_stride, params, n_particles, nx,
+        ny, nz, max_bits, fixed);
+    ch::count_launch();
+    ch::sc_fixed_to_quad_kernel<T><<<cell_grid, 256, 0, s>>>(fixed, max_bits, n_particles, nx, ny,
+                                                             nz, static_cast<T*>(rho));
+  };
+  if (dtype == CH_F32) run(0.0f); else run(0.0);
+  CH_LAUNCH_CHECK();
+  return CH_OK;
+}
+
+extern "C" int ch_cic_deposit_deterministic(const void* positions, const void* extent,
+                                            const void* charges, int64_t n_particles,
+                                            int64_t n_beams, int32_t dims, int32_t nx, int32_t ny,
+                                            int32_t nz, int32_t dtype, void* scratch,
+                                            void* grid_out, void* stream) {
+  CH_SC_COMMON_CHECKS("ch_cic_deposit_deterministic");
+  CH_REQUIRE(dims >= 1 && dims <= 3, "ch_cic_deposit_deterministic: dims must be 1, 2 or 3");
+  CH_REQUIRE(positions && extent && grid_out && scratch && n_particles > 0,
+             "ch_cic_deposit_deterministic: bad arguments");
+  CH_REQUIRE(nx > 0 && (dims < 2 || ny > 0) && (dims < 3 || nz > 0),
+             "ch_cic_deposit_deterministic: bad grid (%d, %d, %d)", nx, ny, nz);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t cells = static_cast<int64_t>(nx) * (dims > 1 ? ny : 1) * (dims > 2 ? nz : 1);
+  auto* fixed = static_cast<unsigned long long*>(scratch);
+  unsigned long long* max_bits = fixed + n_beams * cells;
+  CH_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long) * n_beams * (cells + 1), s));
+  dim3 grid(ch::blocks_for(n_particles, 256), static_cast<unsigned>(n_beams));
+  dim3 cell_grid(ch::blocks_for(cells, 256), static_cast<unsigned>(n_beams));
+  auto run = [&](auto zero) {
+    using T = decltype(zero);
+    ch::cic_max_charge_kernel<T><<<grid, 256, 0, s>>>(
+        static_cast<const T*>(charges), n_particles, nullptr, 0, n_particles, max_bits);
+    ch::count_launch();
+    ch::cic_deposit_fixed_kernel<T><<<grid, 256, 0, s>>>(
+        static_cast<const T*>(positions), static_cast<const T*>(extent),
+        static_cast<const T*>(charges), n_particles, dims, nx, ny, nz, max_bits, fixed);
+    ch::count_launch();
+    ch::cic_fixed_to_grid_kernel<T><<<cell_grid, 256, 0, s>>>(fixed, max_bits, n_particles, cells,
+                                                              static_cast<T*>(grid_out));
+  };
+  if (dtype == CH_F32) run(0.0f); else run(0.0);
   CH_LAUNCH_CHECK();
   return CH_OK;
 }

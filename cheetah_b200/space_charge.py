@@ -77,8 +77,17 @@ class Workspace:
                 out[:, :, 1 - py : 1 - py + 2 * qy, 1 - pz : 1 - pz + 2 * qz] += part
         return out[:, :, 1 : ny + 1, 1 : nz + 1]
 
+    def fixed_point_scratch(self) -> torch.Tensor:
+        """int64 grid + scale word per beam for the deterministic deposit (allocated on demand)."""
+        if self._fixed is None:
+            n_beams, nx, ny, nz = self.phi.shape
+            self._fixed = torch.empty((n_beams * (nx * ny * nz + 1),), dtype=torch.int64,
+                                      device=self.phi.device)
+        return self._fixed
+
     def __init__(self, n_beams: int, grid_shape: tuple, dtype, device) -> None:
         nx, ny, nz = grid_shape
+        self._fixed = None
         cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
         # FFT length per axis: the next power of two >= 2 n (include/cheetah_b200.h)
         lx, ly, lz = (fft_len(v) for v in (nx, ny, nz))
@@ -193,6 +202,11 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
     forces = torch.empty((n_beams, n, 3), dtype=dtype, device=device) if want_intermediates else None
     stream = _capi.current_stream(device)
     ws.prepared_next = None
+    # torch.use_deterministic_algorithms: fixed-order moment sums and fixed-point deposit, and no
+    # moments fused into the gather (its cross-CTA sums are float64 atomics)
+    deterministic = torch.are_deterministic_algorithms_enabled()
+    if deterministic:
+        next_element = None
     reuse = (
         prepared is not None and prepared.workspace is ws and prepared.element is element
         and element is not None
@@ -201,14 +215,23 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
         if reuse:
             ws.slot = prepared.slot
         else:
-            _capi.check(lib.ch_sc_moments_and_params(
+            moment_args = (
                 p.data_ptr(), p_stride, w.data_ptr(), w_stride, n, n_beams,
                 e.data_ptr(), e_stride, _capi.dtype_code(e.dtype),
                 mass.data_ptr(), _capi.dtype_code(mass.dtype),
                 length.data_ptr(), l_stride, _capi.dtype_code(length.dtype),
                 ext[0][0].data_ptr(), ext[0][1], ext[1][0].data_ptr(), ext[1][1],
-                ext[2][0].data_ptr(), ext[2][1], code,
-                nx, ny, nz, code, ws.stats.data_ptr(), ws.params.data_ptr(), stream))
+                ext[2][0].data_ptr(), ext[2][1], code, nx, ny, nz, code,
+            )
+            if deterministic:
+                partials = torch.empty((n_beams * ((n + 1023) // 1024) * 8,), dtype=torch.float64,
+                                       device=device)
+                _capi.check(lib.ch_sc_moments_and_params_deterministic(
+                    *moment_args, partials.data_ptr(), ws.stats.data_ptr(), ws.params.data_ptr(),
+                    stream))
+            else:
+                _capi.check(lib.ch_sc_moments_and_params(
+                    *moment_args, ws.stats.data_ptr(), ws.params.data_ptr(), stream))
         # the Green-function chain only needs the grid parameters: it runs on a side stream
         # concurrently with the deposit and the first two FFT passes of the charge
         main = torch.cuda.current_stream(device)
@@ -229,9 +252,17 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
             ws.green_spectrum.data_ptr(), side.cuda_stream))
         joined = torch.cuda.Event()
         joined.record(side)
-        _capi.check(lib.ch_sc_deposit(
-            p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
-            ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_quad.data_ptr(), stream))
+        if deterministic:
+            # fixed-point accumulation: bit-identical from run to run (ch_sc_deposit_deterministic)
+            _capi.check(lib.ch_sc_deposit_deterministic(
+                p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
+                ws.params.data_ptr(), n, n_beams, nx, ny, nz, code,
+                ws.fixed_point_scratch().data_ptr(), ws.rho_quad.data_ptr(), stream))
+        else:
+            _capi.check(lib.ch_sc_deposit(
+                p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
+                ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_quad.data_ptr(),
+                stream))
         main.wait_event(joined)
         _capi.check(lib.ch_sc_poisson_solve(
             ws.rho_quad.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
@@ -369,7 +400,15 @@ def cloud_in_cell_charge_deposition(positions, bins, extent=None, charges=None):
     grid = torch.empty((n_beams, *shape), dtype=dtype, device=device)
     padded = shape + [1] * (3 - dims)
     with _capi.device_guard(device):
-        _capi.check(_capi.lib().ch_cic_deposit(
-            pos.data_ptr(), ext.data_ptr(), _capi.ptr(q), n, n_beams, dims, *padded,
-            _capi.dtype_code(dtype), grid.data_ptr(), _capi.current_stream(device)))
+        if torch.are_deterministic_algorithms_enabled():
+            scratch = torch.empty((n_beams * (math.prod(shape) + 1),), dtype=torch.int64,
+                                  device=device)
+            _capi.check(_capi.lib().ch_cic_deposit_deterministic(
+                pos.data_ptr(), ext.data_ptr(), _capi.ptr(q), n, n_beams, dims, *padded,
+                _capi.dtype_code(dtype), scratch.data_ptr(), grid.data_ptr(),
+                _capi.current_stream(device)))
+        else:
+            _capi.check(_capi.lib().ch_cic_deposit(
+                pos.data_ptr(), ext.data_ptr(), _capi.ptr(q), n, n_beams, dims, *padded,
+                _capi.dtype_code(dtype), grid.data_ptr(), _capi.current_stream(device)))
     return grid.reshape(*vector_shape, *shape)

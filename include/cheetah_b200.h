@@ -448,6 +448,35 @@ int ch_cic_deposit(const void* positions, const void* extent, const void* charge
                    int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                    void* grid, void* stream);
 
+/* ch_sc_moments_and_params with the per-CTA sums added in a fixed order by the last CTA instead
+ * of with float64 atomics (deterministic mode; partials: n_beams * ceil(N / 1024) * 8 doubles). */
+int ch_sc_moments_and_params_deterministic(
+    const void* particles, int64_t particle_stride, const void* survival, int64_t survival_stride,
+    int64_t n_particles, int64_t n_beams, const void* energy, int64_t energy_stride,
+    int32_t energy_dtype, const void* mass_eV, int32_t mass_dtype, const void* effect_length,
+    int64_t length_stride, int32_t length_dtype, const void* extent_x, int64_t extent_x_stride,
+    const void* extent_y, int64_t extent_y_stride, const void* extent_tau,
+    int64_t extent_tau_stride, int32_t extent_dtype, int32_t nx, int32_t ny, int32_t nz,
+    int32_t dtype, double* partials, double* stats, double* params, void* stream);
+
+/* Deterministic variants of ch_sc_deposit and ch_cic_deposit: the same deposits accumulated in
+ * 64-bit fixed point (integer atomics commute, so the result does not depend on the order in
+ * which the hardware retires them: bit-identical from run to run).  The reference's
+ * scatter_add_ is order-dependent on CUDA; its tests ask torch for deterministic algorithms
+ * (tests/conftest.py:204), and the Python layer selects these entry points when
+ * torch.are_deterministic_algorithms_enabled().  One unit is ~2^-41 of the largest particle
+ * charge.  scratch: n_beams * (cells + 1) * 8 bytes.  About 3x the time of the float atomics. */
+int ch_sc_deposit_deterministic(const void* particles, int64_t particle_stride,
+                                const void* charges, int64_t charge_stride,
+                                const void* survival, int64_t survival_stride,
+                                const double* params, int64_t n_particles, int64_t n_beams,
+                                int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                                void* scratch, void* rho, void* stream);
+int ch_cic_deposit_deterministic(const void* positions, const void* extent, const void* charges,
+                                 int64_t n_particles, int64_t n_beams, int32_t dims,
+                                 int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                                 void* scratch, void* grid, void* stream);
+
 /* Integrated Green function: _integrated_potential + _integrated_green_function
  * (space_charge_kick.py:103-123, :163-291).  The antiderivative is evaluated ONCE per
  * half-shifted lattice point in fp64 (lattice [B][(nx+1)(ny+1)(nz+1)] doubles; the reference

@@ -452,3 +452,64 @@ def test_arbitrary_grid_shapes_match_the_oracle(grid, tag, dtype):
         assert err < (1e-8 if dtype == torch.float64 else 3e-3), (col, float(err))
     for col in (0, 2, 4, 6):
         assert torch.equal(out.particles.cpu()[:, col], particles[:, col])
+
+
+@pytest.fixture()
+def deterministic_algorithms():
+    previous = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    yield
+    torch.use_deterministic_algorithms(previous)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_deterministic_deposit_is_bit_reproducible(deterministic_algorithms, dtype):
+    """With torch.use_deterministic_algorithms (what the reference's test suite sets,
+    tests/conftest.py:204) the deposits accumulate in fixed point: every run gives the same bits,
+    whatever order the atomics retire in; the values agree with the float atomics to rounding."""
+    from cheetah_b200 import space_charge
+
+    torch.manual_seed(21)
+    n = 200_000
+    sigma = torch.tensor([2e-4, 3e-6, 1.5e-4, 5e-6, 2e-5, 1e-3], dtype=torch.float64)
+    particles = (torch.randn((3, n, 7), dtype=torch.float64)
+                 * torch.cat([sigma, torch.ones(1)])).to(dtype)
+    particles[..., 6] = 1.0
+    charges = (torch.rand((3, n), dtype=torch.float64) * 2e-15).to(dtype)
+    args = (
+        particles.to(DEVICE), torch.tensor(4e7, dtype=dtype, device=DEVICE), charges.to(DEVICE),
+        torch.rand((3, n), dtype=torch.float64).to(dtype).to(DEVICE),
+        torch.tensor(510998.95, dtype=dtype, device=DEVICE),
+        torch.tensor(0.4, dtype=dtype, device=DEVICE),
+        tuple(torch.tensor(3.0, dtype=dtype, device=DEVICE) for _ in range(3)), (32, 32, 32),
+    )
+    grids, outs = [], []
+    for _ in range(3):
+        out, ws = space_charge.kick(*args)
+        torch.cuda.synchronize()
+        grids.append(ws.charge_grid().clone())
+        outs.append(out.clone())
+    assert torch.equal(grids[0], grids[1]) and torch.equal(grids[0], grids[2])
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    torch.use_deterministic_algorithms(False)
+    _, ws = space_charge.kick(*args)
+    atomic = ws.charge_grid()
+    scale = atomic.abs().max()
+    assert float((atomic - grids[0]).abs().max() / scale) < (1e-5 if dtype == torch.float32 else 1e-12)
+    assert torch.allclose(grids[0].sum(dim=(1, 2, 3)).double(), atomic.sum(dim=(1, 2, 3)).double(),
+                          rtol=1e-5)
+
+    # general cloud-in-cell entry (1, 2 and 3 dimensions)
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    for dims in (1, 2, 3):
+        positions = torch.rand((2, 50_000, dims), dtype=dtype, device=DEVICE)
+        weights = torch.rand((2, 50_000), dtype=dtype, device=DEVICE) - 0.3  # signed charges
+        bins = (17, 9, 12)[:dims]
+        runs = [space_charge.cloud_in_cell_charge_deposition(positions, bins, None, weights)
+                for _ in range(2)]
+        assert torch.equal(runs[0], runs[1])
+        torch.use_deterministic_algorithms(False)
+        reference_run = space_charge.cloud_in_cell_charge_deposition(positions, bins, None, weights)
+        torch.use_deterministic_algorithms(True, warn_only=True)
+        tol = 2e-5 if dtype == torch.float32 else 1e-12
+        assert float((runs[0] - reference_run).abs().max() / reference_run.abs().max()) < tol
