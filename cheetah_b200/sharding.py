@@ -37,17 +37,32 @@ def broadcast_module(module: torch.nn.Module, src: int = 0) -> int:
     return total
 
 
+# trailing (non-vector) dimensions of the fields that have any; every other field is a scalar
+# per setting
+_INNER_DIMS = {"misalignment": 1, "pixel_size": 1, "resolution": 1, "predefined_transfer_map": 2}
+
+
 def shard_segment(segment, n_settings: int, rank: int, world_size: int):
-    """Slice, in place, every parameter whose leading dimension is the settings batch."""
+    """Slice, in place, every buffer and parameter whose VECTOR shape starts with the settings
+    batch.  The vector shape is what is left of a tensor's shape after the field's own trailing
+    dimensions (2 for ``misalignment`` / ``pixel_size``, 7 x 7 for ``predefined_transfer_map``),
+    so a (2,) ``pixel_size`` is not mistaken for two settings, nor a (7, 7) map for seven."""
     begin, end = shard_bounds(n_settings, rank, world_size)
     from .lowering import flatten
 
     for element in flatten([segment]):
-        for name, tensor in list(element.named_buffers(recurse=False)):
-            if tensor.dim() >= 1 and tensor.shape[0] == n_settings and name != "misalignment":
-                setattr(element, name, tensor[begin:end].contiguous())
-            elif name == "misalignment" and tensor.dim() == 2 and tensor.shape[0] == n_settings:
-                setattr(element, name, tensor[begin:end].contiguous())
+        named = list(element.named_buffers(recurse=False)) + list(
+            element.named_parameters(recurse=False))
+        for name, tensor in named:
+            vector_dims = tensor.dim() - _INNER_DIMS.get(name, 0)
+            if vector_dims < 1 or tensor.shape[0] != n_settings:
+                continue
+            piece = tensor.detach()[begin:end].contiguous()
+            if name in element._parameters:
+                element._parameters[name] = torch.nn.Parameter(
+                    piece, requires_grad=tensor.requires_grad)
+            else:
+                setattr(element, name, piece)
     return begin, end
 
 

@@ -123,3 +123,32 @@ def test_two_ranks_gather_reduced_observables():
         assert torch.equal(got["s"], index * 0.5)
         assert torch.equal(got["cov"], index[:, None, None] * torch.eye(6, dtype=torch.float64))
         assert got["energy"].dim() == 0
+
+
+def test_shard_segment_respects_the_inner_dimensions_of_a_field():
+    """A (2,) ``pixel_size`` / ``misalignment`` is not two settings and a (7, 7) transfer map not
+    seven; per-setting parameters registered as nn.Parameter are sliced too."""
+    import torch
+
+    import cheetah_b200 as cb
+    from cheetah_b200 import sharding
+
+    quad = cb.Quadrupole(length=torch.tensor(0.2), k1=torch.tensor([1.0, 2.0]),
+                         misalignment=torch.tensor([1e-3, -2e-3]))
+    screen = cb.Screen(pixel_size=torch.tensor([1e-5, 2e-5]), resolution=(10, 10))
+    sharding.shard_segment(cb.Segment([quad, screen]), 2, rank=1, world_size=2)
+    assert quad.k1.shape == (1,) and float(quad.k1) == 2.0
+    assert quad.misalignment.shape == (2,) and screen.pixel_size.shape == (2,)
+
+    tm = torch.eye(7).repeat(7, 1, 1)
+    custom = cb.CustomTransferMap(predefined_transfer_map=tm.clone(), length=torch.ones(7))
+    one = cb.CustomTransferMap(predefined_transfer_map=torch.eye(7))
+    sharding.shard_segment(cb.Segment([custom, one]), 7, rank=0, world_size=7)
+    assert custom.predefined_transfer_map.shape == (1, 7, 7) and custom.length.shape == (1,)
+    assert one.predefined_transfer_map.shape == (7, 7)
+
+    drift = cb.Drift(length=torch.tensor([0.5, 0.6, 0.7, 0.8]))
+    drift._parameters["length"] = torch.nn.Parameter(drift._buffers.pop("length"),
+                                                     requires_grad=False)
+    sharding.shard_segment(cb.Segment([drift]), 4, rank=1, world_size=2)
+    assert drift.length.shape == (2,) and float(drift.length[0]) == pytest.approx(0.7)
