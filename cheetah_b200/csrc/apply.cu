@@ -114,6 +114,16 @@ __device__ __forceinline__ T affine_row(const T* c, const T (&p)[7]) {
 }
 
 
+// the same without the tau column (CH_FLAG_NO_TAU_COLUMN: c[4] == 0)
+template <typename T, bool UNIT7>
+__device__ __forceinline__ T affine_row_no_tau(const T* c, const T (&p)[7]) {
+  T acc = UNIT7 ? c[6] : c[6] * p[6];
+  acc = fma_t(c[5], p[5], acc);
+#pragma unroll
+  for (int j = 3; j >= 0; --j) acc = fma_t(c[j], p[j], acc);
+  return acc;
+}
+
 __device__ __forceinline__ uint32_t record_flags(float header) { return __float_as_uint(header); }
 __device__ __forceinline__ uint32_t record_flags(double header) {
   return static_cast<uint32_t>(__double_as_longlong(header));
@@ -133,7 +143,10 @@ using Acc = T;
 // the final map into the staging tile.  SPARSE drops the structurally-zero terms (flags).
 // With MOMENTS the outgoing coordinates are also accumulated into `acc` (see the kernel) about
 // `pilot`, the image of the beam's first particle under the same map.
-template <typename T, int P, int THREADS, bool UNIT7, bool SPARSE, int MOMENTS, bool WRITE,
+// MODE: 0 dense (72 multiply-adds with three apertures), 1 sparse (29; all four CH_FLAG_* hold),
+// 2 coupled (56: x-y coupling and dispersion allowed, but no tau column in rows 0-3 and delta
+// untouched -- solenoids, tilted magnets, dipoles without RF)
+template <typename T, int P, int THREADS, bool UNIT7, int MODE, int MOMENTS, bool WRITE,
           bool CAVITY, int ROW = 7>
 __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
                                                 uint32_t elliptical_mask, const T (&p)[P][7],
@@ -149,10 +162,13 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       T x, y;
-      if constexpr (SPARSE) {
+      if constexpr (MODE == 1) {
         const T w = UNIT7 ? T(1) : p[k][6];
         x = fma_t(q[0], p[k][0], fma_t(q[1], p[k][1], fma_t(q[5], p[k][5], UNIT7 ? q[6] : q[6] * w)));
         y = fma_t(q[9], p[k][2], fma_t(q[10], p[k][3], UNIT7 ? q[13] : q[13] * w));
+      } else if constexpr (MODE == 2) {
+        x = affine_row_no_tau<T, UNIT7>(q, p[k]);
+        y = affine_row_no_tau<T, UNIT7>(q + 7, p[k]);
       } else {
         x = affine_row<T, UNIT7>(q, p[k]);
         y = affine_row<T, UNIT7>(q + 7, p[k]);
@@ -191,7 +207,7 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
   };
   // the six outgoing coordinates of one particle
   auto map_rows = [&](const T (&in)[7], T (&out)[6]) {
-    if constexpr (SPARSE) {
+    if constexpr (MODE == 1) {
       const T w = UNIT7 ? T(1) : in[6];
       auto constant = [&](int i) { return UNIT7 ? m[i * 7 + 6] : m[i * 7 + 6] * w; };
       out[0] = fma_t(m[0], in[0], fma_t(m[1], in[1], fma_t(m[5], in[5], constant(0))));
@@ -200,6 +216,11 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
       out[3] = fma_t(m[23], in[2], fma_t(m[24], in[3], constant(3)));
       out[4] = fma_t(m[28], in[0],
                      fma_t(m[29], in[1], fma_t(m[32], in[4], fma_t(m[33], in[5], constant(4)))));
+      out[5] = in[5];
+    } else if constexpr (MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[i] = affine_row_no_tau<T, UNIT7>(m + i * 7, in);
+      out[4] = affine_row<T, UNIT7>(m + 28, in);
       out[5] = in[5];
     } else {
 #pragma unroll
@@ -211,7 +232,7 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       T* row = stage + (tid + k * THREADS) * ROW;
-      if constexpr (SPARSE) {
+      if constexpr (MODE == 1) {
         const T w = UNIT7 ? T(1) : p[k][6];
         auto constant = [&](int i) { return UNIT7 ? m[i * 7 + 6] : m[i * 7 + 6] * w; };
         row[0] = fma_t(m[0], p[k][0], fma_t(m[1], p[k][1], fma_t(m[5], p[k][5], constant(0))));
@@ -221,6 +242,11 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
         row[4] = fma_t(m[28], p[k][0],
                        fma_t(m[29], p[k][1],
                              fma_t(m[32], p[k][4], fma_t(m[33], p[k][5], constant(4)))));
+        row[5] = p[k][5];
+      } else if constexpr (MODE == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) row[i] = affine_row_no_tau<T, UNIT7>(m + i * 7, p[k]);
+        row[4] = affine_row<T, UNIT7>(m + 28, p[k]);
         row[5] = p[k][5];
       } else {
 #pragma unroll
@@ -473,11 +499,15 @@ apply_maps_kernel(const ApplyArgs<T> a) {
     }
     const T* cavity =
         rec + CH_RECORD_HEADER + CH_RECORD_MAP + a.n_apertures * CH_RECORD_APERTURE;
+    constexpr uint32_t kCoupled = CH_FLAG_NO_TAU_COLUMN | CH_FLAG_DELTA_IDENTITY;
     if ((flags & kSparse) == kSparse)
-      process_setting<T, P, THREADS, UNIT7, true, MOMENTS, WRITE, CAVITY, ROW>(
+      process_setting<T, P, THREADS, UNIT7, 1, MOMENTS, WRITE, CAVITY, ROW>(
+          rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc, cavity);
+    else if ((flags & kCoupled) == kCoupled && !CAVITY)
+      process_setting<T, P, THREADS, UNIT7, 2, MOMENTS, WRITE, CAVITY, ROW>(
           rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc, cavity);
     else
-      process_setting<T, P, THREADS, UNIT7, false, MOMENTS, WRITE, CAVITY, ROW>(
+      process_setting<T, P, THREADS, UNIT7, 0, MOMENTS, WRITE, CAVITY, ROW>(
           rec, a.n_apertures, a.elliptical_mask, p, sv, stage, tid, first, pilot, acc, cavity);
     if constexpr (COMPACT) {
       if (a.survival_u8 != nullptr) {

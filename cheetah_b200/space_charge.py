@@ -165,13 +165,15 @@ def _workspace(n_beams: int, grid_shape: tuple, dtype, device) -> Workspace:
 
 def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, grid_shape,
          want_intermediates: bool = False, prepared: Prepared | None = None, element=None,
-         fuse_records=None, next_element=None):
+         fuse_records=None, next_element=None, records_ready=None):
     """Run one kick on already-broadcast inputs; returns (particles_out [B,N,7], workspace).
 
     ``prepared``: the grid parameters were computed by the previous kick (skip the moments pass).
     ``fuse_records`` (``[1 or B, record_len]`` compose records): apply that linear map to the
-    kicked particles in the same pass.  ``next_element``: also compute the moments and grid
-    parameters of that following SpaceChargeKick; ``workspace.prepared_next`` is then set."""
+    kicked particles in the same pass (``records_ready``: CUDA event after which they are
+    valid, when they were composed on another stream).  ``next_element``: also compute the moments
+    and grid parameters of that following SpaceChargeKick; ``workspace.prepared_next`` is then
+    set."""
     device, dtype = particles.device, particles.dtype
     lib = _capi.lib()
     code = _capi.dtype_code(dtype)
@@ -267,6 +269,8 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
         _capi.check(lib.ch_sc_poisson_solve(
             ws.rho_quad.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
             nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))
+        if records_ready is not None:
+            main.wait_event(records_ready)
         nxt = None
         next_slot = 1 - ws.slot
         if next_element is not None:
@@ -335,7 +339,7 @@ def track(element, incoming):
 
 
 def track_fused(element, incoming, prepared: Prepared | None = None, fuse_records=None,
-                next_element=None):
+                next_element=None, records_ready=None):
     """``SpaceChargeKick.track`` plus, optionally, the linear map of the following section and
     the moments of the following kick in the same particle pass.  Returns (beam, Prepared|None);
     the caller adds the section length to ``s`` when it passed ``fuse_records``."""
@@ -357,7 +361,7 @@ def track_fused(element, incoming, prepared: Prepared | None = None, fuse_record
         incoming.species.mass_eV, element.effect_length,
         (element.grid_extent_x, element.grid_extent_y, element.grid_extent_tau),
         element.grid_shape, prepared=prepared, element=element, fuse_records=fuse_records,
-        next_element=next_element,
+        next_element=next_element, records_ready=records_ready,
     )
     # the reference drops the (1,) helper dimension again when nothing is vectorised
     out_shape = _bshape(

@@ -456,6 +456,15 @@ def second_order_transfer_map(element, energy: torch.Tensor, species) -> torch.T
 # Set to False to run every stage as its own pass (tests compare the two paths).
 fuse_space_charge = True
 
+_compose_streams: dict = {}
+
+
+def _compose_stream(device) -> torch.cuda.Stream:
+    stream = _compose_streams.get(device)
+    if stream is None:
+        stream = _compose_streams[device] = torch.cuda.Stream(device)
+    return stream
+
 
 def _track_space_charge(program, stages: list, i: int, beam, prepared):
     """SpaceChargeKick stage ``i`` with its neighbours fused into the gather pass when the lattice
@@ -488,14 +497,30 @@ def _track_space_charge(program, stages: list, i: int, beam, prepared):
                         candidate.effect_length, candidate.grid_extent_x,
                         candidate.grid_extent_y, candidate.grid_extent_tau))):
                 next_element = candidate
-    new_s = None
+    records_ready = None
     if section is not None:
-        records, vm = _compose(program, section, beam.energy, beam.species, beam.particles.dtype)
-        new_s = beam.s + _section_length(records, vm, section.length_shape)
+        # The maps of the following section only depend on the lattice and the beam energy: they
+        # are composed on a side stream while the kick's deposit and Poisson solve run, and the
+        # gather pass waits for them (one beam: 20 us of 128 per kick off the critical path).
+        device = beam.particles.device
+        main = torch.cuda.current_stream(device)
+        side = _compose_stream(device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            records, vm = _compose(program, section, beam.energy, beam.species,
+                                   beam.particles.dtype)
+            records_ready = torch.cuda.Event()
+            records_ready.record(side)
+        records.record_stream(main)
     outgoing, prepared = space_charge.track_fused(
-        element, beam, prepared=prepared, fuse_records=records, next_element=next_element
+        element, beam, prepared=prepared, fuse_records=records, next_element=next_element,
+        records_ready=records_ready,
     )
     if section is not None:
+        # (the kick made the main stream wait for the records)
+        new_s = beam.s + _section_length(records, vm, section.length_shape)
         outgoing = _new_beam(
             outgoing, outgoing.particles, outgoing.energy, outgoing.particle_charges,
             outgoing.survival_probabilities, new_s, outgoing.species.clone(),
