@@ -1748,33 +1748,43 @@ sc_field_brick_kernel(const float* __restrict__ phi, const double* __restrict__ 
   const int pz = nz + 1, py = kBrickRows + 1;
   const int node_count = 2 * py * pz;
   const int plane = ny * nz;
-  for (int t = threadIdx.x; t < node_count; t += blockDim.x) {
-    const int k = t % pz, j = (t / pz) % py, a = t / (pz * py);
+  // one warp per node row (a, j): lanes run along z, no integer divisions (the kernel is bound
+  // by instruction issue, ncu: 81 %)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (int row = warp; row < 2 * py; row += warps) {
+    const int a = row >= py ? 1 : 0, j = row - a * py;
     const int i = cx + a, jj = y0 + j;
-    float ex = 0.0f, ey = 0.0f, ez = 0.0f;
-    if (i < nx && jj < ny && k < nz) {
-      const int idx = (i * ny + jj) * nz + k;
-      if (i > 0 && i < nx - 1) ex = scale * ((f[idx + plane] - f[idx - plane]) * hx);
-      if (jj > 0 && jj < ny - 1) ey = scale * ((f[idx + nz] - f[idx - nz]) * hy);
-      if (k > 0 && k < nz - 1) ez = scale * ((f[idx + 1] - f[idx - 1]) * hz);
+    const bool inside_xy = i < nx && jj < ny;
+    const bool x_ok = i > 0 && i < nx - 1, y_ok = jj > 0 && jj < ny - 1;
+    const int base = (i * ny + jj) * nz;
+    for (int k = lane; k < pz; k += 32) {
+      float ex = 0.0f, ey = 0.0f, ez = 0.0f;
+      if (inside_xy && k < nz) {
+        const int idx = base + k;
+        if (x_ok) ex = scale * ((f[idx + plane] - f[idx - plane]) * hx);
+        if (y_ok) ey = scale * ((f[idx + nz] - f[idx - nz]) * hy);
+        if (k > 0 && k < nz - 1) ez = scale * ((f[idx + 1] - f[idx - 1]) * hz);
+      }
+      const int t = row * pz + k;
+      nodes[t] = ex;
+      nodes[node_count + t] = ey;
+      nodes[2 * node_count + t] = ez;
     }
-    nodes[t] = ex;
-    nodes[node_count + t] = ey;
-    nodes[2 * node_count + t] = ez;
   }
   __syncthreads();
-  // item = (row, cz, component s, half h): 4 corner values = one 16-byte store; consecutive items
-  // are consecutive in memory.  Half h holds corners q = 4 h + (2 dy + dz): dx = h.
+  // item = (cz, component, half h) of one cell row: 4 corner values = one 16-byte store;
+  // consecutive items are consecutive in memory.  Half h holds corners q = 4 h + (2 dy + dz).
   const int rows = min(kBrickRows, ny - y0);
   float4* out = reinterpret_cast<float4*>(
       bricks + (blockIdx.z * total + (static_cast<int64_t>(cx) * ny + y0) * nz) * kBrickFloats);
-  const int items = rows * nz * 6;
-  for (int t = threadIdx.x; t < items; t += blockDim.x) {
-    const int cell = t / 6, sub = t - cell * 6;
-    const int h = sub & 1, comp = sub >> 1;
-    const int r = cell / nz, cz = cell - r * nz;
-    const float* src = nodes + comp * node_count + (h * py + r) * pz + cz;
-    out[t] = make_float4(src[0], src[1], src[pz], src[pz + 1]);
+  const int row_items = nz * 6;
+  for (int r = 0; r < rows; ++r) {
+    for (int t = threadIdx.x; t < row_items; t += blockDim.x) {
+      const int cz = t / 6, sub = t - cz * 6;
+      const int h = sub & 1, comp = sub >> 1;
+      const float* src = nodes + comp * node_count + (h * py + r) * pz + cz;
+      out[r * row_items + t] = make_float4(src[0], src[1], src[pz], src[pz + 1]);
+    }
   }
 }
 

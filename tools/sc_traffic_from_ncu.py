@@ -51,18 +51,16 @@ def main(path: str, beams: int) -> None:
         entry[0] += 1
         entry[1] += total
         entry[2] += float(row[time_col]) * {"us": 1.0, "ms": 1e3, "ns": 1e-3}[units[time_col]]
-    # launches per kick: the fused gather runs once per kick
-    kicks = max(1, per_kernel.get("sc_gather_brick_kernel", per_kernel.get(
-        "sc_gather_kick_kernel", [1]))[0])
+    # launches of each kernel in ONE kick (the capture window may straddle two kicks)
+    per_kick_launches = {"fftr_even_strided_kernel": 2, "fft_even_pass_kernel": 3,
+                         "fftr_strided_kernel": 3, "fft_strided_kernel": 3}
+    kicks = 1
     stages = defaultdict(float)
     detail = {}
     for kernel, (launches, total, us) in per_kernel.items():
-        if kernel == "sc_moments_kernel":
-            per_kick = total / launches  # first kick only
-        else:
-            per_kick = total / kicks
-        stages[STAGES[kernel]] += per_kick / beams
-        detail[kernel] = {"launches": launches, "dram_bytes_per_launch": total / launches,
+        per_launch = total / launches
+        stages[STAGES[kernel]] += per_launch * per_kick_launches.get(kernel, 1) / beams
+        detail[kernel] = {"launches_captured": launches, "dram_bytes_per_launch": per_launch,
                           "us_per_launch_under_ncu": us / launches}
     json.dump({
         "source": path, "beams": beams, "kicks_captured": kicks,
