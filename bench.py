@@ -685,10 +685,12 @@ def run_ares(args) -> None:
         )
         tracker = HostTracker(host_segment, args.particles, per_rank, device=device, dtype=dtype,
                               chunk_settings=64, ring=4)
-        checksum = Checksum()
+        # reader threads of the host consumer: the box's cores are shared by the ranks
+        readers = max(2, min(12, ((os.cpu_count() or 8) - 4) // world))
+        checksum = Checksum(readers)
         tracker.track(host_beam, consumer=checksum)  # warm-up (pins, lowers, first-touch)
         ctx.barrier()
-        checksum = Checksum()
+        checksum = Checksum(readers)
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             tracker.track(host_beam, consumer=checksum)

@@ -510,3 +510,31 @@ def test_incoming_survival_with_vector_dims_of_its_own(dtype):
     assert torch.equal(out.survival_probabilities.cpu(), expected["survival_probabilities"])
     err = gu.column_scaled_error(out.particles, expected["particles"])
     assert err < (1e-12 if dtype == torch.float64 else 2e-6)
+
+
+def test_survey_ranges_k1_30_parity():
+    """SURVEY 8d's first recipe for config 3 -- k1 ~ U(-30, 30) 1/m^2, corrector angles ~
+    U(-1e-3, 1e-3) rad -- which the bench narrows (these ranges over-focus ARES until the beam is
+    kilometres wide).  As a parity case it exercises map entries up to ~1e9: the apertures are
+    opened to 100 m instead (mean survival 56 %), float32 on the GPU against the
+    float64 oracle on the same inputs."""
+    import workloads
+    from oracle import lattice_io
+
+    n_settings, n = 64, 5000
+    particles = workloads.twiss_beam_particles(n)
+    lattice32 = workloads.ares_survey_ranges(n_settings, torch.float32, x_max=100.0)
+    truth = oracle.track(
+        lattice_io.cast(lattice_io.cast(lattice32, torch.float32), torch.float64),
+        workloads.oracle_beam(particles.float(), torch.float64),
+    )
+    segment = workloads.product_segment(lattice32, DEVICE, torch.float32)
+    out = segment.track(workloads.product_beam(particles, DEVICE, torch.float32))
+    survival = truth["survival_probabilities"]
+    assert 0.3 < float(survival.mean()) < 0.7
+    assert torch.equal(out.survival_probabilities.cpu().double(), survival)
+    assert float(truth["particles"].abs().max()) > 1e3  # the regime this test is about
+    # per setting: error relative to the largest coordinate of that setting and column
+    scale = truth["particles"].abs().amax(dim=-2, keepdim=True).clamp_min(1e-30)
+    err = ((out.particles.cpu().double() - truth["particles"]).abs() / scale)[..., :6].max()
+    assert float(err) < 2e-6, float(err)
