@@ -1411,7 +1411,7 @@ sc_field_kernel(const T* __restrict__ phi, const double* __restrict__ params, in
 // buffer per device: like the reference ("not thread-safe by construction"), two host
 // threads must not track space charge on the same device at the same time.
 constexpr int kConstMaps = 256;
-constexpr int kConstMapPitch = 44;  // 42 coefficients, rows of 7
+constexpr int kConstMapPitch = 44;  // the record's header (flags, length) + 42 coefficients
 __constant__ float c_gather_maps[kConstMaps * kConstMapPitch];
 
 template <typename T>
@@ -1718,8 +1718,12 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
 // by shuffle (2.7 ms: fewer L1 wavefronts but 60 shuffles per particle); a two-stage software
 // pipeline at 2 CTAs per SM (3.3 ms); 4 CTAs per SM at 64 registers (2.7-2.9 ms); building and
 // consuming the bricks in L2-sized groups of beams (1 beam per group 5.1 ms, 2: 4.4, all: 3.3
-// including the field pass -- short launches pay their tails, and the gather is bound inside
-// the SM: its time follows the instruction count).
+// including the field pass -- short launches pay their tails).  What bounds the kernel now
+// (ncu at 128 beams, profiles/r02_sc_kernels_b128_ncu_full.txt): warps wait on their brick and
+// tile loads (long scoreboard 7.3 per issue) with 24 warps per SM at 80 registers; neither fewer
+// instructions (the sparse map saves 28 FMAs per particle: no change) nor L2-resident bricks
+// (all beams reading one array: 3.14 instead of 3.26 ms with the field pass) move it -- it is
+// the number of loads in flight per SM that a register-staged gather can keep.
 constexpr int kBrickFloats = 24;
 constexpr int kBrickRows = 8;
 
@@ -1961,12 +1965,30 @@ sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_
       if (fusion.records != nullptr) {  // particles @ tm.mT of the following linear section
         float mapped[6];
         if (fusion.const_maps) {
+          const float* m = cmap + CH_RECORD_HEADER;
+          // the record's sparsity flags (ch_compose_maps; uniform over the CTA): an uncoupled
+          // section without tau dependence -- drifts, upright quadrupoles, correctors -- needs 14
+          // of the 42 multiply-adds (the chains of apply_maps_kernel's sparse branch)
+          constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
+                                       CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
+          if ((__float_as_uint(cmap[0]) & kSparse) == kSparse) {
+            const float w = row[6];
+            mapped[0] = fmaf(m[0], row[0], fmaf(m[1], row[1], fmaf(m[5], row[5], m[6] * w)));
+            mapped[1] = fmaf(m[7], row[0], fmaf(m[8], row[1], fmaf(m[12], row[5], m[13] * w)));
+            mapped[2] = fmaf(m[16], row[2], fmaf(m[17], row[3], m[20] * w));
+            mapped[3] = fmaf(m[23], row[2], fmaf(m[24], row[3], m[27] * w));
+            mapped[4] = fmaf(m[28], row[0],
+                             fmaf(m[29], row[1],
+                                  fmaf(m[32], row[4], fmaf(m[33], row[5], m[34] * w))));
+            mapped[5] = row[5];
+          } else {
 #pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            float a = cmap[i * 7 + 6] * row[6];
+            for (int i = 0; i < 6; ++i) {
+              float a = m[i * 7 + 6] * row[6];
 #pragma unroll
-            for (int j = 5; j >= 0; --j) a = fmaf(cmap[i * 7 + j], row[j], a);
-            mapped[i] = a;
+              for (int j = 5; j >= 0; --j) a = fmaf(m[i * 7 + j], row[j], a);
+              mapped[i] = a;
+            }
           }
         } else {
 #pragma unroll
@@ -2877,10 +2899,10 @@ int gather_fused(const FusedArgs& a, cudaStream_t s) {
       void* symbol = nullptr;
       CH_CUDA(cudaGetSymbolAddress(&symbol, ch::c_gather_maps));
       CH_CUDA(cudaMemcpy2DAsync(
-          symbol, sizeof(float) * ch::kConstMapPitch,
-          static_cast<const float*>(a.records) + CH_RECORD_HEADER,
-          sizeof(float) * (a.record_stride == 0 ? CH_RECORD_MAP : a.record_stride),
-          sizeof(float) * CH_RECORD_MAP, static_cast<size_t>(n_maps), cudaMemcpyDeviceToDevice, s));
+          symbol, sizeof(float) * ch::kConstMapPitch, a.records,
+          sizeof(float) * (a.record_stride == 0 ? ch::kConstMapPitch : a.record_stride),
+          sizeof(float) * (CH_RECORD_HEADER + CH_RECORD_MAP), static_cast<size_t>(n_maps),
+          cudaMemcpyDeviceToDevice, s));
       const_maps = 1;
     }
   }
