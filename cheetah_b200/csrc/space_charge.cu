@@ -1716,7 +1716,9 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
 // of the fused moments, the fused pass went from 3.9 to 2.6 ms for 128 beams x 1e6 particles.
 // Measured and rejected on the way (128 beams): four lanes per particle, one sector each, weights
 // by shuffle (2.7 ms: fewer L1 wavefronts but 60 shuffles per particle); a two-stage software
-// pipeline at 2 CTAs per SM (3.3 ms); 4 CTAs per SM at 64 registers (2.7-2.9 ms); building and
+// pipeline at 2 CTAs per SM (3.3 ms); 4 CTAs per SM at 64 registers (2.7-2.9 ms); the bricks of
+// a thread's particles requested up front with 16-byte cp.async copies into shared-memory slots
+// (512-particle tiles: 4.8 instead of 3.3 ms with the field pass); building and
 // consuming the bricks in L2-sized groups of beams (1 beam per group 5.1 ms, 2: 4.4, all: 3.3
 // including the field pass -- short launches pay their tails).  What bounds the kernel now
 // (ncu at 128 beams, profiles/r02_sc_kernels_b128_ncu_full.txt): warps wait on their brick and
