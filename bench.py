@@ -852,6 +852,16 @@ def space_charge_section(ctx: Context, args) -> dict:
               f"{args.beams}-beam BASELINE configs[4] on 8 GPUs")
     ctx.barrier()
     section["ms_per_step"] = ctx.max_over_ranks(section["ms_per_step"])
+    # every rank tracks its own `share` beams with no collective: the job's throughput is the sum
+    # (at 8 ranks this IS BASELINE configs[4]: 1024 beams on 8 GPUs)
+    section["all_ranks"] = {
+        "beams": share * ctx.world, "n_gpus": ctx.world,
+        "value": share * ctx.world * args.particles * section["n_elements"]
+                 / (section["ms_per_step"] * 1e-3),
+        "unit": UNIT,
+        "particle_kicks_per_s": share * ctx.world * args.particles * section["kicks"]
+                                / (section["ms_per_step"] * 1e-3),
+    }
     out["config5_share"] = section
     torch.cuda.empty_cache()
     return out
