@@ -13,6 +13,7 @@
 // atomics they save); the 3-D convolution is three shared-memory FFT passes.
 #include <math_constants.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 
@@ -1408,8 +1409,8 @@ sc_field_kernel(const T* __restrict__ phi, const double* __restrict__ params, in
 // constant memory before the launch, so that the 42 coefficients reach the FMAs through the
 // uniform datapath (ULDC) instead of 12 shared-memory loads per particle -- the shared-memory /
 // L1 data stage was the busiest unit of the kernel (72 %, a third of it these loads).  One
-// buffer per device: like the reference ("not thread-safe by construction"), two host
-// threads must not track space charge on the same device at the same time.
+// buffer per device, owned by the first stream that uses it (gather_fused): other streams keep
+// the shared-memory path, so concurrent tracks on one device cannot overwrite each other's maps.
 constexpr int kConstMaps = 256;
 constexpr int kConstMapPitch = 44;  // the record's header (flags, length) + 42 coefficients
 __constant__ float c_gather_maps[kConstMaps * kConstMapPitch];
@@ -2897,7 +2898,20 @@ int gather_fused(const FusedArgs& a, cudaStream_t s) {
   int const_maps = 0;
   if (a.dtype == CH_F32 && a.field_layout == CH_SC_FIELD_BRICKS && a.records != nullptr) {
     const int64_t n_maps = a.record_stride == 0 ? 1 : a.n_beams;
-    if (n_maps <= ch::kConstMaps) {
+    // One constant buffer per device: it belongs to the first stream that uses it.  Work on
+    // that stream is ordered, so the copy below cannot overtake a gather that still reads the
+    // previous maps; any other stream (a second host thread tracking on the same device) takes
+    // the shared-memory path instead of racing for the buffer.
+    static std::atomic<uintptr_t> owner[64];  // 0: unclaimed, else stream handle + 1
+    int device = 0;
+    CH_CUDA(cudaGetDevice(&device));
+    bool mine = false;
+    if (device >= 0 && device < 64) {
+      const uintptr_t me = reinterpret_cast<uintptr_t>(s) + 1;
+      uintptr_t expected = 0;
+      mine = owner[device].compare_exchange_strong(expected, me) || expected == me;
+    }
+    if (mine && n_maps <= ch::kConstMaps) {
       void* symbol = nullptr;
       CH_CUDA(cudaGetSymbolAddress(&symbol, ch::c_gather_maps));
       CH_CUDA(cudaMemcpy2DAsync(

@@ -513,3 +513,41 @@ def test_deterministic_deposit_is_bit_reproducible(deterministic_algorithms, dty
         torch.use_deterministic_algorithms(True, warn_only=True)
         tol = 2e-5 if dtype == torch.float32 else 1e-12
         assert float((runs[0] - reference_run).abs().max() / reference_run.abs().max()) < tol
+
+
+def test_concurrent_tracks_on_two_streams_keep_their_own_maps():
+    """The fused section's maps travel through ONE constant-memory buffer per device; it belongs
+    to the first stream that uses it and other streams fall back to shared memory, so two host
+    threads tracking different lattices at the same time cannot see each other's maps."""
+    import threading
+
+    import cheetah_b200 as cb
+
+    dtype = torch.float32
+    torch.manual_seed(17)
+    beam = cb.ParticleBeam.from_parameters(
+        num_particles=200_000, total_charge=torch.tensor(5e-10), energy=torch.tensor(5e7),
+        device=DEVICE, dtype=dtype,
+    )
+    segments = [_fodo_with_kicks(dtype, vector_k1=[k1]) for k1 in (4.2, -6.0)]
+    expected = [segment.track(beam).particles.clone() for segment in segments]  # default stream
+    torch.cuda.synchronize()
+    results = [None, None]
+    streams = [torch.cuda.Stream(DEVICE) for _ in range(2)]
+
+    def work(i):
+        with torch.cuda.stream(streams[i]):
+            for _ in range(3):
+                results[i] = segments[i].track(beam).particles
+        streams[i].synchronize()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for got, want in zip(results, expected):
+        scale = want.abs().amax(dim=-2, keepdim=True).clamp_min(1e-30)
+        assert float(((got - want).abs() / scale).max()) < 5e-5
+    # the two lattices really differ
+    assert float((expected[0] - expected[1]).abs().max()) > 1e-6
