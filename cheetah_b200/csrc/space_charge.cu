@@ -636,12 +636,12 @@ __device__ __forceinline__ double igf_antiderivative(double x, double y, double 
 //                  + 1/1920 sum_a e_a^4 (105 t_a^4 - 90 t_a^2 + 9)
 //                  + 1/576 sum_{a<b} e_a^2 e_b^2 (105 t_a^2 t_b^2 - 15 (t_a^2 + t_b^2) + 3)] + O(e^6)
 // (derivatives of 1/r: d^n/dx^n = (-1)^n n! P_n(x / r) / r^(n+1)).  For r >= kFarRatio h_max the
-// truncation error is < 5e-8 of the value (tools/dev/igf_far_field.py, against 50-digit
-// arithmetic) -- below float32 resolution -- at ~60 fp64 operations instead of the ~1000 of an
-// exact antiderivative corner.  Float32 beams use it (the spectrum is float32 anyway); float64
-// beams keep the exact 8-corner difference everywhere.  With 9:1 cells (BASELINE configs[3]) 87 %
-// of the lattice is far field.
-constexpr double kFarRatio = 6.0;
+// truncation error is <= 1.3e-7 of the value (tools/dev/igf_far_field.py, against 50-digit
+// arithmetic) -- float32 resolution -- at ~60 float32 operations instead of the ~1000 fp64 ones
+// of an exact antiderivative corner.  Float32 beams use it (the spectrum is float32 anyway);
+// float64 beams keep the exact 8-corner difference everywhere.  With 9:1 cells (BASELINE
+// configs[3]) 90 % of the lattice is far field.
+constexpr double kFarRatio = 5.0;
 
 struct GreenGeometry {
   double dx, dy, dt;  // cell sizes, d_tau scaled by gamma (space_charge_kick.py:185-189)
@@ -666,21 +666,26 @@ __device__ __forceinline__ bool green_is_near(const GreenGeometry& g, int i, int
   return x * x + y * y + t * t < g.near_r2 * slack;
 }
 
-__device__ __forceinline__ double igf_far_field(const GreenGeometry& g, int i, int j, int k) {
-  const double x2 = (i * g.dx) * (i * g.dx), y2 = (j * g.dy) * (j * g.dy),
-               t2 = (k * g.dt) * (k * g.dt);
-  const double inv_r2 = 1.0 / (x2 + y2 + t2);
-  const double tx = x2 * inv_r2, ty = y2 * inv_r2, tt = t2 * inv_r2;
-  const double ex = g.dx * g.dx * inv_r2, ey = g.dy * g.dy * inv_r2, et = g.dt * g.dt * inv_r2;
-  const double s2 = ex * (3.0 * tx - 1.0) + ey * (3.0 * ty - 1.0) + et * (3.0 * tt - 1.0);
-  const double s4a = ex * ex * ((105.0 * tx - 90.0) * tx + 9.0) +
-                     ey * ey * ((105.0 * ty - 90.0) * ty + 9.0) +
-                     et * et * ((105.0 * tt - 90.0) * tt + 9.0);
-  const double s4b = ex * ey * (105.0 * tx * ty - 15.0 * (tx + ty) + 3.0) +
-                     ex * et * (105.0 * tx * tt - 15.0 * (tx + tt) + 3.0) +
-                     ey * et * (105.0 * ty * tt - 15.0 * (ty + tt) + 3.0);
-  return g.dx * g.dy * g.dt * sqrt(inv_r2) *
-         (1.0 + s2 * (1.0 / 24.0) + s4a * (1.0 / 1920.0) + s4b * (1.0 / 576.0));
+// (float32: only float32 beams take the far field, and the value is stored as float32 anyway;
+// measured error of this evaluation 2-3e-7 of the value, tools/dev/igf_far_field.py)
+__device__ __forceinline__ float igf_far_field(const GreenGeometry& g, int i, int j, int k) {
+  const float x = static_cast<float>(i * g.dx), y = static_cast<float>(j * g.dy),
+              t = static_cast<float>(k * g.dt);
+  const float hx2 = static_cast<float>(g.dx * g.dx), hy2 = static_cast<float>(g.dy * g.dy),
+              ht2 = static_cast<float>(g.dt * g.dt);
+  const float x2 = x * x, y2 = y * y, t2 = t * t;
+  const float inv_r2 = 1.0f / (x2 + y2 + t2);
+  const float tx = x2 * inv_r2, ty = y2 * inv_r2, tt = t2 * inv_r2;
+  const float ex = hx2 * inv_r2, ey = hy2 * inv_r2, et = ht2 * inv_r2;
+  const float s2 = ex * (3.0f * tx - 1.0f) + ey * (3.0f * ty - 1.0f) + et * (3.0f * tt - 1.0f);
+  const float s4a = ex * ex * ((105.0f * tx - 90.0f) * tx + 9.0f) +
+                    ey * ey * ((105.0f * ty - 90.0f) * ty + 9.0f) +
+                    et * et * ((105.0f * tt - 90.0f) * tt + 9.0f);
+  const float s4b = ex * ey * (105.0f * tx * ty - 15.0f * (tx + ty) + 3.0f) +
+                    ex * et * (105.0f * tx * tt - 15.0f * (tx + tt) + 3.0f) +
+                    ey * et * (105.0f * ty * tt - 15.0f * (ty + tt) + 3.0f);
+  return static_cast<float>(g.dx * g.dy * g.dt) * sqrtf(inv_r2) *
+         (1.0f + s2 * (1.0f / 24.0f) + s4a * (1.0f / 1920.0f) + s4b * (1.0f / 576.0f));
 }
 
 // Green function value at grid point (i, j, k): far field, or the 8-corner signed difference of

@@ -483,9 +483,9 @@ int ch_cic_deposit_deterministic(const void* positions, const void* extent, cons
  * evaluates it 8 n^3 times).  If `green` is not NULL the differenced, mirrored array
  * [B][2nx][2ny][2nz] of the reference is also written (plane n of every axis zero) -- used by
  * the parity tests; the solver itself only needs the lattice.  d_tau is scaled by gamma.
- * float32 beams: lattice points further than 6 x the largest cell size from the origin are not
+ * float32 beams: lattice points further than 5 x the largest cell size from the origin are not
  * written -- their Green function is the 4th-order far-field series of the cell integral
- * (truncation < 5e-8, below float32 resolution), evaluated by the consumers of the lattice. */
+ * (2-3e-7 of the value in float32), evaluated by the consumers of the lattice.               */
 int ch_sc_green_function(const double* params, int64_t n_beams,
                          int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
                          double* lattice, void* green, void* stream);

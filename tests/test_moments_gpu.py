@@ -113,3 +113,37 @@ def test_track_moments_with_full_covariance(dtype, keep):
     assert plain.cov is None and torch.allclose(plain.sigma, observed.sigma, rtol=1e-6)
     if keep:
         assert torch.equal(result[0].particles, out.particles)
+
+
+def test_track_moments_against_the_oracle_beam():
+    """Directly against the reference's definitions: the float64 CPU oracle tracks the beam and
+    mu / sigma / survivor count are taken from ITS outgoing beam (ParticleBeam.mu_* / sigma_*,
+    particle_beam.py:1699-1805), not from this package's own tracked particles."""
+    from oracle import lattice_io
+    from oracle import track_oracle as oracle
+
+    n, settings = 50_000, 5
+    description = workloads.ares_config3(settings, torch.float32)
+    particles = workloads.twiss_beam_particles(n)
+    particles[:, :4] *= 40.0
+    survival = (torch.rand(n, generator=torch.Generator().manual_seed(5)) > 0.2).float()
+
+    truth_beam = workloads.oracle_beam(particles.float(), torch.float64)
+    truth_beam["survival_probabilities"] = survival.double()
+    truth = oracle.track(
+        lattice_io.cast(lattice_io.cast(description, torch.float32), torch.float64), truth_beam)
+
+    class Out:  # what reference_moments reads
+        particles = truth["particles"]
+        survival_probabilities = truth["survival_probabilities"]
+
+    mu, sigma, s0 = reference_moments(Out)
+    segment = workloads.product_segment(description, DEVICE, torch.float32)
+    beam = workloads.product_beam(particles, DEVICE, torch.float32)
+    beam.survival_probabilities = survival.to(DEVICE)
+    observed = segment.track_moments(beam)
+    assert torch.equal(observed.num_particles_survived.cpu().double(), s0)
+    assert 0.05 < float(s0.mean()) / n < 0.95
+    scale = sigma.abs().clamp_min(1e-30)
+    assert ((observed.mu.cpu().double() - mu).abs() / scale).max() < 2e-5
+    assert ((observed.sigma.cpu().double() - sigma).abs() / scale).max() < 2e-5
