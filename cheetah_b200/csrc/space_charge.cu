@@ -1722,7 +1722,10 @@ sc_gather_kick_kernel(const T* __restrict__ particles_in, int64_t particle_strid
 // of the fused moments, the fused pass went from 3.9 to 2.6 ms for 128 beams x 1e6 particles.
 // Measured and rejected on the way (128 beams): four lanes per particle, one sector each, weights
 // by shuffle (2.7 ms: fewer L1 wavefronts but 60 shuffles per particle); a two-stage software
-// pipeline at 2 CTAs per SM (3.3 ms); 4 CTAs per SM at 64 registers (2.7-2.9 ms); the bricks of
+// pipeline at 2 CTAs per SM (3.3 ms), and at 3 CTAs per SM with one or two sets of sector
+// registers (fused 3.4-3.5 ms with the field pass against 3.26: spills; the plain kick without
+// fusion gains, 3.9 -> 3.0 ms, but it only runs for the last kick of a lattice); 4 CTAs per SM at
+// 64 registers (2.7-2.9 ms); the bricks of
 // a thread's particles requested up front with 16-byte cp.async copies into shared-memory slots
 // (512-particle tiles: 4.8 instead of 3.3 ms with the field pass); building and
 // consuming the bricks in L2-sized groups of beams (1 beam per group 5.1 ms, 2: 4.4, all: 3.3

@@ -52,6 +52,12 @@ def main():
     beam = cb.ParticleBeam(particles, torch.tensor(1e8, device=device), particle_charges=charges,
                            species=cb.Species("electron", device=device, dtype=dtype))
     beam._unit_seventh = True
+    import os
+
+    if os.environ.get("CH_TIMELINE_UNFUSED"):  # every stage as its own pass
+        from cheetah_b200 import tracking
+
+        tracking.fuse_space_charge = False
     proxy = Proxy(_capi.lib())
     _capi._lib = proxy
     for _ in range(2):
