@@ -304,6 +304,15 @@ SIGNATURES = {
             c_void_p, c_void_p,
         ],
     ),
+    "ch_sc_solve": (
+        c_int32,
+        [
+            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+            c_void_p, c_int64, c_int64,
+            c_int32, c_int32, c_int32, c_int32,
+            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+        ],
+    ),
     "ch_sc_field_gather": (
         c_int32,
         [

@@ -3076,3 +3076,70 @@ extern "C" int ch_sc_field_gather(
                     forces_out};
   return gather_fused(a, static_cast<cudaStream_t>(stream));
 }
+
+// ---------------------------------------------------------------------------------------
+// one call for the grid half of a kick
+// ---------------------------------------------------------------------------------------
+namespace {
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+// A high-priority side stream and two events per device, created on first use (before any graph
+// capture: GraphedTrack warms the path up first).
+int side_stream(SideStream** out) {
+  static SideStream table[64];
+  static std::atomic<int> ready[64];
+  int device = 0;
+  CH_CUDA(cudaGetDevice(&device));
+  CH_REQUIRE(device >= 0 && device < 64, "ch_sc_solve: device index %d out of range", device);
+  SideStream& entry = table[device];
+  if (ready[device].load(std::memory_order_acquire) != 2) {
+    int expected = 0;
+    if (ready[device].compare_exchange_strong(expected, 1)) {
+      int least = 0, greatest = 0;
+      CH_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      CH_CUDA(cudaStreamCreateWithPriority(&entry.stream, cudaStreamNonBlocking, greatest));
+      CH_CUDA(cudaEventCreateWithFlags(&entry.fork, cudaEventDisableTiming));
+      CH_CUDA(cudaEventCreateWithFlags(&entry.join, cudaEventDisableTiming));
+      ready[device].store(2, std::memory_order_release);
+    } else {
+      while (ready[device].load(std::memory_order_acquire) != 2) {
+      }
+    }
+  }
+  *out = &entry;
+  return CH_OK;
+}
+}  // namespace
+
+extern "C" int ch_sc_solve(const void* particles, int64_t particle_stride, const void* charges,
+                           int64_t charge_stride, const void* survival, int64_t survival_stride,
+                           const double* params, int64_t n_particles, int64_t n_beams, int32_t nx,
+                           int32_t ny, int32_t nz, int32_t dtype, void* rho, double* lattice,
+                           void* green_scratch, void* green_spectrum, void* rho_spectrum,
+                           void* phi, void* stream) {
+  CH_SC_COMMON_CHECKS("ch_sc_solve");
+  SideStream* side = nullptr;
+  int status = side_stream(&side);
+  if (status != CH_OK) return status;
+  cudaStream_t main = static_cast<cudaStream_t>(stream);
+  // the Green-function chain only needs the grid parameters: it runs on the side stream next to
+  // the deposit (which is bound by L2 reductions, not by the SMs) and joins before the x pass
+  CH_CUDA(cudaEventRecord(side->fork, main));
+  CH_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  status = ch_sc_green_function(params, n_beams, nx, ny, nz, dtype, lattice, nullptr, side->stream);
+  if (status != CH_OK) return status;
+  status = ch_sc_green_spectrum(lattice, params, n_beams, nx, ny, nz, dtype, green_scratch,
+                                green_spectrum, side->stream);
+  if (status != CH_OK) return status;
+  CH_CUDA(cudaEventRecord(side->join, side->stream));
+  status = ch_sc_deposit(particles, particle_stride, charges, charge_stride, survival,
+                         survival_stride, params, n_particles, n_beams, nx, ny, nz, dtype, rho,
+                         stream);
+  if (status != CH_OK) return status;
+  CH_CUDA(cudaStreamWaitEvent(main, side->join, 0));
+  return ch_sc_poisson_solve(rho, green_spectrum, params, n_beams, nx, ny, nz, dtype, rho_spectrum,
+                             phi, stream);
+}

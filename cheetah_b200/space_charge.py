@@ -234,41 +234,51 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
             else:
                 _capi.check(lib.ch_sc_moments_and_params(
                     *moment_args, ws.stats.data_ptr(), ws.params.data_ptr(), stream))
-        # the Green-function chain only needs the grid parameters: it runs on a side stream
-        # concurrently with the deposit and the first two FFT passes of the charge
         main = torch.cuda.current_stream(device)
-        side = _side_stream(device)
-        forked = torch.cuda.Event()
-        forked.record(main)
-        side.wait_event(forked)
-        ws.green = (
-            torch.empty((n_beams, 2 * nx, 2 * ny, 2 * nz), dtype=dtype, device=device)
-            if want_intermediates else None
-        )
-        _capi.check(lib.ch_sc_green_function(
-            ws.params.data_ptr(), n_beams, nx, ny, nz, code, ws.lattice.data_ptr(),
-            _capi.ptr(ws.green), side.cuda_stream))
-        _capi.check(lib.ch_sc_green_spectrum(
-            ws.lattice.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
-            ws.green_scratch.data_ptr(),
-            ws.green_spectrum.data_ptr(), side.cuda_stream))
-        joined = torch.cuda.Event()
-        joined.record(side)
-        if deterministic:
-            # fixed-point accumulation: bit-identical from run to run (ch_sc_deposit_deterministic)
-            _capi.check(lib.ch_sc_deposit_deterministic(
-                p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
-                ws.params.data_ptr(), n, n_beams, nx, ny, nz, code,
-                ws.fixed_point_scratch().data_ptr(), ws.rho_quad.data_ptr(), stream))
+        if deterministic or want_intermediates:
+            # the Green-function chain only needs the grid parameters: it runs on a side stream
+            # concurrently with the deposit and the first two FFT passes of the charge
+            side = _side_stream(device)
+            forked = torch.cuda.Event()
+            forked.record(main)
+            side.wait_event(forked)
+            ws.green = (
+                torch.empty((n_beams, 2 * nx, 2 * ny, 2 * nz), dtype=dtype, device=device)
+                if want_intermediates else None
+            )
+            _capi.check(lib.ch_sc_green_function(
+                ws.params.data_ptr(), n_beams, nx, ny, nz, code, ws.lattice.data_ptr(),
+                _capi.ptr(ws.green), side.cuda_stream))
+            _capi.check(lib.ch_sc_green_spectrum(
+                ws.lattice.data_ptr(), ws.params.data_ptr(), n_beams, nx, ny, nz, code,
+                ws.green_scratch.data_ptr(),
+                ws.green_spectrum.data_ptr(), side.cuda_stream))
+            joined = torch.cuda.Event()
+            joined.record(side)
+            if deterministic:
+                # fixed-point accumulation: bit-identical from run to run
+                _capi.check(lib.ch_sc_deposit_deterministic(
+                    p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
+                    ws.params.data_ptr(), n, n_beams, nx, ny, nz, code,
+                    ws.fixed_point_scratch().data_ptr(), ws.rho_quad.data_ptr(), stream))
+            else:
+                _capi.check(lib.ch_sc_deposit(
+                    p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
+                    ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_quad.data_ptr(),
+                    stream))
+            main.wait_event(joined)
+            _capi.check(lib.ch_sc_poisson_solve(
+                ws.rho_quad.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(),
+                n_beams, nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))
         else:
-            _capi.check(lib.ch_sc_deposit(
+            # the same four stages in one C call (its own side stream and events)
+            ws.green = None
+            _capi.check(lib.ch_sc_solve(
                 p.data_ptr(), p_stride, q.data_ptr(), q_stride, w.data_ptr(), w_stride,
                 ws.params.data_ptr(), n, n_beams, nx, ny, nz, code, ws.rho_quad.data_ptr(),
+                ws.lattice.data_ptr(), ws.green_scratch.data_ptr(),
+                ws.green_spectrum.data_ptr(), ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(),
                 stream))
-        main.wait_event(joined)
-        _capi.check(lib.ch_sc_poisson_solve(
-            ws.rho_quad.data_ptr(), ws.green_spectrum.data_ptr(), ws.params.data_ptr(), n_beams,
-            nx, ny, nz, code, ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(), stream))
         if records_ready is not None:
             main.wait_event(records_ready)
         nxt = None

@@ -569,6 +569,18 @@ int ch_sc_gather_kick_fused(const void* particles_in, int64_t particle_stride,
                             int32_t next_nx, int32_t next_ny, int32_t next_nz,
                             void* particles_out, void* stream);
 
+/* The grid half of one kick in one call: ch_sc_green_function + ch_sc_green_spectrum on an
+ * internal high-priority side stream next to ch_sc_deposit on `stream`, joined before
+ * ch_sc_poisson_solve (what the Python layer did with four calls and two events: at one beam
+ * an eager kick is bound by the host's call rate).  Buffers as in those four functions.       */
+int ch_sc_solve(const void* particles, int64_t particle_stride,
+                const void* charges, int64_t charge_stride,
+                const void* survival, int64_t survival_stride,
+                const double* params, int64_t n_particles, int64_t n_beams,
+                int32_t nx, int32_t ny, int32_t nz, int32_t dtype,
+                void* rho, double* lattice, void* green_scratch, void* green_spectrum,
+                void* rho_spectrum, void* phi, void* stream);
+
 /* float32: ch_sc_field_bricks + ch_sc_gather_kick[_fused] interleaved per group of `group_beams`
  * beams: the bricks of a group are built from phi [B][nx*ny*nz] into `bricks`
  * (group_beams * nx*ny*nz * 24 floats, reused by every group) right before the group's gather
