@@ -147,3 +147,40 @@ def test_track_moments_against_the_oracle_beam():
     scale = sigma.abs().clamp_min(1e-30)
     assert ((observed.mu.cpu().double() - mu).abs() / scale).max() < 2e-5
     assert ((observed.sigma.cpu().double() - sigma).abs() / scale).max() < 2e-5
+
+
+@pytest.mark.parametrize("covariance", [False, True], ids=["moments", "cov"])
+@pytest.mark.parametrize("shape", ["rectangular", "elliptical"])
+@pytest.mark.parametrize("n_apertures", [1, 2, 3, 4])
+@pytest.mark.parametrize("beam_per_setting", [False, True], ids=["shared_beam", "beam_per_setting"])
+def test_observables_kernel_variants(n_apertures, shape, covariance, beam_per_setting):
+    """Every dispatch of the observables-only path (apply.cu): the kernel specialised for one
+    beam under many settings (0-3 apertures, rectangular-only or with elliptical ones, with and
+    without the covariance sums) and the general kernel (four apertures, a beam per setting)
+    against the moments of the materialised outgoing beam."""
+    import cheetah_b200 as cb
+
+    t = lambda v: torch.tensor(v, device=DEVICE, dtype=torch.float32)  # noqa: E731
+    elements = [cb.Quadrupole(length=t(0.2), k1=t([4.0, -3.0, 1.5, 0.0, 2.5]))]
+    for i in range(n_apertures):
+        elements += [cb.Drift(length=t(0.4 + 0.1 * i)),
+                     cb.Aperture(x_max=t(2.5e-4 + 5e-5 * i), y_max=t(3e-4 - 2e-5 * i), shape=shape)]
+    elements += [cb.Quadrupole(length=t(0.2), k1=t(-2.0)), cb.Drift(length=t(0.5))]
+    segment = cb.Segment(elements)
+    torch.manual_seed(11)
+    n = 70_001
+    beam = cb.ParticleBeam.from_parameters(num_particles=n, device=DEVICE, dtype=torch.float32)
+    if beam_per_setting:
+        beam.particles = beam.particles.unsqueeze(0) * t([1.0, 1.1, 0.9, 1.2, 0.8]).view(5, 1, 1)
+        beam.particles[..., 6] = 1.0
+    out = segment.track(beam)
+    assert 0.05 < float(out.survival_probabilities.mean()) < 0.95
+    mu, sigma, s0 = reference_moments(out)
+    observed = segment.track_moments(beam, covariance=covariance)
+    assert torch.equal(observed.num_particles_survived.double(), s0)
+    assert ((observed.mu.double() - mu).abs() / sigma).max() < 2e-5
+    assert ((observed.sigma.double() - sigma).abs() / sigma).max() < 2e-5
+    if covariance:
+        expected = reference_covariance(out)
+        scale = sigma.unsqueeze(-1) * sigma.unsqueeze(-2)
+        assert float(((observed.cov.double() - expected).abs() / scale).max()) < 3e-5
