@@ -456,53 +456,64 @@ def ares_parity(ctx: Context, args, beam, reference_out) -> dict:
 
 
 def ares_dense_section(ctx: Context, args, beam, per_rank: int, begin: int, end: int) -> dict:
-    """The generic (dense 72-FMA) branch of apply_maps_kernel: ARES with both solenoids powered
-    and one quadrupole tilted, so that no sparsity flag holds (solenoid.py:74-116,
-    track_methods.py:345-382)."""
+    """The other two branches of the apply kernel on the same workload.  `coupled` (56
+    multiply-adds): ARES with both solenoids powered and one quadrupole tilted (x-y coupling,
+    solenoid.py:74-116, track_methods.py:345-382).  `tau_coupled` (all 72): the same followed by a
+    CustomTransferMap with a tau column and a changed delta row, so that no sparsity flag holds.
+    The top-level keys are the coupled variant (what this section has reported since round 2)."""
     from cheetah_b200 import tracking
 
     dtype = torch.float32
-    lattice = workloads.ares_config3_dense(args.settings, dtype, begin, end)
-    segment = workloads.product_segment(lattice, ctx.device, dtype)
-    out = None
-    for _ in range(2):
-        del out
-        out = segment.track(beam)
-    ctx.barrier()
-    tracking.apply_events = []
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = max(3, args.steps // 2)
-    start.record()
-    for _ in range(steps):
-        del out
-        out = segment.track(beam)
-    stop.record()
-    ctx.barrier()
-    apply_ms = [a.elapsed_time(b) for a, b in tracking.apply_events]
-    tracking.apply_events = None
-    survival = float(out.survival_probabilities.mean())
-    del out
-    torch.cuda.empty_cache()
-    ms = ctx.max_over_ranks(start.elapsed_time(stop)) / steps
     peak, _ = peak_hbm()
     nbytes = per_rank * args.particles * 32 + args.particles * 32
-    mean_apply = sum(apply_ms) / len(apply_ms)
-    return {
-        "workload": "ARES x 1e6 particles x 4096 settings with ARLIMSOG1A/B powered (k = 0.5, "
-                    "-0.4 1/m) and AREAMQZM2 tilted by 0.3 rad: x-y coupled maps, the dense branch",
-        "ms_per_step": ms,
-        "value": args.settings * args.particles * N_ELEMENTS / (ms * 1e-3),
-        "unit": UNIT,
-        "mean_survival": survival,
-        "roofline": {
-            "kernel": "apply_maps_kernel<float, 4, 256, UNIT7=1, MOMENTS=0, WRITE=1, CAVITY=0>, "
-                      "dense branch",
-            "bound": "hbm", "achieved": nbytes / (mean_apply * 1e-3) / 1e9, "peak": peak,
-            "unit": "GB/s", "frac": nbytes / (mean_apply * 1e-3) / 1e9 / peak,
-            "mean_launch_ms": mean_apply, "algorithmic_bytes_per_launch": nbytes,
-            "traffic": None,
-        },
-    }
+
+    def measure(lattice, label, branch):
+        segment = workloads.product_segment(lattice, ctx.device, dtype)
+        out = None
+        for _ in range(2):
+            del out
+            out = segment.track(beam)
+        ctx.barrier()
+        tracking.apply_events = []
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = max(3, args.steps // 2)
+        start.record()
+        for _ in range(steps):
+            del out
+            out = segment.track(beam)
+        stop.record()
+        ctx.barrier()
+        apply_ms = [a.elapsed_time(b) for a, b in tracking.apply_events]
+        tracking.apply_events = None
+        survival = float(out.survival_probabilities.mean())
+        del out
+        torch.cuda.empty_cache()
+        ms = ctx.max_over_ranks(start.elapsed_time(stop)) / steps
+        mean_apply = sum(apply_ms) / len(apply_ms)
+        return {
+            "workload": label,
+            "ms_per_step": ms,
+            "value": args.settings * args.particles * N_ELEMENTS / (ms * 1e-3),
+            "unit": UNIT,
+            "mean_survival": survival,
+            "roofline": {
+                "kernel": f"apply_shared_beam_kernel<NAP=3, ELLIPTICAL=0>, {branch}",
+                "bound": "hbm", "achieved": nbytes / (mean_apply * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": nbytes / (mean_apply * 1e-3) / 1e9 / peak,
+                "mean_launch_ms": mean_apply, "algorithmic_bytes_per_launch": nbytes,
+                "traffic": None,
+            },
+        }
+
+    result = measure(
+        workloads.ares_config3_dense(args.settings, dtype, begin, end),
+        "ARES x 1e6 particles x 4096 settings with ARLIMSOG1A/B powered (k = 0.5, -0.4 1/m) and "
+        "AREAMQZM2 tilted by 0.3 rad: x-y coupled maps", "coupled branch (56 multiply-adds)")
+    result["tau_coupled"] = measure(
+        workloads.ares_config3_tau_coupled(args.settings, dtype, begin, end),
+        "the same followed by a CustomTransferMap with a tau column and a changed delta row: no "
+        "sparsity flag holds", "dense branch (72 multiply-adds)")
+    return result
 
 
 def peak_hbm() -> tuple[float, str]:
@@ -625,8 +636,8 @@ def run_ares(args) -> None:
         traffic = per_unit * per_rank * args.particles
         traffic_note = "ncu dram bytes at 256 settings, scaled per (particle, setting)"
     roofline = {
-        "kernel": "apply_maps_kernel<float, 4, 256, UNIT7=1, MOMENTS=0, WRITE=1, CAVITY=0> "
-                  "(ch_apply_maps), sparse branch",
+        "kernel": "apply_shared_beam_kernel<NAP=3, ELLIPTICAL=0> (ch_apply_maps: one beam under "
+                  "consecutive settings; 4 particles per thread, 256 threads), sparse branch",
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
@@ -660,7 +671,7 @@ def run_ares(args) -> None:
                               max(3, args.steps // 2), 1)
         observables = {
             "what": "Segment.track_moments: mu, sigma (6 each) and surviving-particle count per "
-                    "setting from observe_maps_kernel (packed FFMA2 pairs); outgoing particles never "
+                    "setting from observe_shared_beam_kernel (packed FFMA2 pairs); outgoing particles never "
                     "written",
             "value": args.settings * args.particles * N_ELEMENTS / (o_ms * 1e-3),
             "unit": UNIT,

@@ -21,123 +21,11 @@
 // covariance epilogue and the cavity tail), observe_maps_kernel (float32 observables only: the
 // same tiling on packed FFMA2 pairs, nothing written but 20 / 36 sums per setting) and
 // apply_maps_parameter_kernel (ParameterBeam: mu' = M mu, cov' = M cov M^T).
-#include <type_traits>
-
-#include "ch_common.cuh"
+#include "apply_common.cuh"
 
 namespace ch {
 namespace {
 
-template <typename T>
-struct ApplyArgs {
-  const T* particles_in;
-  const T* survival_in;  // may be null -> ones
-  const T* records;
-  T* particles_out;
-  T* survival_out;  // may be null iff n_apertures == 0
-  const int32_t* particle_index;
-  const int32_t* survival_index;
-  const int32_t* record_index;
-  int64_t particle_stride;  // elements per batch entry of particles_in (0 = shared)
-  int64_t survival_stride;
-  int64_t record_stride;
-  int64_t n_particles;
-  int64_t n_settings;
-  int32_t record_len;
-  int32_t n_apertures;
-  uint32_t elliptical_mask;
-  int32_t settings_per_cta;
-  int32_t bulk_in;   // particles_in tiles satisfy the 16-byte rules of cp.async.bulk
-  int32_t bulk_out;  // particles_out tiles do
-  double* moments_out;  // [n_settings][CH_MOMENTS] survival-weighted sums (MOMENTS kernels)
-  int32_t has_cavity;   // the record ends with a CH_RECORD_CAVITY block
-  int32_t covariance;   // moments_out has CH_MOMENTS_COV entries per setting (full 6x6 sums)
-  // COMPACT kernels (ch_apply_maps_compact): particles_out holds 6 coordinates per row and
-  // the survival mask may be written as one byte per particle instead of a T
-  int32_t compact;
-  uint8_t* survival_u8;
-};
-
-template <typename T>
-struct Vec4;
-template <>
-struct Vec4<float> {
-  using type = float4;
-  static constexpr int lanes = 4;
-};
-template <>
-struct Vec4<double> {
-  using type = double2;
-  static constexpr int lanes = 2;
-};
-
-// exact IEEE helpers so that masks follow the reference's unfused elementwise ops
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ void sincos_t(float x, float& s, float& c) { sincosf(x, &s, &c); }
-__device__ __forceinline__ void sincos_t(double x, double& s, double& c) { sincos(x, &s, &c); }
-__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
-
-// load `n` scalars (n % lanes == 0, 16-byte aligned) from shared memory as 128-bit words
-template <typename T, int N>
-__device__ __forceinline__ void load_coefficients(T (&dst)[N], const T* src) {
-  using V = typename Vec4<T>::type;
-  constexpr int L = Vec4<T>::lanes;
-  static_assert(N % L == 0, "coefficient block must be a whole number of 128-bit words");
-#pragma unroll
-  for (int i = 0; i < N / L; ++i) {
-    const V v = reinterpret_cast<const V*>(src)[i];
-    if constexpr (L == 4) {
-      dst[4 * i + 0] = v.x;
-      dst[4 * i + 1] = v.y;
-      dst[4 * i + 2] = v.z;
-      dst[4 * i + 3] = v.w;
-    } else {
-      dst[2 * i + 0] = v.x;
-      dst[2 * i + 1] = v.y;
-    }
-  }
-}
-
-template <typename T, bool UNIT7>
-__device__ __forceinline__ T affine_row(const T* c, const T (&p)[7]) {
-  // c[0..6] . (p0..p5, p6) ; with UNIT7 the seventh coordinate is known to be 1
-  T acc = UNIT7 ? c[6] : c[6] * p[6];
-#pragma unroll
-  for (int j = 5; j >= 0; --j) acc = fma_t(c[j], p[j], acc);
-  return acc;
-}
-
-
-// the same without the tau column (CH_FLAG_NO_TAU_COLUMN: c[4] == 0)
-template <typename T, bool UNIT7>
-__device__ __forceinline__ T affine_row_no_tau(const T* c, const T (&p)[7]) {
-  T acc = UNIT7 ? c[6] : c[6] * p[6];
-  acc = fma_t(c[5], p[5], acc);
-#pragma unroll
-  for (int j = 3; j >= 0; --j) acc = fma_t(c[j], p[j], acc);
-  return acc;
-}
-
-__device__ __forceinline__ uint32_t record_flags(float header) { return __float_as_uint(header); }
-__device__ __forceinline__ uint32_t record_flags(double header) {
-  return static_cast<uint32_t>(__double_as_longlong(header));
-}
-
-// |v| < bound  <=>  -bound < v < bound for bound >= 0 (NaNs compare false either way)
-__device__ __forceinline__ bool inside(float v, float bound) { return fabsf(v) < bound; }
-__device__ __forceinline__ bool inside(double v, double bound) { return fabs(v) < bound; }
-
-// accumulator type of the fused moments: the beam dtype (float32 partial sums per thread about the
-// pilot for float32 beams, fp64 for float64 beams -- the reference's golden dtype); fp64 across
-// threads and tiles in both cases
-template <typename T>
-using Acc = T;
 
 // One lattice setting for this thread's P particles: survival masks at every aperture, then
 // the final map into the staging tile.  SPARSE drops the structurally-zero terms (flags).
@@ -303,45 +191,6 @@ __device__ __forceinline__ void process_setting(const T* rec, int n_apertures,
       }
     }
   }
-}
-
-// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles instead of 80: every
-// round halves the number of values a lane is responsible for.  Afterwards lane L (L even)
-// holds the warp total of value index ((L >> 4) & 1) * 8 + ((L >> 3) & 1) * 4 +
-// ((L >> 2) & 1) * 2 + ((L >> 1) & 1).
-template <typename A>
-__device__ __forceinline__ A packed_warp_sum(A (&v)[16], int lane) {
-#pragma unroll
-  for (int round = 0; round < 4; ++round) {
-    const int offset = 16 >> round;      // 16, 8, 4, 2
-    const int keep = 8 >> round;         // 8, 4, 2, 1 values kept
-    const bool upper = (lane & offset) != 0;
-#pragma unroll
-    for (int i = 0; i < keep; ++i) {
-      const A send = upper ? v[i] : v[i + keep];
-      const A mine = upper ? v[i + keep] : v[i];
-      v[i] = mine + __shfl_xor_sync(0xffffffffu, send, offset);
-    }
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
-// Same for 32 per-lane values (5 rounds, 31 shuffles): afterwards lane L holds the warp total of
-// value index L.
-template <typename A>
-__device__ __forceinline__ A packed_warp_sum(A (&v)[32], int lane) {
-#pragma unroll
-  for (int round = 0; round < 5; ++round) {
-    const int offset = 16 >> round;  // 16, 8, 4, 2, 1 = number of values kept
-    const bool upper = (lane & offset) != 0;
-#pragma unroll
-    for (int i = 0; i < offset; ++i) {
-      const A send = upper ? v[i] : v[i + offset];
-      const A mine = upper ? v[i + offset] : v[i];
-      v[i] = mine + __shfl_xor_sync(0xffffffffu, send, offset);
-    }
-  }
-  return v[0];
 }
 
 template <typename T, int P, int THREADS, bool UNIT7, int MOMENTS, bool WRITE, bool CAVITY,
@@ -575,31 +424,6 @@ apply_maps_kernel(const ApplyArgs<T> a) {
 // memory so that one broadcast LDS.128 delivers two ready-made (c, c) operands.  The chains are
 // the same fma sequences as in process_setting, so aperture masks are bit-identical to the
 // particle-writing kernel's.
-using f2 = float2;
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
-
-// `n` duplicated coefficients (n even) from shared memory, two per 128-bit word
-template <int N>
-__device__ __forceinline__ void load_pairs(f2 (&dst)[N], const f2* src) {
-  static_assert(N % 2 == 0, "whole 128-bit words");
-#pragma unroll
-  for (int i = 0; i < N / 2; ++i) {
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
-    dst[2 * i] = f2{v.x, v.y};
-    dst[2 * i + 1] = f2{v.z, v.w};
-  }
-}
-
-template <bool UNIT7>
-__device__ __forceinline__ f2 affine_row2(const f2* c, const f2 (&p)[7]) {
-  f2 acc = UNIT7 ? c[6] : mul2(c[6], p[6]);
-#pragma unroll
-  for (int j = 5; j >= 0; --j) acc = fma2(c[j], p[j], acc);
-  return acc;
-}
-
 template <int PAIRS, bool UNIT7, bool SPARSE, int MOMENTS>
 __device__ __forceinline__ void observe_setting(const f2* rec2, int n_apertures,
                                                 uint32_t elliptical_mask,
@@ -910,277 +734,6 @@ observe_maps_kernel(const ApplyArgs<float> a) {
   }
 }
 
-// ---- the common call of the above, specialised ---------------------------------------------------
-// Segment.track_moments of ONE beam under many settings (shared beam and incoming survival,
-// consecutive records, unit seventh column, at most three apertures: the ARES case).  Same
-// arithmetic, same chains and the same masks as observe_maps_kernel; what goes away is the
-// bookkeeping per setting: the aperture count and the record length are compile-time constants
-// (records live in a static shared array, every LDS has an immediate offset, the aperture block
-// is unrolled and its selects overlap the next block's FFMA2s), the beam is loaded once before
-// the loop, the record pointer advances by one addition and the masks use a chained predicate
-// (2 FSETP + 1 FSEL per particle and aperture).
-__device__ __forceinline__ float keep_if_inside(float sv, float x, float x_max, float y,
-                                                float y_max) {
-  float out;
-  asm("{\n"
-      "  .reg .pred p;\n"
-      "  .reg .f32 ax, ay;\n"
-      "  abs.f32 ax, %1;\n"
-      "  abs.f32 ay, %3;\n"
-      "  setp.lt.f32 p, ax, %2;\n"
-      "  setp.lt.and.f32 p, ay, %4, p;\n"
-      "  selp.f32 %0, %5, 0f00000000, p;\n"
-      "}"
-      : "=f"(out)
-      : "f"(x), "f"(x_max), "f"(y), "f"(y_max), "f"(sv));
-  return out;
-}
-
-template <int NAP, bool SPARSE, int MOMENTS, bool ELLIPTICAL>
-__device__ __forceinline__ void observe_setting_lean(const f2* rec2, uint32_t elliptical_mask,
-                                                     const f2 (&p)[4][7], f2 (&sv)[4],
-                                                     const float (&first_particle)[7],
-                                                     float (&pilot)[6],
-                                                     f2 (&acc)[MOMENTS == 2 ? 29 : 14]) {
-  constexpr int PAIRS = 4;
-#pragma unroll
-  for (int ap = 0; ap < NAP; ++ap) {
-    f2 q[16];
-    load_pairs(q, rec2 + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
-    const float x_max = q[14].x, y_max = q[15].x;
-    f2 x[PAIRS], y[PAIRS];
-#pragma unroll
-    for (int k = 0; k < PAIRS; ++k) {
-      if constexpr (SPARSE) {
-        x[k] = fma2(q[0], p[k][0], fma2(q[1], p[k][1], fma2(q[5], p[k][5], q[6])));
-        y[k] = fma2(q[9], p[k][2], fma2(q[10], p[k][3], q[13]));
-      } else {
-        x[k] = affine_row2<true>(q, p[k]);
-        y[k] = affine_row2<true>(q + 7, p[k]);
-      }
-    }
-    // ELLIPTICAL = false: no aperture of the section is elliptical, the whole setting is one
-    // basic block and the selects of one aperture are scheduled between the FFMA2s of the next
-    if (ELLIPTICAL && ((elliptical_mask >> ap) & 1u)) {
-      const float xx = mul_rn(x_max, x_max), yy = mul_rn(y_max, y_max);
-#pragma unroll
-      for (int k = 0; k < PAIRS; ++k) {
-        const bool lo = add_rn(div_rn(mul_rn(x[k].x, x[k].x), xx),
-                               div_rn(mul_rn(y[k].x, y[k].x), yy)) <= 1.0f;
-        const bool hi = add_rn(div_rn(mul_rn(x[k].y, x[k].y), xx),
-                               div_rn(mul_rn(y[k].y, y[k].y), yy)) <= 1.0f;
-        sv[k].x = lo ? sv[k].x : 0.0f;
-        sv[k].y = hi ? sv[k].y : 0.0f;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < PAIRS; ++k) {
-        sv[k].x = keep_if_inside(sv[k].x, x[k].x, x_max, y[k].x, y_max);
-        sv[k].y = keep_if_inside(sv[k].y, x[k].y, x_max, y[k].y, y_max);
-      }
-    }
-  }
-
-  f2 c[44];
-  load_pairs(c, rec2);
-  const f2* m = c + CH_RECORD_HEADER;
-  {
-    const float(&in)[7] = first_particle;
-    if constexpr (SPARSE) {
-      pilot[0] = fmaf(m[0].x, in[0], fmaf(m[1].x, in[1], fmaf(m[5].x, in[5], m[6].x)));
-      pilot[1] = fmaf(m[7].x, in[0], fmaf(m[8].x, in[1], fmaf(m[12].x, in[5], m[13].x)));
-      pilot[2] = fmaf(m[16].x, in[2], fmaf(m[17].x, in[3], m[20].x));
-      pilot[3] = fmaf(m[23].x, in[2], fmaf(m[24].x, in[3], m[27].x));
-      pilot[4] = fmaf(m[28].x, in[0],
-                      fmaf(m[29].x, in[1], fmaf(m[32].x, in[4], fmaf(m[33].x, in[5], m[34].x))));
-      pilot[5] = in[5];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        float acc1 = m[i * 7 + 6].x;
-#pragma unroll
-        for (int j = 5; j >= 0; --j) acc1 = fmaf(m[i * 7 + j].x, in[j], acc1);
-        pilot[i] = acc1;
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < PAIRS; ++k) {
-    f2 out[6];
-    if constexpr (SPARSE) {
-      out[0] = fma2(m[0], p[k][0], fma2(m[1], p[k][1], fma2(m[5], p[k][5], m[6])));
-      out[1] = fma2(m[7], p[k][0], fma2(m[8], p[k][1], fma2(m[12], p[k][5], m[13])));
-      out[2] = fma2(m[16], p[k][2], fma2(m[17], p[k][3], m[20]));
-      out[3] = fma2(m[23], p[k][2], fma2(m[24], p[k][3], m[27]));
-      out[4] = fma2(m[28], p[k][0],
-                    fma2(m[29], p[k][1], fma2(m[32], p[k][4], fma2(m[33], p[k][5], m[34]))));
-      out[5] = p[k][5];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) out[i] = affine_row2<true>(m + i * 7, p[k]);
-    }
-    const f2 w = sv[k];
-    f2 d[6], wd[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      d[i] = add2(out[i], f2{-pilot[i], -pilot[i]});
-      wd[i] = mul2(w, d[i]);
-    }
-    if (k == 0) {  // first pair: the sums start here (no zero-filled accumulators)
-      acc[0] = w;
-      acc[1] = mul2(w, w);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        acc[2 + i] = wd[i];
-        acc[8 + i] = mul2(wd[i], d[i]);
-      }
-    } else {
-      acc[0] = add2(acc[0], w);
-      acc[1] = fma2(w, w, acc[1]);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        acc[2 + i] = add2(acc[2 + i], wd[i]);
-        acc[8 + i] = fma2(wd[i], d[i], acc[8 + i]);
-      }
-    }
-    if constexpr (MOMENTS == 2) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = i + 1; j < 6; ++j) {
-          const int slot = 14 + i * (11 - i) / 2 + (j - i - 1);
-          acc[slot] = k == 0 ? mul2(wd[i], d[j]) : fma2(wd[i], d[j], acc[slot]);
-        }
-    }
-  }
-}
-
-constexpr int kLeanThreads = 128, kLeanP = 8;
-
-template <int NAP, int MOMENTS, bool ELLIPTICAL>
-__global__ void __launch_bounds__(kLeanThreads, MOMENTS == 2 ? (ELLIPTICAL ? 2 : 3) : 4)
-observe_shared_beam_kernel(const ApplyArgs<float> a) {
-  constexpr int THREADS = kLeanThreads, PAIRS = kLeanP / 2, TP = kLeanP * THREADS;
-  constexpr int RECLEN = CH_RECORD_LEN(NAP);
-  constexpr int NACC = MOMENTS == 2 ? 32 : 16;
-  constexpr int NSUM = MOMENTS == 2 ? 29 : 14;
-  constexpr int NOUT = MOMENTS == 2 ? CH_MOMENTS_COV : CH_MOMENTS;
-  static_assert(RECLEN % 2 == 0 && RECLEN <= THREADS, "one record entry per thread");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);
-  __shared__ __align__(16) f2 recs[2][RECLEN];
-  __shared__ float partial[2][THREADS / 32][NACC];
-  __shared__ float pilot_shared[2][8];
-  __shared__ uint64_t bar;
-
-  const int tid = threadIdx.x;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * TP;
-  const int count = static_cast<int>(min(static_cast<int64_t>(TP), a.n_particles - n0));
-  const int64_t b_begin = static_cast<int64_t>(blockIdx.y) * a.settings_per_cta;
-  const int n_local =
-      static_cast<int>(min(a.n_settings - b_begin, static_cast<int64_t>(a.settings_per_cta)));
-  if (n_local <= 0) return;
-
-  // ---- the beam: once per CTA ------------------------------------------------------------
-  const float* rec_src = a.records + b_begin * a.record_stride;
-  float fetched = tid < RECLEN ? rec_src[tid] : 0.0f;
-  {
-    const float* src = a.particles_in + n0 * 7;
-    if (a.bulk_in) {
-      if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-        const uint32_t bytes = static_cast<uint32_t>(count) * 7u * sizeof(float);
-        mbar_expect_tx(&bar, bytes);
-        bulk_load(tile, src, bytes, &bar);
-      }
-      __syncthreads();  // the barrier is initialised before anybody waits on it
-      mbar_wait(&bar, 0);
-    } else {
-      for (int i = tid; i < count * 7; i += THREADS) tile[i] = src[i];
-      __syncthreads();
-    }
-  }
-  f2 p[PAIRS][7], sv_in[PAIRS];
-#pragma unroll
-  for (int k = 0; k < PAIRS; ++k) {
-    const int lo = tid + (2 * k) * THREADS, hi = lo + THREADS;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      p[k][j].x = lo < count ? tile[lo * 7 + j] : 0.0f;
-      p[k][j].y = hi < count ? tile[hi * 7 + j] : 0.0f;
-    }
-    // lanes past the end of the beam must not count
-    sv_in[k].x = lo < count ? (a.survival_in ? a.survival_in[n0 + lo] : 1.0f) : 0.0f;
-    sv_in[k].y = hi < count ? (a.survival_in ? a.survival_in[n0 + hi] : 1.0f) : 0.0f;
-  }
-  float first[7];
-#pragma unroll
-  for (int j = 0; j < 7; ++j) first[j] = a.particles_in[j];
-  if (tid < RECLEN) recs[0][tid] = f2{fetched, fetched};
-
-  double* out = a.moments_out + b_begin * NOUT;
-  auto flush_moments = [&](int buf, double* dst) {
-    if (tid < NSUM) {
-      double total = 0.0;
-#pragma unroll
-      for (int wi = 0; wi < THREADS / 32; ++wi) total += static_cast<double>(partial[buf][wi][tid]);
-      atomicAdd(dst + (tid < 14 ? tid : tid + 6), total);
-    } else if (tid >= 32 && tid < 38 && blockIdx.x == 0) {
-      dst[14 + (tid - 32)] = static_cast<double>(pilot_shared[buf][tid - 32]);
-    }
-  };
-  constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
-                               CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
-  const int lane = tid & 31;
-  const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
-                   ((lane >> 1) & 1);
-
-#pragma unroll 1
-  for (int it = 0; it < n_local; ++it) {
-    const int buf = it & 1;
-    __syncthreads();  // record `it` is complete; so is partial[buf ^ 1]
-    if (it > 0) {
-      flush_moments(buf ^ 1, out);
-      out += NOUT;
-    }
-    if (it + 1 < n_local) {  // in flight during the arithmetic below
-      rec_src += a.record_stride;
-      fetched = tid < RECLEN ? rec_src[tid] : 0.0f;
-    }
-    const f2* rec2 = recs[buf];
-    f2 sv[PAIRS];
-#pragma unroll
-    for (int k = 0; k < PAIRS; ++k) sv[k] = sv_in[k];
-    float pilot[6];
-    f2 acc2[NSUM];
-    if ((record_flags(rec2[0].x) & kSparse) == kSparse)
-      observe_setting_lean<NAP, true, MOMENTS, ELLIPTICAL>(rec2, a.elliptical_mask, p, sv, first,
-                                                           pilot, acc2);
-    else
-      observe_setting_lean<NAP, false, MOMENTS, ELLIPTICAL>(rec2, a.elliptical_mask, p, sv, first,
-                                                            pilot, acc2);
-    if (it + 1 < n_local && tid < RECLEN) recs[buf ^ 1][tid] = f2{fetched, fetched};
-    float acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NSUM; ++i) acc[i] = acc2[i].x + acc2[i].y;
-    const float total = packed_warp_sum(acc, lane);
-    if constexpr (MOMENTS == 2) {
-      partial[buf][tid >> 5][lane] = total;
-    } else if ((lane & 1) == 0) {
-      partial[buf][tid >> 5][slot] = total;
-    }
-    if (tid == 0) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) pilot_shared[buf][i] = pilot[i];
-    }
-  }
-  __syncthreads();
-  flush_moments((n_local - 1) & 1, out);
-}
-
 // (covariance with 2 pairs x 256 threads -- 124 registers, 16 warps/SM instead of 8 -- measured
 // 23.8 ms against 21.3 ms: the 31-shuffle reduction per warp and setting doubles per particle)
 constexpr int kObserveP = 8, kObserveThreads = 128;
@@ -1193,36 +746,8 @@ int launch_observe(const ApplyArgs<float>& args, bool unit_seventh, cudaStream_t
   const int64_t chunks = (args.n_settings + args.settings_per_cta - 1) / args.settings_per_cta;
   CH_REQUIRE(tiles <= 2147483647LL && chunks <= 65535, "ch_apply_maps_moments: grid too large");
   dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(chunks));
-  // one beam (and one incoming survival vector) under consecutive records: the specialised kernel
-  const bool shared_beam =
-      unit_seventh && args.particle_stride == 0 && args.record_index == nullptr &&
-      (args.survival_in == nullptr || args.survival_stride == 0) &&
-      args.survival_out == nullptr && args.n_apertures <= 3 &&
-      args.record_len == CH_RECORD_LEN(args.n_apertures);
-  if (shared_beam) {
-    static_assert(kLeanP * kLeanThreads == TP, "same tiling");
-    const size_t tile_bytes = sizeof(float) * TP * 7;
-    auto lean = [&](auto kernel) -> int {
-      kernel<<<grid, kLeanThreads, tile_bytes, stream>>>(args);
-      CH_LAUNCH_CHECK();
-      return CH_OK;
-    };
-    auto with_apertures = [&](auto moments) -> int {
-      constexpr int M = decltype(moments)::value;
-      const bool elliptical = (args.elliptical_mask & ((1u << args.n_apertures) - 1u)) != 0;
-      switch (args.n_apertures) {
-        case 0: return lean(observe_shared_beam_kernel<0, M, false>);
-        case 1: return elliptical ? lean(observe_shared_beam_kernel<1, M, true>)
-                                  : lean(observe_shared_beam_kernel<1, M, false>);
-        case 2: return elliptical ? lean(observe_shared_beam_kernel<2, M, true>)
-                                  : lean(observe_shared_beam_kernel<2, M, false>);
-        default: return elliptical ? lean(observe_shared_beam_kernel<3, M, true>)
-                                   : lean(observe_shared_beam_kernel<3, M, false>);
-      }
-    };
-    return args.covariance ? with_apertures(std::integral_constant<int, 2>{})
-                           : with_apertures(std::integral_constant<int, 1>{});
-  }
+  if (shared_beam_call(args, unit_seventh) && args.survival_out == nullptr)
+    return launch_observe_shared_beam(args, stream);
   auto launch = [&](auto kernel) -> int {
     CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
@@ -1279,6 +804,12 @@ int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t strea
     return with_cavity(unit, M0{}, std::true_type{});
   };
   int status;
+  if constexpr (sizeof(T) == 4) {
+    // particles out, nothing else: the kernels specialised for one beam under many settings
+    if (args.moments_out == nullptr && args.particles_out != nullptr &&
+        shared_beam_call(args, unit_seventh))
+      return launch_apply_shared_beam(args, stream);
+  }
   if (args.compact)
     status = launch(apply_maps_kernel<T, P, THREADS, true, 0, true, false, true>);
   else

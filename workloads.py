@@ -86,6 +86,21 @@ def ares_config3_dense(n_settings: int, dtype=torch.float32, begin: int = 0,
     return lattice
 
 
+def ares_config3_tau_coupled(n_settings: int, dtype=torch.float32, begin: int = 0,
+                             end: int | None = None) -> list:
+    """`ares_config3_dense` followed by a short CustomTransferMap whose matrix couples tau into
+    x and changes the delta row (what an off-crest RF structure or a dipole with RF does to a
+    merged map): no sparsity flag holds, every setting takes the 72-multiply-add branch."""
+    lattice = ares_config3_dense(n_settings, dtype, begin, end)
+    matrix = torch.eye(7, dtype=dtype)
+    matrix[0, 4], matrix[1, 4], matrix[2, 4] = 2e-3, -1e-3, 5e-4
+    matrix[5, 4], matrix[5, 0], matrix[4, 5] = 3e-3, 1e-3, 0.2
+    lattice.append({"type": "CustomTransferMap", "name": "tau_coupling",
+                    "length": torch.tensor(0.1, dtype=dtype),
+                    "predefined_transfer_map": matrix})
+    return lattice
+
+
 def ares_survey_ranges(n_settings: int, dtype=torch.float32, x_max: float = 0.5) -> list:
     """The ranges SURVEY 8d first proposed -- k1 ~ U(-30, 30) 1/m^2, corrector angles ~
     U(-1e-3, 1e-3) rad, seed 1 -- with the two apertures opened to `x_max` instead of narrowing
