@@ -78,6 +78,8 @@ class HostTracker:
         import copy
 
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = dtype
         self.n_particles = n_particles
         self.n_settings = n_settings
@@ -111,6 +113,27 @@ class HostTracker:
             else:
                 owner._parameters[attr] = torch.nn.Parameter(view, requires_grad=False)
         self.staged_versions = {}
+        # Tensors whose VALUES shape the lowering (a cavity is an active element only when its
+        # voltage is non-zero, lowering.LatticeProgram.watched) must not share the version counter
+        # of the flat block -- every upload would look like an edit and force a re-lowering
+        # (14 ms of Python for ARES).  They keep storage of their own and are copied only when the
+        # host tensor changed.
+        self.separate = {}
+        program = tracking._plan(list(self.device_segment.elements), self.device, (),
+                                 self.device_segment)
+        watched = {t.data_ptr() for t, _ in program.watched}
+        for name, off, nbytes, shape, tdtype in self.layout:
+            if nbytes and self.flat_dev.data_ptr() + off in watched:
+                own = self.flat_dev[off:off + nbytes].view(tdtype).reshape(shape).clone()
+                path, _, attr = name.rpartition(".")
+                owner = self.device_segment.get_submodule(path) if path else self.device_segment
+                if attr in owner._buffers:
+                    owner._buffers[attr] = own
+                else:
+                    owner._parameters[attr] = torch.nn.Parameter(own, requires_grad=False)
+                self.separate[name] = own
+        # the buffers were re-pointed behind Element.__setattr__: drop the cached plan
+        object.__setattr__(self.device_segment, "_plan_cache", None)
         n, c = n_particles, self.chunk
         self.beam_dev = torch.empty((n, 7), dtype=dtype, device=self.device)
         self.survival_dev = torch.empty((n,), dtype=dtype, device=self.device)
@@ -178,6 +201,10 @@ class HostTracker:
             if self.staged_versions.get(name) == key:
                 continue
             self.staged_versions[name] = key
+            if name in self.separate:  # changed on the host: the plan sees the new version
+                self.separate[name].copy_(src.detach(), non_blocking=False)
+                self.h2d_bytes += nbytes
+                continue
             self.flat_pinned[off:off + nbytes].view(tdtype).reshape(shape).copy_(src.detach())
         # the lattice block crosses the bus every call (the host may have changed any of it)
         self.flat_dev.copy_(self.flat_pinned, non_blocking=True)

@@ -103,6 +103,34 @@ def test_host_tracker_sees_rebound_and_in_place_settings():
     assert torch.equal(third, expected.mu.cpu().nan_to_num(nan=-1.0))
 
 
+def test_host_tracker_keeps_its_plan_between_calls():
+    """Uploading the lattice block must not look like an edit of the lattice: the lowered program
+    of the device lattice is reused from call to call (value-watched tensors -- the cavity
+    voltages of ARES -- live outside the flat block), yet a voltage changed on the host is seen."""
+    from cheetah_b200 import tracking
+    from cheetah_b200.host import HostTracker
+
+    n, b = 2000, 4
+    host_segment, device_segment, host_beam, particles = _host_case(n, b)
+    tracker = HostTracker(host_segment, n, b, device=DEVICE, chunk_settings=4)
+    assert tracker.separate, "ARES has cavities: their voltages shape the lowering"
+    tracker.track_moments(host_beam)
+    plan = tracking._plan(list(tracker.device_segment.elements), torch.device(DEVICE), (),
+                          tracker.device_segment)
+    before = tracker.track_moments(host_beam).mu.clone()
+    assert tracking._plan(list(tracker.device_segment.elements), torch.device(DEVICE), (),
+                          tracker.device_segment) is plan
+    cavity = next(e for e in host_segment.elements if type(e).__name__ == "Cavity")
+    cavity.voltage = torch.tensor(2e6)
+    cavity.phase = torch.tensor(-20.0)
+    getattr(device_segment, cavity.name).voltage = torch.tensor(2e6, device=DEVICE)
+    getattr(device_segment, cavity.name).phase = torch.tensor(-20.0, device=DEVICE)
+    after = tracker.track_moments(host_beam)
+    expected = device_segment.track_moments(workloads.product_beam(particles, DEVICE, torch.float32))
+    assert not torch.equal(before.nan_to_num(nan=-1.0), after.mu.nan_to_num(nan=-1.0))
+    assert torch.equal(after.mu.nan_to_num(nan=-1.0), expected.mu.cpu().nan_to_num(nan=-1.0))
+
+
 def test_track_host_space_charge_lattice_round_trip():
     """Any lattice through the general host path: FODO cell with two space-charge kicks."""
     from cheetah_b200.host import track_host
