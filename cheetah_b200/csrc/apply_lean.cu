@@ -179,9 +179,7 @@ observe_shared_beam_kernel(const ApplyArgs<float> a) {
       static_cast<int>(min(a.n_settings - b_begin, static_cast<int64_t>(a.settings_per_cta)));
   if (n_local <= 0) return;
 
-  // ---- the beam: once per CTA ------------------------------------------------------------
-  const float* rec_src = a.records + b_begin * a.record_stride;
-  float fetched = tid < RECLEN ? rec_src[tid] : 0.0f;
+  // ---- the beam: once per CTA (before the wait for the compose kernel: see below) -----------
   {
     const float* src = a.particles_in + n0 * 7;
     if (a.bulk_in) {
@@ -215,6 +213,11 @@ observe_shared_beam_kernel(const ApplyArgs<float> a) {
   float first[7];
 #pragma unroll
   for (int j = 0; j < 7; ++j) first[j] = a.particles_in[j];
+  // the records come from the compose kernel launched just before: this kernel may have started
+  // while that one was still running
+  grid_dependency_wait();
+  const float* rec_src = a.records + b_begin * a.record_stride;
+  float fetched = tid < RECLEN ? rec_src[tid] : 0.0f;
   if (tid < RECLEN) recs[0][tid] = f2{fetched, fetched};
 
   double* out = a.moments_out + b_begin * NOUT;
@@ -371,8 +374,6 @@ apply_shared_beam_kernel(const ApplyArgs<float> a) {
       static_cast<int>(min(a.n_settings - b_begin, static_cast<int64_t>(a.settings_per_cta)));
   if (n_local <= 0) return;
 
-  const float* rec_src = a.records + b_begin * a.record_stride;
-  float fetched = tid < RECLEN ? rec_src[tid] : 0.0f;
   {
     const float* src = a.particles_in + n0 * 7;
     if (a.bulk_in) {
@@ -398,6 +399,10 @@ apply_shared_beam_kernel(const ApplyArgs<float> a) {
     for (int j = 0; j < 7; ++j) p[k][j] = local < count ? stage1[local * 7 + j] : 0.0f;
     sv_in[k] = (a.survival_in != nullptr && local < count) ? a.survival_in[n0 + local] : 1.0f;
   }
+  // the records come from the compose kernel launched just before (see the observables kernel)
+  grid_dependency_wait();
+  const float* rec_src = a.records + b_begin * a.record_stride;
+  float fetched = tid < RECLEN ? rec_src[tid] : 0.0f;
   if (tid < RECLEN) recs[0][tid] = fetched;
   __syncthreads();  // record 0 complete; everybody holds its particles (stage1 is reused later)
 
@@ -494,9 +499,10 @@ int launch_observe_shared_beam(const ApplyArgs<float>& args, cudaStream_t stream
   const size_t tile_bytes = sizeof(float) * TP * 7;
   auto run = [&](auto moments) -> int {
     return with_apertures(args, [&](auto nap, auto elliptical) -> int {
-      observe_shared_beam_kernel<decltype(nap)::value, decltype(moments)::value,
-                                 decltype(elliptical)::value>
-          <<<grid, kLeanThreads, tile_bytes, stream>>>(args);
+      CH_CUDA(launch_dependent(
+          observe_shared_beam_kernel<decltype(nap)::value, decltype(moments)::value,
+                                     decltype(elliptical)::value>,
+          grid, dim3(kLeanThreads), tile_bytes, stream, args));
       CH_LAUNCH_CHECK();
       return CH_OK;
     });
@@ -516,7 +522,7 @@ int launch_apply_shared_beam(const ApplyArgs<float>& args, cudaStream_t stream) 
     auto kernel = apply_shared_beam_kernel<decltype(nap)::value, decltype(elliptical)::value>;
     CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-    kernel<<<grid, kApplyLeanThreads, smem, stream>>>(args);
+    CH_CUDA(launch_dependent(kernel, grid, dim3(kApplyLeanThreads), smem, stream, args));
     CH_LAUNCH_CHECK();
     return CH_OK;
   });

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "cheetah_b200.h"
 
@@ -43,6 +44,26 @@ void count_launch(int n = 1);
     }                                                                                  \
     ch::count_launch();                                                                \
   } while (0)
+
+// Launch `kernel` so that it may overlap the tail of the previous kernel in `stream`
+// (programmatic stream serialization); the kernel calls grid_dependency_wait() before it touches
+// anything that kernel wrote.
+template <typename... KernelArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KernelArgs...), dim3 grid, dim3 block,
+                                    size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t config = {};
+  config.gridDim = grid;
+  config.blockDim = block;
+  config.dynamicSmemBytes = smem;
+  config.stream = stream;
+  cudaLaunchAttribute attribute[1];
+  attribute[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attribute[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool disabled = std::getenv("CH_NO_DEPENDENT_LAUNCH") != nullptr;  // A/B timing
+  config.attrs = attribute;
+  config.numAttrs = disabled ? 0 : 1;
+  return cudaLaunchKernelEx(&config, kernel, static_cast<KernelArgs>(args)...);
+}
 
 // ---- a scalar read through a (pointer, stride, dtype) triple -------------------------
 struct ScalarRef {
@@ -119,6 +140,14 @@ __device__ __forceinline__ void bulk_wait_read() {
 template <int N>
 __device__ __forceinline__ void bulk_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Programmatic dependent launch (griddepcontrol): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may begin before the previous kernel of the
+// stream has finished; everything it reads from that kernel must come after this wait (a no-op
+// for a normal launch).
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // make generic-proxy shared-memory writes visible to the async proxy (TMA engine)

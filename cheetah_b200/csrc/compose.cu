@@ -500,6 +500,10 @@ compose_maps_kernel(Program prog, int32_t op_begin, int32_t op_end, ScalarRef en
   __shared__ int32_t n_cuts_shared;
   __shared__ uint32_t flags_shared;
 
+  // Programmatic dependent launch: the apply kernel that follows in the stream may start its
+  // prologue (particle tile -> registers) now; it waits (griddepcontrol.wait) for this grid to
+  // finish before it reads a record.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 7;     // column owned inside a group (7: length accumulator)
