@@ -758,22 +758,26 @@ def run_ares(args) -> None:
         torch.cuda.synchronize()
         c_start, c_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 50
-        c_start.record()
-        for _ in range(reps):
-            segment2.track(beam)
-        c_stop.record()
-        torch.cuda.synchronize()
-        eager_ms = c_start.elapsed_time(c_stop) / reps
+
+        def batch_median(call):
+            # these calls last tens of microseconds: the host's launch rate is part of what is
+            # measured, so take the median of five batches instead of one
+            samples = []
+            for _ in range(5):
+                c_start.record()
+                for _ in range(reps):
+                    call()
+                c_stop.record()
+                torch.cuda.synchronize()
+                samples.append(c_start.elapsed_time(c_stop) / reps)
+            return sorted(samples)[2]
+
+        eager_ms = batch_median(lambda: segment2.track(beam))
         graphed = cb.GraphedTrack(segment2, beam)
         for _ in range(3):
             graphed.replay()
         torch.cuda.synchronize()
-        c_start.record()
-        for _ in range(reps):
-            graphed.replay()
-        c_stop.record()
-        torch.cuda.synchronize()
-        graph_ms = c_start.elapsed_time(c_stop) / reps
+        graph_ms = batch_median(graphed.replay)
         config2 = {
             "workload": f"ARES Segment ({N_ELEMENTS} elements), {args.particles} particles, ONE "
                         "setting (README magnet values), linear maps -- BASELINE configs[1]; the "
