@@ -102,28 +102,39 @@ __device__ __forceinline__ void observe_setting_lean(const f2* rec2, uint32_t el
       }
     }
   }
+  // Distances from the pilot come straight out of the fma chains: the constant of row i is
+  // replaced by (constant - pilot_i), so the chain ends on u_i - c_i instead of u_i (one rounding
+  // less than subtracting afterwards, and 20 packed additions fewer per setting).
+  f2 shifted[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float c = m[i * 7 + 6].x - pilot[i];
+    shifted[i] = f2{c, c};
+  }
 #pragma unroll
   for (int k = 0; k < PAIRS; ++k) {
-    f2 out[6];
+    f2 d[6];
     if constexpr (SPARSE) {
-      out[0] = fma2(m[0], p[k][0], fma2(m[1], p[k][1], fma2(m[5], p[k][5], m[6])));
-      out[1] = fma2(m[7], p[k][0], fma2(m[8], p[k][1], fma2(m[12], p[k][5], m[13])));
-      out[2] = fma2(m[16], p[k][2], fma2(m[17], p[k][3], m[20]));
-      out[3] = fma2(m[23], p[k][2], fma2(m[24], p[k][3], m[27]));
-      out[4] = fma2(m[28], p[k][0],
-                    fma2(m[29], p[k][1], fma2(m[32], p[k][4], fma2(m[33], p[k][5], m[34]))));
-      out[5] = p[k][5];
+      d[0] = fma2(m[0], p[k][0], fma2(m[1], p[k][1], fma2(m[5], p[k][5], shifted[0])));
+      d[1] = fma2(m[7], p[k][0], fma2(m[8], p[k][1], fma2(m[12], p[k][5], shifted[1])));
+      d[2] = fma2(m[16], p[k][2], fma2(m[17], p[k][3], shifted[2]));
+      d[3] = fma2(m[23], p[k][2], fma2(m[24], p[k][3], shifted[3]));
+      d[4] = fma2(m[28], p[k][0],
+                  fma2(m[29], p[k][1], fma2(m[32], p[k][4], fma2(m[33], p[k][5], shifted[4]))));
+      d[5] = add2(p[k][5], f2{-pilot[5], -pilot[5]});
     } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) out[i] = affine_row2<true>(m + i * 7, p[k]);
+      for (int i = 0; i < 6; ++i) {
+        f2 acc1 = shifted[i];
+#pragma unroll
+        for (int j = 5; j >= 0; --j) acc1 = fma2(m[i * 7 + j], p[k][j], acc1);
+        d[i] = acc1;
+      }
     }
     const f2 w = sv[k];
-    f2 d[6], wd[6];
+    f2 wd[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      d[i] = add2(out[i], f2{-pilot[i], -pilot[i]});
-      wd[i] = mul2(w, d[i]);
-    }
+    for (int i = 0; i < 6; ++i) wd[i] = mul2(w, d[i]);
     if (k == 0) {  // first pair: the sums start here (no zero-filled accumulators)
       acc[0] = w;
       acc[1] = mul2(w, w);
