@@ -467,7 +467,14 @@ def ares_dense_section(ctx: Context, args, beam, per_rank: int, begin: int, end:
     peak, _ = peak_hbm()
     nbytes = per_rank * args.particles * 32 + args.particles * 32
 
+    traffic_path = REPO / "profiles" / "apply_maps_traffic.json"
+    branches = json.loads(traffic_path.read_text()).get("branches", {}) \
+        if traffic_path.exists() else {}
+
     def measure(lattice, label, branch):
+        # DRAM bytes of one ncu --set full capture of this branch at 256 settings, scaled per
+        # (particle, setting) to this launch (see the headline's traffic_note)
+        per_unit = branches.get(branch.split()[0], {}).get("dram_bytes_per_particle_setting")
         segment = workloads.product_segment(lattice, ctx.device, dtype)
         out = None
         for _ in range(2):
@@ -501,7 +508,7 @@ def ares_dense_section(ctx: Context, args, beam, per_rank: int, begin: int, end:
                 "bound": "hbm", "achieved": nbytes / (mean_apply * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": nbytes / (mean_apply * 1e-3) / 1e9 / peak,
                 "mean_launch_ms": mean_apply, "algorithmic_bytes_per_launch": nbytes,
-                "traffic": None,
+                "traffic": per_unit * per_rank * args.particles if per_unit else None,
             },
         }
 
