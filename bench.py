@@ -90,6 +90,7 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines: list[str] = []
+        self.first = 0
 
     def start(self) -> None:
         try:
@@ -106,6 +107,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self, timeout: float = 3.0) -> None:
+        """Call right before the timed region, with the same load already running: waits until
+        nvidia-smi delivers (its start-up can take longer than a 200 ms timed region) and makes
+        stop() report the samples from here on."""
+        if self.proc is None:
+            return
+        deadline = time.time() + timeout
+        while not self.lines and time.time() < deadline:
+            time.sleep(0.01)
+        self.first = len(self.lines)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -113,7 +125,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, sm_max, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        # samples of the timed region; if it was too short for one, those of the warm-up steps
+        # (the same kernels) that ran right before it
+        lines = self.lines[self.first:] or self.lines
+        for line in lines:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -601,16 +616,17 @@ def run_ares(args) -> None:
 
     # ---- device-resident timing ----------------------------------------------------------------
     out = None
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
     for _ in range(max(1, args.warmup)):
         del out
         out = segment.track(beam)
     survival_mean = float(out.survival_probabilities.mean())
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank)
-    sampler.start()
     tracking.apply_events = []
     launches_before = _capi.launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark()
     ctx.barrier()
     start.record()
     for _ in range(args.steps):
@@ -914,13 +930,14 @@ def run_space_charge(args) -> None:
             out = segment.track(beam)
             del out
 
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
     for _ in range(max(1, args.warmup)):
         step()
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank)
-    sampler.start()
     launches_before = _capi.launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark()
     ctx.barrier()
     start.record()
     for _ in range(args.steps):
