@@ -282,3 +282,26 @@ def test_tiny_and_ragged_beams(n):
         reference = diag.screen_reading(spec, beam)
         image = screen.reading.cpu()
         assert float((image - reference).abs().max()) <= 1e-9 * float(reference.max()) + 1e-300
+
+
+def test_config3_workload_against_the_oracle_at_full_beam_size():
+    """The bench workload itself (BASELINE configs[2]: ARES, 1e6 particles, settings 0..3 of the
+    4096 drawn by workloads.ares_config3) on the GPU in float32 against the float64 CPU oracle:
+    2e-6 of the column scale, survival masks exactly equal (what bench.py reports as
+    `parity_check` for settings 0..7)."""
+    from oracle import lattice_io
+    from oracle import track_oracle as oracle
+    from tests import golden_utils as gu
+
+    dtype = torch.float32
+    description = workloads.ares_config3(4096, dtype, 0, 4)
+    particles = workloads.twiss_beam_particles(N)
+    segment = workloads.product_segment(description, DEVICE, dtype)
+    out = segment.track(workloads.product_beam(particles, DEVICE, dtype))
+    assert out.particles.shape == (4, N, 7)
+    truth = oracle.track(lattice_io.cast(lattice_io.cast(description, dtype), torch.float64),
+                         workloads.oracle_beam(particles.to(dtype), torch.float64))
+    assert gu.column_scaled_error(out.particles, truth["particles"]) < 2e-6
+    mask = out.survival_probabilities.cpu().double()
+    assert torch.equal(mask, truth["survival_probabilities"].expand_as(mask))
+    assert 0.1 < float(mask.mean()) < 0.9
