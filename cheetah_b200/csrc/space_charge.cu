@@ -1842,14 +1842,15 @@ __device__ __forceinline__ void load_sector(const float* src, bool active, float
 
 // Gather + kick on bricks (see sc_gather_kick_kernel for what FUSED adds).  The kick is the
 // float32 difference form of that kernel.
-template <bool FUSED>
+// P particles per thread (tiles of 256 P particles): chosen per launch, see launch_gather_bricks
+template <bool FUSED, int P = 4>
 __global__ void __launch_bounds__(256, 3)
 sc_gather_brick_kernel(const float* __restrict__ particles_in, int64_t particle_stride,
                        const float* __restrict__ bricks, const double* __restrict__ params,
                        int64_t n_particles, int nx, int ny, int nz, int bulk_in, int bulk_out,
                        float* __restrict__ particles_out, float* __restrict__ forces_out,
                        const GatherFusion<float> fusion, int beam0) {
-  constexpr int P = 4, THREADS = 256, TP = P * THREADS;
+  constexpr int THREADS = 256, TP = P * THREADS;
   constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);  // [TP][7]
@@ -2815,17 +2816,44 @@ int launch_gather_bricks(const float* particles_in, int64_t particle_stride, con
                          const double* params, int64_t n_particles, int beam0, int group, int nx,
                          int ny, int nz, float* particles_out, float* forces_out,
                          const ch::GatherFusion<float>* fusion, cudaStream_t s) {
-  dim3 grid(static_cast<unsigned>((n_particles + 1023) / 1024), static_cast<unsigned>(group));
+  // Particles per thread: 4 (tiles of 1024) unless the launch is only a few waves of CTAs long
+  // (3 CTAs of 256 threads per SM): one beam of 1e6 particles is 977 tiles = 2.2 waves with the
+  // last one a fifth full; tiles of 768 (3 full waves of shorter CTAs) or 1280 (2 waves) finish
+  // sooner -- config 4 as a CUDA graph 11.96 -> 11.35 ms.
+  int per_thread = 4;
+  {
+    const int64_t slots = 148 * 3;
+    auto waves = [&](int p) {
+      const int64_t ctas = (n_particles + 256 * p - 1) / (256 * p) * group;
+      return (ctas + slots - 1) / slots;
+    };
+    if (waves(4) < 20) {
+      int64_t best = waves(4) * 4;
+      for (int p : {3, 5})
+        if (waves(p) * p < best) {
+          best = waves(p) * p;
+          per_thread = p;
+        }
+    }
+  }
+  const int tile = 256 * per_thread;
+  dim3 grid(static_cast<unsigned>((n_particles + tile - 1) / tile), static_cast<unsigned>(group));
   const int bulk_in = ch::bulk_compatible<float>(particles_in, n_particles, particle_stride);
   const int bulk_out = ch::bulk_compatible<float>(particles_out, n_particles, n_particles * 7);
-  const size_t smem = 1024 * 7 * sizeof(float);
+  const size_t smem = static_cast<size_t>(tile) * 7 * sizeof(float);
   auto launch = [&](auto kernel, const ch::GatherFusion<float>& f) {
     kernel<<<grid, 256, smem, s>>>(particles_in, particle_stride, bricks, params, n_particles, nx,
                                    ny, nz, bulk_in, bulk_out, particles_out, forces_out, f, beam0);
   };
   const ch::GatherFusion<float> none{};
-  fusion ? launch(ch::sc_gather_brick_kernel<true>, *fusion)
-         : launch(ch::sc_gather_brick_kernel<false>, none);
+  auto with_tile = [&](auto p) {
+    constexpr int P = decltype(p)::value;
+    fusion ? launch(ch::sc_gather_brick_kernel<true, P>, *fusion)
+           : launch(ch::sc_gather_brick_kernel<false, P>, none);
+  };
+  if (per_thread == 5) with_tile(std::integral_constant<int, 5>{});
+  else if (per_thread == 3) with_tile(std::integral_constant<int, 3>{});
+  else with_tile(std::integral_constant<int, 4>{});
   CH_LAUNCH_CHECK();
   return CH_OK;
 }
