@@ -804,12 +804,10 @@ int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t strea
     return with_cavity(unit, M0{}, std::true_type{});
   };
   int status;
-  if constexpr (sizeof(T) == 4) {
-    // particles out, nothing else: the kernels specialised for one beam under many settings
-    if (args.moments_out == nullptr && args.particles_out != nullptr &&
-        shared_beam_call(args, unit_seventh))
-      return launch_apply_shared_beam(args, stream);
-  }
+  // particles out, nothing else: the kernels specialised for one beam under many settings
+  if (args.moments_out == nullptr && args.particles_out != nullptr &&
+      shared_beam_call(args, unit_seventh))
+    return launch_apply_shared_beam(args, stream);
   if (args.compact)
     status = launch(apply_maps_kernel<T, P, THREADS, true, 0, true, false, true>);
   else

@@ -39,9 +39,11 @@ struct ApplyArgs {
 };
 
 // apply_lean.cu
-bool shared_beam_call(const ApplyArgs<float>& args, bool unit_seventh);
+template <typename T>
+bool shared_beam_call(const ApplyArgs<T>& args, bool unit_seventh);
 int launch_observe_shared_beam(const ApplyArgs<float>& args, cudaStream_t stream);
-int launch_apply_shared_beam(const ApplyArgs<float>& args, cudaStream_t stream);
+template <typename T>
+int launch_apply_shared_beam(const ApplyArgs<T>& args, cudaStream_t stream);
 
 namespace {
 

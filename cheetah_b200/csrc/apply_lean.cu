@@ -303,78 +303,85 @@ observe_shared_beam_kernel(const ApplyArgs<float> a) {
 // purposes: the rows of this setting are complete (the elected thread hands the tile to the TMA
 // engine right after it), the next record is committed, and the tile of the previous setting has
 // been read by the engine (the elected thread waits for that just before the barrier).
-constexpr int kApplyLeanThreads = 256, kApplyLeanP = 4;
+constexpr int kApplyLeanThreads = 256;
+// particles per thread: tiles of 1024 float32 / 512 float64 particles (28 KB either way)
+template <typename T>
+constexpr int kApplyLeanP = sizeof(T) == 4 ? 4 : 2;
 
-template <int NAP, int MODE, bool ELLIPTICAL>
-__device__ __forceinline__ void apply_setting_lean(const float* rec, uint32_t elliptical_mask,
-                                                   const float (&p)[kApplyLeanP][7],
-                                                   float (&sv)[kApplyLeanP], float* stage,
-                                                   int tid) {
-  constexpr int P = kApplyLeanP, THREADS = kApplyLeanThreads;
+__device__ __forceinline__ double keep_if_inside(double sv, double x, double x_max, double y,
+                                                 double y_max) {
+  return (inside(x, x_max) && inside(y, y_max)) ? sv : 0.0;
+}
+
+template <typename T, int NAP, int MODE, bool ELLIPTICAL>
+__device__ __forceinline__ void apply_setting_lean(const T* rec, uint32_t elliptical_mask,
+                                                   const T (&p)[kApplyLeanP<T>][7],
+                                                   T (&sv)[kApplyLeanP<T>], T* stage, int tid) {
+  constexpr int P = kApplyLeanP<T>, THREADS = kApplyLeanThreads;
 #pragma unroll
   for (int ap = 0; ap < NAP; ++ap) {
-    float q[16];
+    T q[16];
     load_coefficients(q, rec + CH_RECORD_HEADER + CH_RECORD_MAP + ap * CH_RECORD_APERTURE);
-    const float x_max = q[14], y_max = q[15];
+    const T x_max = q[14], y_max = q[15];
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      float x, y;
+      T x, y;
       if constexpr (MODE == 1) {
-        x = fmaf(q[0], p[k][0], fmaf(q[1], p[k][1], fmaf(q[5], p[k][5], q[6])));
-        y = fmaf(q[9], p[k][2], fmaf(q[10], p[k][3], q[13]));
+        x = fma_t(q[0], p[k][0], fma_t(q[1], p[k][1], fma_t(q[5], p[k][5], q[6])));
+        y = fma_t(q[9], p[k][2], fma_t(q[10], p[k][3], q[13]));
       } else if constexpr (MODE == 2) {
-        x = affine_row_no_tau<float, true>(q, p[k]);
-        y = affine_row_no_tau<float, true>(q + 7, p[k]);
+        x = affine_row_no_tau<T, true>(q, p[k]);
+        y = affine_row_no_tau<T, true>(q + 7, p[k]);
       } else {
-        x = affine_row<float, true>(q, p[k]);
-        y = affine_row<float, true>(q + 7, p[k]);
+        x = affine_row<T, true>(q, p[k]);
+        y = affine_row<T, true>(q + 7, p[k]);
       }
       if (ELLIPTICAL && ((elliptical_mask >> ap) & 1u)) {
-        const float ex = div_rn(mul_rn(x, x), mul_rn(x_max, x_max));
-        const float ey = div_rn(mul_rn(y, y), mul_rn(y_max, y_max));
-        sv[k] = add_rn(ex, ey) <= 1.0f ? sv[k] : 0.0f;
+        const T ex = div_rn(mul_rn(x, x), mul_rn(x_max, x_max));
+        const T ey = div_rn(mul_rn(y, y), mul_rn(y_max, y_max));
+        sv[k] = add_rn(ex, ey) <= T(1) ? sv[k] : T(0);
       } else {
         sv[k] = keep_if_inside(sv[k], x, x_max, y, y_max);
       }
     }
   }
-  float c[44];
+  T c[44];
   load_coefficients(c, rec);
-  const float* m = c + CH_RECORD_HEADER;
+  const T* m = c + CH_RECORD_HEADER;
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    float* row = stage + (tid + k * THREADS) * 7;
+    T* row = stage + (tid + k * THREADS) * 7;
     if constexpr (MODE == 1) {
-      row[0] = fmaf(m[0], p[k][0], fmaf(m[1], p[k][1], fmaf(m[5], p[k][5], m[6])));
-      row[1] = fmaf(m[7], p[k][0], fmaf(m[8], p[k][1], fmaf(m[12], p[k][5], m[13])));
-      row[2] = fmaf(m[16], p[k][2], fmaf(m[17], p[k][3], m[20]));
-      row[3] = fmaf(m[23], p[k][2], fmaf(m[24], p[k][3], m[27]));
-      row[4] = fmaf(m[28], p[k][0],
-                    fmaf(m[29], p[k][1], fmaf(m[32], p[k][4], fmaf(m[33], p[k][5], m[34]))));
+      row[0] = fma_t(m[0], p[k][0], fma_t(m[1], p[k][1], fma_t(m[5], p[k][5], m[6])));
+      row[1] = fma_t(m[7], p[k][0], fma_t(m[8], p[k][1], fma_t(m[12], p[k][5], m[13])));
+      row[2] = fma_t(m[16], p[k][2], fma_t(m[17], p[k][3], m[20]));
+      row[3] = fma_t(m[23], p[k][2], fma_t(m[24], p[k][3], m[27]));
+      row[4] = fma_t(m[28], p[k][0],
+                    fma_t(m[29], p[k][1], fma_t(m[32], p[k][4], fma_t(m[33], p[k][5], m[34]))));
       row[5] = p[k][5];
     } else if constexpr (MODE == 2) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) row[i] = affine_row_no_tau<float, true>(m + i * 7, p[k]);
-      row[4] = affine_row<float, true>(m + 28, p[k]);
+      for (int i = 0; i < 4; ++i) row[i] = affine_row_no_tau<T, true>(m + i * 7, p[k]);
+      row[4] = affine_row<T, true>(m + 28, p[k]);
       row[5] = p[k][5];
     } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) row[i] = affine_row<float, true>(m + i * 7, p[k]);
+      for (int i = 0; i < 6; ++i) row[i] = affine_row<T, true>(m + i * 7, p[k]);
     }
-    row[6] = 1.0f;
+    row[6] = T(1);
   }
 }
 
-template <int NAP, bool ELLIPTICAL>
-__global__ void __launch_bounds__(kApplyLeanThreads, 3)
-apply_shared_beam_kernel(const ApplyArgs<float> a) {
-  constexpr int THREADS = kApplyLeanThreads, P = kApplyLeanP, TP = P * THREADS;
+template <typename T, int NAP, bool ELLIPTICAL>
+__global__ void __launch_bounds__(kApplyLeanThreads, sizeof(T) == 4 ? 3 : 2)
+apply_shared_beam_kernel(const ApplyArgs<T> a) {
+  constexpr int THREADS = kApplyLeanThreads, P = kApplyLeanP<T>, TP = P * THREADS;
   constexpr int RECLEN = CH_RECORD_LEN(NAP);
   static_assert(RECLEN % 4 == 0 && RECLEN <= THREADS, "one record entry per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage0 = reinterpret_cast<float*>(smem_raw);
-  float* stage1 = stage0 + TP * 7;
-  __shared__ __align__(16) float recs[2][RECLEN];
+  T* stage0 = reinterpret_cast<T*>(smem_raw);
+  T* stage1 = stage0 + TP * 7;
+  __shared__ __align__(16) T recs[2][RECLEN];
   __shared__ uint64_t bar;
 
   const int tid = threadIdx.x;
@@ -386,12 +393,12 @@ apply_shared_beam_kernel(const ApplyArgs<float> a) {
   if (n_local <= 0) return;
 
   {
-    const float* src = a.particles_in + n0 * 7;
+    const T* src = a.particles_in + n0 * 7;
     if (a.bulk_in) {
       if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
-        const uint32_t bytes = static_cast<uint32_t>(count) * 7u * sizeof(float);
+        const uint32_t bytes = static_cast<uint32_t>(count) * 7u * sizeof(T);
         mbar_expect_tx(&bar, bytes);
         bulk_load(stage1, src, bytes, &bar);
       }
@@ -402,26 +409,26 @@ apply_shared_beam_kernel(const ApplyArgs<float> a) {
       __syncthreads();
     }
   }
-  float p[P][7], sv_in[P];
+  T p[P][7], sv_in[P];
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     const int local = tid + k * THREADS;
 #pragma unroll
-    for (int j = 0; j < 7; ++j) p[k][j] = local < count ? stage1[local * 7 + j] : 0.0f;
-    sv_in[k] = (a.survival_in != nullptr && local < count) ? a.survival_in[n0 + local] : 1.0f;
+    for (int j = 0; j < 7; ++j) p[k][j] = local < count ? stage1[local * 7 + j] : T(0);
+    sv_in[k] = (a.survival_in != nullptr && local < count) ? a.survival_in[n0 + local] : T(1);
   }
   // the records come from the compose kernel launched just before (see the observables kernel)
   grid_dependency_wait();
-  const float* rec_src = a.records + b_begin * a.record_stride;
-  float fetched = tid < RECLEN ? rec_src[tid] : 0.0f;
+  const T* rec_src = a.records + b_begin * a.record_stride;
+  T fetched = tid < RECLEN ? rec_src[tid] : T(0);
   if (tid < RECLEN) recs[0][tid] = fetched;
   __syncthreads();  // record 0 complete; everybody holds its particles (stage1 is reused later)
 
-  float* out = a.particles_out + (b_begin * a.n_particles + n0) * 7;
-  float* survival_out =
+  T* out = a.particles_out + (b_begin * a.n_particles + n0) * 7;
+  T* survival_out =
       a.survival_out != nullptr ? a.survival_out + b_begin * a.n_particles + n0 : nullptr;
   const int64_t out_step = a.n_particles * 7;
-  const uint32_t tile_bytes = static_cast<uint32_t>(count) * 7u * sizeof(float);
+  const uint32_t tile_bytes = static_cast<uint32_t>(count) * 7u * sizeof(T);
   constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
                                CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
   constexpr uint32_t kCoupled = CH_FLAG_NO_TAU_COLUMN | CH_FLAG_DELTA_IDENTITY;
@@ -429,22 +436,22 @@ apply_shared_beam_kernel(const ApplyArgs<float> a) {
 #pragma unroll 1
   for (int it = 0; it < n_local; ++it) {
     const int buf = it & 1;
-    float* stage = buf ? stage1 : stage0;
-    const float* rec = recs[buf];
+    T* stage = buf ? stage1 : stage0;
+    const T* rec = recs[buf];
     if (it + 1 < n_local) {  // in flight during the arithmetic below
       rec_src += a.record_stride;
-      fetched = tid < RECLEN ? rec_src[tid] : 0.0f;
+      fetched = tid < RECLEN ? rec_src[tid] : T(0);
     }
-    float sv[P];
+    T sv[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) sv[k] = sv_in[k];
     const uint32_t flags = record_flags(rec[0]);
     if ((flags & kSparse) == kSparse)
-      apply_setting_lean<NAP, 1, ELLIPTICAL>(rec, a.elliptical_mask, p, sv, stage, tid);
+      apply_setting_lean<T, NAP, 1, ELLIPTICAL>(rec, a.elliptical_mask, p, sv, stage, tid);
     else if ((flags & kCoupled) == kCoupled)
-      apply_setting_lean<NAP, 2, ELLIPTICAL>(rec, a.elliptical_mask, p, sv, stage, tid);
+      apply_setting_lean<T, NAP, 2, ELLIPTICAL>(rec, a.elliptical_mask, p, sv, stage, tid);
     else
-      apply_setting_lean<NAP, 0, ELLIPTICAL>(rec, a.elliptical_mask, p, sv, stage, tid);
+      apply_setting_lean<T, NAP, 0, ELLIPTICAL>(rec, a.elliptical_mask, p, sv, stage, tid);
     if (survival_out != nullptr) {
 #pragma unroll
       for (int k = 0; k < P; ++k) {
@@ -478,15 +485,19 @@ apply_shared_beam_kernel(const ApplyArgs<float> a) {
 
 // One beam (and one incoming survival vector) under consecutive records with at most three
 // apertures and no cavity tail: the call shape the kernels of this file are specialised for.
-bool shared_beam_call(const ApplyArgs<float>& args, bool unit_seventh) {
+template <typename T>
+bool shared_beam_call(const ApplyArgs<T>& args, bool unit_seventh) {
   return unit_seventh && args.particle_stride == 0 && args.record_index == nullptr &&
          (args.survival_in == nullptr || args.survival_stride == 0) && args.n_apertures <= 3 &&
          args.record_len == CH_RECORD_LEN(args.n_apertures) && !args.has_cavity && !args.compact;
 }
 
+template bool shared_beam_call<float>(const ApplyArgs<float>&, bool);
+template bool shared_beam_call<double>(const ApplyArgs<double>&, bool);
+
 namespace {
-template <typename Launch>
-int with_apertures(const ApplyArgs<float>& args, Launch&& launch) {
+template <typename T, typename Launch>
+int with_apertures(const ApplyArgs<T>& args, Launch&& launch) {
   const bool elliptical = (args.elliptical_mask & ((1u << args.n_apertures) - 1u)) != 0;
   using std::integral_constant;
   auto pick = [&](auto nap) -> int {
@@ -522,15 +533,16 @@ int launch_observe_shared_beam(const ApplyArgs<float>& args, cudaStream_t stream
                          : run(std::integral_constant<int, 1>{});
 }
 
-int launch_apply_shared_beam(const ApplyArgs<float>& args, cudaStream_t stream) {
-  constexpr int TP = kApplyLeanP * kApplyLeanThreads;
+template <typename T>
+int launch_apply_shared_beam(const ApplyArgs<T>& args, cudaStream_t stream) {
+  constexpr int TP = kApplyLeanP<T> * kApplyLeanThreads;
   const int64_t tiles = (args.n_particles + TP - 1) / TP;
   const int64_t chunks = (args.n_settings + args.settings_per_cta - 1) / args.settings_per_cta;
   CH_REQUIRE(tiles <= 2147483647LL && chunks <= 65535, "ch_apply_maps: grid too large");
   const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(chunks));
-  const size_t smem = sizeof(float) * 2 * TP * 7;
+  const size_t smem = sizeof(T) * 2 * TP * 7;
   return with_apertures(args, [&](auto nap, auto elliptical) -> int {
-    auto kernel = apply_shared_beam_kernel<decltype(nap)::value, decltype(elliptical)::value>;
+    auto kernel = apply_shared_beam_kernel<T, decltype(nap)::value, decltype(elliptical)::value>;
     CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
     CH_CUDA(launch_dependent(kernel, grid, dim3(kApplyLeanThreads), smem, stream, args));
@@ -538,5 +550,7 @@ int launch_apply_shared_beam(const ApplyArgs<float>& args, cudaStream_t stream) 
     return CH_OK;
   });
 }
+template int launch_apply_shared_beam<float>(const ApplyArgs<float>&, cudaStream_t);
+template int launch_apply_shared_beam<double>(const ApplyArgs<double>&, cudaStream_t);
 
 }  // namespace ch

@@ -10,10 +10,10 @@ pytestmark = pytest.mark.gpu
 DEVICE = "cuda"
 
 
-def _segment(n_apertures, shape, coupling):
+def _segment(n_apertures, shape, coupling, dtype=torch.float32):
     import cheetah_b200 as cb
 
-    t = lambda v: torch.tensor(v, device=DEVICE, dtype=torch.float32)  # noqa: E731
+    t = lambda v: torch.tensor(v, device=DEVICE, dtype=dtype)  # noqa: E731
     tilt = 0.3 if coupling != "sparse" else 0.0
     elements = [cb.Quadrupole(length=t(0.2), k1=t([4.0, -3.0, 1.5, 0.0, 2.5, -1.0, 0.7]),
                               tilt=t(tilt)),
@@ -31,25 +31,26 @@ def _segment(n_apertures, shape, coupling):
     return cb.Segment(elements)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
 @pytest.mark.parametrize("coupling", ["sparse", "coupled", "dense"])
 @pytest.mark.parametrize("shape", ["rectangular", "elliptical"])
 @pytest.mark.parametrize("n_apertures", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("n", [70_001, 1024, 37])
-def test_shared_beam_track_equals_general_kernel(n, n_apertures, shape, coupling):
+def test_shared_beam_track_equals_general_kernel(n, n_apertures, shape, coupling, dtype):
     import cheetah_b200 as cb
 
     if n_apertures == 0 and shape == "elliptical":
         pytest.skip("no aperture to shape")
-    segment = _segment(n_apertures, shape, coupling)
+    segment = _segment(n_apertures, shape, coupling, dtype)
     torch.manual_seed(3)
-    beam = cb.ParticleBeam.from_parameters(num_particles=n, device=DEVICE, dtype=torch.float32)
-    beam.survival_probabilities = (torch.rand(n, device=DEVICE) > 0.1).float()
+    beam = cb.ParticleBeam.from_parameters(num_particles=n, device=DEVICE, dtype=dtype)
+    beam.survival_probabilities = (torch.rand(n, device=DEVICE) > 0.1).to(dtype)
     out = segment.track(beam)  # one beam, seven settings: apply_shared_beam_kernel up to 3 apertures
 
     per_setting = cb.ParticleBeam(
         particles=beam.particles.unsqueeze(0).repeat(7, 1, 1), energy=beam.energy,
         survival_probabilities=beam.survival_probabilities.unsqueeze(0).repeat(7, 1),
-        particle_charges=beam.particle_charges, device=DEVICE, dtype=torch.float32)
+        particle_charges=beam.particle_charges, device=DEVICE, dtype=dtype)
     general = segment.track(per_setting)  # a beam per setting: apply_maps_kernel
     assert out.particles.shape == (7, n, 7)
     assert torch.equal(out.particles, general.particles)
