@@ -519,7 +519,7 @@ def ares_dense_section(ctx: Context, args, beam, per_rank: int, begin: int, end:
             "unit": UNIT,
             "mean_survival": survival,
             "roofline": {
-                "kernel": f"apply_shared_beam_kernel<NAP=3, ELLIPTICAL=0>, {branch}",
+                "kernel": f"apply_shared_beam_kernel<float, NAP=3, ELLIPTICAL=0>, {branch}",
                 "bound": "hbm", "achieved": nbytes / (mean_apply * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": nbytes / (mean_apply * 1e-3) / 1e9 / peak,
                 "mean_launch_ms": mean_apply, "algorithmic_bytes_per_launch": nbytes,
@@ -659,7 +659,7 @@ def run_ares(args) -> None:
         traffic = per_unit * per_rank * args.particles
         traffic_note = "ncu dram bytes at 256 settings, scaled per (particle, setting)"
     roofline = {
-        "kernel": "apply_shared_beam_kernel<NAP=3, ELLIPTICAL=0> (ch_apply_maps: one beam under "
+        "kernel": "apply_shared_beam_kernel<float, NAP=3, ELLIPTICAL=0> (ch_apply_maps: one beam under "
                   "consecutive settings; 4 particles per thread, 256 threads), sparse branch",
         "bound": "hbm",
         "achieved": achieved,
