@@ -8,10 +8,10 @@
 namespace ch {
 namespace {
 
-// ---- the common call of the above, specialised ---------------------------------------------------
+// ---- observables only ---------------------------------------------------------------------------
 // Segment.track_moments of ONE beam under many settings (shared beam and incoming survival,
 // consecutive records, unit seventh column, at most three apertures: the ARES case).  Same
-// arithmetic, same chains and the same masks as observe_maps_kernel; what goes away is the
+// arithmetic, same chains and the same masks as observe_maps_kernel (apply.cu); what goes away is the
 // bookkeeping per setting: the aperture count and the record length are compile-time constants
 // (records live in a static shared array, every LDS has an immediate offset, the aperture block
 // is unrolled and its selects overlap the next block's FFMA2s), the beam is loaded once before
