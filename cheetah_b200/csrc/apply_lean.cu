@@ -34,7 +34,18 @@ __device__ __forceinline__ float keep_if_inside(float sv, float x, float x_max, 
   return out;
 }
 
-template <int NAP, bool SPARSE, int MOMENTS, bool ELLIPTICAL>
+// c[0..3] . p[0..3] + c[5] p[5] + c[6]: a row without tau dependence (CH_FLAG_NO_TAU_COLUMN), the
+// chain of affine_row_no_tau
+__device__ __forceinline__ f2 affine_row_no_tau2(const f2* c, const f2 (&p)[7], f2 constant) {
+  f2 acc = fma2(c[5], p[5], constant);
+#pragma unroll
+  for (int j = 3; j >= 0; --j) acc = fma2(c[j], p[j], acc);
+  return acc;
+}
+
+// MODE as in process_setting (apply.cu): 0 dense, 1 sparse, 2 coupled (x-y coupling and dispersion
+// allowed, no tau column in rows 0-3, delta untouched)
+template <int NAP, int MODE, int MOMENTS, bool ELLIPTICAL>
 __device__ __forceinline__ void observe_setting_lean(const f2* rec2, uint32_t elliptical_mask,
                                                      const f2 (&p)[4][7], f2 (&sv)[4],
                                                      const float (&first_particle)[7],
@@ -49,9 +60,12 @@ __device__ __forceinline__ void observe_setting_lean(const f2* rec2, uint32_t el
     f2 x[PAIRS], y[PAIRS];
 #pragma unroll
     for (int k = 0; k < PAIRS; ++k) {
-      if constexpr (SPARSE) {
+      if constexpr (MODE == 1) {
         x[k] = fma2(q[0], p[k][0], fma2(q[1], p[k][1], fma2(q[5], p[k][5], q[6])));
         y[k] = fma2(q[9], p[k][2], fma2(q[10], p[k][3], q[13]));
+      } else if constexpr (MODE == 2) {
+        x[k] = affine_row_no_tau2(q, p[k], q[6]);
+        y[k] = affine_row_no_tau2(q + 7, p[k], q[13]);
       } else {
         x[k] = affine_row2<true>(q, p[k]);
         y[k] = affine_row2<true>(q + 7, p[k]);
@@ -84,13 +98,26 @@ __device__ __forceinline__ void observe_setting_lean(const f2* rec2, uint32_t el
   const f2* m = c + CH_RECORD_HEADER;
   {
     const float(&in)[7] = first_particle;
-    if constexpr (SPARSE) {
+    if constexpr (MODE == 1) {
       pilot[0] = fmaf(m[0].x, in[0], fmaf(m[1].x, in[1], fmaf(m[5].x, in[5], m[6].x)));
       pilot[1] = fmaf(m[7].x, in[0], fmaf(m[8].x, in[1], fmaf(m[12].x, in[5], m[13].x)));
       pilot[2] = fmaf(m[16].x, in[2], fmaf(m[17].x, in[3], m[20].x));
       pilot[3] = fmaf(m[23].x, in[2], fmaf(m[24].x, in[3], m[27].x));
       pilot[4] = fmaf(m[28].x, in[0],
                       fmaf(m[29].x, in[1], fmaf(m[32].x, in[4], fmaf(m[33].x, in[5], m[34].x))));
+      pilot[5] = in[5];
+    } else if constexpr (MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float acc1 = fmaf(m[i * 7 + 5].x, in[5], m[i * 7 + 6].x);
+#pragma unroll
+        for (int j = 3; j >= 0; --j) acc1 = fmaf(m[i * 7 + j].x, in[j], acc1);
+        pilot[i] = acc1;
+      }
+      float acc4 = m[34].x;
+#pragma unroll
+      for (int j = 5; j >= 0; --j) acc4 = fmaf(m[28 + j].x, in[j], acc4);
+      pilot[4] = acc4;
       pilot[5] = in[5];
     } else {
 #pragma unroll
@@ -114,13 +141,23 @@ __device__ __forceinline__ void observe_setting_lean(const f2* rec2, uint32_t el
 #pragma unroll
   for (int k = 0; k < PAIRS; ++k) {
     f2 d[6];
-    if constexpr (SPARSE) {
+    if constexpr (MODE == 1) {
       d[0] = fma2(m[0], p[k][0], fma2(m[1], p[k][1], fma2(m[5], p[k][5], shifted[0])));
       d[1] = fma2(m[7], p[k][0], fma2(m[8], p[k][1], fma2(m[12], p[k][5], shifted[1])));
       d[2] = fma2(m[16], p[k][2], fma2(m[17], p[k][3], shifted[2]));
       d[3] = fma2(m[23], p[k][2], fma2(m[24], p[k][3], shifted[3]));
       d[4] = fma2(m[28], p[k][0],
                   fma2(m[29], p[k][1], fma2(m[32], p[k][4], fma2(m[33], p[k][5], shifted[4]))));
+      d[5] = add2(p[k][5], f2{-pilot[5], -pilot[5]});
+    } else if constexpr (MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[i] = affine_row_no_tau2(m + i * 7, p[k], shifted[i]);
+      {
+        f2 acc1 = shifted[4];
+#pragma unroll
+        for (int j = 5; j >= 0; --j) acc1 = fma2(m[28 + j], p[k][j], acc1);
+        d[4] = acc1;
+      }
       d[5] = add2(p[k][5], f2{-pilot[5], -pilot[5]});
     } else {
 #pragma unroll
@@ -244,6 +281,7 @@ observe_shared_beam_kernel(const ApplyArgs<float> a) {
   };
   constexpr uint32_t kSparse = CH_FLAG_XY_UNCOUPLED | CH_FLAG_NO_TAU_COLUMN |
                                CH_FLAG_NO_Y_DISPERSION | CH_FLAG_DELTA_IDENTITY;
+  constexpr uint32_t kCoupled = CH_FLAG_NO_TAU_COLUMN | CH_FLAG_DELTA_IDENTITY;
   const int lane = tid & 31;
   const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
                    ((lane >> 1) & 1);
@@ -266,12 +304,16 @@ observe_shared_beam_kernel(const ApplyArgs<float> a) {
     for (int k = 0; k < PAIRS; ++k) sv[k] = sv_in[k];
     float pilot[6];
     f2 acc2[NSUM];
-    if ((record_flags(rec2[0].x) & kSparse) == kSparse)
-      observe_setting_lean<NAP, true, MOMENTS, ELLIPTICAL>(rec2, a.elliptical_mask, p, sv, first,
-                                                           pilot, acc2);
+    const uint32_t flags = record_flags(rec2[0].x);
+    if ((flags & kSparse) == kSparse)
+      observe_setting_lean<NAP, 1, MOMENTS, ELLIPTICAL>(rec2, a.elliptical_mask, p, sv, first,
+                                                        pilot, acc2);
+    else if ((flags & kCoupled) == kCoupled)
+      observe_setting_lean<NAP, 2, MOMENTS, ELLIPTICAL>(rec2, a.elliptical_mask, p, sv, first,
+                                                        pilot, acc2);
     else
-      observe_setting_lean<NAP, false, MOMENTS, ELLIPTICAL>(rec2, a.elliptical_mask, p, sv, first,
-                                                            pilot, acc2);
+      observe_setting_lean<NAP, 0, MOMENTS, ELLIPTICAL>(rec2, a.elliptical_mask, p, sv, first,
+                                                        pilot, acc2);
     if (it + 1 < n_local && tid < RECLEN) recs[buf ^ 1][tid] = f2{fetched, fetched};
     float acc[NACC];
 #pragma unroll

@@ -153,7 +153,8 @@ def test_track_moments_against_the_oracle_beam():
 @pytest.mark.parametrize("shape", ["rectangular", "elliptical"])
 @pytest.mark.parametrize("n_apertures", [1, 2, 3, 4])
 @pytest.mark.parametrize("beam_per_setting", [False, True], ids=["shared_beam", "beam_per_setting"])
-def test_observables_kernel_variants(n_apertures, shape, covariance, beam_per_setting):
+@pytest.mark.parametrize("coupling", ["sparse", "coupled", "dense"])
+def test_observables_kernel_variants(n_apertures, shape, covariance, beam_per_setting, coupling):
     """Every dispatch of the observables-only path (apply.cu): the kernel specialised for one
     beam under many settings (0-3 apertures, rectangular-only or with elliptical ones, with and
     without the covariance sums) and the general kernel (four apertures, a beam per setting)
@@ -161,7 +162,14 @@ def test_observables_kernel_variants(n_apertures, shape, covariance, beam_per_se
     import cheetah_b200 as cb
 
     t = lambda v: torch.tensor(v, device=DEVICE, dtype=torch.float32)  # noqa: E731
-    elements = [cb.Quadrupole(length=t(0.2), k1=t([4.0, -3.0, 1.5, 0.0, 2.5]))]
+    tilt = 0.0 if coupling == "sparse" else 0.3  # a tilted quadrupole couples x and y
+    elements = [cb.Quadrupole(length=t(0.2), k1=t([4.0, -3.0, 1.5, 0.0, 2.5]), tilt=t(tilt))]
+    if coupling == "dense":  # a tau column and a changed delta row: no sparsity flag holds
+        matrix = torch.eye(7)
+        matrix[0, 4], matrix[1, 4], matrix[2, 4] = 2e-3, -1e-3, 5e-4
+        matrix[5, 4], matrix[5, 0], matrix[4, 5] = 3e-3, 1e-3, 0.2
+        elements.append(cb.CustomTransferMap(predefined_transfer_map=t(matrix.tolist()),
+                                             length=t(0.1)))
     for i in range(n_apertures):
         elements += [cb.Drift(length=t(0.4 + 0.1 * i)),
                      cb.Aperture(x_max=t(2.5e-4 + 5e-5 * i), y_max=t(3e-4 - 2e-5 * i), shape=shape)]
