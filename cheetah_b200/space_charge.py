@@ -19,6 +19,8 @@ from .tracking import _bshape, _new_beam
 
 def _flat(tensor: torch.Tensor, vector_shape: tuple, inner: tuple, dtype) -> tuple:
     """(contiguous tensor, batch stride in elements) of ``tensor`` viewed as [B, *inner]."""
+    if tensor.dim() == len(inner) and tensor.dtype == dtype and tensor.is_contiguous():
+        return tensor, 0  # nothing vectorised (the usual case): one value for every beam
     vshape = tuple(tensor.shape[: tensor.dim() - len(inner)])
     if tensor.dtype != dtype:
         tensor = tensor.to(dtype)
@@ -150,11 +152,10 @@ def _side_stream(device) -> torch.cuda.Stream:
     return stream
 
 
-def _workspace(n_beams: int, grid_shape: tuple, dtype, device) -> Workspace:
+def _workspace(n_beams: int, grid_shape: tuple, dtype, device, stream: int) -> Workspace:
     """One cached workspace per (batch, grid, dtype, device, stream): kicks on a stream are
     ordered, so the scratch of the previous kick is free when the next one starts."""
-    key = (n_beams, tuple(grid_shape), dtype, device,
-           torch.cuda.current_stream(device).cuda_stream, use_field_bricks, brick_group_bytes)
+    key = (n_beams, tuple(grid_shape), dtype, device, stream, use_field_bricks, brick_group_bytes)
     ws = _workspace_cache.get(key)
     if ws is None:
         if len(_workspace_cache) >= 4:
@@ -165,7 +166,7 @@ def _workspace(n_beams: int, grid_shape: tuple, dtype, device) -> Workspace:
 
 def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, grid_shape,
          want_intermediates: bool = False, prepared: Prepared | None = None, element=None,
-         fuse_records=None, next_element=None, records_ready=None):
+         fuse_records=None, next_element=None, records_ready=None, next_tensors=None):
     """Run one kick on already-broadcast inputs; returns (particles_out [B,N,7], workspace).
 
     ``prepared``: the grid parameters were computed by the previous kick (skip the moments pass).
@@ -199,10 +200,10 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
     ext = [_scalar_ref(x, vector_shape, dtype) for x in extents]
     mass = mass_eV if mass_eV.dtype in (torch.float32, torch.float64) else mass_eV.to(dtype)
 
-    ws = _workspace(n_beams, (nx, ny, nz), dtype, device)
+    stream = _capi.current_stream(device)
+    ws = _workspace(n_beams, (nx, ny, nz), dtype, device, stream)
     out = torch.empty((n_beams, n, 7), dtype=dtype, device=device)
     forces = torch.empty((n_beams, n, 3), dtype=dtype, device=device) if want_intermediates else None
-    stream = _capi.current_stream(device)
     ws.prepared_next = None
     # torch.use_deterministic_algorithms: fixed-order moment sums and fixed-point deposit, and no
     # moments fused into the gather (its cross-CTA sums are float64 atomics)
@@ -234,8 +235,8 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
             else:
                 _capi.check(lib.ch_sc_moments_and_params(
                     *moment_args, ws.stats.data_ptr(), ws.params.data_ptr(), stream))
-        main = torch.cuda.current_stream(device)
         if deterministic or want_intermediates:
+            main = torch.cuda.current_stream(device)
             # the Green-function chain only needs the grid parameters: it runs on a side stream
             # concurrently with the deposit and the first two FFT passes of the charge
             side = _side_stream(device)
@@ -280,16 +281,13 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
                 ws.green_spectrum.data_ptr(), ws.rho_spectrum.data_ptr(), ws.phi.data_ptr(),
                 stream))
         if records_ready is not None:
-            main.wait_event(records_ready)
+            torch.cuda.current_stream(device).wait_event(records_ready)
         nxt = None
         next_slot = 1 - ws.slot
         if next_element is not None:
-            nlen, nl_stride = _scalar_ref(next_element.effect_length, vector_shape, dtype)
-            next = [
-                _scalar_ref(x, vector_shape, dtype)
-                for x in (next_element.grid_extent_x, next_element.grid_extent_y,
-                          next_element.grid_extent_tau)
-            ]
+            following = next_tensors or KickTensors(next_element)
+            nlen, nl_stride = _scalar_ref(following.effect_length, vector_shape, dtype)
+            next = [_scalar_ref(x, vector_shape, dtype) for x in following.extents]
             nxt = (nlen, nl_stride, next)
         record_stride = 0
         if fuse_records is not None and fuse_records.shape[0] > 1:
@@ -333,13 +331,28 @@ def kick(particles, energy, charges, survival, mass_eV, effect_length, extents, 
     return out.reshape(*vector_shape, n, 7), ws
 
 
-def kick_vector_shape(element, incoming) -> tuple:
+class KickTensors:
+    """The tensors of one SpaceChargeKick element, read once per lowered program (every attribute
+    of an element is an ``nn.Module.__getattr__`` call, and a kick needs them a dozen times; a
+    re-assigned attribute re-lowers the lattice, so the lowered stage may hold them like the slot
+    table holds the parameters of linear elements)."""
+
+    __slots__ = ("effect_length", "extents", "grid_shape", "shapes")
+
+    def __init__(self, element) -> None:
+        self.effect_length = element.effect_length
+        self.extents = (element.grid_extent_x, element.grid_extent_y, element.grid_extent_tau)
+        self.grid_shape = tuple(int(v) for v in element.grid_shape)
+        self.shapes = (self.effect_length.shape, *(e.shape for e in self.extents))
+
+
+def kick_vector_shape(element, incoming, tensors: KickTensors | None = None) -> tuple:
     """Vector shape one kick works on (space_charge_kick.py:493-528, without the (1,) helper)."""
+    tensors = tensors or KickTensors(element)
     return tuple(_bshape(
         incoming.particles.shape[:-2], incoming.energy.shape,
         incoming.particle_charges.shape[:-1], incoming.survival_probabilities.shape[:-1],
-        element.effect_length.shape, element.grid_extent_x.shape, element.grid_extent_y.shape,
-        element.grid_extent_tau.shape,
+        *tensors.shapes,
     ))
 
 
@@ -349,7 +362,8 @@ def track(element, incoming):
 
 
 def track_fused(element, incoming, prepared: Prepared | None = None, fuse_records=None,
-                next_element=None, records_ready=None):
+                next_element=None, records_ready=None, tensors: KickTensors | None = None,
+                next_tensors: KickTensors | None = None):
     """``SpaceChargeKick.track`` plus, optionally, the linear map of the following section and
     the moments of the following kick in the same particle pass.  Returns (beam, Prepared|None);
     the caller adds the section length to ``s`` when it passed ``fuse_records``."""
@@ -359,25 +373,26 @@ def track_fused(element, incoming, prepared: Prepared | None = None, fuse_record
     particles = incoming.particles
     if particles.dtype not in (torch.float32, torch.float64):
         raise TypeError(f"cheetah_b200 tracks float32/float64 beams, got {particles.dtype}")
-    for name in ("effect_length", "grid_extent_x", "grid_extent_y", "grid_extent_tau"):
-        tensor = getattr(element, name)
+    tensors = tensors or KickTensors(element)
+    names = ("effect_length", "grid_extent_x", "grid_extent_y", "grid_extent_tau")
+    for name, tensor in zip(names, (tensors.effect_length, *tensors.extents)):
         if tensor.device != particles.device:
             raise ValueError(
                 f"{name} of element {element.name!r} lives on {tensor.device} but the beam is on "
                 f"{particles.device}; move the lattice with `segment.to(device)` first"
             )
+    if next_element is not None and next_tensors is None:
+        next_tensors = KickTensors(next_element)
     out, ws = kick(
         particles, incoming.energy, incoming.particle_charges, incoming.survival_probabilities,
-        incoming.species.mass_eV, element.effect_length,
-        (element.grid_extent_x, element.grid_extent_y, element.grid_extent_tau),
-        element.grid_shape, prepared=prepared, element=element, fuse_records=fuse_records,
-        next_element=next_element, records_ready=records_ready,
+        incoming.species.mass_eV, tensors.effect_length, tensors.extents,
+        tensors.grid_shape, prepared=prepared, element=element, fuse_records=fuse_records,
+        next_element=next_element, records_ready=records_ready, next_tensors=next_tensors,
     )
     # the reference drops the (1,) helper dimension again when nothing is vectorised
     out_shape = _bshape(
         particles.shape[:-2], incoming.energy.shape, incoming.particle_charges.shape[:-1],
-        incoming.survival_probabilities.shape[:-1], element.effect_length.shape,
-        element.grid_extent_x.shape, element.grid_extent_y.shape, element.grid_extent_tau.shape,
+        incoming.survival_probabilities.shape[:-1], *tensors.shapes,
     )
     out = out.reshape(*out_shape, particles.shape[-2], 7)
     outgoing = _new_beam(

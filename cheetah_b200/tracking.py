@@ -472,10 +472,17 @@ def _track_space_charge(program, stages: list, i: int, beam, prepared):
     beam) and the moments of the kick after that.  Returns (beam, prepared, stages consumed)."""
     from . import space_charge
 
+    def kick_tensors(stage):  # read once per lowered program, see space_charge.KickTensors
+        cached = stage.__dict__.get("_kick_tensors")
+        if cached is None:
+            cached = stage.__dict__["_kick_tensors"] = space_charge.KickTensors(stage.element)
+        return cached
+
     element = stages[i].element
-    section = records = next_element = None
+    tensors = kick_tensors(stages[i])
+    section = records = next_element = next_tensors = None
     if fuse_space_charge and type(beam).__name__ == "ParticleBeam":
-        vs = space_charge.kick_vector_shape(element, beam)
+        vs = space_charge.kick_vector_shape(element, beam, tensors)
         j = i + 1
         if j < len(stages) and isinstance(stages[j], lowering.LinearSection):
             candidate = stages[j]
@@ -489,14 +496,12 @@ def _track_space_charge(program, stages: list, i: int, beam, prepared):
         if j < len(stages) and isinstance(stages[j], lowering.Barrier) \
                 and stages[j].kind == "space_charge":
             candidate = stages[j].element
-            shapes = [candidate.effect_length.shape, candidate.grid_extent_x.shape,
-                      candidate.grid_extent_y.shape, candidate.grid_extent_tau.shape]
-            if (tuple(candidate.grid_shape) == tuple(element.grid_shape)
-                    and tuple(_bshape(vs, *shapes)) == vs
+            following = kick_tensors(stages[j])
+            if (following.grid_shape == tensors.grid_shape
+                    and tuple(_bshape(vs, *following.shapes)) == vs
                     and all(t.device == beam.particles.device for t in (
-                        candidate.effect_length, candidate.grid_extent_x,
-                        candidate.grid_extent_y, candidate.grid_extent_tau))):
-                next_element = candidate
+                        following.effect_length, *following.extents))):
+                next_element, next_tensors = candidate, following
     records_ready = None
     if section is not None:
         # The maps of the following section only depend on the lattice and the beam energy: they
@@ -524,7 +529,7 @@ def _track_space_charge(program, stages: list, i: int, beam, prepared):
                                    beam.particles.dtype)
     outgoing, prepared = space_charge.track_fused(
         element, beam, prepared=prepared, fuse_records=records, next_element=next_element,
-        records_ready=records_ready,
+        records_ready=records_ready, tensors=tensors, next_tensors=next_tensors,
     )
     if section is not None:
         # (the kick made the main stream wait for the records)
