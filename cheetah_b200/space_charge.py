@@ -363,7 +363,7 @@ def track(element, incoming):
 
 def track_fused(element, incoming, prepared: Prepared | None = None, fuse_records=None,
                 next_element=None, records_ready=None, tensors: KickTensors | None = None,
-                next_tensors: KickTensors | None = None):
+                next_tensors: KickTensors | None = None, s=None, species=None):
     """``SpaceChargeKick.track`` plus, optionally, the linear map of the following section and
     the moments of the following kick in the same particle pass.  Returns (beam, Prepared|None);
     the caller adds the section length to ``s`` when it passed ``fuse_records``."""
@@ -395,9 +395,12 @@ def track_fused(element, incoming, prepared: Prepared | None = None, fuse_record
         incoming.survival_probabilities.shape[:-1], *tensors.shapes,
     )
     out = out.reshape(*out_shape, particles.shape[-2], 7)
+    # (`s`, `species`: the caller fused a linear section into the kick and passes the path length
+    # after it, so that the outgoing beam is built once)
     outgoing = _new_beam(
         incoming, out, incoming.energy, incoming.particle_charges,
-        incoming.survival_probabilities, incoming.s, incoming.species,
+        incoming.survival_probabilities, incoming.s if s is None else s,
+        incoming.species if species is None else species,
         getattr(incoming, "_unit_seventh", None),
     )
     return outgoing, ws.prepared_next

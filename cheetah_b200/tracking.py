@@ -527,6 +527,14 @@ def _track_space_charge(program, stages: list, i: int, beam, prepared):
         else:
             records, vm = _compose(program, section, beam.energy, beam.species,
                                    beam.particles.dtype)
+            # same stream as the kick: the outgoing beam is built once, with its final s
+            new_s = beam.s + _section_length(records, vm, section.length_shape)
+            outgoing, prepared = space_charge.track_fused(
+                element, beam, prepared=prepared, fuse_records=records,
+                next_element=next_element, tensors=tensors, next_tensors=next_tensors,
+                s=new_s, species=beam.species.clone(),
+            )
+            return outgoing, prepared, 2
     outgoing, prepared = space_charge.track_fused(
         element, beam, prepared=prepared, fuse_records=records, next_element=next_element,
         records_ready=records_ready, tensors=tensors, next_tensors=next_tensors,
