@@ -2273,10 +2273,12 @@ int green_spectrum(const double* lattice, const double* params, int far_field, i
   return CH_OK;
 }
 
+// `green_ready` (optional): event after which green_spectrum_compact is valid when it is computed
+// on another stream; only the x convolution waits for it, the charge's z and y passes do not.
 template <typename T>
 int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* params, int64_t B,
                   int nx, int ny, int nz, typename fft::Complex<T>::type* rs, T* phi,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, cudaEvent_t green_ready = nullptr) {
   using C = typename fft::Complex<T>::type;
   const int Nx = fft_len(nx), Ny = fft_len(ny), Nz = fft_len(nz), Kz = Nz / 2 + 1;
   const int lx = log2_exact(Nx), ly = log2_exact(Ny), lz = log2_exact(Nz);
@@ -2317,6 +2319,7 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
         });
       });
       CH_LAUNCH_CHECK();
+      if (green_ready != nullptr) CH_CUDA(cudaStreamWaitEvent(stream, green_ready, 0));
       fftr_dispatch(Nx, [&](auto L) {
         constexpr int LEN = decltype(L)::value;
         const int inner = Ny * Kz;
@@ -2369,6 +2372,7 @@ int poisson_solve(const T* rho, const T* green_spectrum_compact, const double* p
     CH_LAUNCH_CHECK();
   }
   // ---- x: forward . multiply by the Green spectrum . inverse, fused; only x < nx stored ----
+  if (green_ready != nullptr) CH_CUDA(cudaStreamWaitEvent(stream, green_ready, 0));
   {
     auto k = fft_strided_kernel<T, 2>;
     if (allow_smem(k, s_smem(Nx)) != CH_OK) return CH_ECUDA;
@@ -3153,8 +3157,13 @@ extern "C" int ch_sc_solve(const void* particles, int64_t particle_stride, const
   int status = side_stream(&side);
   if (status != CH_OK) return status;
   cudaStream_t main = static_cast<cudaStream_t>(stream);
-  // the Green-function chain only needs the grid parameters: it runs on the side stream next to
-  // the deposit (which is bound by L2 reductions, not by the SMs) and joins before the x pass
+  // The Green-function chain only needs the grid parameters: it runs on the side stream next to
+  // the deposit and joins right before the x convolution, the first kernel that reads its
+  // spectrum (not before the Poisson solve: the charge's quad sum, z and y passes do not need it;
+  // config 4 as a CUDA graph 11.8 -> 11.2 ms).  Starting the chain AFTER the deposit when there
+  // are many beams -- the deposit, bound by the L2's reduction rate, takes 2.6 instead of 1.97 ms
+  // for 128 beams while the chain shares the SMs -- measured slower (716 instead of 710 ms per 100
+  // kicks).
   CH_CUDA(cudaEventRecord(side->fork, main));
   CH_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
   status = ch_sc_green_function(params, n_beams, nx, ny, nz, dtype, lattice, nullptr, side->stream);
@@ -3167,7 +3176,15 @@ extern "C" int ch_sc_solve(const void* particles, int64_t particle_stride, const
                          survival_stride, params, n_particles, n_beams, nx, ny, nz, dtype, rho,
                          stream);
   if (status != CH_OK) return status;
-  CH_CUDA(cudaStreamWaitEvent(main, side->join, 0));
-  return ch_sc_poisson_solve(rho, green_spectrum, params, n_beams, nx, ny, nz, dtype, rho_spectrum,
-                             phi, stream);
+  CH_REQUIRE(rho && green_spectrum && params && rho_spectrum && phi,
+             "ch_sc_solve: NULL pointer argument");
+  if (dtype == CH_F32)
+    return ch::poisson_solve<float>(static_cast<const float*>(rho),
+                                    static_cast<const float*>(green_spectrum), params, n_beams,
+                                    nx, ny, nz, static_cast<float2*>(rho_spectrum),
+                                    static_cast<float*>(phi), main, side->join);
+  return ch::poisson_solve<double>(static_cast<const double*>(rho),
+                                   static_cast<const double*>(green_spectrum), params, n_beams, nx,
+                                   ny, nz, static_cast<double2*>(rho_spectrum),
+                                   static_cast<double*>(phi), main, side->join);
 }

@@ -570,9 +570,10 @@ int ch_sc_gather_kick_fused(const void* particles_in, int64_t particle_stride,
                             void* particles_out, void* stream);
 
 /* The grid half of one kick in one call: ch_sc_green_function + ch_sc_green_spectrum on an
- * internal high-priority side stream next to ch_sc_deposit on `stream`, joined before
- * ch_sc_poisson_solve (what the Python layer did with four calls and two events: at one beam
- * an eager kick is bound by the host's call rate).  Buffers as in those four functions.       */
+ * internal high-priority side stream next to ch_sc_deposit on `stream`, joined inside the
+ * Poisson solve right before its x convolution, the first kernel that reads the Green spectrum
+ * (the Python layer's four calls and two events join before ch_sc_poisson_solve; at one beam an
+ * eager kick is bound by the host's call rate).  Buffers as in those four functions.          */
 int ch_sc_solve(const void* particles, int64_t particle_stride,
                 const void* charges, int64_t charge_stride,
                 const void* survival, int64_t survival_stride,
