@@ -749,8 +749,7 @@ int launch_observe(const ApplyArgs<float>& args, bool unit_seventh, cudaStream_t
   if (shared_beam_call(args, unit_seventh) && args.survival_out == nullptr)
     return launch_observe_shared_beam(args, stream);
   auto launch = [&](auto kernel) -> int {
-    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
+    CH_CUDA(allow_dynamic_smem(reinterpret_cast<const void*>(kernel), static_cast<int>(smem)));
     kernel<<<grid, kObserveThreads, smem, stream>>>(args);
     return CH_OK;
   };
@@ -776,8 +775,7 @@ int launch_apply(const ApplyArgs<T>& args, bool unit_seventh, cudaStream_t strea
   CH_REQUIRE(tiles <= 2147483647LL && chunks <= 65535, "ch_apply_maps: grid too large");
   dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(chunks));
   auto launch = [&](auto kernel) -> int {
-    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
+    CH_CUDA(allow_dynamic_smem(reinterpret_cast<const void*>(kernel), static_cast<int>(smem)));
     kernel<<<grid, THREADS, smem, stream>>>(args);
     return CH_OK;
   };

@@ -585,8 +585,7 @@ int launch_apply_shared_beam(const ApplyArgs<T>& args, cudaStream_t stream) {
   const size_t smem = sizeof(T) * 2 * TP * 7;
   return with_apertures(args, [&](auto nap, auto elliptical) -> int {
     auto kernel = apply_shared_beam_kernel<T, decltype(nap)::value, decltype(elliptical)::value>;
-    CH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
+    CH_CUDA(allow_dynamic_smem(reinterpret_cast<const void*>(kernel), static_cast<int>(smem)));
     CH_CUDA(launch_dependent(kernel, grid, dim3(kApplyLeanThreads), smem, stream, args));
     CH_LAUNCH_CHECK();
     return CH_OK;

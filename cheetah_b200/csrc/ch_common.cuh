@@ -15,6 +15,8 @@ namespace ch {
 // ---- error channel (thread local, never throws across the ABI) -----------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// opt a kernel in to `bytes` of dynamic shared memory (cached per kernel and device)
+cudaError_t allow_dynamic_smem(const void* kernel, int bytes);
 
 #define CH_REQUIRE(cond, ...)          \
   do {                                 \

@@ -711,13 +711,13 @@ extern "C" int ch_compose_maps(const ch_program* program, int32_t op_begin, int3
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int smem = ch::kChunk * ch::kCoef * sizeof(double);  // + ~27 KB static: opt in above 48 KB
   if (record_dtype == CH_F32) {
-    CH_CUDA(cudaFuncSetAttribute(ch::compose_maps_kernel<float>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CH_CUDA(ch::allow_dynamic_smem(
+        reinterpret_cast<const void*>(ch::compose_maps_kernel<float>), smem));
     ch::compose_maps_kernel<float><<<blocks, ch::kThreads, smem, s>>>(
         prog, op_begin, op_end, e, m, q, n_apertures, static_cast<float*>(records), record_len);
   } else {
-    CH_CUDA(cudaFuncSetAttribute(ch::compose_maps_kernel<double>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CH_CUDA(ch::allow_dynamic_smem(
+        reinterpret_cast<const void*>(ch::compose_maps_kernel<double>), smem));
     ch::compose_maps_kernel<double><<<blocks, ch::kThreads, smem, s>>>(
         prog, op_begin, op_end, e, m, q, n_apertures, static_cast<double*>(records), record_len);
   }

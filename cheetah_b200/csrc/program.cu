@@ -1,5 +1,7 @@
 // Library plumbing: error channel, launch counter and the device-resident lattice program.
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "ch_common.cuh"
@@ -17,6 +19,23 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs a driver call; a kernel keeps the
+// attribute per device, so it is only raised when a launch needs more than it was given before.
+cudaError_t allow_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex guard;
+  static std::unordered_map<uint64_t, int> granted;
+  int device = 0;
+  cudaError_t err = cudaGetDevice(&device);
+  if (err != cudaSuccess) return err;
+  const uint64_t key = reinterpret_cast<uint64_t>(kernel) ^ (static_cast<uint64_t>(device) << 56);
+  std::lock_guard<std::mutex> lock(guard);
+  auto it = granted.find(key);
+  if (it != granted.end() && it->second >= bytes) return cudaSuccess;
+  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (err == cudaSuccess) granted[key] = bytes;
+  return err;
+}
 
 }  // namespace ch
 
